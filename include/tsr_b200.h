@@ -1,0 +1,146 @@
+/*
+ * tsr_b200.h -- C ABI of libtsr_b200.so, the B200 (sm_100a) implementation of the
+ * template_speech_rec data-parallel scoring path.
+ *
+ * The reference has no FFI: its boundary is "import code_parts", "import
+ * spread_waliji_patches", "import compute_likelihood_linear_filter" (Cython modules built in
+ * place, template_speech_rec/setup.py:35-41) plus the pure-Python classes
+ * bernoulli_mixture.BernoulliMixture / bernoulli_em.Bernoulli_Mixture.  Each entry point
+ * below is what a binding for one of those reference functions calls; the reference
+ * function it replaces is cited as file:line (paths relative to the reference root).
+ * INTEGRATION.md shows the ctypes stubs.
+ *
+ * Conventions
+ *   - every array pointer is a DEVICE pointer unless the parameter is named host_*;
+ *   - every call is asynchronous on the caller's `stream` (a cudaStream_t passed as void*);
+ *   - return value: TSR_OK (0) or a negative TSR_ERR_*; tsr_last_error() gives the text;
+ *   - no exceptions, no allocation of caller-visible memory, no hidden synchronisation
+ *     (the *_blob_bytes / *_rowwords helpers let the caller size every buffer);
+ *   - there is NO CPU fallback: on a device that is not compute capability 10.x the compute
+ *     entry points return TSR_ERR_UNSUPPORTED.
+ *
+ * Packed representations (resident in HBM between stages)
+ *   edge bits   uint8  [B][T][F]            bit e of byte (t,f) = X[t,f,e], e < E <= 8
+ *   codes       uint8  [B][To][Fo]          0 = background, p in 1..K = best part (K <= 255)
+ *   feature bits uint32 [B][T][rowwords]    bit (d % 32) of word (d / 32) = feature d of the row;
+ *                                           rowwords = tsr_rowwords(D) (even: rows padded to 64 features)
+ */
+#ifndef TSR_B200_H
+#define TSR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TSR_OK               0
+#define TSR_ERR_INVALID     -1   /* bad argument (shape, range, null pointer) */
+#define TSR_ERR_CUDA        -2   /* a CUDA runtime call or launch failed */
+#define TSR_ERR_UNSUPPORTED -3   /* not an sm_100 device, or shape outside the kernel's limits */
+
+#define TSR_ABI_VERSION 1
+
+/* detection kernels selectable through `impl` arguments (per-stage choice) */
+#define TSR_IMPL_TENSOR 0   /* tcgen05 / TMEM path (default) */
+#define TSR_IMPL_SIMT   1   /* CUDA-core cross-check path, fp32 sequential accumulation */
+
+int         tsr_abi_version(void);
+const char* tsr_last_error(void);            /* thread-local, valid until the next failing call */
+int         tsr_device_supported(void);      /* 1 if the current device is compute capability 10.x */
+int         tsr_rowwords(int D);             /* uint32 words per packed feature row (multiple of 2) */
+
+/* ---- K0: boundary packing (NumPy-layout uint8 <-> packed bits) ------------------------- */
+/* X uint8 [B][T][F][E] (any nonzero = edge, as `if X[i,j,z]` code_parts.pyx:29) -> bits [B][T][F] */
+int tsr_pack_edges(const uint8_t* X, uint8_t* bits, int B, int T, int F, int E, void* stream);
+int tsr_unpack_edges(const uint8_t* bits, uint8_t* X, int B, int T, int F, int E, void* stream);
+/* F uint8 [R][D] (nonzero test, compute_likelihood_linear_filter.pyx:168) -> bits [R][rowwords] */
+int tsr_pack_features_u8(const uint8_t* Fm, uint32_t* bits, long long R, int D, int rowwords, void* stream);
+int tsr_unpack_features_u8(const uint32_t* bits, uint8_t* Fm, long long R, int D, int rowwords, void* stream);
+
+/* ---- K1a: edge spreading --------------------------------------------------------------
+ * Replaces edge_signal_proc.spread_edgemap/_spread_edges (edge_signal_proc.py:1397-1417)
+ * and the 'all' box branch (edge_signal_proc.py:1623-1632, 1664-1673).
+ * out bit e at (t,f) = OR_{k=-radius..radius} in bit e at (t + k*dt[e], f + k*df[e]), zero
+ * outside the utterance and outside the `block_len`-frame block of t (block_len = 0: no
+ * blocks; the reference spreads per 40-frame block, edge_signal_proc.py:1635-1663).
+ * mode 0: line along host_dirs[e] = {df (frequency step), dt (time step)} per orientation
+ *         (int8 [8][2], HOST pointer, copied at launch);  mode 1: (2r+1)^2 box, dirs ignored. */
+int tsr_spread_edges(const uint8_t* bits_in, uint8_t* bits_out, int B, int T, int F, int radius, int mode,
+                     const int8_t* host_dirs, int block_len, void* stream);
+
+/* ---- K2: part coding --------------------------------------------------------------------
+ * Replaces code_parts.code_parts (code_parts.pyx:70-135), code_parts_fast (:247-295),
+ * code_parts_mask (:353-404) and the np.argmax the callers apply (get_train_data.py:2621).
+ * tsr_prepare_parts turns the reference's float64 log_parts / log_invparts [K][ph][pw][E]
+ * (device pointers) into the kernel's weight blob: W = lp - lip split into bf16 hi + lo
+ * planes in UMMA core-matrix order, c[k] = sum(lip) in fp32, edge-count columns. */
+size_t tsr_parts_blob_bytes(int K, int ph, int pw);
+int    tsr_prepare_parts(const double* log_parts, const double* log_invparts, int K, int ph, int pw, int E,
+                         const uint8_t* mask_or_null /* [ph][pw], code_parts_mask's M */, void* blob, void* stream);
+/* codes[b][i][j] = 0 if gate fails else 1 + argmax_k score (lowest k wins ties);
+ * gate: count >= threshold [and mask_count > mask_threshold when mask_threshold >= 0].
+ * scores_or_null float [B][To][Fo][K] (score = sum_{a,b,z} X ? lp : lip, written for every
+ * location); counts_or_null uint16 [B][To][Fo] edge counts.  To = T-ph+1, Fo = F-pw+1. */
+int tsr_code_parts(const uint8_t* bits, const void* parts_blob, int K, int ph, int pw, int threshold,
+                   int mask_threshold, uint8_t* codes, float* scores_or_null, uint16_t* counts_or_null, int B, int T,
+                   int F, int impl, void* stream);
+
+/* ---- K1b: part-code spreading -----------------------------------------------------------
+ * Replaces code_parts.spread_patches (code_parts.pyx:406-457) == spread_waliji_patches
+ * (spread_waliji_patches.pyx:15-59).  featbits row (b,i) holds Fo*K features, feature
+ * j*K + (p-1) set iff part p occurs within |di|<=r0, |dj|<=r1 of (i,j) (clipped). */
+int tsr_spread_codes(const uint8_t* codes, uint32_t* featbits, int B, int To, int Fo, int K, int r0, int r1,
+                     int rowwords, void* stream);
+/* Replaces code_parts.spread_graph_patches (code_parts.pyx:459-503): in place, sequential in
+ * p1 within each cell.  graph uint8 [K][K]. */
+int tsr_spread_graph(uint32_t* featbits, const uint8_t* graph, long long R, int Fo, int K, int rowwords, void* stream);
+
+/* ---- K3: sliding Bernoulli-template LLR detection ------------------------------------------
+ * Replaces compute_likelihood_linear_filter.detect (compute_likelihood_linear_filter.pyx:
+ * 135-176), the per-component loop + np.maximum of get_train_data._compute_detection_E
+ * (get_train_data.py:964-992) and detect_float_max's fused max/argmax (:221-278).
+ * tsr_prepare_filters: LF float32 [M][L][D] -> blob of bf16 hi/lo planes in UMMA order. */
+size_t tsr_filter_blob_bytes(int M, int L, int D);
+int    tsr_prepare_filters(const float* LF, int M, int L, int D, void* blob, void* stream);
+/* featbits [B][T][rowwords].  scores float [B][T][M]: scores[b][t][m] = sum_{tau,d}
+ * bit(b,t+tau,d) * LF[m][tau][d] for t <= T-L, 0 for the L-1 tail frames (detect's contract,
+ * :157-158).  impl = TSR_IMPL_TENSOR | TSR_IMPL_SIMT (SIMT needs LF_or_null = the fp32 filters). */
+int tsr_detect(const uint32_t* featbits, int B, int T, int D, int rowwords, const void* filter_blob,
+               const float* LF_or_null, int M, int L, float* scores, int impl, void* stream);
+/* best[b][t] = max_m (scores[b][t][m] + cs[m]), arg = first m attaining it (strict >, :275);
+ * tail frames: tail_mode 0 -> best 0, arg 0 (detect_float_max); 1 -> max_m cs[m] with its arg
+ * (what get_train_data.py:962-992 produces by adding c to the zero tail). */
+int tsr_detect_reduce(const float* scores, const float* cs, int B, int T, int M, int L, int tail_mode, float* best,
+                      uint16_t* arg, void* stream);
+/* Real-valued features: detect_float (:178-219), detect_float2d (:281-318), detect_spectral
+ * (:322-359), detect_float_max (:221-278).  fp32, separate multiply and add in the reference's
+ * (tau,f,k) order; each accumulation starts at init_or_null[m] (detect_float_max's cs, :258) or 0. */
+int tsr_detect_float(const float* Fm, int B, int T, int D, const float* LF, int M, int L, const float* init_or_null,
+                     float* scores, void* stream);
+
+/* ---- K4: Bernoulli-mixture EM -----------------------------------------------------------------
+ * Replaces BernoulliMixture.get_template_loglikelihoods/_compute_loglikelihoods
+ * (bernoulli_mixture.py:263-291), M_step/threshold_templates (:177-193) and the same steps
+ * of bernoulli_em.Bernoulli_Mixture (bernoulli_em.py:36-49, 103-127).
+ * E-step over this rank's rows: S[n][k] = sum_d x ? logT : logInvT; ll = S + logw;
+ * aff = row-softmax(ll) (or one-hot argmax of S when hard != 0); stats[K*D .. K*D+K) += column
+ * sums of aff; stats_ll[0] += sum_n logsumexp(ll).  M accumulation: stats[k*D+d] += sum_n
+ * aff[n][k] x[n][d].  The caller all-reduces stats/stats_ll across ranks (NCCL) and calls
+ * tsr_em_finalize, which every rank runs identically. */
+size_t tsr_em_workspace_bytes(long long N, int D, int K);   /* scratch for the two calls below (K <= 64) */
+int tsr_em_estep(const uint32_t* Xbits, long long N, int D, int rowwords, int K, const float* logT,
+                 const float* logInvT, const float* logw, float* aff, float* scores_or_null, float* stats,
+                 double* stats_ll, int hard, void* workspace, int impl, void* stream);
+int tsr_em_mstep(const uint32_t* Xbits, long long N, int D, int rowwords, int K, const float* aff, float* stats,
+                 void* workspace, void* stream);
+/* weights = respsum / N_total; T = numer / N_total / weights clipped to [min_prob, 1-min_prob];
+ * logT, logInvT, logw refreshed (all float32, as bernoulli_mixture.py:178-184). */
+int tsr_em_finalize(const float* stats, long long N_total, int D, int K, float min_prob, float* templates,
+                    float* logT, float* logInvT, float* weights, float* logw, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TSR_B200_H */

@@ -1,0 +1,78 @@
+"""ctypes binding of libtsr_b200.so (include/tsr_b200.h).  No fallback: if the library is
+missing or the device is not a B200-class GPU the product path raises."""
+import ctypes
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libtsr_b200.so")
+
+TSR_OK, TSR_ERR_INVALID, TSR_ERR_CUDA, TSR_ERR_UNSUPPORTED = 0, -1, -2, -3
+IMPL_TENSOR, IMPL_SIMT = 0, 1
+
+_vp, _i, _ll, _sz, _f = ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_size_t, ctypes.c_float
+
+# name -> (restype, argtypes); this table is also what tests/test_abi.py checks against the header
+SIGNATURES = {
+    "tsr_abi_version": (_i, []),
+    "tsr_last_error": (ctypes.c_char_p, []),
+    "tsr_device_supported": (_i, []),
+    "tsr_rowwords": (_i, [_i]),
+    "tsr_pack_edges": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
+    "tsr_unpack_edges": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
+    "tsr_pack_features_u8": (_i, [_vp, _vp, _ll, _i, _i, _vp]),
+    "tsr_unpack_features_u8": (_i, [_vp, _vp, _ll, _i, _i, _vp]),
+    "tsr_spread_edges": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _i, _vp]),
+    "tsr_parts_blob_bytes": (_sz, [_i, _i, _i]),
+    "tsr_prepare_parts": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "tsr_code_parts": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "tsr_spread_codes": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "tsr_spread_graph": (_i, [_vp, _vp, _ll, _i, _i, _i, _vp]),
+    "tsr_filter_blob_bytes": (_sz, [_i, _i, _i]),
+    "tsr_prepare_filters": (_i, [_vp, _i, _i, _i, _vp, _vp]),
+    "tsr_detect": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _vp, _i, _vp]),
+    "tsr_detect_reduce": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "tsr_detect_float": (_i, [_vp, _i, _i, _i, _vp, _i, _i, _vp, _vp, _vp]),
+    "tsr_em_workspace_bytes": (_sz, [_ll, _i, _i]),
+    "tsr_em_estep": (_i, [_vp, _ll, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _vp]),
+    "tsr_em_mstep": (_i, [_vp, _ll, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "tsr_em_finalize": (_i, [_vp, _ll, _i, _i, _f, _vp, _vp, _vp, _vp, _vp, _vp]),
+}
+
+_lib = None
+
+
+class TsrError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load the CUDA library; fail loudly if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise TsrError("libtsr_b200.so is not built (%s). Run `python __graft_entry__.py build`; "
+                           "there is no CPU fallback." % LIB_PATH)
+        l = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(l, name)
+            fn.restype = res
+            fn.argtypes = args
+        if l.tsr_abi_version() != 1:
+            raise TsrError("libtsr_b200.so ABI version mismatch")
+        _lib = l
+    return _lib
+
+
+def check(rc):
+    if rc == TSR_OK:
+        return
+    msg = lib().tsr_last_error().decode("utf-8", "replace")
+    if rc == TSR_ERR_INVALID:
+        raise ValueError(msg)
+    if rc == TSR_ERR_UNSUPPORTED:
+        raise TsrError("unsupported: " + msg)
+    raise TsrError("CUDA error: " + msg)
+
+
+def call(name, *args):
+    check(getattr(lib(), name)(*args))

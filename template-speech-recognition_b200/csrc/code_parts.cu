@@ -1,0 +1,406 @@
+// code_parts.cu -- K2: Bernoulli part coding of every ph x pw x 8 patch of the packed edge map,
+// fused with the edge-count gate and the arg-max (code_parts.pyx:70-135, get_train_data.py:2621).
+//
+//   score[loc][k] = c[k] + sum_{a,b,z} X[i+a][j+b][z] * W[k][a][b][z],   W = lp - lip, c = sum lip
+//
+// Tensor path (TSR_IMPL_TENSOR): one persistent CTA per SM, warp specialised.
+//   producers (4 warps)  expand packed edge bytes of a 128-location tile (+halo) into bf16 {0,1}
+//                        rows in shared memory: one 16-byte row per (t,f) position, positions
+//                        flattened p = t*F + f, so location p's patch row `a` is the 16*pw bytes
+//                        starting at position p + a*F.
+//   MMA issuer (1 thread) tcgen05.mma M=128 x N=N_pad x K=16, A straight out of that buffer with
+//                        a K-major no-swizzle descriptor whose core-matrix rows are the 16-byte
+//                        positions (row stride 16 B = one frequency bin, SBO = 128 B, LBO = the
+//                        distance to the next (a,b) group): the im2col is never materialised.
+//                        hi and lo bf16 weight planes accumulate into the same TMEM columns.
+//   epilogue (4 warps)   tcgen05.ld the 128 x N_pad fp32 tile, add c[k], running arg-max (lowest k
+//                        wins ties), read the exact edge counts from two extra weight columns
+//                        (all-ones / mask), apply the gate, store uint8 codes.
+// Two TMEM accumulator buffers and a 4-deep A ring overlap the three roles.
+#include "common.cuh"
+
+namespace tsr {
+
+struct PartsLayout {
+    int K, ph, pw, npad, nsteps, nq;
+    size_t off_w, off_c, off_wf, off_mask, total;
+};
+
+__host__ __device__ inline PartsLayout parts_layout(int K, int ph, int pw) {
+    PartsLayout L;
+    L.K = K; L.ph = ph; L.pw = pw;
+    L.nq = ph * pw;
+    L.npad = ((K + 2) + 15) & ~15;
+    L.nsteps = (L.nq + 1) / 2;
+    L.off_w = 0;
+    L.off_c = (size_t)2 * L.nsteps * L.npad * 32;
+    L.off_wf = L.off_c + (size_t)L.npad * 4;
+    L.off_mask = L.off_wf + (size_t)L.nq * 8 * L.npad * 4;
+    L.total = L.off_mask + 16;
+    return L;
+}
+
+// ------------------------------------------------------------------------------ prepare
+// One thread per (n, q, z) weight: n < K parts, n == K all-ones count column, n == K+1 mask column.
+__global__ void prepare_parts_kernel(const double* __restrict__ lp, const double* __restrict__ lip, int E,
+                                     const uint8_t* __restrict__ mask, uint8_t* __restrict__ blob, PartsLayout L) {
+    const int total = L.npad * L.nsteps * 16;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        int n = i / (L.nsteps * 16);
+        int rem = i - n * (L.nsteps * 16);
+        int s = rem >> 4, e = rem & 15;
+        int q = 2 * s + (e >> 3), z = e & 7;
+        double w = 0.0;
+        if (q < L.nq && z < E) {
+            if (n < L.K) {
+                size_t idx = ((size_t)n * L.nq + q) * E + z;
+                w = lp[idx] - lip[idx];
+            } else if (n == L.K) {
+                w = 1.0;
+            } else if (n == L.K + 1) {
+                w = (mask && mask[q]) ? 1.0 : 0.0;
+            }
+        }
+        __nv_bfloat16 hi = __double2bfloat16(w);
+        __nv_bfloat16 lo = __double2bfloat16(w - (double)__bfloat162float(hi));
+        size_t o = (((size_t)s * 2 + (e >> 3)) * L.npad + n) * 16 + z * 2;
+        *reinterpret_cast<__nv_bfloat16*>(blob + L.off_w + o) = hi;
+        *reinterpret_cast<__nv_bfloat16*>(blob + L.off_w + (size_t)L.nsteps * L.npad * 32 + o) = lo;
+        if (q < L.nq) reinterpret_cast<float*>(blob + L.off_wf)[((size_t)q * 8 + z) * L.npad + n] = (float)w;
+    }
+    // c[k] = sum lip (float64, reference order), one thread per part
+    for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < L.npad; n += gridDim.x * blockDim.x) {
+        double c = 0.0;
+        if (n < L.K)
+            for (int i = 0; i < L.nq * E; ++i) c += lip[(size_t)n * L.nq * E + i];
+        reinterpret_cast<float*>(blob + L.off_c)[n] = (float)c;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        unsigned long long m = 0;
+        if (mask)
+            for (int q = 0; q < L.nq; ++q)
+                if (mask[q]) m |= 1ull << q;
+        reinterpret_cast<unsigned long long*>(blob + L.off_mask)[0] = m;
+        reinterpret_cast<unsigned long long*>(blob + L.off_mask)[1] = 0;
+    }
+}
+
+struct CodeArgs {
+    const uint8_t* bits;
+    const uint8_t* blob;
+    uint8_t* codes;
+    float* scores;
+    uint16_t* counts;
+    int B, T, F, To, Fo;
+    int threshold, mask_threshold;
+    PartsLayout L;
+};
+
+// --------------------------------------------------------------------------- SIMT path
+// One warp per location, lanes over parts; walks the set bits of the window in (a,b,z) order and
+// adds fp32 W rows from shared memory.  Cross-check / comparison kernel (per-stage choice).
+__global__ void __launch_bounds__(256) code_parts_simt_kernel(CodeArgs A) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const PartsLayout& L = A.L;
+    float* wf = reinterpret_cast<float*>(smem);                 // [nq*8][npad]
+    float* cs = wf + (size_t)L.nq * 8 * L.npad;                 // [npad]
+    {
+        const float* gw = reinterpret_cast<const float*>(A.blob + L.off_wf);
+        const float* gc = reinterpret_cast<const float*>(A.blob + L.off_c);
+        for (int i = threadIdx.x; i < L.nq * 8 * L.npad; i += blockDim.x) wf[i] = gw[i];
+        for (int i = threadIdx.x; i < L.npad; i += blockDim.x) cs[i] = gc[i];
+    }
+    const unsigned long long maskbits = *reinterpret_cast<const unsigned long long*>(A.blob + L.off_mask);
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const long long nloc = (long long)A.B * A.To * A.Fo;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long loc = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; loc < nloc; loc += nwarps) {
+        int j = (int)(loc % A.Fo);
+        long long tmp = loc / A.Fo;
+        int i = (int)(tmp % A.To);
+        int b = (int)(tmp / A.To);
+        const uint8_t* base = A.bits + ((size_t)b * A.T + i) * A.F + j;
+        float acc[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) acc[u] = (lane + 32 * u < L.K) ? cs[lane + 32 * u] : 0.f;
+        int count = 0, mcount = 0;
+        for (int q = 0; q < L.nq; ++q) {
+            int a = q / L.pw, c = q - a * L.pw;
+            uint32_t byte = base[(size_t)a * A.F + c];          // warp-uniform address: broadcast load
+            int pc = __popc(byte);
+            count += pc;
+            if ((maskbits >> q) & 1ull) mcount += pc;
+            while (byte) {
+                int z = __ffs(byte) - 1;
+                byte &= byte - 1;
+                const float* wrow = wf + (size_t)(q * 8 + z) * L.npad;
+#pragma unroll
+                for (int u = 0; u < 8; ++u)
+                    if (32 * u < L.K) {
+                        int k = lane + 32 * u;
+                        if (k < L.K) acc[u] = __fadd_rn(acc[u], wrow[k]);
+                    }
+            }
+        }
+        // arg-max, lowest k wins ties
+        float best = -INFINITY;
+        int bestk = 0x7fffffff;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            int k = lane + 32 * u;
+            if (k < L.K && acc[u] > best) { best = acc[u]; bestk = k; }
+        }
+        for (int off = 16; off > 0; off >>= 1) {
+            float ob = __shfl_xor_sync(0xffffffffu, best, off);
+            int ok = __shfl_xor_sync(0xffffffffu, bestk, off);
+            if (ob > best || (ob == best && ok < bestk)) { best = ob; bestk = ok; }
+        }
+        bool gate = count >= A.threshold && (A.mask_threshold < 0 || mcount > A.mask_threshold);
+        if (lane == 0) {
+            if (A.codes) A.codes[loc] = gate ? (uint8_t)(bestk + 1) : 0;
+            if (A.counts) A.counts[loc] = (uint16_t)count;
+        }
+        if (A.scores) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                int k = lane + 32 * u;
+                if (k < L.K) A.scores[loc * L.K + k] = acc[u];
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------- tensor path
+#define CP_NSTAGE 4
+#define CP_THREADS 288   // warps 0-3 epilogue, warp 4 MMA/TMEM, warps 5-8 producers
+
+struct CodeSmem {   // offsets into dynamic shared memory
+    uint32_t w, c, a, bars, stage_bytes, npos, total;
+};
+__host__ __device__ inline CodeSmem code_smem_layout(const PartsLayout& L, int F) {
+    CodeSmem S;
+    S.w = 0;
+    S.c = (uint32_t)(2 * L.nsteps * L.npad * 32);
+    S.a = (S.c + L.npad * 4 + 127) & ~127u;
+    S.npos = 128 + (L.ph - 1) * F + (L.pw - 1) + 2;
+    S.stage_bytes = (S.npos * 16 + 127) & ~127u;
+    S.bars = S.a + CP_NSTAGE * S.stage_bytes;
+    S.total = S.bars + 128;
+    return S;
+}
+
+__global__ void __launch_bounds__(CP_THREADS, 1) code_parts_tc_kernel(CodeArgs A, int tiles_per_utt, long long ntiles) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const PartsLayout& L = A.L;
+    const CodeSmem S = code_smem_layout(L, A.F);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S.bars);       // [CP_NSTAGE]
+    uint64_t* empty_bar = full_bar + CP_NSTAGE;                            // [CP_NSTAGE]
+    uint64_t* tfull_bar = empty_bar + CP_NSTAGE;                           // [2]
+    uint64_t* tempty_bar = tfull_bar + 2;                                  // [2]
+    uint64_t* w_bar = tempty_bar + 2;                                      // [1]
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(w_bar + 1);
+    const float* cs = reinterpret_cast<const float*>(smem + S.c);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < CP_NSTAGE; ++s) { mbar_init(&full_bar[s], 128); mbar_init(&empty_bar[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 128); }
+        mbar_init(w_bar, 1);
+        mbar_fence_init();
+    }
+    if (warp == 4) tmem_alloc<512>(tmem_ptr);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    // weights + c: one bulk (TMA) copy per plane, landed once per CTA
+    const uint32_t wbytes = S.c + L.npad * 4;
+    if (threadIdx.x == 0) {
+        mbar_arrive_expect_tx(w_bar, wbytes);
+        const uint32_t half = (uint32_t)(L.nsteps * L.npad * 32);
+        bulk_g2s(smem + S.w, A.blob + L.off_w, half, w_bar);
+        bulk_g2s(smem + S.w + half, A.blob + L.off_w + half, half, w_bar);
+        bulk_g2s(smem + S.c, A.blob + L.off_c, L.npad * 4, w_bar);
+    }
+
+    if (warp >= 5) {
+        // ================================ producers ================================
+        const int pt = threadIdx.x - 160;
+        uint32_t it = 0;
+        for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+            const int stage = it % CP_NSTAGE;
+            const uint32_t ph = (it / CP_NSTAGE) & 1;
+            const int b = (int)(tile / tiles_per_utt);
+            const int p0 = (int)(tile % tiles_per_utt) * 128;
+            const uint8_t* src = A.bits + (size_t)b * A.T * A.F;
+            const int plimit = A.T * A.F;
+            mbar_wait(&empty_bar[stage], ph ^ 1);
+            uint8_t* dst = smem + S.a + stage * S.stage_bytes;
+            for (int pos = pt; pos < (int)S.npos; pos += 128) {
+                int p = p0 + pos;
+                uint32_t byte = p < plimit ? src[p] : 0u;
+                *reinterpret_cast<uint4*>(dst + pos * 16) = expand_byte_bf16(byte);
+            }
+            fence_proxy_async_smem();
+            mbar_arrive(&full_bar[stage]);
+        }
+    } else if (warp == 4) {
+        // ================================ MMA issuer ================================
+        mbar_wait(w_bar, 0);
+        const uint32_t idesc = umma_idesc_bf16_f32(128, L.npad);
+        const uint32_t wbase = smem_u32(smem + S.w);
+        const uint32_t nb_lbo = L.npad * 16;
+        uint32_t it = 0;
+        for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+            const int stage = it % CP_NSTAGE;
+            const uint32_t ph = (it / CP_NSTAGE) & 1;
+            const int acc = it & 1;
+            const uint32_t aph = (it >> 1) & 1;
+            mbar_wait(&full_bar[stage], ph);
+            mbar_wait(&tempty_bar[acc], aph ^ 1);
+            tc_fence_after();
+            if (lane == 0) {
+                const uint32_t abase = smem_u32(smem + S.a + stage * S.stage_bytes);
+                const uint32_t d_tmem = tmem_base + acc * 256;
+                bool first = true;
+                for (int plane = 0; plane < 2; ++plane)
+                    for (int s = 0; s < L.nsteps; ++s) {
+                        int q0 = 2 * s, q1 = 2 * s + 1;
+                        uint32_t off0 = ((q0 / L.pw) * A.F + (q0 % L.pw)) * 16;
+                        uint32_t off1 = q1 < L.nq ? ((q1 / L.pw) * A.F + (q1 % L.pw)) * 16 : off0 + 16;
+                        uint64_t adesc = umma_desc_kmajor_noswz(abase + off0, off1 - off0, 128);
+                        uint64_t bdesc = umma_desc_kmajor_noswz(wbase + ((plane * L.nsteps + s) * 2) * nb_lbo, nb_lbo, 128);
+                        umma_bf16(d_tmem, adesc, bdesc, idesc, !first);
+                        first = false;
+                    }
+                umma_commit(&empty_bar[stage]);   // A stage reusable once these MMAs retire
+                umma_commit(&tfull_bar[acc]);     // accumulator ready for the epilogue
+            }
+            __syncwarp();
+        }
+    } else {
+        // ================================ epilogue ================================
+        mbar_wait(w_bar, 0);   // c[] lives in the same bulk transaction
+        const int e = threadIdx.x;   // TMEM lane == tile row
+        uint32_t it = 0;
+        for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+            const int acc = it & 1;
+            const uint32_t aph = (it >> 1) & 1;
+            const int b = (int)(tile / tiles_per_utt);
+            const int p = (int)(tile % tiles_per_utt) * 128 + e;
+            const int t = p / A.F, f = p - t * A.F;
+            const bool valid = t < A.To && f < A.Fo;
+            const size_t loc = ((size_t)b * A.To + t) * A.Fo + f;
+            mbar_wait(&tfull_bar[acc], aph);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + acc * 256 + ((uint32_t)(warp * 32) << 16);
+            float best = -INFINITY;
+            int bestk = 0;
+            float fcount = 0.f, fmcount = 0.f;
+            for (int n0 = 0; n0 < L.npad; n0 += 16) {
+                uint32_t v[16];
+                tmem_ld16(taddr + n0, v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const int n = n0 + i;
+                    const float x = __uint_as_float(v[i]);
+                    if (n < L.K) {
+                        const float sc = x + cs[n];
+                        if (sc > best) { best = sc; bestk = n; }
+                        if (A.scores && valid) A.scores[loc * L.K + n] = sc;
+                    } else if (n == L.K) {
+                        fcount = x;
+                    } else if (n == L.K + 1) {
+                        fmcount = x;
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&tempty_bar[acc]);
+            if (valid) {
+                const int count = (int)(fcount + 0.5f), mcount = (int)(fmcount + 0.5f);
+                const bool gate = count >= A.threshold && (A.mask_threshold < 0 || mcount > A.mask_threshold);
+                if (A.codes) A.codes[loc] = gate ? (uint8_t)(bestk + 1) : 0;
+                if (A.counts) A.counts[loc] = (uint16_t)count;
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) {
+        tc_fence_after();
+        tmem_dealloc<512>(tmem_base);
+    }
+}
+
+}  // namespace tsr
+
+using namespace tsr;
+
+extern "C" {
+
+size_t tsr_parts_blob_bytes(int K, int ph, int pw) {
+    if (K < 1 || ph < 1 || pw < 1) return 0;
+    return parts_layout(K, ph, pw).total;
+}
+
+int tsr_prepare_parts(const double* log_parts, const double* log_invparts, int K, int ph, int pw, int E,
+                      const uint8_t* mask_or_null, void* blob, void* stream) {
+    TSR_REQUIRE(log_parts && log_invparts && blob, "tsr_prepare_parts: null pointer");
+    TSR_REQUIRE(K >= 1 && K <= 238, "tsr_prepare_parts: need 1 <= num_parts <= 238 (got %d)", K);
+    TSR_REQUIRE(ph >= 1 && pw >= 1 && ph * pw <= 64, "tsr_prepare_parts: part window %dx%d unsupported (ph*pw <= 64)", ph, pw);
+    TSR_REQUIRE(E >= 1 && E <= 8, "tsr_prepare_parts: need 1 <= E <= 8 (got %d)", E);
+    int rc = require_sm100("tsr_prepare_parts");
+    if (rc) return rc;
+    PartsLayout L = parts_layout(K, ph, pw);
+    TSR_CUDA(cudaMemsetAsync((uint8_t*)blob + L.off_wf, 0, L.total - L.off_wf, (cudaStream_t)stream));
+    prepare_parts_kernel<<<64, 256, 0, (cudaStream_t)stream>>>(log_parts, log_invparts, E, mask_or_null, (uint8_t*)blob, L);
+    return check_launch("tsr_prepare_parts");
+}
+
+int tsr_code_parts(const uint8_t* bits, const void* parts_blob, int K, int ph, int pw, int threshold,
+                   int mask_threshold, uint8_t* codes, float* scores_or_null, uint16_t* counts_or_null, int B, int T,
+                   int F, int impl, void* stream) {
+    TSR_REQUIRE(bits && parts_blob, "tsr_code_parts: null pointer");
+    TSR_REQUIRE(codes || scores_or_null || counts_or_null, "tsr_code_parts: no output requested");
+    TSR_REQUIRE(K >= 1 && K <= 238 && ph >= 1 && pw >= 1 && ph * pw <= 64, "tsr_code_parts: unsupported parts shape");
+    TSR_REQUIRE(B >= 0 && T >= ph && F >= pw, "tsr_code_parts: input (T=%d,F=%d) smaller than the part window (%d,%d)", T, F, ph, pw);
+    TSR_REQUIRE(impl == TSR_IMPL_TENSOR || impl == TSR_IMPL_SIMT, "tsr_code_parts: unknown impl %d", impl);
+    TSR_REQUIRE((long long)T * F < (1ll << 30), "tsr_code_parts: utterance too large (T*F >= 2^30); split in time");
+    if (B == 0) return TSR_OK;
+    int rc = require_sm100("tsr_code_parts");
+    if (rc) return rc;
+    CodeArgs A;
+    A.bits = bits; A.blob = (const uint8_t*)parts_blob; A.codes = codes; A.scores = scores_or_null; A.counts = counts_or_null;
+    A.B = B; A.T = T; A.F = F; A.To = T - ph + 1; A.Fo = F - pw + 1;
+    A.threshold = threshold; A.mask_threshold = mask_threshold;
+    A.L = parts_layout(K, ph, pw);
+    const int nsm = sm_count();
+    if (impl == TSR_IMPL_SIMT) {
+        size_t smem = ((size_t)A.L.nq * 8 + 1) * A.L.npad * 4;
+        TSR_REQUIRE(smem <= 220 * 1024, "tsr_code_parts(simt): weights do not fit shared memory");
+        TSR_CUDA(cudaFuncSetAttribute(code_parts_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int blocks = nsm * (smem <= 100 * 1024 ? 2 : 1);
+        code_parts_simt_kernel<<<blocks, 256, smem, (cudaStream_t)stream>>>(A);
+        return check_launch("tsr_code_parts(simt)");
+    }
+    CodeSmem S = code_smem_layout(A.L, F);
+    if (S.total > 227 * 1024) {
+        set_error("tsr_code_parts: K=%d parts %dx%d with F=%d needs %u B of shared memory (> 227 KB)", K, ph, pw, F, S.total);
+        return TSR_ERR_UNSUPPORTED;
+    }
+    TSR_REQUIRE((uint32_t)((ph - 1) * F + pw) * 16 < (1u << 18), "tsr_code_parts: F too large for the patch descriptor");
+    const int tiles_per_utt = (int)(((long long)A.To * F + 127) / 128);
+    const long long ntiles = (long long)tiles_per_utt * B;
+    TSR_CUDA(cudaFuncSetAttribute(code_parts_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S.total));
+    int blocks = (int)(ntiles < nsm ? ntiles : nsm);
+    code_parts_tc_kernel<<<blocks, CP_THREADS, S.total, (cudaStream_t)stream>>>(A, tiles_per_utt, ntiles);
+    return check_launch("tsr_code_parts");
+}
+
+}  // extern "C"

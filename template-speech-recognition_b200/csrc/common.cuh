@@ -1,0 +1,191 @@
+// common.cuh -- shared device helpers for the sm_100a kernels: error plumbing, mbarrier /
+// bulk-copy (TMA) / tcgen05 inline-PTX wrappers, bit -> bf16 expansion.
+//
+// Everything here targets sm_100a only (compile with -gencode arch=compute_100a,code=sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/tsr_b200.h"
+
+namespace tsr {
+
+// ----------------------------------------------------------------------------- host errors
+void set_error(const char* fmt, ...);
+int  check_launch(const char* what);          // cudaGetLastError -> TSR_ERR_CUDA
+int  sm_count();                              // multiProcessorCount of the current device
+int  require_sm100(const char* what);         // TSR_ERR_UNSUPPORTED unless cc 10.x
+
+#define TSR_REQUIRE(cond, ...)                                   \
+    do {                                                         \
+        if (!(cond)) {                                           \
+            tsr::set_error(__VA_ARGS__);                         \
+            return TSR_ERR_INVALID;                              \
+        }                                                        \
+    } while (0)
+
+#define TSR_CUDA(call)                                                                   \
+    do {                                                                                 \
+        cudaError_t e__ = (call);                                                        \
+        if (e__ != cudaSuccess) {                                                        \
+            tsr::set_error("%s failed: %s", #call, cudaGetErrorString(e__));             \
+            return TSR_ERR_CUDA;                                                         \
+        }                                                                                \
+    } while (0)
+
+// ----------------------------------------------------------------------------- device PTX
+#ifdef __CUDACC__
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+// Spin bound for every barrier wait: a lost arrival traps (CUDA error) instead of hanging
+// the box.  ~2^26 polls with back-off is seconds of wall time, far above any legitimate wait.
+#define TSR_SPIN_LIMIT (1u << 26)
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if (++spins > TSR_SPIN_LIMIT) {
+            printf("tsr_b200: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+            __trap();
+        }
+    }
+}
+
+// generic-proxy smem writes -> visible to the async proxy (tcgen05.mma / bulk copies)
+__device__ __forceinline__ void fence_proxy_async_smem() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+// 1-D bulk copy global -> shared (TMA engine, UBLKCP in SASS); completes on an mbarrier.
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+
+// ---- TMEM allocation (one full warp executes these) -------------------------------------
+template <uint32_t kCols>
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_result) {
+    static_assert(kCols == 32 || kCols == 64 || kCols == 128 || kCols == 256 || kCols == 512, "TMEM cols");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)),
+                 "n"(kCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <uint32_t kCols>
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(kCols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// ---- UMMA descriptors ------------------------------------------------------------------
+// Shared-memory matrix descriptor, K-major, SWIZZLE_NONE ("interleave") canonical layout:
+// core matrix = 8 rows x 16 bytes with rows 16 B apart; SBO = byte distance between 8-row
+// groups (M/N direction); LBO = byte distance between the two 8-element K groups of one
+// K=16 MMA.  Bit layout: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48),
+// layout_type=0 [61,64).
+__device__ __forceinline__ uint64_t umma_desc_kmajor_noswz(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    return d;
+}
+// Instruction descriptor for kind::f16 with BF16 A/B (K-major both) and FP32 accumulate.
+__host__ __device__ constexpr uint32_t umma_idesc_bf16_f32(int M, int N) {
+    return (1u << 4)                       // c_format  = F32
+           | (1u << 7)                     // a_format  = BF16
+           | (1u << 10)                    // b_format  = BF16
+           | ((uint32_t)(N >> 3) << 17)    // n_dim
+           | ((uint32_t)(M >> 4) << 24);   // m_dim
+}
+// D[tmem] (+)= A[smem] * B[smem]; one thread issues for the CTA.
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                          bool accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"((uint32_t)accumulate)
+        : "memory");
+}
+// mbarrier arrives once all previously issued tcgen05.mma of this thread have completed
+// (implies tcgen05.fence::before_thread_sync).
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+
+// TMEM -> registers: 32 lanes x 16 consecutive fp32 columns; lane i of the warp reads TMEM
+// lane (taddr.lane + i).  A warp may only touch the lane quadrant 32*(warp_id % 4).
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ---- bit -> bf16 expansion ---------------------------------------------------------------
+// 8 bits -> 8 bf16 values in {0.0, 1.0} (0x0000 / 0x3F80), bit i -> element i.
+__device__ __forceinline__ uint4 expand_byte_bf16(uint32_t b) {
+    uint4 r;
+    // two bits per 32-bit word: bit0 -> low half, bit1 -> high half; (x & 0x00010001) * 0x3F80 has no carries
+    r.x = (((b) | (b << 15)) & 0x00010001u) * 0x3F80u;
+    b >>= 2;
+    r.y = (((b) | (b << 15)) & 0x00010001u) * 0x3F80u;
+    b >>= 2;
+    r.z = (((b) | (b << 15)) & 0x00010001u) * 0x3F80u;
+    b >>= 2;
+    r.w = (((b) | (b << 15)) & 0x00010001u) * 0x3F80u;
+    return r;
+}
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+#endif  // __CUDACC__
+
+}  // namespace tsr

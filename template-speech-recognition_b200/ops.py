@@ -1,0 +1,258 @@
+"""Device-resident batched API over the C ABI (torch tensors in, torch tensors out).
+
+This is the layer the benchmark and the reference-signature modules (code_parts.py,
+spread_waliji_patches.py, compute_likelihood_linear_filter.py, bernoulli_mixture.py)
+sit on.  torch is used for device memory and streams only; every computation is a call
+into libtsr_b200.so on the current CUDA stream.  Nothing here touches the CPU oracle.
+"""
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import IMPL_SIMT, IMPL_TENSOR  # noqa: F401
+
+# Orientation table produced by the reference edge extractor (edge_signal_proc.py:1751-1821,
+# returned by _edge_map_no_threshold and passed to spread_edgemap by every pipeline caller):
+# rows are (frequency step, time step) of orientation block e.
+DEFAULT_EDGE_ORIENTATIONS = np.array([[0, 1], [0, -1], [1, 0], [-1, 0], [1, 1], [-1, -1], [-1, 1], [1, -1]], np.int8)
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def _dev(t, dtype, name):
+    if not (isinstance(t, torch.Tensor) and t.is_cuda):
+        raise ValueError("%s must be a CUDA tensor" % name)
+    if t.dtype != dtype:
+        raise ValueError("%s: dtype mismatch, expected %s but got %s" % (name, dtype, t.dtype))
+    return t.contiguous()
+
+
+def rowwords(D):
+    return _lib.lib().tsr_rowwords(int(D))
+
+
+# ------------------------------------------------------------------------------- K0
+def pack_edges(X):
+    """X uint8 (B,T,F,E) -> bits uint8 (B,T,F); any nonzero counts as an edge."""
+    X = _dev(X, torch.uint8, "X")
+    B, T, F, E = X.shape
+    bits = torch.empty((B, T, F), dtype=torch.uint8, device=X.device)
+    _lib.call("tsr_pack_edges", _ptr(X), _ptr(bits), B, T, F, E, _stream())
+    return bits
+
+
+def unpack_edges(bits, E=8):
+    bits = _dev(bits, torch.uint8, "bits")
+    B, T, F = bits.shape
+    X = torch.empty((B, T, F, E), dtype=torch.uint8, device=bits.device)
+    _lib.call("tsr_unpack_edges", _ptr(bits), _ptr(X), B, T, F, E, _stream())
+    return X
+
+
+def pack_features(Fm):
+    """Fm uint8 (B,T,D) -> featbits int32 (B,T,rowwords(D)) (bit pattern of uint32 words)."""
+    Fm = _dev(Fm, torch.uint8, "F")
+    B, T, D = Fm.shape
+    rw = rowwords(D)
+    bits = torch.empty((B, T, rw), dtype=torch.int32, device=Fm.device)
+    _lib.call("tsr_pack_features_u8", _ptr(Fm), _ptr(bits), B * T, D, rw, _stream())
+    return bits
+
+
+def unpack_features(featbits, D):
+    featbits = _dev(featbits, torch.int32, "featbits")
+    B, T, rw = featbits.shape
+    Fm = torch.empty((B, T, D), dtype=torch.uint8, device=featbits.device)
+    _lib.call("tsr_unpack_features_u8", _ptr(featbits), _ptr(Fm), B * T, D, rw, _stream())
+    return Fm
+
+
+# ------------------------------------------------------------------------------ K1a
+def spread_edges(bits, radius, orientations=None, mode="line", block_len=0):
+    """Edge spreading on packed edge bytes (edge_signal_proc.py:1397-1417 / :1623-1632)."""
+    bits = _dev(bits, torch.uint8, "bits")
+    B, T, F = bits.shape
+    out = torch.empty_like(bits)
+    if mode == "line":
+        dirs = np.ascontiguousarray(DEFAULT_EDGE_ORIENTATIONS if orientations is None else orientations)
+        if dirs.shape != (8, 2) or np.any(dirs != np.round(dirs)):
+            raise ValueError("orientations must be 8 integer (frequency step, time step) pairs")
+        dirs = np.ascontiguousarray(dirs, dtype=np.int8)
+        _lib.call("tsr_spread_edges", _ptr(bits), _ptr(out), B, T, F, int(radius), 0, dirs.ctypes.data, int(block_len), _stream())
+    elif mode == "box":
+        _lib.call("tsr_spread_edges", _ptr(bits), _ptr(out), B, T, F, int(radius), 1, 0, int(block_len), _stream())
+    else:
+        raise ValueError("mode must be 'line' or 'box'")
+    return out
+
+
+# ------------------------------------------------------------------------------- K2
+class PartsModel:
+    """Device copy of a part dictionary in the coding kernel's layout (tsr_prepare_parts)."""
+
+    def __init__(self, log_parts, log_invparts, mask=None, device="cuda"):
+        lp = np.ascontiguousarray(log_parts)
+        lip = np.ascontiguousarray(log_invparts)
+        if lp.dtype != np.float64 or lip.dtype != np.float64:
+            raise ValueError("Buffer dtype mismatch, expected 'DTYPE_t' (float64) but got '%s'" % lp.dtype)
+        if lp.ndim != 4 or lip.shape != lp.shape:
+            raise ValueError("Buffer has wrong number of dimensions (expected 4, got %d)" % lp.ndim)
+        self.K, self.ph, self.pw, self.E = lp.shape
+        nbytes = _lib.lib().tsr_parts_blob_bytes(self.K, self.ph, self.pw)
+        self.blob = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        d_lp = torch.from_numpy(lp).to(device)
+        d_lip = torch.from_numpy(lip).to(device)
+        d_mask = None
+        if mask is not None:
+            m = np.ascontiguousarray(mask, dtype=np.uint8)
+            if m.shape != (self.ph, self.pw):
+                raise ValueError("mask must have the part window shape (%d,%d)" % (self.ph, self.pw))
+            d_mask = torch.from_numpy((m != 0).astype(np.uint8)).to(device)
+        _lib.call("tsr_prepare_parts", _ptr(d_lp), _ptr(d_lip), self.K, self.ph, self.pw, self.E, _ptr(d_mask),
+                  _ptr(self.blob), _stream())
+        torch.cuda.current_stream().synchronize()   # d_lp/d_lip may be freed after this returns
+
+
+def code_parts(bits, parts, threshold, mask_threshold=-1, want_codes=True, want_scores=False, want_counts=False,
+               impl=IMPL_TENSOR):
+    """bits uint8 (B,T,F) -> (codes uint8 (B,To,Fo) | None, scores float32 (B,To,Fo,K) | None,
+    counts int16 (B,To,Fo) | None)."""
+    bits = _dev(bits, torch.uint8, "bits")
+    B, T, F = bits.shape
+    To, Fo = T - parts.ph + 1, F - parts.pw + 1
+    if To < 1 or Fo < 1:
+        raise ValueError("input (%d,%d) smaller than the part window (%d,%d)" % (T, F, parts.ph, parts.pw))
+    dev = bits.device
+    codes = torch.empty((B, To, Fo), dtype=torch.uint8, device=dev) if want_codes else None
+    scores = torch.empty((B, To, Fo, parts.K), dtype=torch.float32, device=dev) if want_scores else None
+    counts = torch.empty((B, To, Fo), dtype=torch.int16, device=dev) if want_counts else None
+    _lib.call("tsr_code_parts", _ptr(bits), _ptr(parts.blob), parts.K, parts.ph, parts.pw, int(threshold),
+              int(mask_threshold), _ptr(codes), _ptr(scores), _ptr(counts), B, T, F, int(impl), _stream())
+    return codes, scores, counts
+
+
+# ------------------------------------------------------------------------------ K1b
+def spread_codes(codes, K, r0, r1):
+    """codes uint8 (B,To,Fo) -> featbits int32 (B,To,rowwords(Fo*K))."""
+    codes = _dev(codes, torch.uint8, "codes")
+    B, To, Fo = codes.shape
+    rw = rowwords(Fo * K)
+    out = torch.empty((B, To, rw), dtype=torch.int32, device=codes.device)
+    _lib.call("tsr_spread_codes", _ptr(codes), _ptr(out), B, To, Fo, int(K), int(r0), int(r1), rw, _stream())
+    return out
+
+
+def spread_graph(featbits, graph, Fo, K):
+    """In place on featbits (B,To,rowwords): part-graph spreading (code_parts.pyx:459-503)."""
+    featbits = _dev(featbits, torch.int32, "featbits")
+    graph = _dev(graph, torch.uint8, "graph")
+    if tuple(graph.shape) != (K, K):
+        raise ValueError("part_graph must be (%d,%d)" % (K, K))
+    R = featbits.shape[0] * featbits.shape[1]
+    _lib.call("tsr_spread_graph", _ptr(featbits), _ptr(graph), R, int(Fo), int(K), featbits.shape[2], _stream())
+    return featbits
+
+
+# ------------------------------------------------------------------------------- K3
+class FilterBank:
+    """M linear filters of L frames x D features (compute_likelihood_linear_filter's LF),
+    resident on the device both as fp32 (SIMT cross-check) and as the tensor kernel's blob."""
+
+    def __init__(self, LF, cs=None, device="cuda"):
+        LF = np.ascontiguousarray(LF)
+        if LF.dtype != np.float32:
+            raise ValueError("Buffer dtype mismatch, expected 'DTYPE_t' (float32) but got '%s'" % LF.dtype)
+        if LF.ndim < 3:
+            raise ValueError("LF must be (M, L, ...)")
+        self.M, self.L = LF.shape[0], LF.shape[1]
+        self.D = int(np.prod(LF.shape[2:]))
+        self.LF = torch.from_numpy(LF.reshape(self.M, self.L, self.D)).to(device)
+        self.cs = None if cs is None else torch.as_tensor(np.asarray(cs, dtype=np.float32).reshape(self.M)).to(device)
+        nbytes = _lib.lib().tsr_filter_blob_bytes(self.M, self.L, self.D)
+        if nbytes == 0:
+            raise ValueError("unsupported filter shape M=%d L=%d D=%d (need 1 <= L <= 256)" % (self.M, self.L, self.D))
+        self.blob = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        _lib.call("tsr_prepare_filters", _ptr(self.LF), self.M, self.L, self.D, _ptr(self.blob), _stream())
+
+
+def detect(featbits, bank, D=None, impl=IMPL_TENSOR, out=None):
+    """featbits int32 (B,T,rowwords) -> scores float32 (B,T,M), zero in the L-1 tail frames."""
+    featbits = _dev(featbits, torch.int32, "featbits")
+    B, T, rw = featbits.shape
+    D = bank.D if D is None else D
+    if rw != rowwords(D) or D != bank.D:
+        raise ValueError("feature width %d does not match the filters (%d)" % (D, bank.D))
+    if out is None:
+        out = torch.empty((B, T, bank.M), dtype=torch.float32, device=featbits.device)
+    _lib.call("tsr_detect", _ptr(featbits), B, T, D, rw, _ptr(bank.blob), _ptr(bank.LF), bank.M, bank.L, _ptr(out),
+              int(impl), _stream())
+    return out
+
+
+def detect_reduce(scores, cs, L, tail_mode=1):
+    """scores (B,T,M), cs (M,) | None -> (best float32 (B,T), arg int16 (B,T) holding uint16 ids)."""
+    scores = _dev(scores, torch.float32, "scores")
+    B, T, M = scores.shape
+    best = torch.empty((B, T), dtype=torch.float32, device=scores.device)
+    arg = torch.empty((B, T), dtype=torch.int16, device=scores.device)
+    _lib.call("tsr_detect_reduce", _ptr(scores), _ptr(cs), B, T, M, int(L), int(tail_mode), _ptr(best), _ptr(arg), _stream())
+    return best, arg
+
+
+def detect_float(Fm, LF, init=None):
+    """Fm float32 (B,T,D), LF float32 (M,L,D) device tensors -> scores (B,T,M); accumulations
+    start at init[m] when given."""
+    Fm = _dev(Fm, torch.float32, "F")
+    LF = _dev(LF, torch.float32, "LF")
+    B, T, D = Fm.shape
+    M, L, D2 = LF.shape
+    if D != D2:
+        raise ValueError("feature width mismatch")
+    out = torch.empty((B, T, M), dtype=torch.float32, device=Fm.device)
+    _lib.call("tsr_detect_float", _ptr(Fm), B, T, D, _ptr(LF), M, L, _ptr(init), _ptr(out), _stream())
+    return out
+
+
+# ------------------------------------------------------------------------------- K4
+class EmState:
+    """Device state of one rank's share of a Bernoulli-mixture EM problem."""
+
+    def __init__(self, Xbits, D, K):
+        self.X = _dev(Xbits, torch.int32, "Xbits")
+        if self.X.dim() != 2:
+            raise ValueError("Xbits must be (N, rowwords)")
+        self.N, self.rw = self.X.shape
+        self.D, self.K = int(D), int(K)
+        if self.rw != rowwords(D):
+            raise ValueError("Xbits width does not match D")
+        dev = self.X.device
+        nbytes = _lib.lib().tsr_em_workspace_bytes(self.N, self.D, self.K)
+        if nbytes == 0:
+            raise ValueError("unsupported EM shape (need 1 <= num_mix <= 64)")
+        self.ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        self.aff = torch.zeros((self.N, self.K), dtype=torch.float32, device=dev)
+        # stats = [K*D numerators | K responsibility sums]; ll kept separately in float64
+        self.stats = torch.zeros(self.K * self.D + self.K, dtype=torch.float32, device=dev)
+        self.ll = torch.zeros(1, dtype=torch.float64, device=dev)
+
+    def estep(self, logT, logInvT, logw, hard=False, impl=IMPL_TENSOR, scores_out=None):
+        self.stats.zero_()
+        self.ll.zero_()
+        _lib.call("tsr_em_estep", _ptr(self.X), self.N, self.D, self.rw, self.K, _ptr(logT), _ptr(logInvT), _ptr(logw),
+                  _ptr(self.aff), _ptr(scores_out), _ptr(self.stats), _ptr(self.ll), int(bool(hard)), _ptr(self.ws),
+                  int(impl), _stream())
+
+    def mstep_accumulate(self):
+        _lib.call("tsr_em_mstep", _ptr(self.X), self.N, self.D, self.rw, self.K, _ptr(self.aff), _ptr(self.stats),
+                  _ptr(self.ws), _stream())
+
+
+def em_finalize(stats, N_total, D, K, min_prob, templates, logT, logInvT, weights, logw):
+    _lib.call("tsr_em_finalize", _ptr(stats), int(N_total), int(D), int(K), float(min_prob), _ptr(templates), _ptr(logT),
+              _ptr(logInvT), _ptr(weights), _ptr(logw), _stream())

@@ -1,0 +1,189 @@
+"""The oracle (oracle/tsr_oracle.c + oracle/oracle.py) pinned against the reference:
+golden vectors generated from the compiled reference Cython, the compiled reference itself
+when present in this container, the docstring known-answer of BernoulliMixture, and
+independent NumPy/SciPy formulations.  CPU only."""
+import numpy as np
+import pytest
+
+from tsr_b200 import synth
+
+
+# ------------------------------------------------------------------ golden fixtures
+def test_code_parts_golden(oracle, golden):
+    g = golden
+    out = oracle.code_parts(g["cp_X"], g["cp_lp"], g["cp_lip"], int(g["cp_thr"]))
+    assert out.dtype == np.float64 and out.shape == g["cp_out"].shape
+    np.testing.assert_array_equal(out, g["cp_out"])          # same order, same f64 arithmetic: bit-exact
+    np.testing.assert_array_equal(oracle.code_parts_fast(g["cp_X"], g["cp_lp"], g["cp_lip"], 12), g["cp_out_fast"])
+    np.testing.assert_array_equal(oracle.code_parts(g["cp_X"], g["cp2_lp"], g["cp2_lip"], 5), g["cp2_out"])
+    # both sides of the threshold occur in the fixture
+    gate = g["cp_out"][..., 0] != 0
+    assert gate.any() and (~gate).any()
+
+
+def test_spread_patches_golden(oracle, golden):
+    g = golden
+    np.testing.assert_array_equal(oracle.spread_patches(g["cp_codes"], 2, 2, 7), g["sp_22"])
+    np.testing.assert_array_equal(oracle.spread_waliji_patches(g["cp_codes"], 1, 3, 7), g["sp_13"])
+    np.testing.assert_array_equal(oracle.spread_patches(g["cp_codes"], 0, 0, 7), g["sp_00"])
+    S = g["sp_00"].copy()
+    oracle.spread_graph_patches(S, g["graph"])
+    np.testing.assert_array_equal(S, g["sp_graph"])
+
+
+def test_detect_golden(oracle, golden):
+    g = golden
+    np.testing.assert_array_equal(oracle.detect(g["dt_F"], g["dt_LF"]), g["dt_out"])      # f32 sequential: bit-exact
+    np.testing.assert_array_equal(oracle.detect_float(g["df_F"], g["dt_LF"]), g["df_out"])
+    mx, am = oracle.detect_float_max(g["df_F"], g["dm_LF"], g["dm_cs"])
+    np.testing.assert_array_equal(mx, g["dm_max"])
+    np.testing.assert_array_equal(am, g["dm_arg"])
+    np.testing.assert_array_equal(oracle.detect_float2d(g["d2_F"], g["d2_LF"]), g["d2_out"])
+    np.testing.assert_array_equal(oracle.detect_spectral(g["d2_F"], g["d2_LF"]), g["d2_spec"])
+    np.testing.assert_array_equal(oracle.get_max_detect_examples(g["de_F"], g["de_LF"], g["de_len"]), g["de_max"])
+    # detect's contract: length T, the L-1 tail entries are exactly 0
+    L = g["dt_LF"].shape[0]
+    assert g["dt_out"].shape == (g["dt_F"].shape[0],) and np.all(g["dt_out"][-(L - 1):] == 0)
+
+
+# ------------------------------------------------- live differential vs compiled reference
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_against_compiled_reference(oracle, ref, seed):
+    if ref is None:
+        pytest.skip("oracle/_ref not built (no /root/reference here)")
+    cp, swp, clf = ref
+    rs = np.random.RandomState(seed)
+    T, F = rs.randint(8, 40), rs.randint(6, 20)
+    K = rs.randint(1, 12)
+    X = (rs.rand(T, F, 8) < rs.uniform(0.05, 0.3)).astype(np.uint8)
+    P = np.clip(rs.rand(K, 5, 5, 8) ** 2, .01, .99)
+    lp, lip = np.log(P), np.log(1 - P)
+    thr = int(rs.randint(0, 30))
+    a, b = oracle.code_parts(X, lp, lip, thr), cp.code_parts(X, lp, lip, thr)
+    np.testing.assert_array_equal(a, b)
+    np.testing.assert_array_equal(oracle.code_parts_fast(X, lp, lip, thr), cp.code_parts_fast(X, lp, lip, thr))
+    codes = np.argmax(b, -1)
+    r0, r1 = rs.randint(0, 4), rs.randint(0, 6)
+    np.testing.assert_array_equal(oracle.spread_patches(codes, r0, r1, K), cp.spread_patches(codes, r0, r1, K))
+    np.testing.assert_array_equal(oracle.spread_patches(codes, r0, r1, K), swp.spread_waliji_patches(codes, r0, r1, K))
+    S = cp.spread_patches(codes, r0, r1, K)
+    L = rs.randint(1, T - 4)
+    LF = rs.randn(L, S.shape[1], K).astype(np.float32)
+    np.testing.assert_array_equal(oracle.detect(S, LF), clf.detect(S, LF))
+    # first-window mask count agrees with the reference (its later windows read M out of bounds)
+    M = (rs.rand(5, 5) < 0.5).astype(np.uint8)
+    o = oracle.code_parts_mask(X[:5, :5], M, lp, lip, 0, 0)
+    r = cp.code_parts_mask(X[:5, :5].copy(), M, lp, lip, 0, 0)
+    np.testing.assert_array_equal(o, r)
+
+
+def test_reference_rejects_float32_parts(ref):
+    if ref is None:
+        pytest.skip("oracle/_ref not built")
+    X = np.zeros((6, 6, 8), np.uint8)
+    lp = np.zeros((2, 5, 5, 8), np.float32)
+    with pytest.raises(ValueError, match="Buffer dtype mismatch"):
+        ref[0].code_parts(X, lp, lp, 1)
+
+
+# ----------------------------------------------------- independent formulations
+def test_code_parts_equals_correlation(oracle):
+    """Development/092412/scripts/test_new_part_coding.py:9-37: scores are
+    correlate(E, lp) + correlate(1-E, lip) over the valid region."""
+    from scipy.signal import correlate
+    rs = np.random.RandomState(5)
+    X = (rs.rand(14, 11, 8) < 0.2).astype(np.uint8)
+    P = np.clip(rs.rand(3, 5, 5, 8) ** 2, .01, .99)
+    lp, lip = np.log(P), np.log(1 - P)
+    out = oracle.code_parts(X, lp, lip, 0)
+    for k in range(3):
+        ref = correlate(X.astype(float), lp[k], mode="valid")[..., 0] + correlate(1. - X, lip[k], mode="valid")[..., 0]
+        np.testing.assert_allclose(out[..., k + 1], ref, rtol=1e-12, atol=1e-10)
+
+
+def test_planted_parts_are_recovered(oracle):
+    """Development/092412/scripts/test_waliji_coding.py:72-120 pattern: every 5x5x8 block is the
+    most likely configuration of part j, so the code at block origins must be j+1."""
+    K = 12
+    rs = np.random.RandomState(11)
+    P = np.where(rs.rand(K, 5, 5, 8) < 0.3, 0.9, 0.05)
+    lp, lip = np.log(P), np.log(1 - P)
+    X = np.zeros((5 * K, 5, 8), np.uint8)
+    for j in range(K):
+        X[5 * j:5 * j + 5] = P[j] > 0.5
+    codes = np.argmax(oracle.code_parts(X, lp, lip, 1), -1)
+    np.testing.assert_array_equal(codes[::5, 0], np.arange(K) + 1)
+
+
+def test_spread_edges_vs_ndimage(oracle):
+    from scipy.ndimage import maximum_filter
+    rs = np.random.RandomState(3)
+    T = (rs.rand(9, 17) < 0.15).astype(np.float64)
+    for s in (1, 2, 3):
+        np.testing.assert_array_equal(oracle._spread_edges(T, (1, 0), s), maximum_filter(T, size=(2 * s + 1, 1), mode="constant"))
+        np.testing.assert_array_equal(oracle._spread_edges(T, (0, -1), s), maximum_filter(T, size=(1, 2 * s + 1), mode="constant"))
+        fp = np.eye(2 * s + 1)
+        np.testing.assert_array_equal(oracle._spread_edges(T, (1, 1), s), maximum_filter(T, footprint=fp, mode="constant"))
+        np.testing.assert_array_equal(oracle._spread_edges(T, (-1, 1), s), maximum_filter(T, footprint=fp[::-1], mode="constant"))
+        E = np.vstack([T, T])
+        oracle.spread_edgemap_all(E, [0, 9, 18], s)
+        np.testing.assert_array_equal(E[:9], maximum_filter(T, size=(2 * s + 1, 2 * s + 1), mode="constant"))
+
+
+def test_linear_filter_identities(oracle):
+    """Development/071912/fast_like/test_fast_like.py:61-75: W, C against the closed forms and
+    sum(E*W)+C == log P(E|T) - log P(E|bgd)."""
+    rs = np.random.RandomState(7)
+    T = rs.uniform(.05, .95, (6, 4, 3))
+    bg = rs.uniform(.05, .4, (4, 3))
+    W, c = oracle.construct_linear_filter(T, bg)
+    assert W.dtype == np.float32
+    np.testing.assert_allclose(W, np.log(T / (1 - T)) - np.log(bg / (1 - bg)), rtol=1e-6)
+    np.testing.assert_allclose(c, np.log((1 - T) / (1 - bg)).sum(), rtol=1e-12)
+    E = (rs.rand(6, 4, 3) < 0.3).astype(float)
+    llr = (E * np.log(T) + (1 - E) * np.log(1 - T)).sum() - (E * np.log(bg) + (1 - E) * np.log(1 - bg)).sum()
+    np.testing.assert_allclose((E * W).sum() + c, llr, rtol=1e-5)
+    Wc, cc = oracle.construct_linear_filter(T, bg, all_cs=True)
+    np.testing.assert_allclose(cc[-1], c, rtol=1e-12)
+    # single-window score == detect at one offset (+ A13), test_template.py:25-41
+    tmpl, bgd = T.reshape(6, 12).T, bg.reshape(12)
+    s, C = oracle.score_template_background_section(tmpl, bgd, E.reshape(6, 12).T)
+    np.testing.assert_allclose(s + C, llr, rtol=1e-9)
+    d = oracle.detect(E.astype(np.uint8), W)
+    np.testing.assert_allclose(d[0], s, rtol=1e-5)
+
+
+# -------------------------------------------------------------- Bernoulli mixture KAT
+def test_bernoulli_mixture_docstring_kat(oracle):
+    """bernoulli_mixture.py:50-71, the only numeric known-answer on the hot path."""
+    data = np.array([[1, 1, 0], [0, 0, 1], [1, 1, 1]])
+    m = oracle.BernoulliMixture(2, data)
+    m.run_EM(1e-3)
+    np.testing.assert_allclose(m.templates, [[.95, .95, .50010438], [.05, .05, .95]], atol=1e-5)
+    np.testing.assert_allclose(m.weights, [.66671347, .33328653], atol=1e-5)
+    np.testing.assert_allclose(m.affinities, [[9.99861515e-01, 1.38484719e-04], [2.90861524e-03, 9.97091385e-01],
+                                              [9.97376426e-01, 2.62357439e-03]], atol=1e-5)
+
+
+def test_bernoulli_mixture_planted(oracle):
+    """tests.py:491-506 recipe: planted templates are recovered and the log-likelihood is monotone."""
+    X, z, T, w = synth.em_data(N=600, D=36, K=3, seed=4)
+    m = oracle.BernoulliMixture(3, X)
+    m.run_EM(1e-6, min_probability=.01)
+    tr = np.array(m.loglikelihood_trace)
+    assert np.all(np.diff(tr) > -1e-6 * np.abs(tr[:-1]))
+    # each planted template is matched by some estimated one
+    err = np.abs(m.templates[:, None, :] - T[None]).mean(-1)
+    assert err.min(0).max() < 0.08
+    m2 = oracle.Bernoulli_Mixture(3, X.reshape(600, 6, 6))
+    m2.run_EM(1e-4)
+    assert np.isfinite(m2.loglikelihood) and m2.templates.min() >= .05 and m2.templates.max() <= .95
+
+
+def test_synth_generators_are_seeded():
+    a, b = synth.utterance_edges(3), synth.utterance_edges(3)
+    np.testing.assert_array_equal(a, b)
+    assert a.shape == (300, 40, 8) and a.dtype == np.uint8 and 0.03 < a.mean() < 0.2
+    assert synth.fast_edge_batch(4).shape == (4, 300, 40, 8)
+    lp, lip = synth.parts(5)
+    assert lp.dtype == np.float64 and np.allclose(np.exp(lp) + np.exp(lip), 1)
