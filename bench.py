@@ -1,0 +1,358 @@
+#!/usr/bin/env python
+"""bench.py -- edge-frames/second coded + scored (BASELINE.json metric).
+
+Workload at every N: the full scoring pipeline of BASELINE config 3 on a batch of synthetic
+utterances (300 frames x 40 bands x 8 edges) PER GPU -- edge spreading (radius 1 per 40-frame
+block) -> code_parts (100 parts of 5x5x8, threshold 12, fused arg-max) -> part-code spreading
+(2,2) -> 32-component mixture of 40-frame part-level templates LLR detection -> max/arg-max.
+Config 2 (spread + code + spread only) is the "coding" subset of the same step and is reported
+under "stages".  Utterances shard across ranks with no data-path collective ("weak" scaling).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl native|reference]
+
+One JSON line on stdout (rank 0).  `value` = frames of all ranks / max-over-ranks device time
+with inputs resident in HBM; `e2e` = same metric through the public NumPy-facing batch API with
+pinned HOST buffers (H2D of the uint8 edge tensors and D2H of the score tracks inside the timed
+region); `roofline` = the dominant kernel (detection) against the measured bf16 peak;
+`cpu_baseline` = the reference Cython (oracle/_ref) or its C port timed on the host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+T_FRAMES, F_BANDS, E_EDGES = 300, 40, 8
+K_PARTS, PH, PW = 100, 5, 5
+M_TEMPL, L_TEMPL = 32, 40
+TO, FO = T_FRAMES - PH + 1, F_BANDS - PW + 1
+EDGE_THR, PART_SPREAD, EDGE_RADIUS, EDGE_BLOCK = 12, (2, 2), 1, 40
+
+# algorithmic work per utterance; hi+lo split NOT counted
+FLOP_CODE = 2.0 * TO * FO * PH * PW * E_EDGES * K_PARTS                 # 426.2 MFLOP
+FLOP_DETECT = 2.0 * (TO - L_TEMPL + 1) * L_TEMPL * FO * K_PARTS * M_TEMPL   # 2.369 GFLOP
+BYTES_SPREAD_EDGES = 2.0 * T_FRAMES * F_BANDS                           # 24 000 B
+BYTES_SPREAD_CODES = (1 + 4 * 4) * FO * TO                              # 181 152 B  (1 B code + 16 B bitset per location)
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sustained=d["bf16_tflops_sustained"], src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, src="fallback")
+
+
+# --------------------------------------------------------------------------- clocks sampler
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------ CPU arm
+def _cpu_worker(args):
+    """Full reference chain for one utterance on one core; returns (t_code, t_detect_per_template*M_sub)."""
+    u, m_sub, use_ref = args
+    from oracle import oracle
+    from tsr_b200 import synth, ops
+    ref = oracle.load_ref() if use_ref else None
+    cp_code = ref[0].code_parts if ref else oracle.code_parts
+    cp_spread = ref[0].spread_patches if ref else oracle.spread_patches
+    det = ref[2].detect if ref else oracle.detect
+    lp, lip = synth.parts(K_PARTS)
+    Tm, bgd = synth.templates(M=m_sub, L=L_TEMPL, Fd=FO, Kd=K_PARTS)
+    W, c = synth.linear_filters(Tm, bgd)
+    X = synth.utterance_edges(u)
+    ori = ops.DEFAULT_EDGE_ORIENTATIONS.astype(int)
+    t0 = time.perf_counter()
+    Xs = np.zeros_like(X)
+    for e in range(8):                                      # edge_signal_proc.py:1635-1663, NumPy restatement
+        for s in range(0, T_FRAMES, EDGE_BLOCK):
+            Xs[s:s + EDGE_BLOCK, :, e] = oracle._spread_edges(X[s:s + EDGE_BLOCK, :, e].T.astype(float), ori[e], EDGE_RADIUS).T
+    out = cp_code(Xs, lp, lip, EDGE_THR)                    # get_train_data.py:2619-2625
+    codes = np.argmax(out, -1)
+    S = cp_spread(codes, PART_SPREAD[0], PART_SPREAD[1], K_PARTS)
+    t1 = time.perf_counter()
+    best = det(S, W[0]) + c[0]                              # get_train_data.py:964-992
+    for m in range(1, m_sub):
+        best = np.maximum(det(S, W[m]) + c[m], best)
+    t2 = time.perf_counter()
+    return t1 - t0, t2 - t1
+
+
+def cpu_arm(n_utts, m_sub, cores):
+    """Time the reference CPU path on `n_utts` utterances over `cores` worker processes.
+    Returns (frames_per_second, description).  Detection is run with m_sub of the 32 templates and
+    its time scaled by 32/m_sub (each template is an independent, identical-cost detect() call)."""
+    import multiprocessing as mp
+    from oracle import oracle
+    oracle.build()
+    use_ref = oracle.load_ref() is not None
+    ctx = mp.get_context("fork")
+    jobs = [(u, m_sub, use_ref) for u in range(n_utts)]
+    t0 = time.perf_counter()
+    if cores > 1:
+        with ctx.Pool(cores) as pool:
+            res = pool.map(_cpu_worker, jobs, chunksize=1)
+    else:
+        res = [_cpu_worker(j) for j in jobs]
+    wall = time.perf_counter() - t0
+    t_code = sum(r[0] for r in res)
+    t_det = sum(r[1] for r in res)
+    scale = (t_code + t_det * M_TEMPL / m_sub) / max(t_code + t_det, 1e-9)
+    fps = n_utts * T_FRAMES / (wall * scale)
+    kind = "reference" if use_ref else "port"
+    sample = ("%d utterances x full chain (spread, code_parts, argmax, spread_patches, detect x %d of %d templates, "
+              "detect time scaled x%.1f); %d worker processes; wall %.1f s" % (n_utts, m_sub, M_TEMPL, M_TEMPL / m_sub, cores, wall))
+    return fps, kind, sample
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    per_step_budget = 200.0 / max(args.steps + args.warmup, 1)
+    # one utterance costs ~0.35 s (coding) + ~0.11 s per template on one core
+    m_sub = int(max(1, min(M_TEMPL, (per_step_budget - 0.6) / 0.15)))
+    vals = []
+    for i in range(args.warmup + args.steps):
+        fps, kind, sample = cpu_arm(cores, m_sub, cores)
+        if i >= args.warmup:
+            vals.append(fps)
+    v = float(np.mean(vals))
+    ms = 1e3 * cores * T_FRAMES / v
+    line = {"impl": "reference", "metric": "edge-frames/sec coded+scored", "value": v, "unit": "frames/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64/f32 (reference CPU arithmetic)", "data": "synthetic",
+            "config": workload_config(cores),
+            "cpu_baseline": {"value": v, "unit": "frames/s", "cores": cores, "kind": kind, "sample": sample},
+            "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def workload_config(batch):
+    return {"workload": "config3 full scoring pipeline: spread_edges(r=1,block=40) -> code_parts(100 parts 5x5x8, thr 12, argmax) "
+                        "-> spread_patches(2,2) -> 32 x 40-frame part-level template LLR detect -> max/argmax",
+            "utterance": "300 frames x 40 bands x 8 edges", "utterances_per_gpu": batch, "parts": K_PARTS, "templates": M_TEMPL,
+            "template_frames": L_TEMPL, "sharding": "by utterance, no collective",
+            "l2": "256 MB flush buffer written between timed steps; per-step working set (138 MB feature bits + 39 MB scores) also exceeds the 126 MB L2"}
+
+
+# ------------------------------------------------------------------------------ GPU arm
+def run_native(args):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from tsr_b200 import ops, synth
+    from tsr_b200.pipeline import ScoringPipeline
+
+    B = args.batch
+    lp, lip = synth.parts(K_PARTS)
+    Tm, bgd = synth.templates(M=M_TEMPL, L=L_TEMPL, Fd=FO, Kd=K_PARTS)
+    W, c = synth.linear_filters(Tm, bgd)
+    pipe = ScoringPipeline(lp, lip, W, c, edge_threshold=EDGE_THR, part_spread=PART_SPREAD,
+                           edge_spread_radius=EDGE_RADIUS, edge_block_len=EDGE_BLOCK, device=dev)
+    if args.simt:
+        pipe.impl_code = pipe.impl_detect = ops.IMPL_SIMT
+    X = synth.fast_edge_batch(B, seed=7 + rank)                               # (B,300,40,8) uint8 host
+    X_pinned = torch.from_numpy(X).pin_memory()
+    bits = ops.pack_edges(X_pinned.to(dev))                                    # resident input of the kernel-only timing
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream()
+
+    names = ["spread_edges", "code_parts", "spread_codes", "detect", "reduce"]
+
+    def step(evs=None):
+        def mark(i):
+            if evs is not None:
+                evs[i].record(stream)
+        mark(0)
+        sb = ops.spread_edges(bits, EDGE_RADIUS, None, "line", EDGE_BLOCK)
+        mark(1)
+        codes, _, _ = ops.code_parts(sb, pipe.parts, EDGE_THR, impl=pipe.impl_code)
+        mark(2)
+        fb = ops.spread_codes(codes, K_PARTS, *PART_SPREAD)
+        mark(3)
+        scores = ops.detect(fb, pipe.bank, impl=pipe.impl_detect)
+        mark(4)
+        best, arg = ops.detect_reduce(scores, pipe.bank.cs, L_TEMPL, tail_mode=1)
+        mark(5)
+        return best, arg
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    all_evs = []
+    for _ in range(args.steps):
+        flush.fill_(1)                                                          # evict L2 (outside the per-step events)
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
+        step(evs)
+        all_evs.append(evs)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    step_ms = [e[0].elapsed_time(e[5]) for e in all_evs]
+    stage_ms = [float(np.mean([e[i].elapsed_time(e[i + 1]) for e in all_evs])) for i in range(5)]
+    total_ms = float(sum(step_ms))
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+
+    # ---- e2e: NumPy-facing batch call, pinned host in, host out, chunked so copies overlap compute
+    res_best = torch.empty((B, TO), dtype=torch.float32).pin_memory()
+    res_arg = torch.empty((B, TO), dtype=torch.int16).pin_memory()
+    nchunk = 4
+    cs = (B + nchunk - 1) // nchunk
+    copy_stream = torch.cuda.Stream(device=dev)
+
+    def e2e_step():
+        done = []
+        for s in range(0, B, cs):
+            with torch.cuda.stream(copy_stream):
+                xd = X_pinned[s:s + cs].to(dev, non_blocking=True)
+                ev = torch.cuda.Event(); ev.record(copy_stream)
+            stream.wait_event(ev)
+            b_ = ops.pack_edges(xd)
+            xd.record_stream(stream)
+            best, arg, _ = pipe(b_)
+            res_best[s:s + cs].copy_(best, non_blocking=True)
+            res_arg[s:s + cs].copy_(arg, non_blocking=True)
+            done.append((best, arg))
+        stream.synchronize()
+
+    e2e_steps = max(2, min(args.steps, 5))
+    e2e_step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s = float(t.item())
+    clocks = sampler.stop() if rank == 0 else None
+
+    if rank == 0:
+        peaks = measured_peaks()
+        frames = B * T_FRAMES * world
+        value = frames * args.steps / (total_ms * 1e-3)
+        det_ms = stage_ms[3]
+        det_tf = FLOP_DETECT * B / (det_ms * 1e-3) / 1e12
+        code_tf = FLOP_CODE * B / (stage_ms[1] * 1e-3) / 1e12
+        stages = {
+            "spread_edges": {"ms": stage_ms[0], "bound": "hbm", "achieved_gbs": BYTES_SPREAD_EDGES * B / (stage_ms[0] * 1e-3) / 1e9,
+                             "frac": BYTES_SPREAD_EDGES * B / (stage_ms[0] * 1e-3) / 1e9 / peaks["hbm"]},
+            "code_parts": {"ms": stage_ms[1], "bound": "tensor", "achieved_tflops": code_tf, "frac": code_tf / peaks["tf_sustained"]},
+            "spread_codes": {"ms": stage_ms[2], "bound": "hbm", "achieved_gbs": BYTES_SPREAD_CODES * B / (stage_ms[2] * 1e-3) / 1e9,
+                             "frac": BYTES_SPREAD_CODES * B / (stage_ms[2] * 1e-3) / 1e9 / peaks["hbm"]},
+            "detect": {"ms": det_ms, "bound": "tensor", "achieved_tflops": det_tf, "frac": det_tf / peaks["tf_sustained"]},
+            "reduce": {"ms": stage_ms[4]},
+            "config2_coding_frames_per_s": B * T_FRAMES * world / (sum(stage_ms[:3]) * 1e-3),
+        }
+        line = {
+            "metric": "edge-frames/sec coded+scored", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16 hi+lo x {0,1} bf16, fp32 accumulate (u8 bit-packed for spreading)",
+            "data": "synthetic", "config": workload_config(B),
+            "roofline": {"kernel": "detect_tc_kernel", "bound": "tensor", "achieved": det_tf, "peak": peaks["tf_sustained"],
+                         "unit": "TFLOP/s", "frac": det_tf / peaks["tf_sustained"], "traffic": None,
+                         "peak_source": peaks["src"] + " bf16_tflops_sustained (kernel timed inside the step)",
+                         "algorithmic_flop_per_launch": FLOP_DETECT * B,
+                         "note": "algorithmic FLOPs count the single-pass contraction; the bf16 hi+lo split issues 2x"},
+            "stages": stages,
+            "e2e": {"value": frames * e2e_steps / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": int(X_pinned.numel()),
+                    "d2h_bytes_per_step": int(res_best.numel() * 4 + res_arg.numel() * 2),
+                    "api": "pipeline.ScoringPipeline on pinned uint8 (B,300,40,8) host edges, 4 chunks, copy/compute overlap"},
+            "gpu_launches": 5 * args.steps,
+            "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu:
+            cores = os.cpu_count() or 1
+            n_utts = max(cores, 4) if cores <= 64 else cores
+            fps, kind, sample = cpu_arm(n_utts, 8, cores)
+            line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": cores, "kind": kind, "sample": sample}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=1024, help="utterances per GPU")
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--simt", action="store_true", help="use the SIMT cross-check kernels for coding and detection")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3 if args.impl == "native" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_native(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -18,6 +18,7 @@ _INT_MAX = 2 ** 31 - 1
 
 
 def _parts(log_parts, log_invparts, mask=None):
+    """Validated, cached device copy of a part dictionary (arguments are checked before any GPU work)."""
     lp = typed(log_parts, np.float64, 4, "DTYPE_t")
     lip = typed(log_invparts, np.float64, 4, "DTYPE_t")
     if lip.shape != lp.shape:
@@ -51,6 +52,7 @@ def _run(X, parts, threshold, mask_threshold=-1):
 def code_parts(X, log_parts, log_invparts, threshold):
     """code_parts.pyx:70-135.  Returns float64 (T-ph+1, F-pw+1, K+1): slot 0 is -inf and slots
     1..K the part log-likelihoods where the window holds >= threshold edges, all zeros otherwise."""
+    X = typed(X, np.uint8, 3, "UINT_t")
     parts = _parts(log_parts, log_invparts)
     gate, scores, _ = _run(X, parts, _unsigned_threshold(threshold))
     out = np.zeros(scores.shape[:2] + (parts.K + 1,), np.float64)
@@ -62,6 +64,7 @@ def code_parts(X, log_parts, log_invparts, threshold):
 def code_parts_fast(X, log_parts, log_invparts, threshold):
     """code_parts.pyx:247-295: as code_parts but slot 0 = sum_k(score_k - 1) above threshold
     (:290-291) and 1.0 below (:293)."""
+    X = typed(X, np.uint8, 3, "UINT_t")
     parts = _parts(log_parts, log_invparts)
     gate, scores, _ = _run(X, parts, _unsigned_threshold(threshold))
     out = np.zeros(scores.shape[:2] + (parts.K + 1,), np.float64)
@@ -74,6 +77,7 @@ def code_parts_mask(X, M, log_parts, log_invparts, mask_threshold, absolute_thre
     """code_parts.pyx:353-404: gate = count >= absolute_threshold and mask_count > mask_threshold,
     mask_count counting edges under the 2-D window mask M (window-relative; the reference indexes
     M with absolute coordinates, which reads out of bounds -- see DESIGN.md)."""
+    X = typed(X, np.uint8, 3, "UINT_t")
     M = typed(M, np.uint8, 2, "UINT_t")
     parts = _parts(log_parts, log_invparts, mask=M)
     mt = int(mask_threshold)

@@ -1,0 +1,175 @@
+"""K3 parity on the GPU: sliding LLR detection.  The SIMT kernel reproduces the reference's
+float32 sequential sums bit for bit; the tcgen05 kernel matches the float64 sum within 1e-5
+relative (of the score scale), as does the reference's own float32 arithmetic."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(900)]
+RTOL = 1e-5
+
+
+def _f64_detect(F, LF):
+    T, L = F.shape[0], LF.shape[0]
+    out = np.zeros(T)
+    Ff = (F.reshape(T, -1) != 0).astype(np.float64)
+    W = LF.reshape(L, -1).astype(np.float64)
+    for t in range(T - L + 1):
+        out[t] = (Ff[t:t + L] * W).sum()
+    return out
+
+
+def _close(got, want, scale=None):
+    scale = np.abs(want).max() if scale is None else scale
+    err = np.abs(got - want).max()
+    assert err <= RTOL * max(scale, 1e-30), "max abs err %g vs scale %g (rel %g)" % (err, scale, err / scale)
+    return err / max(scale, 1e-30)
+
+
+def _gpu_detect(F, LF, impl):
+    """F uint8 (B,T,D1,D2), LF float32 (M,L,D1,D2) -> scores (B,T,M)"""
+    from tsr_b200 import ops
+    B, T = F.shape[:2]
+    bank = ops.FilterBank(LF)
+    fb = ops.pack_features(torch.from_numpy(np.ascontiguousarray(F.reshape(B, T, -1))).cuda())
+    out = ops.detect(fb, bank, impl=impl)
+    torch.cuda.synchronize()
+    return out.cpu().numpy()
+
+
+def test_detect_golden_simt_bit_exact(cuda, golden):
+    g = golden
+    out = _gpu_detect(g["dt_F"][None], g["dt_LF"][None], 1)
+    np.testing.assert_array_equal(out[0, :, 0], g["dt_out"])
+
+
+def test_detect_golden_tensor(cuda, golden):
+    g = golden
+    out = _gpu_detect(g["dt_F"][None], g["dt_LF"][None], 0)[0, :, 0]
+    _close(out, _f64_detect(g["dt_F"], g["dt_LF"]))
+    L = g["dt_LF"].shape[0]
+    assert np.all(out[-(L - 1):] == 0)
+    from tsr_b200 import compute_likelihood_linear_filter as clf
+    d = clf.detect(g["dt_F"], g["dt_LF"])
+    assert d.dtype == np.float32 and d.shape == g["dt_out"].shape
+    _close(d, g["dt_out"].astype(np.float64))
+
+
+def test_detect_config1_edge_level(cuda, oracle):
+    """BASELINE config 1: one (300,40,8) utterance, one 40-frame edge-level template."""
+    from tsr_b200 import synth, compute_likelihood_linear_filter as clf
+    X = synth.utterance_edges(0)
+    T, bgd = synth.templates(M=1, L=40, Fd=40, Kd=8)
+    W, c = synth.linear_filters(T, bgd)
+    ref32 = oracle.detect(X, W[0])
+    ref64 = _f64_detect(X, W[0])
+    got = clf.detect(X, W[0])
+    r = _close(got, ref64)
+    r32 = np.abs(ref32 - ref64).max() / np.abs(ref64).max()
+    print("edge-level detect: tensor rel err %.2e; reference float32 rel err %.2e" % (r, r32))
+    np.testing.assert_array_equal(_gpu_detect(X[None], W, 1)[0, :, 0], ref32)
+    assert np.all(got[261:] == 0) and np.all(got[:261] != 0)
+
+
+@pytest.mark.parametrize("impl", [1, 0], ids=["simt", "tensor"])
+def test_detect_part_level_mixture(cuda, oracle, impl):
+    """Config 3 shapes: S (296,36,100) spread part features, M = 32 templates of 40 frames."""
+    from tsr_b200 import synth
+    rs = np.random.RandomState(5)
+    M = 32 if impl == 0 else 3
+    S = (rs.rand(2, 296, 36, 100) < 0.136).astype(np.uint8)
+    T, bgd = synth.templates(M=M, L=40, Fd=36, Kd=100)
+    W, c = synth.linear_filters(T, bgd)
+    got = _gpu_detect(S, W, impl)
+    assert got.shape == (2, 296, M)
+    worst = 0.0
+    for m in sorted(set([0, 1, M - 1])):
+        for b in range(2):
+            ref64 = _f64_detect(S[b], W[m])
+            if impl == 1:
+                np.testing.assert_array_equal(got[b, :, m], oracle.detect(S[b], W[m]))
+            worst = max(worst, _close(got[b, :, m], ref64))
+    print("part-level detect rel err %.2e" % worst)
+    assert np.all(got[:, 257:, :] == 0)
+
+
+@pytest.mark.parametrize("B,T,D1,D2,M,L", [(1, 9, 3, 5, 1, 9), (3, 50, 7, 9, 5, 1), (2, 130, 40, 8, 7, 40),
+                                         (5, 77, 1, 1, 33, 13), (1, 700, 4, 16, 2, 200), (4, 20, 36, 100, 2, 3)])
+def test_detect_shapes(cuda, B, T, D1, D2, M, L):
+    rs = np.random.RandomState(B * 1000 + T)
+    F = (rs.rand(B, T, D1, D2) < 0.2).astype(np.uint8)
+    LF = rs.randn(M, L, D1, D2).astype(np.float32)
+    t = _gpu_detect(F, LF, 0)
+    s = _gpu_detect(F, LF, 1)
+    scale = np.abs(s).max()
+    for b in range(B):
+        for m in range(M):
+            _close(t[b, :, m], _f64_detect(F[b], LF[m]), scale)
+    np.testing.assert_allclose(t, s, atol=RTOL * scale)
+    if L > 1:
+        assert np.all(t[:, T - L + 1:, :] == 0)
+
+
+def test_detect_template_longer_than_input(cuda):
+    from tsr_b200 import compute_likelihood_linear_filter as clf
+    out = clf.detect(np.ones((5, 2, 2), np.uint8), np.ones((6, 2, 2), np.float32))
+    np.testing.assert_array_equal(out, np.zeros(5, np.float32))
+
+
+def test_detect_reduce_and_mixture_semantics(cuda):
+    """max / argmax over components exactly as get_train_data.py:964-992 computes them."""
+    from tsr_b200 import ops
+    rs = np.random.RandomState(6)
+    B, T, M, L = 3, 40, 5, 8
+    scores = rs.randn(B, T, M).astype(np.float32)
+    scores[:, T - L + 1:] = 0
+    scores[0, 3, :] = 1.0                                   # exact tie: first component wins
+    cs = rs.randn(M).astype(np.float32)
+    best, arg = ops.detect_reduce(torch.from_numpy(scores).cuda(), torch.from_numpy(cs).cuda(), L, tail_mode=1)
+    v = scores + cs[None, None]
+    want = v[..., 0].copy(); ids = np.zeros((B, T), np.uint16)
+    for m in range(1, M):                                    # the reference's running np.maximum with strict >
+        upd = v[..., m] > want
+        ids[upd] = m
+        want = np.maximum(v[..., m], want)
+    np.testing.assert_array_equal(best.cpu().numpy(), want)
+    np.testing.assert_array_equal(arg.cpu().numpy().view(np.uint16), ids)
+    best0, arg0 = ops.detect_reduce(torch.from_numpy(scores).cuda(), torch.from_numpy(cs).cuda(), L, tail_mode=0)
+    assert np.all(best0.cpu().numpy()[:, T - L + 1:] == 0) and np.all(arg0.cpu().numpy()[:, T - L + 1:] == 0)
+
+
+def test_float_variants_bit_exact(cuda, golden):
+    from tsr_b200 import compute_likelihood_linear_filter as clf
+    g = golden
+    np.testing.assert_array_equal(clf.detect_float(g["df_F"], g["dt_LF"]), g["df_out"])
+    mx, am = clf.detect_float_max(g["df_F"], g["dm_LF"], g["dm_cs"])
+    assert mx.dtype == np.float32 and am.dtype == np.uint16
+    np.testing.assert_array_equal(mx, g["dm_max"])
+    np.testing.assert_array_equal(am, g["dm_arg"])
+    np.testing.assert_array_equal(clf.detect_float2d(g["d2_F"], g["d2_LF"]), g["d2_out"])
+    np.testing.assert_array_equal(clf.detect_spectral(g["d2_F"], g["d2_LF"]), g["d2_spec"])
+
+
+def test_detect_examples(cuda, oracle, golden):
+    from tsr_b200 import compute_likelihood_linear_filter as clf
+    g = golden
+    mx = clf.get_max_detect_examples(g["de_F"], g["de_LF"], g["de_len"])
+    np.testing.assert_allclose(mx, g["de_max"], rtol=RTOL, atol=RTOL * np.abs(g["de_max"]).max())
+    de = clf.detect_examples(g["de_F"], g["de_LF"], g["de_len"], 25)
+    want = oracle.detect_examples(g["de_F"], g["de_LF"], g["de_len"], 25)
+    np.testing.assert_allclose(de, want, atol=RTOL * np.abs(want).max())
+
+
+def test_single_window_score(cuda, oracle):
+    from tsr_b200 import test_template as tt, estimate_template as et
+    rs = np.random.RandomState(7)
+    tmpl, bgd = rs.uniform(.05, .95, (12, 6)), rs.uniform(.05, .4, 12)
+    E = (rs.rand(12, 6) < 0.3).astype(float)
+    s, C = tt.score_template_background_section(tmpl, bgd, E)
+    s0, C0 = oracle.score_template_background_section(tmpl, bgd, E)
+    np.testing.assert_allclose(s, s0, rtol=RTOL)
+    np.testing.assert_allclose(C, C0, rtol=1e-12)
+    W, c = et.construct_linear_filter(tmpl.T.reshape(6, 12), bgd)
+    W0, c0 = oracle.construct_linear_filter(tmpl.T.reshape(6, 12), bgd)
+    np.testing.assert_array_equal(W, W0)
+    np.testing.assert_allclose(c, c0, rtol=1e-14)

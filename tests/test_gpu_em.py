@@ -1,0 +1,99 @@
+"""K4 parity on the GPU: Bernoulli-mixture EM against the NumPy restatement of
+bernoulli_mixture.py / bernoulli_em.py and the docstring known-answer (bernoulli_mixture.py:50-71)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(900)]
+RTOL = 1e-5
+
+
+def test_docstring_kat(cuda):
+    from tsr_b200.bernoulli_mixture import BernoulliMixture
+    data = np.array([[1, 1, 0], [0, 0, 1], [1, 1, 1]])
+    m = BernoulliMixture(2, data)
+    m.run_EM(1e-3)
+    np.testing.assert_allclose(m.templates, [[.95, .95, .50010438], [.05, .05, .95]], atol=1e-5)
+    np.testing.assert_allclose(m.weights, [.66671347, .33328653], atol=1e-5)
+    np.testing.assert_allclose(m.affinities, [[9.99861515e-01, 1.38484719e-04], [2.90861524e-03, 9.97091385e-01],
+                                              [9.97376426e-01, 2.62357439e-03]], atol=1e-5)
+    assert m.templates.shape == (2, 3) and m.affinities.dtype == np.float32
+
+
+@pytest.mark.parametrize("impl", [1, 0], ids=["simt", "tensor"])
+@pytest.mark.parametrize("N,D,K", [(700, 200, 7), (300, 1000, 16), (129, 33, 2)])
+def test_estep_matches_numpy(cuda, N, D, K, impl):
+    from tsr_b200 import ops, synth
+    X, _, T, w = synth.em_data(N=N, D=D, K=K, seed=N)
+    rs = np.random.RandomState(1)
+    Tm = np.clip(rs.rand(K, D), .05, .95).astype(np.float32)
+    wts = rs.dirichlet(np.ones(K)).astype(np.float32)
+    logT, logI, logw = np.log(Tm), np.log(1 - Tm), np.log(wts)
+    fb = ops.pack_features(torch.from_numpy(X[None]).cuda())[0]
+    st = ops.EmState(fb, D, K)
+    scores = torch.empty((N, K), dtype=torch.float32, device="cuda")
+    st.estep(torch.from_numpy(logT).cuda(), torch.from_numpy(logI).cuda(), torch.from_numpy(logw).cuda(),
+             impl=impl, scores_out=scores)
+    st.mstep_accumulate()
+    torch.cuda.synchronize()
+    Xd = X.astype(np.float64)
+    S = Xd @ logT.astype(np.float64).T + (1 - Xd) @ logI.astype(np.float64).T
+    np.testing.assert_allclose(scores.cpu().numpy(), S, rtol=RTOL)
+    ll = S + logw[None].astype(np.float64)
+    mx = ll.max(1, keepdims=True)
+    p = np.exp(ll - mx)
+    aff = p / p.sum(1, keepdims=True)
+    np.testing.assert_allclose(float(st.ll.item()), (np.log(p.sum(1)) + mx[:, 0]).sum(), rtol=1e-6)
+    np.testing.assert_allclose(st.aff.cpu().numpy(), aff, atol=2e-4)
+    stats = st.stats.cpu().numpy()
+    np.testing.assert_allclose(stats[K * D:], aff.sum(0), rtol=1e-4)
+    a32 = st.aff.cpu().numpy().astype(np.float64)
+    np.testing.assert_allclose(stats[:K * D].reshape(K, D), a32.T @ Xd, rtol=1e-5, atol=1e-4)
+
+
+def test_em_matches_restatement(cuda, oracle):
+    """Whole run_EM against the NumPy restatement: same iteration count, log-likelihood trace within
+    1e-5 relative, templates and weights close."""
+    from tsr_b200 import synth
+    from tsr_b200.bernoulli_mixture import BernoulliMixture
+    X, z, T, w = synth.em_data(N=3000, D=200, K=5, seed=21)
+    a = oracle.BernoulliMixture(5, X)
+    a.run_EM(1e-5, min_probability=.01)
+    b = BernoulliMixture(5, X)
+    b.run_EM(1e-5, min_probability=.01)
+    assert abs(a.iterations - b.iterations) <= 1
+    n = min(len(a.loglikelihood_trace), len(b.loglikelihood_trace))
+    np.testing.assert_allclose(b.loglikelihood_trace[:n], a.loglikelihood_trace[:n], rtol=RTOL)
+    if a.iterations == b.iterations:
+        np.testing.assert_allclose(b.templates, a.templates, atol=2e-3)
+        np.testing.assert_allclose(b.weights, a.weights, atol=1e-3)
+    assert b.templates.shape == (5, 200) and b.work_templates.dtype == np.float32
+    # hard assignment variant (:271-275)
+    c = oracle.BernoulliMixture(5, X); c.run_EM(1e-4, hard_assignment=True, max_iter=15)
+    d = BernoulliMixture(5, X); d.run_EM(1e-4, hard_assignment=True, max_iter=15)
+    np.testing.assert_allclose(d.loglikelihood_trace[0], c.loglikelihood_trace[0], rtol=RTOL)
+    assert set(np.unique(d.affinities)) <= {0.0, 1.0}
+
+
+def test_first_version_em(cuda, oracle):
+    from tsr_b200 import synth
+    from tsr_b200.bernoulli_em import Bernoulli_Mixture
+    X, _, _, _ = synth.em_data(N=400, D=36, K=3, seed=5)
+    a = oracle.Bernoulli_Mixture(3, X.reshape(400, 6, 6)); a.run_EM(1e-3)
+    b = Bernoulli_Mixture(3, X.reshape(400, 6, 6)); b.run_EM(1e-3)
+    np.testing.assert_allclose(b.loglikelihood, a.loglikelihood, rtol=1e-4)
+    assert b.templates.shape == (3, 6, 6) and b.templates.dtype == np.float64
+    assert b.templates.min() >= .05 - 1e-7 and b.templates.max() <= .95 + 1e-7
+
+
+def test_planted_templates_recovered(cuda):
+    """tests.py:491-506 recipe at D = 12 800 (40 frames x 40 bands x 8 edges), K = 16."""
+    from tsr_b200 import synth
+    from tsr_b200.bernoulli_mixture import BernoulliMixture
+    X, z, T, w = synth.em_data(N=4000, D=12800, K=16, seed=3)
+    m = BernoulliMixture(16, X)
+    m.run_EM(1e-6, min_probability=.05, max_iter=30)
+    tr = np.array(m.loglikelihood_trace)
+    assert np.all(np.diff(tr) > -1e-5 * np.abs(tr[:-1]))
+    err = np.abs(m.templates[:, None, :] - T[None]).mean(-1)
+    assert err.min(0).max() < 0.05

@@ -1,0 +1,41 @@
+"""End-to-end parity of the batched pipeline (spread -> code_parts -> spread_patches -> mixture
+LLR detection) against the oracle chained exactly as get_train_data.py:2576-2631 and :927-1011 do."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(900)]
+
+
+def test_pipeline_matches_oracle_chain(cuda, oracle):
+    from tsr_b200 import ops, synth
+    from tsr_b200.pipeline import ScoringPipeline
+    B, M = 4, 6
+    lp, lip = synth.parts(100)
+    T, bgd = synth.templates(M=M, L=40, Fd=36, Kd=100)
+    W, c = synth.linear_filters(T, bgd)
+    X = synth.utterance_batch(B)
+    pipe = ScoringPipeline(lp, lip, W, c, edge_threshold=12, part_spread=(2, 2), edge_spread_radius=1, edge_block_len=40)
+    bits = pipe.from_numpy(X)
+    best, arg, codes = pipe(bits)
+    torch.cuda.synchronize()
+    best, arg, codes = best.cpu().numpy(), arg.cpu().numpy().view(np.uint16), codes.cpu().numpy()
+    ori = ops.DEFAULT_EDGE_ORIENTATIONS.astype(int)
+    for b in range(B):
+        # K1a: per 40-frame block, radius 1 (edge_signal_proc.py:1635-1663)
+        Xs = np.zeros_like(X[b])
+        for e in range(8):
+            for s in range(0, 300, 40):
+                blk = X[b, s:s + 40, :, e].T.astype(np.float64)
+                Xs[s:s + 40, :, e] = oracle._spread_edges(blk, ori[e], 1).T
+        out = oracle.code_parts(Xs, lp, lip, 12)
+        ref_codes = np.argmax(out, -1)
+        mism = ref_codes != codes[b]
+        assert mism.sum() <= 2
+        S = oracle.spread_patches(codes[b].astype(np.int64), 2, 2, 100)       # continue from the GPU's codes
+        v = np.stack([oracle.detect(S, W[m]).astype(np.float64) + c[m] for m in range(M)], -1)
+        want = v.max(-1)
+        np.testing.assert_allclose(best[b], want, atol=1e-5 * np.abs(want).max())
+        top2 = np.sort(v, -1)
+        clear = (top2[:, -1] - top2[:, -2]) > 1e-4 * np.abs(top2[:, -1])
+        np.testing.assert_array_equal(arg[b][clear], v.argmax(-1)[clear])
