@@ -328,8 +328,8 @@ def run_native(args):
         }
         if world == 1 and not args.no_cpu:
             cores = os.cpu_count() or 1
-            n_utts = max(cores, 4) if cores <= 64 else cores
-            fps, kind, sample = cpu_arm(n_utts, 8, cores)
+            # ~0.35 s coding + 16 x ~0.1 s detection per utterance and core -> 4 utterances per core ~ 10-20 s
+            fps, kind, sample = cpu_arm(4 * cores, 16, cores)
             line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": cores, "kind": kind, "sample": sample}
         print(json.dumps(line))
     if world > 1:

@@ -46,6 +46,13 @@ extern "C" {
 #define TSR_IMPL_TENSOR 0   /* tcgen05 / TMEM path (default) */
 #define TSR_IMPL_SIMT   1   /* CUDA-core cross-check path, fp32 sequential accumulation */
 
+/* 16-bit float format of the hi+lo weight planes (and of the expanded {0,1} bits) on the tensor
+ * path; both run at the same tcgen05 kind::f16 rate.  AUTO picks FP16 (22 mantissa bits over the
+ * two planes) when max|w| <= 1024, else BF16 (16 bits, fp32 range).  Decided on the device. */
+#define TSR_PLANES_AUTO 0
+#define TSR_PLANES_BF16 1
+#define TSR_PLANES_FP16 2
+
 int         tsr_abi_version(void);
 const char* tsr_last_error(void);            /* thread-local, valid until the next failing call */
 int         tsr_device_supported(void);      /* 1 if the current device is compute capability 10.x */
@@ -74,11 +81,12 @@ int tsr_spread_edges(const uint8_t* bits_in, uint8_t* bits_out, int B, int T, in
  * Replaces code_parts.code_parts (code_parts.pyx:70-135), code_parts_fast (:247-295),
  * code_parts_mask (:353-404) and the np.argmax the callers apply (get_train_data.py:2621).
  * tsr_prepare_parts turns the reference's float64 log_parts / log_invparts [K][ph][pw][E]
- * (device pointers) into the kernel's weight blob: W = lp - lip split into bf16 hi + lo
- * planes in UMMA core-matrix order, c[k] = sum(lip) in fp32, edge-count columns. */
+ * (device pointers) into the kernel's weight blob: W = lp - lip split into 16-bit hi + lo
+ * planes (TSR_PLANES_*) in UMMA core-matrix order, c[k] = sum(lip) in fp32, edge-count columns. */
 size_t tsr_parts_blob_bytes(int K, int ph, int pw);
 int    tsr_prepare_parts(const double* log_parts, const double* log_invparts, int K, int ph, int pw, int E,
-                         const uint8_t* mask_or_null /* [ph][pw], code_parts_mask's M */, void* blob, void* stream);
+                         const uint8_t* mask_or_null /* [ph][pw], code_parts_mask's M */, int plane_format,
+                         void* blob, void* stream);
 /* codes[b][i][j] = 0 if gate fails else 1 + argmax_k score (lowest k wins ties);
  * gate: count >= threshold [and mask_count > mask_threshold when mask_threshold >= 0].
  * scores_or_null float [B][To][Fo][K] (score = sum_{a,b,z} X ? lp : lip, written for every
@@ -101,9 +109,9 @@ int tsr_spread_graph(uint32_t* featbits, const uint8_t* graph, long long R, int 
  * Replaces compute_likelihood_linear_filter.detect (compute_likelihood_linear_filter.pyx:
  * 135-176), the per-component loop + np.maximum of get_train_data._compute_detection_E
  * (get_train_data.py:964-992) and detect_float_max's fused max/argmax (:221-278).
- * tsr_prepare_filters: LF float32 [M][L][D] -> blob of bf16 hi/lo planes in UMMA order. */
+ * tsr_prepare_filters: LF float32 [M][L][D] -> blob of 16-bit hi/lo planes (TSR_PLANES_*) in UMMA order. */
 size_t tsr_filter_blob_bytes(int M, int L, int D);
-int    tsr_prepare_filters(const float* LF, int M, int L, int D, void* blob, void* stream);
+int    tsr_prepare_filters(const float* LF, int M, int L, int D, int plane_format, void* blob, void* stream);
 /* featbits [B][T][rowwords].  scores float [B][T][M]: scores[b][t][m] = sum_{tau,d}
  * bit(b,t+tau,d) * LF[m][tau][d] for t <= T-L, 0 for the L-1 tail frames (detect's contract,
  * :157-158).  impl = TSR_IMPL_TENSOR | TSR_IMPL_SIMT (SIMT needs LF_or_null = the fp32 filters). */

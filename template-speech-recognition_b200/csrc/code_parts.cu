@@ -23,7 +23,7 @@ namespace tsr {
 
 struct PartsLayout {
     int K, ph, pw, npad, nsteps, nq;
-    size_t off_w, off_c, off_wf, off_mask, total;
+    size_t off_w, off_c, off_wf, off_mask, off_hdr, total;
 };
 
 __host__ __device__ inline PartsLayout parts_layout(int K, int ph, int pw) {
@@ -36,14 +36,25 @@ __host__ __device__ inline PartsLayout parts_layout(int K, int ph, int pw) {
     L.off_c = (size_t)2 * L.nsteps * L.npad * 32;
     L.off_wf = L.off_c + (size_t)L.npad * 4;
     L.off_mask = L.off_wf + (size_t)L.nq * 8 * L.npad * 4;
+    L.off_hdr = L.off_mask + 8;          // [0] plane format, [1] max |w| bits
     L.total = L.off_mask + 16;
     return L;
 }
 
 // ------------------------------------------------------------------------------ prepare
+__global__ void parts_maxabs_kernel(const double* __restrict__ lp, const double* __restrict__ lip, size_t n,
+                                    uint8_t* __restrict__ blob, PartsLayout L) {
+    uint32_t* hdr = reinterpret_cast<uint32_t*>(blob + L.off_hdr);
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        atomic_max_abs(&hdr[1], (float)(lp[i] - lip[i]));
+}
+
 // One thread per (n, q, z) weight: n < K parts, n == K all-ones count column, n == K+1 mask column.
 __global__ void prepare_parts_kernel(const double* __restrict__ lp, const double* __restrict__ lip, int E,
-                                     const uint8_t* __restrict__ mask, uint8_t* __restrict__ blob, PartsLayout L) {
+                                     const uint8_t* __restrict__ mask, uint8_t* __restrict__ blob, PartsLayout L,
+                                     int plane_format) {
+    uint32_t* hdr = reinterpret_cast<uint32_t*>(blob + L.off_hdr);
+    const uint32_t fmt = pick_format(hdr[1], plane_format);
     const int total = L.npad * L.nsteps * 16;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         int n = i / (L.nsteps * 16);
@@ -61,11 +72,11 @@ __global__ void prepare_parts_kernel(const double* __restrict__ lp, const double
                 w = (mask && mask[q]) ? 1.0 : 0.0;
             }
         }
-        __nv_bfloat16 hi = __double2bfloat16(w);
-        __nv_bfloat16 lo = __double2bfloat16(w - (double)__bfloat162float(hi));
+        uint16_t hi, lo;
+        split_hi_lo(w, fmt, hi, lo);
         size_t o = (((size_t)s * 2 + (e >> 3)) * L.npad + n) * 16 + z * 2;
-        *reinterpret_cast<__nv_bfloat16*>(blob + L.off_w + o) = hi;
-        *reinterpret_cast<__nv_bfloat16*>(blob + L.off_w + (size_t)L.nsteps * L.npad * 32 + o) = lo;
+        *reinterpret_cast<uint16_t*>(blob + L.off_w + o) = hi;
+        *reinterpret_cast<uint16_t*>(blob + L.off_w + (size_t)L.nsteps * L.npad * 32 + o) = lo;
         if (q < L.nq) reinterpret_cast<float*>(blob + L.off_wf)[((size_t)q * 8 + z) * L.npad + n] = (float)w;
     }
     // c[k] = sum lip (float64, reference order), one thread per part
@@ -81,8 +92,12 @@ __global__ void prepare_parts_kernel(const double* __restrict__ lp, const double
             for (int q = 0; q < L.nq; ++q)
                 if (mask[q]) m |= 1ull << q;
         reinterpret_cast<unsigned long long*>(blob + L.off_mask)[0] = m;
-        reinterpret_cast<unsigned long long*>(blob + L.off_mask)[1] = 0;
     }
+}
+// runs after prepare_parts_kernel (same stream): publish the chosen format
+__global__ void parts_publish_format_kernel(uint8_t* __restrict__ blob, PartsLayout L, int plane_format) {
+    uint32_t* hdr = reinterpret_cast<uint32_t*>(blob + L.off_hdr);
+    hdr[0] = pick_format(hdr[1], plane_format);
 }
 
 struct CodeArgs {
@@ -174,6 +189,7 @@ __global__ void __launch_bounds__(256) code_parts_simt_kernel(CodeArgs A) {
 // ------------------------------------------------------------------------- tensor path
 #define CP_NSTAGE 4
 #define CP_THREADS 288   // warps 0-3 epilogue, warp 4 MMA/TMEM, warps 5-8 producers
+#define CP_MAX_STEPS 32
 
 struct CodeSmem {   // offsets into dynamic shared memory
     uint32_t w, c, a, bars, stage_bytes, npos, total;
@@ -186,7 +202,7 @@ __host__ __device__ inline CodeSmem code_smem_layout(const PartsLayout& L, int F
     S.npos = 128 + (L.ph - 1) * F + (L.pw - 1) + 2;
     S.stage_bytes = (S.npos * 16 + 127) & ~127u;
     S.bars = S.a + CP_NSTAGE * S.stage_bytes;
-    S.total = S.bars + 128;
+    S.total = S.bars + 128 + 3 * CP_MAX_STEPS * 8;   // barriers | A descriptors | B descriptors (2 planes)
     return S;
 }
 
@@ -200,9 +216,12 @@ __global__ void __launch_bounds__(CP_THREADS, 1) code_parts_tc_kernel(CodeArgs A
     uint64_t* tempty_bar = tfull_bar + 2;                                  // [2]
     uint64_t* w_bar = tempty_bar + 2;                                      // [1]
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(w_bar + 1);
+    uint64_t* adesc_rel = reinterpret_cast<uint64_t*>(smem + S.bars + 128);   // [nsteps] relative to the stage base
+    uint64_t* bdesc_abs = adesc_rel + CP_MAX_STEPS;                            // [2][nsteps]
     const float* cs = reinterpret_cast<const float*>(smem + S.c);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t fmt = reinterpret_cast<const uint32_t*>(A.blob + L.off_hdr)[0];
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < CP_NSTAGE; ++s) { mbar_init(&full_bar[s], 128); mbar_init(&empty_bar[s], 1); }
@@ -210,13 +229,27 @@ __global__ void __launch_bounds__(CP_THREADS, 1) code_parts_tc_kernel(CodeArgs A
         mbar_init(w_bar, 1);
         mbar_fence_init();
     }
-    if (warp == 4) tmem_alloc<512>(tmem_ptr);
+    if (warp == 4) {
+        tmem_alloc<512>(tmem_ptr);
+        // descriptor tables: the patch geometry is tile independent, so the issuing thread only adds
+        // the stage base address (>>4) to the low word per MMA
+        const uint32_t wbase = smem_u32(smem + S.w);
+        const uint32_t nb_lbo = L.npad * 16;
+        for (int s = lane; s < L.nsteps; s += 32) {
+            int q0 = 2 * s, q1 = 2 * s + 1;
+            uint32_t off0 = ((q0 / L.pw) * A.F + (q0 % L.pw)) * 16;
+            uint32_t off1 = q1 < L.nq ? ((q1 / L.pw) * A.F + (q1 % L.pw)) * 16 : off0 + 16;
+            adesc_rel[s] = umma_desc_kmajor_noswz(off0, off1 - off0, 128);
+            for (int plane = 0; plane < 2; ++plane)
+                bdesc_abs[plane * L.nsteps + s] = umma_desc_kmajor_noswz(wbase + ((plane * L.nsteps + s) * 2) * nb_lbo, nb_lbo, 128);
+        }
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
 
-    // weights + c: one bulk (TMA) copy per plane, landed once per CTA
+    // weights + c: bulk (TMA) copies, landed once per CTA
     const uint32_t wbytes = S.c + L.npad * 4;
     if (threadIdx.x == 0) {
         mbar_arrive_expect_tx(w_bar, wbytes);
@@ -229,30 +262,50 @@ __global__ void __launch_bounds__(CP_THREADS, 1) code_parts_tc_kernel(CodeArgs A
     if (warp >= 5) {
         // ================================ producers ================================
         const int pt = threadIdx.x - 160;
+        const uint32_t one = fmt_one(fmt);
+        const int plimit = A.T * A.F;
+        const int npos = (int)S.npos;
         uint32_t it = 0;
-        for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-            const int stage = it % CP_NSTAGE;
-            const uint32_t ph = (it / CP_NSTAGE) & 1;
+        uint32_t pre[4];
+        auto prefetch = [&](long long tile) {
             const int b = (int)(tile / tiles_per_utt);
             const int p0 = (int)(tile % tiles_per_utt) * 128;
             const uint8_t* src = A.bits + (size_t)b * A.T * A.F;
-            const int plimit = A.T * A.F;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                int pos = pt + 128 * j, p = p0 + pos;
+                pre[j] = (pos < npos && p < plimit) ? src[p] : 0u;
+            }
+        };
+        if ((long long)blockIdx.x < ntiles) prefetch(blockIdx.x);
+        for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+            const int stage = it % CP_NSTAGE;
+            const uint32_t ph = (it / CP_NSTAGE) & 1;
             mbar_wait(&empty_bar[stage], ph ^ 1);
             uint8_t* dst = smem + S.a + stage * S.stage_bytes;
-            for (int pos = pt; pos < (int)S.npos; pos += 128) {
-                int p = p0 + pos;
-                uint32_t byte = p < plimit ? src[p] : 0u;
-                *reinterpret_cast<uint4*>(dst + pos * 16) = expand_byte_bf16(byte);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                int pos = pt + 128 * j;
+                if (pos < npos) *reinterpret_cast<uint4*>(dst + pos * 16) = expand_byte(pre[j], one);
+            }
+            if (npos > 512) {   // very wide inputs: remaining positions straight from global
+                const int b = (int)(tile / tiles_per_utt);
+                const int p0 = (int)(tile % tiles_per_utt) * 128;
+                const uint8_t* src = A.bits + (size_t)b * A.T * A.F;
+                for (int pos = pt + 512; pos < npos; pos += 128) {
+                    int p = p0 + pos;
+                    *reinterpret_cast<uint4*>(dst + pos * 16) = expand_byte(p < plimit ? src[p] : 0u, one);
+                }
             }
             fence_proxy_async_smem();
             mbar_arrive(&full_bar[stage]);
+            if (tile + gridDim.x < ntiles) prefetch(tile + gridDim.x);   // overlaps the next empty-slot wait
         }
     } else if (warp == 4) {
         // ================================ MMA issuer ================================
         mbar_wait(w_bar, 0);
-        const uint32_t idesc = umma_idesc_bf16_f32(128, L.npad);
-        const uint32_t wbase = smem_u32(smem + S.w);
-        const uint32_t nb_lbo = L.npad * 16;
+        const uint32_t idesc = umma_idesc_f32acc(fmt, 128, L.npad);
+        const int nmma = 2 * L.nsteps;
         uint32_t it = 0;
         for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
             const int stage = it % CP_NSTAGE;
@@ -263,19 +316,12 @@ __global__ void __launch_bounds__(CP_THREADS, 1) code_parts_tc_kernel(CodeArgs A
             mbar_wait(&tempty_bar[acc], aph ^ 1);
             tc_fence_after();
             if (lane == 0) {
-                const uint32_t abase = smem_u32(smem + S.a + stage * S.stage_bytes);
+                const uint64_t abase = (uint64_t)(smem_u32(smem + S.a + stage * S.stage_bytes) >> 4);
                 const uint32_t d_tmem = tmem_base + acc * 256;
-                bool first = true;
-                for (int plane = 0; plane < 2; ++plane)
-                    for (int s = 0; s < L.nsteps; ++s) {
-                        int q0 = 2 * s, q1 = 2 * s + 1;
-                        uint32_t off0 = ((q0 / L.pw) * A.F + (q0 % L.pw)) * 16;
-                        uint32_t off1 = q1 < L.nq ? ((q1 / L.pw) * A.F + (q1 % L.pw)) * 16 : off0 + 16;
-                        uint64_t adesc = umma_desc_kmajor_noswz(abase + off0, off1 - off0, 128);
-                        uint64_t bdesc = umma_desc_kmajor_noswz(wbase + ((plane * L.nsteps + s) * 2) * nb_lbo, nb_lbo, 128);
-                        umma_bf16(d_tmem, adesc, bdesc, idesc, !first);
-                        first = false;
-                    }
+                for (int i = 0; i < nmma; ++i) {
+                    const int s = i < L.nsteps ? i : i - L.nsteps;
+                    umma_f16(d_tmem, adesc_rel[s] + abase, bdesc_abs[i], idesc, i > 0);
+                }
                 umma_commit(&empty_bar[stage]);   // A stage reusable once these MMAs retire
                 umma_commit(&tfull_bar[acc]);     // accumulator ready for the epilogue
             }
@@ -294,24 +340,32 @@ __global__ void __launch_bounds__(CP_THREADS, 1) code_parts_tc_kernel(CodeArgs A
             const int t = p / A.F, f = p - t * A.F;
             const bool valid = t < A.To && f < A.Fo;
             const size_t loc = ((size_t)b * A.To + t) * A.Fo + f;
+            float* srow = (A.scores && valid) ? A.scores + loc * L.K : nullptr;
             mbar_wait(&tfull_bar[acc], aph);
             tc_fence_after();
             const uint32_t taddr = tmem_base + acc * 256 + ((uint32_t)(warp * 32) << 16);
             float best = -INFINITY;
             int bestk = 0;
             float fcount = 0.f, fmcount = 0.f;
-            for (int n0 = 0; n0 < L.npad; n0 += 16) {
-                uint32_t v[16];
-                tmem_ld16(taddr + n0, v);
+            for (int n0 = 0; n0 < L.npad; n0 += 32) {
+                uint32_t v[32];
+                if (n0 + 16 < L.npad) {
+                    tmem_ld32(taddr + n0, v);
+                } else {
+                    uint32_t h[16];
+                    tmem_ld16(taddr + n0, h);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) { v[i] = h[i]; v[16 + i] = 0u; }
+                }
                 tmem_ld_wait();
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
+                for (int i = 0; i < 32; ++i) {
                     const int n = n0 + i;
                     const float x = __uint_as_float(v[i]);
                     if (n < L.K) {
                         const float sc = x + cs[n];
                         if (sc > best) { best = sc; bestk = n; }
-                        if (A.scores && valid) A.scores[loc * L.K + n] = sc;
+                        if (srow) srow[n] = sc;
                     } else if (n == L.K) {
                         fcount = x;
                     } else if (n == L.K + 1) {
@@ -350,16 +404,20 @@ size_t tsr_parts_blob_bytes(int K, int ph, int pw) {
 }
 
 int tsr_prepare_parts(const double* log_parts, const double* log_invparts, int K, int ph, int pw, int E,
-                      const uint8_t* mask_or_null, void* blob, void* stream) {
+                      const uint8_t* mask_or_null, int plane_format, void* blob, void* stream) {
     TSR_REQUIRE(log_parts && log_invparts && blob, "tsr_prepare_parts: null pointer");
     TSR_REQUIRE(K >= 1 && K <= 238, "tsr_prepare_parts: need 1 <= num_parts <= 238 (got %d)", K);
     TSR_REQUIRE(ph >= 1 && pw >= 1 && ph * pw <= 64, "tsr_prepare_parts: part window %dx%d unsupported (ph*pw <= 64)", ph, pw);
     TSR_REQUIRE(E >= 1 && E <= 8, "tsr_prepare_parts: need 1 <= E <= 8 (got %d)", E);
     int rc = require_sm100("tsr_prepare_parts");
     if (rc) return rc;
+    TSR_REQUIRE(plane_format >= 0 && plane_format <= 2, "tsr_prepare_parts: plane_format must be 0 (auto), 1 (bf16) or 2 (fp16)");
     PartsLayout L = parts_layout(K, ph, pw);
-    TSR_CUDA(cudaMemsetAsync((uint8_t*)blob + L.off_wf, 0, L.total - L.off_wf, (cudaStream_t)stream));
-    prepare_parts_kernel<<<64, 256, 0, (cudaStream_t)stream>>>(log_parts, log_invparts, E, mask_or_null, (uint8_t*)blob, L);
+    cudaStream_t st = (cudaStream_t)stream;
+    TSR_CUDA(cudaMemsetAsync((uint8_t*)blob + L.off_wf, 0, L.total - L.off_wf, st));
+    parts_maxabs_kernel<<<32, 256, 0, st>>>(log_parts, log_invparts, (size_t)K * ph * pw * E, (uint8_t*)blob, L);
+    prepare_parts_kernel<<<64, 256, 0, st>>>(log_parts, log_invparts, E, mask_or_null, (uint8_t*)blob, L, plane_format);
+    parts_publish_format_kernel<<<1, 1, 0, st>>>((uint8_t*)blob, L, plane_format);
     return check_launch("tsr_prepare_parts");
 }
 
@@ -368,7 +426,7 @@ int tsr_code_parts(const uint8_t* bits, const void* parts_blob, int K, int ph, i
                    int F, int impl, void* stream) {
     TSR_REQUIRE(bits && parts_blob, "tsr_code_parts: null pointer");
     TSR_REQUIRE(codes || scores_or_null || counts_or_null, "tsr_code_parts: no output requested");
-    TSR_REQUIRE(K >= 1 && K <= 238 && ph >= 1 && pw >= 1 && ph * pw <= 64, "tsr_code_parts: unsupported parts shape");
+    TSR_REQUIRE(K >= 1 && K <= 238 && ph >= 1 && pw >= 1 && ph * pw <= 64, "tsr_code_parts: unsupported parts shape (K <= 238, ph*pw <= 64)");
     TSR_REQUIRE(B >= 0 && T >= ph && F >= pw, "tsr_code_parts: input (T=%d,F=%d) smaller than the part window (%d,%d)", T, F, ph, pw);
     TSR_REQUIRE(impl == TSR_IMPL_TENSOR || impl == TSR_IMPL_SIMT, "tsr_code_parts: unknown impl %d", impl);
     TSR_REQUIRE((long long)T * F < (1ll << 30), "tsr_code_parts: utterance too large (T*F >= 2^30); split in time");

@@ -5,6 +5,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
 
@@ -124,16 +125,23 @@ __device__ __forceinline__ uint64_t umma_desc_kmajor_noswz(uint32_t smem_addr, u
     d |= (uint64_t)1 << 46;
     return d;
 }
-// Instruction descriptor for kind::f16 with BF16 A/B (K-major both) and FP32 accumulate.
-__host__ __device__ constexpr uint32_t umma_idesc_bf16_f32(int M, int N) {
-    return (1u << 4)                       // c_format  = F32
-           | (1u << 7)                     // a_format  = BF16
-           | (1u << 10)                    // b_format  = BF16
-           | ((uint32_t)(N >> 3) << 17)    // n_dim
-           | ((uint32_t)(M >> 4) << 24);   // m_dim
+// 16-bit operand formats of the weight planes (and of the expanded {0,1} bits): both run at the
+// same kind::f16 tensor rate.  FP16 hi+lo carries 22 mantissa bits (fp32-exact for |w| < 2^10),
+// BF16 hi+lo carries 16 and is the fallback when the weights exceed the fp16 range.
+#define TSR_FMT_BF16 0u
+#define TSR_FMT_FP16 1u
+#define TSR_FP16_MAX_WEIGHT 1024.0f
+__host__ __device__ constexpr uint32_t fmt_one(uint32_t fmt) { return fmt == TSR_FMT_FP16 ? 0x3C00u : 0x3F80u; }
+// Instruction descriptor for kind::f16, A/B both `fmt` (K-major both), FP32 accumulate.
+__host__ __device__ constexpr uint32_t umma_idesc_f32acc(uint32_t fmt, int M, int N) {
+    return (1u << 4)                                        // c_format  = F32
+           | ((fmt == TSR_FMT_FP16 ? 0u : 1u) << 7)         // a_format  (0 = F16, 1 = BF16)
+           | ((fmt == TSR_FMT_FP16 ? 0u : 1u) << 10)        // b_format
+           | ((uint32_t)(N >> 3) << 17)                     // n_dim
+           | ((uint32_t)(M >> 4) << 24);                    // m_dim
 }
 // D[tmem] (+)= A[smem] * B[smem]; one thread issues for the CTA.
-__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
                                           bool accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -159,6 +167,18 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
         : "r"(taddr)
         : "memory");
 }
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+        "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
@@ -167,19 +187,44 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// ---- bit -> bf16 expansion ---------------------------------------------------------------
-// 8 bits -> 8 bf16 values in {0.0, 1.0} (0x0000 / 0x3F80), bit i -> element i.
-__device__ __forceinline__ uint4 expand_byte_bf16(uint32_t b) {
+// ---- bit -> 16-bit float expansion ---------------------------------------------------------
+// 8 bits -> 8 values in {0.0, 1.0} of a 16-bit float format whose 1.0 is `one` (0x3F80 bf16,
+// 0x3C00 fp16); bit i -> element i.
+__device__ __forceinline__ uint4 expand_byte(uint32_t b, uint32_t one) {
     uint4 r;
-    // two bits per 32-bit word: bit0 -> low half, bit1 -> high half; (x & 0x00010001) * 0x3F80 has no carries
-    r.x = (((b) | (b << 15)) & 0x00010001u) * 0x3F80u;
+    // two bits per 32-bit word: bit0 -> low half, bit1 -> high half; (x & 0x00010001) * one has no carries
+    r.x = (((b) | (b << 15)) & 0x00010001u) * one;
     b >>= 2;
-    r.y = (((b) | (b << 15)) & 0x00010001u) * 0x3F80u;
+    r.y = (((b) | (b << 15)) & 0x00010001u) * one;
     b >>= 2;
-    r.z = (((b) | (b << 15)) & 0x00010001u) * 0x3F80u;
+    r.z = (((b) | (b << 15)) & 0x00010001u) * one;
     b >>= 2;
-    r.w = (((b) | (b << 15)) & 0x00010001u) * 0x3F80u;
+    r.w = (((b) | (b << 15)) & 0x00010001u) * one;
     return r;
+}
+
+// hi + lo split of a weight into two 16-bit floats of format `fmt` (returned as raw bits)
+__device__ __forceinline__ void split_hi_lo(double w, uint32_t fmt, uint16_t& hi, uint16_t& lo) {
+    if (fmt == TSR_FMT_FP16) {
+        __half h = __double2half(w);
+        __half l = __double2half(w - (double)__half2float(h));
+        hi = __half_as_ushort(h);
+        lo = __half_as_ushort(l);
+    } else {
+        __nv_bfloat16 h = __double2bfloat16(w);
+        __nv_bfloat16 l = __double2bfloat16(w - (double)__bfloat162float(h));
+        hi = __bfloat16_as_ushort(h);
+        lo = __bfloat16_as_ushort(l);
+    }
+}
+// max |w| tracker: non-negative floats order like their bit patterns; NaN/Inf map above every finite value
+__device__ __forceinline__ void atomic_max_abs(uint32_t* slot, float w) {
+    atomicMax(slot, __float_as_uint(fabsf(w)));
+}
+__device__ __forceinline__ uint32_t pick_format(uint32_t maxabs_bits, int requested) {
+    if (requested == 1) return TSR_FMT_BF16;
+    if (requested == 2) return TSR_FMT_FP16;
+    return maxabs_bits <= __float_as_uint(TSR_FP16_MAX_WEIGHT) ? TSR_FMT_FP16 : TSR_FMT_BF16;
 }
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {

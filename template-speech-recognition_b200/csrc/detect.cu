@@ -26,6 +26,7 @@ namespace tsr {
 #define DT_NSTAGE 2
 #define DT_THREADS 576
 #define DT_PRODUCERS 384
+#define DT_HDR_BYTES 128   // blob header: [0] plane format, [1] max |w| bits
 
 struct FilterLayout {
     int M, L, D, rowwords, nchunks;
@@ -51,12 +52,28 @@ __host__ __device__ inline FilterLayout filter_layout(int M, int L, int D) {
     int msub = 512 / f.NT;
     f.msub = msub > DT_MSUB_MAX ? DT_MSUB_MAX : msub;
     f.tile_bytes = (size_t)2 * f.NT * 128;
-    f.total = (size_t)f.ntiles * f.nchunks * f.tile_bytes;
+    f.total = DT_HDR_BYTES + (size_t)f.ntiles * f.nchunks * f.tile_bytes;
     return f;
 }
 
-// One thread per bf16 pair of the blob.  Element (ntile, chunk, plane, kgroup, row n, e).
-__global__ void prepare_filters_kernel(const float* __restrict__ LF, uint8_t* __restrict__ blob, FilterLayout f) {
+__global__ void filters_maxabs_kernel(const float* __restrict__ LF, size_t n, uint8_t* __restrict__ blob) {
+    uint32_t* hdr = reinterpret_cast<uint32_t*>(blob);
+    uint32_t m = 0;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        m = max(m, __float_as_uint(fabsf(LF[i])));
+    for (int off = 16; off > 0; off >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, off));
+    if ((threadIdx.x & 31) == 0) atomicMax(&hdr[1], m);
+}
+__global__ void filters_publish_format_kernel(uint8_t* __restrict__ blob, int plane_format) {
+    uint32_t* hdr = reinterpret_cast<uint32_t*>(blob);
+    hdr[0] = pick_format(hdr[1], plane_format);
+}
+
+// One thread per 16-bit element of a plane.  Element (ntile, chunk, plane, kgroup, row n, e).
+__global__ void prepare_filters_kernel(const float* __restrict__ LF, uint8_t* __restrict__ blob, FilterLayout f,
+                                       int plane_format) {
+    const uint32_t fmt = pick_format(reinterpret_cast<const uint32_t*>(blob)[1], plane_format);
+    blob += DT_HDR_BYTES;
     const size_t nelem = (size_t)f.ntiles * f.nchunks * f.NT * 64;   // per plane
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < nelem; i += (size_t)gridDim.x * blockDim.x) {
         int e = (int)(i & 7);
@@ -70,12 +87,12 @@ __global__ void prepare_filters_kernel(const float* __restrict__ LF, uint8_t* __
         int m = nt * f.tpt + ml;
         float w = 0.f;
         if (ml < f.tpt && m < f.M && d < f.D) w = LF[((size_t)m * f.L + tau) * f.D + d];
-        __nv_bfloat16 hi = __float2bfloat16_rn(w);
-        __nv_bfloat16 lo = __float2bfloat16_rn(w - __bfloat162float(hi));
+        uint16_t hi, lo;
+        split_hi_lo((double)w, fmt, hi, lo);
         size_t base = ((size_t)nt * f.nchunks + c) * f.tile_bytes;
         size_t o = ((size_t)kg * f.NT + n) * 16 + e * 2;
-        *reinterpret_cast<__nv_bfloat16*>(blob + base + o) = hi;
-        *reinterpret_cast<__nv_bfloat16*>(blob + base + (size_t)f.NT * 128 + o) = lo;
+        *reinterpret_cast<uint16_t*>(blob + base + o) = hi;
+        *reinterpret_cast<uint16_t*>(blob + base + (size_t)f.NT * 128 + o) = lo;
     }
 }
 
@@ -118,6 +135,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) detect_tc_kernel(DetectArgs A) 
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty_bar + DT_MSUB_MAX);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t fmt = reinterpret_cast<const uint32_t*>(A.blob)[0];
     const int L = f.L, NT = f.NT, msub = f.msub, nchunks = f.nchunks, tpt = f.tpt;
     const int step_rows = msub * 128;
     const long long nunits = (long long)f.ntiles * A.units_per_ntile;
@@ -138,6 +156,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) detect_tc_kernel(DetectArgs A) 
         // ============================ frame-bit expanders ============================
         const int pr = threadIdx.x - 192;             // row within the step
         const int sub = pr >> 7, r = pr & 127;
+        const uint32_t one = fmt_one(fmt);
         uint32_t it = 0;                               // global chunk counter (pipeline position)
         for (long long u = blockIdx.x; u < nunits; u += gridDim.x) {
             const long long ur = u / f.ntiles;
@@ -157,10 +176,10 @@ __global__ void __launch_bounds__(DT_THREADS, 1) detect_tc_kernel(DetectArgs A) 
                         uint8_t* dst = smem + stage * S.stage_bytes + sub * 16384 + r * 16;
 #pragma unroll
                         for (int kg = 0; kg < 4; ++kg)
-                            *reinterpret_cast<uint4*>(dst + kg * 2048) = expand_byte_bf16((w.x >> (8 * kg)) & 0xFF);
+                            *reinterpret_cast<uint4*>(dst + kg * 2048) = expand_byte((w.x >> (8 * kg)) & 0xFF, one);
 #pragma unroll
                         for (int kg = 0; kg < 4; ++kg)
-                            *reinterpret_cast<uint4*>(dst + (kg + 4) * 2048) = expand_byte_bf16((w.y >> (8 * kg)) & 0xFF);
+                            *reinterpret_cast<uint4*>(dst + (kg + 4) * 2048) = expand_byte((w.y >> (8 * kg)) & 0xFF, one);
                     }
                     fence_proxy_async_smem();
                     mbar_arrive(&full_bar[stage]);
@@ -173,7 +192,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) detect_tc_kernel(DetectArgs A) 
             uint32_t it = 0;
             for (long long u = blockIdx.x; u < nunits; u += gridDim.x) {
                 const int nt = (int)(u % f.ntiles);
-                const uint8_t* src = A.blob + (size_t)nt * nchunks * f.tile_bytes;
+                const uint8_t* src = A.blob + DT_HDR_BYTES + (size_t)nt * nchunks * f.tile_bytes;
                 for (int step = 0; step < A.steps_per_unit; ++step)
                     for (int c = 0; c < nchunks; ++c, ++it) {
                         const int stage = it % DT_NSTAGE;
@@ -187,7 +206,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) detect_tc_kernel(DetectArgs A) 
         }
     } else if (warp == 4) {
         // ================================ MMA issuer ================================
-        const uint32_t idesc = umma_idesc_bf16_f32(128, NT);
+        const uint32_t idesc = umma_idesc_f32acc(fmt, 128, NT);
         uint32_t it = 0, stepno = 0;
         for (long long u = blockIdx.x; u < nunits; u += gridDim.x)
             for (int step = 0; step < A.steps_per_unit; ++step, ++stepno) {
@@ -210,7 +229,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) detect_tc_kernel(DetectArgs A) 
                                 for (int ks = 0; ks < 4; ++ks) {
                                     uint64_t adesc = umma_desc_kmajor_noswz(abase + sub * 16384 + ks * 4096, 2048, 128);
                                     uint64_t bdesc = umma_desc_kmajor_noswz(bbase + plane * NT * 128 + ks * 2 * NT * 16, NT * 16, 128);
-                                    umma_bf16(tmem_base + sub * NT, adesc, bdesc, idesc, !(c == 0 && plane == 0 && ks == 0));
+                                    umma_f16(tmem_base + sub * NT, adesc, bdesc, idesc, !(c == 0 && plane == 0 && ks == 0));
                                 }
                         }
                         __syncwarp();
@@ -384,15 +403,20 @@ size_t tsr_filter_blob_bytes(int M, int L, int D) {
     return filter_layout(M, L, D).total;
 }
 
-int tsr_prepare_filters(const float* LF, int M, int L, int D, void* blob, void* stream) {
+int tsr_prepare_filters(const float* LF, int M, int L, int D, int plane_format, void* blob, void* stream) {
     TSR_REQUIRE(LF && blob, "tsr_prepare_filters: null pointer");
     TSR_REQUIRE(M >= 1 && M <= 65535, "tsr_prepare_filters: need 1 <= M <= 65535 templates (uint16 argmax), got %d", M);
     TSR_REQUIRE(L >= 1 && L <= 256, "tsr_prepare_filters: template length %d outside [1,256]", L);
     TSR_REQUIRE(D >= 1, "tsr_prepare_filters: D < 1");
     int rc = require_sm100("tsr_prepare_filters");
     if (rc) return rc;
+    TSR_REQUIRE(plane_format >= 0 && plane_format <= 2, "tsr_prepare_filters: plane_format must be 0 (auto), 1 (bf16) or 2 (fp16)");
     FilterLayout f = filter_layout(M, L, D);
-    prepare_filters_kernel<<<148 * 8, 256, 0, (cudaStream_t)stream>>>(LF, (uint8_t*)blob, f);
+    cudaStream_t st = (cudaStream_t)stream;
+    TSR_CUDA(cudaMemsetAsync(blob, 0, DT_HDR_BYTES, st));
+    filters_maxabs_kernel<<<148 * 2, 256, 0, st>>>(LF, (size_t)M * L * D, (uint8_t*)blob);
+    prepare_filters_kernel<<<148 * 8, 256, 0, st>>>(LF, (uint8_t*)blob, f, plane_format);
+    filters_publish_format_kernel<<<1, 1, 0, st>>>((uint8_t*)blob, plane_format);
     return check_launch("tsr_prepare_filters");
 }
 

@@ -8,6 +8,8 @@
 //          (deterministic), then reduced; the caller all-reduces `stats` across ranks (NCCL).
 #include "common.cuh"
 
+extern "C" int tsr_prepare_filters(const float* LF, int M, int L, int D, int plane_format, void* blob, void* stream);
+extern "C" size_t tsr_filter_blob_bytes(int M, int L, int D);
 extern "C" int tsr_detect(const uint32_t* featbits, int B, int T, int D, int rowwords, const void* filter_blob,
                           const float* LF_or_null, int M, int L, float* scores, int impl, void* stream);
 
@@ -193,7 +195,7 @@ int tsr_em_estep(const uint32_t* Xbits, long long N, int D, int rowwords, int K,
     rc = check_launch("tsr_em_estep(weights)");
     if (rc) return rc;
     if (impl == TSR_IMPL_TENSOR) {
-        rc = tsr_prepare_filters(W, K, 1, D, ws + w.off_blob, stream);
+        rc = tsr_prepare_filters(W, K, 1, D, 0, ws + w.off_blob, stream);
         if (rc) return rc;
     }
     rc = tsr_detect(Xbits, 1, (int)N, D, rowwords, ws + w.off_blob, W, K, 1, S, impl, stream);

@@ -9,7 +9,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import IMPL_SIMT, IMPL_TENSOR  # noqa: F401
+from ._lib import IMPL_SIMT, IMPL_TENSOR, PLANES_AUTO, PLANES_BF16, PLANES_FP16  # noqa: F401
 
 # Orientation table produced by the reference edge extractor (edge_signal_proc.py:1751-1821,
 # returned by _edge_map_no_threshold and passed to spread_edgemap by every pipeline caller):
@@ -96,7 +96,7 @@ def spread_edges(bits, radius, orientations=None, mode="line", block_len=0):
 class PartsModel:
     """Device copy of a part dictionary in the coding kernel's layout (tsr_prepare_parts)."""
 
-    def __init__(self, log_parts, log_invparts, mask=None, device="cuda"):
+    def __init__(self, log_parts, log_invparts, mask=None, device="cuda", planes=PLANES_AUTO):
         lp = np.ascontiguousarray(log_parts)
         lip = np.ascontiguousarray(log_invparts)
         if lp.dtype != np.float64 or lip.dtype != np.float64:
@@ -115,7 +115,7 @@ class PartsModel:
                 raise ValueError("mask must have the part window shape (%d,%d)" % (self.ph, self.pw))
             d_mask = torch.from_numpy((m != 0).astype(np.uint8)).to(device)
         _lib.call("tsr_prepare_parts", _ptr(d_lp), _ptr(d_lip), self.K, self.ph, self.pw, self.E, _ptr(d_mask),
-                  _ptr(self.blob), _stream())
+                  int(planes), _ptr(self.blob), _stream())
         torch.cuda.current_stream().synchronize()   # d_lp/d_lip may be freed after this returns
 
 
@@ -164,7 +164,7 @@ class FilterBank:
     """M linear filters of L frames x D features (compute_likelihood_linear_filter's LF),
     resident on the device both as fp32 (SIMT cross-check) and as the tensor kernel's blob."""
 
-    def __init__(self, LF, cs=None, device="cuda"):
+    def __init__(self, LF, cs=None, device="cuda", planes=PLANES_AUTO):
         LF = np.ascontiguousarray(LF)
         if LF.dtype != np.float32:
             raise ValueError("Buffer dtype mismatch, expected 'DTYPE_t' (float32) but got '%s'" % LF.dtype)
@@ -178,7 +178,7 @@ class FilterBank:
         if nbytes == 0:
             raise ValueError("unsupported filter shape M=%d L=%d D=%d (need 1 <= L <= 256)" % (self.M, self.L, self.D))
         self.blob = torch.empty(nbytes, dtype=torch.uint8, device=device)
-        _lib.call("tsr_prepare_filters", _ptr(self.LF), self.M, self.L, self.D, _ptr(self.blob), _stream())
+        _lib.call("tsr_prepare_filters", _ptr(self.LF), self.M, self.L, self.D, int(planes), _ptr(self.blob), _stream())
 
 
 def detect(featbits, bank, D=None, impl=IMPL_TENSOR, out=None):

@@ -86,14 +86,19 @@ def test_first_version_em(cuda, oracle):
     assert b.templates.min() >= .05 - 1e-7 and b.templates.max() <= .95 + 1e-7
 
 
-def test_planted_templates_recovered(cuda):
-    """tests.py:491-506 recipe at D = 12 800 (40 frames x 40 bands x 8 edges), K = 16."""
+def test_config4_shape_against_restatement(cuda, oracle):
+    """BASELINE config 4 shape (D = 12 800 = 40 frames x 40 bands x 8 edges, K = 16) on a 2 000-row
+    sample: log-likelihood trace of the GPU EM against the NumPy restatement, 1e-5 relative."""
     from tsr_b200 import synth
     from tsr_b200.bernoulli_mixture import BernoulliMixture
-    X, z, T, w = synth.em_data(N=4000, D=12800, K=16, seed=3)
-    m = BernoulliMixture(16, X)
-    m.run_EM(1e-6, min_probability=.05, max_iter=30)
-    tr = np.array(m.loglikelihood_trace)
-    assert np.all(np.diff(tr) > -1e-5 * np.abs(tr[:-1]))
-    err = np.abs(m.templates[:, None, :] - T[None]).mean(-1)
-    assert err.min(0).max() < 0.05
+    X, z, T, w = synth.em_data(N=2000, D=12800, K=16, seed=3)
+    a = oracle.BernoulliMixture(16, X)
+    a.run_EM(1e-6, min_probability=.05, max_iter=12)
+    b = BernoulliMixture(16, X)
+    b.run_EM(1e-6, min_probability=.05, max_iter=12)
+    n = min(len(a.loglikelihood_trace), len(b.loglikelihood_trace))
+    assert n >= 11
+    np.testing.assert_allclose(b.loglikelihood_trace[:n], a.loglikelihood_trace[:n], rtol=RTOL)
+    tr = np.array(b.loglikelihood_trace)
+    assert np.all(np.diff(tr) > -1e-5 * np.abs(tr[:-1]))          # EM never decreases the likelihood
+    np.testing.assert_allclose(b.weights, a.weights, atol=2e-3)
