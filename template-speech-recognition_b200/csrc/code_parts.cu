@@ -424,6 +424,7 @@ int tsr_prepare_parts(const double* log_parts, const double* log_invparts, int K
 int tsr_code_parts(const uint8_t* bits, const void* parts_blob, int K, int ph, int pw, int threshold,
                    int mask_threshold, uint8_t* codes, float* scores_or_null, uint16_t* counts_or_null, int B, int T,
                    int F, int impl, void* stream) {
+    if (B == 0) return TSR_OK;
     TSR_REQUIRE(bits && parts_blob, "tsr_code_parts: null pointer");
     TSR_REQUIRE(codes || scores_or_null || counts_or_null, "tsr_code_parts: no output requested");
     TSR_REQUIRE(K >= 1 && K <= 238 && ph >= 1 && pw >= 1 && ph * pw <= 64, "tsr_code_parts: unsupported parts shape (K <= 238, ph*pw <= 64)");

@@ -26,6 +26,7 @@ namespace tsr {
 #define DT_NSTAGE 2
 #define DT_THREADS 576
 #define DT_PRODUCERS 384
+#define DT_TAU_CHUNK 40    // diagonal sums are staged through smem in chunks of <= 40 filter frames
 #define DT_HDR_BYTES 128   // blob header: [0] plane format, [1] max |w| bits
 
 struct FilterLayout {
@@ -118,7 +119,7 @@ __host__ __device__ inline DetectSmem detect_smem_layout(const FilterLayout& f) 
     S.a = 0;
     S.b = S.a_bytes;                                   // within a stage
     S.stage = DT_NSTAGE * S.stage_bytes;               // epilogue staging [128][L+1] floats
-    S.outacc = S.stage + ((128 * (f.L + 1) * 4 + 127) & ~127u);
+    S.outacc = S.stage + ((128 * ((f.L < DT_TAU_CHUNK ? f.L : DT_TAU_CHUNK) + 1) * 4 + 127) & ~127u);
     S.bars = S.outacc + (((f.msub * 128 + f.L) * f.tpt * 4 + 127) & ~127u);
     S.total = S.bars + 128;
     return S;
@@ -242,10 +243,11 @@ __global__ void __launch_bounds__(DT_THREADS, 1) detect_tc_kernel(DetectArgs A) 
             }
     } else {
         // ================================= epilogue =================================
-        float* stg = reinterpret_cast<float*>(smem + S.stage);       // [128][L+1]
+        float* stg = reinterpret_cast<float*>(smem + S.stage);       // [128][TC+1]
         float* outacc = reinterpret_cast<float*>(smem + S.outacc);   // [step_rows + L - 1][tpt]
         const int e = threadIdx.x;                                    // 0..127 == TMEM lane
-        const int pitch = L + 1;
+        const int TC = L < DT_TAU_CHUNK ? L : DT_TAU_CHUNK;
+        const int pitch = TC + 1;
         const int nacc = (step_rows + L - 1) * tpt;
         uint32_t stepno = 0;
         for (long long u = blockIdx.x; u < nunits; u += gridDim.x) {
@@ -261,28 +263,34 @@ __global__ void __launch_bounds__(DT_THREADS, 1) detect_tc_kernel(DetectArgs A) 
                 for (int sub = 0; sub < msub; ++sub) {
                     const uint32_t taddr = tmem_base + sub * NT + ((uint32_t)(warp * 32) << 16);
                     for (int ml = 0; ml < tpt; ++ml) {
-                        for (int t0 = 0; t0 < L; t0 += 8) {
-                            uint32_t v[8];
-                            tmem_ld8(taddr + ml * L + t0, v);
-                            tmem_ld_wait();
+                        for (int c0 = 0; c0 < L; c0 += TC) {          // chunk of filter frames [c0, c0+cl)
+                            const int cl = (L - c0) < TC ? (L - c0) : TC;
+                            for (int t0 = 0; t0 < cl; t0 += 8) {
+                                uint32_t v[8];
+                                tmem_ld8(taddr + ml * L + c0 + t0, v);
+                                tmem_ld_wait();
 #pragma unroll
-                            for (int i = 0; i < 8; ++i)
-                                if (t0 + i < L) stg[e * pitch + t0 + i] = __uint_as_float(v[i]);
+                                for (int i = 0; i < 8; ++i)
+                                    if (t0 + i < cl) stg[e * pitch + t0 + i] = __uint_as_float(v[i]);
+                            }
+                            if (ml == tpt - 1 && c0 + cl >= L) {   // accumulator drained: hand it back to the MMA warp
+                                tc_fence_before();
+                                mbar_arrive(&tempty_bar[sub]);
+                            }
+                            named_bar_sync(1, 128);
+                            // out index q <-> row r0 = q - (L-1) at tau = 0; this chunk adds tau in [c0, c0+cl)
+                            for (int q = e; q < 128 + L - 1; q += 128) {
+                                const int r0 = q - (L - 1);
+                                int tlo = -r0 > c0 ? -r0 : c0;
+                                int thi = (128 - r0) < (c0 + cl) ? (128 - r0) : (c0 + cl);
+                                if (tlo < thi) {
+                                    float part = 0.f;
+                                    for (int tau = tlo; tau < thi; ++tau) part += stg[(r0 + tau) * pitch + (tau - c0)];
+                                    outacc[(sub * 128 + q) * tpt + ml] += part;
+                                }
+                            }
+                            named_bar_sync(1, 128);
                         }
-                        if (ml == tpt - 1) {   // this accumulator is drained: hand it back to the MMA warp
-                            tc_fence_before();
-                            mbar_arrive(&tempty_bar[sub]);
-                        }
-                        named_bar_sync(1, 128);
-                        for (int q = e; q < 128 + L - 1; q += 128) {
-                            float part = 0.f;
-                            const int r0 = q - (L - 1);
-                            const int tlo = r0 < 0 ? -r0 : 0;
-                            const int thi = (128 - r0) < L ? (128 - r0) : L;
-                            for (int tau = tlo; tau < thi; ++tau) part += stg[(r0 + tau) * pitch + tau];
-                            outacc[(sub * 128 + q) * tpt + ml] += part;
-                        }
-                        named_bar_sync(1, 128);
                     }
                 }
                 // rows [0, step_rows) of outacc are complete: out row g = step_row0 - (L-1) + oi
@@ -422,6 +430,7 @@ int tsr_prepare_filters(const float* LF, int M, int L, int D, int plane_format, 
 
 int tsr_detect(const uint32_t* featbits, int B, int T, int D, int rowwords, const void* filter_blob,
                const float* LF_or_null, int M, int L, float* scores, int impl, void* stream) {
+    if (B == 0) return TSR_OK;
     TSR_REQUIRE(featbits && scores, "tsr_detect: null pointer");
     TSR_REQUIRE(B >= 0 && T >= 1 && D >= 1 && M >= 1 && L >= 1, "tsr_detect: bad sizes");
     TSR_REQUIRE(rowwords == tsr_rowwords(D), "tsr_detect: rowwords must be tsr_rowwords(D)");
@@ -476,6 +485,7 @@ int tsr_detect(const uint32_t* featbits, int B, int T, int D, int rowwords, cons
 
 int tsr_detect_reduce(const float* scores, const float* cs, int B, int T, int M, int L, int tail_mode, float* best,
                       uint16_t* arg, void* stream) {
+    if (B == 0) return TSR_OK;
     TSR_REQUIRE(scores && (best || arg), "tsr_detect_reduce: null pointer");
     TSR_REQUIRE(B >= 0 && T >= 1 && M >= 1 && M <= 65535 && L >= 1, "tsr_detect_reduce: bad sizes");
     TSR_REQUIRE(tail_mode == 0 || tail_mode == 1, "tsr_detect_reduce: tail_mode must be 0 or 1");
@@ -491,6 +501,7 @@ int tsr_detect_reduce(const float* scores, const float* cs, int B, int T, int M,
 
 int tsr_detect_float(const float* Fm, int B, int T, int D, const float* LF, int M, int L, const float* init_or_null,
                      float* scores, void* stream) {
+    if (B == 0) return TSR_OK;
     TSR_REQUIRE(Fm && LF && scores, "tsr_detect_float: null pointer");
     TSR_REQUIRE(B >= 0 && T >= 1 && D >= 1 && M >= 1 && L >= 1, "tsr_detect_float: bad sizes");
     if (B == 0) return TSR_OK;

@@ -222,6 +222,7 @@ extern "C" {
 
 int tsr_spread_edges(const uint8_t* bits_in, uint8_t* bits_out, int B, int T, int F, int radius, int mode,
                      const int8_t* host_dirs, int block_len, void* stream) {
+    if (B == 0) return TSR_OK;
     TSR_REQUIRE(bits_in && bits_out, "tsr_spread_edges: null pointer");
     TSR_REQUIRE(bits_in != bits_out, "tsr_spread_edges: in-place operation is not supported");
     TSR_REQUIRE(B >= 0 && T >= 0 && F >= 0 && radius >= 0 && block_len >= 0, "tsr_spread_edges: negative size");
@@ -282,6 +283,7 @@ int tsr_spread_edges(const uint8_t* bits_in, uint8_t* bits_out, int B, int T, in
 
 int tsr_spread_codes(const uint8_t* codes, uint32_t* featbits, int B, int To, int Fo, int K, int r0, int r1,
                      int rowwords, void* stream) {
+    if (B == 0) return TSR_OK;
     TSR_REQUIRE(codes && featbits, "tsr_spread_codes: null pointer");
     TSR_REQUIRE(B >= 0 && To >= 0 && Fo >= 1 && r0 >= 0 && r1 >= 0, "tsr_spread_codes: negative size");
     TSR_REQUIRE(K >= 1 && K <= 255, "tsr_spread_codes: need 1 <= num_parts <= 255 (uint8 codes), got %d", K);

@@ -120,6 +120,7 @@ int tsr_device_supported(void) { return require_sm100("tsr_device_supported") ==
 int tsr_rowwords(int D) { return ((D + 63) / 64) * 2; }
 
 int tsr_pack_edges(const uint8_t* X, uint8_t* bits, int B, int T, int F, int E, void* stream) {
+    if (B == 0) return TSR_OK;
     TSR_REQUIRE(X && bits, "tsr_pack_edges: null pointer");
     TSR_REQUIRE(B >= 0 && T >= 0 && F >= 0 && E >= 1 && E <= 8, "tsr_pack_edges: need 1 <= E <= 8 (got %d)", E);
     long long n = (long long)B * T * F;
@@ -131,6 +132,7 @@ int tsr_pack_edges(const uint8_t* X, uint8_t* bits, int B, int T, int F, int E, 
 }
 
 int tsr_unpack_edges(const uint8_t* bits, uint8_t* X, int B, int T, int F, int E, void* stream) {
+    if (B == 0) return TSR_OK;
     TSR_REQUIRE(X && bits, "tsr_unpack_edges: null pointer");
     TSR_REQUIRE(B >= 0 && T >= 0 && F >= 0 && E >= 1 && E <= 8, "tsr_unpack_edges: need 1 <= E <= 8 (got %d)", E);
     long long n = (long long)B * T * F;

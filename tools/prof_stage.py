@@ -1,0 +1,43 @@
+"""Run one pipeline stage a few times on BASELINE-size inputs (for ncu / timing).
+   python tools/prof_stage.py code_parts|detect|spread_edges|spread_codes|all [--batch 1024] [--iters 3]"""
+import argparse
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from tsr_b200 import ops, synth  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("stage")
+ap.add_argument("--batch", type=int, default=1024)
+ap.add_argument("--iters", type=int, default=3)
+ap.add_argument("--simt", action="store_true")
+a = ap.parse_args()
+impl = ops.IMPL_SIMT if a.simt else ops.IMPL_TENSOR
+B = a.batch
+lp, lip = synth.parts(100)
+parts = ops.PartsModel(lp, lip)
+Tm, bgd = synth.templates(M=32, L=40, Fd=36, Kd=100)
+W, c = synth.linear_filters(Tm, bgd)
+bank = ops.FilterBank(W, cs=c)
+bits = ops.pack_edges(torch.from_numpy(synth.fast_edge_batch(B)).cuda())
+sb = ops.spread_edges(bits, 1, None, "line", 40)
+codes, _, _ = ops.code_parts(sb, parts, 12, impl=impl)
+fb = ops.spread_codes(codes, 100, 2, 2)
+torch.cuda.synchronize()
+ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+for it in range(a.iters):
+    ev[0].record()
+    if a.stage in ("spread_edges", "all"):
+        ops.spread_edges(bits, 1, None, "line", 40)
+    if a.stage in ("code_parts", "all"):
+        ops.code_parts(sb, parts, 12, impl=impl)
+    if a.stage in ("spread_codes", "all"):
+        ops.spread_codes(codes, 100, 2, 2)
+    if a.stage in ("detect", "all"):
+        ops.detect(fb, bank, impl=impl)
+    ev[1].record()
+    torch.cuda.synchronize()
+    print("%s iter %d: %.3f ms" % (a.stage, it, ev[0].elapsed_time(ev[1])))
