@@ -84,7 +84,8 @@ __global__ void prepare_parts_kernel(const double* __restrict__ lp, const double
         double c = 0.0;
         if (n < L.K)
             for (int i = 0; i < L.nq * E; ++i) c += lip[(size_t)n * L.nq * E + i];
-        reinterpret_cast<float*>(blob + L.off_c)[n] = (float)c;
+        // padded columns (count / mask / zero columns) get -inf: they can never win the arg-max
+        reinterpret_cast<float*>(blob + L.off_c)[n] = n < L.K ? (float)c : -INFINITY;
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         unsigned long long m = 0;
@@ -331,6 +332,7 @@ __global__ void __launch_bounds__(CP_THREADS, 1) code_parts_tc_kernel(CodeArgs A
         // ================================ epilogue ================================
         mbar_wait(w_bar, 0);   // c[] lives in the same bulk transaction
         const int e = threadIdx.x;   // TMEM lane == tile row
+        const int ccol = L.K & ~7;   // 16-column window holding the count (K) and mask-count (K+1) columns
         uint32_t it = 0;
         for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
             const int acc = it & 1;
@@ -340,41 +342,66 @@ __global__ void __launch_bounds__(CP_THREADS, 1) code_parts_tc_kernel(CodeArgs A
             const int t = p / A.F, f = p - t * A.F;
             const bool valid = t < A.To && f < A.Fo;
             const size_t loc = ((size_t)b * A.To + t) * A.Fo + f;
-            float* srow = (A.scores && valid) ? A.scores + loc * L.K : nullptr;
             mbar_wait(&tfull_bar[acc], aph);
             tc_fence_after();
             const uint32_t taddr = tmem_base + acc * 256 + ((uint32_t)(warp * 32) << 16);
-            float best = -INFINITY;
-            int bestk = 0;
-            float fcount = 0.f, fmcount = 0.f;
-            for (int n0 = 0; n0 < L.npad; n0 += 32) {
-                uint32_t v[32];
-                if (n0 + 16 < L.npad) {
-                    tmem_ld32(taddr + n0, v);
-                } else {
-                    uint32_t h[16];
-                    tmem_ld16(taddr + n0, h);
+            // four independent running (max, argmax) chains over columns n = 4j + c; padded columns carry
+            // c = -inf.  Strict '>' within a chain keeps the lowest index; the merge breaks ties by index.
+            float bv[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+            int bk[4] = {0, 1, 2, 3};
+            for (int n0 = 0; n0 < L.npad; n0 += 16) {
+                uint32_t v[16];
+                tmem_ld16(taddr + n0, v);
+                float4 c4[4];
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) { v[i] = h[i]; v[16 + i] = 0u; }
-                }
+                for (int j = 0; j < 4; ++j) c4[j] = *reinterpret_cast<const float4*>(cs + n0 + 4 * j);
                 tmem_ld_wait();
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const int n = n0 + i;
-                    const float x = __uint_as_float(v[i]);
-                    if (n < L.K) {
-                        const float sc = x + cs[n];
-                        if (sc > best) { best = sc; bestk = n; }
-                        if (srow) srow[n] = sc;
-                    } else if (n == L.K) {
-                        fcount = x;
-                    } else if (n == L.K + 1) {
-                        fmcount = x;
+                for (int j = 0; j < 4; ++j) {
+                    const float s0 = __uint_as_float(v[4 * j + 0]) + c4[j].x;
+                    const float s1 = __uint_as_float(v[4 * j + 1]) + c4[j].y;
+                    const float s2 = __uint_as_float(v[4 * j + 2]) + c4[j].z;
+                    const float s3 = __uint_as_float(v[4 * j + 3]) + c4[j].w;
+                    const int n = n0 + 4 * j;
+                    if (s0 > bv[0]) { bv[0] = s0; bk[0] = n; }
+                    if (s1 > bv[1]) { bv[1] = s1; bk[1] = n + 1; }
+                    if (s2 > bv[2]) { bv[2] = s2; bk[2] = n + 2; }
+                    if (s3 > bv[3]) { bv[3] = s3; bk[3] = n + 3; }
+                }
+                if (A.scores) {   // drop-in path only: full score map (uniform branch)
+                    if (valid) {
+                        float* srow = A.scores + loc * L.K;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const int n = n0 + 4 * j;
+                            if (n + 0 < L.K) srow[n + 0] = __uint_as_float(v[4 * j + 0]) + c4[j].x;
+                            if (n + 1 < L.K) srow[n + 1] = __uint_as_float(v[4 * j + 1]) + c4[j].y;
+                            if (n + 2 < L.K) srow[n + 2] = __uint_as_float(v[4 * j + 2]) + c4[j].z;
+                            if (n + 3 < L.K) srow[n + 3] = __uint_as_float(v[4 * j + 3]) + c4[j].w;
+                        }
                     }
+                }
+            }
+            // exact integer edge counts from the all-ones / mask weight columns
+            float fcount = 0.f, fmcount = 0.f;
+            {
+                uint32_t v[16];
+                tmem_ld16(taddr + ccol, v);
+                tmem_ld_wait();
+                const int o = L.K - ccol;
+#pragma unroll
+                for (int i = 0; i < 9; ++i) {
+                    if (i == o) fcount = __uint_as_float(v[i]);
+                    if (i == o + 1) fmcount = __uint_as_float(v[i]);
                 }
             }
             tc_fence_before();
             mbar_arrive(&tempty_bar[acc]);
+            float best = bv[0];
+            int bestk = bk[0];
+#pragma unroll
+            for (int c = 1; c < 4; ++c)
+                if (bv[c] > best || (bv[c] == best && bk[c] < bestk)) { best = bv[c]; bestk = bk[c]; }
             if (valid) {
                 const int count = (int)(fcount + 0.5f), mcount = (int)(fmcount + 0.5f);
                 const bool gate = count >= A.threshold && (A.mask_threshold < 0 || mcount > A.mask_threshold);

@@ -75,10 +75,11 @@ __global__ void __launch_bounds__(256) spread_edges_kernel(const uint8_t* __rest
 
 // ================================================================================= K1b
 // codes uint8 [B][To][Fo] -> featbits uint32 [B][To][rowwords], feature j*K + (p-1).
-// CTA = (b, tile of RT output rows).  Three smem phases per output row, no atomics:
-//   colset[j][kw] = OR_{|x0-i|<=r0} onehot(code[x0][j])      (time direction)
-//   wset[j][kw]   = OR_{|x1-j|<=r1} colset[x1][kw]            (frequency direction)
-//   word w of the packed row gathers the K-bit sets that overlap features [32w, 32w+32).
+// CTA = (b, tile of RT output rows); three tile-wide smem phases, no atomics:
+//   colset[r][j][:] = OR_{|x0-i|<=r0} onehot(code[x0][j])      (time direction, Kw words per cell)
+//   wset[r][j][:]   = OR_{|x1-j|<=r1} colset[r][x1][:]          (frequency direction)
+//   word w of packed row r gathers the K-bit sets overlapping features [32w, 32w+32).
+#define TSR_SC_MAX_KW 8
 __global__ void __launch_bounds__(256) spread_codes_kernel(const uint8_t* __restrict__ codes,
                                                            uint32_t* __restrict__ featbits, int To, int Fo, int K,
                                                            int r0, int r1, int rowwords, int RT) {
@@ -87,59 +88,84 @@ __global__ void __launch_bounds__(256) spread_codes_kernel(const uint8_t* __rest
     const int b = blockIdx.y;
     const int i0 = blockIdx.x * RT;
     const int rows_in = RT + 2 * r0;
-    uint8_t* scode = smem;                                               // [rows_in][Fo]
-    uint32_t* colset = reinterpret_cast<uint32_t*>(smem + ((rows_in * Fo + 15) & ~15));  // [Fo][Kw]
-    uint32_t* wset = colset + Fo * Kw;                                   // [Fo+1][Kw] (+1 zero row)
+    const int nrow = min(RT, To - i0);
+    uint8_t* scode = smem;                                                                 // [rows_in][Fo]
+    uint32_t* colset = reinterpret_cast<uint32_t*>(smem + ((rows_in * Fo + 15) & ~15));    // [RT][Fo][Kw]
+    uint32_t* wset = colset + RT * Fo * Kw;                                                // [RT][Fo][Kw]
+    int2* wtab = reinterpret_cast<int2*>(wset + RT * Fo * Kw);                             // [rowwords] (j, o) of bit 32w
 
     for (int i = threadIdx.x; i < rows_in * Fo; i += blockDim.x) {
         int r = i / Fo, j = i - r * Fo;
         int x0 = i0 - r0 + r;
         scode[i] = (x0 >= 0 && x0 < To) ? codes[((size_t)b * To + x0) * Fo + j] : 0;
     }
-    for (int i = threadIdx.x; i < Kw; i += blockDim.x) wset[Fo * Kw + i] = 0;
+    for (int w = threadIdx.x; w < rowwords; w += blockDim.x) {
+        int d = 32 * w;
+        wtab[w] = make_int2(d / K, d % K);
+    }
     __syncthreads();
 
+    // phase 1: one thread per (row, j) builds the Kw-word set of the 2*r0+1 codes above/below
+    for (int q = threadIdx.x; q < nrow * Fo; q += blockDim.x) {
+        int r = q / Fo, j = q - r * Fo;
+        uint32_t s[TSR_SC_MAX_KW];
+#pragma unroll
+        for (int kw = 0; kw < TSR_SC_MAX_KW; ++kw) s[kw] = 0;
+        for (int a = 0; a <= 2 * r0; ++a) {
+            int p = scode[(r + a) * Fo + j];
+            if (p > 0) {
+                uint32_t bit = 1u << ((p - 1) & 31);
+                int kwp = (p - 1) >> 5;
+#pragma unroll
+                for (int kw = 0; kw < TSR_SC_MAX_KW; ++kw)
+                    if (kw == kwp) s[kw] |= bit;
+            }
+        }
+#pragma unroll
+        for (int kw = 0; kw < TSR_SC_MAX_KW; ++kw)
+            if (kw < Kw) colset[q * Kw + kw] = s[kw];
+    }
+    __syncthreads();
+    // phase 2: OR along frequency
+    for (int q = threadIdx.x; q < nrow * Fo; q += blockDim.x) {
+        int r = q / Fo, j = q - r * Fo;
+        int lo = max(0, j - r1), hi = min(Fo - 1, j + r1);
+        uint32_t s[TSR_SC_MAX_KW];
+#pragma unroll
+        for (int kw = 0; kw < TSR_SC_MAX_KW; ++kw) s[kw] = 0;
+        for (int x1 = lo; x1 <= hi; ++x1) {
+            const uint32_t* c = colset + (r * Fo + x1) * Kw;
+#pragma unroll
+            for (int kw = 0; kw < TSR_SC_MAX_KW; ++kw)
+                if (kw < Kw) s[kw] |= c[kw];
+        }
+#pragma unroll
+        for (int kw = 0; kw < TSR_SC_MAX_KW; ++kw)
+            if (kw < Kw) wset[q * Kw + kw] = s[kw];
+    }
+    __syncthreads();
+    // phase 3: gather into tightly packed rows, coalesced 32-bit stores
     const int D = Fo * K;
-    for (int r = 0; r < RT; ++r) {
-        const int i = i0 + r;
-        if (i >= To) break;
-        for (int q = threadIdx.x; q < Fo * Kw; q += blockDim.x) {
-            int j = q / Kw, kw = q - j * Kw;
-            uint32_t s = 0;
-            for (int a = 0; a <= 2 * r0; ++a) {
-                int p = scode[(r + a) * Fo + j];
-                if (p > 0 && ((p - 1) >> 5) == kw) s |= 1u << ((p - 1) & 31);
-            }
-            colset[q] = s;
+    for (int q = threadIdx.x; q < nrow * rowwords; q += blockDim.x) {
+        int r = q / rowwords, w = q - r * rowwords;
+        uint32_t word = 0;
+        int d = 32 * w;
+        const int dend = min(32 * w + 32, D);
+        int2 jo = wtab[w];
+        int j = jo.x, o = jo.y;
+        while (d < dend) {
+            int n = min(K - o, dend - d);
+            const uint32_t* sp = wset + (r * Fo + j) * Kw;
+            uint32_t lo32 = sp[o >> 5];
+            uint32_t hi32 = ((o >> 5) + 1 < Kw) ? sp[(o >> 5) + 1] : 0u;
+            uint32_t chunk = __funnelshift_r(lo32, hi32, o & 31);
+            if (n < 32) chunk &= (1u << n) - 1u;
+            word |= chunk << (d - 32 * w);
+            d += n;
+            o += n;
+            if (o >= K) { o = 0; ++j; }
         }
-        __syncthreads();
-        for (int q = threadIdx.x; q < Fo * Kw; q += blockDim.x) {
-            int j = q / Kw, kw = q - j * Kw;
-            uint32_t s = 0;
-            int lo = max(0, j - r1), hi = min(Fo - 1, j + r1);
-            for (int x1 = lo; x1 <= hi; ++x1) s |= colset[x1 * Kw + kw];
-            wset[q] = s;
-        }
-        __syncthreads();
-        uint32_t* dst = featbits + ((size_t)b * To + i) * rowwords;
-        for (int w = threadIdx.x; w < rowwords; w += blockDim.x) {
-            uint32_t word = 0;
-            int d = 32 * w;
-            const int dend = min(32 * w + 32, D);
-            while (d < dend) {
-                int j = d / K, o = d - j * K;
-                int n = min(K - o, dend - d);
-                const uint32_t* s = wset + j * Kw;
-                uint32_t lo32 = s[o >> 5];
-                uint32_t hi32 = ((o >> 5) + 1 < Kw) ? s[(o >> 5) + 1] : 0u;
-                uint32_t chunk = __funnelshift_r(lo32, hi32, o & 31);
-                if (n < 32) chunk &= (1u << n) - 1u;
-                word |= chunk << (d - 32 * w);
-                d += n;
-            }
-            dst[w] = word;
-        }
-        __syncthreads();
+        featbits[((size_t)b * To + i0 + r) * rowwords + w] = word;
     }
 }
 
@@ -293,8 +319,9 @@ int tsr_spread_codes(const uint8_t* codes, uint32_t* featbits, int B, int To, in
     if (rc) return rc;
     const int Kw = (K + 31) >> 5;
     int RT = 37;
+    while (RT > 1 && (size_t)2 * RT * Fo * Kw * 4 > 44 * 1024) RT = (RT + 1) / 2;
     if (RT > To) RT = To;
-    size_t smem = (((size_t)(RT + 2 * r0) * Fo + 15) & ~(size_t)15) + (size_t)(2 * Fo + 1) * Kw * 4;
+    size_t smem = (((size_t)(RT + 2 * r0) * Fo + 15) & ~(size_t)15) + (size_t)2 * RT * Fo * Kw * 4 + (size_t)rowwords * 8;
     TSR_REQUIRE(smem <= 200 * 1024, "tsr_spread_codes: tile does not fit shared memory");
     if (smem > 48 * 1024)
         TSR_CUDA(cudaFuncSetAttribute(spread_codes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
