@@ -189,7 +189,7 @@ __global__ void __launch_bounds__(256) code_parts_simt_kernel(CodeArgs A) {
 
 // ------------------------------------------------------------------------- tensor path
 #define CP_NSTAGE 4
-#define CP_THREADS 288   // warps 0-3 epilogue, warp 4 MMA/TMEM, warps 5-8 producers
+#define CP_THREADS 416   // warps 0-3 epilogue (even tiles), 4 MMA/TMEM, 5-8 producers, 9-12 epilogue (odd tiles)
 #define CP_MAX_STEPS 32
 
 struct CodeSmem {   // offsets into dynamic shared memory
@@ -199,11 +199,11 @@ __host__ __device__ inline CodeSmem code_smem_layout(const PartsLayout& L, int F
     CodeSmem S;
     S.w = 0;
     S.c = (uint32_t)(2 * L.nsteps * L.npad * 32);
-    S.a = (S.c + L.npad * 4 + 127) & ~127u;
+    S.a = (S.c + (L.npad + 32) * 4 + 127) & ~127u;   // c[] padded with 32 x -inf for the 32-column loads
     S.npos = 128 + (L.ph - 1) * F + (L.pw - 1) + 2;
     S.stage_bytes = (S.npos * 16 + 127) & ~127u;
     S.bars = S.a + CP_NSTAGE * S.stage_bytes;
-    S.total = S.bars + 128 + 3 * CP_MAX_STEPS * 8;   // barriers | A descriptors | B descriptors (2 planes)
+    S.total = S.bars + 128;
     return S;
 }
 
@@ -217,8 +217,6 @@ __global__ void __launch_bounds__(CP_THREADS, 1) code_parts_tc_kernel(CodeArgs A
     uint64_t* tempty_bar = tfull_bar + 2;                                  // [2]
     uint64_t* w_bar = tempty_bar + 2;                                      // [1]
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(w_bar + 1);
-    uint64_t* adesc_rel = reinterpret_cast<uint64_t*>(smem + S.bars + 128);   // [nsteps] relative to the stage base
-    uint64_t* bdesc_abs = adesc_rel + CP_MAX_STEPS;                            // [2][nsteps]
     const float* cs = reinterpret_cast<const float*>(smem + S.c);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -232,19 +230,8 @@ __global__ void __launch_bounds__(CP_THREADS, 1) code_parts_tc_kernel(CodeArgs A
     }
     if (warp == 4) {
         tmem_alloc<512>(tmem_ptr);
-        // descriptor tables: the patch geometry is tile independent, so the issuing thread only adds
-        // the stage base address (>>4) to the low word per MMA
-        const uint32_t wbase = smem_u32(smem + S.w);
-        const uint32_t nb_lbo = L.npad * 16;
-        for (int s = lane; s < L.nsteps; s += 32) {
-            int q0 = 2 * s, q1 = 2 * s + 1;
-            uint32_t off0 = ((q0 / L.pw) * A.F + (q0 % L.pw)) * 16;
-            uint32_t off1 = q1 < L.nq ? ((q1 / L.pw) * A.F + (q1 % L.pw)) * 16 : off0 + 16;
-            adesc_rel[s] = umma_desc_kmajor_noswz(off0, off1 - off0, 128);
-            for (int plane = 0; plane < 2; ++plane)
-                bdesc_abs[plane * L.nsteps + s] = umma_desc_kmajor_noswz(wbase + ((plane * L.nsteps + s) * 2) * nb_lbo, nb_lbo, 128);
-        }
     }
+    if (threadIdx.x < 32) reinterpret_cast<float*>(smem + S.c)[L.npad + threadIdx.x] = -INFINITY;   // tail for 32-wide reads
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -260,7 +247,7 @@ __global__ void __launch_bounds__(CP_THREADS, 1) code_parts_tc_kernel(CodeArgs A
         bulk_g2s(smem + S.c, A.blob + L.off_c, L.npad * 4, w_bar);
     }
 
-    if (warp >= 5) {
+    if (warp >= 5 && warp <= 8) {
         // ================================ producers ================================
         const int pt = threadIdx.x - 160;
         const uint32_t one = fmt_one(fmt);
@@ -306,7 +293,10 @@ __global__ void __launch_bounds__(CP_THREADS, 1) code_parts_tc_kernel(CodeArgs A
         // ================================ MMA issuer ================================
         mbar_wait(w_bar, 0);
         const uint32_t idesc = umma_idesc_f32acc(fmt, 128, L.npad);
-        const int nmma = 2 * L.nsteps;
+        const uint64_t desc_hi = ((uint64_t)(128 >> 4) << 32) | ((uint64_t)1 << 46);        // SBO = 128 B, version 1
+        const uint64_t b_hi = ((uint64_t)L.npad << 16) | desc_hi;                              // LBO = npad*16 B
+        const uint32_t b_lo0 = smem_u32(smem + S.w) >> 4;
+        const uint32_t b_step = 2 * L.npad;                                                    // one K step = 2 k-groups
         uint32_t it = 0;
         for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
             const int stage = it % CP_NSTAGE;
@@ -317,11 +307,27 @@ __global__ void __launch_bounds__(CP_THREADS, 1) code_parts_tc_kernel(CodeArgs A
             mbar_wait(&tempty_bar[acc], aph ^ 1);
             tc_fence_after();
             if (lane == 0) {
-                const uint64_t abase = (uint64_t)(smem_u32(smem + S.a + stage * S.stage_bytes) >> 4);
+                // Descriptors by pure register arithmetic (no table loads on the issue path).  In 16-byte
+                // units a position is 1, so patch group q = (a,b) sits at offset a*F + b from the stage base.
+                const uint32_t a_base = smem_u32(smem + S.a + stage * S.stage_bytes) >> 4;
                 const uint32_t d_tmem = tmem_base + acc * 256;
-                for (int i = 0; i < nmma; ++i) {
-                    const int s = i < L.nsteps ? i : i - L.nsteps;
-                    umma_f16(d_tmem, adesc_rel[s] + abase, bdesc_abs[i], idesc, i > 0);
+                uint32_t b_lo = b_lo0;
+                bool accum = false;
+                for (int plane = 0; plane < 2; ++plane) {
+                    int pa = 0, pb = 0;                       // (a,b) of group q0 = 2s
+                    for (int s = 0; s < L.nsteps; ++s) {
+                        const uint32_t off0 = pa * A.F + pb;
+                        int pb1 = pb + 1, pa1 = pa;
+                        if (pb1 == L.pw) { pb1 = 0; ++pa1; }
+                        const uint32_t off1 = (2 * s + 1 < L.nq) ? pa1 * A.F + pb1 : off0 + 1;
+                        const uint64_t adesc = (uint64_t)(a_base + off0) | ((uint64_t)(off1 - off0) << 16) | desc_hi;
+                        const uint64_t bdesc = (uint64_t)b_lo | b_hi;
+                        umma_f16(d_tmem, adesc, bdesc, idesc, accum);
+                        accum = true;
+                        b_lo += b_step;
+                        pb = pb1 + 1; pa = pa1;
+                        if (pb == L.pw) { pb = 0; ++pa; }
+                    }
                 }
                 umma_commit(&empty_bar[stage]);   // A stage reusable once these MMAs retire
                 umma_commit(&tfull_bar[acc]);     // accumulator ready for the epilogue
@@ -330,12 +336,14 @@ __global__ void __launch_bounds__(CP_THREADS, 1) code_parts_tc_kernel(CodeArgs A
         }
     } else {
         // ================================ epilogue ================================
+        // two warp sets: warps 0-3 drain accumulator 0 (even tiles), warps 9-12 accumulator 1 (odd tiles)
         mbar_wait(w_bar, 0);   // c[] lives in the same bulk transaction
-        const int e = threadIdx.x;   // TMEM lane == tile row
+        const int eset = warp >= 9 ? 1 : 0;
+        const int e = (warp & 3) * 32 + lane;   // TMEM lane == tile row (lane quadrant = warp % 4)
         const int ccol = L.K & ~7;   // 16-column window holding the count (K) and mask-count (K+1) columns
-        uint32_t it = 0;
-        for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-            const int acc = it & 1;
+        uint32_t it = eset;
+        for (long long tile = blockIdx.x + (long long)eset * gridDim.x; tile < ntiles; tile += 2ll * gridDim.x, it += 2) {
+            const int acc = eset;
             const uint32_t aph = (it >> 1) & 1;
             const int b = (int)(tile / tiles_per_utt);
             const int p = (int)(tile % tiles_per_utt) * 128 + e;
@@ -344,42 +352,45 @@ __global__ void __launch_bounds__(CP_THREADS, 1) code_parts_tc_kernel(CodeArgs A
             const size_t loc = ((size_t)b * A.To + t) * A.Fo + f;
             mbar_wait(&tfull_bar[acc], aph);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + acc * 256 + ((uint32_t)(warp * 32) << 16);
+            const uint32_t taddr = tmem_base + acc * 256 + ((uint32_t)((warp & 3) * 32) << 16);
             // four independent running (max, argmax) chains over columns n = 4j + c; padded columns carry
             // c = -inf.  Strict '>' within a chain keeps the lowest index; the merge breaks ties by index.
             float bv[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
             int bk[4] = {0, 1, 2, 3};
-            for (int n0 = 0; n0 < L.npad; n0 += 16) {
-                uint32_t v[16];
-                tmem_ld16(taddr + n0, v);
-                float4 c4[4];
+            auto process32 = [&](const uint32_t (&v)[32], int n0) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) c4[j] = *reinterpret_cast<const float4*>(cs + n0 + 4 * j);
-                tmem_ld_wait();
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const float s0 = __uint_as_float(v[4 * j + 0]) + c4[j].x;
-                    const float s1 = __uint_as_float(v[4 * j + 1]) + c4[j].y;
-                    const float s2 = __uint_as_float(v[4 * j + 2]) + c4[j].z;
-                    const float s3 = __uint_as_float(v[4 * j + 3]) + c4[j].w;
+                for (int j = 0; j < 8; ++j) {
+                    const float4 c4 = *reinterpret_cast<const float4*>(cs + n0 + 4 * j);
+                    const float s0 = __uint_as_float(v[4 * j + 0]) + c4.x;
+                    const float s1 = __uint_as_float(v[4 * j + 1]) + c4.y;
+                    const float s2 = __uint_as_float(v[4 * j + 2]) + c4.z;
+                    const float s3 = __uint_as_float(v[4 * j + 3]) + c4.w;
                     const int n = n0 + 4 * j;
                     if (s0 > bv[0]) { bv[0] = s0; bk[0] = n; }
                     if (s1 > bv[1]) { bv[1] = s1; bk[1] = n + 1; }
                     if (s2 > bv[2]) { bv[2] = s2; bk[2] = n + 2; }
                     if (s3 > bv[3]) { bv[3] = s3; bk[3] = n + 3; }
-                }
-                if (A.scores) {   // drop-in path only: full score map (uniform branch)
-                    if (valid) {
+                    if (A.scores && valid) {   // drop-in path only: full score map
                         float* srow = A.scores + loc * L.K;
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const int n = n0 + 4 * j;
-                            if (n + 0 < L.K) srow[n + 0] = __uint_as_float(v[4 * j + 0]) + c4[j].x;
-                            if (n + 1 < L.K) srow[n + 1] = __uint_as_float(v[4 * j + 1]) + c4[j].y;
-                            if (n + 2 < L.K) srow[n + 2] = __uint_as_float(v[4 * j + 2]) + c4[j].z;
-                            if (n + 3 < L.K) srow[n + 3] = __uint_as_float(v[4 * j + 3]) + c4[j].w;
-                        }
+                        if (n + 0 < L.K) srow[n + 0] = s0;
+                        if (n + 1 < L.K) srow[n + 1] = s1;
+                        if (n + 2 < L.K) srow[n + 2] = s2;
+                        if (n + 3 < L.K) srow[n + 3] = s3;
                     }
+                }
+            };
+            // software-pipelined TMEM reads: the load of the next 32 columns is in flight while the
+            // current 32 are reduced (columns past npad hold stale data; their c is -inf / NaN never wins)
+            uint32_t va[32], vb[32];
+            tmem_ld32(taddr, va);
+            for (int n0 = 0; n0 < L.npad; n0 += 64) {
+                tmem_ld_wait();
+                if (n0 + 32 < L.npad) tmem_ld32(taddr + n0 + 32, vb);
+                process32(va, n0);
+                if (n0 + 32 < L.npad) {
+                    tmem_ld_wait();
+                    if (n0 + 64 < L.npad) tmem_ld32(taddr + n0 + 64, va);
+                    process32(vb, n0 + 32);
                 }
             }
             // exact integer edge counts from the all-ones / mask weight columns
