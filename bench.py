@@ -200,7 +200,9 @@ def run_native(args):
     Tm, bgd = synth.templates(M=M_TEMPL, L=L_TEMPL, Fd=FO, Kd=K_PARTS)
     W, c = synth.linear_filters(Tm, bgd)
     pipe = ScoringPipeline(lp, lip, W, c, edge_threshold=EDGE_THR, part_spread=PART_SPREAD,
-                           edge_spread_radius=EDGE_RADIUS, edge_block_len=EDGE_BLOCK, device=dev)
+                           edge_spread_radius=EDGE_RADIUS, edge_block_len=EDGE_BLOCK, device=dev,
+                           detect_planes={"fp16": ops.PLANES_FP16, "bf16": ops.PLANES_BF16, "int8x2": ops.PLANES_INT8X2,
+                                          "int8x3": ops.PLANES_INT8X3}[args.planes])
     if args.simt:
         pipe.impl_code = pipe.impl_detect = ops.IMPL_SIMT
     X = synth.fast_edge_batch(B, seed=7 + rank)                               # (B,300,40,8) uint8 host
@@ -345,6 +347,8 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--simt", action="store_true", help="use the SIMT cross-check kernels for coding and detection")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--planes", default="int8x3", choices=["fp16", "bf16", "int8x2", "int8x3"],
+                    help="weight-plane format of the detection stage (DESIGN.md section 4)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3 if args.impl == "native" else args.warmup

@@ -52,6 +52,11 @@ extern "C" {
 #define TSR_PLANES_AUTO 0
 #define TSR_PLANES_BF16 1
 #define TSR_PLANES_FP16 2
+/* Detection / EM only: fixed-point filters q = round(w / scale[m]) as 2 or 3 balanced base-256
+ * int8 digit planes, uint8 {0,1} bits, tcgen05 kind::i8 with exact int32 accumulation (twice the
+ * f16 rate).  Falls back to the FP16/BF16 kind when planes * L > 240 columns. */
+#define TSR_PLANES_INT8X2 3
+#define TSR_PLANES_INT8X3 4
 
 int         tsr_abi_version(void);
 const char* tsr_last_error(void);            /* thread-local, valid until the next failing call */
@@ -110,13 +115,14 @@ int tsr_spread_graph(uint32_t* featbits, const uint8_t* graph, long long R, int 
  * 135-176), the per-component loop + np.maximum of get_train_data._compute_detection_E
  * (get_train_data.py:964-992) and detect_float_max's fused max/argmax (:221-278).
  * tsr_prepare_filters: LF float32 [M][L][D] -> blob of 16-bit hi/lo planes (TSR_PLANES_*) in UMMA order. */
-size_t tsr_filter_blob_bytes(int M, int L, int D);
+size_t tsr_filter_blob_bytes(int M, int L, int D, int plane_format);
 int    tsr_prepare_filters(const float* LF, int M, int L, int D, int plane_format, void* blob, void* stream);
 /* featbits [B][T][rowwords].  scores float [B][T][M]: scores[b][t][m] = sum_{tau,d}
  * bit(b,t+tau,d) * LF[m][tau][d] for t <= T-L, 0 for the L-1 tail frames (detect's contract,
  * :157-158).  impl = TSR_IMPL_TENSOR | TSR_IMPL_SIMT (SIMT needs LF_or_null = the fp32 filters). */
 int tsr_detect(const uint32_t* featbits, int B, int T, int D, int rowwords, const void* filter_blob,
-               const float* LF_or_null, int M, int L, float* scores, int impl, void* stream);
+               const float* LF_or_null, int M, int L, int plane_format /* as given to tsr_prepare_filters */,
+               float* scores, int impl, void* stream);
 /* best[b][t] = max_m (scores[b][t][m] + cs[m]), arg = first m attaining it (strict >, :275);
  * tail frames: tail_mode 0 -> best 0, arg 0 (detect_float_max); 1 -> max_m cs[m] with its arg
  * (what get_train_data.py:962-992 produces by adding c to the zero tail). */

@@ -8,7 +8,7 @@ LIB_PATH = os.path.join(HERE, "libtsr_b200.so")
 
 TSR_OK, TSR_ERR_INVALID, TSR_ERR_CUDA, TSR_ERR_UNSUPPORTED = 0, -1, -2, -3
 IMPL_TENSOR, IMPL_SIMT = 0, 1
-PLANES_AUTO, PLANES_BF16, PLANES_FP16 = 0, 1, 2
+PLANES_AUTO, PLANES_BF16, PLANES_FP16, PLANES_INT8X2, PLANES_INT8X3 = 0, 1, 2, 3, 4
 
 _vp, _i, _ll, _sz, _f = ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_size_t, ctypes.c_float
 
@@ -28,9 +28,9 @@ SIGNATURES = {
     "tsr_code_parts": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "tsr_spread_codes": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "tsr_spread_graph": (_i, [_vp, _vp, _ll, _i, _i, _i, _vp]),
-    "tsr_filter_blob_bytes": (_sz, [_i, _i, _i]),
+    "tsr_filter_blob_bytes": (_sz, [_i, _i, _i, _i]),
     "tsr_prepare_filters": (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
-    "tsr_detect": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _vp, _i, _vp]),
+    "tsr_detect": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _i, _vp, _i, _vp]),
     "tsr_detect_reduce": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "tsr_detect_float": (_i, [_vp, _i, _i, _i, _vp, _i, _i, _vp, _vp, _vp]),
     "tsr_em_workspace_bytes": (_sz, [_ll, _i, _i]),

@@ -23,6 +23,7 @@ namespace tsr {
 
 struct PartsLayout {
     int K, ph, pw, npad, nsteps, nq;
+    int concat;   // 1: hi and lo planes side by side along N (one MMA of N = 2*npad per K step); 0: two MMAs
     size_t off_w, off_c, off_wf, off_mask, off_hdr, total;
 };
 
@@ -32,6 +33,7 @@ __host__ __device__ inline PartsLayout parts_layout(int K, int ph, int pw) {
     L.nq = ph * pw;
     L.npad = ((K + 2) + 15) & ~15;
     L.nsteps = (L.nq + 1) / 2;
+    L.concat = 2 * L.npad <= 256 ? 1 : 0;
     L.off_w = 0;
     L.off_c = (size_t)2 * L.nsteps * L.npad * 32;
     L.off_wf = L.off_c + (size_t)L.npad * 4;
@@ -74,9 +76,15 @@ __global__ void prepare_parts_kernel(const double* __restrict__ lp, const double
         }
         uint16_t hi, lo;
         split_hi_lo(w, fmt, hi, lo);
-        size_t o = (((size_t)s * 2 + (e >> 3)) * L.npad + n) * 16 + z * 2;
-        *reinterpret_cast<uint16_t*>(blob + L.off_w + o) = hi;
-        *reinterpret_cast<uint16_t*>(blob + L.off_w + (size_t)L.nsteps * L.npad * 32 + o) = lo;
+        if (L.concat) {   // [step][kgroup][row: hi plane 0..npad-1 | lo plane npad..2npad-1][8]
+            size_t o = (((size_t)s * 2 + (e >> 3)) * (2 * L.npad) + n) * 16 + z * 2;
+            *reinterpret_cast<uint16_t*>(blob + L.off_w + o) = hi;
+            *reinterpret_cast<uint16_t*>(blob + L.off_w + o + (size_t)L.npad * 16) = lo;
+        } else {          // [plane][step][kgroup][row][8]
+            size_t o = (((size_t)s * 2 + (e >> 3)) * L.npad + n) * 16 + z * 2;
+            *reinterpret_cast<uint16_t*>(blob + L.off_w + o) = hi;
+            *reinterpret_cast<uint16_t*>(blob + L.off_w + (size_t)L.nsteps * L.npad * 32 + o) = lo;
+        }
         if (q < L.nq) reinterpret_cast<float*>(blob + L.off_wf)[((size_t)q * 8 + z) * L.npad + n] = (float)w;
     }
     // c[k] = sum lip (float64, reference order), one thread per part
@@ -291,12 +299,32 @@ __global__ void __launch_bounds__(CP_THREADS, 1) code_parts_tc_kernel(CodeArgs A
         }
     } else if (warp == 4) {
         // ================================ MMA issuer ================================
+        // The whole warp runs this loop in lock step; one elected lane issues each tcgen05 op.
+        // Per-step descriptor words are tile independent and live in registers (static unroll):
+        //   A low word = (patch group offset in 16-byte units) | LBO << 16   (+ stage base per tile)
+        //   B low word = plane/step address >> 4 | LBO << 16
         mbar_wait(w_bar, 0);
-        const uint32_t idesc = umma_idesc_f32acc(fmt, 128, L.npad);
-        const uint64_t desc_hi = ((uint64_t)(128 >> 4) << 32) | ((uint64_t)1 << 46);        // SBO = 128 B, version 1
-        const uint64_t b_hi = ((uint64_t)L.npad << 16) | desc_hi;                              // LBO = npad*16 B
-        const uint32_t b_lo0 = smem_u32(smem + S.w) >> 4;
-        const uint32_t b_step = 2 * L.npad;                                                    // one K step = 2 k-groups
+        const int nmma_n = L.concat ? 2 * L.npad : L.npad;                 // N of one MMA
+        const uint32_t idesc = umma_idesc_f32acc(fmt, 128, nmma_n);
+        const uint32_t desc_hi = (uint32_t)(128 >> 4) | (1u << 14);        // SBO = 128 B, version 1 (bits 32..47)
+        uint32_t a_lo[CP_MAX_STEPS], b_lo[2 * CP_MAX_STEPS];
+        {
+            const uint32_t b_base = smem_u32(smem + S.w) >> 4;
+            int pa = 0, pb = 0;
+#pragma unroll
+            for (int s = 0; s < CP_MAX_STEPS; ++s) {
+                const uint32_t off0 = pa * A.F + pb;
+                int pb1 = pb + 1, pa1 = pa;
+                if (pb1 == L.pw) { pb1 = 0; ++pa1; }
+                const uint32_t off1 = (2 * s + 1 < L.nq) ? pa1 * A.F + pb1 : off0 + 1;
+                a_lo[s] = off0 | ((off1 - off0) << 16);
+                b_lo[s] = (b_base + (uint32_t)s * 2 * nmma_n) | ((uint32_t)nmma_n << 16);
+                b_lo[CP_MAX_STEPS + s] = (b_base + (uint32_t)(L.nsteps + s) * 2 * nmma_n) | ((uint32_t)nmma_n << 16);
+                pb = pb1 + 1; pa = pa1;
+                if (pb == L.pw) { pb = 0; ++pa; }
+            }
+        }
+        const int nplane_mma = L.concat ? 1 : 2;
         uint32_t it = 0;
         for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
             const int stage = it % CP_NSTAGE;
@@ -306,33 +334,19 @@ __global__ void __launch_bounds__(CP_THREADS, 1) code_parts_tc_kernel(CodeArgs A
             mbar_wait(&full_bar[stage], ph);
             mbar_wait(&tempty_bar[acc], aph ^ 1);
             tc_fence_after();
-            if (lane == 0) {
-                // Descriptors by pure register arithmetic (no table loads on the issue path).  In 16-byte
-                // units a position is 1, so patch group q = (a,b) sits at offset a*F + b from the stage base.
-                const uint32_t a_base = smem_u32(smem + S.a + stage * S.stage_bytes) >> 4;
-                const uint32_t d_tmem = tmem_base + acc * 256;
-                uint32_t b_lo = b_lo0;
-                bool accum = false;
-                for (int plane = 0; plane < 2; ++plane) {
-                    int pa = 0, pb = 0;                       // (a,b) of group q0 = 2s
-                    for (int s = 0; s < L.nsteps; ++s) {
-                        const uint32_t off0 = pa * A.F + pb;
-                        int pb1 = pb + 1, pa1 = pa;
-                        if (pb1 == L.pw) { pb1 = 0; ++pa1; }
-                        const uint32_t off1 = (2 * s + 1 < L.nq) ? pa1 * A.F + pb1 : off0 + 1;
-                        const uint64_t adesc = (uint64_t)(a_base + off0) | ((uint64_t)(off1 - off0) << 16) | desc_hi;
-                        const uint64_t bdesc = (uint64_t)b_lo | b_hi;
-                        umma_f16(d_tmem, adesc, bdesc, idesc, accum);
-                        accum = true;
-                        b_lo += b_step;
-                        pb = pb1 + 1; pa = pa1;
-                        if (pb == L.pw) { pb = 0; ++pa; }
-                    }
+            const uint32_t a_base = smem_u32(smem + S.a + stage * S.stage_bytes) >> 4;
+            const uint32_t d_tmem = tmem_base + acc * 256;
+#pragma unroll
+            for (int i = 0; i < 2 * CP_MAX_STEPS; ++i) {
+                const int s = i % CP_MAX_STEPS;
+                if (s < L.nsteps && i / CP_MAX_STEPS < nplane_mma) {
+                    const uint64_t adesc = ((uint64_t)desc_hi << 32) | (uint64_t)(a_lo[s] + a_base);
+                    const uint64_t bdesc = ((uint64_t)desc_hi << 32) | (uint64_t)b_lo[i];
+                    umma_f16_elect(d_tmem, adesc, bdesc, idesc, i > 0 ? 1u : 0u);
                 }
-                umma_commit(&empty_bar[stage]);   // A stage reusable once these MMAs retire
-                umma_commit(&tfull_bar[acc]);     // accumulator ready for the epilogue
             }
-            __syncwarp();
+            umma_commit_elect(&empty_bar[stage]);   // A stage reusable once these MMAs retire
+            umma_commit_elect(&tfull_bar[acc]);     // accumulator ready for the epilogue
         }
     } else {
         // ================================ epilogue ================================
@@ -357,14 +371,18 @@ __global__ void __launch_bounds__(CP_THREADS, 1) code_parts_tc_kernel(CodeArgs A
             // c = -inf.  Strict '>' within a chain keeps the lowest index; the merge breaks ties by index.
             float bv[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
             int bk[4] = {0, 1, 2, 3};
-            auto process32 = [&](const uint32_t (&v)[32], int n0) {
+            // score = hi column + lo column (concat layout: lo plane sits npad columns further) + c
+            auto process16 = [&](const uint32_t (&vh)[16], const uint32_t (&vl)[16], int n0) {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
+                for (int j = 0; j < 4; ++j) {
                     const float4 c4 = *reinterpret_cast<const float4*>(cs + n0 + 4 * j);
-                    const float s0 = __uint_as_float(v[4 * j + 0]) + c4.x;
-                    const float s1 = __uint_as_float(v[4 * j + 1]) + c4.y;
-                    const float s2 = __uint_as_float(v[4 * j + 2]) + c4.z;
-                    const float s3 = __uint_as_float(v[4 * j + 3]) + c4.w;
+                    float s0 = __uint_as_float(vh[4 * j + 0]), s1 = __uint_as_float(vh[4 * j + 1]);
+                    float s2 = __uint_as_float(vh[4 * j + 2]), s3 = __uint_as_float(vh[4 * j + 3]);
+                    if (L.concat) {
+                        s0 += __uint_as_float(vl[4 * j + 0]); s1 += __uint_as_float(vl[4 * j + 1]);
+                        s2 += __uint_as_float(vl[4 * j + 2]); s3 += __uint_as_float(vl[4 * j + 3]);
+                    }
+                    s0 += c4.x; s1 += c4.y; s2 += c4.z; s3 += c4.w;
                     const int n = n0 + 4 * j;
                     if (s0 > bv[0]) { bv[0] = s0; bk[0] = n; }
                     if (s1 > bv[1]) { bv[1] = s1; bk[1] = n + 1; }
@@ -379,18 +397,25 @@ __global__ void __launch_bounds__(CP_THREADS, 1) code_parts_tc_kernel(CodeArgs A
                     }
                 }
             };
-            // software-pipelined TMEM reads: the load of the next 32 columns is in flight while the
-            // current 32 are reduced (columns past npad hold stale data; their c is -inf / NaN never wins)
-            uint32_t va[32], vb[32];
-            tmem_ld32(taddr, va);
-            for (int n0 = 0; n0 < L.npad; n0 += 64) {
+            // software-pipelined TMEM reads: the next 16 columns (of both planes) are in flight while the
+            // current 16 are reduced
+            uint32_t ha[16], la[16], hb[16], lb[16];
+            tmem_ld16(taddr, ha);
+            if (L.concat) tmem_ld16(taddr + L.npad, la);
+            for (int n0 = 0; n0 < L.npad; n0 += 32) {
                 tmem_ld_wait();
-                if (n0 + 32 < L.npad) tmem_ld32(taddr + n0 + 32, vb);
-                process32(va, n0);
-                if (n0 + 32 < L.npad) {
+                if (n0 + 16 < L.npad) {
+                    tmem_ld16(taddr + n0 + 16, hb);
+                    if (L.concat) tmem_ld16(taddr + L.npad + n0 + 16, lb);
+                }
+                process16(ha, la, n0);
+                if (n0 + 16 < L.npad) {
                     tmem_ld_wait();
-                    if (n0 + 64 < L.npad) tmem_ld32(taddr + n0 + 64, va);
-                    process32(vb, n0 + 32);
+                    if (n0 + 32 < L.npad) {
+                        tmem_ld16(taddr + n0 + 32, ha);
+                        if (L.concat) tmem_ld16(taddr + L.npad + n0 + 32, la);
+                    }
+                    process16(hb, lb, n0 + 16);
                 }
             }
             // exact integer edge counts from the all-ones / mask weight columns

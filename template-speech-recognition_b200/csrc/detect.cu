@@ -18,82 +18,138 @@
 //   warp  4     MMA issuer + TMEM allocation
 //   warp  5     filter-tile loader (cp.async.bulk, one 2*NT*128-byte copy per 64-feature chunk)
 //   warps 6-17  frame-bit expanders (one row of the 384-row step each)
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace tsr {
 
 #define DT_MSUB_MAX 3
-#define DT_NSTAGE 2
+#define DT_MAX_STAGES 4
 #define DT_THREADS 576
 #define DT_PRODUCERS 384
 #define DT_TAU_CHUNK 40    // diagonal sums are staged through smem in chunks of <= 40 filter frames
-#define DT_HDR_BYTES 128   // blob header: [0] plane format, [1] max |w| bits
+#define DT_NT_MAX 240      // widest N tile: tcgen05.mma issue costs ~100 cycles, so each MMA should carry >= that much work
 
+// Operand kinds.  F16: hi+lo 16-bit float planes accumulate into the same fp32 TMEM columns.
+// I8: the filters are fixed-point integers q = round(w / scale[m]) split into P balanced base-256
+// digits (int8 planes) that occupy separate column groups; bits are expanded to uint8 {0,1};
+// kind::i8 MMAs (K = 32, twice the f16 rate) accumulate exactly in int32, the diagonal sums stay
+// integer, and the planes are recombined and scaled once per output value.
 struct FilterLayout {
     int M, L, D, rowwords, nchunks;
-    int tpt;      // templates per N tile
-    int NT;       // N tile = roundup16(tpt*L)
-    int ntiles;   // ceil(M / tpt)
+    int kind;     // 0 = F16 planes, 1 = I8 planes
+    int P;        // planes (2 for F16; 2 or 3 for I8)
+    int vpt;      // column groups per template: P for I8, 1 for F16
+    int tptv;     // column groups ("virtual templates") per N tile, a multiple of vpt
+    int NT;       // N tile = roundup16(tptv*L)
+    int ntiles;   // ceil(M*vpt / tptv)
     int msub;     // 128-row accumulators per step (msub*NT <= 512)
-    size_t tile_bytes;   // one (ntile, chunk): 2 planes * NT rows * 128 B
+    int nstage;   // smem pipeline depth
+    size_t tile_bytes;   // one (ntile, chunk) filter tile
+    size_t hdr_bytes;    // [0] plane format, [1] max|w| bits, then float scale[M] (I8)
     size_t total;
 };
 
-__host__ __device__ inline FilterLayout filter_layout(int M, int L, int D) {
+__host__ __device__ inline FilterLayout filter_layout(int M, int L, int D, int planes) {
     FilterLayout f;
     f.M = M; f.L = L; f.D = D;
     f.rowwords = ((D + 63) / 64) * 2;
     f.nchunks = f.rowwords / 2;
-    int tpt = 160 / L;
-    if (tpt < 1) tpt = 1;
-    if (tpt > M) tpt = M;
-    f.tpt = tpt;
-    f.NT = (tpt * L + 15) & ~15;
-    f.ntiles = (M + tpt - 1) / tpt;
+    f.kind = (planes == TSR_PLANES_INT8X2 || planes == TSR_PLANES_INT8X3) ? 1 : 0;
+    f.P = planes == TSR_PLANES_INT8X3 ? 3 : 2;
+    if (f.kind == 1 && f.P * L > DT_NT_MAX) { f.kind = 0; f.P = 2; }   // planes of a template must share a tile
+    f.vpt = f.kind ? f.P : 1;
+    int tptv = (DT_NT_MAX / (f.vpt * L)) * f.vpt;
+    if (tptv < f.vpt) tptv = f.vpt;
+    if (tptv > M * f.vpt) tptv = M * f.vpt;
+    f.tptv = tptv;
+    f.NT = (tptv * L + 15) & ~15;
+    f.ntiles = (M * f.vpt + tptv - 1) / tptv;
     int msub = 512 / f.NT;
     f.msub = msub > DT_MSUB_MAX ? DT_MSUB_MAX : msub;
-    f.tile_bytes = (size_t)2 * f.NT * 128;
-    f.total = DT_HDR_BYTES + (size_t)f.ntiles * f.nchunks * f.tile_bytes;
+    f.tile_bytes = f.kind ? (size_t)f.NT * 64 : (size_t)2 * f.NT * 128;
+    f.hdr_bytes = 128 + (((size_t)M * 4 + 127) & ~(size_t)127);
+    f.total = f.hdr_bytes + (size_t)f.ntiles * f.nchunks * f.tile_bytes;
+    size_t stage = (size_t)f.msub * (f.kind ? 8192 : 16384) + f.tile_bytes;
+    int ns = (int)((160 * 1024) / stage);
+    f.nstage = ns < 2 ? 2 : (ns > DT_MAX_STAGES ? DT_MAX_STAGES : ns);
     return f;
 }
 
-__global__ void filters_maxabs_kernel(const float* __restrict__ LF, size_t n, uint8_t* __restrict__ blob) {
+// per-template max |w| (I8 scales) and the global max (F16 format choice)
+__global__ void filters_maxabs_kernel(const float* __restrict__ LF, int M, size_t per_template, uint8_t* __restrict__ blob) {
     uint32_t* hdr = reinterpret_cast<uint32_t*>(blob);
-    uint32_t m = 0;
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
-        m = max(m, __float_as_uint(fabsf(LF[i])));
-    for (int off = 16; off > 0; off >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, off));
-    if ((threadIdx.x & 31) == 0) atomicMax(&hdr[1], m);
+    uint32_t* tmax = hdr + 32;   // scale slots double as max|w| bit patterns until published
+    const int m = blockIdx.y;
+    const float* w = LF + (size_t)m * per_template;
+    uint32_t mx = 0;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < per_template; i += (size_t)gridDim.x * blockDim.x)
+        mx = max(mx, __float_as_uint(fabsf(w[i])));
+    for (int off = 16; off > 0; off >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+    if ((threadIdx.x & 31) == 0) { atomicMax(&tmax[m], mx); atomicMax(&hdr[1], mx); }
 }
-__global__ void filters_publish_format_kernel(uint8_t* __restrict__ blob, int plane_format) {
+__global__ void filters_publish_kernel(uint8_t* __restrict__ blob, int plane_format, FilterLayout f) {
     uint32_t* hdr = reinterpret_cast<uint32_t*>(blob);
-    hdr[0] = pick_format(hdr[1], plane_format);
+    if (threadIdx.x == 0 && blockIdx.x == 0)
+        hdr[0] = f.kind ? (uint32_t)(100 + f.P) : pick_format(hdr[1], plane_format == TSR_PLANES_BF16 ? 1 : (plane_format == TSR_PLANES_FP16 ? 2 : 0));
+    if (f.kind) {   // turn max|w| into the quantisation step of each template
+        const float qmax = f.P == 3 ? 8355711.f : 32639.f;   // largest value of P balanced base-256 digits
+        float* scale = reinterpret_cast<float*>(hdr + 32);
+        for (int m = blockIdx.x * blockDim.x + threadIdx.x; m < f.M; m += gridDim.x * blockDim.x) {
+            float mx = __uint_as_float(reinterpret_cast<uint32_t*>(scale)[m]);
+            scale[m] = mx > 0.f ? mx / qmax : 1.f;
+        }
+    }
 }
 
-// One thread per 16-bit element of a plane.  Element (ntile, chunk, plane, kgroup, row n, e).
+// One thread per weight element of a (tile, chunk): column n = (group v, frame tau), v = m*vpt + plane.
 __global__ void prepare_filters_kernel(const float* __restrict__ LF, uint8_t* __restrict__ blob, FilterLayout f,
                                        int plane_format) {
-    const uint32_t fmt = pick_format(reinterpret_cast<const uint32_t*>(blob)[1], plane_format);
-    blob += DT_HDR_BYTES;
-    const size_t nelem = (size_t)f.ntiles * f.nchunks * f.NT * 64;   // per plane
+    const uint32_t* hdr = reinterpret_cast<const uint32_t*>(blob);
+    const uint32_t fmt = pick_format(hdr[1], plane_format == TSR_PLANES_BF16 ? 1 : (plane_format == TSR_PLANES_FP16 ? 2 : 0));
+    const uint32_t* tmaxbits = hdr + 32;
+    uint8_t* tiles = blob + f.hdr_bytes;
+    const size_t nelem = (size_t)f.ntiles * f.nchunks * f.NT * 64;
+    const float qmax = f.P == 3 ? 8355711.f : 32639.f;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < nelem; i += (size_t)gridDim.x * blockDim.x) {
-        int e = (int)(i & 7);
-        size_t r = i >> 3;
-        int n = (int)(r % f.NT); r /= f.NT;
-        int kg = (int)(r & 7); r >>= 3;
-        int c = (int)(r % f.nchunks);
-        int nt = (int)(r / f.nchunks);
-        int d = c * 64 + kg * 8 + e;
-        int ml = n / f.L, tau = n - ml * f.L;
-        int m = nt * f.tpt + ml;
+        const int dd = (int)(i & 63);                 // feature within the chunk
+        size_t r = i >> 6;
+        const int n = (int)(r % f.NT); r /= f.NT;
+        const int c = (int)(r % f.nchunks);
+        const int nt = (int)(r / f.nchunks);
+        const int d = c * 64 + dd;
+        const int vl = n / f.L, tau = n - vl * f.L;
+        const int v = nt * f.tptv + vl;
+        const int m = v / f.vpt, plane = v - m * f.vpt;
         float w = 0.f;
-        if (ml < f.tpt && m < f.M && d < f.D) w = LF[((size_t)m * f.L + tau) * f.D + d];
-        uint16_t hi, lo;
-        split_hi_lo((double)w, fmt, hi, lo);
-        size_t base = ((size_t)nt * f.nchunks + c) * f.tile_bytes;
-        size_t o = ((size_t)kg * f.NT + n) * 16 + e * 2;
-        *reinterpret_cast<uint16_t*>(blob + base + o) = hi;
-        *reinterpret_cast<uint16_t*>(blob + base + (size_t)f.NT * 128 + o) = lo;
+        const bool live = vl < f.tptv && m < f.M && d < f.D;
+        if (live) w = LF[((size_t)m * f.L + tau) * f.D + d];
+        uint8_t* tile = tiles + ((size_t)nt * f.nchunks + c) * f.tile_bytes;
+        if (f.kind) {
+            int q = 0;
+            if (live) {
+                const float mx = __uint_as_float(tmaxbits[m]);
+                const float sc = mx > 0.f ? mx / qmax : 1.f;
+                float qf = rintf(w / sc);
+                qf = fminf(fmaxf(qf, -qmax), qmax);
+                q = (int)qf;
+            }
+            int digit = 0;
+            for (int pl = 0; pl <= plane; ++pl) {      // balanced base-256 digits, least significant first
+                digit = ((q + 128) & 255) - 128;
+                q = (q - digit) >> 8;
+            }
+            const int kg = dd >> 4, e = dd & 15;
+            tile[((size_t)kg * f.NT + n) * 16 + e] = (uint8_t)(int8_t)digit;
+        } else {
+            uint16_t hi, lo;
+            split_hi_lo((double)w, fmt, hi, lo);
+            const int kg = dd >> 3, e = dd & 7;
+            const size_t o = ((size_t)kg * f.NT + n) * 16 + e * 2;
+            *reinterpret_cast<uint16_t*>(tile + o) = hi;
+            *reinterpret_cast<uint16_t*>(tile + (size_t)f.NT * 128 + o) = lo;
+        }
     }
 }
 
@@ -110,39 +166,60 @@ struct DetectArgs {
 };
 
 struct DetectSmem {
-    uint32_t a, b, stage, outacc, bars, stage_bytes, a_bytes, total;
+    uint32_t b, stage, outacc, bars, stage_bytes, a_bytes, a_sub, total;
 };
 __host__ __device__ inline DetectSmem detect_smem_layout(const FilterLayout& f) {
     DetectSmem S;
-    S.a_bytes = f.msub * 16384;
+    S.a_sub = f.kind ? 8192 : 16384;
+    S.a_bytes = f.msub * S.a_sub;
     S.stage_bytes = S.a_bytes + (uint32_t)f.tile_bytes;
-    S.a = 0;
     S.b = S.a_bytes;                                   // within a stage
-    S.stage = DT_NSTAGE * S.stage_bytes;               // epilogue staging [128][L+1] floats
+    S.stage = f.nstage * S.stage_bytes;                // epilogue staging [128][TC+1] words
     S.outacc = S.stage + ((128 * ((f.L < DT_TAU_CHUNK ? f.L : DT_TAU_CHUNK) + 1) * 4 + 127) & ~127u);
-    S.bars = S.outacc + (((f.msub * 128 + f.L) * f.tpt * 4 + 127) & ~127u);
-    S.total = S.bars + 128;
+    S.bars = S.outacc + (((f.msub * 128 + f.L) * f.tptv * 4 + 127) & ~127u);
+    S.total = S.bars + 256;
     return S;
 }
 
+// 16 bits -> 16 bytes in {0,1} (uint8 A operand of the I8 path)
+__device__ __forceinline__ uint4 expand16_u8(uint32_t b) {
+    uint4 r;
+    r.x = ((b & 0xFu) * 0x00204081u) & 0x01010101u;
+    r.y = (((b >> 4) & 0xFu) * 0x00204081u) & 0x01010101u;
+    r.z = (((b >> 8) & 0xFu) * 0x00204081u) & 0x01010101u;
+    r.w = (((b >> 12) & 0xFu) * 0x00204081u) & 0x01010101u;
+    return r;
+}
+__device__ __forceinline__ void umma_i8_elect(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                              uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+template <bool I8>
 __global__ void __launch_bounds__(DT_THREADS, 1) detect_tc_kernel(DetectArgs A) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const FilterLayout& f = A.f;
     const DetectSmem S = detect_smem_layout(f);
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S.bars);   // [DT_NSTAGE]
-    uint64_t* empty_bar = full_bar + DT_NSTAGE;                        // [DT_NSTAGE]
-    uint64_t* tfull_bar = empty_bar + DT_NSTAGE;                       // [1]
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S.bars);   // [DT_MAX_STAGES]
+    uint64_t* empty_bar = full_bar + DT_MAX_STAGES;                    // [DT_MAX_STAGES]
+    uint64_t* tfull_bar = empty_bar + DT_MAX_STAGES;                   // [1]
     uint64_t* tempty_bar = tfull_bar + 1;                              // [DT_MSUB_MAX]
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty_bar + DT_MSUB_MAX);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t fmt = reinterpret_cast<const uint32_t*>(A.blob)[0];
-    const int L = f.L, NT = f.NT, msub = f.msub, nchunks = f.nchunks, tpt = f.tpt;
+    const int L = f.L, NT = f.NT, msub = f.msub, nchunks = f.nchunks, tptv = f.tptv, nstage = f.nstage;
     const int step_rows = msub * 128;
     const long long nunits = (long long)f.ntiles * A.units_per_ntile;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < DT_NSTAGE; ++s) { mbar_init(&full_bar[s], DT_PRODUCERS + 1); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < DT_MAX_STAGES; ++s) { mbar_init(&full_bar[s], DT_PRODUCERS + 1); mbar_init(&empty_bar[s], 1); }
         mbar_init(tfull_bar, 1);
         for (int s = 0; s < DT_MSUB_MAX; ++s) mbar_init(&tempty_bar[s], 128);
         mbar_fence_init();
@@ -159,6 +236,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) detect_tc_kernel(DetectArgs A) 
         const int sub = pr >> 7, r = pr & 127;
         const uint32_t one = fmt_one(fmt);
         uint32_t it = 0;                               // global chunk counter (pipeline position)
+        int stage = 0; uint32_t ph = 0;
         for (long long u = blockIdx.x; u < nunits; u += gridDim.x) {
             const long long ur = u / f.ntiles;
             const long long o0 = ur * A.rows_per_unit;
@@ -168,112 +246,133 @@ __global__ void __launch_bounds__(DT_THREADS, 1) detect_tc_kernel(DetectArgs A) 
                 const long long g = o0 + (long long)step * step_rows + pr;
                 const bool live = pr < step_rows && g < in_end;
                 const uint2* src = reinterpret_cast<const uint2*>(A.bits + (live ? g : 0) * f.rowwords);
+                uint2 w = live ? __ldg(src) : make_uint2(0u, 0u);
                 for (int c = 0; c < nchunks; ++c, ++it) {
-                    const int stage = it % DT_NSTAGE;
-                    const uint32_t ph = (it / DT_NSTAGE) & 1;
-                    uint2 w = live ? __ldg(src + c) : make_uint2(0u, 0u);
+                    uint2 wn = (live && c + 1 < nchunks) ? __ldg(src + c + 1) : make_uint2(0u, 0u);   // prefetch
                     mbar_wait(&empty_bar[stage], ph ^ 1);
                     if (pr < step_rows) {
-                        uint8_t* dst = smem + stage * S.stage_bytes + sub * 16384 + r * 16;
+                        uint8_t* dst = smem + stage * S.stage_bytes + sub * S.a_sub + r * 16;
+                        if (I8) {
+                            *reinterpret_cast<uint4*>(dst) = expand16_u8(w.x & 0xFFFF);
+                            *reinterpret_cast<uint4*>(dst + 2048) = expand16_u8(w.x >> 16);
+                            *reinterpret_cast<uint4*>(dst + 4096) = expand16_u8(w.y & 0xFFFF);
+                            *reinterpret_cast<uint4*>(dst + 6144) = expand16_u8(w.y >> 16);
+                        } else {
 #pragma unroll
-                        for (int kg = 0; kg < 4; ++kg)
-                            *reinterpret_cast<uint4*>(dst + kg * 2048) = expand_byte((w.x >> (8 * kg)) & 0xFF, one);
+                            for (int kg = 0; kg < 4; ++kg)
+                                *reinterpret_cast<uint4*>(dst + kg * 2048) = expand_byte((w.x >> (8 * kg)) & 0xFF, one);
 #pragma unroll
-                        for (int kg = 0; kg < 4; ++kg)
-                            *reinterpret_cast<uint4*>(dst + (kg + 4) * 2048) = expand_byte((w.y >> (8 * kg)) & 0xFF, one);
+                            for (int kg = 0; kg < 4; ++kg)
+                                *reinterpret_cast<uint4*>(dst + (kg + 4) * 2048) = expand_byte((w.y >> (8 * kg)) & 0xFF, one);
+                        }
                     }
                     fence_proxy_async_smem();
                     mbar_arrive(&full_bar[stage]);
+                    w = wn;
+                    if (++stage == nstage) { stage = 0; ph ^= 1; }
                 }
             }
         }
     } else if (warp == 5) {
         // ============================ filter-tile loader ============================
         if (lane == 0) {
-            uint32_t it = 0;
+            int stage = 0; uint32_t ph = 0;
             for (long long u = blockIdx.x; u < nunits; u += gridDim.x) {
                 const int nt = (int)(u % f.ntiles);
-                const uint8_t* src = A.blob + DT_HDR_BYTES + (size_t)nt * nchunks * f.tile_bytes;
+                const uint8_t* src = A.blob + f.hdr_bytes + (size_t)nt * nchunks * f.tile_bytes;
                 for (int step = 0; step < A.steps_per_unit; ++step)
-                    for (int c = 0; c < nchunks; ++c, ++it) {
-                        const int stage = it % DT_NSTAGE;
-                        const uint32_t ph = (it / DT_NSTAGE) & 1;
+                    for (int c = 0; c < nchunks; ++c) {
                         mbar_wait(&empty_bar[stage], ph ^ 1);
                         mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)f.tile_bytes);
                         bulk_g2s(smem + stage * S.stage_bytes + S.b, src + (size_t)c * f.tile_bytes, (uint32_t)f.tile_bytes,
                                  &full_bar[stage]);
+                        if (++stage == nstage) { stage = 0; ph ^= 1; }
                     }
             }
         }
     } else if (warp == 4) {
         // ================================ MMA issuer ================================
-        const uint32_t idesc = umma_idesc_f32acc(fmt, 128, NT);
-        uint32_t it = 0, stepno = 0;
+        // warp-uniform loop, one elected lane issues (see umma_f16_elect)
+        const uint32_t idesc = I8 ? ((2u << 4) | (0u << 7) | (1u << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24))
+                                  : umma_idesc_f32acc(fmt, 128, NT);
+        const uint32_t desc_hi = (uint32_t)(128 >> 4) | (1u << 14);                 // SBO = 128 B, version 1
+        const uint64_t a_hi = ((uint64_t)desc_hi << 32) | ((uint64_t)(2048 >> 4) << 16);   // LBO = 2048 B
+        const uint64_t b_hi = ((uint64_t)desc_hi << 32) | ((uint64_t)NT << 16);            // LBO = NT*16 B
+        int stage = 0; uint32_t ph = 0;
+        uint32_t stepno = 0;
         for (long long u = blockIdx.x; u < nunits; u += gridDim.x)
             for (int step = 0; step < A.steps_per_unit; ++step, ++stepno) {
-                for (int c = 0; c < nchunks; ++c, ++it) {
-                    const int stage = it % DT_NSTAGE;
-                    const uint32_t ph = (it / DT_NSTAGE) & 1;
+                for (int c = 0; c < nchunks; ++c) {
                     mbar_wait(&full_bar[stage], ph);
                     tc_fence_after();
-                    const uint32_t abase = smem_u32(smem + stage * S.stage_bytes);
-                    const uint32_t bbase = abase + S.b;
+                    const uint32_t abase = smem_u32(smem + stage * S.stage_bytes) >> 4;
+                    const uint32_t bbase = abase + (S.b >> 4);
                     for (int sub = 0; sub < msub; ++sub) {
                         if (c == 0) {
                             mbar_wait(&tempty_bar[sub], (stepno & 1) ^ 1);
                             tc_fence_after();
                         }
-                        if (lane == 0) {
+                        const uint32_t d_tmem = tmem_base + sub * NT;
+                        if (I8) {
+#pragma unroll
+                            for (int ks = 0; ks < 2; ++ks) {   // K = 32 per MMA: 2 x 16-byte k-groups
+                                const uint64_t adesc = a_hi | (uint64_t)(abase + sub * (8192 >> 4) + ks * (4096 >> 4));
+                                const uint64_t bdesc = b_hi | (uint64_t)(bbase + ks * 2 * NT);
+                                umma_i8_elect(d_tmem, adesc, bdesc, idesc, (c | ks) != 0 ? 1u : 0u);
+                            }
+                        } else {
 #pragma unroll
                             for (int plane = 0; plane < 2; ++plane)
 #pragma unroll
                                 for (int ks = 0; ks < 4; ++ks) {
-                                    uint64_t adesc = umma_desc_kmajor_noswz(abase + sub * 16384 + ks * 4096, 2048, 128);
-                                    uint64_t bdesc = umma_desc_kmajor_noswz(bbase + plane * NT * 128 + ks * 2 * NT * 16, NT * 16, 128);
-                                    umma_f16(tmem_base + sub * NT, adesc, bdesc, idesc, !(c == 0 && plane == 0 && ks == 0));
+                                    const uint64_t adesc = a_hi | (uint64_t)(abase + sub * (16384 >> 4) + ks * (4096 >> 4));
+                                    const uint64_t bdesc = b_hi | (uint64_t)(bbase + plane * NT * 8 + ks * 2 * NT);
+                                    umma_f16_elect(d_tmem, adesc, bdesc, idesc, (c | plane | ks) != 0 ? 1u : 0u);
                                 }
                         }
-                        __syncwarp();
                     }
-                    if (lane == 0) umma_commit(&empty_bar[stage]);
-                    __syncwarp();
+                    umma_commit_elect(&empty_bar[stage]);
+                    if (++stage == nstage) { stage = 0; ph ^= 1; }
                 }
-                if (lane == 0) umma_commit(tfull_bar);
-                __syncwarp();
+                umma_commit_elect(tfull_bar);
             }
     } else {
         // ================================= epilogue =================================
-        float* stg = reinterpret_cast<float*>(smem + S.stage);       // [128][TC+1]
-        float* outacc = reinterpret_cast<float*>(smem + S.outacc);   // [step_rows + L - 1][tpt]
+        // accumulators are fp32 (F16 kind) or int32 (I8 kind); staging and diagonal sums use the same type
+        typedef typename std::conditional<I8, int, float>::type acc_t;
+        acc_t* stg = reinterpret_cast<acc_t*>(smem + S.stage);       // [128][TC+1]
+        acc_t* outacc = reinterpret_cast<acc_t*>(smem + S.outacc);   // [step_rows + L - 1][tptv]
+        const float* scale = reinterpret_cast<const float*>(A.blob + 128);
         const int e = threadIdx.x;                                    // 0..127 == TMEM lane
         const int TC = L < DT_TAU_CHUNK ? L : DT_TAU_CHUNK;
         const int pitch = TC + 1;
-        const int nacc = (step_rows + L - 1) * tpt;
+        const int nacc = (step_rows + L - 1) * tptv;
+        const int vpt = f.vpt, tpt = tptv / vpt;
         uint32_t stepno = 0;
         for (long long u = blockIdx.x; u < nunits; u += gridDim.x) {
             const int nt = (int)(u % f.ntiles);
             const long long ur = u / f.ntiles;
             const long long o0 = ur * A.rows_per_unit;
             long long o1 = o0 + A.rows_per_unit; if (o1 > A.R) o1 = A.R;
-            for (int i = e; i < nacc; i += 128) outacc[i] = 0.f;
+            for (int i = e; i < nacc; i += 128) outacc[i] = 0;
             named_bar_sync(1, 128);
             for (int step = 0; step < A.steps_per_unit; ++step, ++stepno) {
                 mbar_wait(tfull_bar, stepno & 1);
                 tc_fence_after();
                 for (int sub = 0; sub < msub; ++sub) {
                     const uint32_t taddr = tmem_base + sub * NT + ((uint32_t)(warp * 32) << 16);
-                    for (int ml = 0; ml < tpt; ++ml) {
+                    for (int vl = 0; vl < tptv; ++vl) {
                         for (int c0 = 0; c0 < L; c0 += TC) {          // chunk of filter frames [c0, c0+cl)
                             const int cl = (L - c0) < TC ? (L - c0) : TC;
                             for (int t0 = 0; t0 < cl; t0 += 8) {
                                 uint32_t v[8];
-                                tmem_ld8(taddr + ml * L + c0 + t0, v);
+                                tmem_ld8(taddr + vl * L + c0 + t0, v);
                                 tmem_ld_wait();
 #pragma unroll
                                 for (int i = 0; i < 8; ++i)
-                                    if (t0 + i < cl) stg[e * pitch + t0 + i] = __uint_as_float(v[i]);
+                                    if (t0 + i < cl) reinterpret_cast<uint32_t*>(stg)[e * pitch + t0 + i] = v[i];
                             }
-                            if (ml == tpt - 1 && c0 + cl >= L) {   // accumulator drained: hand it back to the MMA warp
+                            if (vl == tptv - 1 && c0 + cl >= L) {   // accumulator drained: hand it back to the MMA warp
                                 tc_fence_before();
                                 mbar_arrive(&tempty_bar[sub]);
                             }
@@ -284,9 +383,9 @@ __global__ void __launch_bounds__(DT_THREADS, 1) detect_tc_kernel(DetectArgs A) 
                                 int tlo = -r0 > c0 ? -r0 : c0;
                                 int thi = (128 - r0) < (c0 + cl) ? (128 - r0) : (c0 + cl);
                                 if (tlo < thi) {
-                                    float part = 0.f;
+                                    acc_t part = 0;
                                     for (int tau = tlo; tau < thi; ++tau) part += stg[(r0 + tau) * pitch + (tau - c0)];
-                                    outacc[(sub * 128 + q) * tpt + ml] += part;
+                                    outacc[(sub * 128 + q) * tptv + vl] += part;
                                 }
                             }
                             named_bar_sync(1, 128);
@@ -301,21 +400,31 @@ __global__ void __launch_bounds__(DT_THREADS, 1) detect_tc_kernel(DetectArgs A) 
                     const int m = nt * tpt + ml;
                     if (g >= o0 && g < o1 && m < f.M) {
                         const int tl = (int)(g % A.T);
-                        A.scores[g * f.M + m] = (tl <= A.T - L) ? outacc[i] : 0.f;
+                        float val = 0.f;
+                        if (tl <= A.T - L) {
+                            const acc_t* a = outacc + oi * tptv + ml * vpt;
+                            if (I8) {   // recombine the base-256 digit planes exactly, then scale once
+                                double q = (double)a[0] + 256.0 * (double)a[1];
+                                if (vpt == 3) q += 65536.0 * (double)a[2];
+                                val = (float)(q * (double)scale[m]);
+                            } else {
+                                val = (float)a[0];
+                            }
+                        }
+                        A.scores[g * f.M + m] = val;
                     }
                 }
                 named_bar_sync(1, 128);
-                // carry the L-1 unfinished rows to the front, clear the rest (read phase, barrier,
-                // write phase; (L-1)*tpt < 256 so a thread holds at most two values)
+                // carry the L-1 unfinished rows to the front, clear the rest (read phase, barrier, write phase)
                 {
-                    const int keep = (L - 1) * tpt;
-                    float tmp[2] = {0.f, 0.f};
+                    const int keep = (L - 1) * tptv;
+                    acc_t tmp[12];
                     int cnt = 0;
-                    for (int i = e; i < keep; i += 128) tmp[cnt++] = outacc[i + step_rows * tpt];
+                    for (int i = e; i < keep; i += 128) tmp[cnt++] = outacc[i + step_rows * tptv];
                     named_bar_sync(1, 128);
                     cnt = 0;
                     for (int i = e; i < keep; i += 128) outacc[i] = tmp[cnt++];
-                    for (int i = keep + e; i < nacc; i += 128) outacc[i] = 0.f;
+                    for (int i = keep + e; i < nacc; i += 128) outacc[i] = 0;
                     named_bar_sync(1, 128);
                 }
             }
@@ -406,9 +515,9 @@ using namespace tsr;
 
 extern "C" {
 
-size_t tsr_filter_blob_bytes(int M, int L, int D) {
-    if (M < 1 || L < 1 || L > 256 || D < 1) return 0;
-    return filter_layout(M, L, D).total;
+size_t tsr_filter_blob_bytes(int M, int L, int D, int plane_format) {
+    if (M < 1 || L < 1 || L > 256 || D < 1 || plane_format < 0 || plane_format > 4) return 0;
+    return filter_layout(M, L, D, plane_format).total;
 }
 
 int tsr_prepare_filters(const float* LF, int M, int L, int D, int plane_format, void* blob, void* stream) {
@@ -416,26 +525,26 @@ int tsr_prepare_filters(const float* LF, int M, int L, int D, int plane_format, 
     TSR_REQUIRE(M >= 1 && M <= 65535, "tsr_prepare_filters: need 1 <= M <= 65535 templates (uint16 argmax), got %d", M);
     TSR_REQUIRE(L >= 1 && L <= 256, "tsr_prepare_filters: template length %d outside [1,256]", L);
     TSR_REQUIRE(D >= 1, "tsr_prepare_filters: D < 1");
+    TSR_REQUIRE(plane_format >= 0 && plane_format <= 4, "tsr_prepare_filters: plane_format must be one of TSR_PLANES_*");
     int rc = require_sm100("tsr_prepare_filters");
     if (rc) return rc;
-    TSR_REQUIRE(plane_format >= 0 && plane_format <= 2, "tsr_prepare_filters: plane_format must be 0 (auto), 1 (bf16) or 2 (fp16)");
-    FilterLayout f = filter_layout(M, L, D);
+    FilterLayout f = filter_layout(M, L, D, plane_format);
     cudaStream_t st = (cudaStream_t)stream;
-    TSR_CUDA(cudaMemsetAsync(blob, 0, DT_HDR_BYTES, st));
-    filters_maxabs_kernel<<<148 * 2, 256, 0, st>>>(LF, (size_t)M * L * D, (uint8_t*)blob);
+    TSR_CUDA(cudaMemsetAsync(blob, 0, f.hdr_bytes, st));
+    dim3 g(16, M);
+    filters_maxabs_kernel<<<g, 256, 0, st>>>(LF, M, (size_t)L * D, (uint8_t*)blob);
     prepare_filters_kernel<<<148 * 8, 256, 0, st>>>(LF, (uint8_t*)blob, f, plane_format);
-    filters_publish_format_kernel<<<1, 1, 0, st>>>((uint8_t*)blob, plane_format);
+    filters_publish_kernel<<<(M + 255) / 256, 256, 0, st>>>((uint8_t*)blob, plane_format, f);
     return check_launch("tsr_prepare_filters");
 }
 
 int tsr_detect(const uint32_t* featbits, int B, int T, int D, int rowwords, const void* filter_blob,
-               const float* LF_or_null, int M, int L, float* scores, int impl, void* stream) {
+               const float* LF_or_null, int M, int L, int plane_format, float* scores, int impl, void* stream) {
     if (B == 0) return TSR_OK;
     TSR_REQUIRE(featbits && scores, "tsr_detect: null pointer");
     TSR_REQUIRE(B >= 0 && T >= 1 && D >= 1 && M >= 1 && L >= 1, "tsr_detect: bad sizes");
     TSR_REQUIRE(rowwords == tsr_rowwords(D), "tsr_detect: rowwords must be tsr_rowwords(D)");
     TSR_REQUIRE(impl == TSR_IMPL_TENSOR || impl == TSR_IMPL_SIMT, "tsr_detect: unknown impl %d", impl);
-    if (B == 0) return TSR_OK;
     int rc = require_sm100("tsr_detect");
     if (rc) return rc;
     const long long R = (long long)B * T;
@@ -452,9 +561,10 @@ int tsr_detect(const uint32_t* featbits, int B, int T, int D, int rowwords, cons
     }
     TSR_REQUIRE(filter_blob, "tsr_detect: needs the prepared filter blob");
     TSR_REQUIRE(L <= 256, "tsr_detect: template length %d > 256 unsupported on the tensor path", L);
+    TSR_REQUIRE(plane_format >= 0 && plane_format <= 4, "tsr_detect: plane_format must be one of TSR_PLANES_*");
     DetectArgs A;
     A.bits = featbits; A.blob = (const uint8_t*)filter_blob; A.scores = scores; A.R = R; A.T = T;
-    A.f = filter_layout(M, L, D);
+    A.f = filter_layout(M, L, D, plane_format);
     DetectSmem S = detect_smem_layout(A.f);
     if (S.total > 227 * 1024) {
         set_error("tsr_detect: L=%d needs %u B of shared memory (> 227 KB)", L, S.total);
@@ -477,9 +587,14 @@ int tsr_detect(const uint32_t* featbits, int B, int T, int D, int rowwords, cons
     A.rows_per_unit = (int)((R + best_U - 1) / best_U);
     A.steps_per_unit = (A.rows_per_unit + L - 1 + step_rows - 1) / step_rows;
     const long long nunits = (long long)A.f.ntiles * best_U;
-    TSR_CUDA(cudaFuncSetAttribute(detect_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S.total));
     int blocks = (int)(nunits < nsm ? nunits : nsm);
-    detect_tc_kernel<<<blocks, DT_THREADS, S.total, (cudaStream_t)stream>>>(A);
+    if (A.f.kind) {
+        TSR_CUDA(cudaFuncSetAttribute(detect_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S.total));
+        detect_tc_kernel<true><<<blocks, DT_THREADS, S.total, (cudaStream_t)stream>>>(A);
+    } else {
+        TSR_CUDA(cudaFuncSetAttribute(detect_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S.total));
+        detect_tc_kernel<false><<<blocks, DT_THREADS, S.total, (cudaStream_t)stream>>>(A);
+    }
     return check_launch("tsr_detect");
 }
 

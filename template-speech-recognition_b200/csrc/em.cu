@@ -9,9 +9,10 @@
 #include "common.cuh"
 
 extern "C" int tsr_prepare_filters(const float* LF, int M, int L, int D, int plane_format, void* blob, void* stream);
-extern "C" size_t tsr_filter_blob_bytes(int M, int L, int D);
+extern "C" size_t tsr_filter_blob_bytes(int M, int L, int D, int plane_format);
 extern "C" int tsr_detect(const uint32_t* featbits, int B, int T, int D, int rowwords, const void* filter_blob,
-                          const float* LF_or_null, int M, int L, float* scores, int impl, void* stream);
+                          const float* LF_or_null, int M, int L, int plane_format, float* scores, int impl, void* stream);
+#define EM_PLANES TSR_PLANES_AUTO
 
 namespace tsr {
 
@@ -27,7 +28,7 @@ static EmWorkspace em_workspace(long long N, int D, int K) {
     w.off_w = 0;
     w.off_c = up((size_t)K * D * 4);
     w.off_blob = w.off_c + up((size_t)K * 4);
-    w.off_scores = w.off_blob + up(tsr_filter_blob_bytes(K, 1, D));
+    w.off_scores = w.off_blob + up(tsr_filter_blob_bytes(K, 1, D, EM_PLANES));
     w.off_partial = w.off_scores + up((size_t)N * K * 4);
     w.total = w.off_partial + up((size_t)EM_MSPLIT * K * D * 4);
     return w;
@@ -195,10 +196,10 @@ int tsr_em_estep(const uint32_t* Xbits, long long N, int D, int rowwords, int K,
     rc = check_launch("tsr_em_estep(weights)");
     if (rc) return rc;
     if (impl == TSR_IMPL_TENSOR) {
-        rc = tsr_prepare_filters(W, K, 1, D, 0, ws + w.off_blob, stream);
+        rc = tsr_prepare_filters(W, K, 1, D, EM_PLANES, ws + w.off_blob, stream);
         if (rc) return rc;
     }
-    rc = tsr_detect(Xbits, 1, (int)N, D, rowwords, ws + w.off_blob, W, K, 1, S, impl, stream);
+    rc = tsr_detect(Xbits, 1, (int)N, D, rowwords, ws + w.off_blob, W, K, 1, EM_PLANES, S, impl, stream);
     if (rc) return rc;
     em_posterior_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(S, c, logw, N, K, aff, scores_or_null,
                                                                       stats + (size_t)K * D, stats_ll, hard);

@@ -9,7 +9,8 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import IMPL_SIMT, IMPL_TENSOR, PLANES_AUTO, PLANES_BF16, PLANES_FP16  # noqa: F401
+from ._lib import (IMPL_SIMT, IMPL_TENSOR, PLANES_AUTO, PLANES_BF16, PLANES_FP16,  # noqa: F401
+                   PLANES_INT8X2, PLANES_INT8X3)
 
 # Orientation table produced by the reference edge extractor (edge_signal_proc.py:1751-1821,
 # returned by _edge_map_no_threshold and passed to spread_edgemap by every pipeline caller):
@@ -174,7 +175,8 @@ class FilterBank:
         self.D = int(np.prod(LF.shape[2:]))
         self.LF = torch.from_numpy(LF.reshape(self.M, self.L, self.D)).to(device)
         self.cs = None if cs is None else torch.as_tensor(np.asarray(cs, dtype=np.float32).reshape(self.M)).to(device)
-        nbytes = _lib.lib().tsr_filter_blob_bytes(self.M, self.L, self.D)
+        self.planes = int(planes)
+        nbytes = _lib.lib().tsr_filter_blob_bytes(self.M, self.L, self.D, self.planes)
         if nbytes == 0:
             raise ValueError("unsupported filter shape M=%d L=%d D=%d (need 1 <= L <= 256)" % (self.M, self.L, self.D))
         self.blob = torch.empty(nbytes, dtype=torch.uint8, device=device)
@@ -190,8 +192,8 @@ def detect(featbits, bank, D=None, impl=IMPL_TENSOR, out=None):
         raise ValueError("feature width %d does not match the filters (%d)" % (D, bank.D))
     if out is None:
         out = torch.empty((B, T, bank.M), dtype=torch.float32, device=featbits.device)
-    _lib.call("tsr_detect", _ptr(featbits), B, T, D, rw, _ptr(bank.blob), _ptr(bank.LF), bank.M, bank.L, _ptr(out),
-              int(impl), _stream())
+    _lib.call("tsr_detect", _ptr(featbits), B, T, D, rw, _ptr(bank.blob), _ptr(bank.LF), bank.M, bank.L, bank.planes,
+              _ptr(out), int(impl), _stream())
     return out
 
 

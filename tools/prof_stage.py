@@ -14,6 +14,7 @@ ap.add_argument("stage")
 ap.add_argument("--batch", type=int, default=1024)
 ap.add_argument("--iters", type=int, default=3)
 ap.add_argument("--simt", action="store_true")
+ap.add_argument("--planes", type=int, default=4)
 a = ap.parse_args()
 impl = ops.IMPL_SIMT if a.simt else ops.IMPL_TENSOR
 B = a.batch
@@ -21,7 +22,7 @@ lp, lip = synth.parts(100)
 parts = ops.PartsModel(lp, lip)
 Tm, bgd = synth.templates(M=32, L=40, Fd=36, Kd=100)
 W, c = synth.linear_filters(Tm, bgd)
-bank = ops.FilterBank(W, cs=c)
+bank = ops.FilterBank(W, cs=c, planes=a.planes)
 bits = ops.pack_edges(torch.from_numpy(synth.fast_edge_batch(B)).cuda())
 sb = ops.spread_edges(bits, 1, None, "line", 40)
 codes, _, _ = ops.code_parts(sb, parts, 12, impl=impl)
