@@ -23,7 +23,6 @@ namespace tsr {
 
 struct PartsLayout {
     int K, ph, pw, npad, nsteps, nq;
-    int concat;   // 1: hi and lo planes side by side along N (one MMA of N = 2*npad per K step); 0: two MMAs
     size_t off_w, off_c, off_wf, off_mask, off_hdr, total;
 };
 
@@ -33,7 +32,6 @@ __host__ __device__ inline PartsLayout parts_layout(int K, int ph, int pw) {
     L.nq = ph * pw;
     L.npad = ((K + 2) + 15) & ~15;
     L.nsteps = (L.nq + 1) / 2;
-    L.concat = 2 * L.npad <= 256 ? 1 : 0;
     L.off_w = 0;
     L.off_c = (size_t)2 * L.nsteps * L.npad * 32;
     L.off_wf = L.off_c + (size_t)L.npad * 4;
@@ -76,15 +74,10 @@ __global__ void prepare_parts_kernel(const double* __restrict__ lp, const double
         }
         uint16_t hi, lo;
         split_hi_lo(w, fmt, hi, lo);
-        if (L.concat) {   // [step][kgroup][row: hi plane 0..npad-1 | lo plane npad..2npad-1][8]
-            size_t o = (((size_t)s * 2 + (e >> 3)) * (2 * L.npad) + n) * 16 + z * 2;
-            *reinterpret_cast<uint16_t*>(blob + L.off_w + o) = hi;
-            *reinterpret_cast<uint16_t*>(blob + L.off_w + o + (size_t)L.npad * 16) = lo;
-        } else {          // [plane][step][kgroup][row][8]
-            size_t o = (((size_t)s * 2 + (e >> 3)) * L.npad + n) * 16 + z * 2;
-            *reinterpret_cast<uint16_t*>(blob + L.off_w + o) = hi;
-            *reinterpret_cast<uint16_t*>(blob + L.off_w + (size_t)L.nsteps * L.npad * 32 + o) = lo;
-        }
+        // [plane][step][kgroup][row][8]: both planes accumulate into the same TMEM columns
+        size_t o = (((size_t)s * 2 + (e >> 3)) * L.npad + n) * 16 + z * 2;
+        *reinterpret_cast<uint16_t*>(blob + L.off_w + o) = hi;
+        *reinterpret_cast<uint16_t*>(blob + L.off_w + (size_t)L.nsteps * L.npad * 32 + o) = lo;
         if (q < L.nq) reinterpret_cast<float*>(blob + L.off_wf)[((size_t)q * 8 + z) * L.npad + n] = (float)w;
     }
     // c[k] = sum lip (float64, reference order), one thread per part
@@ -118,7 +111,14 @@ struct CodeArgs {
     int B, T, F, To, Fo;
     int threshold, mask_threshold;
     PartsLayout L;
+    int dbg;            // debug experiments: 1 = epilogue skips TMEM reads, 2 = MMA warp skips tcgen05.mma
+    long long* trace;   // optional debug timeline of CTA 0: [tile][8] clock64 stamps (tools/trace_code_parts.py)
 };
+#define CP_TRACE_TILES 96
+#define CP_TRACE(slot)                                                                              \
+    do {                                                                                            \
+        if (A.trace && blockIdx.x == 0 && it < CP_TRACE_TILES && lane == 0) A.trace[it * 8 + (slot)] = clock64(); \
+    } while (0)
 
 // --------------------------------------------------------------------------- SIMT path
 // One warp per location, lanes over parts; walks the set bits of the window in (a,b,z) order and
@@ -197,7 +197,7 @@ __global__ void __launch_bounds__(256) code_parts_simt_kernel(CodeArgs A) {
 
 // ------------------------------------------------------------------------- tensor path
 #define CP_NSTAGE 4
-#define CP_THREADS 416   // warps 0-3 epilogue (even tiles), 4 MMA/TMEM, 5-8 producers, 9-12 epilogue (odd tiles)
+#define CP_THREADS 416   // warps 0-3 / 4-7 epilogue (even / odd tiles), 8-11 producers, 12 MMA + TMEM (highest id: wins arbitration)
 #define CP_MAX_STEPS 32
 
 struct CodeSmem {   // offsets into dynamic shared memory
@@ -211,10 +211,13 @@ __host__ __device__ inline CodeSmem code_smem_layout(const PartsLayout& L, int F
     S.npos = 128 + (L.ph - 1) * F + (L.pw - 1) + 2;
     S.stage_bytes = (S.npos * 16 + 127) & ~127u;
     S.bars = S.a + CP_NSTAGE * S.stage_bytes;
-    S.total = S.bars + 128;
+    S.total = S.bars + 128 + CP_MAX_STEPS * 4;   // barriers | generic-path A descriptor words
     return S;
 }
 
+// NSTEPS_CT > 0: K-step count known at compile time (13 for the 5x5 parts of every reference config): the
+// issue loop is fully unrolled with the descriptor words in registers.  NSTEPS_CT == 0: generic, smem table.
+template <int NSTEPS_CT>
 __global__ void __launch_bounds__(CP_THREADS, 1) code_parts_tc_kernel(CodeArgs A, int tiles_per_utt, long long ntiles) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const PartsLayout& L = A.L;
@@ -236,7 +239,7 @@ __global__ void __launch_bounds__(CP_THREADS, 1) code_parts_tc_kernel(CodeArgs A
         mbar_init(w_bar, 1);
         mbar_fence_init();
     }
-    if (warp == 4) {
+    if (warp == 12) {
         tmem_alloc<512>(tmem_ptr);
     }
     if (threadIdx.x < 32) reinterpret_cast<float*>(smem + S.c)[L.npad + threadIdx.x] = -INFINITY;   // tail for 32-wide reads
@@ -255,9 +258,9 @@ __global__ void __launch_bounds__(CP_THREADS, 1) code_parts_tc_kernel(CodeArgs A
         bulk_g2s(smem + S.c, A.blob + L.off_c, L.npad * 4, w_bar);
     }
 
-    if (warp >= 5 && warp <= 8) {
+    if (warp >= 8 && warp <= 11) {
         // ================================ producers ================================
-        const int pt = threadIdx.x - 160;
+        const int pt = threadIdx.x - 256;
         const uint32_t one = fmt_one(fmt);
         const int plimit = A.T * A.F;
         const int npos = (int)S.npos;
@@ -277,7 +280,8 @@ __global__ void __launch_bounds__(CP_THREADS, 1) code_parts_tc_kernel(CodeArgs A
         for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
             const int stage = it % CP_NSTAGE;
             const uint32_t ph = (it / CP_NSTAGE) & 1;
-            mbar_wait(&empty_bar[stage], ph ^ 1);
+            mbar_wait_relaxed(&empty_bar[stage], ph ^ 1);
+            if (warp == 8) CP_TRACE(0);
             uint8_t* dst = smem + S.a + stage * S.stage_bytes;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -295,36 +299,44 @@ __global__ void __launch_bounds__(CP_THREADS, 1) code_parts_tc_kernel(CodeArgs A
             }
             fence_proxy_async_smem();
             mbar_arrive(&full_bar[stage]);
+            if (warp == 8) CP_TRACE(1);
             if (tile + gridDim.x < ntiles) prefetch(tile + gridDim.x);   // overlaps the next empty-slot wait
         }
-    } else if (warp == 4) {
+    } else if (warp == 12) {
         // ================================ MMA issuer ================================
-        // The whole warp runs this loop in lock step; one elected lane issues each tcgen05 op.
-        // Per-step descriptor words are tile independent and live in registers (static unroll):
+        // The whole warp runs this loop in lock step; one elected lane issues each tcgen05 op.  The
+        // issuing warp executes ~10 instructions per MMA: at 56 tensor cycles per MMA anything more
+        // (divisions, table walks, 64-way predicated unrolls) makes the issue loop the bottleneck.
         //   A low word = (patch group offset in 16-byte units) | LBO << 16   (+ stage base per tile)
         //   B low word = plane/step address >> 4 | LBO << 16
         mbar_wait(w_bar, 0);
-        const int nmma_n = L.concat ? 2 * L.npad : L.npad;                 // N of one MMA
-        const uint32_t idesc = umma_idesc_f32acc(fmt, 128, nmma_n);
-        const uint32_t desc_hi = (uint32_t)(128 >> 4) | (1u << 14);        // SBO = 128 B, version 1 (bits 32..47)
-        uint32_t a_lo[CP_MAX_STEPS], b_lo[2 * CP_MAX_STEPS];
+        const uint32_t idesc = umma_idesc_f32acc(fmt, 128, L.npad);
+        const uint64_t desc_hi = (uint64_t)((uint32_t)(128 >> 4) | (1u << 14)) << 32;   // SBO = 128 B, version 1
+        const uint32_t b_base = (smem_u32(smem + S.w) >> 4) | ((uint32_t)L.npad << 16);
+        const uint32_t b_step = 2 * L.npad;
+        constexpr int NS = NSTEPS_CT > 0 ? NSTEPS_CT : 1;
+        uint32_t a_lo[NS];
+        uint32_t* a_tab = reinterpret_cast<uint32_t*>(smem + S.bars + 128);   // generic path: [nsteps]
         {
-            const uint32_t b_base = smem_u32(smem + S.w) >> 4;
             int pa = 0, pb = 0;
-#pragma unroll
-            for (int s = 0; s < CP_MAX_STEPS; ++s) {
+            for (int s = 0; s < L.nsteps; ++s) {
                 const uint32_t off0 = pa * A.F + pb;
                 int pb1 = pb + 1, pa1 = pa;
                 if (pb1 == L.pw) { pb1 = 0; ++pa1; }
                 const uint32_t off1 = (2 * s + 1 < L.nq) ? pa1 * A.F + pb1 : off0 + 1;
-                a_lo[s] = off0 | ((off1 - off0) << 16);
-                b_lo[s] = (b_base + (uint32_t)s * 2 * nmma_n) | ((uint32_t)nmma_n << 16);
-                b_lo[CP_MAX_STEPS + s] = (b_base + (uint32_t)(L.nsteps + s) * 2 * nmma_n) | ((uint32_t)nmma_n << 16);
+                const uint32_t w = off0 | ((off1 - off0) << 16);
+                if (NSTEPS_CT > 0) {
+#pragma unroll
+                    for (int k = 0; k < NS; ++k)
+                        if (k == s) a_lo[k] = w;
+                } else if (lane == 0) {
+                    a_tab[s] = w;
+                }
                 pb = pb1 + 1; pa = pa1;
                 if (pb == L.pw) { pb = 0; ++pa; }
             }
+            __syncwarp();
         }
-        const int nplane_mma = L.concat ? 1 : 2;
         uint32_t it = 0;
         for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
             const int stage = it % CP_NSTAGE;
@@ -332,27 +344,41 @@ __global__ void __launch_bounds__(CP_THREADS, 1) code_parts_tc_kernel(CodeArgs A
             const int acc = it & 1;
             const uint32_t aph = (it >> 1) & 1;
             mbar_wait(&full_bar[stage], ph);
+            CP_TRACE(2);
             mbar_wait(&tempty_bar[acc], aph ^ 1);
+            CP_TRACE(3);
             tc_fence_after();
             const uint32_t a_base = smem_u32(smem + S.a + stage * S.stage_bytes) >> 4;
             const uint32_t d_tmem = tmem_base + acc * 256;
+            if (!(A.dbg & 2)) {
+                uint32_t b_lo = b_base;
+                if (NSTEPS_CT > 0) {
 #pragma unroll
-            for (int i = 0; i < 2 * CP_MAX_STEPS; ++i) {
-                const int s = i % CP_MAX_STEPS;
-                if (s < L.nsteps && i / CP_MAX_STEPS < nplane_mma) {
-                    const uint64_t adesc = ((uint64_t)desc_hi << 32) | (uint64_t)(a_lo[s] + a_base);
-                    const uint64_t bdesc = ((uint64_t)desc_hi << 32) | (uint64_t)b_lo[i];
-                    umma_f16_elect(d_tmem, adesc, bdesc, idesc, i > 0 ? 1u : 0u);
+                    for (int plane = 0; plane < 2; ++plane)
+#pragma unroll
+                        for (int s = 0; s < NS; ++s) {
+                            umma_f16_elect(d_tmem, desc_hi | (uint64_t)(a_lo[s] + a_base), desc_hi | (uint64_t)b_lo, idesc,
+                                           (plane | s) != 0 ? 1u : 0u);
+                            b_lo += b_step;
+                        }
+                } else {
+                    for (int plane = 0; plane < 2; ++plane)
+                        for (int s = 0; s < L.nsteps; ++s) {
+                            umma_f16_elect(d_tmem, desc_hi | (uint64_t)(a_tab[s] + a_base), desc_hi | (uint64_t)b_lo, idesc,
+                                           (plane | s) != 0 ? 1u : 0u);
+                            b_lo += b_step;
+                        }
                 }
             }
             umma_commit_elect(&empty_bar[stage]);   // A stage reusable once these MMAs retire
             umma_commit_elect(&tfull_bar[acc]);     // accumulator ready for the epilogue
+            CP_TRACE(4);
         }
     } else {
         // ================================ epilogue ================================
-        // two warp sets: warps 0-3 drain accumulator 0 (even tiles), warps 9-12 accumulator 1 (odd tiles)
-        mbar_wait(w_bar, 0);   // c[] lives in the same bulk transaction
-        const int eset = warp >= 9 ? 1 : 0;
+        // two warp sets: warps 0-3 drain accumulator 0 (even tiles), warps 4-7 accumulator 1 (odd tiles)
+        mbar_wait_relaxed(w_bar, 0);   // c[] lives in the same bulk transaction
+        const int eset = warp >= 4 ? 1 : 0;
         const int e = (warp & 3) * 32 + lane;   // TMEM lane == tile row (lane quadrant = warp % 4)
         const int ccol = L.K & ~7;   // 16-column window holding the count (K) and mask-count (K+1) columns
         uint32_t it = eset;
@@ -364,58 +390,49 @@ __global__ void __launch_bounds__(CP_THREADS, 1) code_parts_tc_kernel(CodeArgs A
             const int t = p / A.F, f = p - t * A.F;
             const bool valid = t < A.To && f < A.Fo;
             const size_t loc = ((size_t)b * A.To + t) * A.Fo + f;
-            mbar_wait(&tfull_bar[acc], aph);
+            mbar_wait_relaxed(&tfull_bar[acc], aph);
+            if ((warp & 3) == 0) CP_TRACE(5);
             tc_fence_after();
             const uint32_t taddr = tmem_base + acc * 256 + ((uint32_t)((warp & 3) * 32) << 16);
             // four independent running (max, argmax) chains over columns n = 4j + c; padded columns carry
             // c = -inf.  Strict '>' within a chain keeps the lowest index; the merge breaks ties by index.
             float bv[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
             int bk[4] = {0, 1, 2, 3};
-            // score = hi column + lo column (concat layout: lo plane sits npad columns further) + c
-            auto process16 = [&](const uint32_t (&vh)[16], const uint32_t (&vl)[16], int n0) {
+            // All TMEM loads of a 64-column block are issued back to back and waited for once; the
+            // reduction then runs on registers, one guard per 16 columns, c[] fetched 16 at a time.
+            for (int nb = 0; nb < ((A.dbg & 1) ? 0 : L.npad); nb += 64) {
+                uint32_t v[64];
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (nb + 16 * j < L.npad) tmem_ld16(taddr + nb + 16 * j, *reinterpret_cast<uint32_t(*)[16]>(&v[16 * j]));
+                tmem_ld_wait();
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    const float4 c4 = *reinterpret_cast<const float4*>(cs + n0 + 4 * j);
-                    float s0 = __uint_as_float(vh[4 * j + 0]), s1 = __uint_as_float(vh[4 * j + 1]);
-                    float s2 = __uint_as_float(vh[4 * j + 2]), s3 = __uint_as_float(vh[4 * j + 3]);
-                    if (L.concat) {
-                        s0 += __uint_as_float(vl[4 * j + 0]); s1 += __uint_as_float(vl[4 * j + 1]);
-                        s2 += __uint_as_float(vl[4 * j + 2]); s3 += __uint_as_float(vl[4 * j + 3]);
-                    }
-                    s0 += c4.x; s1 += c4.y; s2 += c4.z; s3 += c4.w;
-                    const int n = n0 + 4 * j;
-                    if (s0 > bv[0]) { bv[0] = s0; bk[0] = n; }
-                    if (s1 > bv[1]) { bv[1] = s1; bk[1] = n + 1; }
-                    if (s2 > bv[2]) { bv[2] = s2; bk[2] = n + 2; }
-                    if (s3 > bv[3]) { bv[3] = s3; bk[3] = n + 3; }
-                    if (A.scores && valid) {   // drop-in path only: full score map
-                        float* srow = A.scores + loc * L.K;
-                        if (n + 0 < L.K) srow[n + 0] = s0;
-                        if (n + 1 < L.K) srow[n + 1] = s1;
-                        if (n + 2 < L.K) srow[n + 2] = s2;
-                        if (n + 3 < L.K) srow[n + 3] = s3;
+                    if (nb + 16 * j < L.npad) {
+                        const int n = nb + 16 * j;
+                        const float4* c4p = reinterpret_cast<const float4*>(cs + n);
+                        const float4 ca = c4p[0], cb = c4p[1], cc = c4p[2], cd = c4p[3];
+                        const float cv[16] = {ca.x, ca.y, ca.z, ca.w, cb.x, cb.y, cb.z, cb.w,
+                                              cc.x, cc.y, cc.z, cc.w, cd.x, cd.y, cd.z, cd.w};
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            const float sc = __uint_as_float(v[16 * j + i]) + cv[i];
+                            if (sc > bv[i & 3]) { bv[i & 3] = sc; bk[i & 3] = n + i; }
+                        }
                     }
                 }
-            };
-            // software-pipelined TMEM reads: the next 16 columns (of both planes) are in flight while the
-            // current 16 are reduced
-            uint32_t ha[16], la[16], hb[16], lb[16];
-            tmem_ld16(taddr, ha);
-            if (L.concat) tmem_ld16(taddr + L.npad, la);
-            for (int n0 = 0; n0 < L.npad; n0 += 32) {
-                tmem_ld_wait();
-                if (n0 + 16 < L.npad) {
-                    tmem_ld16(taddr + n0 + 16, hb);
-                    if (L.concat) tmem_ld16(taddr + L.npad + n0 + 16, lb);
-                }
-                process16(ha, la, n0);
-                if (n0 + 16 < L.npad) {
+            }
+            if (A.scores && !(A.dbg & 1)) {   // drop-in path only: the full score map
+                // tcgen05.ld is warp-collective (.sync.aligned): the branch above is warp-uniform and only
+                // the global stores are predicated on the lane's own validity
+                float* srow = A.scores + loc * L.K;
+                for (int n0 = 0; n0 < L.K; n0 += 16) {
+                    uint32_t v[16];
+                    tmem_ld16(taddr + n0, v);
                     tmem_ld_wait();
-                    if (n0 + 32 < L.npad) {
-                        tmem_ld16(taddr + n0 + 32, ha);
-                        if (L.concat) tmem_ld16(taddr + L.npad + n0 + 32, la);
-                    }
-                    process16(hb, lb, n0 + 16);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i)
+                        if (valid && n0 + i < L.K) srow[n0 + i] = __uint_as_float(v[i]) + cs[n0 + i];
                 }
             }
             // exact integer edge counts from the all-ones / mask weight columns
@@ -433,6 +450,7 @@ __global__ void __launch_bounds__(CP_THREADS, 1) code_parts_tc_kernel(CodeArgs A
             }
             tc_fence_before();
             mbar_arrive(&tempty_bar[acc]);
+            if ((warp & 3) == 0) CP_TRACE(6);
             float best = bv[0];
             int bestk = bk[0];
 #pragma unroll
@@ -444,12 +462,13 @@ __global__ void __launch_bounds__(CP_THREADS, 1) code_parts_tc_kernel(CodeArgs A
                 if (A.codes) A.codes[loc] = gate ? (uint8_t)(bestk + 1) : 0;
                 if (A.counts) A.counts[loc] = (uint16_t)count;
             }
+            if ((warp & 3) == 0) CP_TRACE(7);
         }
     }
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 4) {
+    if (warp == 12) {
         tc_fence_after();
         tmem_dealloc<512>(tmem_base);
     }
@@ -459,7 +478,14 @@ __global__ void __launch_bounds__(CP_THREADS, 1) code_parts_tc_kernel(CodeArgs A
 
 using namespace tsr;
 
+static long long* g_code_trace = nullptr;
+static int g_code_dbg = 0;   // debug hook, see tsr_debug_set_code_trace
+
 extern "C" {
+
+/* Debug only (not in the public header): device buffer of CP_TRACE_TILES*8 int64 clock stamps. */
+void tsr_debug_set_code_trace(long long* dev_buf) { g_code_trace = dev_buf; }
+void tsr_debug_set_code_flags(int flags) { g_code_dbg = flags; }
 
 size_t tsr_parts_blob_bytes(int K, int ph, int pw) {
     if (K < 1 || ph < 1 || pw < 1) return 0;
@@ -501,6 +527,8 @@ int tsr_code_parts(const uint8_t* bits, const void* parts_blob, int K, int ph, i
     A.bits = bits; A.blob = (const uint8_t*)parts_blob; A.codes = codes; A.scores = scores_or_null; A.counts = counts_or_null;
     A.B = B; A.T = T; A.F = F; A.To = T - ph + 1; A.Fo = F - pw + 1;
     A.threshold = threshold; A.mask_threshold = mask_threshold;
+    A.trace = g_code_trace;
+    A.dbg = g_code_dbg;
     A.L = parts_layout(K, ph, pw);
     const int nsm = sm_count();
     if (impl == TSR_IMPL_SIMT) {
@@ -519,9 +547,14 @@ int tsr_code_parts(const uint8_t* bits, const void* parts_blob, int K, int ph, i
     TSR_REQUIRE((uint32_t)((ph - 1) * F + pw) * 16 < (1u << 18), "tsr_code_parts: F too large for the patch descriptor");
     const int tiles_per_utt = (int)(((long long)A.To * F + 127) / 128);
     const long long ntiles = (long long)tiles_per_utt * B;
-    TSR_CUDA(cudaFuncSetAttribute(code_parts_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S.total));
     int blocks = (int)(ntiles < nsm ? ntiles : nsm);
-    code_parts_tc_kernel<<<blocks, CP_THREADS, S.total, (cudaStream_t)stream>>>(A, tiles_per_utt, ntiles);
+    if (A.L.nsteps == 13) {
+        TSR_CUDA(cudaFuncSetAttribute(code_parts_tc_kernel<13>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S.total));
+        code_parts_tc_kernel<13><<<blocks, CP_THREADS, S.total, (cudaStream_t)stream>>>(A, tiles_per_utt, ntiles);
+    } else {
+        TSR_CUDA(cudaFuncSetAttribute(code_parts_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S.total));
+        code_parts_tc_kernel<0><<<blocks, CP_THREADS, S.total, (cudaStream_t)stream>>>(A, tiles_per_utt, ntiles);
+    }
     return check_launch("tsr_code_parts");
 }
 

@@ -60,20 +60,37 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                  : "memory");
 }
+// try_wait with a suspend-time hint: the hardware parks the thread (no issue slots consumed) until
+// the phase completes or the hint (ns) expires -- a plain poll loop in a high-priority warp starves
+// the other warps of its SMSP (measured: 10x slower epilogues next to a spinning MMA warp).
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(100000u)
         : "memory");
     return ok != 0;
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
+        if (++spins > TSR_SPIN_LIMIT) {
+            printf("tsr_b200: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+            __trap();
+        }
+    }
+}
+
+// Same wait for warps that are NOT on the critical issue path (producers, epilogue): back off
+// between polls so the spinning warp does not take issue slots from the MMA-issuing warp (the
+// SMSP arbiter favours higher warp ids; a tight poll loop in a higher-id warp starves it).
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        __nanosleep(40);
         if (++spins > TSR_SPIN_LIMIT) {
             printf("tsr_b200: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
             __trap();

@@ -14,10 +14,11 @@
 // per template group: the "sliding reuse" is total.
 //
 // CTA (persistent, 1 per SM, 576 threads):
-//   warps 0-3   epilogue: TMEM -> smem staging -> diagonal sums -> global
-//   warp  4     MMA issuer + TMEM allocation
-//   warp  5     filter-tile loader (cp.async.bulk, one 2*NT*128-byte copy per 64-feature chunk)
-//   warps 6-17  frame-bit expanders (one row of the 384-row step each)
+// Warp ids are ordered by how critical the role is (the SMSP arbiter favours higher ids):
+//   warp  0     filter-tile loader (cp.async.bulk, one copy per pipeline stage)
+//   warps 1-12  frame-bit expanders (one row of the 384-row step each)
+//   warps 13-16 epilogue: TMEM -> smem staging -> diagonal sums -> global (TMEM lane quadrant = warp % 4)
+//   warp  17    MMA issuer + TMEM allocation
 #include <type_traits>
 
 #include "common.cuh"
@@ -46,6 +47,7 @@ struct FilterLayout {
     int ntiles;   // ceil(M*vpt / tptv)
     int msub;     // 128-row accumulators per step (msub*NT <= 512)
     int nstage;   // smem pipeline depth
+    int fps;      // features per pipeline stage: 64 (F16, 8 k-groups of 8) or 128 (I8, 8 k-groups of 16)
     size_t tile_bytes;   // one (ntile, chunk) filter tile
     size_t hdr_bytes;    // [0] plane format, [1] max|w| bits, then float scale[M] (I8)
     size_t total;
@@ -55,7 +57,6 @@ __host__ __device__ inline FilterLayout filter_layout(int M, int L, int D, int p
     FilterLayout f;
     f.M = M; f.L = L; f.D = D;
     f.rowwords = ((D + 63) / 64) * 2;
-    f.nchunks = f.rowwords / 2;
     f.kind = (planes == TSR_PLANES_INT8X2 || planes == TSR_PLANES_INT8X3) ? 1 : 0;
     f.P = planes == TSR_PLANES_INT8X3 ? 3 : 2;
     if (f.kind == 1 && f.P * L > DT_NT_MAX) { f.kind = 0; f.P = 2; }   // planes of a template must share a tile
@@ -68,11 +69,16 @@ __host__ __device__ inline FilterLayout filter_layout(int M, int L, int D, int p
     f.ntiles = (M * f.vpt + tptv - 1) / tptv;
     int msub = 512 / f.NT;
     f.msub = msub > DT_MSUB_MAX ? DT_MSUB_MAX : msub;
-    f.tile_bytes = f.kind ? (size_t)f.NT * 64 : (size_t)2 * f.NT * 128;
+    f.fps = f.kind ? 128 : 64;
+    f.nchunks = (D + f.fps - 1) / f.fps;
+    f.tile_bytes = f.kind ? (size_t)f.NT * 128 : (size_t)2 * f.NT * 128;
     f.hdr_bytes = 128 + (((size_t)M * 4 + 127) & ~(size_t)127);
     f.total = f.hdr_bytes + (size_t)f.ntiles * f.nchunks * f.tile_bytes;
-    size_t stage = (size_t)f.msub * (f.kind ? 8192 : 16384) + f.tile_bytes;
-    int ns = (int)((160 * 1024) / stage);
+    // pipeline depth from what is left of 227 KB after the epilogue staging and accumulators
+    const size_t stage = (size_t)f.msub * 16384 + f.tile_bytes;
+    const size_t fixed = ((128 * (DT_TAU_CHUNK + 1) * 4 + 127) & ~(size_t)127) +
+                         ((((size_t)f.msub * 128 + L) * f.tptv * 4 + 127) & ~(size_t)127) + 512;
+    int ns = (int)((227 * 1024 - fixed) / stage);
     f.nstage = ns < 2 ? 2 : (ns > DT_MAX_STAGES ? DT_MAX_STAGES : ns);
     return f;
 }
@@ -110,15 +116,15 @@ __global__ void prepare_filters_kernel(const float* __restrict__ LF, uint8_t* __
     const uint32_t fmt = pick_format(hdr[1], plane_format == TSR_PLANES_BF16 ? 1 : (plane_format == TSR_PLANES_FP16 ? 2 : 0));
     const uint32_t* tmaxbits = hdr + 32;
     uint8_t* tiles = blob + f.hdr_bytes;
-    const size_t nelem = (size_t)f.ntiles * f.nchunks * f.NT * 64;
+    const size_t nelem = (size_t)f.ntiles * f.nchunks * f.NT * f.fps;
     const float qmax = f.P == 3 ? 8355711.f : 32639.f;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < nelem; i += (size_t)gridDim.x * blockDim.x) {
-        const int dd = (int)(i & 63);                 // feature within the chunk
-        size_t r = i >> 6;
+        const int dd = (int)(i % f.fps);              // feature within the chunk
+        size_t r = i / f.fps;
         const int n = (int)(r % f.NT); r /= f.NT;
         const int c = (int)(r % f.nchunks);
         const int nt = (int)(r / f.nchunks);
-        const int d = c * 64 + dd;
+        const int d = c * f.fps + dd;
         const int vl = n / f.L, tau = n - vl * f.L;
         const int v = nt * f.tptv + vl;
         const int m = v / f.vpt, plane = v - m * f.vpt;
@@ -163,19 +169,25 @@ struct DetectArgs {
     int units_per_ntile;
     int steps_per_unit;
     FilterLayout f;
+    long long* trace;   // optional debug timeline of CTA 0: [stage iteration][8] clock64 stamps
 };
+#define DT_TRACE_ITERS 256
+#define DT_TRACE(itv, slot)                                                                          \
+    do {                                                                                             \
+        if (A.trace && blockIdx.x == 0 && (itv) < DT_TRACE_ITERS && lane == 0) A.trace[(itv) * 8 + (slot)] = clock64(); \
+    } while (0)
 
 struct DetectSmem {
     uint32_t b, stage, outacc, bars, stage_bytes, a_bytes, a_sub, total;
 };
 __host__ __device__ inline DetectSmem detect_smem_layout(const FilterLayout& f) {
     DetectSmem S;
-    S.a_sub = f.kind ? 8192 : 16384;
+    S.a_sub = 16384;   // 128 rows x 128 bytes per sub-tile and stage for both kinds
     S.a_bytes = f.msub * S.a_sub;
     S.stage_bytes = S.a_bytes + (uint32_t)f.tile_bytes;
     S.b = S.a_bytes;                                   // within a stage
     S.stage = f.nstage * S.stage_bytes;                // epilogue staging [128][TC+1] words
-    S.outacc = S.stage + ((128 * ((f.L < DT_TAU_CHUNK ? f.L : DT_TAU_CHUNK) + 1) * 4 + 127) & ~127u);
+    S.outacc = S.stage + ((128 * (DT_TAU_CHUNK + 1) * 4 + 127) & ~127u);
     S.bars = S.outacc + (((f.msub * 128 + f.L) * f.tptv * 4 + 127) & ~127u);
     S.total = S.bars + 256;
     return S;
@@ -224,15 +236,15 @@ __global__ void __launch_bounds__(DT_THREADS, 1) detect_tc_kernel(DetectArgs A) 
         for (int s = 0; s < DT_MSUB_MAX; ++s) mbar_init(&tempty_bar[s], 128);
         mbar_fence_init();
     }
-    if (warp == 4) tmem_alloc<512>(tmem_ptr);
+    if (warp == 17) tmem_alloc<512>(tmem_ptr);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
 
-    if (warp >= 6) {
+    if (warp >= 1 && warp <= 12) {
         // ============================ frame-bit expanders ============================
-        const int pr = threadIdx.x - 192;             // row within the step
+        const int pr = threadIdx.x - 32;              // row within the step
         const int sub = pr >> 7, r = pr & 127;
         const uint32_t one = fmt_one(fmt);
         uint32_t it = 0;                               // global chunk counter (pipeline position)
@@ -246,18 +258,31 @@ __global__ void __launch_bounds__(DT_THREADS, 1) detect_tc_kernel(DetectArgs A) 
                 const long long g = o0 + (long long)step * step_rows + pr;
                 const bool live = pr < step_rows && g < in_end;
                 const uint2* src = reinterpret_cast<const uint2*>(A.bits + (live ? g : 0) * f.rowwords);
-                uint2 w = live ? __ldg(src) : make_uint2(0u, 0u);
+                const int nw2 = f.rowwords >> 1;                  // 64-bit words per row
+                const int w2ps = I8 ? 2 : 1;                      // 64-bit words per stage
+                auto fetch = [&](int c, uint2& lo, uint2& hi) {
+                    lo = (live && c * w2ps < nw2) ? __ldg(src + c * w2ps) : make_uint2(0u, 0u);
+                    hi = (I8 && live && c * w2ps + 1 < nw2) ? __ldg(src + c * w2ps + 1) : make_uint2(0u, 0u);
+                };
+                uint2 w, wh;
+                fetch(0, w, wh);
                 for (int c = 0; c < nchunks; ++c, ++it) {
-                    uint2 wn = (live && c + 1 < nchunks) ? __ldg(src + c + 1) : make_uint2(0u, 0u);   // prefetch
-                    mbar_wait(&empty_bar[stage], ph ^ 1);
+                    uint2 wn, wnh;
+                    fetch(c + 1 < nchunks ? c + 1 : c, wn, wnh);   // prefetch the next chunk's bits
+                    mbar_wait_relaxed(&empty_bar[stage], ph ^ 1);
+                    if (warp == 1) DT_TRACE(it, 0);
                     if (pr < step_rows) {
                         uint8_t* dst = smem + stage * S.stage_bytes + sub * S.a_sub + r * 16;
-                        if (I8) {
+                        if (I8) {   // 128 features -> 8 k-groups of 16 uint8
                             *reinterpret_cast<uint4*>(dst) = expand16_u8(w.x & 0xFFFF);
                             *reinterpret_cast<uint4*>(dst + 2048) = expand16_u8(w.x >> 16);
                             *reinterpret_cast<uint4*>(dst + 4096) = expand16_u8(w.y & 0xFFFF);
                             *reinterpret_cast<uint4*>(dst + 6144) = expand16_u8(w.y >> 16);
-                        } else {
+                            *reinterpret_cast<uint4*>(dst + 8192) = expand16_u8(wh.x & 0xFFFF);
+                            *reinterpret_cast<uint4*>(dst + 10240) = expand16_u8(wh.x >> 16);
+                            *reinterpret_cast<uint4*>(dst + 12288) = expand16_u8(wh.y & 0xFFFF);
+                            *reinterpret_cast<uint4*>(dst + 14336) = expand16_u8(wh.y >> 16);
+                        } else {    // 64 features -> 8 k-groups of 8 16-bit floats
 #pragma unroll
                             for (int kg = 0; kg < 4; ++kg)
                                 *reinterpret_cast<uint4*>(dst + kg * 2048) = expand_byte((w.x >> (8 * kg)) & 0xFF, one);
@@ -268,21 +293,24 @@ __global__ void __launch_bounds__(DT_THREADS, 1) detect_tc_kernel(DetectArgs A) 
                     }
                     fence_proxy_async_smem();
                     mbar_arrive(&full_bar[stage]);
-                    w = wn;
+                    if (warp == 1) DT_TRACE(it, 1);
+                    w = wn; wh = wnh;
                     if (++stage == nstage) { stage = 0; ph ^= 1; }
                 }
             }
         }
-    } else if (warp == 5) {
+    } else if (warp == 0) {
         // ============================ filter-tile loader ============================
         if (lane == 0) {
             int stage = 0; uint32_t ph = 0;
+            uint32_t it = 0;
             for (long long u = blockIdx.x; u < nunits; u += gridDim.x) {
                 const int nt = (int)(u % f.ntiles);
                 const uint8_t* src = A.blob + f.hdr_bytes + (size_t)nt * nchunks * f.tile_bytes;
                 for (int step = 0; step < A.steps_per_unit; ++step)
-                    for (int c = 0; c < nchunks; ++c) {
-                        mbar_wait(&empty_bar[stage], ph ^ 1);
+                    for (int c = 0; c < nchunks; ++c, ++it) {
+                        mbar_wait_relaxed(&empty_bar[stage], ph ^ 1);
+                        DT_TRACE(it, 2);
                         mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)f.tile_bytes);
                         bulk_g2s(smem + stage * S.stage_bytes + S.b, src + (size_t)c * f.tile_bytes, (uint32_t)f.tile_bytes,
                                  &full_bar[stage]);
@@ -290,7 +318,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) detect_tc_kernel(DetectArgs A) 
                     }
             }
         }
-    } else if (warp == 4) {
+    } else if (warp == 17) {
         // ================================ MMA issuer ================================
         // warp-uniform loop, one elected lane issues (see umma_f16_elect)
         const uint32_t idesc = I8 ? ((2u << 4) | (0u << 7) | (1u << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24))
@@ -299,11 +327,12 @@ __global__ void __launch_bounds__(DT_THREADS, 1) detect_tc_kernel(DetectArgs A) 
         const uint64_t a_hi = ((uint64_t)desc_hi << 32) | ((uint64_t)(2048 >> 4) << 16);   // LBO = 2048 B
         const uint64_t b_hi = ((uint64_t)desc_hi << 32) | ((uint64_t)NT << 16);            // LBO = NT*16 B
         int stage = 0; uint32_t ph = 0;
-        uint32_t stepno = 0;
+        uint32_t stepno = 0, it = 0;
         for (long long u = blockIdx.x; u < nunits; u += gridDim.x)
             for (int step = 0; step < A.steps_per_unit; ++step, ++stepno) {
-                for (int c = 0; c < nchunks; ++c) {
+                for (int c = 0; c < nchunks; ++c, ++it) {
                     mbar_wait(&full_bar[stage], ph);
+                    DT_TRACE(it, 4);
                     tc_fence_after();
                     const uint32_t abase = smem_u32(smem + stage * S.stage_bytes) >> 4;
                     const uint32_t bbase = abase + (S.b >> 4);
@@ -315,8 +344,8 @@ __global__ void __launch_bounds__(DT_THREADS, 1) detect_tc_kernel(DetectArgs A) 
                         const uint32_t d_tmem = tmem_base + sub * NT;
                         if (I8) {
 #pragma unroll
-                            for (int ks = 0; ks < 2; ++ks) {   // K = 32 per MMA: 2 x 16-byte k-groups
-                                const uint64_t adesc = a_hi | (uint64_t)(abase + sub * (8192 >> 4) + ks * (4096 >> 4));
+                            for (int ks = 0; ks < 4; ++ks) {   // K = 32 per MMA: 2 x 16-byte k-groups, 128 features per stage
+                                const uint64_t adesc = a_hi | (uint64_t)(abase + sub * (16384 >> 4) + ks * (4096 >> 4));
                                 const uint64_t bdesc = b_hi | (uint64_t)(bbase + ks * 2 * NT);
                                 umma_i8_elect(d_tmem, adesc, bdesc, idesc, (c | ks) != 0 ? 1u : 0u);
                             }
@@ -332,6 +361,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) detect_tc_kernel(DetectArgs A) 
                         }
                     }
                     umma_commit_elect(&empty_bar[stage]);
+                    DT_TRACE(it, 5);
                     if (++stage == nstage) { stage = 0; ph ^= 1; }
                 }
                 umma_commit_elect(tfull_bar);
@@ -340,12 +370,13 @@ __global__ void __launch_bounds__(DT_THREADS, 1) detect_tc_kernel(DetectArgs A) 
         // ================================= epilogue =================================
         // accumulators are fp32 (F16 kind) or int32 (I8 kind); staging and diagonal sums use the same type
         typedef typename std::conditional<I8, int, float>::type acc_t;
-        acc_t* stg = reinterpret_cast<acc_t*>(smem + S.stage);       // [128][TC+1]
+        constexpr int PITCH = DT_TAU_CHUNK + 1;                      // odd word pitch: conflict-free rows and diagonals
+        acc_t* stg = reinterpret_cast<acc_t*>(smem + S.stage);       // [128][PITCH]
         acc_t* outacc = reinterpret_cast<acc_t*>(smem + S.outacc);   // [step_rows + L - 1][tptv]
         const float* scale = reinterpret_cast<const float*>(A.blob + 128);
-        const int e = threadIdx.x;                                    // 0..127 == TMEM lane
+        const int quad = warp & 3;                                    // TMEM lane quadrant of this warp
+        const int e = quad * 32 + lane;                               // 0..127 == TMEM lane == row of the sub-tile
         const int TC = L < DT_TAU_CHUNK ? L : DT_TAU_CHUNK;
-        const int pitch = TC + 1;
         const int nacc = (step_rows + L - 1) * tptv;
         const int vpt = f.vpt, tpt = tptv / vpt;
         uint32_t stepno = 0;
@@ -357,36 +388,70 @@ __global__ void __launch_bounds__(DT_THREADS, 1) detect_tc_kernel(DetectArgs A) 
             for (int i = e; i < nacc; i += 128) outacc[i] = 0;
             named_bar_sync(1, 128);
             for (int step = 0; step < A.steps_per_unit; ++step, ++stepno) {
-                mbar_wait(tfull_bar, stepno & 1);
+                mbar_wait_relaxed(tfull_bar, stepno & 1);
+                if (quad == 0) DT_TRACE(stepno, 6);
                 tc_fence_after();
                 for (int sub = 0; sub < msub; ++sub) {
-                    const uint32_t taddr = tmem_base + sub * NT + ((uint32_t)(warp * 32) << 16);
+                    const uint32_t taddr = tmem_base + sub * NT + ((uint32_t)(quad * 32) << 16);
                     for (int vl = 0; vl < tptv; ++vl) {
                         for (int c0 = 0; c0 < L; c0 += TC) {          // chunk of filter frames [c0, c0+cl)
                             const int cl = (L - c0) < TC ? (L - c0) : TC;
-                            for (int t0 = 0; t0 < cl; t0 += 8) {
-                                uint32_t v[8];
-                                tmem_ld8(taddr + vl * L + c0 + t0, v);
-                                tmem_ld_wait();
+                            // all TMEM loads of the chunk in flight at once, one wait; frames past the chunk
+                            // end are zeroed by select so that the sums below need no bounds checks
+                            uint32_t v[DT_TAU_CHUNK];
 #pragma unroll
-                                for (int i = 0; i < 8; ++i)
-                                    if (t0 + i < cl) reinterpret_cast<uint32_t*>(stg)[e * pitch + t0 + i] = v[i];
+                            for (int t0 = 0; t0 < DT_TAU_CHUNK; t0 += 8) {
+                                if (t0 < cl) {                                     // warp-uniform
+                                    tmem_ld8(taddr + vl * L + c0 + t0, *reinterpret_cast<uint32_t(*)[8]>(&v[t0]));
+                                } else {
+#pragma unroll
+                                    for (int i = 0; i < 8; ++i) v[t0 + i] = 0u;
+                                }
+                            }
+                            tmem_ld_wait();
+                            {
+                                uint32_t* srow = reinterpret_cast<uint32_t*>(stg) + e * PITCH;
+#pragma unroll
+                                for (int i = 0; i < DT_TAU_CHUNK; ++i) srow[i] = i < cl ? v[i] : 0u;
                             }
                             if (vl == tptv - 1 && c0 + cl >= L) {   // accumulator drained: hand it back to the MMA warp
                                 tc_fence_before();
                                 mbar_arrive(&tempty_bar[sub]);
                             }
                             named_bar_sync(1, 128);
-                            // out index q <-> row r0 = q - (L-1) at tau = 0; this chunk adds tau in [c0, c0+cl)
-                            for (int q = e; q < 128 + L - 1; q += 128) {
-                                const int r0 = q - (L - 1);
-                                int tlo = -r0 > c0 ? -r0 : c0;
-                                int thi = (128 - r0) < (c0 + cl) ? (128 - r0) : (c0 + cl);
-                                if (tlo < thi) {
-                                    acc_t part = 0;
-                                    for (int tau = tlo; tau < thi; ++tau) part += stg[(r0 + tau) * pitch + (tau - c0)];
-                                    outacc[(sub * 128 + q) * tptv + vl] += part;
+                            // Diagonal sums.  Thread e owns the out indices q_k = e + 128k, k = 0,1,2 (k = 2 only
+                            // for L > 129).  q_k reads rows e + 128k - (L-1) + tau, inside [0,128) for exactly
+                            // one k per tau: k = 0 for tau >= ts = (L-1)-e, k = 1 for ts-128 <= tau < ts, else 2.
+                            // Every tau costs one unconditional load from one of three rows 128 apart (rows
+                            // outside the tile are other shared memory and are discarded by select); tau ascends
+                            // within each sum => fixed summation order.  Straight-line code, no branches.
+                            {
+                                const int ts = (L - 1) - e - c0;                      // chunk-relative switch point
+                                const acc_t* pA = stg + (e - (L - 1) + c0) * PITCH;   // row of q_0 at tr = 0
+                                acc_t s0 = 0, s1 = 0, s2 = 0;
+                                if (L <= 129 && cl == DT_TAU_CHUNK) {          // hot path: full 40-frame chunk
+#pragma unroll
+                                    for (int tr = 0; tr < DT_TAU_CHUNK; ++tr) {
+                                        const bool k0 = tr >= ts;
+                                        const acc_t x = pA[tr * (PITCH + 1) + (k0 ? 0 : 128 * PITCH)];
+                                        s0 += k0 ? x : (acc_t)0;
+                                        s1 += k0 ? (acc_t)0 : x;
+                                    }
+                                } else {                                        // short chunks / long templates
+#pragma unroll
+                                    for (int tr = 0; tr < DT_TAU_CHUNK; ++tr) {
+                                        const int tc = tr < cl ? tr : cl - 1;   // keep the address inside the tile
+                                        const bool live = tr < cl;
+                                        const bool k0 = tc >= ts, k2 = tc < ts - 128;
+                                        const acc_t x = pA[tc * (PITCH + 1) + (k0 ? 0 : (k2 ? 256 : 128)) * PITCH];
+                                        s0 += (live && k0) ? x : (acc_t)0;
+                                        s1 += (live && !k0 && !k2) ? x : (acc_t)0;
+                                        s2 += (live && k2) ? x : (acc_t)0;
+                                    }
                                 }
+                                outacc[(sub * 128 + e) * tptv + vl] += s0;
+                                if (e < L - 1) outacc[(sub * 128 + e + 128) * tptv + vl] += s1;
+                                if (e + 128 < L - 1) outacc[(sub * 128 + e + 256) * tptv + vl] += s2;
                             }
                             named_bar_sync(1, 128);
                         }
@@ -427,13 +492,14 @@ __global__ void __launch_bounds__(DT_THREADS, 1) detect_tc_kernel(DetectArgs A) 
                     for (int i = keep + e; i < nacc; i += 128) outacc[i] = 0;
                     named_bar_sync(1, 128);
                 }
+                if (quad == 0) DT_TRACE(stepno, 7);
             }
         }
     }
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 4) {
+    if (warp == 17) {
         tc_fence_after();
         tmem_dealloc<512>(tmem_base);
     }
@@ -513,7 +579,12 @@ __global__ void detect_reduce_kernel(const float* __restrict__ scores, const flo
 
 using namespace tsr;
 
+static long long* g_detect_trace = nullptr;   // debug hook
+
 extern "C" {
+
+/* Debug only (not in the public header): device buffer of DT_TRACE_ITERS*8 int64 clock stamps. */
+void tsr_debug_set_detect_trace(long long* dev_buf) { g_detect_trace = dev_buf; }
 
 size_t tsr_filter_blob_bytes(int M, int L, int D, int plane_format) {
     if (M < 1 || L < 1 || L > 256 || D < 1 || plane_format < 0 || plane_format > 4) return 0;
@@ -565,6 +636,7 @@ int tsr_detect(const uint32_t* featbits, int B, int T, int D, int rowwords, cons
     DetectArgs A;
     A.bits = featbits; A.blob = (const uint8_t*)filter_blob; A.scores = scores; A.R = R; A.T = T;
     A.f = filter_layout(M, L, D, plane_format);
+    A.trace = g_detect_trace;
     DetectSmem S = detect_smem_layout(A.f);
     if (S.total > 227 * 1024) {
         set_error("tsr_detect: L=%d needs %u B of shared memory (> 227 KB)", L, S.total);

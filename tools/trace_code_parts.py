@@ -1,0 +1,28 @@
+"""Dump the per-tile timeline of CTA 0 of code_parts_tc_kernel (debug hook)."""
+import ctypes, os, sys
+import numpy as np, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from tsr_b200 import ops, synth, _lib
+lib = _lib.lib()
+lp, lip = synth.parts(100)
+parts = ops.PartsModel(lp, lip)
+bits = ops.pack_edges(torch.from_numpy(synth.fast_edge_batch(1024)).cuda())
+ops.code_parts(bits, parts, 12)
+torch.cuda.synchronize()
+flags = int(sys.argv[1]) if len(sys.argv) > 1 else 0
+lib.tsr_debug_set_code_flags(flags)
+print("debug flags", flags)
+buf = torch.zeros(96 * 8, dtype=torch.int64, device="cuda")
+lib.tsr_debug_set_code_trace.argtypes = [ctypes.c_void_p]
+lib.tsr_debug_set_code_trace(buf.data_ptr())
+ops.code_parts(bits, parts, 12)
+torch.cuda.synchronize()
+lib.tsr_debug_set_code_trace(None)
+t = buf.cpu().numpy().reshape(96, 8)
+t0 = t[t > 0].min()
+names = ["prod:empty_ok", "prod:arrived", "mma:full_ok", "mma:tempty_ok", "mma:issued", "epi:tfull_ok", "epi:tmem_free", "epi:done"]
+print("tile " + " ".join("%14s" % n for n in names))
+for i in range(30, 36):
+    print("%4d " % i + " ".join("%14d" % (x - t0 if x else -1) for x in t[i]))
+d = np.diff(t[8:90, 4])
+print("mean cycles between consecutive tiles' MMA issue:", d.mean())

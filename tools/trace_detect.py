@@ -1,0 +1,30 @@
+"""Dump the per-stage timeline of CTA 0 of detect_tc_kernel (debug hook)."""
+import ctypes, os, sys
+import numpy as np, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from tsr_b200 import ops, synth, _lib
+lib = _lib.lib()
+planes = int(sys.argv[1]) if len(sys.argv) > 1 else 4
+Tm, bgd = synth.templates(M=32, L=40, Fd=36, Kd=100)
+W, c = synth.linear_filters(Tm, bgd)
+bank = ops.FilterBank(W, cs=c, planes=planes)
+rs = np.random.RandomState(0)
+fb = torch.from_numpy(rs.randint(-2**31, 2**31 - 1, (1024, 296, 114), dtype=np.int64).astype(np.int32)).cuda()
+fb &= torch.from_numpy(rs.randint(-2**31, 2**31 - 1, (1024, 296, 114), dtype=np.int64).astype(np.int32)).cuda()
+ops.detect(fb, bank)
+torch.cuda.synchronize()
+buf = torch.zeros(256 * 8, dtype=torch.int64, device="cuda")
+lib.tsr_debug_set_detect_trace.argtypes = [ctypes.c_void_p]
+lib.tsr_debug_set_detect_trace(buf.data_ptr())
+ops.detect(fb, bank)
+torch.cuda.synchronize()
+lib.tsr_debug_set_detect_trace(None)
+t = buf.cpu().numpy().reshape(256, 8)
+t0 = t[t > 0].min()
+names = ["exp:empty_ok", "exp:arrived", "ld:empty_ok", "-", "mma:full_ok", "mma:commit", "epi:tfull", "epi:done"]
+print("planes", planes)
+print("iter " + " ".join("%13s" % n for n in names))
+for i in list(range(0, 4)) + list(range(60, 76)):
+    print("%4d " % i + " ".join("%13d" % (x - t0 if x else -1) for x in t[i]))
+d = np.diff(t[60:250, 5])
+print("mean cycles between consecutive stage commits:", d.mean())
