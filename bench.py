@@ -43,6 +43,17 @@ BYTES_SPREAD_EDGES = 2.0 * T_FRAMES * F_BANDS                           # 24 000
 BYTES_SPREAD_CODES = (1 + 4 * 4) * FO * TO                              # 181 152 B  (1 B code + 16 B bitset per location)
 
 
+def ncu_traffic(kernel, batch):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture
+    (profiles/ncu_summary.json), or None when no capture exists for this kernel / batch size."""
+    p = os.path.join(ROOT, "profiles", "ncu_summary.json")
+    try:
+        d = json.load(open(p)).get(kernel, {})
+        return d.get("dram_bytes") if d.get("batch") == batch else None
+    except (OSError, ValueError):
+        return None
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -53,41 +64,48 @@ def measured_peaks():
 
 # --------------------------------------------------------------------------- clocks sampler
 class ClockSampler:
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """Samples SM clock and throttle reasons DURING the timed region (NVML, every ~2 ms; falls back
+    to `nvidia-smi -lms` when pynvml is unavailable)."""
+    NAMES = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4,
+             "hw_power_brake_slowdown": 0x80}
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.sm, self.reasons, self.stop_flag, self.thread, self.max_mhz = index, [], set(), False, None, None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
-            self.thread.start()
-        except OSError:
-            self.proc = None
+            import pynvml
+            pynvml.nvmlInit()
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(visible.split(",")[self.index]) if visible and visible.split(",")[self.index].isdigit() else self.index
+            h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            def loop():
+                while not self.stop_flag:
+                    try:
+                        self.sm.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                        r = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h) if hasattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons") \
+                            else pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                        for n, bit in self.NAMES.items():
+                            if r & bit:
+                                self.reasons.add(n)
+                    except Exception:
+                        pass
+                    time.sleep(0.002)
+            self.thread = threading.Thread(target=loop, daemon=True)
+            self.thread.start()
+        except Exception as e:   # noqa: BLE001
+            self.err = str(e)
+            self.thread = None
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+        if self.thread is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable: %s" % getattr(self, "err", "?")]}
+        self.stop_flag = True
+        self.thread.join(timeout=2)
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.sm)}
 
 
 # ------------------------------------------------------------------------------ CPU arm
@@ -248,6 +266,7 @@ def run_native(args):
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
+    clocks = sampler.stop() if rank == 0 else None          # clocks cover exactly the timed region
     step_ms = [e[0].elapsed_time(e[5]) for e in all_evs]
     stage_ms = [float(np.mean([e[i].elapsed_time(e[i + 1]) for e in all_evs])) for i in range(5)]
     total_ms = float(sum(step_ms))
@@ -292,7 +311,6 @@ def run_native(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_s = float(t.item())
-    clocks = sampler.stop() if rank == 0 else None
 
     if rank == 0:
         peaks = measured_peaks()
@@ -317,7 +335,7 @@ def run_native(args):
             "vs_baseline": None, "dtype": "bf16 hi+lo x {0,1} bf16, fp32 accumulate (u8 bit-packed for spreading)",
             "data": "synthetic", "config": workload_config(B),
             "roofline": {"kernel": "detect_tc_kernel", "bound": "tensor", "achieved": det_tf, "peak": peaks["tf_sustained"],
-                         "unit": "TFLOP/s", "frac": det_tf / peaks["tf_sustained"], "traffic": None,
+                         "unit": "TFLOP/s", "frac": det_tf / peaks["tf_sustained"], "traffic": ncu_traffic("detect_tc_kernel", B),
                          "peak_source": peaks["src"] + " bf16_tflops_sustained (kernel timed inside the step)",
                          "algorithmic_flop_per_launch": FLOP_DETECT * B,
                          "note": "algorithmic FLOPs count the single-pass contraction; the bf16 hi+lo split issues 2x"},

@@ -64,22 +64,30 @@ __host__ __device__ inline FilterLayout filter_layout(int M, int L, int D, int p
     int tptv = (DT_NT_MAX / (f.vpt * L)) * f.vpt;
     if (tptv < f.vpt) tptv = f.vpt;
     if (tptv > M * f.vpt) tptv = M * f.vpt;
-    f.tptv = tptv;
-    f.NT = (tptv * L + 15) & ~15;
-    f.ntiles = (M * f.vpt + tptv - 1) / tptv;
-    int msub = 512 / f.NT;
-    f.msub = msub > DT_MSUB_MAX ? DT_MSUB_MAX : msub;
     f.fps = f.kind ? 128 : 64;
     f.nchunks = (D + f.fps - 1) / f.fps;
-    f.tile_bytes = f.kind ? (size_t)f.NT * 128 : (size_t)2 * f.NT * 128;
     f.hdr_bytes = 128 + (((size_t)M * 4 + 127) & ~(size_t)127);
+    int msub_cap = DT_MSUB_MAX;
+    for (;;) {   // shrink rows per step, then templates per tile, until two pipeline stages fit in 227 KB
+        f.tptv = tptv;
+        f.NT = (tptv * L + 15) & ~15;
+        f.ntiles = (M * f.vpt + tptv - 1) / tptv;
+        int msub = 512 / f.NT;
+        f.msub = msub > msub_cap ? msub_cap : msub;
+        f.tile_bytes = f.kind ? (size_t)f.NT * 128 : (size_t)2 * f.NT * 128;
+        const size_t stage = (size_t)f.msub * 16384 + f.tile_bytes;
+        const size_t fixed = (((128 + DT_TAU_CHUNK) * (DT_TAU_CHUNK + 1) * 4 + 127) & ~(size_t)127) +
+                             ((((size_t)f.msub * 128 + L) * f.tptv * 4 + 127) & ~(size_t)127) + 512;
+        const long long avail = 227 * 1024 - (long long)fixed;
+        int ns = avail > 0 ? (int)(avail / (long long)stage) : 0;
+        if (ns >= 2 || (f.msub == 1 && tptv == f.vpt)) {
+            f.nstage = ns < 2 ? 2 : (ns > DT_MAX_STAGES ? DT_MAX_STAGES : ns);
+            break;
+        }
+        if (f.msub > 1) msub_cap = f.msub - 1;
+        else tptv -= f.vpt;
+    }
     f.total = f.hdr_bytes + (size_t)f.ntiles * f.nchunks * f.tile_bytes;
-    // pipeline depth from what is left of 227 KB after the epilogue staging and accumulators
-    const size_t stage = (size_t)f.msub * 16384 + f.tile_bytes;
-    const size_t fixed = ((128 * (DT_TAU_CHUNK + 1) * 4 + 127) & ~(size_t)127) +
-                         ((((size_t)f.msub * 128 + L) * f.tptv * 4 + 127) & ~(size_t)127) + 512;
-    int ns = (int)((227 * 1024 - fixed) / stage);
-    f.nstage = ns < 2 ? 2 : (ns > DT_MAX_STAGES ? DT_MAX_STAGES : ns);
     return f;
 }
 
@@ -187,7 +195,7 @@ __host__ __device__ inline DetectSmem detect_smem_layout(const FilterLayout& f) 
     S.stage_bytes = S.a_bytes + (uint32_t)f.tile_bytes;
     S.b = S.a_bytes;                                   // within a stage
     S.stage = f.nstage * S.stage_bytes;                // epilogue staging [128][TC+1] words
-    S.outacc = S.stage + ((128 * (DT_TAU_CHUNK + 1) * 4 + 127) & ~127u);
+    S.outacc = S.stage + (((128 + DT_TAU_CHUNK) * (DT_TAU_CHUNK + 1) * 4 + 127) & ~127u);
     S.bars = S.outacc + (((f.msub * 128 + f.L) * f.tptv * 4 + 127) & ~127u);
     S.total = S.bars + 256;
     return S;
@@ -231,7 +239,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) detect_tc_kernel(DetectArgs A) 
     const long long nunits = (long long)f.ntiles * A.units_per_ntile;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < DT_MAX_STAGES; ++s) { mbar_init(&full_bar[s], DT_PRODUCERS + 1); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < DT_MAX_STAGES; ++s) { mbar_init(&full_bar[s], DT_PRODUCERS / 2 + 1); mbar_init(&empty_bar[s], 1); }
         mbar_init(tfull_bar, 1);
         for (int s = 0; s < DT_MSUB_MAX; ++s) mbar_init(&tempty_bar[s], 128);
         mbar_fence_init();
@@ -244,10 +252,16 @@ __global__ void __launch_bounds__(DT_THREADS, 1) detect_tc_kernel(DetectArgs A) 
 
     if (warp >= 1 && warp <= 12) {
         // ============================ frame-bit expanders ============================
-        const int pr = threadIdx.x - 32;              // row within the step
-        const int sub = pr >> 7, r = pr & 127;
+        // Two groups of 6 warps take alternate pipeline stages (group = stage parity); a thread expands
+        // two rows of the 384-row step per stage it owns.  The proxy fence + mbarrier arrive that end a
+        // stage cost several hundred cycles of latency; alternating groups overlaps them with the other
+        // group's expansion work.
+        const int grp = (warp - 1) / 6;                  // 0 or 1
+        const int tg = threadIdx.x - 32 - grp * 192;     // 0..191 within the group
         const uint32_t one = fmt_one(fmt);
-        uint32_t it = 0;                               // global chunk counter (pipeline position)
+        const int nw2 = f.rowwords >> 1;                  // 64-bit words per row
+        const int w2ps = I8 ? 2 : 1;                      // 64-bit words per stage
+        uint32_t it = 0;                                  // global chunk counter (pipeline position)
         int stage = 0; uint32_t ph = 0;
         for (long long u = blockIdx.x; u < nunits; u += gridDim.x) {
             const long long ur = u / f.ntiles;
@@ -255,46 +269,53 @@ __global__ void __launch_bounds__(DT_THREADS, 1) detect_tc_kernel(DetectArgs A) 
             long long o1 = o0 + A.rows_per_unit; if (o1 > A.R) o1 = A.R;
             long long in_end = o1 + L - 1; if (in_end > A.R) in_end = A.R;
             for (int step = 0; step < A.steps_per_unit; ++step) {
-                const long long g = o0 + (long long)step * step_rows + pr;
-                const bool live = pr < step_rows && g < in_end;
-                const uint2* src = reinterpret_cast<const uint2*>(A.bits + (live ? g : 0) * f.rowwords);
-                const int nw2 = f.rowwords >> 1;                  // 64-bit words per row
-                const int w2ps = I8 ? 2 : 1;                      // 64-bit words per stage
-                auto fetch = [&](int c, uint2& lo, uint2& hi) {
-                    lo = (live && c * w2ps < nw2) ? __ldg(src + c * w2ps) : make_uint2(0u, 0u);
-                    hi = (I8 && live && c * w2ps + 1 < nw2) ? __ldg(src + c * w2ps + 1) : make_uint2(0u, 0u);
-                };
-                uint2 w, wh;
-                fetch(0, w, wh);
+                const uint2* src[2];
+                bool live[2];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int pr = tg + h * 192;                                   // row within the step
+                    const long long g = o0 + (long long)step * step_rows + pr;
+                    live[h] = pr < step_rows && g < in_end;
+                    src[h] = reinterpret_cast<const uint2*>(A.bits + (live[h] ? g : 0) * f.rowwords);
+                }
                 for (int c = 0; c < nchunks; ++c, ++it) {
-                    uint2 wn, wnh;
-                    fetch(c + 1 < nchunks ? c + 1 : c, wn, wnh);   // prefetch the next chunk's bits
-                    mbar_wait_relaxed(&empty_bar[stage], ph ^ 1);
-                    if (warp == 1) DT_TRACE(it, 0);
-                    if (pr < step_rows) {
-                        uint8_t* dst = smem + stage * S.stage_bytes + sub * S.a_sub + r * 16;
-                        if (I8) {   // 128 features -> 8 k-groups of 16 uint8
-                            *reinterpret_cast<uint4*>(dst) = expand16_u8(w.x & 0xFFFF);
-                            *reinterpret_cast<uint4*>(dst + 2048) = expand16_u8(w.x >> 16);
-                            *reinterpret_cast<uint4*>(dst + 4096) = expand16_u8(w.y & 0xFFFF);
-                            *reinterpret_cast<uint4*>(dst + 6144) = expand16_u8(w.y >> 16);
-                            *reinterpret_cast<uint4*>(dst + 8192) = expand16_u8(wh.x & 0xFFFF);
-                            *reinterpret_cast<uint4*>(dst + 10240) = expand16_u8(wh.x >> 16);
-                            *reinterpret_cast<uint4*>(dst + 12288) = expand16_u8(wh.y & 0xFFFF);
-                            *reinterpret_cast<uint4*>(dst + 14336) = expand16_u8(wh.y >> 16);
-                        } else {    // 64 features -> 8 k-groups of 8 16-bit floats
+                    if ((int)(it & 1) == grp) {
+                        uint2 w[2], wh[2];
 #pragma unroll
-                            for (int kg = 0; kg < 4; ++kg)
-                                *reinterpret_cast<uint4*>(dst + kg * 2048) = expand_byte((w.x >> (8 * kg)) & 0xFF, one);
-#pragma unroll
-                            for (int kg = 0; kg < 4; ++kg)
-                                *reinterpret_cast<uint4*>(dst + (kg + 4) * 2048) = expand_byte((w.y >> (8 * kg)) & 0xFF, one);
+                        for (int h = 0; h < 2; ++h) {
+                            w[h] = (live[h] && c * w2ps < nw2) ? __ldg(src[h] + c * w2ps) : make_uint2(0u, 0u);
+                            wh[h] = (I8 && live[h] && c * w2ps + 1 < nw2) ? __ldg(src[h] + c * w2ps + 1) : make_uint2(0u, 0u);
                         }
+                        mbar_wait_relaxed(&empty_bar[stage], ph ^ 1);
+                        if (warp == 1 || warp == 7) DT_TRACE(it, 0);
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            const int pr = tg + h * 192;
+                            if (pr < step_rows) {
+                                uint8_t* dst = smem + stage * S.stage_bytes + (pr >> 7) * S.a_sub + (pr & 127) * 16;
+                                if (I8) {   // 128 features -> 8 k-groups of 16 uint8
+                                    *reinterpret_cast<uint4*>(dst) = expand16_u8(w[h].x & 0xFFFF);
+                                    *reinterpret_cast<uint4*>(dst + 2048) = expand16_u8(w[h].x >> 16);
+                                    *reinterpret_cast<uint4*>(dst + 4096) = expand16_u8(w[h].y & 0xFFFF);
+                                    *reinterpret_cast<uint4*>(dst + 6144) = expand16_u8(w[h].y >> 16);
+                                    *reinterpret_cast<uint4*>(dst + 8192) = expand16_u8(wh[h].x & 0xFFFF);
+                                    *reinterpret_cast<uint4*>(dst + 10240) = expand16_u8(wh[h].x >> 16);
+                                    *reinterpret_cast<uint4*>(dst + 12288) = expand16_u8(wh[h].y & 0xFFFF);
+                                    *reinterpret_cast<uint4*>(dst + 14336) = expand16_u8(wh[h].y >> 16);
+                                } else {    // 64 features -> 8 k-groups of 8 16-bit floats
+#pragma unroll
+                                    for (int kg = 0; kg < 4; ++kg)
+                                        *reinterpret_cast<uint4*>(dst + kg * 2048) = expand_byte((w[h].x >> (8 * kg)) & 0xFF, one);
+#pragma unroll
+                                    for (int kg = 0; kg < 4; ++kg)
+                                        *reinterpret_cast<uint4*>(dst + (kg + 4) * 2048) = expand_byte((w[h].y >> (8 * kg)) & 0xFF, one);
+                                }
+                            }
+                        }
+                        fence_proxy_async_smem();
+                        mbar_arrive(&full_bar[stage]);
+                        if (warp == 1 || warp == 7) DT_TRACE(it, 1);
                     }
-                    fence_proxy_async_smem();
-                    mbar_arrive(&full_bar[stage]);
-                    if (warp == 1) DT_TRACE(it, 1);
-                    w = wn; wh = wnh;
                     if (++stage == nstage) { stage = 0; ph ^= 1; }
                 }
             }
@@ -371,7 +392,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) detect_tc_kernel(DetectArgs A) 
         // accumulators are fp32 (F16 kind) or int32 (I8 kind); staging and diagonal sums use the same type
         typedef typename std::conditional<I8, int, float>::type acc_t;
         constexpr int PITCH = DT_TAU_CHUNK + 1;                      // odd word pitch: conflict-free rows and diagonals
-        acc_t* stg = reinterpret_cast<acc_t*>(smem + S.stage);       // [128][PITCH]
+        acc_t* stg = reinterpret_cast<acc_t*>(smem + S.stage);       // skewed staging [128 + TC - 1][PITCH]
         acc_t* outacc = reinterpret_cast<acc_t*>(smem + S.outacc);   // [step_rows + L - 1][tptv]
         const float* scale = reinterpret_cast<const float*>(A.blob + 128);
         const int quad = warp & 3;                                    // TMEM lane quadrant of this warp
@@ -379,6 +400,14 @@ __global__ void __launch_bounds__(DT_THREADS, 1) detect_tc_kernel(DetectArgs A) 
         const int TC = L < DT_TAU_CHUNK ? L : DT_TAU_CHUNK;
         const int nacc = (step_rows + L - 1) * tptv;
         const int vpt = f.vpt, tpt = tptv / vpt;
+        // Skewed staging: thread e writes C[e][tau] to row q' = e - tr + (DT_TAU_CHUNK-1), column tr, so
+        // that a diagonal of the tile becomes a ROW of the staging buffer and the diagonal sum a plain row
+        // sum (one load + one add per element, no masks).  Cells no (e,tr) maps to -- the two triangles at
+        // the top and bottom -- are zeroed once here and never written again.
+        constexpr int SROWS = 128 + DT_TAU_CHUNK - 1;
+        for (int i = e; i < SROWS * PITCH; i += 128) stg[i] = 0;
+        // the 39 extra rows (q' >= 128) are spread over the four warps: lanes 0..9 of each take one
+        const int xrow = lane < 10 ? 128 + quad * 10 + lane : -1;
         uint32_t stepno = 0;
         for (long long u = blockIdx.x; u < nunits; u += gridDim.x) {
             const int nt = (int)(u % f.ntiles);
@@ -410,48 +439,28 @@ __global__ void __launch_bounds__(DT_THREADS, 1) detect_tc_kernel(DetectArgs A) 
                             }
                             tmem_ld_wait();
                             {
-                                uint32_t* srow = reinterpret_cast<uint32_t*>(stg) + e * PITCH;
+                                uint32_t* sp = reinterpret_cast<uint32_t*>(stg) + (e + DT_TAU_CHUNK - 1) * PITCH;
 #pragma unroll
-                                for (int i = 0; i < DT_TAU_CHUNK; ++i) srow[i] = i < cl ? v[i] : 0u;
+                                for (int i = 0; i < DT_TAU_CHUNK; ++i) sp[i - i * PITCH] = i < cl ? v[i] : 0u;   // row e-i+39, col i
                             }
                             if (vl == tptv - 1 && c0 + cl >= L) {   // accumulator drained: hand it back to the MMA warp
                                 tc_fence_before();
                                 mbar_arrive(&tempty_bar[sub]);
                             }
                             named_bar_sync(1, 128);
-                            // Diagonal sums.  Thread e owns the out indices q_k = e + 128k, k = 0,1,2 (k = 2 only
-                            // for L > 129).  q_k reads rows e + 128k - (L-1) + tau, inside [0,128) for exactly
-                            // one k per tau: k = 0 for tau >= ts = (L-1)-e, k = 1 for ts-128 <= tau < ts, else 2.
-                            // Every tau costs one unconditional load from one of three rows 128 apart (rows
-                            // outside the tile are other shared memory and are discarded by select); tau ascends
-                            // within each sum => fixed summation order.  Straight-line code, no branches.
+                            // row q' of the staging buffer = sum over the chunk's frames of C[q'+tr-39][c0+tr]:
+                            // the partial diagonal sum of out index q = q' + (L - DT_TAU_CHUNK - c0).
                             {
-                                const int ts = (L - 1) - e - c0;                      // chunk-relative switch point
-                                const acc_t* pA = stg + (e - (L - 1) + c0) * PITCH;   // row of q_0 at tr = 0
-                                acc_t s0 = 0, s1 = 0, s2 = 0;
-                                if (L <= 129 && cl == DT_TAU_CHUNK) {          // hot path: full 40-frame chunk
+                                const int qoff = L - DT_TAU_CHUNK - c0;
+                                acc_t s0 = 0, s1 = 0;
+                                const acc_t* r0p = stg + e * PITCH;
+                                const acc_t* r1p = stg + (xrow < 0 ? 0 : xrow) * PITCH;
 #pragma unroll
-                                    for (int tr = 0; tr < DT_TAU_CHUNK; ++tr) {
-                                        const bool k0 = tr >= ts;
-                                        const acc_t x = pA[tr * (PITCH + 1) + (k0 ? 0 : 128 * PITCH)];
-                                        s0 += k0 ? x : (acc_t)0;
-                                        s1 += k0 ? (acc_t)0 : x;
-                                    }
-                                } else {                                        // short chunks / long templates
-#pragma unroll
-                                    for (int tr = 0; tr < DT_TAU_CHUNK; ++tr) {
-                                        const int tc = tr < cl ? tr : cl - 1;   // keep the address inside the tile
-                                        const bool live = tr < cl;
-                                        const bool k0 = tc >= ts, k2 = tc < ts - 128;
-                                        const acc_t x = pA[tc * (PITCH + 1) + (k0 ? 0 : (k2 ? 256 : 128)) * PITCH];
-                                        s0 += (live && k0) ? x : (acc_t)0;
-                                        s1 += (live && !k0 && !k2) ? x : (acc_t)0;
-                                        s2 += (live && k2) ? x : (acc_t)0;
-                                    }
-                                }
-                                outacc[(sub * 128 + e) * tptv + vl] += s0;
-                                if (e < L - 1) outacc[(sub * 128 + e + 128) * tptv + vl] += s1;
-                                if (e + 128 < L - 1) outacc[(sub * 128 + e + 256) * tptv + vl] += s2;
+                                for (int tr = 0; tr < DT_TAU_CHUNK; ++tr) { s0 += r0p[tr]; s1 += r1p[tr]; }
+                                const int q0 = e + qoff;
+                                if (q0 >= 0) outacc[(sub * 128 + q0) * tptv + vl] += s0;
+                                const int q1 = xrow + qoff;
+                                if (xrow >= 0 && xrow < SROWS && q1 >= 0) outacc[(sub * 128 + q1) * tptv + vl] += s1;
                             }
                             named_bar_sync(1, 128);
                         }
