@@ -176,3 +176,23 @@ def test_single_window_score(cuda, oracle):
     W0, c0 = oracle.construct_linear_filter(tmpl.T.reshape(6, 12), bgd)
     np.testing.assert_array_equal(W, W0)
     np.testing.assert_allclose(c, c0, rtol=1e-14)
+
+
+def test_long_stream_many_templates(cuda, oracle):
+    """Config 5 in miniature: ONE long stream (no utterance boundaries to hide behind: 20 000 frames,
+    beyond the 16-bit limits the reference silently wraps at) scored against 50 templates; row ranges
+    are split across CTAs with L-1 frames of overlap.  Checked against the bit-exact SIMT kernel
+    everywhere and against the oracle on a slice."""
+    from tsr_b200 import ops
+    rs = np.random.RandomState(12)
+    T, D1, D2, M, L = 20000, 40, 8, 50, 40
+    F = (rs.rand(1, T, D1, D2) < 0.15).astype(np.uint8)
+    LF = (rs.randn(M, L, D1, D2) * 1.5).astype(np.float32)
+    t = _gpu_detect(F, LF, 0, 4)
+    s = _gpu_detect(F, LF, 1)
+    scale = np.abs(s).max()
+    assert np.abs(t - s).max() <= RTOL * scale
+    assert np.all(t[0, T - L + 1:] == 0) and np.all(t[0, :T - L + 1, 0] != 0)
+    sl = slice(9000, 9400)
+    ref = oracle.detect(F[0, sl], LF[7])
+    np.testing.assert_array_equal(s[0, 9000:9400 - L + 1, 7], ref[:400 - L + 1])
