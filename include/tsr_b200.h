@@ -147,8 +147,16 @@ size_t tsr_em_workspace_bytes(long long N, int D, int K);   /* scratch for the t
 int tsr_em_estep(const uint32_t* Xbits, long long N, int D, int rowwords, int K, const float* logT,
                  const float* logInvT, const float* logw, float* aff, float* scores_or_null, float* stats,
                  double* stats_ll, int hard, void* workspace, int impl, void* stream);
-int tsr_em_mstep(const uint32_t* Xbits, long long N, int D, int rowwords, int K, const float* aff, float* stats,
-                 void* workspace, void* stream);
+/* Tensor-core M-step: needs XT, the bit matrix transposed once per data set:
+ * XT uint32 [D][N_pad/32], N_pad = tsr_em_npad(N,D,K) (rows padded so each of the
+ * tsr_em_segments(N,D,K) contraction segments is a multiple of 128 data rows). */
+int       tsr_em_segments(long long N, int D, int K);
+long long tsr_em_npad(long long N, int D, int K);
+int tsr_transpose_bits(const uint32_t* Xbits, long long N, int D, int rowwords, uint32_t* XTbits, long long N_pad,
+                       void* stream);
+int tsr_em_mstep(const uint32_t* Xbits, const uint32_t* XTbits_or_null /* required for TSR_IMPL_TENSOR */,
+                 long long N, int D, int rowwords, int K, const float* aff, float* stats, void* workspace, int impl,
+                 void* stream);
 /* weights = respsum / N_total; T = numer / N_total / weights clipped to [min_prob, 1-min_prob];
  * logT, logInvT, logw refreshed (all float32, as bernoulli_mixture.py:178-184). */
 int tsr_em_finalize(const float* stats, long long N_total, int D, int K, float min_prob, float* templates,

@@ -35,7 +35,10 @@ SIGNATURES = {
     "tsr_detect_float": (_i, [_vp, _i, _i, _i, _vp, _i, _i, _vp, _vp, _vp]),
     "tsr_em_workspace_bytes": (_sz, [_ll, _i, _i]),
     "tsr_em_estep": (_i, [_vp, _ll, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _vp]),
-    "tsr_em_mstep": (_i, [_vp, _ll, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "tsr_em_segments": (_i, [_ll, _i, _i]),
+    "tsr_em_npad": (_ll, [_ll, _i, _i]),
+    "tsr_transpose_bits": (_i, [_vp, _ll, _i, _i, _vp, _ll, _vp]),
+    "tsr_em_mstep": (_i, [_vp, _vp, _ll, _i, _i, _i, _vp, _vp, _vp, _i, _vp]),
     "tsr_em_finalize": (_i, [_vp, _ll, _i, _i, _f, _vp, _vp, _vp, _vp, _vp, _vp]),
 }
 

@@ -10,28 +10,103 @@
 
 extern "C" int tsr_prepare_filters(const float* LF, int M, int L, int D, int plane_format, void* blob, void* stream);
 extern "C" size_t tsr_filter_blob_bytes(int M, int L, int D, int plane_format);
+extern "C" int tsr_rowwords(int D);
 extern "C" int tsr_detect(const uint32_t* featbits, int B, int T, int D, int rowwords, const void* filter_blob,
                           const float* LF_or_null, int M, int L, int plane_format, float* scores, int impl, void* stream);
-#define EM_PLANES TSR_PLANES_AUTO
+#define EM_PLANES TSR_PLANES_INT8X3
 
 namespace tsr {
 
 #define EM_MAX_K 64
 #define EM_MSPLIT 64
 
+// Tensor-core M-step geometry: the transposed bit matrix XT [D][N_pad] is viewed as D*S rows of
+// N_pad/S "features" (row d*S+s = segment s of feature d's column); the posteriors become K*S
+// "templates" (template s*K+k = aff[segment s rows][k]); one detection-style contraction (L = 1,
+// INT8X3, exact int32 accumulation) yields every (row, template) product and the S useful
+// diagonal blocks are gathered into the numerators.  S only exists to spread the contraction
+// over enough CTAs; the off-diagonal work it wastes is a few percent of one E-step.
+struct EmGeom {
+    int S;
+    long long Npad, seg;
+};
+static EmGeom em_geom(long long N, int D, int K) {
+    EmGeom g;
+    long long want = (2LL * 148 * 256 + D - 1) / D;      // row-steps for ~2 waves of 148 CTAs
+    int S = (int)(want < 1 ? 1 : (want > 16 ? 16 : want));
+    while (S > 1 && (long long)S * 128 > N) --S;
+    g.S = S;
+    g.Npad = ((N + (long long)S * 128 - 1) / ((long long)S * 128)) * (long long)S * 128;
+    g.seg = g.Npad / S;
+    return g;
+}
+
 struct EmWorkspace {
-    size_t off_w, off_c, off_blob, off_scores, off_partial, total;
+    size_t off_w, off_c, off_blob, off_scores, off_partial, off_mlf, off_mblob, off_mscores, total;
 };
 static EmWorkspace em_workspace(long long N, int D, int K) {
     EmWorkspace w;
     auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    const EmGeom g = em_geom(N, D, K);
     w.off_w = 0;
     w.off_c = up((size_t)K * D * 4);
     w.off_blob = w.off_c + up((size_t)K * 4);
     w.off_scores = w.off_blob + up(tsr_filter_blob_bytes(K, 1, D, EM_PLANES));
     w.off_partial = w.off_scores + up((size_t)N * K * 4);
-    w.total = w.off_partial + up((size_t)EM_MSPLIT * K * D * 4);
+    w.off_mlf = w.off_partial + up((size_t)EM_MSPLIT * K * D * 4);
+    w.off_mblob = w.off_mlf + up((size_t)K * g.Npad * 4);
+    w.off_mscores = w.off_mblob + up(tsr_filter_blob_bytes(K * g.S, 1, (int)g.seg, TSR_PLANES_INT8X3));
+    w.total = w.off_mscores + up((size_t)D * g.S * K * g.S * 4);
     return w;
+}
+
+// XT[d][n] = X[n][d]: each warp transposes a 32x32 bit block with 32 ballots.
+__global__ void transpose_bits_kernel(const uint32_t* __restrict__ X, long long N, int D, int rowwords,
+                                      uint32_t* __restrict__ XT, long long nt_words) {
+    const int lane = threadIdx.x & 31;
+    const long long nblk_n = nt_words;                       // 32-row blocks (incl. zero padding)
+    const int nblk_d = (D + 31) / 32;
+    const long long total = nblk_n * nblk_d;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long wid = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5; wid < total; wid += nwarps) {
+        const long long bn = wid / nblk_d;
+        const int bd = (int)(wid - bn * nblk_d);
+        const long long n = bn * 32 + lane;
+        const uint32_t word = n < N ? X[n * rowwords + bd] : 0u;
+        uint32_t mine = 0;
+#pragma unroll
+        for (int bit = 0; bit < 32; ++bit) {
+            const uint32_t col = __ballot_sync(0xffffffffu, (word >> bit) & 1u);   // bit `bit` of 32 rows
+            if (lane == bit) mine = col;
+        }
+        const int d = bd * 32 + lane;
+        if (d < D) XT[(size_t)d * nt_words + bn] = mine;
+    }
+}
+
+// LF[(s*K + k)][n'] = aff[s*seg + n'][k]  (zero beyond N)
+__global__ void em_aff_to_filters_kernel(const float* __restrict__ aff, long long N, int K, int S, long long seg,
+                                         float* __restrict__ LF) {
+    const long long total = (long long)K * S * seg;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long np = i % seg;
+        const long long m = i / seg;
+        const int sidx = (int)(m / K), k = (int)(m - (long long)sidx * K);
+        const long long n = sidx * seg + np;
+        LF[i] = n < N ? aff[n * K + k] : 0.f;
+    }
+}
+
+// numer[k][d] += sum_s scores[(d*S + s)][(s*K + k)]
+__global__ void em_gather_numer_kernel(const float* __restrict__ scores, int D, int K, int S, float* __restrict__ numer) {
+    const long long total = (long long)K * D;
+    const int M = K * S;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int k = (int)(i / D), d = (int)(i - (long long)k * D);
+        float acc = 0.f;
+        for (int sidx = 0; sidx < S; ++sidx) acc += scores[((size_t)d * S + sidx) * M + (size_t)sidx * K + k];
+        numer[i] += acc;
+    }
 }
 
 // W = logT - logInvT (one thread per element); c[k] by one warp per component, fixed order.
@@ -206,24 +281,56 @@ int tsr_em_estep(const uint32_t* Xbits, long long N, int D, int rowwords, int K,
     return check_launch("tsr_em_estep(posterior)");
 }
 
-int tsr_em_mstep(const uint32_t* Xbits, long long N, int D, int rowwords, int K, const float* aff, float* stats,
-                 void* workspace, void* stream) {
+int tsr_em_segments(long long N, int D, int K) { return (N < 1 || D < 1 || K < 1) ? 0 : em_geom(N, D, K).S; }
+long long tsr_em_npad(long long N, int D, int K) { return (N < 1 || D < 1 || K < 1) ? 0 : em_geom(N, D, K).Npad; }
+
+int tsr_transpose_bits(const uint32_t* Xbits, long long N, int D, int rowwords, uint32_t* XTbits, long long N_pad,
+                       void* stream) {
+    TSR_REQUIRE(Xbits && XTbits, "tsr_transpose_bits: null pointer");
+    TSR_REQUIRE(N >= 1 && D >= 1 && rowwords == tsr_rowwords(D) && N_pad >= N && N_pad % 64 == 0, "tsr_transpose_bits: bad sizes");
+    int rc = require_sm100("tsr_transpose_bits");
+    if (rc) return rc;
+    transpose_bits_kernel<<<148 * 8, 256, 0, (cudaStream_t)stream>>>(Xbits, N, D, rowwords, XTbits, N_pad / 32);
+    return check_launch("tsr_transpose_bits");
+}
+
+int tsr_em_mstep(const uint32_t* Xbits, const uint32_t* XTbits_or_null, long long N, int D, int rowwords, int K,
+                 const float* aff, float* stats, void* workspace, int impl, void* stream) {
     TSR_REQUIRE(Xbits && aff && stats && workspace, "tsr_em_mstep: null pointer");
     TSR_REQUIRE(K >= 1 && K <= EM_MAX_K, "tsr_em_mstep: need 1 <= num_mix <= %d (got %d)", EM_MAX_K, K);
     TSR_REQUIRE(N >= 0 && D >= 1 && rowwords == tsr_rowwords(D), "tsr_em_mstep: bad sizes");
+    TSR_REQUIRE(impl == TSR_IMPL_TENSOR || impl == TSR_IMPL_SIMT, "tsr_em_mstep: unknown impl %d", impl);
     if (N == 0) return TSR_OK;
     int rc = require_sm100("tsr_em_mstep");
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     EmWorkspace w = em_workspace(N, D, K);
-    float* partial = (float*)((uint8_t*)workspace + w.off_partial);
-    int nsplit = (int)(N < EM_MSPLIT * 128 ? (N + 127) / 128 : EM_MSPLIT);
-    dim3 grid((rowwords + 7) / 8, nsplit);
-    em_mstep_partial_kernel<<<grid, 256, 0, st>>>(Xbits, aff, N, D, rowwords, K, partial);
-    rc = check_launch("tsr_em_mstep(partial)");
+    uint8_t* ws = (uint8_t*)workspace;
+    if (impl == TSR_IMPL_SIMT) {
+        float* partial = (float*)(ws + w.off_partial);
+        int nsplit = (int)(N < EM_MSPLIT * 128 ? (N + 127) / 128 : EM_MSPLIT);
+        dim3 grid((rowwords + 7) / 8, nsplit);
+        em_mstep_partial_kernel<<<grid, 256, 0, st>>>(Xbits, aff, N, D, rowwords, K, partial);
+        rc = check_launch("tsr_em_mstep(partial)");
+        if (rc) return rc;
+        em_mstep_reduce_kernel<<<148 * 2, 256, 0, st>>>(partial, nsplit, K, D, stats);
+        return check_launch("tsr_em_mstep(reduce)");
+    }
+    TSR_REQUIRE(XTbits_or_null, "tsr_em_mstep: the tensor path needs the transposed bits (tsr_transpose_bits)");
+    const EmGeom g = em_geom(N, D, K);
+    TSR_REQUIRE(g.seg < (1ll << 31) && (long long)D * g.S < (1ll << 31), "tsr_em_mstep: problem too large");
+    float* LF = (float*)(ws + w.off_mlf);
+    float* scores = (float*)(ws + w.off_mscores);
+    em_aff_to_filters_kernel<<<148 * 8, 256, 0, st>>>(aff, N, K, g.S, g.seg, LF);
+    rc = check_launch("tsr_em_mstep(filters)");
     if (rc) return rc;
-    em_mstep_reduce_kernel<<<148 * 2, 256, 0, st>>>(partial, nsplit, K, D, stats);
-    return check_launch("tsr_em_mstep(reduce)");
+    rc = tsr_prepare_filters(LF, K * g.S, 1, (int)g.seg, TSR_PLANES_INT8X3, ws + w.off_mblob, stream);
+    if (rc) return rc;
+    rc = tsr_detect(XTbits_or_null, 1, D * g.S, (int)g.seg, tsr_rowwords((int)g.seg), ws + w.off_mblob, LF, K * g.S, 1,
+                    TSR_PLANES_INT8X3, scores, TSR_IMPL_TENSOR, stream);
+    if (rc) return rc;
+    em_gather_numer_kernel<<<148 * 2, 256, 0, st>>>(scores, D, K, g.S, stats);
+    return check_launch("tsr_em_mstep(gather)");
 }
 
 int tsr_em_finalize(const float* stats, long long N_total, int D, int K, float min_prob, float* templates,

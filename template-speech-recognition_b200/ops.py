@@ -238,6 +238,10 @@ class EmState:
         if nbytes == 0:
             raise ValueError("unsupported EM shape (need 1 <= num_mix <= 64)")
         self.ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        # transposed bits for the tensor-core M-step (one-time, 1 bit per datum)
+        self.Npad = int(_lib.lib().tsr_em_npad(self.N, self.D, self.K))
+        self.XT = torch.zeros((self.D, self.Npad // 32), dtype=torch.int32, device=dev)
+        _lib.call("tsr_transpose_bits", _ptr(self.X), self.N, self.D, self.rw, _ptr(self.XT), self.Npad, _stream())
         self.aff = torch.zeros((self.N, self.K), dtype=torch.float32, device=dev)
         # stats = [K*D numerators | K responsibility sums]; ll kept separately in float64
         self.stats = torch.zeros(self.K * self.D + self.K, dtype=torch.float32, device=dev)
@@ -250,9 +254,9 @@ class EmState:
                   _ptr(self.aff), _ptr(scores_out), _ptr(self.stats), _ptr(self.ll), int(bool(hard)), _ptr(self.ws),
                   int(impl), _stream())
 
-    def mstep_accumulate(self):
-        _lib.call("tsr_em_mstep", _ptr(self.X), self.N, self.D, self.rw, self.K, _ptr(self.aff), _ptr(self.stats),
-                  _ptr(self.ws), _stream())
+    def mstep_accumulate(self, impl=IMPL_TENSOR):
+        _lib.call("tsr_em_mstep", _ptr(self.X), _ptr(self.XT), self.N, self.D, self.rw, self.K, _ptr(self.aff),
+                  _ptr(self.stats), _ptr(self.ws), int(impl), _stream())
 
 
 def em_finalize(stats, N_total, D, K, min_prob, templates, logT, logInvT, weights, logw):

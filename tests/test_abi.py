@@ -14,7 +14,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def _header_functions():
     text = open(os.path.join(ROOT, "include", "tsr_b200.h")).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    decls = re.findall(r"\b(?:int|size_t|const char\*)\s+(tsr_\w+)\s*\(([^;]*?)\)\s*;", text, flags=re.S)
+    decls = re.findall(r"\b(?:int|size_t|long long|const char\*)\s+(tsr_\w+)\s*\(([^;]*?)\)\s*;", text, flags=re.S)
     return {name: [a.strip() for a in args.split(",") if a.strip() and a.strip() != "void"] for name, args in decls}
 
 

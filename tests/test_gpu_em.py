@@ -34,7 +34,7 @@ def test_estep_matches_numpy(cuda, N, D, K, impl):
     scores = torch.empty((N, K), dtype=torch.float32, device="cuda")
     st.estep(torch.from_numpy(logT).cuda(), torch.from_numpy(logI).cuda(), torch.from_numpy(logw).cuda(),
              impl=impl, scores_out=scores)
-    st.mstep_accumulate()
+    st.mstep_accumulate(impl=impl)
     torch.cuda.synchronize()
     Xd = X.astype(np.float64)
     S = Xd @ logT.astype(np.float64).T + (1 - Xd) @ logI.astype(np.float64).T
