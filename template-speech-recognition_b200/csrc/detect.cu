@@ -16,9 +16,10 @@
 // CTA (persistent, 1 per SM, 576 threads):
 // Warp ids are ordered by how critical the role is (the SMSP arbiter favours higher ids):
 //   warp  0     filter-tile loader (cp.async.bulk, one copy per pipeline stage)
-//   warps 1-12  frame-bit expanders (one row of the 384-row step each)
-//   warps 13-16 epilogue: TMEM -> smem staging -> diagonal sums -> global (TMEM lane quadrant = warp % 4)
-//   warp  17    MMA issuer + TMEM allocation
+//   warps 1-8   frame-bit expanders, two groups of 4 warps on alternate stages (a thread expands one row
+//               of each 128-row sub-tile)
+//   warps 9-12  epilogue: TMEM -> smem staging -> diagonal sums -> global (TMEM lane quadrant = warp % 4)
+//   warp  13    MMA issuer + TMEM allocation
 #include <type_traits>
 
 #include "common.cuh"
@@ -27,8 +28,8 @@ namespace tsr {
 
 #define DT_MSUB_MAX 3
 #define DT_MAX_STAGES 4
-#define DT_THREADS 576
-#define DT_PRODUCERS 384
+#define DT_THREADS 448     // 14 warps: <= 144 registers per thread
+#define DT_PRODUCERS 256   // two groups of 128 expander threads
 #define DT_TAU_CHUNK 40    // diagonal sums are staged through smem in chunks of <= 40 filter frames
 #define DT_NT_MAX 240      // widest N tile: tcgen05.mma issue costs ~100 cycles, so each MMA should carry >= that much work
 
@@ -48,6 +49,10 @@ struct FilterLayout {
     int msub;     // 128-row accumulators per step (msub*NT <= 512)
     int nstage;   // smem pipeline depth
     int fps;      // features per pipeline stage: 64 (F16, 8 k-groups of 8) or 128 (I8, 8 k-groups of 16)
+    int fold;     // frames folded into the contraction ("super-row" = fold consecutive frames); 1 for F16
+    int Lf;       // columns per group = ceil(L / fold): column tau' covers frames tau'*fold .. +fold-1
+    int Lc;       // fold * (Lf - 1): row shift of the last column = unfinished rows carried between steps
+    int Kf;       // contraction length per super-row = fold * rowwords * 32
     size_t tile_bytes;   // one (ntile, chunk) filter tile
     size_t hdr_bytes;    // [0] plane format, [1] max|w| bits, then float scale[M] (I8)
     size_t total;
@@ -59,25 +64,48 @@ __host__ __device__ inline FilterLayout filter_layout(int M, int L, int D, int p
     f.rowwords = ((D + 63) / 64) * 2;
     f.kind = (planes == TSR_PLANES_INT8X2 || planes == TSR_PLANES_INT8X3) ? 1 : 0;
     f.P = planes == TSR_PLANES_INT8X3 ? 3 : 2;
-    if (f.kind == 1 && f.P * L > DT_NT_MAX) { f.kind = 0; f.P = 2; }   // planes of a template must share a tile
     f.vpt = f.kind ? f.P : 1;
-    int tptv = (DT_NT_MAX / (f.vpt * L)) * f.vpt;
+    f.fps = f.kind ? 128 : 64;
+    f.hdr_bytes = 128 + (((size_t)M * 4 + 127) & ~(size_t)127);
+    // Frame folding (I8 only: integer accumulation is exact however long the chain).  Folding `fold`
+    // consecutive frames into K divides the number of (row, column) products the epilogue has to
+    // diagonal-sum by `fold` at identical MMA work.  Pick the fold that fills the N tiles best;
+    // ties go to the larger fold.
+    int best_fold = 1;
+    if (f.kind) {
+        double best = -1.0;
+        for (int fo = 1; fo <= L; ++fo) {
+            const int Lf = (L + fo - 1) / fo;
+            if (f.vpt * Lf > DT_NT_MAX) continue;
+            int tp = (DT_NT_MAX / (f.vpt * Lf)) * f.vpt;
+            if (tp > M * f.vpt) tp = M * f.vpt;
+            const int NT = (tp * Lf + 15) & ~15;
+            const int nt = (M * f.vpt + tp - 1) / tp;
+            double eff = (double)(M * f.vpt) * L / fo / ((double)nt * NT);    // useful columns / issued columns
+            eff *= NT >= 208 ? 1.0 : (double)NT / 208.0;                        // small-N MMAs are issue bound
+            eff /= 1.0 + 0.65 / fo;                                             // epilogue ~0.65x the MMA time unfolded
+            if (eff >= best - 1e-9) { best = eff; best_fold = fo; }
+        }
+    }
+    f.fold = best_fold;
+    f.Lf = (L + f.fold - 1) / f.fold;
+    f.Lc = f.fold * (f.Lf - 1);
+    f.Kf = f.fold * f.rowwords * 32;
+    f.nchunks = (f.Kf + f.fps - 1) / f.fps;
+    int tptv = (DT_NT_MAX / (f.vpt * f.Lf)) * f.vpt;
     if (tptv < f.vpt) tptv = f.vpt;
     if (tptv > M * f.vpt) tptv = M * f.vpt;
-    f.fps = f.kind ? 128 : 64;
-    f.nchunks = (D + f.fps - 1) / f.fps;
-    f.hdr_bytes = 128 + (((size_t)M * 4 + 127) & ~(size_t)127);
     int msub_cap = DT_MSUB_MAX;
     for (;;) {   // shrink rows per step, then templates per tile, until two pipeline stages fit in 227 KB
         f.tptv = tptv;
-        f.NT = (tptv * L + 15) & ~15;
+        f.NT = (tptv * f.Lf + 15) & ~15;
         f.ntiles = (M * f.vpt + tptv - 1) / tptv;
         int msub = 512 / f.NT;
         f.msub = msub > msub_cap ? msub_cap : msub;
         f.tile_bytes = f.kind ? (size_t)f.NT * 128 : (size_t)2 * f.NT * 128;
         const size_t stage = (size_t)f.msub * 16384 + f.tile_bytes;
         const size_t fixed = (((128 + DT_TAU_CHUNK) * (DT_TAU_CHUNK + 1) * 4 + 127) & ~(size_t)127) +
-                             ((((size_t)f.msub * 128 + L) * f.tptv * 4 + 127) & ~(size_t)127) + 512;
+                             ((((size_t)f.msub * 128 + f.Lc + 1) * f.tptv * 4 + 127) & ~(size_t)127) + 512;
         const long long avail = 227 * 1024 - (long long)fixed;
         int ns = avail > 0 ? (int)(avail / (long long)stage) : 0;
         if (ns >= 2 || (f.msub == 1 && tptv == f.vpt)) {
@@ -132,12 +160,15 @@ __global__ void prepare_filters_kernel(const float* __restrict__ LF, uint8_t* __
         const int n = (int)(r % f.NT); r /= f.NT;
         const int c = (int)(r % f.nchunks);
         const int nt = (int)(r / f.nchunks);
-        const int d = c * f.fps + dd;
-        const int vl = n / f.L, tau = n - vl * f.L;
+        const int kf = c * f.fps + dd;                 // position in the folded contraction
+        const int dpad = f.rowwords * 32;
+        const int phi = kf / dpad, d = kf - phi * dpad; // frame within the super-row, feature within the frame
+        const int vl = n / f.Lf, tauf = n - vl * f.Lf;
+        const int tau = tauf * f.fold + phi;
         const int v = nt * f.tptv + vl;
         const int m = v / f.vpt, plane = v - m * f.vpt;
         float w = 0.f;
-        const bool live = vl < f.tptv && m < f.M && d < f.D;
+        const bool live = vl < f.tptv && m < f.M && d < f.D && phi < f.fold && tau < f.L;
         if (live) w = LF[((size_t)m * f.L + tau) * f.D + d];
         uint8_t* tile = tiles + ((size_t)nt * f.nchunks + c) * f.tile_bytes;
         if (f.kind) {
@@ -196,7 +227,7 @@ __host__ __device__ inline DetectSmem detect_smem_layout(const FilterLayout& f) 
     S.b = S.a_bytes;                                   // within a stage
     S.stage = f.nstage * S.stage_bytes;                // epilogue staging [128][TC+1] words
     S.outacc = S.stage + (((128 + DT_TAU_CHUNK) * (DT_TAU_CHUNK + 1) * 4 + 127) & ~127u);
-    S.bars = S.outacc + (((f.msub * 128 + f.L) * f.tptv * 4 + 127) & ~127u);
+    S.bars = S.outacc + (((f.msub * 128 + f.Lc + 1) * f.tptv * 4 + 127) & ~127u);
     S.total = S.bars + 256;
     return S;
 }
@@ -244,20 +275,20 @@ __global__ void __launch_bounds__(DT_THREADS, 1) detect_tc_kernel(DetectArgs A) 
         for (int s = 0; s < DT_MSUB_MAX; ++s) mbar_init(&tempty_bar[s], 128);
         mbar_fence_init();
     }
-    if (warp == 17) tmem_alloc<512>(tmem_ptr);
+    if (warp == 13) tmem_alloc<512>(tmem_ptr);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
 
-    if (warp >= 1 && warp <= 12) {
+    if (warp >= 1 && warp <= 8) {
         // ============================ frame-bit expanders ============================
-        // Two groups of 6 warps take alternate pipeline stages (group = stage parity); a thread expands
-        // two rows of the 384-row step per stage it owns.  The proxy fence + mbarrier arrive that end a
+        // Two groups of 4 warps take alternate pipeline stages (group = stage parity); a thread expands
+        // one row of each 128-row sub-tile per stage it owns.  The proxy fence + mbarrier arrive that end a
         // stage cost several hundred cycles of latency; alternating groups overlaps them with the other
         // group's expansion work.
-        const int grp = (warp - 1) / 6;                  // 0 or 1
-        const int tg = threadIdx.x - 32 - grp * 192;     // 0..191 within the group
+        const int grp = (warp - 1) / 4;                  // 0 or 1
+        const int tg = threadIdx.x - 32 - grp * 128;     // 0..127 within the group == row of a sub-tile
         const uint32_t one = fmt_one(fmt);
         const int nw2 = f.rowwords >> 1;                  // 64-bit words per row
         const int w2ps = I8 ? 2 : 1;                      // 64-bit words per stage
@@ -269,30 +300,35 @@ __global__ void __launch_bounds__(DT_THREADS, 1) detect_tc_kernel(DetectArgs A) 
             long long o1 = o0 + A.rows_per_unit; if (o1 > A.R) o1 = A.R;
             long long in_end = o1 + L - 1; if (in_end > A.R) in_end = A.R;
             for (int step = 0; step < A.steps_per_unit; ++step) {
-                const uint2* src[2];
-                bool live[2];
+                long long grow[DT_MSUB_MAX];
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int pr = tg + h * 192;                                   // row within the step
-                    const long long g = o0 + (long long)step * step_rows + pr;
-                    live[h] = pr < step_rows && g < in_end;
-                    src[h] = reinterpret_cast<const uint2*>(A.bits + (live[h] ? g : 0) * f.rowwords);
-                }
+                for (int h = 0; h < DT_MSUB_MAX; ++h)                              // row tg of sub-tile h
+                    grow[h] = h < msub ? o0 + (long long)step * step_rows + h * 128 + tg : in_end;   // in_end: reads as zeros
+                // 64-bit word w of super-row g lives in frame g + w / nw2 at word w % nw2 (frames beyond the
+                // unit's input range read as zero: they only meet zero weights or invalid outputs)
+                auto fetch = [&](int h, int wq) -> uint2 {
+                    const int phi = wq / nw2;
+                    const long long fr = grow[h] + phi;
+                    return (phi < f.fold && fr < in_end)
+                               ? __ldg(reinterpret_cast<const uint2*>(A.bits + fr * f.rowwords) + (wq - phi * nw2))
+                               : make_uint2(0u, 0u);
+                };
                 for (int c = 0; c < nchunks; ++c, ++it) {
                     if ((int)(it & 1) == grp) {
-                        uint2 w[2], wh[2];
+                        uint2 w[DT_MSUB_MAX], wh[DT_MSUB_MAX];
 #pragma unroll
-                        for (int h = 0; h < 2; ++h) {
-                            w[h] = (live[h] && c * w2ps < nw2) ? __ldg(src[h] + c * w2ps) : make_uint2(0u, 0u);
-                            wh[h] = (I8 && live[h] && c * w2ps + 1 < nw2) ? __ldg(src[h] + c * w2ps + 1) : make_uint2(0u, 0u);
+                        for (int h = 0; h < DT_MSUB_MAX; ++h) {
+                            if (h < msub) {
+                                w[h] = fetch(h, c * w2ps);
+                                wh[h] = I8 ? fetch(h, c * w2ps + 1) : make_uint2(0u, 0u);
+                            }
                         }
                         mbar_wait_relaxed(&empty_bar[stage], ph ^ 1);
-                        if (warp == 1 || warp == 7) DT_TRACE(it, 0);
+                        if (warp == 1 || warp == 5) DT_TRACE(it, 0);
 #pragma unroll
-                        for (int h = 0; h < 2; ++h) {
-                            const int pr = tg + h * 192;
-                            if (pr < step_rows) {
-                                uint8_t* dst = smem + stage * S.stage_bytes + (pr >> 7) * S.a_sub + (pr & 127) * 16;
+                        for (int h = 0; h < DT_MSUB_MAX; ++h) {
+                            if (h < msub) {
+                                uint8_t* dst = smem + stage * S.stage_bytes + h * S.a_sub + tg * 16;
                                 if (I8) {   // 128 features -> 8 k-groups of 16 uint8
                                     *reinterpret_cast<uint4*>(dst) = expand16_u8(w[h].x & 0xFFFF);
                                     *reinterpret_cast<uint4*>(dst + 2048) = expand16_u8(w[h].x >> 16);
@@ -314,7 +350,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) detect_tc_kernel(DetectArgs A) 
                         }
                         fence_proxy_async_smem();
                         mbar_arrive(&full_bar[stage]);
-                        if (warp == 1 || warp == 7) DT_TRACE(it, 1);
+                        if (warp == 1 || warp == 5) DT_TRACE(it, 1);
                     }
                     if (++stage == nstage) { stage = 0; ph ^= 1; }
                 }
@@ -339,7 +375,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) detect_tc_kernel(DetectArgs A) 
                     }
             }
         }
-    } else if (warp == 17) {
+    } else if (warp == 13) {
         // ================================ MMA issuer ================================
         // warp-uniform loop, one elected lane issues (see umma_f16_elect)
         const uint32_t idesc = I8 ? ((2u << 4) | (0u << 7) | (1u << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24))
@@ -397,16 +433,22 @@ __global__ void __launch_bounds__(DT_THREADS, 1) detect_tc_kernel(DetectArgs A) 
         const float* scale = reinterpret_cast<const float*>(A.blob + 128);
         const int quad = warp & 3;                                    // TMEM lane quadrant of this warp
         const int e = quad * 32 + lane;                               // 0..127 == TMEM lane == row of the sub-tile
-        const int TC = L < DT_TAU_CHUNK ? L : DT_TAU_CHUNK;
-        const int nacc = (step_rows + L - 1) * tptv;
+        // Columns of a group are the folded frames tau' = 0..Lf-1; column tau' belongs to the out row
+        // fold*tau' rows above.  They are staged TCf columns at a time, TCf chosen so that the skew
+        // fold*(TCf-1) stays within the DT_TAU_CHUNK-1 extra staging rows.
+        const int Lf = f.Lf, fold = f.fold, Lc = f.Lc;
+        int TCf = (DT_TAU_CHUNK - 1) / fold + 1;
+        if (TCf > Lf) TCf = Lf;
+        const int skew = fold * (TCf - 1);                 // row shift of the last column of a chunk
+        const int srows = 128 + skew;                       // staging rows in use
+        const int nacc = (step_rows + Lc) * tptv;
         const int vpt = f.vpt, tpt = tptv / vpt;
-        // Skewed staging: thread e writes C[e][tau] to row q' = e - tr + (DT_TAU_CHUNK-1), column tr, so
-        // that a diagonal of the tile becomes a ROW of the staging buffer and the diagonal sum a plain row
-        // sum (one load + one add per element, no masks).  Cells no (e,tr) maps to -- the two triangles at
-        // the top and bottom -- are zeroed once here and never written again.
-        constexpr int SROWS = 128 + DT_TAU_CHUNK - 1;
-        for (int i = e; i < SROWS * PITCH; i += 128) stg[i] = 0;
-        // the 39 extra rows (q' >= 128) are spread over the four warps: lanes 0..9 of each take one
+        // Skewed staging: thread e writes C[e][c0+tr] to row q' = e - fold*tr + skew, column tr, so that a
+        // diagonal of the tile becomes a ROW of the staging buffer and the diagonal sum a plain row sum (one
+        // load + one add per element, no masks).  Cells no (e,tr) maps to -- the two triangles at the top
+        // and bottom -- are zeroed once here and never written again.
+        for (int i = e; i < (128 + DT_TAU_CHUNK) * PITCH; i += 128) stg[i] = 0;
+        // the extra rows (q' >= 128) are spread over the four warps: lanes 0..9 of each take one
         const int xrow = lane < 10 ? 128 + quad * 10 + lane : -1;
         uint32_t stepno = 0;
         for (long long u = blockIdx.x; u < nunits; u += gridDim.x) {
@@ -422,16 +464,114 @@ __global__ void __launch_bounds__(DT_THREADS, 1) detect_tc_kernel(DetectArgs A) 
                 tc_fence_after();
                 for (int sub = 0; sub < msub; ++sub) {
                     const uint32_t taddr = tmem_base + sub * NT + ((uint32_t)(quad * 32) << 16);
+                    if (Lc < DT_TAU_CHUNK) {
+                        // ---- whole groups per pass: gp = floor(40 / Lf) groups = up to 40 TMEM columns ----
+                        const int gp = DT_TAU_CHUNK / Lf;
+                        for (int vl0 = 0; vl0 < tptv; vl0 += gp) {
+                            const int g = (tptv - vl0) < gp ? (tptv - vl0) : gp;
+                            const int cn = g * Lf;                                 // live columns of this pass
+                            uint32_t v[DT_TAU_CHUNK];
+#pragma unroll
+                            for (int t0 = 0; t0 < DT_TAU_CHUNK; t0 += 8) {
+                                if (t0 < cn) {                                     // warp-uniform
+                                    tmem_ld8(taddr + vl0 * Lf + t0, *reinterpret_cast<uint32_t(*)[8]>(&v[t0]));
+                                } else {
+#pragma unroll
+                                    for (int i = 0; i < 8; ++i) v[t0 + i] = 0u;
+                                }
+                            }
+                            tmem_ld_wait();
+                            // column i (frame tr = i % Lf of group i / Lf) goes to staging row e + Lc - fold*tr.
+                            // Compile-time Lf (the common fold choices) gives straight-line code with
+                            // immediate offsets; other values take the counter-driven generic path.
+                            auto store_skewed = [&](auto lfc) {
+                                constexpr int LFC = decltype(lfc)::value;
+                                uint32_t* sp = reinterpret_cast<uint32_t*>(stg) + (e + Lc) * PITCH;
+                                if constexpr (LFC > 0) {
+                                    const int rstep = fold * PITCH;
+#pragma unroll
+                                    for (int i = 0; i < DT_TAU_CHUNK; ++i)
+                                        if ((i / LFC) * LFC + LFC <= DT_TAU_CHUNK)            // whole groups only (static)
+                                            sp[i - (i % LFC) * rstep] = i < cn ? v[i] : 0u;
+                                } else {
+                                    int roff = 0, tr = 0;
+#pragma unroll
+                                    for (int i = 0; i < DT_TAU_CHUNK; ++i) {
+                                        sp[roff + i] = i < cn ? v[i] : 0u;
+                                        if (++tr == Lf) { tr = 0; roff = 0; } else { roff -= fold * PITCH; }
+                                    }
+                                }
+                            };
+                            switch (Lf) {
+                                case 40: store_skewed(std::integral_constant<int, 40>{}); break;
+                                case 20: store_skewed(std::integral_constant<int, 20>{}); break;
+                                case 10: store_skewed(std::integral_constant<int, 10>{}); break;
+                                case 8: store_skewed(std::integral_constant<int, 8>{}); break;
+                                case 5: store_skewed(std::integral_constant<int, 5>{}); break;
+                                case 4: store_skewed(std::integral_constant<int, 4>{}); break;
+                                case 2: store_skewed(std::integral_constant<int, 2>{}); break;
+                                case 1: store_skewed(std::integral_constant<int, 1>{}); break;
+                                default: store_skewed(std::integral_constant<int, 0>{}); break;
+                            }
+                            if (vl0 + g >= tptv) {   // accumulator drained: hand it back to the MMA warp
+                                tc_fence_before();
+                                mbar_arrive(&tempty_bar[sub]);
+                            }
+                            named_bar_sync(1, 128);
+                            // row q' holds, per group, the Lf terms of out index q' (staging row == out index)
+                            auto sum_rows = [&](auto lfc) {
+                                constexpr int LFC = decltype(lfc)::value;
+                                const acc_t* r0p = stg + e * PITCH;
+                                const acc_t* r1p = stg + (xrow < 0 ? 0 : xrow) * PITCH;
+                                const bool x_ok = xrow >= 0 && xrow <= 128 + Lc;
+                                acc_t* o0p = outacc + (sub * 128 + e) * tptv + vl0;
+                                acc_t* o1p = outacc + (sub * 128 + (x_ok ? xrow : 0)) * tptv + vl0;
+                                if constexpr (LFC > 0) {
+                                    constexpr int NG = DT_TAU_CHUNK / LFC;
+#pragma unroll
+                                    for (int gi = 0; gi < NG; ++gi) {
+                                        acc_t s0 = 0, s1 = 0;
+#pragma unroll
+                                        for (int tr = 0; tr < LFC; ++tr) { s0 += r0p[gi * LFC + tr]; s1 += r1p[gi * LFC + tr]; }
+                                        if (gi < g) { o0p[gi] += s0; if (x_ok) o1p[gi] += s1; }
+                                    }
+                                } else {
+                                    acc_t s0 = 0, s1 = 0;
+                                    int tr = 0, gi = 0;
+#pragma unroll
+                                    for (int i = 0; i < DT_TAU_CHUNK; ++i) {
+                                        s0 += r0p[i]; s1 += r1p[i];
+                                        if (++tr == Lf) {                              // end of a group: warp-uniform
+                                            if (gi < g) { o0p[gi] += s0; if (x_ok) o1p[gi] += s1; }
+                                            s0 = 0; s1 = 0; tr = 0; ++gi;
+                                        }
+                                    }
+                                }
+                            };
+                            switch (Lf) {
+                                case 40: sum_rows(std::integral_constant<int, 40>{}); break;
+                                case 20: sum_rows(std::integral_constant<int, 20>{}); break;
+                                case 10: sum_rows(std::integral_constant<int, 10>{}); break;
+                                case 8: sum_rows(std::integral_constant<int, 8>{}); break;
+                                case 5: sum_rows(std::integral_constant<int, 5>{}); break;
+                                case 4: sum_rows(std::integral_constant<int, 4>{}); break;
+                                case 2: sum_rows(std::integral_constant<int, 2>{}); break;
+                                case 1: sum_rows(std::integral_constant<int, 1>{}); break;
+                                default: sum_rows(std::integral_constant<int, 0>{}); break;
+                            }
+                            named_bar_sync(1, 128);
+                        }
+                    } else
                     for (int vl = 0; vl < tptv; ++vl) {
-                        for (int c0 = 0; c0 < L; c0 += TC) {          // chunk of filter frames [c0, c0+cl)
-                            const int cl = (L - c0) < TC ? (L - c0) : TC;
-                            // all TMEM loads of the chunk in flight at once, one wait; frames past the chunk
+                        for (int c0 = 0; c0 < Lf; c0 += TCf) {         // chunk of columns [c0, c0+cl)
+                            const int cl = (Lf - c0) < TCf ? (Lf - c0) : TCf;
+                            // all TMEM loads of the chunk in flight at once, one wait; columns past the chunk
                             // end are zeroed by select so that the sums below need no bounds checks
                             uint32_t v[DT_TAU_CHUNK];
 #pragma unroll
                             for (int t0 = 0; t0 < DT_TAU_CHUNK; t0 += 8) {
                                 if (t0 < cl) {                                     // warp-uniform
-                                    tmem_ld8(taddr + vl * L + c0 + t0, *reinterpret_cast<uint32_t(*)[8]>(&v[t0]));
+                                    tmem_ld8(taddr + vl * Lf + c0 + t0, *reinterpret_cast<uint32_t(*)[8]>(&v[t0]));
                                 } else {
 #pragma unroll
                                     for (int i = 0; i < 8; ++i) v[t0 + i] = 0u;
@@ -439,35 +579,38 @@ __global__ void __launch_bounds__(DT_THREADS, 1) detect_tc_kernel(DetectArgs A) 
                             }
                             tmem_ld_wait();
                             {
-                                uint32_t* sp = reinterpret_cast<uint32_t*>(stg) + (e + DT_TAU_CHUNK - 1) * PITCH;
+                                uint32_t* sp = reinterpret_cast<uint32_t*>(stg) + (e + skew) * PITCH;
+                                const int dstep = 1 - fold * PITCH;                 // next column, `fold` rows up
 #pragma unroll
-                                for (int i = 0; i < DT_TAU_CHUNK; ++i) sp[i - i * PITCH] = i < cl ? v[i] : 0u;   // row e-i+39, col i
+                                for (int i = 0; i < DT_TAU_CHUNK; ++i)
+                                    if (i < TCf) sp[i * dstep] = i < cl ? v[i] : 0u;   // warp-uniform guard
                             }
-                            if (vl == tptv - 1 && c0 + cl >= L) {   // accumulator drained: hand it back to the MMA warp
+                            if (vl == tptv - 1 && c0 + cl >= Lf) {   // accumulator drained: hand it back to the MMA warp
                                 tc_fence_before();
                                 mbar_arrive(&tempty_bar[sub]);
                             }
                             named_bar_sync(1, 128);
-                            // row q' of the staging buffer = sum over the chunk's frames of C[q'+tr-39][c0+tr]:
-                            // the partial diagonal sum of out index q = q' + (L - DT_TAU_CHUNK - c0).
+                            // row q' of the staging buffer = sum over the chunk's columns of C[q'+fold*tr-skew][c0+tr]:
+                            // the partial diagonal sum of out index q = q' + (Lc - skew - fold*c0).
                             {
-                                const int qoff = L - DT_TAU_CHUNK - c0;
+                                const int qoff = Lc - skew - fold * c0;
                                 acc_t s0 = 0, s1 = 0;
                                 const acc_t* r0p = stg + e * PITCH;
                                 const acc_t* r1p = stg + (xrow < 0 ? 0 : xrow) * PITCH;
 #pragma unroll
-                                for (int tr = 0; tr < DT_TAU_CHUNK; ++tr) { s0 += r0p[tr]; s1 += r1p[tr]; }
+                                for (int tr = 0; tr < DT_TAU_CHUNK; ++tr)
+                                    if (tr < TCf) { s0 += r0p[tr]; s1 += r1p[tr]; }   // warp-uniform guard
                                 const int q0 = e + qoff;
                                 if (q0 >= 0) outacc[(sub * 128 + q0) * tptv + vl] += s0;
                                 const int q1 = xrow + qoff;
-                                if (xrow >= 0 && xrow < SROWS && q1 >= 0) outacc[(sub * 128 + q1) * tptv + vl] += s1;
+                                if (xrow >= 0 && xrow < srows && q1 >= 0) outacc[(sub * 128 + q1) * tptv + vl] += s1;
                             }
                             named_bar_sync(1, 128);
                         }
                     }
                 }
-                // rows [0, step_rows) of outacc are complete: out row g = step_row0 - (L-1) + oi
-                const long long gbase = o0 + (long long)step * step_rows - (L - 1);
+                // rows [0, step_rows) of outacc are complete: out row g = step_row0 - Lc + oi
+                const long long gbase = o0 + (long long)step * step_rows - Lc;
                 for (int i = e; i < step_rows * tpt; i += 128) {
                     const int oi = i / tpt, ml = i - oi * tpt;
                     const long long g = gbase + oi;
@@ -489,15 +632,15 @@ __global__ void __launch_bounds__(DT_THREADS, 1) detect_tc_kernel(DetectArgs A) 
                     }
                 }
                 named_bar_sync(1, 128);
-                // carry the L-1 unfinished rows to the front, clear the rest (read phase, barrier, write phase)
+                // carry the Lc unfinished rows to the front and clear the rest.  dst = src - shift; ascending
+                // passes of `shift` elements never read what an earlier pass wrote, one barrier per pass.
                 {
-                    const int keep = (L - 1) * tptv;
-                    acc_t tmp[12];
-                    int cnt = 0;
-                    for (int i = e; i < keep; i += 128) tmp[cnt++] = outacc[i + step_rows * tptv];
-                    named_bar_sync(1, 128);
-                    cnt = 0;
-                    for (int i = e; i < keep; i += 128) outacc[i] = tmp[cnt++];
+                    const int keep = Lc * tptv, shift = step_rows * tptv;
+                    for (int p0 = 0; p0 < keep; p0 += shift) {
+                        const int p1 = (p0 + shift) < keep ? (p0 + shift) : keep;
+                        for (int i = p0 + e; i < p1; i += 128) outacc[i] = outacc[i + shift];
+                        named_bar_sync(1, 128);
+                    }
                     for (int i = keep + e; i < nacc; i += 128) outacc[i] = 0;
                     named_bar_sync(1, 128);
                 }
@@ -508,7 +651,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) detect_tc_kernel(DetectArgs A) 
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 17) {
+    if (warp == 13) {
         tc_fence_after();
         tmem_dealloc<512>(tmem_base);
     }
@@ -659,14 +802,14 @@ int tsr_detect(const uint32_t* featbits, int B, int T, int D, int rowwords, cons
     const long long maxU = (R + step_rows - 1) / step_rows;
     for (long long U = 1; U <= maxU && U <= 8192; ++U) {
         long long rows = (R + U - 1) / U;
-        long long steps = (rows + L - 1 + step_rows - 1) / step_rows;
+        long long steps = (rows + A.f.Lc + step_rows - 1) / step_rows;
         long long waves = ((long long)A.f.ntiles * U + nsm - 1) / nsm;
         long long cost = waves * steps;
         if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_U = (int)U; }
     }
     A.units_per_ntile = best_U;
     A.rows_per_unit = (int)((R + best_U - 1) / best_U);
-    A.steps_per_unit = (A.rows_per_unit + L - 1 + step_rows - 1) / step_rows;
+    A.steps_per_unit = (A.rows_per_unit + A.f.Lc + step_rows - 1) / step_rows;
     const long long nunits = (long long)A.f.ntiles * best_U;
     int blocks = (int)(nunits < nsm ? nunits : nsm);
     if (A.f.kind) {

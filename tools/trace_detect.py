@@ -28,3 +28,11 @@ for i in list(range(0, 4)) + list(range(60, 76)):
     print("%4d " % i + " ".join("%13d" % (x - t0 if x else -1) for x in t[i]))
 d = np.diff(t[60:250, 5])
 print("mean cycles between consecutive stage commits:", d.mean())
+c5 = t[:, 5]
+d = np.diff(c5[:250])
+big = np.argsort(-d)[:12]
+print("largest gaps between consecutive commits (iter: cycles):", sorted([(int(i), int(d[i])) for i in big]))
+print("median stage period", np.median(d), "sum", d.sum())
+e6, e7 = t[:8, 6], t[:8, 7]
+print("epilogue (tfull -> done) per step:", [(int(b - a)) for a, b in zip(e6, e7) if a and b])
+print("step starts:", [int(x - t0) for x in e6 if x])
