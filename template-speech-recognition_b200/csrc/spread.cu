@@ -1,5 +1,8 @@
 // spread.cu -- bit-packed max-filters: K1a edge spreading, K1b part-code spreading, part-graph
 // spreading.  Integer / bit work, HBM-bound; every result is bit-exact by construction.
+#include <algorithm>
+#include <utility>
+
 #include "common.cuh"
 
 namespace tsr {
@@ -18,8 +21,10 @@ struct SpreadTaps {
 };
 
 // CTA = (utterance b, tile of TT time rows).  The tile plus halo is staged in shared memory as
-// rows of `pitch` bytes (4-aligned, zero padded left/right by padf >= max_df rounded to 4), so a
-// thread producing one 32-bit output word (4 frequency bins) fetches each tap as an unaligned
+// rows of `pitch` bytes (4-aligned, zero padded left/right by padf >= max_df rounded to 4).  A
+// thread produces one 32-bit output word (4 frequency bins).  Taps arrive sorted by dt; with
+// |df| <= 4 (WORDS path) the three words (w-1, w, w+1) of a source row are loaded once per distinct
+// dt and every tap of that row is a funnel shift of them; otherwise each tap fetches an unaligned
 // 4-byte window = two aligned LDS.32 + one funnel shift.
 __global__ void __launch_bounds__(256) spread_edges_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out,
                                                            int T, int F, int TT, int block_len, SpreadTaps taps) {
@@ -31,19 +36,31 @@ __global__ void __launch_bounds__(256) spread_edges_kernel(const uint8_t* __rest
     const int pitch = Fw + 2 * padf + 4;            // +4: the "hi" word of the last window
     const int rows = TT + 2 * taps.max_dt;
     const uint8_t* src = in + (size_t)b * T * F;
+    const bool words = ((F & 3) == 0) && ((reinterpret_cast<uintptr_t>(in) & 3) == 0);
 
     // zero everything, then fill the in-range part
-    for (int i = threadIdx.x * 4; i < rows * pitch; i += blockDim.x * 4) *reinterpret_cast<uint32_t*>(smem + i) = 0u;
+    for (int i = threadIdx.x * 16; i < rows * pitch; i += blockDim.x * 16)
+        *reinterpret_cast<uint4*>(smem + i) = make_uint4(0u, 0u, 0u, 0u);
     __syncthreads();
-    for (int i = threadIdx.x; i < rows * F; i += blockDim.x) {
-        int r = i / F, f = i - r * F;
-        int t = t0 - taps.max_dt + r;
-        if (t >= 0 && t < T) smem[r * pitch + padf + f] = src[(size_t)t * F + f];
+    if (words) {
+        const int wpr = F >> 2;
+        const uint32_t* srcw = reinterpret_cast<const uint32_t*>(src);
+        for (int i = threadIdx.x; i < rows * wpr; i += blockDim.x) {
+            int r = i / wpr, w = i - r * wpr;
+            int t = t0 - taps.max_dt + r;
+            if (t >= 0 && t < T) *reinterpret_cast<uint32_t*>(smem + r * pitch + padf + 4 * w) = __ldg(srcw + (size_t)t * wpr + w);
+        }
+    } else {
+        for (int i = threadIdx.x; i < rows * F; i += blockDim.x) {
+            int r = i / F, f = i - r * F;
+            int t = t0 - taps.max_dt + r;
+            if (t >= 0 && t < T) smem[r * pitch + padf + f] = src[(size_t)t * F + f];
+        }
     }
     __syncthreads();
 
     const int words_per_row = Fw >> 2;
-    const bool aligned_out = (F & 3) == 0;
+    const bool near = taps.max_df <= 4;
     for (int i = threadIdx.x; i < TT * words_per_row; i += blockDim.x) {
         int r = i / words_per_row, w = i - r * words_per_row;
         int t = t0 + r;
@@ -54,18 +71,41 @@ __global__ void __launch_bounds__(256) spread_edges_kernel(const uint8_t* __rest
             blk_hi = min(T, blk_lo + block_len);
         }
         uint32_t acc = 0;
-        for (int k = 0; k < taps.n; ++k) {
-            int ts = t + taps.dt[k];
-            if (ts < blk_lo || ts >= blk_hi) continue;
-            int byte_off = (r + taps.max_dt + taps.dt[k]) * pitch + padf + 4 * w + taps.df[k];
-            int a = byte_off & ~3;
-            uint32_t lo = *reinterpret_cast<const uint32_t*>(smem + a);
-            uint32_t hi = *reinterpret_cast<const uint32_t*>(smem + a + 4);
-            uint32_t v = __funnelshift_r(lo, hi, (byte_off & 3) * 8);
-            acc |= v & (0x01010101u * taps.mask[k]);
+        if (near) {
+            int cur_dt = -1000;
+            bool rowok = false;
+            uint32_t l = 0, m = 0, h = 0;
+            for (int k = 0; k < taps.n; ++k) {
+                const int dt = taps.dt[k];
+                if (dt != cur_dt) {                     // uniform: taps are sorted by dt
+                    cur_dt = dt;
+                    const int ts = t + dt;
+                    rowok = ts >= blk_lo && ts < blk_hi;
+                    if (rowok) {
+                        const uint32_t* rp = reinterpret_cast<const uint32_t*>(smem + (r + taps.max_dt + dt) * pitch + padf) + w;
+                        m = rp[0];
+                        if (padf) { l = rp[-1]; h = rp[1]; }
+                    }
+                }
+                if (!rowok) continue;
+                const int df = taps.df[k];
+                const uint32_t v = df == 0 ? m : (df > 0 ? __funnelshift_rc(m, h, 8 * df) : __funnelshift_lc(l, m, -8 * df));
+                acc |= v & (0x01010101u * taps.mask[k]);
+            }
+        } else {
+            for (int k = 0; k < taps.n; ++k) {
+                int ts = t + taps.dt[k];
+                if (ts < blk_lo || ts >= blk_hi) continue;
+                int byte_off = (r + taps.max_dt + taps.dt[k]) * pitch + padf + 4 * w + taps.df[k];
+                int a = byte_off & ~3;
+                uint32_t lo = *reinterpret_cast<const uint32_t*>(smem + a);
+                uint32_t hi = *reinterpret_cast<const uint32_t*>(smem + a + 4);
+                uint32_t v = __funnelshift_r(lo, hi, (byte_off & 3) * 8);
+                acc |= v & (0x01010101u * taps.mask[k]);
+            }
         }
         uint8_t* dst = out + ((size_t)b * T + t) * F + 4 * w;
-        if (aligned_out) {
+        if (words) {
             *reinterpret_cast<uint32_t*>(dst) = acc;
         } else {
             for (int q = 0; q < 4 && 4 * w + q < F; ++q) dst[q] = (uint8_t)(acc >> (8 * q));
@@ -73,99 +113,180 @@ __global__ void __launch_bounds__(256) spread_edges_kernel(const uint8_t* __rest
     }
 }
 
+// Line mode with unit directions (every component of every orientation in {-1,0,1}: the only table
+// the reference produces, edge_signal_proc.py:1751-1821) and radius R <= 3: the taps fall into four
+// classes -- H (df=+-k, dt=0), V (df=0, dt=+-k), D (df=k, dt=k), A (df=-k, dt=k) -- each with one
+// orientation mask.  A thread owns one 32-bit word column (4 frequency bins) of a run of RL rows and
+// slides down it with the 2R+1 source rows (left, middle, right words) in registers: 3 LDS + ~10R
+// shift/logic instructions per output word instead of a table walk.  Runs never cross a block.
+struct SpreadLineMasks { uint32_t h, v, d, a; };   // orientation masks x 0x01010101
+
+template <int R>
+__global__ void __launch_bounds__(128) spread_edges_line_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out,
+                                                                int T, int wpr, int TT, int RL, int block_len,
+                                                                SpreadLineMasks mk) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint32_t* sw = reinterpret_cast<uint32_t*>(smem);
+    constexpr int W = 2 * R + 1;
+    const int b = blockIdx.y;
+    const int t0 = blockIdx.x * TT;
+    const int pitch = wpr + 2;                       // one zero word left and right of every row
+    const int rows = TT + 2 * R;
+    const uint32_t* src = in + (size_t)b * T * wpr;
+    for (int i = threadIdx.x; i < rows * pitch; i += blockDim.x) {
+        const int r = i / pitch, c = i - r * pitch - 1;
+        const int t = t0 - R + r;
+        sw[i] = (c >= 0 && c < wpr && t >= 0 && t < T) ? __ldg(src + (size_t)t * wpr + c) : 0u;
+    }
+    __syncthreads();
+    const int nrun = (TT + RL - 1) / RL;
+    for (int task = threadIdx.x; task < nrun * wpr; task += blockDim.x) {
+        const int run = task / wpr, w = task - run * wpr;
+        const int ra = run * RL;                      // tile-relative first row of the run
+        const int ta = t0 + ra;
+        if (ta >= T) continue;
+        const int rb = min(min(ra + RL, TT), T - t0);
+        int lo = 0, hi = T;                           // block of the run in absolute frames
+        if (block_len > 0) { lo = (ta / block_len) * block_len; hi = min(T, lo + block_len); }
+        const uint32_t* col = sw + R * pitch + 1 + w; // tile row 0, word w
+        uint32_t wl[W], wm[W], wh[W];
+        auto load = [&](int slot, int r) {            // tile-relative source row r (may be a halo row)
+            const int t = t0 + r;
+            const bool ok = t >= lo && t < hi;
+            const uint32_t* q = col + r * pitch;
+            wl[slot] = ok ? q[-1] : 0u;
+            wm[slot] = ok ? q[0] : 0u;
+            wh[slot] = ok ? q[1] : 0u;
+        };
+#pragma unroll
+        for (int k = 0; k < W - 1; ++k) load(k, ra - R + k);
+        uint32_t* dst = out + ((size_t)b * T + t0) * wpr + w;
+        for (int r = ra; r < rb; r += W) {
+#pragma unroll
+            for (int u = 0; u < W; ++u) {
+                if (r + u < rb) {
+                    load((u + W - 1) % W, r + u + R);
+                    const int c0 = (u + R) % W;
+                    uint32_t acc = wm[c0];
+#pragma unroll
+                    for (int j = 1; j <= R; ++j)
+                        acc |= (__funnelshift_r(wm[c0], wh[c0], 8 * j) | __funnelshift_l(wl[c0], wm[c0], 8 * j)) & mk.h;
+#pragma unroll
+                    for (int k = 1; k <= R; ++k) {
+                        const int sp = (u + R + k) % W, sn = (u + R - k + W) % W;     // rows t+k, t-k
+                        const uint32_t pr = __funnelshift_r(wm[sp], wh[sp], 8 * k);   // row t+k at f+k
+                        const uint32_t pl = __funnelshift_l(wl[sp], wm[sp], 8 * k);   // row t+k at f-k
+                        const uint32_t nr = __funnelshift_r(wm[sn], wh[sn], 8 * k);   // row t-k at f+k
+                        const uint32_t nl = __funnelshift_l(wl[sn], wm[sn], 8 * k);   // row t-k at f-k
+                        acc |= ((wm[sp] | wm[sn]) & mk.v) | ((pr | nl) & mk.d) | ((pl | nr) & mk.a);
+                    }
+                    dst[(size_t)(r + u) * wpr] = acc;
+                }
+            }
+        }
+    }
+}
+
 // ================================================================================= K1b
 // codes uint8 [B][To][Fo] -> featbits uint32 [B][To][rowwords], feature j*K + (p-1).
-// CTA = (b, tile of RT output rows); three tile-wide smem phases, no atomics:
-//   colset[r][j][:] = OR_{|x0-i|<=r0} onehot(code[x0][j])      (time direction, Kw words per cell)
-//   wset[r][j][:]   = OR_{|x1-j|<=r1} colset[r][x1][:]          (frequency direction)
-//   word w of packed row r gathers the K-bit sets overlapping features [32w, 32w+32).
-#define TSR_SC_MAX_KW 8
+// The (2*r0+1) x (2*r1+1) box dilation is separable.  CTA = (b, tile of RT output rows):
+//   A. H[x0][:] = frequency-direction dilation of input row x0 as a PACKED bit row: every nonzero
+//      code p at (x0, x1) ORs bit (x1+k)*K + p-1, |k| <= r1, into row x0 of the smem tile
+//      (2*r1+1 shared-memory atomics per nonzero code; lanes run along x0 and the row pitch is odd,
+//      so the atomics of one instruction fall into distinct banks);
+//   B. out[i][w] = OR_{a <= 2*r0} H[i+a][w]: plain word-wise ORs on the packed rows.  A thread owns
+//      one word column and slides down the rows with the window in registers: one LDS, two LOP3
+//      and one coalesced STG per output word.
+// Rows of H outside the utterance stay zero (clipping to the array, code_parts.pyx:445-452).
+template <int R0>
+__device__ __forceinline__ void sc_vertical_or(const uint32_t* __restrict__ H, uint32_t* __restrict__ out, int pitch,
+                                               int rowwords, int nrow, int r0) {
+    // tasks = (row segment, word column); a thread takes tasks blockDim.x apart
+    const int nseg = max(1, (int)blockDim.x / rowwords);
+    const int per = (nrow + nseg - 1) / nseg;
+    for (int task = threadIdx.x; task < nseg * rowwords; task += blockDim.x) {
+        const int seg = task / rowwords, w = task - seg * rowwords;
+        const int ra = seg * per, rb = min(nrow, ra + per);
+        if (ra >= rb) continue;
+        if constexpr (R0 >= 0) {
+            constexpr int W = 2 * R0 + 1;
+            uint32_t win[W];
+#pragma unroll
+            for (int a = 0; a < W - 1; ++a) win[a] = H[(ra + a) * pitch + w];
+            for (int r = ra; r < rb; r += W) {
+#pragma unroll
+                for (int u = 0; u < W; ++u) {
+                    if (r + u < rb) {
+                        win[(u + W - 1) % W] = H[(r + u + W - 1) * pitch + w];
+                        uint32_t acc = 0;
+#pragma unroll
+                        for (int a = 0; a < W; ++a) acc |= win[a];
+                        out[(size_t)(r + u) * rowwords + w] = acc;
+                    }
+                }
+            }
+        } else {
+            for (int r = ra; r < rb; ++r) {
+                uint32_t acc = 0;
+                for (int a = 0; a <= 2 * r0; ++a) acc |= H[(r + a) * pitch + w];
+                out[(size_t)r * rowwords + w] = acc;
+            }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256) spread_codes_kernel(const uint8_t* __restrict__ codes,
                                                            uint32_t* __restrict__ featbits, int To, int Fo, int K,
-                                                           int r0, int r1, int rowwords, int RT) {
+                                                           int r0, int r1, int rowwords, int RT, int pitch) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    const int Kw = (K + 31) >> 5;
     const int b = blockIdx.y;
     const int i0 = blockIdx.x * RT;
     const int rows_in = RT + 2 * r0;
     const int nrow = min(RT, To - i0);
-    uint8_t* scode = smem;                                                                 // [rows_in][Fo]
-    uint32_t* colset = reinterpret_cast<uint32_t*>(smem + ((rows_in * Fo + 15) & ~15));    // [RT][Fo][Kw]
-    uint32_t* wset = colset + RT * Fo * Kw;                                                // [RT][Fo][Kw]
-    int2* wtab = reinterpret_cast<int2*>(wset + RT * Fo * Kw);                             // [rowwords] (j, o) of bit 32w
+    uint32_t* H = reinterpret_cast<uint32_t*>(smem);                    // [rows_in][pitch]
+    uint8_t* scode = smem + (((size_t)rows_in * pitch * 4 + 15) & ~(size_t)15) + 16;   // [rows_in][Fo]
 
-    for (int i = threadIdx.x; i < rows_in * Fo; i += blockDim.x) {
-        int r = i / Fo, j = i - r * Fo;
-        int x0 = i0 - r0 + r;
-        scode[i] = (x0 >= 0 && x0 < To) ? codes[((size_t)b * To + x0) * Fo + j] : 0;
-    }
-    for (int w = threadIdx.x; w < rowwords; w += blockDim.x) {
-        int d = 32 * w;
-        wtab[w] = make_int2(d / K, d % K);
+    const int hwords = rows_in * pitch;
+    for (int i = threadIdx.x * 4; i < ((hwords + 3) & ~3); i += blockDim.x * 4)
+        *reinterpret_cast<uint4*>(H + i) = make_uint4(0u, 0u, 0u, 0u);
+    // stage the code rows (coalesced), rows outside the utterance read as background
+    const long long gfirst = ((long long)b * To + i0 - r0) * Fo;        // byte offset of tile row 0
+    const uint8_t* gsrc = codes + gfirst;
+    const int xlo = max(0, r0 - i0), xhi = min(rows_in, To - i0 + r0);   // tile rows inside the utterance
+    if (((Fo & 3) == 0) && ((reinterpret_cast<uintptr_t>(codes) & 3) == 0)) {
+        const int Fw = Fo >> 2;
+        for (int i = threadIdx.x; i < rows_in * Fw; i += blockDim.x) {
+            const int x0 = i / Fw;
+            reinterpret_cast<uint32_t*>(scode)[i] =
+                (x0 >= xlo && x0 < xhi) ? __ldg(reinterpret_cast<const uint32_t*>(gsrc) + i) : 0u;
+        }
+    } else {
+        for (int i = threadIdx.x; i < rows_in * Fo; i += blockDim.x) {
+            const int x0 = i / Fo;
+            scode[i] = (x0 >= xlo && x0 < xhi) ? __ldg(gsrc + i) : (uint8_t)0;
+        }
     }
     __syncthreads();
-
-    // phase 1: one thread per (row, j) builds the Kw-word set of the 2*r0+1 codes above/below
-    for (int q = threadIdx.x; q < nrow * Fo; q += blockDim.x) {
-        int r = q / Fo, j = q - r * Fo;
-        uint32_t s[TSR_SC_MAX_KW];
-#pragma unroll
-        for (int kw = 0; kw < TSR_SC_MAX_KW; ++kw) s[kw] = 0;
-        for (int a = 0; a <= 2 * r0; ++a) {
-            int p = scode[(r + a) * Fo + j];
-            if (p > 0) {
-                uint32_t bit = 1u << ((p - 1) & 31);
-                int kwp = (p - 1) >> 5;
-#pragma unroll
-                for (int kw = 0; kw < TSR_SC_MAX_KW; ++kw)
-                    if (kw == kwp) s[kw] |= bit;
-            }
+    // A: horizontal dilation into packed rows.  q -> (x1, x0) with x0 fastest (lanes along time).
+    for (int q = threadIdx.x; q < rows_in * Fo; q += blockDim.x) {
+        const int x1 = q / rows_in, x0 = q - x1 * rows_in;
+        const int p = scode[x0 * Fo + x1];
+        if (p > 0) {
+            uint32_t* hrow = H + x0 * pitch;
+            const int jlo = max(0, x1 - r1), jhi = min(Fo - 1, x1 + r1);
+            int d = jlo * K + p - 1;
+            for (int j = jlo; j <= jhi; ++j, d += K) atomicOr(hrow + (d >> 5), 1u << (d & 31));
         }
-#pragma unroll
-        for (int kw = 0; kw < TSR_SC_MAX_KW; ++kw)
-            if (kw < Kw) colset[q * Kw + kw] = s[kw];
     }
     __syncthreads();
-    // phase 2: OR along frequency
-    for (int q = threadIdx.x; q < nrow * Fo; q += blockDim.x) {
-        int r = q / Fo, j = q - r * Fo;
-        int lo = max(0, j - r1), hi = min(Fo - 1, j + r1);
-        uint32_t s[TSR_SC_MAX_KW];
-#pragma unroll
-        for (int kw = 0; kw < TSR_SC_MAX_KW; ++kw) s[kw] = 0;
-        for (int x1 = lo; x1 <= hi; ++x1) {
-            const uint32_t* c = colset + (r * Fo + x1) * Kw;
-#pragma unroll
-            for (int kw = 0; kw < TSR_SC_MAX_KW; ++kw)
-                if (kw < Kw) s[kw] |= c[kw];
-        }
-#pragma unroll
-        for (int kw = 0; kw < TSR_SC_MAX_KW; ++kw)
-            if (kw < Kw) wset[q * Kw + kw] = s[kw];
-    }
-    __syncthreads();
-    // phase 3: gather into tightly packed rows, coalesced 32-bit stores
-    const int D = Fo * K;
-    for (int q = threadIdx.x; q < nrow * rowwords; q += blockDim.x) {
-        int r = q / rowwords, w = q - r * rowwords;
-        uint32_t word = 0;
-        int d = 32 * w;
-        const int dend = min(32 * w + 32, D);
-        int2 jo = wtab[w];
-        int j = jo.x, o = jo.y;
-        while (d < dend) {
-            int n = min(K - o, dend - d);
-            const uint32_t* sp = wset + (r * Fo + j) * Kw;
-            uint32_t lo32 = sp[o >> 5];
-            uint32_t hi32 = ((o >> 5) + 1 < Kw) ? sp[(o >> 5) + 1] : 0u;
-            uint32_t chunk = __funnelshift_r(lo32, hi32, o & 31);
-            if (n < 32) chunk &= (1u << n) - 1u;
-            word |= chunk << (d - 32 * w);
-            d += n;
-            o += n;
-            if (o >= K) { o = 0; ++j; }
-        }
-        featbits[((size_t)b * To + i0 + r) * rowwords + w] = word;
+    uint32_t* out = featbits + ((size_t)b * To + i0) * rowwords;
+    switch (r0) {
+        case 0: sc_vertical_or<0>(H, out, pitch, rowwords, nrow, r0); break;
+        case 1: sc_vertical_or<1>(H, out, pitch, rowwords, nrow, r0); break;
+        case 2: sc_vertical_or<2>(H, out, pitch, rowwords, nrow, r0); break;
+        case 3: sc_vertical_or<3>(H, out, pitch, rowwords, nrow, r0); break;
+        case 5: sc_vertical_or<5>(H, out, pitch, rowwords, nrow, r0); break;
+        default: sc_vertical_or<-1>(H, out, pitch, rowwords, nrow, r0); break;
     }
 }
 
@@ -292,16 +413,62 @@ int tsr_spread_edges(const uint8_t* bits_in, uint8_t* bits_out, int B, int T, in
     }
     int rc = require_sm100("tsr_spread_edges");
     if (rc) return rc;
-    int TT = (block_len > 0 && block_len <= 64) ? block_len : 32;
+    TSR_REQUIRE(B <= 65535, "tsr_spread_edges: B > 65535; split the batch");
+    // fast path: line mode, unit directions, radius 1..3, word-aligned rows
+    if (mode == 0 && radius >= 1 && radius <= 3 && (F & 3) == 0 && ((uintptr_t)bits_in & 3) == 0 && ((uintptr_t)bits_out & 3) == 0) {
+        bool unit = true;
+        SpreadLineMasks mk = {0u, 0u, 0u, 0u};
+        for (int e = 0; e < 8; ++e) {
+            const int df = host_dirs[2 * e], dt = host_dirs[2 * e + 1];
+            if (abs(df) > 1 || abs(dt) > 1) unit = false;
+            const uint32_t bit = 0x01010101u << e;
+            if (df != 0 && dt == 0) mk.h |= bit;
+            else if (df == 0 && dt != 0) mk.v |= bit;
+            else if (df * dt > 0) mk.d |= bit;
+            else if (df * dt < 0) mk.a |= bit;
+        }
+        int RL = 0;     // rows per run: a divisor of block_len in [8,20], else the whole block, else 16
+        if (block_len == 0) RL = 16;
+        else {
+            for (int c = 20; c >= 8 && !RL; --c) if (block_len % c == 0) RL = c;
+            if (!RL && block_len <= 64) RL = block_len;
+        }
+        if (unit && RL) {
+            int TT = block_len == 0 ? 128 : (block_len >= 128 ? block_len : block_len * (128 / block_len));
+            if (TT > T) TT = block_len == 0 ? T : ((T + block_len - 1) / block_len) * block_len;
+            const int wpr = F >> 2;
+            const size_t smem = (size_t)(TT + 2 * radius) * (wpr + 2) * 4;
+            if (smem <= 48 * 1024) {
+                dim3 grid((T + TT - 1) / TT, B);
+                const uint32_t* in32 = reinterpret_cast<const uint32_t*>(bits_in);
+                uint32_t* out32 = reinterpret_cast<uint32_t*>(bits_out);
+                cudaStream_t st = (cudaStream_t)stream;
+                if (radius == 1) spread_edges_line_kernel<1><<<grid, 128, smem, st>>>(in32, out32, T, wpr, TT, RL, block_len, mk);
+                else if (radius == 2) spread_edges_line_kernel<2><<<grid, 128, smem, st>>>(in32, out32, T, wpr, TT, RL, block_len, mk);
+                else spread_edges_line_kernel<3><<<grid, 128, smem, st>>>(in32, out32, T, wpr, TT, RL, block_len, mk);
+                return check_launch("tsr_spread_edges");
+            }
+        }
+    }
+    // sort the taps by dt (insertion sort; <= 160 entries): the kernel reloads a source row per distinct dt
+    for (int i = 1; i < taps.n; ++i)
+        for (int j = i; j > 0 && taps.dt[j - 1] > taps.dt[j]; --j) {
+            std::swap(taps.dt[j - 1], taps.dt[j]);
+            std::swap(taps.df[j - 1], taps.df[j]);
+            std::swap(taps.mask[j - 1], taps.mask[j]);
+        }
+    // tile = about 128 frames, a whole number of blocks when spreading is per block
+    int TT = 128;
+    if (block_len > 0) TT = block_len >= 128 ? block_len : block_len * (128 / block_len);
     if (TT > T) TT = T;
     const int padf = (taps.max_df + 3) & ~3;
     const int pitch = ((F + 3) & ~3) + 2 * padf + 4;
+    while (TT > 8 && (size_t)(TT + 2 * taps.max_dt) * pitch > 64 * 1024) TT = (TT + 1) / 2;
     size_t smem = (size_t)(TT + 2 * taps.max_dt) * pitch;
-    smem = (smem + 15) & ~(size_t)15;
+    smem = ((smem + 15) & ~(size_t)15) + 16;
     TSR_REQUIRE(smem <= 200 * 1024, "tsr_spread_edges: tile does not fit shared memory (F=%d radius=%d)", F, radius);
     if (smem > 48 * 1024)
         TSR_CUDA(cudaFuncSetAttribute(spread_edges_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    TSR_REQUIRE(B <= 65535, "tsr_spread_edges: B > 65535; split the batch");
     dim3 grid((T + TT - 1) / TT, B);
     spread_edges_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(bits_in, bits_out, T, F, TT, block_len, taps);
     return check_launch("tsr_spread_edges");
@@ -317,17 +484,21 @@ int tsr_spread_codes(const uint8_t* codes, uint32_t* featbits, int B, int To, in
     if ((long long)B * To == 0) return TSR_OK;
     int rc = require_sm100("tsr_spread_codes");
     if (rc) return rc;
-    const int Kw = (K + 31) >> 5;
-    int RT = 37;
-    while (RT > 1 && (size_t)2 * RT * Fo * Kw * 4 > 44 * 1024) RT = (RT + 1) / 2;
+    // tile rows: 4 tiles per 296-row utterance at the BASELINE shape (36 KB, 6 CTAs per SM); smaller when
+    // the packed rows are long.  More word columns than threads: several passes over the column range.
+    const int pitch = rowwords | 1;                                  // odd: conflict-free column access
+    int RT = 74;
+    while (RT > 4 && (size_t)(RT + 2 * r0) * (pitch * 4 + Fo) > 96 * 1024) RT = (RT + 1) / 2;
     if (RT > To) RT = To;
-    size_t smem = (((size_t)(RT + 2 * r0) * Fo + 15) & ~(size_t)15) + (size_t)2 * RT * Fo * Kw * 4 + (size_t)rowwords * 8;
+    const size_t hbytes = (((size_t)(RT + 2 * r0) * pitch * 4 + 15) & ~(size_t)15) + 16;
+    size_t smem = hbytes + (((size_t)(RT + 2 * r0) * Fo + 15) & ~(size_t)15);
     TSR_REQUIRE(smem <= 200 * 1024, "tsr_spread_codes: tile does not fit shared memory");
     if (smem > 48 * 1024)
         TSR_CUDA(cudaFuncSetAttribute(spread_codes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     TSR_REQUIRE(B <= 65535, "tsr_spread_codes: B > 65535; split the batch");
     dim3 grid((To + RT - 1) / RT, B);
-    spread_codes_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(codes, featbits, To, Fo, K, r0, r1, rowwords, RT);
+    spread_codes_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(codes, featbits, To, Fo, K, r0, r1, rowwords, RT,
+                                                                     pitch);
     return check_launch("tsr_spread_codes");
 }
 
