@@ -200,7 +200,7 @@ __global__ void __launch_bounds__(128) spread_edges_line_kernel(const uint32_t* 
 // Rows of H outside the utterance stay zero (clipping to the array, code_parts.pyx:445-452).
 template <int R0>
 __device__ __forceinline__ void sc_vertical_or(const uint32_t* __restrict__ H, uint32_t* __restrict__ out, int pitch,
-                                               int rowwords, int nrow, int r0) {
+                                               int rowwords, int nrow, int r0, int D) {
     // tasks = (row segment, word column); a thread takes tasks blockDim.x apart
     const int nseg = max(1, (int)blockDim.x / rowwords);
     const int per = (nrow + nseg - 1) / nseg;
@@ -208,85 +208,118 @@ __device__ __forceinline__ void sc_vertical_or(const uint32_t* __restrict__ H, u
         const int seg = task / rowwords, w = task - seg * rowwords;
         const int ra = seg * per, rb = min(nrow, ra + per);
         if (ra >= rb) continue;
+        // bits >= D of the row are padding and stay zero (out-of-range cells spill into them in phase A)
+        const int live = D - 32 * w;
+        const uint32_t keep = live >= 32 ? 0xFFFFFFFFu : (live <= 0 ? 0u : ((1u << live) - 1u));
+        const uint32_t* hp = H + ra * pitch + w;
+        uint32_t* op = out + (size_t)ra * rowwords + w;
         if constexpr (R0 >= 0) {
             constexpr int W = 2 * R0 + 1;
             uint32_t win[W];
 #pragma unroll
-            for (int a = 0; a < W - 1; ++a) win[a] = H[(ra + a) * pitch + w];
+            for (int a = 0; a < W - 1; ++a) win[a] = hp[a * pitch];
+            hp += (W - 1) * pitch;
             for (int r = ra; r < rb; r += W) {
 #pragma unroll
                 for (int u = 0; u < W; ++u) {
                     if (r + u < rb) {
-                        win[(u + W - 1) % W] = H[(r + u + W - 1) * pitch + w];
+                        win[(u + W - 1) % W] = *hp;
+                        hp += pitch;
                         uint32_t acc = 0;
 #pragma unroll
                         for (int a = 0; a < W; ++a) acc |= win[a];
-                        out[(size_t)(r + u) * rowwords + w] = acc;
+                        *op = acc & keep;
+                        op += rowwords;
                     }
                 }
             }
         } else {
             for (int r = ra; r < rb; ++r) {
                 uint32_t acc = 0;
-                for (int a = 0; a <= 2 * r0; ++a) acc |= H[(r + a) * pitch + w];
-                out[(size_t)r * rowwords + w] = acc;
+                for (int a = 0; a <= 2 * r0; ++a) acc |= hp[a * pitch];
+                *op = acc & keep;
+                hp += pitch;
+                op += rowwords;
             }
         }
     }
 }
 
+// one nonzero code p at column x1 of packed row hrow: bits (x1+k)*K + p-1, |k| <= r1, shifted by the
+// left slack `off` (out-of-range columns land in the slack / padding and are never read back)
+template <int R1>
+__device__ __forceinline__ void sc_scatter(uint32_t* hrow, int d, int K, int r1) {
+    if constexpr (R1 >= 0) {
+#pragma unroll
+        for (int k = 0; k < 2 * R1 + 1; ++k, d += K) atomicOr(hrow + (d >> 5), 1u << (d & 31));
+    } else {
+        for (int k = 0; k <= 2 * r1; ++k, d += K) atomicOr(hrow + (d >> 5), 1u << (d & 31));
+    }
+}
+
+// H rows: [offw slack words | rowwords | right slack]; pitch odd.
+template <int R1>
 __global__ void __launch_bounds__(256) spread_codes_kernel(const uint8_t* __restrict__ codes,
                                                            uint32_t* __restrict__ featbits, int To, int Fo, int K,
-                                                           int r0, int r1, int rowwords, int RT, int pitch) {
+                                                           int r0, int r1, int rowwords, int RT, int pitch, int offw) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const int b = blockIdx.y;
     const int i0 = blockIdx.x * RT;
     const int rows_in = RT + 2 * r0;
     const int nrow = min(RT, To - i0);
     uint32_t* H = reinterpret_cast<uint32_t*>(smem);                    // [rows_in][pitch]
-    uint8_t* scode = smem + (((size_t)rows_in * pitch * 4 + 15) & ~(size_t)15) + 16;   // [rows_in][Fo]
 
     const int hwords = rows_in * pitch;
     for (int i = threadIdx.x * 4; i < ((hwords + 3) & ~3); i += blockDim.x * 4)
         *reinterpret_cast<uint4*>(H + i) = make_uint4(0u, 0u, 0u, 0u);
-    // stage the code rows (coalesced), rows outside the utterance read as background
-    const long long gfirst = ((long long)b * To + i0 - r0) * Fo;        // byte offset of tile row 0
-    const uint8_t* gsrc = codes + gfirst;
+    __syncthreads();
+    // A: horizontal dilation into packed rows.  Rows outside the utterance contribute nothing.
     const int xlo = max(0, r0 - i0), xhi = min(rows_in, To - i0 + r0);   // tile rows inside the utterance
+    const uint8_t* gsrc = codes + ((long long)b * To + i0 - r0) * Fo;   // tile row 0
+    const int dbase = offw * 32 - r1 * K - 1;                            // bit of (column 0 - r1, part 0)
     if (((Fo & 3) == 0) && ((reinterpret_cast<uintptr_t>(codes) & 3) == 0)) {
+        // a thread takes 4 consecutive cells (one 32-bit word of codes); silent rows skip as whole warps
         const int Fw = Fo >> 2;
-        for (int i = threadIdx.x; i < rows_in * Fw; i += blockDim.x) {
-            const int x0 = i / Fw;
-            reinterpret_cast<uint32_t*>(scode)[i] =
-                (x0 >= xlo && x0 < xhi) ? __ldg(reinterpret_cast<const uint32_t*>(gsrc) + i) : 0u;
+        const int n = (xhi - xlo) * Fw;
+        const uint32_t* gw = reinterpret_cast<const uint32_t*>(gsrc) + xlo * Fw;
+        const float inv = 1.0f / (float)Fw;
+        for (int q = threadIdx.x; q < n; q += blockDim.x) {
+            const uint32_t c4 = __ldg(gw + q);
+            if (c4 == 0u) continue;
+            int x0 = (int)(((float)q + 0.5f) * inv);
+            const int wq = q - x0 * Fw;
+            x0 += xlo;
+            uint32_t* hrow = H + x0 * pitch;
+            const int d0 = dbase + 4 * wq * K;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int pcode = (c4 >> (8 * i)) & 255;
+                if (pcode) sc_scatter<R1>(hrow, d0 + i * K + pcode, K, r1);
+            }
         }
     } else {
-        for (int i = threadIdx.x; i < rows_in * Fo; i += blockDim.x) {
-            const int x0 = i / Fo;
-            scode[i] = (x0 >= xlo && x0 < xhi) ? __ldg(gsrc + i) : (uint8_t)0;
-        }
-    }
-    __syncthreads();
-    // A: horizontal dilation into packed rows.  q -> (x1, x0) with x0 fastest (lanes along time).
-    for (int q = threadIdx.x; q < rows_in * Fo; q += blockDim.x) {
-        const int x1 = q / rows_in, x0 = q - x1 * rows_in;
-        const int p = scode[x0 * Fo + x1];
-        if (p > 0) {
-            uint32_t* hrow = H + x0 * pitch;
-            const int jlo = max(0, x1 - r1), jhi = min(Fo - 1, x1 + r1);
-            int d = jlo * K + p - 1;
-            for (int j = jlo; j <= jhi; ++j, d += K) atomicOr(hrow + (d >> 5), 1u << (d & 31));
+        const int n = (xhi - xlo) * Fo;
+        const float inv = 1.0f / (float)Fo;
+        for (int q = threadIdx.x; q < n; q += blockDim.x) {
+            const int pcode = __ldg(gsrc + xlo * Fo + q);
+            if (pcode == 0) continue;
+            int x0 = (int)(((float)q + 0.5f) * inv);
+            const int x1 = q - x0 * Fo;
+            x0 += xlo;
+            sc_scatter<R1>(H + x0 * pitch, dbase + x1 * K + pcode, K, r1);
         }
     }
     __syncthreads();
     uint32_t* out = featbits + ((size_t)b * To + i0) * rowwords;
+    const uint32_t* H0 = H + offw;
+    const int D = Fo * K;
     switch (r0) {
-        case 0: sc_vertical_or<0>(H, out, pitch, rowwords, nrow, r0); break;
-        case 1: sc_vertical_or<1>(H, out, pitch, rowwords, nrow, r0); break;
-        case 2: sc_vertical_or<2>(H, out, pitch, rowwords, nrow, r0); break;
-        case 3: sc_vertical_or<3>(H, out, pitch, rowwords, nrow, r0); break;
-        case 5: sc_vertical_or<5>(H, out, pitch, rowwords, nrow, r0); break;
-        default: sc_vertical_or<-1>(H, out, pitch, rowwords, nrow, r0); break;
+        case 0: sc_vertical_or<0>(H0, out, pitch, rowwords, nrow, r0, D); break;
+        case 1: sc_vertical_or<1>(H0, out, pitch, rowwords, nrow, r0, D); break;
+        case 2: sc_vertical_or<2>(H0, out, pitch, rowwords, nrow, r0, D); break;
+        case 3: sc_vertical_or<3>(H0, out, pitch, rowwords, nrow, r0, D); break;
+        case 5: sc_vertical_or<5>(H0, out, pitch, rowwords, nrow, r0, D); break;
+        default: sc_vertical_or<-1>(H0, out, pitch, rowwords, nrow, r0, D); break;
     }
 }
 
@@ -484,21 +517,36 @@ int tsr_spread_codes(const uint8_t* codes, uint32_t* featbits, int B, int To, in
     if ((long long)B * To == 0) return TSR_OK;
     int rc = require_sm100("tsr_spread_codes");
     if (rc) return rc;
-    // tile rows: 4 tiles per 296-row utterance at the BASELINE shape (36 KB, 6 CTAs per SM); smaller when
-    // the packed rows are long.  More word columns than threads: several passes over the column range.
-    const int pitch = rowwords | 1;                                  // odd: conflict-free column access
+    // packed smem rows: left slack of ceil(r1*K/32) words, the row, right slack for columns Fo..Fo+r1-1;
+    // odd pitch (conflict-free column access).  4 tiles per 296-row utterance at the BASELINE shape.
+    const int offw = (r1 * K + 31) / 32;
+    const int needw = offw + ((Fo + r1) * K + 31) / 32 + 1;
+    const int pitch = (needw > offw + rowwords ? needw : offw + rowwords) | 1;
     int RT = 74;
-    while (RT > 4 && (size_t)(RT + 2 * r0) * (pitch * 4 + Fo) > 96 * 1024) RT = (RT + 1) / 2;
+    while (RT > 4 && (size_t)(RT + 2 * r0) * pitch * 4 > 96 * 1024) RT = (RT + 1) / 2;
     if (RT > To) RT = To;
-    const size_t hbytes = (((size_t)(RT + 2 * r0) * pitch * 4 + 15) & ~(size_t)15) + 16;
-    size_t smem = hbytes + (((size_t)(RT + 2 * r0) * Fo + 15) & ~(size_t)15);
+    size_t smem = (((size_t)(RT + 2 * r0) * pitch * 4 + 15) & ~(size_t)15) + 16;
     TSR_REQUIRE(smem <= 200 * 1024, "tsr_spread_codes: tile does not fit shared memory");
-    if (smem > 48 * 1024)
-        TSR_CUDA(cudaFuncSetAttribute(spread_codes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     TSR_REQUIRE(B <= 65535, "tsr_spread_codes: B > 65535; split the batch");
     dim3 grid((To + RT - 1) / RT, B);
-    spread_codes_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(codes, featbits, To, Fo, K, r0, r1, rowwords, RT,
-                                                                     pitch);
+    cudaStream_t st = (cudaStream_t)stream;
+#define TSR_SC_LAUNCH(R1)                                                                                          \
+    do {                                                                                                           \
+        if (smem > 48 * 1024)                                                                                      \
+            TSR_CUDA(cudaFuncSetAttribute(spread_codes_kernel<R1>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
+                                          (int)smem));                                                             \
+        spread_codes_kernel<R1><<<grid, 256, smem, st>>>(codes, featbits, To, Fo, K, r0, r1, rowwords, RT, pitch, \
+                                                         offw);                                                    \
+    } while (0)
+    switch (r1) {
+        case 0: TSR_SC_LAUNCH(0); break;
+        case 1: TSR_SC_LAUNCH(1); break;
+        case 2: TSR_SC_LAUNCH(2); break;
+        case 3: TSR_SC_LAUNCH(3); break;
+        case 5: TSR_SC_LAUNCH(5); break;
+        default: TSR_SC_LAUNCH(-1); break;
+    }
+#undef TSR_SC_LAUNCH
     return check_launch("tsr_spread_codes");
 }
 
