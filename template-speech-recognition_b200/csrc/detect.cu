@@ -709,21 +709,57 @@ __global__ void detect_float_kernel(const float* __restrict__ Fm, const float* _
 }
 
 // best/arg over templates, first maximum wins (strict >, detect_float_max :268-277).
-__global__ void detect_reduce_kernel(const float* __restrict__ scores, const float* __restrict__ cs, long long R, int T,
-                                     int M, int L, int tail_mode, float* __restrict__ best, uint16_t* __restrict__ arg) {
-    for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < R; g += (long long)gridDim.x * blockDim.x) {
-        const int tl = (int)(g % T);
-        const bool valid = tl <= T - L;
-        float bv = 0.f;
-        int bm = 0;
-        if (valid || tail_mode == 1) {
-            for (int m = 0; m < M; ++m) {
-                float v = (valid ? scores[g * M + m] : 0.f) + (cs ? cs[m] : 0.f);
-                if (m == 0 || v > bv) { bv = v; bm = m; }
+// Eight lanes share a row: lane q takes templates 4q..4q+3 (+32, +64, ...) as one 16-byte load, so a
+// warp reads 4 rows x 128 B contiguously; (value, index) pairs are then combined with three shuffles,
+// the lower index winning ties -- the same result as the sequential strict-> scan.
+__global__ void __launch_bounds__(256) detect_reduce_kernel(const float* __restrict__ scores, const float* __restrict__ cs,
+                                                            long long R, int T, int M, int L, int tail_mode,
+                                                            float* __restrict__ best, uint16_t* __restrict__ arg) {
+    const int q = threadIdx.x & 7;
+    const bool vec = (M & 3) == 0 && (reinterpret_cast<uintptr_t>(scores) & 15) == 0;
+    const long long stride = (long long)gridDim.x * (blockDim.x >> 3);
+    const long long nloop = (R + stride - 1) / stride;          // same trip count for every lane (shuffles below)
+    long long g = blockIdx.x * (long long)(blockDim.x >> 3) + (threadIdx.x >> 3);
+    for (long long it = 0; it < nloop; ++it, g += stride) {
+        const bool live = g < R;
+        const int tl = live ? (int)(g % T) : 0;
+        const bool valid = live && tl <= T - L;
+        float bv = -INFINITY;
+        int bm = 0x7fffffff;
+        if (valid || (live && tail_mode == 1)) {
+            for (int m0 = 4 * q; m0 < M; m0 += 32) {
+                float v[4] = {0.f, 0.f, 0.f, 0.f};
+                if (valid) {
+                    if (vec) {
+                        const float4 x = __ldcs(reinterpret_cast<const float4*>(scores + g * M + m0));
+                        v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w;
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+                            if (m0 + i < M) v[i] = scores[g * M + m0 + i];
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    if (m0 + i < M) {
+                        const float x = v[i] + (cs ? __ldg(cs + m0 + i) : 0.f);
+                        if (x > bv) { bv = x; bm = m0 + i; }
+                    }
+                }
             }
         }
-        if (best) best[g] = bv;
-        if (arg) arg[g] = (uint16_t)bm;
+#pragma unroll
+        for (int off = 4; off >= 1; off >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, bv, off);
+            const int om = __shfl_xor_sync(0xffffffffu, bm, off);
+            if (ov > bv || (ov == bv && om < bm)) { bv = ov; bm = om; }
+        }
+        if (live && q == 0) {
+            if (!(valid || tail_mode == 1)) bv = 0.f;
+            if (bm == 0x7fffffff) bm = 0;
+            if (best) best[g] = bv;
+            if (arg) arg[g] = (uint16_t)bm;
+        }
     }
 }
 
@@ -832,8 +868,8 @@ int tsr_detect_reduce(const float* scores, const float* cs, int B, int T, int M,
     int rc = require_sm100("tsr_detect_reduce");
     if (rc) return rc;
     const long long R = (long long)B * T;
-    long long blocks = (R + 255) / 256;
-    if (blocks > 148LL * 16) blocks = 148LL * 16;
+    long long blocks = (R + 31) / 32;          // 32 rows per 256-thread CTA
+    if (blocks > 148LL * 32) blocks = 148LL * 32;
     detect_reduce_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(scores, cs, R, T, M, L, tail_mode, best, arg);
     return check_launch("tsr_detect_reduce");
 }
