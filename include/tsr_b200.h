@@ -100,6 +100,38 @@ int tsr_code_parts(const uint8_t* bits, const void* parts_blob, int K, int ph, i
                    int mask_threshold, uint8_t* codes, float* scores_or_null, uint16_t* counts_or_null, int B, int T,
                    int F, int impl, void* stream);
 
+/* Replaces the magnitude / auxiliary Bernoulli terms of code_parts.code_parts_mag_aux
+ * (code_parts.pyx:138-242).  scores float [B][To][Fo][K] holds the edge log-likelihoods written by
+ * tsr_code_parts (scores_or_null); on return every gated location (thresh_mask[b][i+ph/2][j+pw/2] != 0,
+ * :191-192) additionally carries, per part k, the sum over the ph window rows of the auxiliary terms
+ * (X_aux uint8 [B][T][aux_dim], log_aux_* double [K][ph*aux_dim], :199-206), the band-magnitude term
+ * (X_mags uint8 [B][T][mag_dim], log_mag_* double [K][ph+mag_dim], :208-210, :232-237) and the
+ * centre-band profile (:218-228); ungated locations are set to 0.  gate_or_null uint8 [B][To][Fo]. */
+int tsr_code_parts_mag_aux_terms(float* scores, uint8_t* gate_or_null, const uint8_t* X_mags, const uint8_t* X_aux,
+                                 const uint8_t* thresh_mask, const double* log_mag_parts, const double* log_mag_invparts,
+                                 const double* log_aux_parts, const double* log_aux_invparts, int B, int T, int F, int K,
+                                 int ph, int pw, int mag_dim, int aux_dim, void* stream);
+
+/* ---- N1: patch extraction for part-dictionary EM ---------------------------------------------
+ * Replaces code_parts.get_parts_mask (code_parts.pyx:297-348) and the edge-count selection of
+ * extract_local_features_tied (extract_local_features.py:36-38).
+ * tsr_patch_counts: counts[b][i][j] = edges of the ph x pw window at (i,j) under the window-relative
+ *   0/1 mask (mask_or_null uint8 [ph][pw], device; null = all ones, _count_edges :18-31).
+ * tsr_patch_select: slot[idx] = rank of location idx among the locations with lo <= count < hi in
+ *   row-major (b,i,j) order -- the reference's patch_id (:331-346) -- or -1; *total = their number.
+ *   workspace: tsr_patch_select_workspace_bytes(n_loc) bytes.
+ * tsr_patch_gather: for every selected location writes patch_set uint8 [n][ph][pw][E] (0/1),
+ *   S_patch double [n][ph][pw] (from S double [B][T][F]), locs uint32 [n][3] = (b,i,j) and/or
+ *   patchbits uint32 [n][tsr_rowwords(ph*pw*E)] (feature (a*pw+c)*E+z: the EM kernels' input). */
+int    tsr_patch_counts(const uint8_t* bits, const uint8_t* mask_or_null, int B, int T, int F, int ph, int pw,
+                        uint32_t* counts, void* stream);
+size_t tsr_patch_select_workspace_bytes(long long n_loc);
+int    tsr_patch_select(const uint32_t* counts, long long n_loc, unsigned int lo, unsigned int hi, int32_t* slot,
+                        uint32_t* total, void* workspace, void* stream);
+int    tsr_patch_gather(const uint8_t* bits, const double* S_or_null, const int32_t* slot, int B, int T, int F, int E,
+                        int ph, int pw, uint8_t* patch_set_or_null, double* S_patch_or_null, uint32_t* locs_or_null,
+                        uint32_t* patchbits_or_null, void* stream);
+
 /* ---- K1b: part-code spreading -----------------------------------------------------------
  * Replaces code_parts.spread_patches (code_parts.pyx:406-457) == spread_waliji_patches
  * (spread_waliji_patches.pyx:15-59).  featbits row (b,i) holds Fo*K features, feature

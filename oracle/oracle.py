@@ -115,6 +115,22 @@ def code_parts_mask(X, M, log_parts, log_invparts, mask_threshold, absolute_thre
     return _code("oracle_code_parts_mask", X, log_parts, log_invparts, mask_threshold, absolute_threshold, M=M)
 
 
+def code_parts_mag_aux(X_edges, X_mags, X_aux, log_parts, log_invparts, log_mag_parts, log_mag_invparts,
+                       log_aux_parts, log_aux_invparts, X_thresh_mask):
+    """code_parts.pyx:138-242"""
+    X = _c(X_edges, np.uint8); Xm = _c(X_mags, np.uint8); Xa = _c(X_aux, np.uint8); tm = _c(X_thresh_mask, np.uint8)
+    lp, lip, lmp, lmip, lap, laip = (_c(a, np.float64) for a in (log_parts, log_invparts, log_mag_parts, log_mag_invparts,
+                                                                  log_aux_parts, log_aux_invparts))
+    T, F, E = X.shape
+    K, ph, pw, _ = lp.shape
+    assert lmp.shape == (K, ph + Xm.shape[1]) and lap.shape == (K, ph * Xa.shape[1])
+    out = np.empty((T - ph + 1, F - pw + 1, K + 1), np.float64)
+    lib().oracle_code_parts_mag_aux(_p(X, _u8), T, F, E, _p(Xm, _u8), Xm.shape[1], _p(Xa, _u8), Xa.shape[1], _p(lp, _f64),
+                                    _p(lip, _f64), _p(lmp, _f64), _p(lmip, _f64), _p(lap, _f64), _p(laip, _f64),
+                                    _p(tm, _u8), K, ph, pw, _p(out, _f64))
+    return out
+
+
 def spread_patches(X, r0, r1, num_parts):
     """code_parts.pyx:406-457 == spread_waliji_patches.pyx:15-59"""
     X = _c(X, np.int64)

@@ -128,6 +128,54 @@ void oracle_code_parts_mask(const uint8_t *X, int T, int F, int E, const uint8_t
         }
 }
 
+/* ---- code_parts.pyx:138-242  code_parts_mag_aux -------------------------------------
+ * Same loop nest and float64 accumulation order as the reference: per window row i the
+ * auxiliary terms (:199-206), then per column j the band-magnitude flag (:209-210), the edge
+ * terms (:211-217) and -- at the centre column only -- the band profile (:218-228), then the
+ * row's magnitude term (:232-237).  Gate: X_thresh_mask at the window centre (:191-192).
+ * All index arithmetic is unsigned-int C division, as in the Cython. */
+void oracle_code_parts_mag_aux(const uint8_t *X, int T, int F, int E, const uint8_t *X_mags, int mag_dim,
+                               const uint8_t *X_aux, int aux_dim, const double *lp, const double *lip,
+                               const double *lmp, const double *lmip, const double *lap, const double *laip,
+                               const uint8_t *tmask, int K, int ph, int pw, double *out)
+{
+    const int To = T - ph + 1, Fo = F - pw + 1;
+    const size_t stride = (size_t)ph * pw * E;
+    const int magw = ph + mag_dim, auxw = ph * aux_dim;
+    memset(out, 0, sizeof(double) * (size_t)To * Fo * (K + 1));
+    for (unsigned int i0 = 0; i0 < (unsigned int)To; ++i0)
+        for (unsigned int j0 = 0; j0 < (unsigned int)Fo; ++j0) {
+            double *o = out + ((size_t)i0 * Fo + j0) * (K + 1);
+            if (!tmask[(size_t)(i0 + ph / 2) * F + (j0 + pw / 2)]) { o[0] = 0.0; continue; }
+            o[0] = -INFINITY;
+            for (unsigned int i = 0; i < (unsigned int)ph; ++i) {
+                unsigned int tmp_freq_mag = 0;
+                for (unsigned int j = 0; j < (unsigned int)aux_dim; ++j) {
+                    const double *tab = X_aux[(size_t)(i0 + i) * aux_dim + j] ? lap : laip;
+                    for (int k = 0; k < K; ++k) o[k + 1] += tab[(size_t)k * auxw + i * aux_dim + j];
+                }
+                for (unsigned int j = 0; j < (unsigned int)pw; ++j) {
+                    if (X_mags[(size_t)(i0 + i) * mag_dim + (((j0 + j) * (unsigned int)mag_dim) / (unsigned int)F)]) tmp_freq_mag = 1;
+                    for (int z = 0; z < E; ++z) {
+                        const size_t w = ((size_t)i * pw + j) * E + z;
+                        const double *tab = X[((size_t)(i0 + i) * F + (j0 + j)) * E + z] ? lp : lip;
+                        for (int k = 0; k < K; ++k) o[k + 1] += tab[k * stride + w];
+                    }
+                    if (j == (unsigned int)pw / 2)
+                        for (unsigned int q = 0; q < (unsigned int)mag_dim; ++q) {
+                            const unsigned int c = ((j0 + j) * (unsigned int)mag_dim) / (unsigned int)F;
+                            const double *tab = ((c - q) * (c - q) > 1) ? lmip : lmp;
+                            for (int k = 0; k < K; ++k) o[k + 1] += tab[(size_t)k * magw + q + ph];
+                        }
+                }
+                {
+                    const double *tab = tmp_freq_mag ? lmp : lmip;
+                    for (int k = 0; k < K; ++k) o[k + 1] += tab[(size_t)k * magw + i];
+                }
+            }
+        }
+}
+
 /* ---- code_parts.pyx:406-457 spread_patches == spread_waliji_patches.pyx:15-59 -------
  * X int64 (D0,D1) codes (0 = background); out uint8 (D0,D1,K), zeroed here. */
 void oracle_spread_patches(const int64_t *X, int D0, int D1, int r0, int r1, int K, uint8_t *out)

@@ -26,6 +26,11 @@ SIGNATURES = {
     "tsr_parts_blob_bytes": (_sz, [_i, _i, _i]),
     "tsr_prepare_parts": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _i, _vp, _vp]),
     "tsr_code_parts": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "tsr_code_parts_mag_aux_terms": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "tsr_patch_counts": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
+    "tsr_patch_select_workspace_bytes": (_sz, [_ll]),
+    "tsr_patch_select": (_i, [_vp, _ll, ctypes.c_uint, ctypes.c_uint, _vp, _vp, _vp, _vp]),
+    "tsr_patch_gather": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "tsr_spread_codes": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "tsr_spread_graph": (_i, [_vp, _vp, _ll, _i, _i, _i, _vp]),
     "tsr_filter_blob_bytes": (_sz, [_i, _i, _i, _i]),

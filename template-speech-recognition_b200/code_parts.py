@@ -90,15 +90,58 @@ def code_parts_mask(X, M, log_parts, log_invparts, mask_threshold, absolute_thre
     return out
 
 
-def code_parts_mag_aux(*args, **kwargs):
-    """code_parts.pyx:138-242 (magnitude / auxiliary-feature variant) is outside the hot-path
-    scope (not in any BASELINE config)."""
-    raise NotImplementedError("code_parts_mag_aux is not part of the B200 scoring path (SURVEY §8 A4)")
+def code_parts_mag_aux(X_edges, X_mags, X_aux, log_parts, log_invparts, log_mag_parts, log_mag_invparts,
+                       log_aux_parts, log_aux_invparts, X_thresh_mask):
+    """code_parts.pyx:138-242: edge log-likelihoods plus band-magnitude and auxiliary Bernoulli terms,
+    gated by X_thresh_mask at the window centre (:191-192; no edge-count threshold).  The edge
+    contraction runs on the tensor kernel, the extra terms in tsr_code_parts_mag_aux_terms."""
+    X = typed(X_edges, np.uint8, 3, "UINT_t")
+    Xm = typed(X_mags, np.uint8, 2, "UINT_t")
+    Xa = typed(X_aux, np.uint8, 2, "UINT_t")
+    parts = _parts(log_parts, log_invparts)
+    tabs = [typed(t, np.float64, 2, "DTYPE_t") for t in (log_mag_parts, log_mag_invparts, log_aux_parts, log_aux_invparts)]
+    Tm = typed(X_thresh_mask, np.uint8, 2, "UINT_t")
+    if X.shape[2] != parts.E:
+        raise ValueError("X has %d edge types but the parts have %d" % (X.shape[2], parts.E))
+    if Xm.shape[0] != X.shape[0] or Xa.shape[0] != X.shape[0] or Tm.shape != X.shape[:2]:
+        raise ValueError("X_mags, X_aux and X_thresh_mask must follow the first dimensions of X_edges")
+    bits = ops.pack_edges(to_dev(X[None]))
+    _, scores, _ = ops.code_parts(bits, parts, 0, want_codes=False, want_scores=True)
+    gate = ops.code_parts_mag_aux_terms(scores, to_dev(Xm[None]), to_dev(Xa[None]), to_dev(Tm[None]),
+                                        *[to_dev(t) for t in tabs], parts.ph, parts.pw)
+    gate = gate[0].cpu().numpy() != 0
+    out = np.zeros(gate.shape + (parts.K + 1,), np.float64)
+    out[..., 1:] = scores[0].cpu().numpy()
+    out[..., 0] = np.where(gate, -np.inf, 0.0)
+    return out
 
 
 def get_parts_mask(X, M, S, threshold):
-    """code_parts.pyx:297-348: patch extraction for part-dictionary EM ("next" row N1)."""
-    raise NotImplementedError("get_parts_mask is a 'next' row (SURVEY §8(f) N1), not built yet")
+    """code_parts.pyx:297-348: every ph x pw x E patch whose masked edge count is >= threshold, in
+    row-major order, with the matching spectrogram patches, the count map and the patch origins.
+    Returns (patch_set uint8 (n,ph,pw,E), S_patch_set float64 (n,ph,pw), patch_counts uint32 (To,Fo),
+    patch_locs uint32 (n,2)).  The 2-D mask is window-relative (see code_parts_mask)."""
+    X = typed(X, np.uint8, 3, "UINT_t")
+    M = typed(M, np.uint8, 2, "UINT_t")
+    S = typed(S, np.float64, 2, "DTYPE_t")
+    ph, pw = M.shape
+    if X.shape[0] < ph or X.shape[1] < pw:
+        raise ValueError("X (%d,%d) is smaller than the mask window (%d,%d)" % (X.shape[0], X.shape[1], ph, pw))
+    if S.shape != X.shape[:2]:
+        raise ValueError("S must have the first two dimensions of X")
+    if X.shape[2] > 8:
+        raise ValueError("more than 8 edge types per location are not supported by the packed representation")
+    bits = ops.pack_edges(to_dev(X[None]))
+    r = ops.extract_patches(bits, ph, pw, _unsigned_threshold(threshold), mask=to_dev((M != 0).astype(np.uint8)),
+                            S=to_dev(S[None]), E=X.shape[2], want_bytes=True, want_bits=False)
+    # the reference copies the raw bytes of X; nonzero values other than 1 are restored from X here
+    locs = r["locs"].cpu().numpy().astype(np.uint32)[:, 1:]
+    patches = r["patches"].cpu().numpy()
+    if X.max(initial=0) > 1 and len(locs):
+        ii = locs[:, 0, None, None] + np.arange(ph)[None, :, None]
+        jj = locs[:, 1, None, None] + np.arange(pw)[None, None, :]
+        patches = X[ii, jj]
+    return patches, r["S_patches"].cpu().numpy(), r["counts"][0].cpu().numpy().astype(np.uint32), locs
 
 
 def _check_codes(X, num_parts):

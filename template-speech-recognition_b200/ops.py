@@ -138,6 +138,78 @@ def code_parts(bits, parts, threshold, mask_threshold=-1, want_codes=True, want_
     return codes, scores, counts
 
 
+def code_parts_mag_aux_terms(scores, X_mags, X_aux, thresh_mask, log_mag_parts, log_mag_invparts, log_aux_parts,
+                             log_aux_invparts, ph, pw):
+    """In place on scores float32 (B,To,Fo,K) (edge log-likelihoods from code_parts): adds the magnitude
+    and auxiliary terms of code_parts_mag_aux (code_parts.pyx:195-239) at gated locations, zeroes the
+    rest.  Returns the gate uint8 (B,To,Fo)."""
+    scores = _dev(scores, torch.float32, "scores")
+    X_mags, X_aux, thresh_mask = (_dev(t, torch.uint8, n) for t, n in ((X_mags, "X_mags"), (X_aux, "X_aux"), (thresh_mask, "X_thresh_mask")))
+    tabs = [_dev(t, torch.float64, "log tables") for t in (log_mag_parts, log_mag_invparts, log_aux_parts, log_aux_invparts)]
+    B, To, Fo, K = scores.shape
+    T, F = To + ph - 1, Fo + pw - 1
+    mag_dim, aux_dim = X_mags.shape[2], X_aux.shape[2]
+    if tuple(thresh_mask.shape) != (B, T, F) or X_mags.shape[:2] != (B, T) or X_aux.shape[:2] != (B, T):
+        raise ValueError("X_mags / X_aux / X_thresh_mask do not match the edge map shape")
+    if tuple(tabs[0].shape) != (K, ph + mag_dim) or tabs[1].shape != tabs[0].shape:
+        raise ValueError("log_mag_parts must be (K, part_x_dim + mag_dim)")
+    if tuple(tabs[2].shape) != (K, ph * aux_dim) or tabs[3].shape != tabs[2].shape:
+        raise ValueError("log_aux_parts must be (K, part_x_dim * aux_dim)")
+    gate = torch.empty((B, To, Fo), dtype=torch.uint8, device=scores.device)
+    _lib.call("tsr_code_parts_mag_aux_terms", _ptr(scores), _ptr(gate), _ptr(X_mags), _ptr(X_aux), _ptr(thresh_mask),
+              _ptr(tabs[0]), _ptr(tabs[1]), _ptr(tabs[2]), _ptr(tabs[3]), B, T, F, K, int(ph), int(pw), mag_dim, aux_dim,
+              _stream())
+    return gate
+
+
+# ------------------------------------------------------------------------------- N1
+def patch_counts(bits, ph, pw, mask=None):
+    """bits uint8 (B,T,F) -> int32 (B,To,Fo) edge counts of every ph x pw window (under the 0/1 window mask)."""
+    bits = _dev(bits, torch.uint8, "bits")
+    B, T, F = bits.shape
+    if T < ph or F < pw:
+        raise ValueError("input (%d,%d) smaller than the window (%d,%d)" % (T, F, ph, pw))
+    if mask is not None:
+        mask = _dev(mask, torch.uint8, "mask")
+        if tuple(mask.shape) != (ph, pw):
+            raise ValueError("mask must be (%d,%d)" % (ph, pw))
+    counts = torch.empty((B, T - ph + 1, F - pw + 1), dtype=torch.int32, device=bits.device)
+    _lib.call("tsr_patch_counts", _ptr(bits), _ptr(mask), B, T, F, int(ph), int(pw), _ptr(counts), _stream())
+    return counts
+
+
+def extract_patches(bits, ph, pw, lo, hi=None, mask=None, S=None, E=8, want_bytes=False, want_bits=True):
+    """Ordered compaction of the windows with lo <= count < hi (code_parts.pyx:316-347).
+    Returns dict(counts, n, locs (n,3) int32 (b,i,j), bits (n,rowwords) int32 | None,
+    patches (n,ph,pw,E) uint8 | None, S_patches (n,ph,pw) float64 | None).  One device->host read
+    of the patch count sizes the outputs."""
+    counts = patch_counts(bits, ph, pw, mask)
+    B, T, F = bits.shape
+    n_loc = counts.numel()
+    dev = bits.device
+    slot = torch.empty(n_loc, dtype=torch.int32, device=dev)
+    total = torch.zeros(1, dtype=torch.int32, device=dev)
+    ws = torch.empty(max(_lib.lib().tsr_patch_select_workspace_bytes(n_loc), 4), dtype=torch.uint8, device=dev)
+    lo = max(0, min(int(lo), 2 ** 32 - 1))
+    hi = 2 ** 32 - 1 if hi is None else max(0, min(int(hi), 2 ** 32 - 1))
+    _lib.call("tsr_patch_select", _ptr(counts), n_loc, lo, hi, _ptr(slot), _ptr(total), _ptr(ws), _stream())
+    n = int(total.item())
+    rw = rowwords(ph * pw * E)
+    locs = torch.empty((n, 3), dtype=torch.int32, device=dev)
+    pbits = torch.empty((n, rw), dtype=torch.int32, device=dev) if want_bits else None
+    pset = torch.empty((n, ph, pw, E), dtype=torch.uint8, device=dev) if want_bytes else None
+    Sp = None
+    if S is not None:
+        S = _dev(S, torch.float64, "S")
+        if tuple(S.shape) != (B, T, F):
+            raise ValueError("S must match the edge map shape")
+        Sp = torch.empty((n, ph, pw), dtype=torch.float64, device=dev)
+    if n:
+        _lib.call("tsr_patch_gather", _ptr(bits), _ptr(S), _ptr(slot), B, T, F, int(E), int(ph), int(pw), _ptr(pset), _ptr(Sp),
+                  _ptr(locs), _ptr(pbits), _stream())
+    return dict(counts=counts, n=n, locs=locs, bits=pbits, patches=pset, S_patches=Sp)
+
+
 # ------------------------------------------------------------------------------ K1b
 def spread_codes(codes, K, r0, r1):
     """codes uint8 (B,To,Fo) -> featbits int32 (B,To,rowwords(Fo*K))."""

@@ -42,6 +42,19 @@ def main():
     P2 = np.clip(rs.rand(4, 3, 4, 8) ** 2, .01, .99)
     out.update(cp2_lp=np.log(P2), cp2_lip=np.log(1 - P2))
     out["cp2_out"] = cp.code_parts(X, np.log(P2), np.log(1 - P2), 5)
+    # ---- code_parts_mag_aux (code_parts.pyx:138-242): 6 magnitude bands, 3 auxiliary features
+    Xm = (rs.rand(22, 6) < 0.4).astype(np.uint8)
+    Xa = (rs.rand(22, 3) < 0.5).astype(np.uint8)
+    tm = (rs.rand(22, 13) < 0.6).astype(np.uint8)
+    Pm, Pa = np.clip(rs.rand(7, 5 + 6), .01, .99), np.clip(rs.rand(7, 5 * 3), .01, .99)
+    out.update(ma_Xm=Xm, ma_Xa=Xa, ma_tm=tm, ma_lmp=np.log(Pm), ma_lmip=np.log(1 - Pm), ma_lap=np.log(Pa), ma_laip=np.log(1 - Pa))
+    out["ma_out"] = cp.code_parts_mag_aux(X, Xm, Xa, lp, lip, np.log(Pm), np.log(1 - Pm), np.log(Pa), np.log(1 - Pa), tm)
+    # ---- get_parts_mask (code_parts.pyx:297-348) on a single window (the reference indexes the mask with
+    # absolute coordinates, so only the first window of a larger map is well defined)
+    Mk = (rs.rand(5, 5) < 0.6).astype(np.uint8)
+    Sx = rs.randn(5, 5)
+    ps, Sp, pc, pl = cp.get_parts_mask(X[8:13, 3:8].copy(), Mk, Sx, 3)
+    out.update(gp_M=Mk, gp_S=Sx, gp_patches=ps, gp_Sp=Sp, gp_counts=pc, gp_locs=pl)
     # ---- detection: F (40,6,5), L = 9
     F = (rs.rand(40, 6, 5) < 0.2).astype(np.uint8)
     LF = rs.randn(9, 6, 5).astype(np.float32)

@@ -88,5 +88,9 @@ def test_cython_style_argument_errors():
         code_parts.spread_patches(np.zeros((70000, 1), np.int64), 1, 1, 3)
     with pytest.raises(ValueError, match="Buffer dtype mismatch"):
         clf.detect(np.zeros((4, 2, 2), np.uint8), np.zeros((2, 2, 2), np.float64))
-    with pytest.raises(NotImplementedError):
-        code_parts.code_parts_mag_aux()
+    z2, z4 = np.zeros((8, 2), np.uint8), np.zeros((3, 5, 5, 8))
+    with pytest.raises(ValueError, match="Buffer dtype mismatch"):   # X_mags must be uint8 (code_parts.pyx:137)
+        code_parts.code_parts_mag_aux(np.zeros((8, 8, 8), np.uint8), z2.astype(np.float64), z2, z4, z4, np.zeros((3, 7)),
+                                      np.zeros((3, 7)), np.zeros((3, 10)), np.zeros((3, 10)), np.zeros((8, 8), np.uint8))
+    with pytest.raises(ValueError, match="wrong number of dimensions"):
+        code_parts.get_parts_mask(np.zeros((8, 8), np.uint8), np.ones((5, 5), np.uint8), np.zeros((8, 8)), 3)

@@ -21,6 +21,19 @@ def test_code_parts_golden(oracle, golden):
     assert gate.any() and (~gate).any()
 
 
+def test_code_parts_mag_aux_and_get_parts_mask_golden(oracle, golden):
+    g = golden
+    out = oracle.code_parts_mag_aux(g["cp_X"], g["ma_Xm"], g["ma_Xa"], g["cp_lp"], g["cp_lip"], g["ma_lmp"], g["ma_lmip"],
+                                    g["ma_lap"], g["ma_laip"], g["ma_tm"])
+    np.testing.assert_array_equal(out, g["ma_out"])          # same loop nest, same f64 arithmetic: bit-exact
+    gate = g["ma_out"][..., 0] != 0
+    assert gate.any() and (~gate).any()
+    ps, Sp, pc, pl = oracle.get_parts_mask(g["cp_X"][8:13, 3:8], g["gp_M"], g["gp_S"], 3)
+    for a, b in ((ps, g["gp_patches"]), (Sp, g["gp_Sp"]), (pc, g["gp_counts"]), (pl, g["gp_locs"])):
+        assert a.dtype == b.dtype
+        np.testing.assert_array_equal(a, b)
+
+
 def test_spread_patches_golden(oracle, golden):
     g = golden
     np.testing.assert_array_equal(oracle.spread_patches(g["cp_codes"], 2, 2, 7), g["sp_22"])
@@ -75,6 +88,23 @@ def test_against_compiled_reference(oracle, ref, seed):
     o = oracle.code_parts_mask(X[:5, :5], M, lp, lip, 0, 0)
     r = cp.code_parts_mask(X[:5, :5].copy(), M, lp, lip, 0, 0)
     np.testing.assert_array_equal(o, r)
+
+
+@pytest.mark.parametrize("seed", [0, 1])
+def test_mag_aux_against_compiled_reference(oracle, ref, seed):
+    if ref is None:
+        pytest.skip("oracle/_ref not built (no /root/reference here)")
+    rs = np.random.RandomState(100 + seed)
+    T, F, K, md, ad = rs.randint(8, 30), rs.randint(6, 20), rs.randint(1, 9), rs.randint(1, 9), rs.randint(0, 4)
+    X = (rs.rand(T, F, 8) < 0.2).astype(np.uint8)
+    Xm, Xa, tm = ((rs.rand(*sh) < 0.5).astype(np.uint8) for sh in ((T, md), (T, ad), (T, F)))
+    tabs = []
+    for sh in ((K, 5, 5, 8), (K, 5 + md), (K, 5 * ad)):
+        P = np.clip(rs.rand(*sh), .01, .99)
+        tabs += [np.log(P), np.log(1 - P)]
+    a = oracle.code_parts_mag_aux(X, Xm, Xa, *tabs, tm)
+    b = ref[0].code_parts_mag_aux(X, Xm, Xa, *tabs, tm)
+    np.testing.assert_array_equal(a, b)
 
 
 def test_reference_rejects_float32_parts(ref):
