@@ -28,6 +28,7 @@ namespace tsr {
 
 #define DT_MSUB_MAX 3
 #define DT_MAX_STAGES 4
+#define DT_MAX_BSTAGES 8   // I8: ring of 64-feature filter tiles
 #define DT_THREADS 448     // 14 warps: <= 144 registers per thread
 #define DT_PRODUCERS 256   // two groups of 128 expander threads
 #define DT_TAU_CHUNK 40    // diagonal sums are staged through smem in chunks of <= 40 filter frames
@@ -48,7 +49,9 @@ struct FilterLayout {
     int ntiles;   // ceil(M*vpt / tptv)
     int msub;     // 128-row accumulators per step (msub*NT <= 512)
     int nstage;   // smem pipeline depth
-    int fps;      // features per pipeline stage: 64 (F16, 8 k-groups of 8) or 128 (I8, 8 k-groups of 16)
+    int fps;      // features per filter tile: 64 (F16: 8 k-groups of 8 halves; I8: 4 k-groups of 16 bytes)
+    int ncf;      // I8: 128-feature chunks per frame; the expanded frame strip of a chunk serves all `fold` phases
+    int strip_rows, kgs;   // I8: rows of an A strip (msub*128 + fold - 1, rounded up to 8) and its k-group stride in bytes
     int fold;     // frames folded into the contraction ("super-row" = fold consecutive frames); 1 for F16
     int Lf;       // columns per group = ceil(L / fold): column tau' covers frames tau'*fold .. +fold-1
     int Lc;       // fold * (Lf - 1): row shift of the last column = unfinished rows carried between steps
@@ -65,7 +68,9 @@ __host__ __device__ inline FilterLayout filter_layout(int M, int L, int D, int p
     f.kind = (planes == TSR_PLANES_INT8X2 || planes == TSR_PLANES_INT8X3) ? 1 : 0;
     f.P = planes == TSR_PLANES_INT8X3 ? 3 : 2;
     f.vpt = f.kind ? f.P : 1;
-    f.fps = f.kind ? 128 : 64;
+    f.fps = 64;
+    f.ncf = (f.rowwords * 32 + 127) / 128;
+    f.strip_rows = f.kgs = 0;
     f.hdr_bytes = 128 + (((size_t)M * 4 + 127) & ~(size_t)127);
     // Frame folding (I8 only: integer accumulation is exact however long the chain).  Folding `fold`
     // consecutive frames into K divides the number of (row, column) products the epilogue has to
@@ -91,7 +96,8 @@ __host__ __device__ inline FilterLayout filter_layout(int M, int L, int D, int p
     f.Lf = (L + f.fold - 1) / f.fold;
     f.Lc = f.fold * (f.Lf - 1);
     f.Kf = f.fold * f.rowwords * 32;
-    f.nchunks = (f.Kf + f.fps - 1) / f.fps;
+    // I8 contraction order: (frame chunk cf, phase phi, 64-feature half) -- one expanded A strip per cf
+    f.nchunks = f.kind ? f.ncf * f.fold * 2 : (f.Kf + f.fps - 1) / f.fps;
     int tptv = (DT_NT_MAX / (f.vpt * f.Lf)) * f.vpt;
     if (tptv < f.vpt) tptv = f.vpt;
     if (tptv > M * f.vpt) tptv = M * f.vpt;
@@ -102,14 +108,23 @@ __host__ __device__ inline FilterLayout filter_layout(int M, int L, int D, int p
         f.ntiles = (M * f.vpt + tptv - 1) / tptv;
         int msub = 512 / f.NT;
         f.msub = msub > msub_cap ? msub_cap : msub;
-        f.tile_bytes = f.kind ? (size_t)f.NT * 128 : (size_t)2 * f.NT * 128;
-        const size_t stage = (size_t)f.msub * 16384 + f.tile_bytes;
+        f.tile_bytes = f.kind ? (size_t)f.NT * 64 : (size_t)2 * f.NT * 128;
         const size_t fixed = (((128 + DT_TAU_CHUNK) * (DT_TAU_CHUNK + 1) * 4 + 127) & ~(size_t)127) +
                              ((((size_t)f.msub * 128 + f.Lc + 1) * f.tptv * 4 + 127) & ~(size_t)127) + 512;
         const long long avail = 227 * 1024 - (long long)fixed;
-        int ns = avail > 0 ? (int)(avail / (long long)stage) : 0;
+        int ns;
+        if (f.kind) {   // two A strips + a ring of filter tiles
+            f.strip_rows = (f.msub * 128 + f.fold - 1 + 7) & ~7;
+            f.kgs = f.strip_rows * 16;
+            const long long rest = avail - 2LL * 8 * f.kgs;
+            ns = rest > 0 ? (int)(rest / (long long)f.tile_bytes) : 0;
+        } else {
+            const size_t stage = (size_t)f.msub * 16384 + f.tile_bytes;
+            ns = avail > 0 ? (int)(avail / (long long)stage) : 0;
+        }
         if (ns >= 2 || (f.msub == 1 && tptv == f.vpt)) {
-            f.nstage = ns < 2 ? 2 : (ns > DT_MAX_STAGES ? DT_MAX_STAGES : ns);
+            const int cap = f.kind ? DT_MAX_BSTAGES : DT_MAX_STAGES;
+            f.nstage = ns < 2 ? 2 : (ns > cap ? cap : ns);
             break;
         }
         if (f.msub > 1) msub_cap = f.msub - 1;
@@ -160,9 +175,16 @@ __global__ void prepare_filters_kernel(const float* __restrict__ LF, uint8_t* __
         const int n = (int)(r % f.NT); r /= f.NT;
         const int c = (int)(r % f.nchunks);
         const int nt = (int)(r / f.nchunks);
-        const int kf = c * f.fps + dd;                 // position in the folded contraction
-        const int dpad = f.rowwords * 32;
-        const int phi = kf / dpad, d = kf - phi * dpad; // frame within the super-row, feature within the frame
+        int phi, d;                                     // frame within the super-row, feature within the frame
+        if (f.kind) {   // chunk c = (cf * fold + phi) * 2 + half
+            const int half = c & 1, cp = c >> 1;
+            phi = cp % f.fold;
+            d = (cp / f.fold) * 128 + half * 64 + dd;
+        } else {
+            const int kf = c * f.fps + dd;              // position in the contraction (fold == 1)
+            const int dpad = f.rowwords * 32;
+            phi = kf / dpad; d = kf - phi * dpad;
+        }
         const int vl = n / f.Lf, tauf = n - vl * f.Lf;
         const int tau = tauf * f.fold + phi;
         const int v = nt * f.tptv + vl;
@@ -217,15 +239,26 @@ struct DetectArgs {
     } while (0)
 
 struct DetectSmem {
-    uint32_t b, stage, outacc, bars, stage_bytes, a_bytes, a_sub, total;
+    uint32_t b, stage, outacc, bars, stage_bytes, a_bytes, a_sub, strip_bytes, total;
 };
+// F16: nstage stages of [msub A sub-tiles | filter tile].  I8: two A strips, then a ring of nstage filter tiles.
 __host__ __device__ inline DetectSmem detect_smem_layout(const FilterLayout& f) {
     DetectSmem S;
-    S.a_sub = 16384;   // 128 rows x 128 bytes per sub-tile and stage for both kinds
-    S.a_bytes = f.msub * S.a_sub;
-    S.stage_bytes = S.a_bytes + (uint32_t)f.tile_bytes;
-    S.b = S.a_bytes;                                   // within a stage
-    S.stage = f.nstage * S.stage_bytes;                // epilogue staging [128][TC+1] words
+    S.a_sub = 16384;   // F16: 128 rows x 128 bytes per sub-tile and stage
+    if (f.kind) {
+        S.strip_bytes = 8u * (uint32_t)f.kgs;
+        S.a_bytes = 2 * S.strip_bytes;
+        S.stage_bytes = (uint32_t)f.tile_bytes;
+        S.b = S.a_bytes;                               // start of the tile ring
+        S.stage = S.b + f.nstage * S.stage_bytes;
+    } else {
+        S.strip_bytes = 0;
+        S.a_bytes = f.msub * S.a_sub;
+        S.stage_bytes = S.a_bytes + (uint32_t)f.tile_bytes;
+        S.b = S.a_bytes;                               // within a stage
+        S.stage = f.nstage * S.stage_bytes;            // epilogue staging [128][TC+1] words
+    }
+    S.stage = (S.stage + 127) & ~127u;
     S.outacc = S.stage + (((128 + DT_TAU_CHUNK) * (DT_TAU_CHUNK + 1) * 4 + 127) & ~127u);
     S.bars = S.outacc + (((f.msub * 128 + f.Lc + 1) * f.tptv * 4 + 127) & ~127u);
     S.total = S.bars + 256;
@@ -257,9 +290,11 @@ __global__ void __launch_bounds__(DT_THREADS, 1) detect_tc_kernel(DetectArgs A) 
     extern __shared__ __align__(1024) uint8_t smem[];
     const FilterLayout& f = A.f;
     const DetectSmem S = detect_smem_layout(f);
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S.bars);   // [DT_MAX_STAGES]
-    uint64_t* empty_bar = full_bar + DT_MAX_STAGES;                    // [DT_MAX_STAGES]
-    uint64_t* tfull_bar = empty_bar + DT_MAX_STAGES;                   // [1]
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S.bars);   // [DT_MAX_BSTAGES]  (I8: filter tile landed)
+    uint64_t* empty_bar = full_bar + DT_MAX_BSTAGES;                   // [DT_MAX_BSTAGES]
+    uint64_t* afull_bar = empty_bar + DT_MAX_BSTAGES;                  // [2]  I8: A strip expanded
+    uint64_t* aempty_bar = afull_bar + 2;                              // [2]
+    uint64_t* tfull_bar = aempty_bar + 2;                              // [1]
     uint64_t* tempty_bar = tfull_bar + 1;                              // [DT_MSUB_MAX]
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty_bar + DT_MSUB_MAX);
 
@@ -270,7 +305,8 @@ __global__ void __launch_bounds__(DT_THREADS, 1) detect_tc_kernel(DetectArgs A) 
     const long long nunits = (long long)f.ntiles * A.units_per_ntile;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < DT_MAX_STAGES; ++s) { mbar_init(&full_bar[s], DT_PRODUCERS / 2 + 1); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < DT_MAX_BSTAGES; ++s) { mbar_init(&full_bar[s], I8 ? 1 : DT_PRODUCERS / 2 + 1); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&afull_bar[s], DT_PRODUCERS); mbar_init(&aempty_bar[s], 1); }
         mbar_init(tfull_bar, 1);
         for (int s = 0; s < DT_MSUB_MAX; ++s) mbar_init(&tempty_bar[s], 128);
         mbar_fence_init();
@@ -287,6 +323,60 @@ __global__ void __launch_bounds__(DT_THREADS, 1) detect_tc_kernel(DetectArgs A) 
         // one row of each 128-row sub-tile per stage it owns.  The proxy fence + mbarrier arrive that end a
         // stage cost several hundred cycles of latency; alternating groups overlaps them with the other
         // group's expansion work.
+        if constexpr (I8) {
+            // I8: all 8 warps expand one A strip per 128-feature frame chunk: rows = the step's frames plus
+            // fold-1 more, 8 k-groups of 16 bytes each, k-group stride kgs.  Row r of phase phi's A tile is
+            // strip row r + phi, so the strip is expanded once and read by all `fold` phases.
+            const int tid = threadIdx.x - 32;                // 0..255
+            const int nw2 = f.rowwords >> 1;                 // 64-bit words per frame
+            const int srows = step_rows + f.fold - 1;        // live strip rows
+            constexpr int RPT = (DT_MSUB_MAX * 128 + 255) / 256 + 1;   // strip rows per thread (<= 384 + fold - 1 rows)
+            uint32_t ita = 0;
+            for (long long u = blockIdx.x; u < nunits; u += gridDim.x) {
+                const long long ur = u / f.ntiles;
+                const long long o0 = ur * A.rows_per_unit;
+                long long o1 = o0 + A.rows_per_unit; if (o1 > A.R) o1 = A.R;
+                long long in_end = o1 + L - 1; if (in_end > A.R) in_end = A.R;
+                for (int step = 0; step < A.steps_per_unit; ++step) {
+                    const long long g0 = o0 + (long long)step * step_rows;
+                    for (int cf = 0; cf < f.ncf; ++cf, ++ita) {
+                        uint2 w[RPT], wh[RPT];
+#pragma unroll
+                        for (int k = 0; k < RPT; ++k) {
+                            const int r = tid + 256 * k;
+                            const long long fr = g0 + r;
+                            const bool ok = r < srows && fr < in_end;
+                            const uint2* src = reinterpret_cast<const uint2*>(A.bits + (ok ? fr : 0) * f.rowwords);
+                            w[k] = (ok && 2 * cf < nw2) ? __ldg(src + 2 * cf) : make_uint2(0u, 0u);
+                            wh[k] = (ok && 2 * cf + 1 < nw2) ? __ldg(src + 2 * cf + 1) : make_uint2(0u, 0u);
+                        }
+                        const int buf = ita & 1;
+                        mbar_wait_relaxed(&aempty_bar[buf], ((ita >> 1) & 1) ^ 1);
+                        if (warp == 1) DT_TRACE(ita, 0);
+                        uint8_t* strip = smem + buf * S.strip_bytes;
+#pragma unroll
+                        for (int k = 0; k < RPT; ++k) {
+                            const int r = tid + 256 * k;
+                            if (r < f.strip_rows) {
+                                uint8_t* dst = strip + r * 16;
+                                const uint32_t kgs = (uint32_t)f.kgs;
+                                *reinterpret_cast<uint4*>(dst) = expand16_u8(w[k].x & 0xFFFF);
+                                *reinterpret_cast<uint4*>(dst + kgs) = expand16_u8(w[k].x >> 16);
+                                *reinterpret_cast<uint4*>(dst + 2 * kgs) = expand16_u8(w[k].y & 0xFFFF);
+                                *reinterpret_cast<uint4*>(dst + 3 * kgs) = expand16_u8(w[k].y >> 16);
+                                *reinterpret_cast<uint4*>(dst + 4 * kgs) = expand16_u8(wh[k].x & 0xFFFF);
+                                *reinterpret_cast<uint4*>(dst + 5 * kgs) = expand16_u8(wh[k].x >> 16);
+                                *reinterpret_cast<uint4*>(dst + 6 * kgs) = expand16_u8(wh[k].y & 0xFFFF);
+                                *reinterpret_cast<uint4*>(dst + 7 * kgs) = expand16_u8(wh[k].y >> 16);
+                            }
+                        }
+                        fence_proxy_async_smem();
+                        mbar_arrive(&afull_bar[buf]);
+                        if (warp == 1) DT_TRACE(ita, 1);
+                    }
+                }
+            }
+        } else {
         const int grp = (warp - 1) / 4;                  // 0 or 1
         const int tg = threadIdx.x - 32 - grp * 128;     // 0..127 within the group == row of a sub-tile
         const uint32_t one = fmt_one(fmt);
@@ -356,6 +446,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) detect_tc_kernel(DetectArgs A) 
                 }
             }
         }
+        }   // F16 expanders
     } else if (warp == 0) {
         // ============================ filter-tile loader ============================
         if (lane == 0) {
@@ -369,8 +460,8 @@ __global__ void __launch_bounds__(DT_THREADS, 1) detect_tc_kernel(DetectArgs A) 
                         mbar_wait_relaxed(&empty_bar[stage], ph ^ 1);
                         DT_TRACE(it, 2);
                         mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)f.tile_bytes);
-                        bulk_g2s(smem + stage * S.stage_bytes + S.b, src + (size_t)c * f.tile_bytes, (uint32_t)f.tile_bytes,
-                                 &full_bar[stage]);
+                        bulk_g2s(smem + (I8 ? S.b + stage * S.stage_bytes : stage * S.stage_bytes + S.b),
+                                 src + (size_t)c * f.tile_bytes, (uint32_t)f.tile_bytes, &full_bar[stage]);
                         if (++stage == nstage) { stage = 0; ph ^= 1; }
                     }
             }
@@ -385,6 +476,48 @@ __global__ void __launch_bounds__(DT_THREADS, 1) detect_tc_kernel(DetectArgs A) 
         const uint64_t b_hi = ((uint64_t)desc_hi << 32) | ((uint64_t)NT << 16);            // LBO = NT*16 B
         int stage = 0; uint32_t ph = 0;
         uint32_t stepno = 0, it = 0;
+        if constexpr (I8) {
+            // per frame chunk cf: wait for its A strip, then fold x 2 filter tiles (64 features = 2 MMAs of
+            // K = 32 per sub-tile each); phase phi reads the strip `phi` rows further down
+            const uint64_t a_hi8 = ((uint64_t)desc_hi << 32) | ((uint64_t)((uint32_t)f.kgs >> 4) << 16);   // LBO = k-group stride
+            const uint32_t kgs16 = (uint32_t)f.kgs >> 4;
+            uint32_t ita = 0;
+            for (long long u = blockIdx.x; u < nunits; u += gridDim.x)
+                for (int step = 0; step < A.steps_per_unit; ++step, ++stepno) {
+                    for (int cf = 0; cf < f.ncf; ++cf, ++ita) {
+                        const int buf = ita & 1;
+                        mbar_wait(&afull_bar[buf], (ita >> 1) & 1);
+                        tc_fence_after();
+                        const uint32_t sbase = smem_u32(smem + buf * S.strip_bytes) >> 4;
+                        for (int phi = 0; phi < f.fold; ++phi)
+                            for (int half = 0; half < 2; ++half, ++it) {
+                                mbar_wait(&full_bar[stage], ph);
+                                DT_TRACE(it, 4);
+                                tc_fence_after();
+                                const uint32_t bbase = smem_u32(smem + S.b + stage * S.stage_bytes) >> 4;
+                                for (int sub = 0; sub < msub; ++sub) {
+                                    if ((cf | phi | half) == 0) {
+                                        mbar_wait(&tempty_bar[sub], (stepno & 1) ^ 1);
+                                        tc_fence_after();
+                                    }
+                                    const uint32_t d_tmem = tmem_base + sub * NT;
+                                    const uint32_t arow = sbase + (uint32_t)(sub * 128 + phi);
+#pragma unroll
+                                    for (int j = 0; j < 2; ++j) {   // K = 32 per MMA: k-groups 2*(2*half+j), +1
+                                        const uint64_t adesc = a_hi8 | (uint64_t)(arow + (uint32_t)(2 * (2 * half + j)) * kgs16);
+                                        const uint64_t bdesc = b_hi | (uint64_t)(bbase + j * 2 * NT);
+                                        umma_i8_elect(d_tmem, adesc, bdesc, idesc, (cf | phi | half | j) != 0 ? 1u : 0u);
+                                    }
+                                }
+                                umma_commit_elect(&empty_bar[stage]);
+                                DT_TRACE(it, 5);
+                                if (++stage == nstage) { stage = 0; ph ^= 1; }
+                            }
+                        umma_commit_elect(&aempty_bar[buf]);
+                    }
+                    umma_commit_elect(tfull_bar);
+                }
+        } else
         for (long long u = blockIdx.x; u < nunits; u += gridDim.x)
             for (int step = 0; step < A.steps_per_unit; ++step, ++stepno) {
                 for (int c = 0; c < nchunks; ++c, ++it) {
