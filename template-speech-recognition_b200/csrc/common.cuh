@@ -45,7 +45,9 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
 
 // Spin bound for every barrier wait: a lost arrival traps (CUDA error) instead of hanging
 // the box.  ~2^26 polls with back-off is seconds of wall time, far above any legitimate wait.
+#ifndef TSR_SPIN_LIMIT
 #define TSR_SPIN_LIMIT (1u << 26)
+#endif
 
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
@@ -124,6 +126,66 @@ __device__ __forceinline__ void tmem_alloc(uint32_t* smem_result) {
 template <uint32_t kCols>
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(kCols) : "memory");
+}
+// ---- CTA pair (cta_group::2) helpers: two CTAs of a cluster on one TPC share one MMA ------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cta address -> shared::cluster address of the same offset in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t saddr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+    return r;
+}
+// arrive on an mbarrier of any CTA of the cluster.  Default semantics (as CUTLASS ClusterBarrier::arrive):
+// a .release.cluster arrive costs a cluster-wide memory barrier (~1000 cycles measured), which serialised
+// the per-tile relay; the data it guards is already in the peer's shared memory (TMA complete_tx /
+// fence.proxy.async + local arrive) when the relaying thread observes the local barrier.
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// wait with cluster-scope acquire: pairs with remote arrivals
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+    uint32_t spins = 0, ok = 0;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2, %3;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity), "r"(100000u)
+            : "memory");
+        if (!ok && ++spins > TSR_SPIN_LIMIT) {
+            printf("tsr_b200: cluster mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+            __trap();
+        }
+    } while (!ok);
+}
+template <uint32_t kCols>
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_result) {   // one warp of EACH CTA of the pair
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)),
+                 "n"(kCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <uint32_t kCols>
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(kCols) : "memory");
+}
+// commit of the leader's cta_group::2 MMAs, arriving on the barrier at this offset in BOTH CTAs
+__device__ __forceinline__ void umma_commit_pair_elect(uint64_t* bar) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}" ::"r"(
+            smem_u32(bar)),
+        "h"((uint16_t)3)
+        : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }

@@ -110,7 +110,7 @@ __host__ __device__ inline FilterLayout filter_layout(int M, int L, int D, int p
         f.msub = msub > msub_cap ? msub_cap : msub;
         f.tile_bytes = f.kind ? (size_t)f.NT * 64 : (size_t)2 * f.NT * 128;
         const size_t fixed = (((128 + DT_TAU_CHUNK) * (DT_TAU_CHUNK + 1) * 4 + 127) & ~(size_t)127) +
-                             ((((size_t)f.msub * 128 + f.Lc + 1) * f.tptv * 4 + 127) & ~(size_t)127) + 512;
+                             ((((size_t)f.msub * 128 + f.Lc + 1) * (f.tptv | 1) * 4 + 127) & ~(size_t)127) + 512;
         const long long avail = 227 * 1024 - (long long)fixed;
         int ns;
         if (f.kind) {   // two A strips + a ring of filter tiles
@@ -231,11 +231,19 @@ struct DetectArgs {
     int steps_per_unit;
     FilterLayout f;
     long long* trace;   // optional debug timeline of CTA 0: [stage iteration][8] clock64 stamps
+    int dbg;            // debug experiments (timing only, wrong results): 1 = every phase reads the strip at row 0
 };
 #define DT_TRACE_ITERS 256
 #define DT_TRACE(itv, slot)                                                                          \
     do {                                                                                             \
         if (A.trace && blockIdx.x == 0 && (itv) < DT_TRACE_ITERS && lane == 0) A.trace[(itv) * 8 + (slot)] = clock64(); \
+    } while (0)
+
+// debug: phase stamps of the drain passes of step 1, rows 192.. of the trace buffer
+#define DT_TRACE_PASS(slot)                                                                                        \
+    do {                                                                                                           \
+        if (A.trace && blockIdx.x == 0 && stepno == 1 && quad == 0 && lane == 0 && passno < 60)                    \
+            A.trace[(192 + passno) * 8 + (slot)] = clock64();                                                      \
     } while (0)
 
 struct DetectSmem {
@@ -260,7 +268,7 @@ __host__ __device__ inline DetectSmem detect_smem_layout(const FilterLayout& f) 
     }
     S.stage = (S.stage + 127) & ~127u;
     S.outacc = S.stage + (((128 + DT_TAU_CHUNK) * (DT_TAU_CHUNK + 1) * 4 + 127) & ~127u);
-    S.bars = S.outacc + (((f.msub * 128 + f.Lc + 1) * f.tptv * 4 + 127) & ~127u);
+    S.bars = S.outacc + (((f.msub * 128 + f.Lc + 1) * (f.tptv | 1) * 4 + 127) & ~127u);
     S.total = S.bars + 256;
     return S;
 }
@@ -501,7 +509,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) detect_tc_kernel(DetectArgs A) 
                                         tc_fence_after();
                                     }
                                     const uint32_t d_tmem = tmem_base + sub * NT;
-                                    const uint32_t arow = sbase + (uint32_t)(sub * 128 + phi);
+                                    const uint32_t arow = sbase + (uint32_t)(sub * 128 + ((A.dbg & 1) ? 0 : phi));
 #pragma unroll
                                     for (int j = 0; j < 2; ++j) {   // K = 32 per MMA: k-groups 2*(2*half+j), +1
                                         const uint64_t adesc = a_hi8 | (uint64_t)(arow + (uint32_t)(2 * (2 * half + j)) * kgs16);
@@ -562,7 +570,8 @@ __global__ void __launch_bounds__(DT_THREADS, 1) detect_tc_kernel(DetectArgs A) 
         typedef typename std::conditional<I8, int, float>::type acc_t;
         constexpr int PITCH = DT_TAU_CHUNK + 1;                      // odd word pitch: conflict-free rows and diagonals
         acc_t* stg = reinterpret_cast<acc_t*>(smem + S.stage);       // skewed staging [128 + TC - 1][PITCH]
-        acc_t* outacc = reinterpret_cast<acc_t*>(smem + S.outacc);   // [step_rows + L - 1][tptv]
+        acc_t* outacc = reinterpret_cast<acc_t*>(smem + S.outacc);   // [step_rows + Lc][opitch]
+        const int opitch = tptv | 1;   // odd row pitch: the per-row accumulations of a warp (one row per lane) hit distinct banks
         const float* scale = reinterpret_cast<const float*>(A.blob + 128);
         const int quad = warp & 3;                                    // TMEM lane quadrant of this warp
         const int e = quad * 32 + lane;                               // 0..127 == TMEM lane == row of the sub-tile
@@ -574,7 +583,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) detect_tc_kernel(DetectArgs A) 
         if (TCf > Lf) TCf = Lf;
         const int skew = fold * (TCf - 1);                 // row shift of the last column of a chunk
         const int srows = 128 + skew;                       // staging rows in use
-        const int nacc = (step_rows + Lc) * tptv;
+        const int nacc = (step_rows + Lc) * opitch;
         const int vpt = f.vpt, tpt = tptv / vpt;
         // Skewed staging: thread e writes C[e][c0+tr] to row q' = e - fold*tr + skew, column tr, so that a
         // diagonal of the tile becomes a ROW of the staging buffer and the diagonal sum a plain row sum (one
@@ -594,6 +603,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) detect_tc_kernel(DetectArgs A) 
             for (int step = 0; step < A.steps_per_unit; ++step, ++stepno) {
                 mbar_wait_relaxed(tfull_bar, stepno & 1);
                 if (quad == 0) DT_TRACE(stepno, 6);
+                int passno = 0; (void)passno;
                 tc_fence_after();
                 for (int sub = 0; sub < msub; ++sub) {
                     const uint32_t taddr = tmem_base + sub * NT + ((uint32_t)(quad * 32) << 16);
@@ -613,7 +623,9 @@ __global__ void __launch_bounds__(DT_THREADS, 1) detect_tc_kernel(DetectArgs A) 
                                     for (int i = 0; i < 8; ++i) v[t0 + i] = 0u;
                                 }
                             }
+                            DT_TRACE_PASS(0);
                             tmem_ld_wait();
+                            DT_TRACE_PASS(1);
                             // column i (frame tr = i % Lf of group i / Lf) goes to staging row e + Lc - fold*tr.
                             // Compile-time Lf (the common fold choices) gives straight-line code with
                             // immediate offsets; other values take the counter-driven generic path.
@@ -650,23 +662,48 @@ __global__ void __launch_bounds__(DT_THREADS, 1) detect_tc_kernel(DetectArgs A) 
                                 tc_fence_before();
                                 mbar_arrive(&tempty_bar[sub]);
                             }
+                            DT_TRACE_PASS(2);
                             named_bar_sync(1, 128);
+                            DT_TRACE_PASS(3);
                             // row q' holds, per group, the Lf terms of out index q' (staging row == out index)
                             auto sum_rows = [&](auto lfc) {
                                 constexpr int LFC = decltype(lfc)::value;
                                 const acc_t* r0p = stg + e * PITCH;
                                 const acc_t* r1p = stg + (xrow < 0 ? 0 : xrow) * PITCH;
                                 const bool x_ok = xrow >= 0 && xrow <= 128 + Lc;
-                                acc_t* o0p = outacc + (sub * 128 + e) * tptv + vl0;
-                                acc_t* o1p = outacc + (sub * 128 + (x_ok ? xrow : 0)) * tptv + vl0;
+                                acc_t* o0p = outacc + (sub * 128 + e) * opitch + vl0;
+                                acc_t* o1p = outacc + (sub * 128 + (x_ok ? xrow : 0)) * opitch + vl0;
                                 if constexpr (LFC > 0) {
+                                    // all row sums, then all accumulator loads, then all stores: the read-modify-write
+                                    // chains of the groups overlap instead of paying one smem round trip each
                                     constexpr int NG = DT_TAU_CHUNK / LFC;
+                                    constexpr int BG = NG < 8 ? NG : 8;      // groups per batch (register budget)
 #pragma unroll
-                                    for (int gi = 0; gi < NG; ++gi) {
-                                        acc_t s0 = 0, s1 = 0;
+                                    for (int g0 = 0; g0 < NG; g0 += BG) {
+                                        acc_t s0[BG], s1[BG], a0[BG], a1[BG];
 #pragma unroll
-                                        for (int tr = 0; tr < LFC; ++tr) { s0 += r0p[gi * LFC + tr]; s1 += r1p[gi * LFC + tr]; }
-                                        if (gi < g) { o0p[gi] += s0; if (x_ok) o1p[gi] += s1; }
+                                        for (int k = 0; k < BG; ++k) {
+                                            s0[k] = 0; s1[k] = 0;
+                                            if (g0 + k < NG) {
+#pragma unroll
+                                                for (int tr = 0; tr < LFC; ++tr) {
+                                                    s0[k] += r0p[(g0 + k) * LFC + tr];
+                                                    s1[k] += r1p[(g0 + k) * LFC + tr];
+                                                }
+                                            }
+                                        }
+#pragma unroll
+                                        for (int k = 0; k < BG; ++k) {
+                                            a0[k] = g0 + k < g ? o0p[g0 + k] : 0;
+                                            a1[k] = (g0 + k < g && x_ok) ? o1p[g0 + k] : 0;
+                                        }
+#pragma unroll
+                                        for (int k = 0; k < BG; ++k) {
+                                            if (g0 + k < g) {
+                                                o0p[g0 + k] = a0[k] + s0[k];
+                                                if (x_ok) o1p[g0 + k] = a1[k] + s1[k];
+                                            }
+                                        }
                                     }
                                 } else {
                                     acc_t s0 = 0, s1 = 0;
@@ -692,7 +729,10 @@ __global__ void __launch_bounds__(DT_THREADS, 1) detect_tc_kernel(DetectArgs A) 
                                 case 1: sum_rows(std::integral_constant<int, 1>{}); break;
                                 default: sum_rows(std::integral_constant<int, 0>{}); break;
                             }
+                            DT_TRACE_PASS(4);
                             named_bar_sync(1, 128);
+                            DT_TRACE_PASS(5);
+                            ++passno;
                         }
                     } else
                     for (int vl = 0; vl < tptv; ++vl) {
@@ -734,9 +774,9 @@ __global__ void __launch_bounds__(DT_THREADS, 1) detect_tc_kernel(DetectArgs A) 
                                 for (int tr = 0; tr < DT_TAU_CHUNK; ++tr)
                                     if (tr < TCf) { s0 += r0p[tr]; s1 += r1p[tr]; }   // warp-uniform guard
                                 const int q0 = e + qoff;
-                                if (q0 >= 0) outacc[(sub * 128 + q0) * tptv + vl] += s0;
+                                if (q0 >= 0) outacc[(sub * 128 + q0) * opitch + vl] += s0;
                                 const int q1 = xrow + qoff;
-                                if (xrow >= 0 && xrow < srows && q1 >= 0) outacc[(sub * 128 + q1) * tptv + vl] += s1;
+                                if (xrow >= 0 && xrow < srows && q1 >= 0) outacc[(sub * 128 + q1) * opitch + vl] += s1;
                             }
                             named_bar_sync(1, 128);
                         }
@@ -752,7 +792,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) detect_tc_kernel(DetectArgs A) 
                         const int tl = (int)(g % A.T);
                         float val = 0.f;
                         if (tl <= A.T - L) {
-                            const acc_t* a = outacc + oi * tptv + ml * vpt;
+                            const acc_t* a = outacc + oi * opitch + ml * vpt;
                             if (I8) {   // recombine the base-256 digit planes exactly, then scale once
                                 double q = (double)a[0] + 256.0 * (double)a[1];
                                 if (vpt == 3) q += 65536.0 * (double)a[2];
@@ -768,7 +808,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) detect_tc_kernel(DetectArgs A) 
                 // carry the Lc unfinished rows to the front and clear the rest.  dst = src - shift; ascending
                 // passes of `shift` elements never read what an earlier pass wrote, one barrier per pass.
                 {
-                    const int keep = Lc * tptv, shift = step_rows * tptv;
+                    const int keep = Lc * opitch, shift = step_rows * opitch;
                     for (int p0 = 0; p0 < keep; p0 += shift) {
                         const int p1 = (p0 + shift) < keep ? (p0 + shift) : keep;
                         for (int i = p0 + e; i < p1; i += 128) outacc[i] = outacc[i + shift];
@@ -901,11 +941,13 @@ __global__ void __launch_bounds__(256) detect_reduce_kernel(const float* __restr
 using namespace tsr;
 
 static long long* g_detect_trace = nullptr;   // debug hook
+static int g_detect_dbg = 0;
 
 extern "C" {
 
 /* Debug only (not in the public header): device buffer of DT_TRACE_ITERS*8 int64 clock stamps. */
 void tsr_debug_set_detect_trace(long long* dev_buf) { g_detect_trace = dev_buf; }
+void tsr_debug_set_detect_flags(int flags) { g_detect_dbg = flags; }
 
 size_t tsr_filter_blob_bytes(int M, int L, int D, int plane_format) {
     if (M < 1 || L < 1 || L > 256 || D < 1 || plane_format < 0 || plane_format > 4) return 0;
@@ -958,6 +1000,7 @@ int tsr_detect(const uint32_t* featbits, int B, int T, int D, int rowwords, cons
     A.bits = featbits; A.blob = (const uint8_t*)filter_blob; A.scores = scores; A.R = R; A.T = T;
     A.f = filter_layout(M, L, D, plane_format);
     A.trace = g_detect_trace;
+    A.dbg = g_detect_dbg;
     DetectSmem S = detect_smem_layout(A.f);
     if (S.total > 227 * 1024) {
         set_error("tsr_detect: L=%d needs %u B of shared memory (> 227 KB)", L, S.total);

@@ -15,13 +15,16 @@ ops.detect(fb, bank)
 torch.cuda.synchronize()
 buf = torch.zeros(256 * 8, dtype=torch.int64, device="cuda")
 lib.tsr_debug_set_detect_trace.argtypes = [ctypes.c_void_p]
+if len(sys.argv) > 2:
+    lib.tsr_debug_set_detect_flags(int(sys.argv[2]))
+    print("debug flags", sys.argv[2])
 lib.tsr_debug_set_detect_trace(buf.data_ptr())
 ops.detect(fb, bank)
 torch.cuda.synchronize()
 lib.tsr_debug_set_detect_trace(None)
 t = buf.cpu().numpy().reshape(256, 8)
 t0 = t[t > 0].min()
-names = ["exp:empty_ok", "exp:arrived", "ld:empty_ok", "-", "mma:full_ok", "mma:commit", "epi:tfull", "epi:done"]
+names = ["exp:empty_ok", "exp:arrived", "ld:empty_ok", "peer:relayed", "mma:full_ok", "mma:commit", "epi:tfull", "epi:done"]
 print("planes", planes)
 print("iter " + " ".join("%13s" % n for n in names))
 for i in list(range(0, 4)) + list(range(60, 76)):
@@ -36,3 +39,11 @@ print("median stage period", np.median(d), "sum", d.sum())
 e6, e7 = t[:8, 6], t[:8, 7]
 print("epilogue (tfull -> done) per step:", [(int(b - a)) for a, b in zip(e6, e7) if a and b])
 print("step starts:", [int(x - t0) for x in e6 if x])
+
+tp = t[192:192 + 14, :6]
+if tp.any():
+    base = e6[1]
+    print("drain passes of step 1 (cycles after tfull): ld_issued ld_done stored bar1 summed bar2")
+    for row in tp:
+        if row[0]:
+            print("   " + " ".join("%7d" % (x - base) for x in row))
