@@ -166,6 +166,17 @@ int tsr_detect_reduce(const float* scores, const float* cs, int B, int T, int M,
 int tsr_detect_float(const float* Fm, int B, int T, int D, const float* LF, int M, int L, const float* init_or_null,
                      float* scores, void* stream);
 
+/* ---- N2: peak picking on detection tracks ------------------------------------------------------
+ * Replaces roc_functions.get_max_above_threshold (roc_functions.py:177-186): flags[b][t] = 1 iff
+ * 1 <= t <= l-2, track[b][t] >= both neighbours and >= threshold, l = length[b] - C0 + 1
+ * (lengths_or_null int32 [B]; null = T).  The flagged frames are compacted in order with
+ * tsr_patch_select(flags, B*T, 1, 0xFFFFFFFF, ...) and written out by tsr_peaks_gather as
+ * peak_bt int32 [n][2] = (b, t) and peak_val float [n]: detections instead of T-length tracks. */
+int tsr_detect_peaks(const float* track, const int* lengths_or_null, int B, int T, int C0, float threshold, uint32_t* flags,
+                     void* stream);
+int tsr_peaks_gather(const float* track, const int32_t* slot, int B, int T, int32_t* peak_bt, float* peak_val_or_null,
+                     void* stream);
+
 /* ---- K4: Bernoulli-mixture EM -----------------------------------------------------------------
  * Replaces BernoulliMixture.get_template_loglikelihoods/_compute_loglikelihoods
  * (bernoulli_mixture.py:263-291), M_step/threshold_templates (:177-193) and the same steps

@@ -167,6 +167,13 @@ def get_parts_mask(X, M, S, threshold):
     return patches, S_patches, counts, locs
 
 
+def get_max_above_threshold(detection_vals, detection_length, threshold, C0):
+    """roc_functions.py:177-186 (the expression itself is valid Python 3 and is kept verbatim in meaning)"""
+    l = detection_length - C0 + 1
+    v = np.asarray(detection_vals)
+    return np.arange(1, l - 1, dtype=np.uint16)[(v[1:l - 1] >= v[:l - 2]) * (v[1:l - 1] >= v[2:l]) * (v[1:l - 1] >= threshold)]
+
+
 # ------------------------------------------------------------------------ detection
 def detect(F, LF):
     """compute_likelihood_linear_filter.pyx:135-176"""

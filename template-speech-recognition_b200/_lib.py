@@ -38,6 +38,8 @@ SIGNATURES = {
     "tsr_detect": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _i, _vp, _i, _vp]),
     "tsr_detect_reduce": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "tsr_detect_float": (_i, [_vp, _i, _i, _i, _vp, _i, _i, _vp, _vp, _vp]),
+    "tsr_detect_peaks": (_i, [_vp, _vp, _i, _i, _i, _f, _vp, _vp]),
+    "tsr_peaks_gather": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp]),
     "tsr_em_workspace_bytes": (_sz, [_ll, _i, _i]),
     "tsr_em_estep": (_i, [_vp, _ll, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _vp]),
     "tsr_em_segments": (_i, [_ll, _i, _i]),

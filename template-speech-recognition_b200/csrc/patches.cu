@@ -198,6 +198,38 @@ __global__ void __launch_bounds__(256) patch_gather_kernel(const uint8_t* __rest
     }
 }
 
+// ------------------------------------------------------------------------------ peak picking (N2)
+// flags[b][t] = 1 iff 1 <= t <= l-2 and v[t] >= v[t-1], v[t] >= v[t+1], v[t] >= threshold, with
+// l = length[b] - C0 + 1 (roc_functions.get_max_above_threshold, roc_functions.py:177-186).
+__global__ void __launch_bounds__(256) detect_peaks_kernel(const float* __restrict__ v, const int* __restrict__ lengths,
+                                                           long long n, int T, int C0, float threshold,
+                                                           uint32_t* __restrict__ flags) {
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < n; idx += (long long)gridDim.x * blockDim.x) {
+        const long long b = idx / T;
+        const int t = (int)(idx - b * T);
+        int l = (lengths ? lengths[b] : T) - C0 + 1;
+        if (l > T) l = T;
+        uint32_t f = 0;
+        if (t >= 1 && t <= l - 2) {
+            const float x = v[idx];
+            f = (x >= v[idx - 1] && x >= v[idx + 1] && x >= threshold) ? 1u : 0u;
+        }
+        flags[idx] = f;
+    }
+}
+__global__ void __launch_bounds__(256) peaks_gather_kernel(const float* __restrict__ v, const int32_t* __restrict__ slot,
+                                                           long long n, int T, int32_t* __restrict__ peak_bt,
+                                                           float* __restrict__ peak_val) {
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < n; idx += (long long)gridDim.x * blockDim.x) {
+        const int32_t s = slot[idx];
+        if (s < 0) continue;
+        const long long b = idx / T;
+        peak_bt[2 * (size_t)s] = (int32_t)b;
+        peak_bt[2 * (size_t)s + 1] = (int32_t)(idx - b * T);
+        if (peak_val) peak_val[s] = v[idx];
+    }
+}
+
 }  // namespace tsr
 
 using namespace tsr;
@@ -281,6 +313,33 @@ int tsr_patch_gather(const uint8_t* bits, const double* S_or_null, const int32_t
                                                                          tsr_rowwords(ph * pw * E), patch_set_or_null,
                                                                          S_patch_or_null, locs_or_null, patchbits_or_null);
     return check_launch("tsr_patch_gather");
+}
+
+int tsr_detect_peaks(const float* track, const int* lengths_or_null, int B, int T, int C0, float threshold, uint32_t* flags,
+                     void* stream) {
+    if (B == 0 || T == 0) return TSR_OK;
+    TSR_REQUIRE(track && flags, "tsr_detect_peaks: null pointer");
+    TSR_REQUIRE(B > 0 && T > 0, "tsr_detect_peaks: bad sizes");
+    int rc = require_sm100("tsr_detect_peaks");
+    if (rc) return rc;
+    const long long n = (long long)B * T;
+    long long blocks = (n + 255) / 256;
+    if (blocks > 148LL * 32) blocks = 148LL * 32;
+    detect_peaks_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(track, lengths_or_null, n, T, C0, threshold, flags);
+    return check_launch("tsr_detect_peaks");
+}
+
+int tsr_peaks_gather(const float* track, const int32_t* slot, int B, int T, int32_t* peak_bt, float* peak_val_or_null,
+                     void* stream) {
+    if (B == 0 || T == 0) return TSR_OK;
+    TSR_REQUIRE(track && slot && peak_bt, "tsr_peaks_gather: null pointer");
+    int rc = require_sm100("tsr_peaks_gather");
+    if (rc) return rc;
+    const long long n = (long long)B * T;
+    long long blocks = (n + 255) / 256;
+    if (blocks > 148LL * 32) blocks = 148LL * 32;
+    peaks_gather_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(track, slot, n, T, peak_bt, peak_val_or_null);
+    return check_launch("tsr_peaks_gather");
 }
 
 }  // extern "C"

@@ -293,6 +293,30 @@ def detect_float(Fm, LF, init=None):
     return out
 
 
+# ------------------------------------------------------------------------------- N2
+def detect_peaks(track, threshold, C0=1, lengths=None):
+    """track float32 (B,T) -> (peak_bt int32 (n,2) rows (b,t) in order, peak_val float32 (n,)): local maxima
+    >= threshold over t in [1, length-C0-1] (roc_functions.py:177-186).  One device->host read of n."""
+    track = _dev(track, torch.float32, "track")
+    B, T = track.shape
+    dev = track.device
+    if lengths is not None:
+        lengths = _dev(lengths, torch.int32, "lengths")
+    n_loc = B * T
+    flags = torch.empty(n_loc, dtype=torch.int32, device=dev)
+    _lib.call("tsr_detect_peaks", _ptr(track), _ptr(lengths), B, T, int(C0), float(threshold), _ptr(flags), _stream())
+    slot = torch.empty(n_loc, dtype=torch.int32, device=dev)
+    total = torch.zeros(1, dtype=torch.int32, device=dev)
+    ws = torch.empty(max(_lib.lib().tsr_patch_select_workspace_bytes(n_loc), 4), dtype=torch.uint8, device=dev)
+    _lib.call("tsr_patch_select", _ptr(flags), n_loc, 1, 2 ** 32 - 1, _ptr(slot), _ptr(total), _ptr(ws), _stream())
+    n = int(total.item())
+    bt = torch.empty((n, 2), dtype=torch.int32, device=dev)
+    val = torch.empty(n, dtype=torch.float32, device=dev)
+    if n:
+        _lib.call("tsr_peaks_gather", _ptr(track), _ptr(slot), B, T, _ptr(bt), _ptr(val), _stream())
+    return bt, val
+
+
 # ------------------------------------------------------------------------------- K4
 class EmState:
     """Device state of one rank's share of a Bernoulli-mixture EM problem."""

@@ -196,3 +196,25 @@ def test_long_stream_many_templates(cuda, oracle):
     sl = slice(9000, 9400)
     ref = oracle.detect(F[0, sl], LF[7])
     np.testing.assert_array_equal(s[0, 9000:9400 - L + 1, 7], ref[:400 - L + 1])
+
+
+def test_peak_picking(cuda, oracle):
+    """roc_functions.get_max_above_threshold (roc_functions.py:177-186): bit-exact index lists, including
+    plateaus (>= on both sides), the excluded first / last frames and the C0-shortened range."""
+    from tsr_b200 import ops, roc_functions as rf
+    rs = np.random.RandomState(21)
+    for (T, dl, C0, thr) in ((300, 300, 1, 0.0), (300, 280, 40, 0.5), (50, 50, 1, -10.0), (4, 4, 1, 0.0), (3, 3, 1, 0.0), (2, 2, 1, 0.0)):
+        v = rs.randn(T).astype(np.float32)
+        v[5:9] = v[5] if T > 9 else v[5:9]                      # a plateau
+        got = rf.get_max_above_threshold(v, dl, thr, C0)
+        want = oracle.get_max_above_threshold(v, dl, thr, C0)
+        assert got.dtype == np.uint16
+        np.testing.assert_array_equal(got, want)
+    # batched device form with per-utterance lengths
+    V = rs.randn(5, 120).astype(np.float32)
+    lens = np.array([120, 80, 3, 2, 100], np.int32)
+    bt, val = ops.detect_peaks(torch.from_numpy(V).cuda(), 0.3, 10, torch.from_numpy(lens).cuda())
+    bt, val = bt.cpu().numpy(), val.cpu().numpy()
+    want = [(b, int(t)) for b in range(5) for t in (oracle.get_max_above_threshold(V[b], int(lens[b]), 0.3, 10) if lens[b] - 10 + 1 >= 3 else [])]
+    assert [tuple(x) for x in bt] == want
+    np.testing.assert_array_equal(val, np.array([V[b, t] for b, t in want], np.float32))
