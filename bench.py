@@ -62,6 +62,21 @@ def measured_peaks():
     return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, src="fallback")
 
 
+DTYPES = {
+    "int8x3": "detect: u8 {0,1} x int8 (3 base-256 digit planes) -> int32 exact; coding: fp16 hi+lo x {0,1} -> fp32; spreading: u8/u32 bit-packed",
+    "int8x2": "detect: u8 {0,1} x int8 (2 digit planes) -> int32; coding: fp16 hi+lo -> fp32; spreading: u8/u32 bit-packed",
+    "fp16": "fp16 hi+lo x {0,1} fp16 -> fp32 (coding and detection); spreading: u8/u32 bit-packed",
+    "bf16": "bf16 hi+lo x {0,1} bf16 -> fp32 (coding and detection); spreading: u8/u32 bit-packed",
+}
+ROOF_NOTES = {
+    "int8x3": "algorithmic FLOPs count the single-pass contraction; the kernel issues 3 int8 digit planes on tcgen05 kind::i8 "
+              "(2x the bf16 rate), so the algorithmic ceiling is 2/3 of the int8 peak = 1.33x the bf16 peak quoted here",
+    "int8x2": "algorithmic FLOPs count the single-pass contraction; 2 int8 planes at 2x the bf16 rate",
+    "fp16": "algorithmic FLOPs count the single-pass contraction; the fp16 hi+lo split issues 2x",
+    "bf16": "algorithmic FLOPs count the single-pass contraction; the bf16 hi+lo split issues 2x",
+}
+
+
 # --------------------------------------------------------------------------- clocks sampler
 class ClockSampler:
     """Samples SM clock and throttle reasons DURING the timed region (NVML, every ~2 ms; falls back
@@ -332,13 +347,13 @@ def run_native(args):
         line = {
             "metric": "edge-frames/sec coded+scored", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "bf16 hi+lo x {0,1} bf16, fp32 accumulate (u8 bit-packed for spreading)",
+            "vs_baseline": None, "dtype": DTYPES[args.planes],
             "data": "synthetic", "config": workload_config(B),
             "roofline": {"kernel": "detect_tc_kernel", "bound": "tensor", "achieved": det_tf, "peak": peaks["tf_sustained"],
                          "unit": "TFLOP/s", "frac": det_tf / peaks["tf_sustained"], "traffic": ncu_traffic("detect_tc_kernel", B),
                          "peak_source": peaks["src"] + " bf16_tflops_sustained (kernel timed inside the step)",
                          "algorithmic_flop_per_launch": FLOP_DETECT * B,
-                         "note": "algorithmic FLOPs count the single-pass contraction; the bf16 hi+lo split issues 2x"},
+                         "note": ROOF_NOTES[args.planes]},
             "stages": stages,
             "e2e": {"value": frames * e2e_steps / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": int(X_pinned.numel()),
                     "d2h_bytes_per_step": int(res_best.numel() * 4 + res_arg.numel() * 2),
@@ -356,6 +371,137 @@ def run_native(args):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------- auxiliary workloads
+def _dist_setup():
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    return torch, dist, rank, world, local, dev
+
+
+def _timed(torch, dist, world, dev, fn, steps, warmup, flush=None):
+    """W warm-up calls, then K calls timed with CUDA events (L2 flushed before each when `flush` is given);
+    returns the max-over-ranks mean milliseconds per call."""
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    evs = []
+    for _ in range(steps):
+        if flush is not None:
+            flush.fill_(1)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record()
+        evs.append((e0, e1))
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t = torch.tensor([sum(a.elapsed_time(b) for a, b in evs) / steps], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def run_em(args):
+    """BASELINE config 4: Bernoulli-mixture EM, N rows sharded over the ranks, one allreduce of the
+    sufficient statistics per iteration.  A step = one EM iteration (E + M + allreduce + finalize)."""
+    torch, dist, rank, world, local, dev = _dist_setup()
+    from tsr_b200 import ops
+    from tsr_b200.em_driver import EmDriver, shard_rows
+    N, D, K = args.em_n, args.em_d, args.em_k
+    lo, hi = shard_rows(N, rank, world)
+    g = torch.Generator(device=dev).manual_seed(3 + rank)
+    rw = ops.rowwords(D)
+    Xb = torch.randint(-2**31, 2**31 - 1, (hi - lo, rw), dtype=torch.int32, device=dev, generator=g)
+    Xb &= torch.randint(-2**31, 2**31 - 1, (hi - lo, rw), dtype=torch.int32, device=dev, generator=g)   # ~25 % ones
+    if D % 32:
+        Xb[:, D // 32] &= (1 << (D % 32)) - 1
+    Xb[:, (D + 31) // 32:] = 0
+
+    class Eng:   # local engine around ops.EmState for rows already packed on the device
+        def __init__(self):
+            self.state = ops.EmState(Xb, D, K); self.N, self.D, self.K, self.device = hi - lo, D, K, dev
+        def new_params(self):
+            z = lambda *s: torch.zeros(s, dtype=torch.float32, device=dev)   # noqa: E731
+            return dict(templates=z(K, D), logT=z(K, D), logInvT=z(K, D), weights=z(K), logw=z(K))
+        def affinities(self): return self.state.aff
+        def estep(self, p, hard, impl=0): self.state.estep(p["logT"], p["logInvT"], p["logw"], hard=hard, impl=impl)
+        def accumulate(self): self.state.mstep_accumulate()
+        stats = property(lambda self: self.state.stats)
+        ll = property(lambda self: self.state.ll)
+        def finalize(self, stats, Nt, mp, p): ops.em_finalize(stats, Nt, D, K, mp, p["templates"], p["logT"], p["logInvT"], p["weights"], p["logw"])
+
+    drv = EmDriver(Eng(), N, group=None)
+    T0 = torch.rand((K, D), device=dev, generator=torch.Generator(device=dev).manual_seed(1)).clamp_(0.05, 0.95)
+    drv.params["templates"].copy_(T0); drv.params["logT"].copy_(torch.log(T0)); drv.params["logInvT"].copy_(torch.log(1 - T0))
+    drv.params["weights"].fill_(1.0 / K); drv.params["logw"].fill_(float(np.log(1.0 / K)))
+    ll = [0.0]
+
+    def step():
+        ll[0] = drv.expectation(); drv.maximization(0.05)
+    ms = _timed(torch, dist, world, dev, step, args.steps, args.warmup)
+    if rank == 0:
+        peaks = measured_peaks()
+        xbytes = N * D / 8.0
+        print(json.dumps({"metric": "Bernoulli-mixture EM iteration time (E + M + allreduce + finalize)", "value": ms, "unit": "ms",
+                          "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": False,
+                          "scaling": "strong", "vs_baseline": None, "dtype": "u8 {0,1} x int8 digit planes -> int32 (E and M contractions), fp32 statistics",
+                          "data": "synthetic", "config": {"workload": "config4 bernoulli_em", "N": N, "D": D, "K": K, "rows_per_gpu": hi - lo,
+                                                          "allreduce_bytes": (K * D + K) * 4 + 8},
+                          "roofline": {"kernel": "detect_tc_kernel (E) + em M-step", "bound": "hbm", "achieved": xbytes / world / (ms * 1e-3) / 1e9,
+                                       "peak": peaks["hbm"], "unit": "GB/s", "frac": xbytes / world / (ms * 1e-3) / 1e9 / peaks["hbm"], "traffic": None,
+                                       "note": "algorithmic bytes = one read of the bit-packed rows per iteration (SURVEY 8(d)); K=16 makes the "
+                                               "tensor-core issue rate, not HBM, the practical bound"},
+                          "loglik": ll[0], "gpu_launches": None}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_stream(args):
+    """BASELINE config 5: one long stream scored against many templates; the stream is sharded in time
+    over the ranks with an L-1 frame halo, no collective.  A step = `--stream-frames` frames (total)."""
+    torch, dist, rank, world, local, dev = _dist_setup()
+    from tsr_b200 import ops
+    M, L = args.stream_templates, L_TEMPL
+    D = FO * K_PARTS if args.stream_level == "part" else F_BANDS * E_EDGES
+    frames = args.stream_frames
+    per = (frames + world - 1) // world
+    n_local = min(per, max(0, frames - rank * per)) + L - 1
+    g = torch.Generator(device=dev).manual_seed(11)
+    W = (torch.randn((M, L, D), device=dev, generator=g) * 1.5).cpu().numpy()
+    bank = ops.FilterBank(W, planes={"fp16": ops.PLANES_FP16, "bf16": ops.PLANES_BF16, "int8x2": ops.PLANES_INT8X2, "int8x3": ops.PLANES_INT8X3}[args.planes], device=dev)
+    del W
+    rw = ops.rowwords(D)
+    g2 = torch.Generator(device=dev).manual_seed(5 + rank)
+    fb = torch.randint(-2**31, 2**31 - 1, (1, n_local, rw), dtype=torch.int32, device=dev, generator=g2)
+    fb &= torch.randint(-2**31, 2**31 - 1, (1, n_local, rw), dtype=torch.int32, device=dev, generator=g2)
+    scores = torch.empty((1, n_local, M), dtype=torch.float32, device=dev)
+    ms = _timed(torch, dist, world, dev, lambda: ops.detect(fb, bank, D=D, out=scores), args.steps, args.warmup)
+    if rank == 0:
+        peaks = measured_peaks()
+        flop = 2.0 * L * D * M * frames
+        tf = flop / world / (ms * 1e-3) / 1e12      # per GPU
+        print(json.dumps({"metric": "stream frames/sec scored against %d templates" % M, "value": frames / (ms * 1e-3), "unit": "frames/s",
+                          "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+                          "scaling": "strong", "vs_baseline": None, "dtype": DTYPES[args.planes], "data": "synthetic",
+                          "config": {"workload": "config5 long-form keyword spotting (%s level, D=%d)" % (args.stream_level, D), "frames_per_step": frames,
+                                     "templates": M, "template_frames": L, "sharding": "time, L-1 frame halo, no collective",
+                                     "one_hour_720000_frames_s": 720000.0 / (frames / (ms * 1e-3))},
+                          "roofline": {"kernel": "detect_tc_kernel", "bound": "tensor", "achieved": tf, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
+                                       "frac": tf / peaks["tf_sustained"], "traffic": None, "note": ROOF_NOTES[args.planes]},
+                          "gpu_launches": args.steps}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -367,11 +513,23 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--planes", default="int8x3", choices=["fp16", "bf16", "int8x2", "int8x3"],
                     help="weight-plane format of the detection stage (DESIGN.md section 4)")
+    ap.add_argument("--workload", default="pipeline", choices=["pipeline", "em", "stream"],
+                    help="pipeline = BASELINE config 3 (the headline line); em = config 4; stream = config 5")
+    ap.add_argument("--em-n", type=int, default=100000)
+    ap.add_argument("--em-d", type=int, default=12800)
+    ap.add_argument("--em-k", type=int, default=16)
+    ap.add_argument("--stream-frames", type=int, default=720000, help="frames per step of the stream workload (1 h = 720000)")
+    ap.add_argument("--stream-templates", type=int, default=1000)
+    ap.add_argument("--stream-level", default="part", choices=["part", "edge"])
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3 if args.impl == "native" else args.warmup
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "em":
+        run_em(args)
+    elif args.workload == "stream":
+        run_stream(args)
     else:
         run_native(args)
 

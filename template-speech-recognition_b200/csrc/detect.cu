@@ -229,6 +229,7 @@ struct DetectArgs {
     int rows_per_unit;      // owned output rows per unit
     int units_per_ntile;
     int steps_per_unit;
+    int ntile_group;        // N tiles whose filter tiles share the L2 at one time (unit order: group, row unit, tile in group)
     FilterLayout f;
     long long* trace;   // optional debug timeline of CTA 0: [stage iteration][8] clock64 stamps
     int dbg;            // debug experiments (timing only, wrong results): 1 = every phase reads the strip at row 0
@@ -293,6 +294,18 @@ __device__ __forceinline__ void umma_i8_elect(uint32_t d_tmem, uint64_t a_desc, 
         : "memory");
 }
 
+// Unit u -> (N tile, row unit).  Units are ordered (tile group, row unit, tile within group) so that the CTAs
+// running at any one time share the filter tiles of a few N tiles (they stay L2 resident: with many
+// templates the whole filter bank is far larger than the L2) while the frame bits stream once per group.
+__device__ __forceinline__ void detect_unit_coords(long long u, int ntiles, int U, int G, int& nt, long long& ur) {
+    const long long per_group = (long long)U * G;
+    const long long ng = u / per_group, rem = u - ng * per_group;
+    const int left = ntiles - (int)ng * G;
+    const int gt = left < G ? left : G;
+    ur = rem / gt;
+    nt = (int)ng * G + (int)(rem - ur * gt);
+}
+
 template <bool I8>
 __global__ void __launch_bounds__(DT_THREADS, 1) detect_tc_kernel(DetectArgs A) {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -341,7 +354,8 @@ __global__ void __launch_bounds__(DT_THREADS, 1) detect_tc_kernel(DetectArgs A) 
             constexpr int RPT = (DT_MSUB_MAX * 128 + 255) / 256 + 1;   // strip rows per thread (<= 384 + fold - 1 rows)
             uint32_t ita = 0;
             for (long long u = blockIdx.x; u < nunits; u += gridDim.x) {
-                const long long ur = u / f.ntiles;
+                int nt_unused; long long ur;
+                detect_unit_coords(u, f.ntiles, A.units_per_ntile, A.ntile_group, nt_unused, ur);
                 const long long o0 = ur * A.rows_per_unit;
                 long long o1 = o0 + A.rows_per_unit; if (o1 > A.R) o1 = A.R;
                 long long in_end = o1 + L - 1; if (in_end > A.R) in_end = A.R;
@@ -393,7 +407,8 @@ __global__ void __launch_bounds__(DT_THREADS, 1) detect_tc_kernel(DetectArgs A) 
         uint32_t it = 0;                                  // global chunk counter (pipeline position)
         int stage = 0; uint32_t ph = 0;
         for (long long u = blockIdx.x; u < nunits; u += gridDim.x) {
-            const long long ur = u / f.ntiles;
+            int nt_unused; long long ur;
+            detect_unit_coords(u, f.ntiles, A.units_per_ntile, A.ntile_group, nt_unused, ur);
             const long long o0 = ur * A.rows_per_unit;
             long long o1 = o0 + A.rows_per_unit; if (o1 > A.R) o1 = A.R;
             long long in_end = o1 + L - 1; if (in_end > A.R) in_end = A.R;
@@ -461,7 +476,8 @@ __global__ void __launch_bounds__(DT_THREADS, 1) detect_tc_kernel(DetectArgs A) 
             int stage = 0; uint32_t ph = 0;
             uint32_t it = 0;
             for (long long u = blockIdx.x; u < nunits; u += gridDim.x) {
-                const int nt = (int)(u % f.ntiles);
+                int nt; long long ur_unused;
+                detect_unit_coords(u, f.ntiles, A.units_per_ntile, A.ntile_group, nt, ur_unused);
                 const uint8_t* src = A.blob + f.hdr_bytes + (size_t)nt * nchunks * f.tile_bytes;
                 for (int step = 0; step < A.steps_per_unit; ++step)
                     for (int c = 0; c < nchunks; ++c, ++it) {
@@ -594,8 +610,8 @@ __global__ void __launch_bounds__(DT_THREADS, 1) detect_tc_kernel(DetectArgs A) 
         const int xrow = lane < 10 ? 128 + quad * 10 + lane : -1;
         uint32_t stepno = 0;
         for (long long u = blockIdx.x; u < nunits; u += gridDim.x) {
-            const int nt = (int)(u % f.ntiles);
-            const long long ur = u / f.ntiles;
+            int nt; long long ur;
+            detect_unit_coords(u, f.ntiles, A.units_per_ntile, A.ntile_group, nt, ur);
             const long long o0 = ur * A.rows_per_unit;
             long long o1 = o0 + A.rows_per_unit; if (o1 > A.R) o1 = A.R;
             for (int i = e; i < nacc; i += 128) outacc[i] = 0;
@@ -1020,6 +1036,13 @@ int tsr_detect(const uint32_t* featbits, int B, int T, int D, int rowwords, cons
         if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_U = (int)U; }
     }
     A.units_per_ntile = best_U;
+    {   // N tiles per group: their filter tiles (one full set each) should fit in about half of the 126 MB L2
+        const size_t set_bytes = (size_t)A.f.nchunks * A.f.tile_bytes;
+        long long G = (long long)(64u << 20) / (long long)(set_bytes ? set_bytes : 1);
+        if (G < 1) G = 1;
+        if (G > A.f.ntiles) G = A.f.ntiles;
+        A.ntile_group = (int)G;
+    }
     A.rows_per_unit = (int)((R + best_U - 1) / best_U);
     A.steps_per_unit = (A.rows_per_unit + A.f.Lc + step_rows - 1) / step_rows;
     const long long nunits = (long long)A.f.ntiles * best_U;
