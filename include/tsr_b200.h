@@ -177,6 +177,25 @@ int tsr_detect_peaks(const float* track, const int* lengths_or_null, int B, int 
 int tsr_peaks_gather(const float* track, const int32_t* slot, int B, int T, int32_t* peak_bt, float* peak_val_or_null,
                      void* stream);
 
+/* ---- N4 / N3: edge front end (feeds K1a) ------------------------------------------------------
+ * tsr_edge_map replaces edge_signal_proc._edge_map_no_threshold (edge_signal_proc.py:1697-1836):
+ *   S double [B][F][T] (frequency rows x time) -> mags double [B][8][F][T], the reference's (8H, time)
+ *   array per utterance; orientation order and the zero borders as the reference writes them.
+ * tsr_threshold_edges replaces threshold_edge_block / threshold_edgemap (:1184-1307) applied per
+ *   `block_len`-frame block as _edge_map_threshold_segments does (:1537-1675), without critical bands:
+ *   per (block, orientation) tau = sorted(positive magnitudes)[int(quantile * n)], an edge is set where
+ *   mag > 0 and mag >= max(tau, host_abst_threshold[e]) (double [8], HOST pointer).  Output: packed edge
+ *   bytes bits [B][T][F] (the input of tsr_spread_edges).  A ragged last block is thresholded on the
+ *   window of the final block_len frames (:1595-1633); that whole window goes to
+ *   tail_bits_or_null [B][min(T,block_len)][F] so the caller can spread it as the reference does.
+ *   taus_or_null double [B][ceil(T/block_len)][8] receives tau (report_level; 0 for an empty block).
+ * tsr_edges_from_spectrogram fuses both: spectrogram in, packed edge bytes out, magnitudes never stored. */
+int tsr_edge_map(const double* S, double* mags, int B, int F, int T, void* stream);
+int tsr_threshold_edges(const double* mags, uint8_t* bits, uint8_t* tail_bits_or_null, double* taus_or_null, int B, int F,
+                        int T, int block_len, double quantile, const double* host_abst_threshold, void* stream);
+int tsr_edges_from_spectrogram(const double* S, uint8_t* bits, uint8_t* tail_bits_or_null, double* taus_or_null, int B, int F,
+                               int T, int block_len, double quantile, const double* host_abst_threshold, void* stream);
+
 /* ---- K4: Bernoulli-mixture EM -----------------------------------------------------------------
  * Replaces BernoulliMixture.get_template_loglikelihoods/_compute_loglikelihoods
  * (bernoulli_mixture.py:263-291), M_step/threshold_templates (:177-193) and the same steps

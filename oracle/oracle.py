@@ -22,8 +22,11 @@ Pinning status (see DESIGN.md "Oracle"):
       from it (tests/golden/make_golden.py).
   Bernoulli mixture EM               : pinned by the docstring known-answer at
       bernoulli_mixture.py:50-71; otherwise parity unpinned by the reference's tests.
-  edge spreading, linear filter      : parity unpinned by the reference's own tests
-      (no fixture exists); restated line by line, cross-checked with scipy.ndimage.
+  edge front end (N4 edge extraction, N3 block thresholding) and edge spreading : pinned by
+      tests/golden/ref_edges.npz, produced by EXECUTING the reference's own functions
+      (tests/golden/make_golden_edges.py; Python-2 idioms patched as documented there).
+  linear filter                      : parity unpinned by the reference's own tests
+      (no fixture exists); restated line by line.
 """
 import ctypes
 import importlib
@@ -250,6 +253,89 @@ def spread_edgemap_all(T, edge_feature_row_breaks, spread_length):
         out = np.empty_like(blk)
         lib().oracle_spread_edges_box(_p(blk, _f64), blk.shape[0], blk.shape[1], int(spread_length), _p(out, _f64))
         T[s:e, :] = out
+
+
+# --------------------------------------------------------- edge front end (N4, N3)
+ABST_THRESHOLD = np.array([0.025, 0.025, 0.015, 0.015, 0.02, 0.02, 0.02, 0.02])   # edge_signal_proc.py:1187
+# orientation table the extractor returns (:1751-1821): (frequency step, time step) per block
+EDGE_ORIENTATIONS = np.array([[0, 1], [0, -1], [1, 0], [-1, 0], [1, 1], [-1, -1], [-1, 1], [1, -1]])
+
+
+def _edge_map_no_threshold(S):
+    """edge_signal_proc.py:1697-1836 (time_axis_0=False, 2-D output).  For each of the four
+    directions: a first-difference field D, kept where it is a (weak) local extremum of the right
+    sign among its two neighbours along the direction; positive member then negative member."""
+    S = np.asarray(S, np.float64)
+    H, W = S.shape
+    E = np.zeros((8 * H, W))
+    # (D, rows of E written, columns of E written, neighbour before, neighbour after) as slices of D
+    mid, lo, hi = slice(1, -1), slice(None, -2), slice(2, None)
+    fields = (
+        (S[:, 1:] - S[:, :-1], slice(0, H), slice(1, -2), (slice(None), lo), (slice(None), hi), (slice(None), mid)),    # :1744-1759
+        (S[1:, :] - S[:-1, :], slice(1, H - 2), slice(None), (lo, slice(None)), (hi, slice(None)), (mid, slice(None))),  # :1764-1779
+        (S[1:, 1:] - S[:-1, :-1], slice(1, H - 2), slice(1, -2), (lo, lo), (hi, hi), (mid, mid)),                        # :1784-1799
+        (S[:-1, 1:] - S[1:, :-1], slice(1, H - 2), slice(1, -2), (hi, lo), (lo, hi), (mid, mid)),                        # :1804-1819
+    )
+    for pair, (D, rows, cols, before, after, centre) in enumerate(fields):
+        C = D[centre]
+        for sign, e in ((1.0, 2 * pair), (-1.0, 2 * pair + 1)):
+            if sign > 0:
+                if not np.any(D > 0):
+                    continue
+                keep = (C >= D[before]) * (C >= D[after]) * (C >= 0)
+                val = C * keep
+            else:
+                if not np.any(D < 0):
+                    continue
+                keep = (C <= D[before]) * (C <= D[after]) * (C <= 0)
+                val = -C * keep
+            E[e * H + (rows.start or 0):e * H + (rows.stop if rows.stop is not None else H), cols] = val
+    breaks = np.arange(9) * H
+    return E, breaks, EDGE_ORIENTATIONS.copy()
+
+
+def threshold_edge_block(E_block, quantile_level, abst_threshold):
+    """edge_signal_proc.py:1261-1307 with convert_to_binary=True: returns (binary block, tau or None)."""
+    pos = E_block > 0
+    vals = np.sort(E_block[pos].ravel())
+    if vals.shape[0] == 0:
+        return np.zeros(E_block.shape), None
+    tau = vals[int(quantile_level * vals.shape[0])]
+    return (pos & (E_block >= max(tau, abst_threshold))).astype(np.float64), tau
+
+
+def threshold_edgemap(E, quantile_level, edge_feature_row_breaks, abst_threshold=ABST_THRESHOLD):
+    """edge_signal_proc.py:1184-1256 without critical bands: returns (binary map, taus (8,))."""
+    out, taus = np.empty(E.shape), np.zeros(len(edge_feature_row_breaks) - 1)
+    for e in range(len(edge_feature_row_breaks) - 1):
+        a, b = int(edge_feature_row_breaks[e]), int(edge_feature_row_breaks[e + 1])
+        out[a:b], tau = threshold_edge_block(E[a:b], quantile_level, abst_threshold[e])
+        taus[e] = 0.0 if tau is None else tau
+    return out, taus
+
+
+def _edge_map_threshold_segments(E, block_length, spread_length, threshold=.7, edge_orientations=EDGE_ORIENTATIONS,
+                                 edge_feature_row_breaks=None, abst_threshold=ABST_THRESHOLD, spread_type='unidirectional'):
+    """edge_signal_proc.py:1537-1675, in place on E (raw magnitudes -> binary, spread per block).  The ragged
+    last block is thresholded and spread on the window of the final block_length frames (:1595-1633)."""
+    length = E.shape[1]
+    if edge_feature_row_breaks is None:
+        edge_feature_row_breaks = np.arange(9) * (E.shape[0] // 8)
+
+    def one(window):
+        binary, _ = threshold_edgemap(window, threshold, edge_feature_row_breaks, abst_threshold)
+        if spread_length > 0 and spread_type == 'unidirectional':
+            spread_edgemap(binary, edge_feature_row_breaks, edge_orientations, spread_length)
+        elif spread_length > 0 and spread_type == 'all':
+            spread_edgemap_all(binary, edge_feature_row_breaks, spread_length)
+        return binary
+
+    nfull, last = length // block_length, length % block_length
+    tail = one(E[:, -block_length:].copy())[:, -last:] if last > 0 else None
+    for blk in range(nfull):
+        E[:, blk * block_length:(blk + 1) * block_length] = one(E[:, blk * block_length:(blk + 1) * block_length])
+    if last > 0:
+        E[:, -last:] = tail
 
 
 # ------------------------------------------------------------- linear filter / LLR

@@ -11,7 +11,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libtsr_b200.so")
-SOURCES = ("util.cu", "spread.cu", "code_parts.cu", "patches.cu", "detect.cu", "em.cu")
+SOURCES = ("util.cu", "spread.cu", "code_parts.cu", "patches.cu", "edges.cu", "detect.cu", "em.cu")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "--use_fast_math=false", "-Xcompiler", "-fPIC", "-Xcompiler", "-O2", "-Xptxas", "-v"]
 

@@ -93,6 +93,73 @@ def spread_edges(bits, radius, orientations=None, mode="line", block_len=0):
     return out
 
 
+# ------------------------------------------------------------------------- N4 / N3
+# edge_signal_proc.py:1187: per-orientation absolute floor of the quantile threshold
+DEFAULT_ABST_THRESHOLD = np.array([0.025, 0.025, 0.015, 0.015, 0.02, 0.02, 0.02, 0.02], np.float64)
+
+
+def edge_map(S):
+    """S float64 (B,F,T) spectrograms -> raw edge magnitudes float64 (B,8,F,T)
+    (edge_signal_proc._edge_map_no_threshold, :1697-1836)."""
+    S = _dev(S, torch.float64, "S")
+    B, F, T = S.shape
+    mags = torch.empty((B, 8, F, T), dtype=torch.float64, device=S.device)
+    _lib.call("tsr_edge_map", _ptr(S), _ptr(mags), B, F, T, _stream())
+    return mags
+
+
+def _threshold(entry, src, B, F, T, block_len, quantile, abst_threshold, want_taus):
+    abst = np.ascontiguousarray(DEFAULT_ABST_THRESHOLD if abst_threshold is None else abst_threshold, dtype=np.float64)
+    if abst.shape != (8,):
+        raise ValueError("abst_threshold must hold 8 values (one per orientation)")
+    block_len = int(block_len)
+    if block_len < 1:
+        raise ValueError("block_len must be positive")
+    bits = torch.empty((B, T, F), dtype=torch.uint8, device=src.device)
+    ragged = T % block_len != 0
+    tail = torch.empty((B, min(T, block_len), F), dtype=torch.uint8, device=src.device) if ragged else None
+    taus = torch.empty((B, -(-T // block_len), 8), dtype=torch.float64, device=src.device) if want_taus else None
+    _lib.call(entry, _ptr(src), _ptr(bits), _ptr(tail), _ptr(taus), B, F, T, block_len, float(quantile), abst.ctypes.data,
+              _stream())
+    return bits, tail, taus
+
+
+def threshold_edges(mags, block_len, quantile=.7, abst_threshold=None, want_taus=False):
+    """Per (block, orientation) quantile thresholding of raw magnitudes (B,8,F,T) -> packed edge bytes
+    (B,T,F) (threshold_edgemap per block, edge_signal_proc.py:1184-1307, 1537-1675).  Returns
+    (bits, tail_bits or None, taus or None); tail_bits is the thresholded window of the final block_len
+    frames when T is not a multiple of block_len (see spread_edge_blocks)."""
+    mags = _dev(mags, torch.float64, "mags")
+    B, E, F, T = mags.shape
+    if E != 8:
+        raise ValueError("mags must have 8 orientation planes")
+    return _threshold("tsr_threshold_edges", mags, B, F, T, block_len, quantile, abst_threshold, want_taus)
+
+
+def edges_from_spectrogram(S, block_len, quantile=.7, abst_threshold=None, want_taus=False):
+    """edge_map + threshold_edges in one kernel: magnitudes are recomputed from a shared-memory tile of the
+    spectrogram and never written to HBM."""
+    S = _dev(S, torch.float64, "S")
+    B, F, T = S.shape
+    return _threshold("tsr_edges_from_spectrogram", S, B, F, T, block_len, quantile, abst_threshold, want_taus)
+
+
+def spread_edge_blocks(bits, tail_bits, radius, block_len, orientations=None, mode="line"):
+    """Spreading as _edge_map_threshold_segments applies it (:1617-1673): inside each block_len-frame block,
+    and for a ragged last block inside the window of the final block_len frames, of which the last
+    T % block_len frames are kept (:1633)."""
+    if radius <= 0:
+        return bits
+    out = spread_edges(bits, radius, orientations, mode, block_len)
+    T = bits.shape[1]
+    last = T % int(block_len)
+    if last:
+        if tail_bits is None:
+            raise ValueError("a ragged last block needs the tail window from threshold_edges")
+        out[:, T - last:] = spread_edges(tail_bits, radius, orientations, mode, 0)[:, -last:]
+    return out
+
+
 # ------------------------------------------------------------------------------- K2
 class PartsModel:
     """Device copy of a part dictionary in the coding kernel's layout (tsr_prepare_parts)."""

@@ -2,6 +2,8 @@
 golden vectors generated from the compiled reference Cython, the compiled reference itself
 when present in this container, the docstring known-answer of BernoulliMixture, and
 independent NumPy/SciPy formulations.  CPU only."""
+import os
+
 import numpy as np
 import pytest
 
@@ -217,3 +219,40 @@ def test_synth_generators_are_seeded():
     assert synth.fast_edge_batch(4).shape == (4, 300, 40, 8)
     lp, lip = synth.parts(5)
     assert lp.dtype == np.float64 and np.allclose(np.exp(lp) + np.exp(lip), 1)
+
+
+# ------------------------------------------------------------------ edge front end (N4, N3) and edge spreading
+GOLD_EDGE_CASES = [(q, s, kind) for q in (0.7, 0.3) for s, kind in ((0, "unidirectional"), (1, "unidirectional"),
+                                                                     (3, "unidirectional"), (2, "all"))]
+
+
+@pytest.fixture(scope="module")
+def golden_edges():
+    return dict(np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_edges.npz")))
+
+
+@pytest.mark.parametrize("tag", ["a", "b", "c"])
+def test_edge_front_end_golden(oracle, golden_edges, tag):
+    """The restatement against outputs of the reference's OWN functions (tests/golden/make_golden_edges.py):
+    edge extraction, block thresholding (full, exact and ragged/short last blocks), both spread types."""
+    g = golden_edges
+    E, breaks, ori = oracle._edge_map_no_threshold(g["S_" + tag])
+    np.testing.assert_array_equal(E, g["E_" + tag])
+    np.testing.assert_array_equal(breaks, g["breaks_" + tag])
+    np.testing.assert_array_equal(ori, g["ori_" + tag])
+    blk = int(g["blk_" + tag])
+    for q, s, kind in GOLD_EDGE_CASES:
+        Eb = g["E_" + tag].copy()
+        oracle._edge_map_threshold_segments(Eb, blk, s, threshold=q, edge_orientations=ori,
+                                            edge_feature_row_breaks=breaks, spread_type=kind)
+        np.testing.assert_array_equal(Eb.astype(np.uint8), g["bin_%s_q%d_s%d_%s" % (tag, int(q * 10), s, kind[:3])])
+    _, taus = oracle.threshold_edgemap(g["E_" + tag][:, :blk].copy(), 0.7, breaks)
+    np.testing.assert_array_equal(taus, g["taus_" + tag])
+
+
+def test_spread_edgemap_golden(oracle, golden_edges):
+    g = golden_edges
+    for s in (1, 2, 3):
+        T = g["spread_in"].astype(np.float64)
+        oracle.spread_edgemap(T, g["spread_breaks"], g["ori_a"], s)
+        np.testing.assert_array_equal(T.astype(np.uint8), g["spread_s%d" % s])

@@ -29,6 +29,11 @@ sb = ops.spread_edges(bits, a.radius, None, "line", 40)
 codes, _, _ = ops.code_parts(sb, parts, 12)
 fb = ops.spread_codes(codes, 100, 2, 2)
 scores = ops.detect(fb, bank)
+spec = None
+if "edges_fused" in a.stages or "edge_map" in a.stages or "threshold" in a.stages:
+    g = torch.Generator(device="cuda").manual_seed(1)
+    spec = (torch.randn((B, 40, 300), dtype=torch.float64, device="cuda", generator=g).cumsum(2) * 0.03)
+    mags = ops.edge_map(spec)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 torch.cuda.synchronize()
 calls = {
@@ -36,6 +41,9 @@ calls = {
     "code_parts": (lambda: ops.code_parts(sb, parts, 12), 2.0 * 296 * 36 * 200 * 100 * B, "FLOP"),
     "spread_codes": (lambda: ops.spread_codes(codes, 100, 2, 2), 17.0 * 36 * 296 * B, "B"),
     "detect": (lambda: ops.detect(fb, bank, out=scores), 2.0 * 257 * 40 * 3600 * 32 * B, "FLOP"),
+    "edges_fused": (lambda: ops.edges_from_spectrogram(spec, 40, 0.7), 9.0 * 300 * 40 * B, "B"),
+    "edge_map": (lambda: ops.edge_map(spec), 72.0 * 300 * 40 * B, "B"),
+    "threshold": (lambda: ops.threshold_edges(mags, 40, 0.7), 65.0 * 300 * 40 * B, "B"),
     "reduce": (lambda: ops.detect_reduce(scores, bank.cs, 40), (32 * 4 + 6.0) * 296 * B, "B"),
 }
 for name in a.stages:
