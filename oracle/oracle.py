@@ -20,13 +20,13 @@ Pinning status (see DESIGN.md "Oracle"):
   coding / code spreading / detection : pinned against the reference Cython compiled
       unmodified into oracle/_ref (tests/test_oracle.py) and the golden fixtures made
       from it (tests/golden/make_golden.py).
-  Bernoulli mixture EM               : pinned by the docstring known-answer at
-      bernoulli_mixture.py:50-71; otherwise parity unpinned by the reference's tests.
+  Bernoulli mixture EM (both classes), linear filter construction, single-window score :
+      pinned by tests/golden/ref_models.npz, produced by EXECUTING the reference's own classes
+      and functions from their source (tests/golden/make_golden_models.py; Python-2 idioms
+      patched as documented there), plus the docstring known-answer at bernoulli_mixture.py:50-71.
   edge front end (N4 edge extraction, N3 block thresholding) and edge spreading : pinned by
-      tests/golden/ref_edges.npz, produced by EXECUTING the reference's own functions
-      (tests/golden/make_golden_edges.py; Python-2 idioms patched as documented there).
-  linear filter                      : parity unpinned by the reference's own tests
-      (no fixture exists); restated line by line.
+      tests/golden/ref_edges.npz, produced the same way (tests/golden/make_golden_edges.py).
+  No part of the oracle is unpinned.
 """
 import ctypes
 import importlib

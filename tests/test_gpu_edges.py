@@ -132,3 +132,13 @@ def test_front_end_feeds_coding(cuda, oracle):
         X = np.ascontiguousarray(E.reshape(8, F, T).transpose(2, 1, 0)).astype(np.uint8)
         ref = np.argmax(oracle.code_parts(X, lp, lip, 12), -1)
         assert (codes[b] != ref).mean() < 1e-3          # near-ties only (tests/test_gpu_code_parts.py pins the margin)
+
+
+def test_spread_edgemap_reference_golden(cuda, golden_edges):
+    """edge spreading drop-in against the reference's own spread_edgemap (executed from source)"""
+    from tsr_b200 import edge_signal_proc as esp
+    g = golden_edges
+    for s in (1, 2, 3):
+        T = g["spread_in"].astype(np.float64)
+        esp.spread_edgemap(T, g["spread_breaks"], g["ori_a"], s)
+        np.testing.assert_array_equal(T.astype(np.uint8), g["spread_s%d" % s])

@@ -102,3 +102,56 @@ def test_config4_shape_against_restatement(cuda, oracle):
     tr = np.array(b.loglikelihood_trace)
     assert np.all(np.diff(tr) > -1e-5 * np.abs(tr[:-1]))          # EM never decreases the likelihood
     np.testing.assert_allclose(b.weights, a.weights, atol=2e-3)
+
+
+# ------------------------------------------------------------------ against the reference's own classes
+def _golden_models():
+    import os
+    return dict(np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_models.npz")))
+
+
+@pytest.mark.parametrize("tag", ["a", "b", "c"])
+def test_bernoulli_mixture_reference_golden(cuda, tag):
+    """GPU run_EM against run_EM of the reference class executed from its source
+    (tests/golden/make_golden_models.py): log-likelihood trace within 1e-5 relative, same stopping iteration."""
+    from tsr_b200.bernoulli_mixture import BernoulliMixture
+    g = _golden_models()
+    kw = eval(str(g["bm_%s_kw" % tag]), {"__builtins__": {}}, {"dict": dict, "True": True, "False": False})
+    tol = kw.pop("tol")
+    m = BernoulliMixture(int(g["bm_%s_K" % tag]), g["bm_%s_X" % tag])
+    m.run_EM(tol, **kw)
+    ref = g["bm_%s_loglik" % tag]
+    n = min(len(ref), len(m.loglikelihood_trace))
+    np.testing.assert_allclose(m.loglikelihood_trace[:n], ref[:n], rtol=RTOL)
+    assert abs(m.iterations - int(g["bm_%s_iterations" % tag])) <= 1
+    assert m.templates.shape == g["bm_%s_templates" % tag].shape
+    if m.iterations == int(g["bm_%s_iterations" % tag]):
+        np.testing.assert_allclose(m.templates, g["bm_%s_templates" % tag], atol=2e-3)
+        np.testing.assert_allclose(m.weights, g["bm_%s_weights" % tag], atol=1e-3)
+        np.testing.assert_allclose(m.affinities, g["bm_%s_affinities" % tag], atol=5e-3)
+
+
+def test_preset_first_version_filters_reference_golden(cuda):
+    from tsr_b200 import estimate_template as et, test_template as tt
+    from tsr_b200.bernoulli_em import Bernoulli_Mixture
+    from tsr_b200.bernoulli_mixture import BernoulliMixture
+    g = _golden_models()
+    m = BernoulliMixture(3, g["bm_p_X"], init_type='preset', init_centers=g["bm_p_centers"])
+    m.run_EM(1e-5, min_probability=.02)
+    n = min(len(g["bm_p_loglik"]), len(m.loglikelihood_trace))
+    np.testing.assert_allclose(m.loglikelihood_trace[:n], g["bm_p_loglik"][:n], rtol=RTOL)
+    if m.iterations == int(g["bm_p_iterations"]):
+        np.testing.assert_allclose(m.templates, g["bm_p_templates"], atol=2e-3)
+    b = Bernoulli_Mixture(2, g["be_X"])
+    b.run_EM(1e-4)
+    np.testing.assert_allclose(b.loglikelihood, g["be_loglik"][-1], rtol=1e-4)
+    np.testing.assert_allclose(b.templates, g["be_templates"], atol=5e-3)
+    W, c = et.construct_linear_filter(g["lf_T"], g["lf_bgd"])
+    np.testing.assert_array_equal(W, g["lf_W"])
+    np.testing.assert_allclose(c, g["lf_c"], rtol=1e-12)
+    W, c = et.construct_linear_filter(g["lf_T"], g["lf_bgd"], all_cs=True)
+    np.testing.assert_allclose(c, g["lf_c_allcs"], rtol=1e-12)
+    fs = et.construct_linear_filters((g["lf_T"], g["lf_T"][::-1] ** 2), g["lf_bgd"])
+    np.testing.assert_array_equal(fs[1][0], g["lfs_W1"])
+    s, C = tt.score_template_background_section(g["sc_template"], g["sc_bgd"], g["sc_E"])
+    np.testing.assert_allclose([s, C], [g["sc_s"], g["sc_C"]], rtol=1e-5)

@@ -256,3 +256,61 @@ def test_spread_edgemap_golden(oracle, golden_edges):
         T = g["spread_in"].astype(np.float64)
         oracle.spread_edgemap(T, g["spread_breaks"], g["ori_a"], s)
         np.testing.assert_array_equal(T.astype(np.uint8), g["spread_s%d" % s])
+
+
+# ------------------------------------------------------------------ model-side code executed from the reference
+@pytest.fixture(scope="module")
+def golden_models():
+    return dict(np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_models.npz")))
+
+
+def _em_kwargs(g, tag):
+    kw = eval(str(g["bm_%s_kw" % tag]), {"__builtins__": {}}, {"dict": dict, "True": True, "False": False})
+    return kw.pop("tol"), kw
+
+
+@pytest.mark.parametrize("tag", ["a", "b", "c"])
+def test_bernoulli_mixture_golden(oracle, golden_models, tag):
+    """run_EM of the restatement against run_EM of the reference class itself (tests/golden/make_golden_models.py):
+    soft and hard assignment, N not a multiple of K, 1-/2-/3-D data shapes, max_iter / min_iter stops."""
+    g = golden_models
+    tol, kw = _em_kwargs(g, tag)
+    m = oracle.BernoulliMixture(int(g["bm_%s_K" % tag]), g["bm_%s_X" % tag])
+    m.run_EM(tol, **kw)
+    assert m.iterations == int(g["bm_%s_iterations" % tag])
+    np.testing.assert_allclose(m.loglikelihood_trace, g["bm_%s_loglik" % tag], rtol=1e-12)
+    np.testing.assert_allclose(m.templates, g["bm_%s_templates" % tag], rtol=1e-6)
+    np.testing.assert_allclose(m.weights, g["bm_%s_weights" % tag], rtol=1e-6)
+    np.testing.assert_allclose(m.affinities, g["bm_%s_affinities" % tag], atol=1e-7)
+
+
+def test_bernoulli_mixture_preset_and_first_version_golden(oracle, golden_models):
+    g = golden_models
+    m = oracle.BernoulliMixture(3, g["bm_p_X"], init_type='preset', init_centers=g["bm_p_centers"])
+    m.run_EM(1e-5, min_probability=.02)
+    assert m.iterations == int(g["bm_p_iterations"])
+    np.testing.assert_allclose(m.loglikelihood_trace, g["bm_p_loglik"], rtol=1e-12)
+    np.testing.assert_allclose(m.templates, g["bm_p_templates"], rtol=1e-6)
+    np.testing.assert_allclose(m.affinities, g["bm_p_affinities"], atol=1e-7)
+    m = oracle.Bernoulli_Mixture(2, g["be_X"])
+    m.run_EM(1e-4)
+    np.testing.assert_allclose(m.templates, g["be_templates"], rtol=1e-12)
+    np.testing.assert_allclose(m.weights, g["be_weights"], rtol=1e-12)
+    np.testing.assert_allclose(m.affinities, g["be_affinities"], atol=1e-12)
+
+
+def test_linear_filter_and_window_score_golden(oracle, golden_models):
+    g = golden_models
+    W, c = oracle.construct_linear_filter(g["lf_T"], g["lf_bgd"])
+    assert W.dtype == np.float32
+    np.testing.assert_array_equal(W, g["lf_W"])
+    np.testing.assert_allclose(c, g["lf_c"], rtol=1e-14)
+    W, c = oracle.construct_linear_filter(g["lf_T"], g["lf_bgd"], all_cs=True)
+    np.testing.assert_array_equal(W, g["lf_W_allcs"])
+    np.testing.assert_allclose(c, g["lf_c_allcs"], rtol=1e-14)
+    fs = oracle.construct_linear_filters((g["lf_T"], g["lf_T"][::-1] ** 2), g["lf_bgd"])
+    np.testing.assert_array_equal(fs[0][0], g["lfs_W0"])
+    np.testing.assert_array_equal(fs[1][0], g["lfs_W1"])
+    np.testing.assert_allclose([fs[0][1], fs[1][1]], [g["lfs_c0"], g["lfs_c1"]], rtol=1e-14)
+    s, C = oracle.score_template_background_section(g["sc_template"], g["sc_bgd"], g["sc_E"])
+    np.testing.assert_allclose([s, C], [g["sc_s"], g["sc_C"]], rtol=1e-14)
