@@ -16,7 +16,9 @@
 //   epilogue (4 warps)   tcgen05.ld the 128 x N_pad fp32 tile, add c[k], running arg-max (lowest k
 //                        wins ties), read the exact edge counts from two extra weight columns
 //                        (all-ones / mask), apply the gate, store uint8 codes.
-// Two TMEM accumulator buffers and a 4-deep A ring overlap the three roles.
+// Four TMEM accumulator buffers (two per epilogue set) and a 4-deep A ring overlap the three roles: an
+// accumulator is held by the epilogue for about as long as the MMAs need to fill it, so with only two the MMA
+// warp idled half the time waiting for a free one.
 #include "common.cuh"
 
 namespace tsr {
@@ -199,6 +201,7 @@ __global__ void __launch_bounds__(256) code_parts_simt_kernel(CodeArgs A) {
 #define CP_NSTAGE 4
 #define CP_THREADS 416   // warps 0-3 / 4-7 epilogue (even / odd tiles), 8-11 producers, 12 MMA + TMEM (highest id: wins arbitration)
 #define CP_MAX_STEPS 32
+#define CP_NACC 4         // barrier slots; TMEM accumulators in use: 4 x 128 columns when N_pad <= 128, else 2 x 256
 
 struct CodeSmem {   // offsets into dynamic shared memory
     uint32_t w, c, a, bars, stage_bytes, npos, total;
@@ -211,7 +214,7 @@ __host__ __device__ inline CodeSmem code_smem_layout(const PartsLayout& L, int F
     S.npos = 128 + (L.ph - 1) * F + (L.pw - 1) + 2;
     S.stage_bytes = (S.npos * 16 + 127) & ~127u;
     S.bars = S.a + CP_NSTAGE * S.stage_bytes;
-    S.total = S.bars + 128 + CP_MAX_STEPS * 4;   // barriers | generic-path A descriptor words
+    S.total = S.bars + 192 + CP_MAX_STEPS * 4;   // barriers | generic-path A descriptor words
     return S;
 }
 
@@ -224,18 +227,19 @@ __global__ void __launch_bounds__(CP_THREADS, 1) code_parts_tc_kernel(CodeArgs A
     const CodeSmem S = code_smem_layout(L, A.F);
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S.bars);       // [CP_NSTAGE]
     uint64_t* empty_bar = full_bar + CP_NSTAGE;                            // [CP_NSTAGE]
-    uint64_t* tfull_bar = empty_bar + CP_NSTAGE;                           // [2]
-    uint64_t* tempty_bar = tfull_bar + 2;                                  // [2]
-    uint64_t* w_bar = tempty_bar + 2;                                      // [1]
+    uint64_t* tfull_bar = empty_bar + CP_NSTAGE;                           // [CP_NACC]
+    uint64_t* tempty_bar = tfull_bar + CP_NACC;                            // [CP_NACC]
+    uint64_t* w_bar = tempty_bar + CP_NACC;                                // [1]
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(w_bar + 1);
     const float* cs = reinterpret_cast<const float*>(smem + S.c);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t fmt = reinterpret_cast<const uint32_t*>(A.blob + L.off_hdr)[0];
+    const uint32_t nacc = L.npad <= 128 ? 4u : 2u, acc_cols = 512u / nacc;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < CP_NSTAGE; ++s) { mbar_init(&full_bar[s], 128); mbar_init(&empty_bar[s], 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 128); }
+        for (int a = 0; a < CP_NACC; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 128); }
         mbar_init(w_bar, 1);
         mbar_fence_init();
     }
@@ -316,7 +320,7 @@ __global__ void __launch_bounds__(CP_THREADS, 1) code_parts_tc_kernel(CodeArgs A
         const uint32_t b_step = 2 * L.npad;
         constexpr int NS = NSTEPS_CT > 0 ? NSTEPS_CT : 1;
         uint32_t a_lo[NS];
-        uint32_t* a_tab = reinterpret_cast<uint32_t*>(smem + S.bars + 128);   // generic path: [nsteps]
+        uint32_t* a_tab = reinterpret_cast<uint32_t*>(smem + S.bars + 192);   // generic path: [nsteps]
         {
             int pa = 0, pb = 0;
             for (int s = 0; s < L.nsteps; ++s) {
@@ -341,15 +345,15 @@ __global__ void __launch_bounds__(CP_THREADS, 1) code_parts_tc_kernel(CodeArgs A
         for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
             const int stage = it % CP_NSTAGE;
             const uint32_t ph = (it / CP_NSTAGE) & 1;
-            const int acc = it & 1;
-            const uint32_t aph = (it >> 1) & 1;
+            const int acc = it % nacc;
+            const uint32_t aph = (it / nacc) & 1;
             mbar_wait(&full_bar[stage], ph);
             CP_TRACE(2);
             mbar_wait(&tempty_bar[acc], aph ^ 1);
             CP_TRACE(3);
             tc_fence_after();
             const uint32_t a_base = smem_u32(smem + S.a + stage * S.stage_bytes) >> 4;
-            const uint32_t d_tmem = tmem_base + acc * 256;
+            const uint32_t d_tmem = tmem_base + acc * acc_cols;
             if (!(A.dbg & 2)) {
                 uint32_t b_lo = b_base;
                 if (NSTEPS_CT > 0) {
@@ -383,8 +387,8 @@ __global__ void __launch_bounds__(CP_THREADS, 1) code_parts_tc_kernel(CodeArgs A
         const int ccol = L.K & ~7;   // 16-column window holding the count (K) and mask-count (K+1) columns
         uint32_t it = eset;
         for (long long tile = blockIdx.x + (long long)eset * gridDim.x; tile < ntiles; tile += 2ll * gridDim.x, it += 2) {
-            const int acc = eset;
-            const uint32_t aph = (it >> 1) & 1;
+            const int acc = it % nacc;             // this set owns accumulators eset and (with four) eset + 2
+            const uint32_t aph = (it / nacc) & 1;
             const int b = (int)(tile / tiles_per_utt);
             const int p = (int)(tile % tiles_per_utt) * 128 + e;
             const int t = p / A.F, f = p - t * A.F;
@@ -393,7 +397,7 @@ __global__ void __launch_bounds__(CP_THREADS, 1) code_parts_tc_kernel(CodeArgs A
             mbar_wait_relaxed(&tfull_bar[acc], aph);
             if ((warp & 3) == 0) CP_TRACE(5);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + acc * 256 + ((uint32_t)((warp & 3) * 32) << 16);
+            const uint32_t taddr = tmem_base + acc * acc_cols + ((uint32_t)((warp & 3) * 32) << 16);
             // four independent running (max, argmax) chains over columns n = 4j + c; padded columns carry
             // c = -inf.  Strict '>' within a chain keeps the lowest index; the merge breaks ties by index.
             float bv[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};

@@ -54,3 +54,68 @@ class ScoringPipeline:
     def from_numpy(self, X):
         """X uint8 (B,T,F,E) host array -> packed edge bytes on the device."""
         return ops.pack_edges(torch.from_numpy(np.ascontiguousarray(X)).to(self.parts.blob.device))
+
+    def stream(self, host_batches, ring=3):
+        """Score a sequence of host batches with the copies hidden behind the kernels.
+
+        host_batches: iterable of uint8 (B,T,F,E) edge tensors in host memory (pinned torch tensors copy
+        asynchronously; NumPy arrays are accepted and staged through a pinned buffer).  Yields, per batch and in
+        order, ``(best float32 (B,To), argbest int16 (B,To))`` as pinned host tensors that stay valid until
+        ``ring - 1`` further batches have been requested.
+
+        Three streams: the H2D copy of batch i+1 (into the other of two device buffers) and the D2H copy of
+        batch i-1's results run while batch i is packed, coded and scored; every batch still moves its own
+        inputs in and its own results out.
+        """
+        dev = self.parts.blob.device
+        main = torch.cuda.current_stream(dev)
+        h2d, d2h = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+        xd, staged, free_ev = [None, None], [None, None], [None, None]
+        outs, out_ev = [None] * ring, [None] * ring
+        pending = None
+        for i, xb in enumerate(host_batches):
+            k = i & 1
+            if not isinstance(xb, torch.Tensor):
+                xb = np.ascontiguousarray(xb)
+                if staged[k] is None or staged[k].shape != xb.shape:
+                    staged[k] = torch.empty(xb.shape, dtype=torch.uint8).pin_memory()
+                if free_ev[k] is not None:
+                    free_ev[k].synchronize()              # the previous copy out of this staging buffer has been consumed
+                staged[k].numpy()[...] = xb
+                xb = staged[k]
+            if xb.dtype != torch.uint8 or xb.dim() != 4:
+                raise ValueError("edge batches must be uint8 (B,T,F,E)")
+            if xd[k] is None or xd[k].shape != xb.shape:
+                xd[k] = torch.empty(xb.shape, dtype=torch.uint8, device=dev)
+            with torch.cuda.stream(h2d):
+                if free_ev[k] is not None:
+                    h2d.wait_event(free_ev[k])            # pack_edges of batch i-2 has finished reading this buffer
+                xd[k].copy_(xb, non_blocking=True)
+                arrived = torch.cuda.Event()
+                arrived.record(h2d)
+            main.wait_event(arrived)
+            bits = ops.pack_edges(xd[k])
+            free_ev[k] = torch.cuda.Event()
+            free_ev[k].record(main)
+            best, arg, _ = self(bits)
+            scored = torch.cuda.Event()
+            scored.record(main)
+            r = i % ring
+            if outs[r] is None or outs[r][0].shape != best.shape:
+                outs[r] = (torch.empty(best.shape, dtype=torch.float32).pin_memory(),
+                           torch.empty(arg.shape, dtype=arg.dtype).pin_memory())
+            with torch.cuda.stream(d2h):
+                d2h.wait_event(scored)
+                outs[r][0].copy_(best, non_blocking=True)
+                outs[r][1].copy_(arg, non_blocking=True)
+                best.record_stream(d2h)
+                arg.record_stream(d2h)
+                out_ev[r] = torch.cuda.Event()
+                out_ev[r].record(d2h)
+            if pending is not None:
+                out_ev[pending].synchronize()
+                yield outs[pending]
+            pending = r
+        if pending is not None:
+            out_ev[pending].synchronize()
+            yield outs[pending]

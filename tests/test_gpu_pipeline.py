@@ -39,3 +39,27 @@ def test_pipeline_matches_oracle_chain(cuda, oracle):
         top2 = np.sort(v, -1)
         clear = (top2[:, -1] - top2[:, -2]) > 1e-4 * np.abs(top2[:, -1])
         np.testing.assert_array_equal(arg[b][clear], v.argmax(-1)[clear])
+
+
+def test_stream_equals_direct_calls(cuda):
+    """ScoringPipeline.stream (double-buffered H2D / D2H on side streams) returns, batch by batch, exactly what a
+    direct call on the same batch returns -- pinned tensors and NumPy arrays in, changing batch sizes, ring reuse."""
+    from tsr_b200 import synth
+    from tsr_b200.pipeline import ScoringPipeline
+    lp, lip = synth.parts(30)
+    T, bgd = synth.templates(M=3, L=10, Fd=36, Kd=30)
+    W, c = synth.linear_filters(T, bgd)
+    pipe = ScoringPipeline(lp, lip, W, c)
+    batches = [synth.fast_edge_batch(b, T=120, seed=s) for s, b in enumerate([5, 5, 3, 8, 8, 8, 1])]
+    want = []
+    for X in batches:
+        best, arg, _ = pipe(pipe.from_numpy(X))
+        want.append((best.cpu().numpy().copy(), arg.cpu().numpy().copy()))
+    mixed = [torch.from_numpy(X).pin_memory() if i % 2 == 0 else X for i, X in enumerate(batches)]
+    n = 0
+    for (best, arg), (wb, wa) in zip(pipe.stream(iter(mixed)), want):
+        np.testing.assert_array_equal(best.numpy(), wb)
+        np.testing.assert_array_equal(arg.numpy(), wa)
+        n += 1
+    assert n == len(batches)
+    assert list(pipe.stream(iter([]))) == []
