@@ -25,7 +25,7 @@ namespace tsr {
 
 struct PartsLayout {
     int K, ph, pw, npad, nsteps, nq;
-    size_t off_w, off_c, off_wf, off_mask, off_hdr, total;
+    size_t off_w, off_cstep, off_c, off_wf, off_mask, off_hdr, total;
 };
 
 __host__ __device__ inline PartsLayout parts_layout(int K, int ph, int pw) {
@@ -35,7 +35,8 @@ __host__ __device__ inline PartsLayout parts_layout(int K, int ph, int pw) {
     L.npad = ((K + 2) + 15) & ~15;
     L.nsteps = (L.nq + 1) / 2;
     L.off_w = 0;
-    L.off_c = (size_t)2 * L.nsteps * L.npad * 32;
+    L.off_cstep = (size_t)2 * L.nsteps * L.npad * 32;   // one more K-step of weights: c[k] in three 16-bit terms
+    L.off_c = L.off_cstep + (size_t)L.npad * 32;
     L.off_wf = L.off_c + (size_t)L.npad * 4;
     L.off_mask = L.off_wf + (size_t)L.nq * 8 * L.npad * 4;
     L.off_hdr = L.off_mask + 8;          // [0] plane format, [1] max |w| bits
@@ -49,9 +50,16 @@ __global__ void parts_maxabs_kernel(const double* __restrict__ lp, const double*
     uint32_t* hdr = reinterpret_cast<uint32_t*>(blob + L.off_hdr);
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
         atomic_max_abs(&hdr[1], (float)(lp[i] - lip[i]));
+    // c[k] = sum lip rides through the tensor cores as well (see prepare_parts_kernel): fp16 planes only if it fits
+    const size_t per = n / L.K;
+    for (size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x; k < (size_t)L.K; k += (size_t)gridDim.x * blockDim.x) {
+        double c = 0.0;
+        for (size_t i = 0; i < per; ++i) c += lip[k * per + i];
+        atomic_max_abs(&hdr[1], (float)(c * (TSR_FP16_MAX_WEIGHT / 60000.0)));
+    }
 }
 
-// One thread per (n, q, z) weight: n < K parts, n == K all-ones count column, n == K+1 mask column.
+// One thread per (n, q, z) weight: n < K parts, n == N_pad-2 all-ones count column, n == N_pad-1 mask column.
 __global__ void prepare_parts_kernel(const double* __restrict__ lp, const double* __restrict__ lip, int E,
                                      const uint8_t* __restrict__ mask, uint8_t* __restrict__ blob, PartsLayout L,
                                      int plane_format) {
@@ -68,9 +76,9 @@ __global__ void prepare_parts_kernel(const double* __restrict__ lp, const double
             if (n < L.K) {
                 size_t idx = ((size_t)n * L.nq + q) * E + z;
                 w = lp[idx] - lip[idx];
-            } else if (n == L.K) {
+            } else if (n == L.npad - 2) {
                 w = 1.0;
-            } else if (n == L.K + 1) {
+            } else if (n == L.npad - 1) {
                 w = (mask && mask[q]) ? 1.0 : 0.0;
             }
         }
@@ -89,6 +97,21 @@ __global__ void prepare_parts_kernel(const double* __restrict__ lp, const double
             for (int i = 0; i < L.nq * E; ++i) c += lip[(size_t)n * L.nq * E + i];
         // padded columns (count / mask / zero columns) get -inf: they can never win the arg-max
         reinterpret_cast<float*>(blob + L.off_c)[n] = n < L.K ? (float)c : -INFINITY;
+        // tensor path: c[k] = t0 + t1 + t2 (16-bit terms, >= 24 significant bits) sits in elements 0..2 of an extra
+        // K-step whose A operand is a constant [1,1,1,0,...] row, so the accumulator starts at c[k] and the epilogue
+        // needs no shared-memory reads (they stall behind the MMA operand traffic).  Padded columns start at 0.
+        uint16_t t[3] = {0, 0, 0};
+        if (n < L.K) {
+            uint16_t lo_unused;
+            double r = c;
+            for (int j = 0; j < 3; ++j) {
+                split_hi_lo(r, fmt, t[j], lo_unused);
+                r -= fmt == TSR_FMT_FP16 ? (double)__half2float(__ushort_as_half(t[j])) : (double)__bfloat162float(__ushort_as_bfloat16(t[j]));
+            }
+        }
+        uint16_t* row = reinterpret_cast<uint16_t*>(blob + L.off_cstep + (size_t)n * 16);          // k-group 0
+        uint16_t* row1 = reinterpret_cast<uint16_t*>(blob + L.off_cstep + ((size_t)L.npad + n) * 16);  // k-group 1
+        for (int j = 0; j < 8; ++j) { row[j] = j < 3 ? t[j] : (uint16_t)0; row1[j] = 0; }
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         unsigned long long m = 0;
@@ -199,18 +222,19 @@ __global__ void __launch_bounds__(256) code_parts_simt_kernel(CodeArgs A) {
 
 // ------------------------------------------------------------------------- tensor path
 #define CP_NSTAGE 4
-#define CP_THREADS 416   // warps 0-3 / 4-7 epilogue (even / odd tiles), 8-11 producers, 12 MMA + TMEM (highest id: wins arbitration)
+#define CP_THREADS 448   // warps 0-3 / 4-7 epilogue (even / odd tiles), 8-11 producers, 12 / 13 MMA issuers (even / odd tiles; highest ids win arbitration)
 #define CP_MAX_STEPS 32
 #define CP_NACC 4         // barrier slots; TMEM accumulators in use: 4 x 128 columns when N_pad <= 128, else 2 x 256
 
 struct CodeSmem {   // offsets into dynamic shared memory
-    uint32_t w, c, a, bars, stage_bytes, npos, total;
+    uint32_t w, cstep, ones, a, bars, stage_bytes, npos, total;
 };
 __host__ __device__ inline CodeSmem code_smem_layout(const PartsLayout& L, int F) {
     CodeSmem S;
     S.w = 0;
-    S.c = (uint32_t)(2 * L.nsteps * L.npad * 32);
-    S.a = (S.c + (L.npad + 32) * 4 + 127) & ~127u;   // c[] padded with 32 x -inf for the 32-column loads
+    S.cstep = (uint32_t)(2 * L.nsteps * L.npad * 32);          // the c[k] K-step, contiguous with the planes in the blob
+    S.ones = (S.cstep + L.npad * 32 + 127) & ~127u;            // its constant A operand: 128 rows of [1,1,1,0,...], 4 KB
+    S.a = S.ones + 4096;
     S.npos = 128 + (L.ph - 1) * F + (L.pw - 1) + 2;
     S.stage_bytes = (S.npos * 16 + 127) & ~127u;
     S.bars = S.a + CP_NSTAGE * S.stage_bytes;
@@ -231,7 +255,6 @@ __global__ void __launch_bounds__(CP_THREADS, 1) code_parts_tc_kernel(CodeArgs A
     uint64_t* tempty_bar = tfull_bar + CP_NACC;                            // [CP_NACC]
     uint64_t* w_bar = tempty_bar + CP_NACC;                                // [1]
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(w_bar + 1);
-    const float* cs = reinterpret_cast<const float*>(smem + S.c);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t fmt = reinterpret_cast<const uint32_t*>(A.blob + L.off_hdr)[0];
@@ -246,20 +269,25 @@ __global__ void __launch_bounds__(CP_THREADS, 1) code_parts_tc_kernel(CodeArgs A
     if (warp == 12) {
         tmem_alloc<512>(tmem_ptr);
     }
-    if (threadIdx.x < 32) reinterpret_cast<float*>(smem + S.c)[L.npad + threadIdx.x] = -INFINITY;   // tail for 32-wide reads
+    {   // constant A operand of the c[k] step: k-group 0 rows = [1,1,1,0,0,0,0,0], k-group 1 (2 KB further) = 0
+        const uint32_t one = fmt_one(fmt);
+        for (int i = threadIdx.x; i < 256; i += blockDim.x)
+            reinterpret_cast<uint4*>(smem + S.ones)[i] = i < 128 ? make_uint4(one | (one << 16), one, 0u, 0u) : make_uint4(0u, 0u, 0u, 0u);
+        fence_proxy_async_smem();
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
 
     // weights + c: bulk (TMA) copies, landed once per CTA
-    const uint32_t wbytes = S.c + L.npad * 4;
+    const uint32_t wbytes = S.cstep + L.npad * 32;
     if (threadIdx.x == 0) {
         mbar_arrive_expect_tx(w_bar, wbytes);
         const uint32_t half = (uint32_t)(L.nsteps * L.npad * 32);
         bulk_g2s(smem + S.w, A.blob + L.off_w, half, w_bar);
         bulk_g2s(smem + S.w + half, A.blob + L.off_w + half, half, w_bar);
-        bulk_g2s(smem + S.c, A.blob + L.off_c, L.npad * 4, w_bar);
+        bulk_g2s(smem + S.cstep, A.blob + L.off_cstep, L.npad * 32, w_bar);
     }
 
     if (warp >= 8 && warp <= 11) {
@@ -285,7 +313,7 @@ __global__ void __launch_bounds__(CP_THREADS, 1) code_parts_tc_kernel(CodeArgs A
             const int stage = it % CP_NSTAGE;
             const uint32_t ph = (it / CP_NSTAGE) & 1;
             mbar_wait_relaxed(&empty_bar[stage], ph ^ 1);
-            if (warp == 8) CP_TRACE(0);
+            if (warp == 8 && !(A.dbg & 4)) CP_TRACE(0);
             uint8_t* dst = smem + S.a + stage * S.stage_bytes;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -303,11 +331,14 @@ __global__ void __launch_bounds__(CP_THREADS, 1) code_parts_tc_kernel(CodeArgs A
             }
             fence_proxy_async_smem();
             mbar_arrive(&full_bar[stage]);
-            if (warp == 8) CP_TRACE(1);
+            if (warp == 8 && !(A.dbg & 4)) CP_TRACE(1);
             if (tile + gridDim.x < ntiles) prefetch(tile + gridDim.x);   // overlaps the next empty-slot wait
         }
-    } else if (warp == 12) {
-        // ================================ MMA issuer ================================
+    } else if (warp >= 12) {
+        // ================================ MMA issuers ================================
+        // One thread can issue a tcgen05.mma only every ~75-90 cycles (tools/ts_probe.cu: 90.7 cycles per MMA from
+        // one warp, 60.4 from two, against 59 cycles of tensor work at N = 112), so two warps on different SMSPs
+        // issue alternate tiles into their own accumulators; each tile's MMAs stay in one thread's program order.
         // The whole warp runs this loop in lock step; one elected lane issues each tcgen05 op.  The
         // issuing warp executes ~10 instructions per MMA: at 56 tensor cycles per MMA anything more
         // (divisions, table walks, 64-way predicated unrolls) makes the issue loop the bottleneck.
@@ -318,6 +349,8 @@ __global__ void __launch_bounds__(CP_THREADS, 1) code_parts_tc_kernel(CodeArgs A
         const uint64_t desc_hi = (uint64_t)((uint32_t)(128 >> 4) | (1u << 14)) << 32;   // SBO = 128 B, version 1
         const uint32_t b_base = (smem_u32(smem + S.w) >> 4) | ((uint32_t)L.npad << 16);
         const uint32_t b_step = 2 * L.npad;
+        const uint64_t ones_desc = umma_desc_kmajor_noswz(smem_u32(smem + S.ones), 2048, 128);
+        const uint64_t cstep_desc = umma_desc_kmajor_noswz(smem_u32(smem + S.cstep), (uint32_t)L.npad * 16, 128);
         constexpr int NS = NSTEPS_CT > 0 ? NSTEPS_CT : 1;
         uint32_t a_lo[NS];
         uint32_t* a_tab = reinterpret_cast<uint32_t*>(smem + S.bars + 192);   // generic path: [nsteps]
@@ -341,50 +374,49 @@ __global__ void __launch_bounds__(CP_THREADS, 1) code_parts_tc_kernel(CodeArgs A
             }
             __syncwarp();
         }
-        uint32_t it = 0;
-        for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+        const int iss = warp - 12;
+        uint32_t it = iss;
+        for (long long tile = blockIdx.x + (long long)iss * gridDim.x; tile < ntiles; tile += 2ll * gridDim.x, it += 2) {
             const int stage = it % CP_NSTAGE;
             const uint32_t ph = (it / CP_NSTAGE) & 1;
             const int acc = it % nacc;
             const uint32_t aph = (it / nacc) & 1;
             mbar_wait(&full_bar[stage], ph);
-            CP_TRACE(2);
+            if (!(A.dbg & 4)) CP_TRACE(2);
             mbar_wait(&tempty_bar[acc], aph ^ 1);
-            CP_TRACE(3);
+            if (!(A.dbg & 4)) CP_TRACE(3);
             tc_fence_after();
             const uint32_t a_base = smem_u32(smem + S.a + stage * S.stage_bytes) >> 4;
             const uint32_t d_tmem = tmem_base + acc * acc_cols;
             if (!(A.dbg & 2)) {
+                // accumulator := c[k] (constant-ones A x the c step), then the 2 x nsteps patch steps accumulate
+                umma_f16_elect(d_tmem, ones_desc, cstep_desc, idesc, 0u);
                 uint32_t b_lo = b_base;
                 if (NSTEPS_CT > 0) {
 #pragma unroll
                     for (int plane = 0; plane < 2; ++plane)
 #pragma unroll
                         for (int s = 0; s < NS; ++s) {
-                            umma_f16_elect(d_tmem, desc_hi | (uint64_t)(a_lo[s] + a_base), desc_hi | (uint64_t)b_lo, idesc,
-                                           (plane | s) != 0 ? 1u : 0u);
+                            umma_f16_elect(d_tmem, desc_hi | (uint64_t)(a_lo[s] + a_base), desc_hi | (uint64_t)b_lo, idesc, 1u);
                             b_lo += b_step;
                         }
                 } else {
                     for (int plane = 0; plane < 2; ++plane)
                         for (int s = 0; s < L.nsteps; ++s) {
-                            umma_f16_elect(d_tmem, desc_hi | (uint64_t)(a_tab[s] + a_base), desc_hi | (uint64_t)b_lo, idesc,
-                                           (plane | s) != 0 ? 1u : 0u);
+                            umma_f16_elect(d_tmem, desc_hi | (uint64_t)(a_tab[s] + a_base), desc_hi | (uint64_t)b_lo, idesc, 1u);
                             b_lo += b_step;
                         }
                 }
             }
             umma_commit_elect(&empty_bar[stage]);   // A stage reusable once these MMAs retire
             umma_commit_elect(&tfull_bar[acc]);     // accumulator ready for the epilogue
-            CP_TRACE(4);
+            if (!(A.dbg & 4)) CP_TRACE(4);
         }
     } else {
         // ================================ epilogue ================================
         // two warp sets: warps 0-3 drain accumulator 0 (even tiles), warps 4-7 accumulator 1 (odd tiles)
-        mbar_wait_relaxed(w_bar, 0);   // c[] lives in the same bulk transaction
         const int eset = warp >= 4 ? 1 : 0;
         const int e = (warp & 3) * 32 + lane;   // TMEM lane == tile row (lane quadrant = warp % 4)
-        const int ccol = L.K & ~7;   // 16-column window holding the count (K) and mask-count (K+1) columns
         uint32_t it = eset;
         for (long long tile = blockIdx.x + (long long)eset * gridDim.x; tile < ntiles; tile += 2ll * gridDim.x, it += 2) {
             const int acc = it % nacc;             // this set owns accumulators eset and (with four) eset + 2
@@ -398,59 +430,47 @@ __global__ void __launch_bounds__(CP_THREADS, 1) code_parts_tc_kernel(CodeArgs A
             if ((warp & 3) == 0) CP_TRACE(5);
             tc_fence_after();
             const uint32_t taddr = tmem_base + acc * acc_cols + ((uint32_t)((warp & 3) * 32) << 16);
-            // four independent running (max, argmax) chains over columns n = 4j + c; padded columns carry
-            // c = -inf.  Strict '>' within a chain keeps the lowest index; the merge breaks ties by index.
+            // four independent running (max, argmax) chains over columns n = 4j + c of the K part columns (c[k] is
+            // already in the accumulator).  Strict '>' within a chain keeps the lowest index; the merge breaks ties by
+            // index.  No shared-memory access in here: LDS stalls for hundreds of cycles behind the MMA operand reads.
             float bv[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
             int bk[4] = {0, 1, 2, 3};
-            // All TMEM loads of a 64-column block are issued back to back and waited for once; the
-            // reduction then runs on registers, one guard per 16 columns, c[] fetched 16 at a time.
+            float fcount = 0.f, fmcount = 0.f;
+            float* srow = A.scores + loc * L.K;      // drop-in path only: the full score map
+            // All TMEM loads of a 64-column block are issued back to back and waited for once.
             for (int nb = 0; nb < ((A.dbg & 1) ? 0 : L.npad); nb += 64) {
                 uint32_t v[64];
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
                     if (nb + 16 * j < L.npad) tmem_ld16(taddr + nb + 16 * j, *reinterpret_cast<uint32_t(*)[16]>(&v[16 * j]));
                 tmem_ld_wait();
+                if ((A.dbg & 4) && (warp & 3) == 0) CP_TRACE(nb ? 3 : 1);
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    if (nb + 16 * j < L.npad) {
-                        const int n = nb + 16 * j;
-                        const float4* c4p = reinterpret_cast<const float4*>(cs + n);
-                        const float4 ca = c4p[0], cb = c4p[1], cc = c4p[2], cd = c4p[3];
-                        const float cv[16] = {ca.x, ca.y, ca.z, ca.w, cb.x, cb.y, cb.z, cb.w,
-                                              cc.x, cc.y, cc.z, cc.w, cd.x, cd.y, cd.z, cd.w};
+                    const int n = nb + 16 * j;
+                    if (n + 16 <= L.K) {                      // whole 16-column group of parts
 #pragma unroll
                         for (int i = 0; i < 16; ++i) {
-                            const float sc = __uint_as_float(v[16 * j + i]) + cv[i];
+                            const float sc = __uint_as_float(v[16 * j + i]);
                             if (sc > bv[i & 3]) { bv[i & 3] = sc; bk[i & 3] = n + i; }
                         }
+                    } else if (n < L.K) {                     // the group that holds the last parts
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            const float sc = __uint_as_float(v[16 * j + i]);
+                            if (n + i < L.K && sc > bv[i & 3]) { bv[i & 3] = sc; bk[i & 3] = n + i; }
+                        }
                     }
-                }
-            }
-            if (A.scores && !(A.dbg & 1)) {   // drop-in path only: the full score map
-                // tcgen05.ld is warp-collective (.sync.aligned): the branch above is warp-uniform and only
-                // the global stores are predicated on the lane's own validity
-                float* srow = A.scores + loc * L.K;
-                for (int n0 = 0; n0 < L.K; n0 += 16) {
-                    uint32_t v[16];
-                    tmem_ld16(taddr + n0, v);
-                    tmem_ld_wait();
+                    if (A.scores && valid && n < L.K) {
 #pragma unroll
-                    for (int i = 0; i < 16; ++i)
-                        if (valid && n0 + i < L.K) srow[n0 + i] = __uint_as_float(v[i]) + cs[n0 + i];
+                        for (int i = 0; i < 16; ++i)
+                            if (n + i < L.K) srow[n + i] = __uint_as_float(v[16 * j + i]);
+                    }
+                    // exact integer edge counts from the all-ones / mask weight columns: the last two columns of the
+                    // padded range, i.e. static register indices (a data-dependent index would push v[] to local memory)
+                    if (n + 16 == L.npad) { fcount = __uint_as_float(v[16 * j + 14]); fmcount = __uint_as_float(v[16 * j + 15]); }
                 }
-            }
-            // exact integer edge counts from the all-ones / mask weight columns
-            float fcount = 0.f, fmcount = 0.f;
-            {
-                uint32_t v[16];
-                tmem_ld16(taddr + ccol, v);
-                tmem_ld_wait();
-                const int o = L.K - ccol;
-#pragma unroll
-                for (int i = 0; i < 9; ++i) {
-                    if (i == o) fcount = __uint_as_float(v[i]);
-                    if (i == o + 1) fmcount = __uint_as_float(v[i]);
-                }
+                if ((A.dbg & 4) && (warp & 3) == 0) CP_TRACE(nb ? 4 : 2);
             }
             tc_fence_before();
             mbar_arrive(&tempty_bar[acc]);

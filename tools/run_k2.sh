@@ -1,8 +1,4 @@
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_pipeline.py -q -m gpu -x --timeout=300 > gpurun_out/test_pipeline.log 2>&1; echo "pipeline exit $?"; tail -4 gpurun_out/test_pipeline.log
-timeout 600 python bench.py > gpurun_out/bench.log 2> gpurun_out/bench.err; echo "bench exit $?"; tail -3 gpurun_out/bench.err
-python - <<'PY'
-import json
-d=json.loads(open('gpurun_out/bench.log').read().strip().split("\n")[-1])
-print(d['value'], d['ms_per_step'], d['e2e'], {k:(v['ms'] if isinstance(v,dict) else v) for k,v in d['stages'].items()})
-PY
+timeout 600 python -m pytest tests/test_gpu_code_parts.py -q -m gpu -x --timeout=300 > gpurun_out/test_code_parts.log 2>&1; echo "code_parts exit $?"; tail -4 gpurun_out/test_code_parts.log
+timeout 300 python tools/time_kernels.py code_parts 2>&1 | tail -3
+for f in 0 4; do timeout 120 python tools/trace_code_parts.py $f 2>&1 | tail -9; done

@@ -21,6 +21,8 @@ lib.tsr_debug_set_code_trace(None)
 t = buf.cpu().numpy().reshape(96, 8)
 t0 = t[t > 0].min()
 names = ["prod:empty_ok", "prod:arrived", "mma:full_ok", "mma:tempty_ok", "mma:issued", "epi:tfull_ok", "epi:tmem_free", "epi:done"]
+if flags & 4:   # epilogue detail: slots 1-4 = first wait::ld done, first block reduced, second wait done, second block reduced
+    names = ["-", "epi:ld1_done", "epi:red1_done", "epi:ld2_done", "epi:red2_done", "epi:tfull_ok", "epi:tmem_free", "epi:done"]
 print("tile " + " ".join("%14s" % n for n in names))
 for i in range(30, 36):
     print("%4d " % i + " ".join("%14d" % (x - t0 if x else -1) for x in t[i]))

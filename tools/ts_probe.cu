@@ -22,16 +22,16 @@ __device__ __forceinline__ void umma_f16_ts_elect(uint32_t d_tmem, uint32_t a_tm
         : "memory");
 }
 
-struct Case { const char* name; int N; int ts; int readers; int cols; int width; };
+struct Case { const char* name; int N; int ts; int readers; int cols; int width; int batches; int issuers; };
 
 __global__ void __launch_bounds__(256, 1) probe_kernel(Case c, int reps, long long* out) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    __shared__ uint64_t bar;
+    __shared__ uint64_t bar2[2];
     __shared__ uint32_t tmem_ptr;
     __shared__ volatile int stop;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int i = threadIdx.x; i < 160 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3C003C00u;
-    if (threadIdx.x == 0) { mbar_init(&bar, 1); mbar_fence_init(); stop = 0; }
+    if (threadIdx.x == 0) { mbar_init(&bar2[0], 1); mbar_init(&bar2[1], 1); mbar_fence_init(); stop = 0; }
     if (warp == 0) tmem_alloc<512>(&tmem_ptr);
     fence_proxy_async_smem();
     tc_fence_before();
@@ -39,14 +39,16 @@ __global__ void __launch_bounds__(256, 1) probe_kernel(Case c, int reps, long lo
     tc_fence_after();
     const uint32_t tmem_base = tmem_ptr;
     // TMEM columns: [0,128) acc0, [128,256) acc1, [256,368) A (104 columns used)
-    if (warp == 0) {
+    if (warp < c.issuers) {
+        uint64_t& bar = bar2[warp];
         const uint32_t abase = smem_u32(smem), bbase = smem_u32(smem + 64 * 1024);
         const uint32_t idesc = umma_idesc_f32acc(TSR_FMT_FP16, 128, c.N);
         uint32_t phase = 0;
         long long t0 = 0;
         for (int r = 0; r < reps + 1; ++r) {
             if (r == 1) t0 = clock64();
-            const uint32_t dt = tmem_base + (r & 1) * 128;
+            const uint32_t dt = tmem_base + (c.issuers > 1 ? warp : (r & 1)) * 128;
+            for (int bb = 0; bb < c.batches; ++bb)
 #pragma unroll
             for (int s = 0; s < 26; ++s) {
                 const uint64_t bd = umma_desc_kmajor_noswz(bbase + (s % 13) * 2 * c.N * 16, c.N * 16, 128);
@@ -58,7 +60,7 @@ __global__ void __launch_bounds__(256, 1) probe_kernel(Case c, int reps, long lo
             phase ^= 1;
         }
         const long long t1 = clock64();
-        if (lane == 0) { out[blockIdx.x * 2] = t1 - t0; stop = 1; }
+        if (lane == 0 && warp == 0) { out[blockIdx.x * 2] = t1 - t0; stop = 1; }
     } else if (warp >= 4 && c.readers) {
         const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
         long long n = 0;
@@ -113,17 +115,16 @@ __global__ void __launch_bounds__(256, 1) probe_kernel(Case c, int reps, long lo
 
 int main() {
     Case cases[] = {
-        {"SS N=112                          ", 112, 0, 0, 128, 32},
-        {"SS N=112 + readers x16 (4 in flight)", 112, 0, 1, 128, 16},
-        {"SS N=112 + readers x32 (2 in flight)", 112, 0, 1, 128, 32},
-        {"SS N=112 + readers x64            ", 112, 0, 1, 128, 64},
-        {"SS N=112 + readers x128           ", 112, 0, 1, 128, 128},
-        {"TS N=112 + readers x128           ", 112, 1, 1, 128, 128},
+        {"SS N=112 2 issuers                 ", 112, 0, 0, 128, 32, 16, 2},
+        {"TS N=112 2 issuers                 ", 112, 1, 0, 128, 32, 16, 2},
+        {"SS N=112 2 issuers + readers x16   ", 112, 0, 1, 128, 16, 16, 2},
+        {"TS N=112 2 issuers + readers x16   ", 112, 1, 1, 128, 16, 16, 2},
+        {"TS N=112 1 issuer                  ", 112, 1, 0, 128, 32, 16, 1},
     };
     long long* d_out;
     cudaMalloc(&d_out, 1024 * sizeof(long long));
     cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-    const int reps = 300;
+    const int reps = 60;
     for (int grid : {1, 148}) {
         printf("grid = %d\n", grid);
         for (auto& c : cases) {
@@ -135,7 +136,7 @@ int main() {
             cudaMemcpy(h, d_out, grid * 2 * sizeof(long long), cudaMemcpyDeviceToHost);
             double mx = 0, rd = 0;
             for (int i = 0; i < grid; ++i) { mx = h[2 * i] > mx ? h[2 * i] : mx; rd += h[2 * i + 1]; }
-            printf("  %s : %6.1f cycles/MMA (floor %4.1f)   readers %.1f B/clk per CTA\n", c.name, mx / (reps * 26.0),
+            printf("  %s : %6.1f cycles/MMA (floor %4.1f)   readers %.1f B/clk per CTA\n", c.name, mx / (reps * 26.0 * c.batches * c.issuers),
                    128.0 * c.N / 256.0, rd / grid / 1000.0);
         }
     }
