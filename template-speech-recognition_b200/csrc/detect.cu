@@ -29,7 +29,7 @@ namespace tsr {
 #define DT_MSUB_MAX 3
 #define DT_MAX_STAGES 4
 #define DT_MAX_BSTAGES 8   // I8: ring of 64-feature filter tiles
-#define DT_THREADS 448     // 14 warps: <= 144 registers per thread
+#define DT_THREADS 480     // 15 warps: <= 136 registers per thread
 #define DT_PRODUCERS 256   // two groups of 128 expander threads
 #define DT_TAU_CHUNK 40    // diagonal sums are staged through smem in chunks of <= 40 filter frames
 #define DT_NT_MAX 240      // widest N tile: tcgen05.mma issue costs ~100 cycles, so each MMA should carry >= that much work
@@ -326,9 +326,10 @@ __global__ void __launch_bounds__(DT_THREADS, 1) detect_tc_kernel(DetectArgs A) 
     const long long nunits = (long long)f.ntiles * A.units_per_ntile;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < DT_MAX_BSTAGES; ++s) { mbar_init(&full_bar[s], I8 ? 1 : DT_PRODUCERS / 2 + 1); mbar_init(&empty_bar[s], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&afull_bar[s], DT_PRODUCERS); mbar_init(&aempty_bar[s], 1); }
-        mbar_init(tfull_bar, 1);
+        // I8: two MMA issuer warps (13, 14) share every pipeline slot, so the consumer-side barriers take two commits
+        for (int s = 0; s < DT_MAX_BSTAGES; ++s) { mbar_init(&full_bar[s], I8 ? 1 : DT_PRODUCERS / 2 + 1); mbar_init(&empty_bar[s], I8 ? 2 : 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&afull_bar[s], DT_PRODUCERS); mbar_init(&aempty_bar[s], I8 ? 2 : 1); }
+        mbar_init(tfull_bar, I8 ? 2 : 1);
         for (int s = 0; s < DT_MSUB_MAX; ++s) mbar_init(&tempty_bar[s], 128);
         mbar_fence_init();
     }
@@ -490,9 +491,13 @@ __global__ void __launch_bounds__(DT_THREADS, 1) detect_tc_kernel(DetectArgs A) 
                     }
             }
         }
-    } else if (warp == 13) {
-        // ================================ MMA issuer ================================
-        // warp-uniform loop, one elected lane issues (see umma_f16_elect)
+    } else if (warp == 13 || (I8 && warp == 14)) {
+        // ================================ MMA issuers ================================
+        // warp-uniform loop, one elected lane issues (see umma_f16_elect).  One thread gets a tcgen05.mma out only
+        // every ~75-90 cycles plus the barrier work between filter tiles (tools/ts_probe.cu), which left the I8
+        // kernel at 141 cycles per 120-cycle MMA: two warps on different SMSPs each issue the MMAs of their own row
+        // sub-tiles (sub = warp - 13, +2, ...) and both commit to every barrier.
+        const int iss = warp - 13;
         const uint32_t idesc = I8 ? ((2u << 4) | (0u << 7) | (1u << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24))
                                   : umma_idesc_f32acc(fmt, 128, NT);
         const uint32_t desc_hi = (uint32_t)(128 >> 4) | (1u << 14);                 // SBO = 128 B, version 1
@@ -516,10 +521,10 @@ __global__ void __launch_bounds__(DT_THREADS, 1) detect_tc_kernel(DetectArgs A) 
                         for (int phi = 0; phi < f.fold; ++phi)
                             for (int half = 0; half < 2; ++half, ++it) {
                                 mbar_wait(&full_bar[stage], ph);
-                                DT_TRACE(it, 4);
+                                if (iss == 0) DT_TRACE(it, 4);
                                 tc_fence_after();
                                 const uint32_t bbase = smem_u32(smem + S.b + stage * S.stage_bytes) >> 4;
-                                for (int sub = 0; sub < msub; ++sub) {
+                                for (int sub = iss; sub < msub; sub += 2) {
                                     if ((cf | phi | half) == 0) {
                                         mbar_wait(&tempty_bar[sub], (stepno & 1) ^ 1);
                                         tc_fence_after();
@@ -534,7 +539,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) detect_tc_kernel(DetectArgs A) 
                                     }
                                 }
                                 umma_commit_elect(&empty_bar[stage]);
-                                DT_TRACE(it, 5);
+                                if (iss == 0) DT_TRACE(it, 5);
                                 if (++stage == nstage) { stage = 0; ph ^= 1; }
                             }
                         umma_commit_elect(&aempty_bar[buf]);
@@ -580,7 +585,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) detect_tc_kernel(DetectArgs A) 
                 }
                 umma_commit_elect(tfull_bar);
             }
-    } else {
+    } else if (warp >= 9 && warp <= 12) {
         // ================================= epilogue =================================
         // accumulators are fp32 (F16 kind) or int32 (I8 kind); staging and diagonal sums use the same type
         typedef typename std::conditional<I8, int, float>::type acc_t;
