@@ -222,7 +222,8 @@ __global__ void __launch_bounds__(256) code_parts_simt_kernel(CodeArgs A) {
 
 // ------------------------------------------------------------------------- tensor path
 #define CP_NSTAGE 4
-#define CP_THREADS 448   // warps 0-3 / 4-7 epilogue (even / odd tiles), 8-11 producers, 12 / 13 MMA issuers (even / odd tiles; highest ids win arbitration)
+#define CP_NISSUE 4
+#define CP_THREADS (384 + 32 * CP_NISSUE)   // warps 0-3 / 4-7 epilogue (even / odd tiles), 8-11 producers, 12.. MMA issuers (tile % CP_NISSUE; highest ids win arbitration)
 #define CP_MAX_STEPS 32
 #define CP_NACC 4         // barrier slots; TMEM accumulators in use: 4 x 128 columns when N_pad <= 128, else 2 x 256
 
@@ -376,7 +377,7 @@ __global__ void __launch_bounds__(CP_THREADS, 1) code_parts_tc_kernel(CodeArgs A
         }
         const int iss = warp - 12;
         uint32_t it = iss;
-        for (long long tile = blockIdx.x + (long long)iss * gridDim.x; tile < ntiles; tile += 2ll * gridDim.x, it += 2) {
+        for (long long tile = blockIdx.x + (long long)iss * gridDim.x; tile < ntiles; tile += (long long)CP_NISSUE * gridDim.x, it += CP_NISSUE) {
             const int stage = it % CP_NSTAGE;
             const uint32_t ph = (it / CP_NSTAGE) & 1;
             const int acc = it % nacc;
