@@ -230,6 +230,7 @@ struct DetectArgs {
     int units_per_ntile;
     int steps_per_unit;
     int ntile_group;        // N tiles whose filter tiles share the L2 at one time (unit order: group, row unit, tile in group)
+    int nissue;             // I8: MMA issuer warps (2 when the whole filter bank is L2 resident, else 1 -- measured, see tsr_detect)
     FilterLayout f;
     long long* trace;   // optional debug timeline of CTA 0: [stage iteration][8] clock64 stamps
     int dbg;            // debug experiments (timing only, wrong results): 1 = every phase reads the strip at row 0
@@ -306,8 +307,10 @@ __device__ __forceinline__ void detect_unit_coords(long long u, int ntiles, int 
     nt = (int)ng * G + (int)(rem - ur * gt);
 }
 
-template <bool I8>
-__global__ void __launch_bounds__(DT_THREADS, 1) detect_tc_kernel(DetectArgs A) {
+// NIS = MMA issuer warps (I8 only): a compile-time constant, because the issue loop is the critical path of the kernel and
+// a run-time stride / barrier count in it cost 6-20 % (measured)
+template <bool I8, int NIS>
+__global__ void __launch_bounds__(448 + 32 * (NIS - 1), 1) detect_tc_kernel(DetectArgs A) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const FilterLayout& f = A.f;
     const DetectSmem S = detect_smem_layout(f);
@@ -327,9 +330,10 @@ __global__ void __launch_bounds__(DT_THREADS, 1) detect_tc_kernel(DetectArgs A) 
 
     if (threadIdx.x == 0) {
         // I8: two MMA issuer warps (13, 14) share every pipeline slot, so the consumer-side barriers take two commits
-        for (int s = 0; s < DT_MAX_BSTAGES; ++s) { mbar_init(&full_bar[s], I8 ? 1 : DT_PRODUCERS / 2 + 1); mbar_init(&empty_bar[s], I8 ? 2 : 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&afull_bar[s], DT_PRODUCERS); mbar_init(&aempty_bar[s], I8 ? 2 : 1); }
-        mbar_init(tfull_bar, I8 ? 2 : 1);
+        constexpr uint32_t nis = NIS;
+        for (int s = 0; s < DT_MAX_BSTAGES; ++s) { mbar_init(&full_bar[s], I8 ? 1 : DT_PRODUCERS / 2 + 1); mbar_init(&empty_bar[s], nis); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&afull_bar[s], DT_PRODUCERS); mbar_init(&aempty_bar[s], nis); }
+        mbar_init(tfull_bar, nis);
         for (int s = 0; s < DT_MSUB_MAX; ++s) mbar_init(&tempty_bar[s], 128);
         mbar_fence_init();
     }
@@ -491,7 +495,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) detect_tc_kernel(DetectArgs A) 
                     }
             }
         }
-    } else if (warp == 13 || (I8 && warp == 14)) {
+    } else if (warp == 13 || (NIS == 2 && warp == 14)) {
         // ================================ MMA issuers ================================
         // warp-uniform loop, one elected lane issues (see umma_f16_elect).  One thread gets a tcgen05.mma out only
         // every ~75-90 cycles plus the barrier work between filter tiles (tools/ts_probe.cu), which left the I8
@@ -524,7 +528,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) detect_tc_kernel(DetectArgs A) 
                                 if (iss == 0) DT_TRACE(it, 4);
                                 tc_fence_after();
                                 const uint32_t bbase = smem_u32(smem + S.b + stage * S.stage_bytes) >> 4;
-                                for (int sub = iss; sub < msub; sub += 2) {
+                                for (int sub = iss; sub < msub; sub += NIS) {
                                     if ((cf | phi | half) == 0) {
                                         mbar_wait(&tempty_bar[sub], (stepno & 1) ^ 1);
                                         tc_fence_after();
@@ -1047,17 +1051,26 @@ int tsr_detect(const uint32_t* featbits, int B, int T, int D, int rowwords, cons
         if (G < 1) G = 1;
         if (G > A.f.ntiles) G = A.f.ntiles;
         A.ntile_group = (int)G;
+        // Two issuer warps lift config 3 (32 templates, bank L2 resident) from 141 to 128 cycles per MMA, 2.62 -> 2.49 ms,
+        // but slow the 1000-template stream (bank 438 MB, streamed through L2 group by group) from 264 to 290 ms.
+        A.nissue = (size_t)A.f.ntiles * set_bytes <= ((size_t)64 << 20) ? 2 : 1;
     }
     A.rows_per_unit = (int)((R + best_U - 1) / best_U);
     A.steps_per_unit = (A.rows_per_unit + A.f.Lc + step_rows - 1) / step_rows;
     const long long nunits = (long long)A.f.ntiles * best_U;
     int blocks = (int)(nunits < nsm ? nunits : nsm);
     if (A.f.kind) {
-        TSR_CUDA(cudaFuncSetAttribute(detect_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S.total));
-        detect_tc_kernel<true><<<blocks, DT_THREADS, S.total, (cudaStream_t)stream>>>(A);
+        // the second issuer is warp 14: launched only when used (an idle 15th warp alone cost the stream config 20 %)
+        if (A.nissue == 2) {
+            TSR_CUDA(cudaFuncSetAttribute(detect_tc_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S.total));
+            detect_tc_kernel<true, 2><<<blocks, DT_THREADS, S.total, (cudaStream_t)stream>>>(A);
+        } else {
+            TSR_CUDA(cudaFuncSetAttribute(detect_tc_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S.total));
+            detect_tc_kernel<true, 1><<<blocks, DT_THREADS - 32, S.total, (cudaStream_t)stream>>>(A);
+        }
     } else {
-        TSR_CUDA(cudaFuncSetAttribute(detect_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S.total));
-        detect_tc_kernel<false><<<blocks, DT_THREADS, S.total, (cudaStream_t)stream>>>(A);
+        TSR_CUDA(cudaFuncSetAttribute(detect_tc_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S.total));
+        detect_tc_kernel<false, 1><<<blocks, DT_THREADS - 32, S.total, (cudaStream_t)stream>>>(A);
     }
     return check_launch("tsr_detect");
 }
