@@ -8,17 +8,21 @@
 //                        rows in shared memory: one 16-byte row per (t,f) position, positions
 //                        flattened p = t*F + f, so location p's patch row `a` is the 16*pw bytes
 //                        starting at position p + a*F.
-//   MMA issuer (1 thread) tcgen05.mma M=128 x N=N_pad x K=16, A straight out of that buffer with
+//   MMA issuers (4 warps, one per SMSP; tile i -> issuer i % 4 -> accumulator i % 4; a single thread gets a
+//                        tcgen05.mma out only every ~75-90 cycles, a 56-cycle MMA needs more than one issuer)
+//                        tcgen05.mma M=128 x N=N_pad x K=16, A straight out of that buffer with
 //                        a K-major no-swizzle descriptor whose core-matrix rows are the 16-byte
 //                        positions (row stride 16 B = one frequency bin, SBO = 128 B, LBO = the
 //                        distance to the next (a,b) group): the im2col is never materialised.
-//                        hi and lo bf16 weight planes accumulate into the same TMEM columns.
-//   epilogue (4 warps)   tcgen05.ld the 128 x N_pad fp32 tile, add c[k], running arg-max (lowest k
+//                        hi and lo 16-bit weight planes accumulate into the same TMEM columns, after
+//                        one extra K-step (constant-ones A) that sets the accumulator to c[k].
+//   epilogue (2 x 4 warps, even / odd tiles) tcgen05.ld the 128 x N_pad fp32 tile, running arg-max (lowest k
 //                        wins ties), read the exact edge counts from two extra weight columns
-//                        (all-ones / mask), apply the gate, store uint8 codes.
+//                        (all-ones / mask, columns N_pad-2 / N_pad-1), apply the gate, store uint8 codes;
+//                        no shared-memory reads (they stall behind the MMA operand traffic).
 // Four TMEM accumulator buffers (two per epilogue set) and a 4-deep A ring overlap the three roles: an
 // accumulator is held by the epilogue for about as long as the MMAs need to fill it, so with only two the MMA
-// warp idled half the time waiting for a free one.
+// warps idled half the time waiting for a free one.
 #include "common.cuh"
 
 namespace tsr {
