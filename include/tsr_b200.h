@@ -177,6 +177,16 @@ int tsr_detect_peaks(const float* track, const int* lengths_or_null, int B, int 
 int tsr_peaks_gather(const float* track, const int32_t* slot, int B, int T, int32_t* peak_bt, float* peak_val_or_null,
                      void* stream);
 
+/* N2, second half: clustering of the picked peaks, one utterance per thread.  Replaces cluster_times.cluster_times
+ * (cluster_times.pyx:133-219) and roc_functions.get_cluster_starts_ends (roc_functions.py:187-212).
+ * peak_bt int32 [n][2] = (b, t) sorted by b then t (tsr_peaks_gather's output), t < 65536.
+ * offsets int32 [B+1]: utterance b's peaks are rows offsets[b] .. offsets[b+1]-1;
+ * partition uint8 [n+B]: utterance b's n_b+1 codes start at offsets[b]+b (2 = cluster start, 0 = continuation,
+ *   closing 2), exactly the reference's cluster_partition;
+ * clusters int32 [n][2]: (first peak, last peak + 1) of utterance b's clusters from row offsets[b]; ncluster int32 [B]. */
+int tsr_cluster_peaks(const int32_t* peak_bt, int n, int B, float C0, float C1, int32_t* offsets, uint8_t* partition,
+                      int32_t* clusters, int32_t* ncluster, void* stream);
+
 /* ---- N4 / N3: edge front end (feeds K1a) ------------------------------------------------------
  * tsr_edge_map replaces edge_signal_proc._edge_map_no_threshold (edge_signal_proc.py:1697-1836):
  *   S double [B][F][T] (frequency rows x time) -> mags double [B][8][F][T], the reference's (8H, time)

@@ -18,7 +18,7 @@ import subprocess
 import sys
 import sysconfig
 
-MODULES = ("code_parts", "spread_waliji_patches", "compute_likelihood_linear_filter")
+MODULES = ("code_parts", "spread_waliji_patches", "compute_likelihood_linear_filter", "cluster_times")
 HERE = os.path.dirname(os.path.abspath(__file__))
 OUT = os.path.join(HERE, "_ref")
 

@@ -177,6 +177,40 @@ def get_max_above_threshold(detection_vals, detection_length, threshold, C0):
     return np.arange(1, l - 1, dtype=np.uint16)[(v[1:l - 1] >= v[:l - 2]) * (v[1:l - 1] >= v[2:l]) * (v[1:l - 1] >= threshold)]
 
 
+def cluster_times(times, C0, C1):
+    """cluster_times.pyx:133-219: times uint16 (n,), strictly increasing -> partition uint8 (n+1,)"""
+    times = _c(times, np.uint16)
+    part = np.zeros(times.shape[0] + 1, np.uint8)
+    lib().oracle_cluster_times(_p(times, ctypes.c_uint16), times.shape[0], ctypes.c_float(C0), ctypes.c_float(C1), _p(part, _u8))
+    return part
+
+
+def get_cluster_starts_ends(potential_detect_times, cluster_partition):
+    """roc_functions.py:187-212: (start, end) = (first peak, last peak + 1) of every cluster"""
+    out, t, d = [], 0, len(potential_detect_times)
+    while t < d:
+        start = potential_detect_times[t]
+        t += 1
+        while cluster_partition[t] != 2:
+            t += 1
+        out.append((start, potential_detect_times[t - 1] + 1))
+    return tuple(out)
+
+
+def load_ref_cluster_times():
+    """compiled reference cluster_times (oracle/_ref) or None"""
+    ref = os.path.join(HERE, "_ref")
+    if not os.path.isdir(ref):
+        return None
+    if ref not in sys.path:
+        sys.path.insert(0, ref)
+    try:
+        m = importlib.import_module("cluster_times")
+    except ImportError:
+        return None
+    return m if os.path.dirname(os.path.abspath(m.__file__)) == ref else None
+
+
 # ------------------------------------------------------------------------ detection
 def detect(F, LF):
     """compute_likelihood_linear_filter.pyx:135-176"""

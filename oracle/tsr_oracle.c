@@ -364,3 +364,48 @@ void oracle_spread_edges_box(const double *Tm, int H, int W, int s, double *out)
             out[(size_t)i * W + j] = m;
         }
 }
+
+/* ------------------------------------------------------------------ detection-time clustering
+ * cluster_times.pyx:133-219 (cluster_times): partition[i] marks times[i] as the start of a cluster
+ * (2 = final, 1 = may still need splitting while the loop runs), partition[n] = 2 closes the list.
+ * Peaks at least C0 frames apart start a new cluster; a cluster whose extent exceeds C1 is cut at its
+ * widest gap.  The reference keeps times and distances in uint16 and C0 / C1 in float32. */
+void oracle_cluster_times(const uint16_t *times, int n, float C0, float C1, uint8_t *part)
+{
+    for (int i = 0; i <= n; ++i) part[i] = 0;
+    part[0] = 1;
+    part[n] = 2;
+    for (int i = 1; i < n; ++i)
+        if ((float)(times[i] - times[i - 1]) >= C0) part[i] = 1;
+    int start = 0;
+    int widest = 0;                                  /* the reference leaves this uninitialised; unused before it is set */
+    while (start < n) {
+        if (part[start + 1] > 0) {                   /* single-element cluster */
+            part[start] = 2;
+            ++start;
+            while (part[start] != 1 && start < n) ++start;
+            continue;
+        }
+        uint16_t max_gap = 0, extent = 0;
+        int k = 1;
+        while (part[start + k] == 0) {
+            uint16_t gap = (uint16_t)(times[start + k] - times[start + k - 1]);
+            if (gap > max_gap) { widest = start + k; max_gap = gap; }
+            extent = (uint16_t)(extent + gap);
+            ++k;
+        }
+        if ((float)extent > C1) {
+            part[widest] = ((float)(times[start + k - 1] - times[widest]) <= C1) ? 2 : 1;
+            if ((float)(times[widest - 1] - times[start]) <= C1) {
+                part[start] = 2;
+                if (part[widest] == 1) start = widest;
+            } else {
+                part[start] = 1;
+            }
+        } else {
+            part[start] = 2;
+            start += k;
+            while (part[start] != 1 && start < n) ++start;
+        }
+    }
+}

@@ -40,6 +40,7 @@ SIGNATURES = {
     "tsr_detect_float": (_i, [_vp, _i, _i, _i, _vp, _i, _i, _vp, _vp, _vp]),
     "tsr_detect_peaks": (_i, [_vp, _vp, _i, _i, _i, _f, _vp, _vp]),
     "tsr_peaks_gather": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp]),
+    "tsr_cluster_peaks": (_i, [_vp, _i, _i, _f, _f, _vp, _vp, _vp, _vp, _vp]),
     "tsr_edge_map": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "tsr_threshold_edges": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, ctypes.c_double, _vp, _vp]),
     "tsr_edges_from_spectrogram": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, ctypes.c_double, _vp, _vp]),

@@ -230,6 +230,79 @@ __global__ void __launch_bounds__(256) peaks_gather_kernel(const float* __restri
     }
 }
 
+// ------------------------------------------------------------------------------ N2: clustering of the peaks
+// One thread per utterance walks its (few) peaks: cluster_times.pyx:133-219 followed by
+// roc_functions.get_cluster_starts_ends (:187-212).  peak_bt rows are (b, t) sorted by b then t.  Peaks at least C0
+// frames apart start a new cluster; a cluster whose extent exceeds C1 is cut at its widest gap (codes: 2 = cluster
+// start, final; 1 = start that the loop may still split; 0 = continuation).  Distances wrap at 16 bits like the
+// reference's uint16 arithmetic (frames are < 65536 on this path).
+__global__ void cluster_peaks_kernel(const int32_t* __restrict__ peak_bt, int n, int B, float C0, float C1,
+                                     int32_t* __restrict__ offsets, uint8_t* __restrict__ partition,
+                                     int32_t* __restrict__ clusters, int32_t* __restrict__ ncluster) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b > B) return;
+    auto lower = [&](int key) {                       // first peak whose utterance index is >= key
+        int lo = 0, hi = n;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (peak_bt[2 * mid] < key) lo = mid + 1; else hi = mid;
+        }
+        return lo;
+    };
+    const int first = lower(b);
+    offsets[b] = first;
+    if (b == B) return;
+    const int m = lower(b + 1) - first;               // peaks of this utterance
+    const int32_t* t = peak_bt + 2 * first + 1;       // t[2*i] = frame of peak i
+    uint8_t* part = partition + first + b;            // m + 1 codes
+    for (int i = 0; i <= m; ++i) part[i] = 0;
+    part[0] = 1;
+    part[m] = 2;
+    for (int i = 1; i < m; ++i)
+        if ((float)(t[2 * i] - t[2 * i - 2]) >= C0) part[i] = 1;
+    int start = 0, widest = 0;
+    while (start < m) {
+        if (part[start + 1] > 0) {
+            part[start] = 2;
+            ++start;
+            while (part[start] != 1 && start < m) ++start;
+            continue;
+        }
+        unsigned int max_gap = 0, extent = 0;
+        int k = 1;
+        while (part[start + k] == 0) {
+            const unsigned int gap = (unsigned int)(t[2 * (start + k)] - t[2 * (start + k - 1)]) & 0xFFFFu;
+            if (gap > max_gap) { widest = start + k; max_gap = gap; }
+            extent = (extent + gap) & 0xFFFFu;
+            ++k;
+        }
+        if ((float)extent > C1) {
+            part[widest] = ((float)(t[2 * (start + k - 1)] - t[2 * widest]) <= C1) ? 2 : 1;
+            if ((float)(t[2 * (widest - 1)] - t[2 * start]) <= C1) {
+                part[start] = 2;
+                if (part[widest] == 1) start = widest;
+            } else {
+                part[start] = 1;
+            }
+        } else {
+            part[start] = 2;
+            start += k;
+            while (part[start] != 1 && start < m) ++start;
+        }
+    }
+    // (start, end) = (first peak, last peak + 1) of every cluster
+    int nc = 0, i = 0;
+    while (i < m) {
+        const int s0 = t[2 * i];
+        ++i;
+        while (part[i] != 2) ++i;
+        clusters[2 * (first + nc)] = s0;
+        clusters[2 * (first + nc) + 1] = t[2 * (i - 1)] + 1;
+        ++nc;
+    }
+    ncluster[b] = nc;
+}
+
 }  // namespace tsr
 
 using namespace tsr;
@@ -340,6 +413,19 @@ int tsr_peaks_gather(const float* track, const int32_t* slot, int B, int T, int3
     if (blocks > 148LL * 32) blocks = 148LL * 32;
     peaks_gather_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(track, slot, n, T, peak_bt, peak_val_or_null);
     return check_launch("tsr_peaks_gather");
+}
+
+int tsr_cluster_peaks(const int32_t* peak_bt, int n, int B, float C0, float C1, int32_t* offsets, uint8_t* partition,
+                      int32_t* clusters, int32_t* ncluster, void* stream) {
+    TSR_REQUIRE(B >= 0 && n >= 0, "tsr_cluster_peaks: negative size");
+    TSR_REQUIRE(offsets && (B == 0 || ncluster), "tsr_cluster_peaks: null pointer");
+    TSR_REQUIRE(n == 0 || (peak_bt && clusters), "tsr_cluster_peaks: null pointer");
+    TSR_REQUIRE(partition || (n == 0 && B == 0), "tsr_cluster_peaks: null pointer");
+    int rc = require_sm100("tsr_cluster_peaks");
+    if (rc) return rc;
+    cluster_peaks_kernel<<<(B + 1 + 127) / 128, 128, 0, (cudaStream_t)stream>>>(peak_bt, n, B, C0, C1, offsets, partition,
+                                                                               clusters, ncluster);
+    return check_launch("tsr_cluster_peaks");
 }
 
 }  // extern "C"

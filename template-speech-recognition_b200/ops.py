@@ -384,6 +384,21 @@ def detect_peaks(track, threshold, C0=1, lengths=None):
     return bt, val
 
 
+def cluster_peaks(peak_bt, B, C0, C1):
+    """Cluster the peaks of every utterance (cluster_times.pyx:133-219 + roc_functions.get_cluster_starts_ends).
+    peak_bt int32 (n,2) from detect_peaks.  Returns (offsets int32 (B+1,), partition uint8 (n+B,), clusters int32
+    (n,2) rows (start, end) -- utterance b's from row offsets[b] --, ncluster int32 (B,))."""
+    peak_bt = _dev(peak_bt, torch.int32, "peak_bt")
+    n, dev = peak_bt.shape[0], peak_bt.device
+    offsets = torch.empty(B + 1, dtype=torch.int32, device=dev)
+    partition = torch.empty(max(n + B, 1), dtype=torch.uint8, device=dev)
+    clusters = torch.empty((n, 2), dtype=torch.int32, device=dev)
+    ncluster = torch.empty(B, dtype=torch.int32, device=dev)
+    _lib.call("tsr_cluster_peaks", _ptr(peak_bt), n, int(B), float(C0), float(C1), _ptr(offsets), _ptr(partition),
+              _ptr(clusters), _ptr(ncluster), _stream())
+    return offsets, partition[:n + B], clusters, ncluster
+
+
 # ------------------------------------------------------------------------------- K4
 class EmState:
     """Device state of one rank's share of a Bernoulli-mixture EM problem."""

@@ -1,5 +1,5 @@
-"""Drop-in for the peak picking of the reference's ``roc_functions`` module
-(template_speech_rec/roc_functions.py): the step right after detection.  NumPy in, NumPy out;
+"""Drop-in for the peak picking and peak clustering of the reference's ``roc_functions`` module
+(template_speech_rec/roc_functions.py): the steps right after detection.  NumPy in, NumPy out;
 the work runs on the GPU (tsr_detect_peaks + ordered compaction), there is no CPU path."""
 import numpy as np
 
@@ -23,3 +23,27 @@ def get_max_above_threshold(detection_vals, detection_length, threshold, C0):
     lengths = to_dev(np.array([int(detection_length)], np.int32))
     bt, _ = ops.detect_peaks(to_dev(v[None]), float(threshold), int(C0), lengths)
     return bt[:, 1].cpu().numpy().astype(np.uint16)
+
+
+def get_cluster_starts_ends(potential_detect_times, cluster_partition):
+    """roc_functions.py:187-212 (host bookkeeping over a handful of peaks): (first peak, last peak + 1) per cluster."""
+    out, t, d = [], 0, len(potential_detect_times)
+    while t < d:
+        start = potential_detect_times[t]
+        t += 1
+        while cluster_partition[t] != 2:
+            t += 1
+        out.append((start, potential_detect_times[t - 1] + 1))
+    return tuple(out)
+
+
+def perform_detection_time_clustering(potential_detect_times, C0, C1):
+    """roc_functions.py:213-222: uint16 strictly increasing peak frames -> tuple of (start, end) clusters."""
+    times = np.ascontiguousarray(potential_detect_times)
+    if times.dtype != np.uint16 or times.ndim != 1:
+        raise ValueError("Buffer dtype mismatch, expected 'npy_uint16' but got '%s'" % times.dtype)
+    bt = np.zeros((times.shape[0], 2), np.int32)
+    bt[:, 1] = times
+    _, _, clusters, ncl = ops.cluster_peaks(to_dev(bt), 1, float(C0), float(C1))
+    c = clusters[:int(ncl[0].item())].cpu().numpy()
+    return tuple((times.dtype.type(a), int(b)) for a, b in c)

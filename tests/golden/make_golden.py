@@ -72,6 +72,16 @@ def main():
     LF64 = rs.randn(9, 6, 5)
     lengths = np.array([25, 10, 0], np.int64)
     out.update(de_F=F4, de_LF=LF64, de_len=lengths, de_max=clf.get_max_detect_examples(F4, LF64, lengths))
+    # ---- clustering of detection peaks (cluster_times.pyx:133-219), compiled reference
+    ct = oracle.load_ref_cluster_times()
+    if ct is None:
+        raise SystemExit("oracle/_ref/cluster_times is not built: run python oracle/build_ref.py first")
+    gaps = [rs.choice([1, 2, 3, 5, 8, 13, 30, 60], size=n) for n in (0, 1, 2, 7, 19, 40, 40, 64)]
+    for i, g in enumerate(gaps):
+        t = np.cumsum(g).astype(np.uint16)
+        C0, C1 = float([3, 3, 5, 5, 10, 3, 33, 8][i]), float([10, 10, 20, 33, 50, 20, 100, 15][i])
+        out["ct_times_%d" % i], out["ct_C_%d" % i] = t, np.array([C0, C1], np.float32)
+        out["ct_part_%d" % i] = ct.cluster_times(t, C0, C1)
     np.savez_compressed(os.path.join(os.path.dirname(os.path.abspath(__file__)), "ref_small.npz"), **out)
     print("wrote ref_small.npz with", len(out), "arrays")
 

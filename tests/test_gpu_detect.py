@@ -218,3 +218,43 @@ def test_peak_picking(cuda, oracle):
     want = [(b, int(t)) for b in range(5) for t in (oracle.get_max_above_threshold(V[b], int(lens[b]), 0.3, 10) if lens[b] - 10 + 1 >= 3 else [])]
     assert [tuple(x) for x in bt] == want
     np.testing.assert_array_equal(val, np.array([V[b, t] for b, t in want], np.float32))
+
+
+def test_cluster_peaks_against_oracle(cuda, oracle, golden):
+    """N2 second half: clustering of the picked peaks on the GPU (one utterance per thread) is bit-exact against the
+    compiled-reference fixtures and the oracle: single peak trains through the reference-signature drop-ins, and a batch
+    of score tracks through detect_peaks -> cluster_peaks."""
+    from tsr_b200 import cluster_times as gct, ops, roc_functions as groc
+    for i in range(8):
+        t, (C0, C1) = golden["ct_times_%d" % i], golden["ct_C_%d" % i]
+        part = gct.cluster_times(t, float(C0), float(C1))
+        np.testing.assert_array_equal(part, golden["ct_part_%d" % i])
+        want = oracle.get_cluster_starts_ends(t, golden["ct_part_%d" % i])
+        got = groc.perform_detection_time_clustering(t, float(C0), float(C1))
+        assert [(int(a), int(b)) for a, b in got] == [(int(a), int(b)) for a, b in want]
+        assert groc.get_cluster_starts_ends(t, part) == want
+    with pytest.raises(ValueError):
+        gct.cluster_times(np.arange(5, dtype=np.int64), 3., 10.)
+    # batch: smooth random tracks, utterances with no peak at all, ragged lengths
+    rs = np.random.RandomState(9)
+    B, T = 37, 300
+    track = np.cumsum(rs.randn(B, T), 1).astype(np.float32)
+    track[5] = -100.0
+    track[B - 1] = -100.0
+    lengths = rs.randint(50, T + 1, B).astype(np.int32)
+    bt, _ = ops.detect_peaks(torch.from_numpy(track).cuda(), 0.5, 3, torch.from_numpy(lengths).cuda())
+    for C0, C1 in ((5., 33.), (10., 20.), (2., 1000.)):
+        off, part, clusters, ncl = (x.cpu().numpy() for x in ops.cluster_peaks(bt, B, C0, C1))
+        btn = bt.cpu().numpy()
+        assert off[0] == 0 and off[B] == btn.shape[0]
+        for b in range(B):
+            t = btn[off[b]:off[b + 1], 1].astype(np.uint16)
+            assert np.all(btn[off[b]:off[b + 1], 0] == b)
+            np.testing.assert_array_equal(t, oracle.get_max_above_threshold(track[b], int(lengths[b]), 0.5, 3))
+            want = oracle.cluster_times(t, C0, C1)
+            np.testing.assert_array_equal(part[off[b] + b:off[b + 1] + b + 1], want)
+            se = oracle.get_cluster_starts_ends(t, want)
+            assert ncl[b] == len(se)
+            assert [tuple(r) for r in clusters[off[b]:off[b] + ncl[b]]] == [(int(a), int(c)) for a, c in se]
+    off, part, clusters, ncl = ops.cluster_peaks(torch.zeros((0, 2), dtype=torch.int32, device="cuda"), 4, 5., 20.)
+    assert off.cpu().tolist() == [0] * 5 and ncl.cpu().tolist() == [0] * 4 and part.cpu().tolist() == [2] * 4

@@ -314,3 +314,22 @@ def test_linear_filter_and_window_score_golden(oracle, golden_models):
     np.testing.assert_allclose([fs[0][1], fs[1][1]], [g["lfs_c0"], g["lfs_c1"]], rtol=1e-14)
     s, C = oracle.score_template_background_section(g["sc_template"], g["sc_bgd"], g["sc_E"])
     np.testing.assert_allclose([s, C], [g["sc_s"], g["sc_C"]], rtol=1e-14)
+
+
+# ------------------------------------------------------------------ clustering of detection peaks
+def test_cluster_times_golden_and_reference(oracle, golden):
+    """cluster_times.pyx:133-219: the C restatement against the fixtures made by the compiled reference and, when
+    oracle/_ref is built here, against the compiled reference on random peak trains."""
+    for i in range(8):
+        t, (C0, C1) = golden["ct_times_%d" % i], golden["ct_C_%d" % i]
+        np.testing.assert_array_equal(oracle.cluster_times(t, float(C0), float(C1)), golden["ct_part_%d" % i])
+    ct = oracle.load_ref_cluster_times()
+    if ct is None:
+        pytest.skip("compiled reference cluster_times not built here")
+    rs = np.random.RandomState(3)
+    for _ in range(400):
+        t = np.cumsum(rs.choice([1, 2, 3, 5, 8, 13, 30, 60], size=rs.randint(0, 50))).astype(np.uint16)
+        C0, C1 = float(rs.choice([2, 3, 5, 10, 33])), float(rs.choice([5, 10, 20, 33, 50, 100]))
+        np.testing.assert_array_equal(oracle.cluster_times(t, C0, C1), ct.cluster_times(t, C0, C1))
+    part = oracle.cluster_times(np.array([3, 4, 9, 30, 31], np.uint16), 5., 20.)
+    assert oracle.get_cluster_starts_ends(np.array([3, 4, 9, 30, 31]), part) == ((3, 5), (9, 10), (30, 32))
