@@ -211,7 +211,7 @@ def workload_config(batch):
                         "-> spread_patches(2,2) -> 32 x 40-frame part-level template LLR detect -> max/argmax",
             "utterance": "300 frames x 40 bands x 8 edges", "utterances_per_gpu": batch, "parts": K_PARTS, "templates": M_TEMPL,
             "template_frames": L_TEMPL, "sharding": "by utterance, no collective",
-            "l2": "256 MB flush buffer written between timed steps; per-step working set (138 MB feature bits + 39 MB scores) also exceeds the 126 MB L2"}
+            "l2": "256 MB flush buffer written between timed steps, then a second 256 MB buffer read so the flush's dirty lines are written back before the step's first event (otherwise the first kernel of the step pays for them); per-step working set (138 MB feature bits + 39 MB scores) also exceeds the 126 MB L2"}
 
 
 # ------------------------------------------------------------------------------ GPU arm
@@ -242,6 +242,7 @@ def run_native(args):
     X_pinned = torch.from_numpy(X).pin_memory()
     bits = ops.pack_edges(X_pinned.to(dev))                                    # resident input of the kernel-only timing
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    flush_rd = torch.zeros(256 << 18, dtype=torch.int32, device=dev)           # read-only second pass: leaves the L2 cold AND clean
     stream = torch.cuda.current_stream()
 
     names = ["spread_edges", "code_parts", "spread_codes", "detect", "reduce"]
@@ -275,6 +276,7 @@ def run_native(args):
     all_evs = []
     for _ in range(args.steps):
         flush.fill_(1)                                                          # evict L2 (outside the per-step events)
+        flush_rd.sum()                                                          # ... and push the fill's dirty lines out to HBM
         evs = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
         step(evs)
         all_evs.append(evs)

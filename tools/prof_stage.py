@@ -39,6 +39,11 @@ for it in range(a.iters):
         ops.spread_codes(codes, 100, 2, 2)
     if a.stage in ("detect", "all"):
         ops.detect(fb, bank, impl=impl)
+    if a.stage == "threshold_blocks":          # N4 + N3 front end: spectrogram -> packed edge bytes
+        if it == 0:
+            g = torch.Generator(device="cuda").manual_seed(1)
+            spec = torch.randn((B, 40, 300), dtype=torch.float64, device="cuda", generator=g).cumsum(2) * 0.03
+        ops.edges_from_spectrogram(spec, 40, 0.7)
     ev[1].record()
     torch.cuda.synchronize()
     print("%s iter %d: %.3f ms" % (a.stage, it, ev[0].elapsed_time(ev[1])))

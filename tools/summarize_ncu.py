@@ -24,7 +24,8 @@ def to_bytes(v, unit):
 summary = {}
 batch = 1024
 for kern, name in (("detect", "detect_tc_kernel"), ("code_parts", "code_parts_tc_kernel"),
-                   ("spread_codes", "spread_codes_kernel"), ("spread_edges", "spread_edges_kernel")):
+                   ("spread_codes", "spread_codes_kernel"), ("spread_edges", "spread_edges_kernel"),
+                   ("threshold_blocks", "threshold_blocks_kernel")):
     rep = os.path.join(ROOT, "gpurun_out", "%s_%s.ncu-rep" % (tag, kern))
     if not os.path.exists(rep):
         continue
