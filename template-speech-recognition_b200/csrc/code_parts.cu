@@ -261,7 +261,9 @@ __global__ void __launch_bounds__(CP_THREADS, 1) code_parts_tc_kernel(CodeArgs A
     uint64_t* w_bar = tempty_bar + CP_NACC;                                // [1]
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(w_bar + 1);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // warp index through a broadcast shuffle: the compiler then knows the role branches are warp-uniform and keeps the
+    // issuers' descriptor arithmetic in uniform registers (no R2UR moves, no elect on the critical issue path)
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     const uint32_t fmt = reinterpret_cast<const uint32_t*>(A.blob + L.off_hdr)[0];
     const uint32_t nacc = L.npad <= 128 ? 4u : 2u, acc_cols = 512u / nacc;
 

@@ -22,6 +22,8 @@
 //   warp  13    MMA issuer + TMEM allocation
 #include <type_traits>
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace tsr {
@@ -322,7 +324,9 @@ __global__ void __launch_bounds__(448 + 32 * (NIS - 1), 1) detect_tc_kernel(Dete
     uint64_t* tempty_bar = tfull_bar + 1;                              // [DT_MSUB_MAX]
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty_bar + DT_MSUB_MAX);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // warp index through a broadcast shuffle: tells the compiler it is warp-uniform, so the role branches are uniform and the
+    // issuer's descriptor arithmetic can stay in uniform registers (fewer R2UR moves on the critical issue path)
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     const uint32_t fmt = reinterpret_cast<const uint32_t*>(A.blob)[0];
     const int L = f.L, NT = f.NT, msub = f.msub, nchunks = f.nchunks, tptv = f.tptv, nstage = f.nstage;
     const int step_rows = msub * 128;
@@ -1054,6 +1058,7 @@ int tsr_detect(const uint32_t* featbits, int B, int T, int D, int rowwords, cons
         // Two issuer warps lift config 3 (32 templates, bank L2 resident) from 141 to 128 cycles per MMA, 2.62 -> 2.49 ms,
         // but slow the 1000-template stream (bank 438 MB, streamed through L2 group by group) from 264 to 290 ms.
         A.nissue = (size_t)A.f.ntiles * set_bytes <= ((size_t)64 << 20) ? 2 : 1;
+        if (const char* ov = getenv("TSR_DEBUG_DETECT_NISSUE")) A.nissue = ov[0] == '2' ? 2 : 1;   // experiments only
     }
     A.rows_per_unit = (int)((R + best_U - 1) / best_U);
     A.steps_per_unit = (A.rows_per_unit + A.f.Lc + step_rows - 1) / step_rows;
