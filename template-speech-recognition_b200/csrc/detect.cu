@@ -311,7 +311,9 @@ __device__ __forceinline__ void detect_unit_coords(long long u, int ntiles, int 
 
 // NIS = MMA issuer warps (I8 only): a compile-time constant, because the issue loop is the critical path of the kernel and
 // a run-time stride / barrier count in it cost 6-20 % (measured)
-template <bool I8, int NIS>
+// UNI: take the warp index through a broadcast shuffle (uniform issue loop).  It wins everywhere except for L = 1 (the EM
+// contractions), where the frame-bit expanders set the pace and the extra spills it causes there cost 5 %.
+template <bool I8, int NIS, bool UNI>
 __global__ void __launch_bounds__(448 + 32 * (NIS - 1), 1) detect_tc_kernel(DetectArgs A) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const FilterLayout& f = A.f;
@@ -326,7 +328,7 @@ __global__ void __launch_bounds__(448 + 32 * (NIS - 1), 1) detect_tc_kernel(Dete
 
     // warp index through a broadcast shuffle: tells the compiler it is warp-uniform, so the role branches are uniform and the
     // issuer's descriptor arithmetic can stay in uniform registers (fewer R2UR moves on the critical issue path)
-    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+    const int warp = UNI ? __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0) : (int)(threadIdx.x >> 5), lane = threadIdx.x & 31;
     const uint32_t fmt = reinterpret_cast<const uint32_t*>(A.blob)[0];
     const int L = f.L, NT = f.NT, msub = f.msub, nchunks = f.nchunks, tptv = f.tptv, nstage = f.nstage;
     const int step_rows = msub * 128;
@@ -1065,17 +1067,17 @@ int tsr_detect(const uint32_t* featbits, int B, int T, int D, int rowwords, cons
     const long long nunits = (long long)A.f.ntiles * best_U;
     int blocks = (int)(nunits < nsm ? nunits : nsm);
     if (A.f.kind) {
-        // the second issuer is warp 14: launched only when used (an idle 15th warp alone cost the stream config 20 %)
-        if (A.nissue == 2) {
-            TSR_CUDA(cudaFuncSetAttribute(detect_tc_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S.total));
-            detect_tc_kernel<true, 2><<<blocks, DT_THREADS, S.total, (cudaStream_t)stream>>>(A);
-        } else {
-            TSR_CUDA(cudaFuncSetAttribute(detect_tc_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S.total));
-            detect_tc_kernel<true, 1><<<blocks, DT_THREADS - 32, S.total, (cudaStream_t)stream>>>(A);
-        }
+        auto launch = [&](auto kern, int threads) {
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S.total);
+            if (e == cudaSuccess) kern<<<blocks, threads, S.total, (cudaStream_t)stream>>>(A);
+            return e;
+        };
+        // the second issuer is warp 14: launched only when used
+        if (A.nissue == 2) TSR_CUDA(L > 1 ? launch(detect_tc_kernel<true, 2, true>, DT_THREADS) : launch(detect_tc_kernel<true, 2, false>, DT_THREADS));
+        else TSR_CUDA(L > 1 ? launch(detect_tc_kernel<true, 1, true>, DT_THREADS - 32) : launch(detect_tc_kernel<true, 1, false>, DT_THREADS - 32));
     } else {
-        TSR_CUDA(cudaFuncSetAttribute(detect_tc_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S.total));
-        detect_tc_kernel<false, 1><<<blocks, DT_THREADS - 32, S.total, (cudaStream_t)stream>>>(A);
+        TSR_CUDA(cudaFuncSetAttribute(detect_tc_kernel<false, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S.total));
+        detect_tc_kernel<false, 1, true><<<blocks, DT_THREADS - 32, S.total, (cudaStream_t)stream>>>(A);
     }
     return check_launch("tsr_detect");
 }
