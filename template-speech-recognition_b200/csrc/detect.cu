@@ -94,6 +94,13 @@ __host__ __device__ inline FilterLayout filter_layout(int M, int L, int D, int p
             if (eff >= best - 1e-9) { best = eff; best_fold = fo; }
         }
     }
+#ifndef __CUDA_ARCH__
+    if (f.kind)   // experiments only: force the fold (must be the same when the filters are prepared and when they are used)
+        if (const char* ov = getenv("TSR_DEBUG_DETECT_FOLD")) {
+            const int fo = atoi(ov);
+            if (fo >= 1 && fo <= L && f.vpt * ((L + fo - 1) / fo) <= DT_NT_MAX) best_fold = fo;
+        }
+#endif
     f.fold = best_fold;
     f.Lf = (L + f.fold - 1) / f.fold;
     f.Lc = f.fold * (f.Lf - 1);
