@@ -1,0 +1,195 @@
+"""BASELINE-size checks of the CUDA path through size-independent properties (the oracle is far too slow at these
+sizes: the reference needs ~3 minutes per 1024-utterance batch on 16 cores):
+
+* batch invariance  -- an utterance scores the same inside the 1024-utterance batch as inside an 8-utterance batch
+                       (tile / unit boundaries, persistent-CTA scheduling, no leakage between utterances): bit-exact;
+* spreading algebra -- OR-linearity, extensivity, box(r) o box(r) = box(2r), separability of the code spreading;
+* coding            -- relabelling the parts relabels the codes; raising the edge threshold only removes codes;
+* detection         -- linear in the filters, equivariant to time shifts, chunk invariant on the 1 h stream (config 5:
+                       720 000 frames x 1000 templates), tensor kernel == sequential-fp32 SIMT kernel on a sample;
+* EM (config 4)     -- hard-assignment M-step numerators are the exact bit counts; the log-likelihood never decreases.
+"""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(900)]
+
+B_FULL = 1024
+
+
+@pytest.fixture(scope="module")
+def full(cuda):
+    from tsr_b200 import ops, synth
+    from tsr_b200.pipeline import ScoringPipeline
+    lp, lip = synth.parts(100)
+    Tm, bgd = synth.templates(M=32, L=40, Fd=36, Kd=100)
+    W, c = synth.linear_filters(Tm, bgd)
+    pipe = ScoringPipeline(lp, lip, W, c)
+    X = synth.fast_edge_batch(B_FULL, seed=11)
+    bits = ops.pack_edges(torch.from_numpy(X).cuda())
+    return dict(pipe=pipe, bits=bits, lp=lp, lip=lip, W=W, c=c)
+
+
+def test_pipeline_batch_invariance(full):
+    from tsr_b200 import ops
+    pipe, bits = full["pipe"], full["bits"]
+    codes, fb = pipe.code(bits)
+    best, arg, scores = pipe.score(fb)
+    rs = np.random.RandomState(0)
+    for start in [0, B_FULL - 8] + list(rs.randint(0, B_FULL - 8, 4)):
+        sl = slice(int(start), int(start) + 8)
+        c8, fb8 = pipe.code(bits[sl].contiguous())
+        b8, a8, s8 = pipe.score(fb8)
+        assert torch.equal(c8, codes[sl]) and torch.equal(fb8, fb[sl])
+        assert torch.equal(s8, scores[sl]) and torch.equal(b8, best[sl]) and torch.equal(a8, arg[sl])
+    # the L-1 tail frames of every utterance are zero, like the reference's detect (:157-158)
+    assert float(scores[:, -39:].abs().max()) == 0.0
+    # part-code histogram is sane: background and real parts both present
+    frac0 = float((codes == 0).float().mean())
+    assert 0.05 < frac0 < 0.95 and int(codes.max()) <= 100
+
+
+def test_edge_spreading_algebra(full):
+    from tsr_b200 import ops
+    bits = full["bits"]
+    other = torch.roll(bits, shifts=(3, 5), dims=(0, 1))
+    for mode, blk in (("line", 40), ("line", 0), ("box", 0)):
+        a = ops.spread_edges(bits, 1, None, mode, blk)
+        b = ops.spread_edges(other, 1, None, mode, blk)
+        ab = ops.spread_edges(bits | other, 1, None, mode, blk)
+        assert torch.equal(ab, a | b)                                   # OR-linear
+        assert torch.equal(a & bits, bits)                              # extensive
+    once = ops.spread_edges(bits, 1, None, "box", 0)
+    assert torch.equal(ops.spread_edges(once, 1, None, "box", 0), ops.spread_edges(bits, 2, None, "box", 0))
+    # per-orientation structure: in line mode orientation e only ever reads orientation e
+    e3 = bits & 0x08
+    assert torch.equal(ops.spread_edges(e3, 2, None, "line", 40) & 0xF7, torch.zeros_like(bits))
+    # pack / unpack round trip at full size
+    assert torch.equal(ops.pack_edges(ops.unpack_edges(bits, 8)), bits)
+
+
+def test_code_spreading_separable(full):
+    from tsr_b200 import ops
+    codes, _ = full["pipe"].code(full["bits"])
+    K = 100
+    full22 = ops.spread_codes(codes, K, 2, 2)
+    horiz = ops.spread_codes(codes, K, 0, 2)
+    acc = torch.zeros_like(horiz)
+    To = codes.shape[1]
+    for a in range(-2, 3):                                               # vertical OR of the horizontal dilation
+        lo, hi = max(0, a), min(To, To + a)
+        acc[:, lo - a:hi - a] |= horiz[:, lo:hi]
+    assert torch.equal(acc, full22)
+    point = ops.spread_codes(codes, K, 0, 0)
+    assert torch.equal(full22 & point, point)
+    # the one-hot map has exactly one bit per coded location
+    ones = ops.unpack_features(point[:64].contiguous(), 36 * K).sum(dtype=torch.int64)
+    assert int(ones) == int((codes[:64] != 0).sum())
+
+
+def test_code_parts_relabelling_and_threshold(full):
+    from tsr_b200 import ops
+    bits = ops.spread_edges(full["bits"], 1, None, "line", 40)
+    lp, lip = full["lp"], full["lip"]
+    perm = np.random.RandomState(1).permutation(100)
+    base = ops.code_parts(bits, ops.PartsModel(lp, lip), 12)[0]
+    permuted = ops.code_parts(bits, ops.PartsModel(lp[perm], lip[perm]), 12)[0]
+    # part k of the permuted dictionary is part perm[k] of the original one
+    lut = torch.from_numpy(np.concatenate([[0], perm + 1]).astype(np.uint8)).cuda()
+    mism = (lut[permuted.long()] != base)
+    assert float(mism.float().mean()) < 1e-5                            # only exact-tie locations may differ
+    hi = ops.code_parts(bits, ops.PartsModel(lp, lip), 20)[0]
+    assert torch.equal(hi[hi != 0], base[hi != 0]) and int((hi != 0).sum()) < int((base != 0).sum())
+    counts = ops.code_parts(bits, ops.PartsModel(lp, lip), 12, want_codes=False, want_counts=True)[2]
+    assert torch.equal(counts >= 12, base != 0) and torch.equal(counts >= 20, hi != 0)
+
+
+def test_detection_linearity_shift_and_simt(full):
+    from tsr_b200 import ops
+    pipe = full["pipe"]
+    _, fb = pipe.code(full["bits"])
+    W = full["W"]
+    rs = np.random.RandomState(2)
+    W2 = (rs.randn(*W.shape) * 0.5).astype(np.float32)
+    s1 = ops.detect(fb, ops.FilterBank(W, planes=ops.PLANES_INT8X3))
+    s2 = ops.detect(fb, ops.FilterBank(W2, planes=ops.PLANES_INT8X3))
+    s12 = ops.detect(fb, ops.FilterBank(W + W2, planes=ops.PLANES_INT8X3))
+    scale = float(s12.abs().max())
+    assert float((s12 - (s1 + s2)).abs().max()) <= 1e-5 * scale         # linear in the filters (weight quantisation only)
+    # time-shift equivariance: dropping the first 7 frames shifts the score track by 7
+    sh = ops.detect(fb[:, 7:].contiguous(), pipe.bank)
+    ref = ops.detect(fb, pipe.bank)
+    assert torch.equal(sh[:, :296 - 7 - 39], ref[:, 7:296 - 39])
+    # tensor kernel against the sequential-fp32 SIMT kernel (bit-identical to the reference) on 16 utterances
+    simt = ops.detect(fb[:16].contiguous(), pipe.bank, impl=ops.IMPL_SIMT)
+    assert float((ref[:16] - simt).abs().max()) <= 1e-5 * float(simt.abs().max())
+
+
+def test_stream_chunk_invariance_config5(cuda):
+    """1 h of frames (720 000) against 1000 40-frame templates: scoring the stream in two chunks with an L-1 frame
+    overlap gives exactly the scores of the whole stream (how the time sharding over GPUs works)."""
+    from tsr_b200 import ops
+    T, M, L, D = 720000, 1000, 40, 3600
+    g = torch.Generator(device="cuda").manual_seed(5)
+    rw = ops.rowwords(D)
+    fb = torch.randint(-2**31, 2**31 - 1, (1, T, rw), dtype=torch.int32, device="cuda", generator=g)
+    fb &= torch.randint(-2**31, 2**31 - 1, (1, T, rw), dtype=torch.int32, device="cuda", generator=g)
+    fb &= torch.randint(-2**31, 2**31 - 1, (1, T, rw), dtype=torch.int32, device="cuda", generator=g)   # density 1/8
+    rs = np.random.RandomState(6)
+    bank = ops.FilterBank((rs.randn(M, L, D) * 0.3).astype(np.float32), planes=ops.PLANES_INT8X3)
+    whole = ops.detect(fb, bank)
+    cut = 360123
+    left = ops.detect(fb[:, :cut + L - 1].contiguous(), bank)
+    right = ops.detect(fb[:, cut:].contiguous(), bank)
+    assert torch.equal(left[:, :cut], whole[:, :cut])
+    assert torch.equal(right, whole[:, cut:])
+    assert float(whole[:, T - L + 1:].abs().max()) == 0.0
+    # a sample of frames against a direct evaluation of the definition in float64
+    F8 = ops.unpack_features(fb[:, 1000:1000 + 64 + L - 1].contiguous(), D)[0].double()           # (64+L-1, D)
+    LF = bank.LF.double()                                                                          # (M, L, D)
+    want = torch.stack([(F8[t:t + L][None] * LF).sum((1, 2)) for t in range(0, 64, 9)])            # (8, M)
+    got = whole[0, 1000:1000 + 64:9].double()
+    assert float((got - want).abs().max()) <= 1e-5 * float(want.abs().max())
+
+
+def test_em_config4_properties(cuda):
+    """N = 100 000 rows, D = 12 800, K = 16: with one-hot affinities the M-step numerators are exact bit counts;
+    over soft EM iterations the log-likelihood never decreases and the parameters stay in range."""
+    from tsr_b200 import ops
+    N, D, K = 100000, 12800, 16
+    g = torch.Generator(device="cuda").manual_seed(3)
+    rw = ops.rowwords(D)
+    X = torch.randint(-2**31, 2**31 - 1, (N, rw), dtype=torch.int32, device="cuda", generator=g)
+    X &= torch.randint(-2**31, 2**31 - 1, (N, rw), dtype=torch.int32, device="cuda", generator=g)
+    st = ops.EmState(X, D, K)
+    T = torch.rand((K, D), device="cuda", generator=g).clamp_(0.05, 0.95)
+    par = dict(templates=T.clone(), logT=torch.log(T), logInvT=torch.log(1 - T),
+               weights=torch.full((K,), 1.0 / K, device="cuda"), logw=torch.full((K,), float(np.log(1.0 / K)), device="cuda"))
+    # hard assignment: numerators[k][d] = number of rows assigned to k with bit d set
+    st.estep(par["logT"], par["logInvT"], par["logw"], hard=True)
+    st.mstep_accumulate()
+    z = st.aff.argmax(1)
+    assert torch.equal(st.aff.sum(1), torch.ones(N, device="cuda")) and set(torch.unique(st.aff).tolist()) <= {0.0, 1.0}
+    numer = st.stats[:K * D].view(K, D)
+    resp = st.stats[K * D:]
+    assert torch.equal(resp, torch.bincount(z, minlength=K).float())
+    for k in (0, 7, 15):
+        rows = X[z == k]
+        bitsum = torch.zeros(D, dtype=torch.int64, device="cuda")
+        for lo in range(0, rows.shape[0], 4096):
+            bitsum += ops.unpack_features(rows[None, lo:lo + 4096].contiguous(), D)[0].sum(0, dtype=torch.int64)
+        # exact integers up to the final float32 scaling of the digit-plane recombination (2217.9998 for 2218)
+        assert torch.equal(numer[k].round().long(), bitsum)
+        assert float((numer[k].double() - bitsum.double()).abs().max()) <= 1e-6 * float(bitsum.max())
+    # soft EM: monotone log-likelihood, parameters in range
+    lls = []
+    for _ in range(6):
+        st.estep(par["logT"], par["logInvT"], par["logw"])
+        lls.append(float(st.ll.item()))
+        st.mstep_accumulate()
+        ops.em_finalize(st.stats, N, D, K, 0.05, par["templates"], par["logT"], par["logInvT"], par["weights"], par["logw"])
+    assert all(b >= a - 1e-7 * abs(a) for a, b in zip(lls, lls[1:])), lls
+    assert abs(float(par["weights"].sum()) - 1.0) < 1e-5
+    assert float(par["templates"].min()) >= 0.05 - 1e-7 and float(par["templates"].max()) <= 0.95 + 1e-7
+    assert float((st.aff.sum(1) - 1).abs().max()) < 1e-5

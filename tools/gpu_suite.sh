@@ -3,7 +3,7 @@
 # smoke and a short bench.  Usage (on the GPU box): bash tools/gpu_suite.sh [bench-args]
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,driver_version,clocks.max.sm --format=csv > gpurun_out/gpu.txt 2>&1
-for f in spread edges code_parts detect em pipeline; do
+for f in spread edges code_parts detect em pipeline full_size; do
   timeout 900 python -m pytest tests/test_gpu_$f.py -q -m gpu -x --timeout=600 -s > gpurun_out/test_$f.log 2>&1
   echo "test_gpu_$f exit $?" | tee -a gpurun_out/summary.txt
   tail -5 gpurun_out/test_$f.log
