@@ -201,39 +201,55 @@ __global__ void __launch_bounds__(128) spread_edges_line_kernel(const uint32_t* 
 template <int R0>
 __device__ __forceinline__ void sc_vertical_or(const uint32_t* __restrict__ H, uint32_t* __restrict__ out, int pitch,
                                                int rowwords, int nrow, int r0, int D) {
-    // tasks = (row segment, word column); a thread takes tasks blockDim.x apart
-    const int nseg = max(1, (int)blockDim.x / rowwords);
-    const int per = (nrow + nseg - 1) / nseg;
-    for (int task = threadIdx.x; task < nseg * rowwords; task += blockDim.x) {
-        const int seg = task / rowwords, w = task - seg * rowwords;
-        const int ra = seg * per, rb = min(nrow, ra + per);
-        if (ra >= rb) continue;
-        // bits >= D of the row are padding and stay zero (out-of-range cells spill into them in phase A)
-        const int live = D - 32 * w;
-        const uint32_t keep = live >= 32 ? 0xFFFFFFFFu : (live <= 0 ? 0u : ((1u << live) - 1u));
-        const uint32_t* hp = H + ra * pitch + w;
-        uint32_t* op = out + (size_t)ra * rowwords + w;
-        if constexpr (R0 >= 0) {
-            constexpr int W = 2 * R0 + 1;
-            uint32_t win[W];
+    if constexpr (R0 >= 0) {
+        // 64-bit words (rowwords, the pitch and H's word offset are even, the output rows 8-byte aligned): half the
+        // LDS / STG instructions of the 32-bit walk -- the kernel is issue bound.  tasks = (row segment, word pair).
+        const int npair = rowwords >> 1;
+        const int nseg = max(1, (int)blockDim.x / npair);
+        const int per = (nrow + nseg - 1) / nseg;
+        constexpr int W = 2 * R0 + 1;
+        for (int task = threadIdx.x; task < nseg * npair; task += blockDim.x) {
+            const int seg = task / npair, w = 2 * (task - seg * npair);
+            const int ra = seg * per, rb = min(nrow, ra + per);
+            if (ra >= rb) continue;
+            // bits >= D of the row are padding and stay zero (out-of-range cells spill into them in phase A)
+            const int live = D - 32 * w;
+            uint2 keep;
+            keep.x = live >= 32 ? 0xFFFFFFFFu : (live <= 0 ? 0u : ((1u << live) - 1u));
+            keep.y = live >= 64 ? 0xFFFFFFFFu : (live <= 32 ? 0u : ((1u << (live - 32)) - 1u));
+            const uint32_t* hp = H + ra * pitch + w;
+            uint32_t* op = out + (size_t)ra * rowwords + w;
+            uint2 win[W];
 #pragma unroll
-            for (int a = 0; a < W - 1; ++a) win[a] = hp[a * pitch];
+            for (int a = 0; a < W - 1; ++a) win[a] = *reinterpret_cast<const uint2*>(hp + a * pitch);
             hp += (W - 1) * pitch;
             for (int r = ra; r < rb; r += W) {
 #pragma unroll
                 for (int u = 0; u < W; ++u) {
                     if (r + u < rb) {
-                        win[(u + W - 1) % W] = *hp;
+                        win[(u + W - 1) % W] = *reinterpret_cast<const uint2*>(hp);
                         hp += pitch;
-                        uint32_t acc = 0;
+                        uint2 acc = make_uint2(0u, 0u);
 #pragma unroll
-                        for (int a = 0; a < W; ++a) acc |= win[a];
-                        *op = acc & keep;
+                        for (int a = 0; a < W; ++a) { acc.x |= win[a].x; acc.y |= win[a].y; }
+                        *reinterpret_cast<uint2*>(op) = make_uint2(acc.x & keep.x, acc.y & keep.y);
                         op += rowwords;
                     }
                 }
             }
-        } else {
+        }
+    } else {
+        // generic radius: tasks = (row segment, word column); a thread takes tasks blockDim.x apart
+        const int nseg = max(1, (int)blockDim.x / rowwords);
+        const int per = (nrow + nseg - 1) / nseg;
+        for (int task = threadIdx.x; task < nseg * rowwords; task += blockDim.x) {
+            const int seg = task / rowwords, w = task - seg * rowwords;
+            const int ra = seg * per, rb = min(nrow, ra + per);
+            if (ra >= rb) continue;
+            const int live = D - 32 * w;
+            const uint32_t keep = live >= 32 ? 0xFFFFFFFFu : (live <= 0 ? 0u : ((1u << live) - 1u));
+            const uint32_t* hp = H + ra * pitch + w;
+            uint32_t* op = out + (size_t)ra * rowwords + w;
             for (int r = ra; r < rb; ++r) {
                 uint32_t acc = 0;
                 for (int a = 0; a <= 2 * r0; ++a) acc |= hp[a * pitch];
@@ -244,9 +260,6 @@ __device__ __forceinline__ void sc_vertical_or(const uint32_t* __restrict__ H, u
         }
     }
 }
-
-// one nonzero code p at column x1 of packed row hrow: bits (x1+k)*K + p-1, |k| <= r1, shifted by the
-// left slack `off` (out-of-range columns land in the slack / padding and are never read back)
 template <int R1>
 __device__ __forceinline__ void sc_scatter(uint32_t* hrow, int d, int K, int r1) {
     if constexpr (R1 >= 0) {
@@ -517,11 +530,12 @@ int tsr_spread_codes(const uint8_t* codes, uint32_t* featbits, int B, int To, in
     if ((long long)B * To == 0) return TSR_OK;
     int rc = require_sm100("tsr_spread_codes");
     if (rc) return rc;
-    // packed smem rows: left slack of ceil(r1*K/32) words, the row, right slack for columns Fo..Fo+r1-1;
-    // odd pitch (conflict-free column access).  4 tiles per 296-row utterance at the BASELINE shape.
-    const int offw = (r1 * K + 31) / 32;
+    // packed smem rows: left slack of ceil(r1*K/32) words, the row, right slack for columns Fo..Fo+r1-1.  4 tiles per 296-row utterance at the BASELINE shape.
+    // even word offset and even pitch (64-bit accesses in phase B), pitch = 2 mod 4 so that rows do not alias banks
+    const int offw = ((r1 * K + 31) / 32 + 1) & ~1;
     const int needw = offw + ((Fo + r1) * K + 31) / 32 + 1;
-    const int pitch = (needw > offw + rowwords ? needw : offw + rowwords) | 1;
+    int pitch = ((needw > offw + rowwords ? needw : offw + rowwords) + 1) & ~1;
+    if ((pitch & 3) == 0) pitch += 2;
     int RT = 74;
     while (RT > 4 && (size_t)(RT + 2 * r0) * pitch * 4 > 96 * 1024) RT = (RT + 1) / 2;
     if (RT > To) RT = To;
