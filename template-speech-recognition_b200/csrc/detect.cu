@@ -929,47 +929,84 @@ __global__ void __launch_bounds__(256) detect_reduce_kernel(const float* __restr
     const int q = threadIdx.x & 7;
     const bool vec = (M & 3) == 0 && (reinterpret_cast<uintptr_t>(scores) & 15) == 0;
     const long long stride = (long long)gridDim.x * (blockDim.x >> 3);
-    const long long nloop = (R + stride - 1) / stride;          // same trip count for every lane (shuffles below)
-    long long g = blockIdx.x * (long long)(blockDim.x >> 3) + (threadIdx.x >> 3);
-    for (long long it = 0; it < nloop; ++it, g += stride) {
-        const bool live = g < R;
-        const int tl = live ? (int)(g % T) : 0;
-        const bool valid = live && tl <= T - L;
-        float bv = -INFINITY;
-        int bm = 0x7fffffff;
-        if (valid || (live && tail_mode == 1)) {
-            for (int m0 = 4 * q; m0 < M; m0 += 32) {
-                float v[4] = {0.f, 0.f, 0.f, 0.f};
-                if (valid) {
-                    if (vec) {
-                        const float4 x = __ldcs(reinterpret_cast<const float4*>(scores + g * M + m0));
-                        v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w;
-                    } else {
+    // two rows per 8-lane group and iteration (two independent 16-byte loads in flight per lane); same trip count for
+    // every lane (shuffles below)
+    const long long nloop = (R + 2 * stride - 1) / (2 * stride);
+    long long g0 = blockIdx.x * (long long)(blockDim.x >> 3) + (threadIdx.x >> 3);
+    for (long long it = 0; it < nloop; ++it, g0 += 2 * stride) {
+        float bv[2];
+        int bm[2];
+        bool live[2], valid[2];
 #pragma unroll
-                        for (int i = 0; i < 4; ++i)
-                            if (m0 + i < M) v[i] = scores[g * M + m0 + i];
+        for (int u = 0; u < 2; ++u) {
+            const long long g = g0 + u * stride;
+            live[u] = g < R;
+            const int tl = live[u] ? (R < (1ll << 31) ? (int)((unsigned)g % (unsigned)T) : (int)(g % T)) : 0;
+            valid[u] = live[u] && tl <= T - L;
+            bv[u] = -INFINITY;
+            bm[u] = 0x7fffffff;
+        }
+        if (vec && M <= 32) {          // one float4 per lane covers the row: both rows' loads issue before either is used
+            float4 x[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                x[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (valid[u] && 4 * q < M) x[u] = __ldcs(reinterpret_cast<const float4*>(scores + (g0 + u * stride) * M + 4 * q));
+            }
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                if ((valid[u] || (live[u] && tail_mode == 1)) && 4 * q < M) {
+                    const float v[4] = {x[u].x, x[u].y, x[u].z, x[u].w};
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float y = v[i] + (cs ? __ldg(cs + 4 * q + i) : 0.f);
+                        if (y > bv[u]) { bv[u] = y; bm[u] = 4 * q + i; }
                     }
                 }
+            }
+        } else {
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    if (m0 + i < M) {
-                        const float x = v[i] + (cs ? __ldg(cs + m0 + i) : 0.f);
-                        if (x > bv) { bv = x; bm = m0 + i; }
+            for (int u = 0; u < 2; ++u) {
+                const long long g = g0 + u * stride;
+                if (valid[u] || (live[u] && tail_mode == 1)) {
+                    for (int m0 = 4 * q; m0 < M; m0 += 32) {
+                        float v[4] = {0.f, 0.f, 0.f, 0.f};
+                        if (valid[u]) {
+                            if (vec) {
+                                const float4 x = __ldcs(reinterpret_cast<const float4*>(scores + g * M + m0));
+                                v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w;
+                            } else {
+#pragma unroll
+                                for (int i = 0; i < 4; ++i)
+                                    if (m0 + i < M) v[i] = scores[g * M + m0 + i];
+                            }
+                        }
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            if (m0 + i < M) {
+                                const float y = v[i] + (cs ? __ldg(cs + m0 + i) : 0.f);
+                                if (y > bv[u]) { bv[u] = y; bm[u] = m0 + i; }
+                            }
+                        }
                     }
                 }
             }
         }
 #pragma unroll
-        for (int off = 4; off >= 1; off >>= 1) {
-            const float ov = __shfl_xor_sync(0xffffffffu, bv, off);
-            const int om = __shfl_xor_sync(0xffffffffu, bm, off);
-            if (ov > bv || (ov == bv && om < bm)) { bv = ov; bm = om; }
-        }
-        if (live && q == 0) {
-            if (!(valid || tail_mode == 1)) bv = 0.f;
-            if (bm == 0x7fffffff) bm = 0;
-            if (best) best[g] = bv;
-            if (arg) arg[g] = (uint16_t)bm;
+        for (int u = 0; u < 2; ++u) {
+#pragma unroll
+            for (int off = 4; off >= 1; off >>= 1) {
+                const float ov = __shfl_xor_sync(0xffffffffu, bv[u], off);
+                const int om = __shfl_xor_sync(0xffffffffu, bm[u], off);
+                if (ov > bv[u] || (ov == bv[u] && om < bm[u])) { bv[u] = ov; bm[u] = om; }
+            }
+            if (live[u] && q == 0) {
+                const long long g = g0 + u * stride;
+                if (!(valid[u] || tail_mode == 1)) bv[u] = 0.f;
+                if (bm[u] == 0x7fffffff) bm[u] = 0;
+                if (best) best[g] = bv[u];
+                if (arg) arg[g] = (uint16_t)bm[u];
+            }
         }
     }
 }
@@ -1099,7 +1136,7 @@ int tsr_detect_reduce(const float* scores, const float* cs, int B, int T, int M,
     int rc = require_sm100("tsr_detect_reduce");
     if (rc) return rc;
     const long long R = (long long)B * T;
-    long long blocks = (R + 31) / 32;          // 32 rows per 256-thread CTA
+    long long blocks = (R + 63) / 64;          // 2 x 32 rows per 256-thread CTA and iteration
     if (blocks > 148LL * 32) blocks = 148LL * 32;
     detect_reduce_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(scores, cs, R, T, M, L, tail_mode, best, arg);
     return check_launch("tsr_detect_reduce");
