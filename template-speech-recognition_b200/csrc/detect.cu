@@ -172,59 +172,76 @@ __global__ void filters_publish_kernel(uint8_t* __restrict__ blob, int plane_for
 // One thread per weight element of a (tile, chunk): column n = (group v, frame tau), v = m*vpt + plane.
 __global__ void prepare_filters_kernel(const float* __restrict__ LF, uint8_t* __restrict__ blob, FilterLayout f,
                                        int plane_format) {
+    // One thread per 16-byte row of a filter tile (16 int8 digits or 8 16-bit values of one column n and one k-group):
+    // the index arithmetic is paid once per row, the loads are 64 / 32 contiguous bytes, consecutive threads write
+    // consecutive rows.  (The EM M-step rebuilds its "filters" -- the affinities -- every iteration.)
     const uint32_t* hdr = reinterpret_cast<const uint32_t*>(blob);
     const uint32_t fmt = pick_format(hdr[1], plane_format == TSR_PLANES_BF16 ? 1 : (plane_format == TSR_PLANES_FP16 ? 2 : 0));
     const uint32_t* tmaxbits = hdr + 32;
     uint8_t* tiles = blob + f.hdr_bytes;
-    const size_t nelem = (size_t)f.ntiles * f.nchunks * f.NT * f.fps;
+    const int ept = f.kind ? 16 : 8;                    // elements per thread
+    const int nkg = f.fps / ept;                        // k-groups per chunk
+    const size_t nrows = (size_t)f.ntiles * f.nchunks * nkg * f.NT;
     const float qmax = f.P == 3 ? 8355711.f : 32639.f;
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < nelem; i += (size_t)gridDim.x * blockDim.x) {
-        const int dd = (int)(i % f.fps);              // feature within the chunk
-        size_t r = i / f.fps;
-        const int n = (int)(r % f.NT); r /= f.NT;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < nrows; i += (size_t)gridDim.x * blockDim.x) {
+        const int n = (int)(i % f.NT);
+        size_t r = i / f.NT;
+        const int kg = (int)(r % nkg); r /= nkg;
         const int c = (int)(r % f.nchunks);
         const int nt = (int)(r / f.nchunks);
-        int phi, d;                                     // frame within the super-row, feature within the frame
+        const int dd0 = kg * ept;                       // first feature of the row within the chunk
+        int phi, d0;                                    // frame within the super-row, first feature within the frame
         if (f.kind) {   // chunk c = (cf * fold + phi) * 2 + half
             const int half = c & 1, cp = c >> 1;
             phi = cp % f.fold;
-            d = (cp / f.fold) * 128 + half * 64 + dd;
+            d0 = (cp / f.fold) * 128 + half * 64 + dd0;
         } else {
-            const int kf = c * f.fps + dd;              // position in the contraction (fold == 1)
+            const int kf = c * f.fps + dd0;             // position in the contraction (fold == 1); rows never straddle frames
             const int dpad = f.rowwords * 32;
-            phi = kf / dpad; d = kf - phi * dpad;
+            phi = kf / dpad; d0 = kf - phi * dpad;
         }
         const int vl = n / f.Lf, tauf = n - vl * f.Lf;
         const int tau = tauf * f.fold + phi;
         const int v = nt * f.tptv + vl;
         const int m = v / f.vpt, plane = v - m * f.vpt;
-        float w = 0.f;
-        const bool live = vl < f.tptv && m < f.M && d < f.D && phi < f.fold && tau < f.L;
-        if (live) w = LF[((size_t)m * f.L + tau) * f.D + d];
+        const bool live = vl < f.tptv && m < f.M && phi < f.fold && tau < f.L;
+        const float* src = LF + ((size_t)(live ? m : 0) * f.L + (live ? tau : 0)) * f.D;
         uint8_t* tile = tiles + ((size_t)nt * f.nchunks + c) * f.tile_bytes;
         if (f.kind) {
-            int q = 0;
+            float sc = 1.f;
             if (live) {
                 const float mx = __uint_as_float(tmaxbits[m]);
-                const float sc = mx > 0.f ? mx / qmax : 1.f;
-                float qf = rintf(w / sc);
-                qf = fminf(fmaxf(qf, -qmax), qmax);
-                q = (int)qf;
+                sc = mx > 0.f ? mx / qmax : 1.f;
             }
-            int digit = 0;
-            for (int pl = 0; pl <= plane; ++pl) {      // balanced base-256 digits, least significant first
-                digit = ((q + 128) & 255) - 128;
-                q = (q - digit) >> 8;
+            uint32_t w4[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+                int digit = 0;
+                if (live && d0 + e < f.D) {
+                    float qf = rintf(src[d0 + e] / sc);
+                    qf = fminf(fmaxf(qf, -qmax), qmax);
+                    int q = (int)qf;
+                    for (int pl = 0; pl <= plane; ++pl) {      // balanced base-256 digits, least significant first
+                        digit = ((q + 128) & 255) - 128;
+                        q = (q - digit) >> 8;
+                    }
+                }
+                w4[e >> 2] |= (uint32_t)(digit & 255) << (8 * (e & 3));
             }
-            const int kg = dd >> 4, e = dd & 15;
-            tile[((size_t)kg * f.NT + n) * 16 + e] = (uint8_t)(int8_t)digit;
+            *reinterpret_cast<uint4*>(tile + ((size_t)kg * f.NT + n) * 16) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
         } else {
-            uint16_t hi, lo;
-            split_hi_lo((double)w, fmt, hi, lo);
-            const int kg = dd >> 3, e = dd & 7;
-            const size_t o = ((size_t)kg * f.NT + n) * 16 + e * 2;
-            *reinterpret_cast<uint16_t*>(tile + o) = hi;
-            *reinterpret_cast<uint16_t*>(tile + (size_t)f.NT * 128 + o) = lo;
+            uint32_t h4[4] = {0u, 0u, 0u, 0u}, l4[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const float w = (live && d0 + e < f.D) ? src[d0 + e] : 0.f;
+                uint16_t hi, lo;
+                split_hi_lo((double)w, fmt, hi, lo);
+                h4[e >> 1] |= (uint32_t)hi << (16 * (e & 1));
+                l4[e >> 1] |= (uint32_t)lo << (16 * (e & 1));
+            }
+            const size_t o = ((size_t)kg * f.NT + n) * 16;
+            *reinterpret_cast<uint4*>(tile + o) = make_uint4(h4[0], h4[1], h4[2], h4[3]);
+            *reinterpret_cast<uint4*>(tile + (size_t)f.NT * 128 + o) = make_uint4(l4[0], l4[1], l4[2], l4[3]);
         }
     }
 }
