@@ -336,7 +336,8 @@ __device__ __forceinline__ void detect_unit_coords(long long u, int ntiles, int 
 // NIS = MMA issuer warps (I8 only): a compile-time constant, because the issue loop is the critical path of the kernel and
 // a run-time stride / barrier count in it cost 6-20 % (measured)
 // UNI: take the warp index through a broadcast shuffle (uniform issue loop).  It wins everywhere except for L = 1 (the EM
-// contractions), where the frame-bit expanders set the pace and the extra spills it causes there cost 5 %.
+// contractions), where the frame-bit expanders set the pace and the extra spills it causes there cost 5 %.  UNI = false is
+// the L = 1 variant: plain warp index and expander groups that take alternate strips (see the expander role).
 template <bool I8, int NIS, bool UNI>
 __global__ void __launch_bounds__(448 + 32 * (NIS - 1), 1) detect_tc_kernel(DetectArgs A) {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -362,7 +363,7 @@ __global__ void __launch_bounds__(448 + 32 * (NIS - 1), 1) detect_tc_kernel(Dete
         // I8: two MMA issuer warps (13, 14) share every pipeline slot, so the consumer-side barriers take two commits
         constexpr uint32_t nis = NIS;
         for (int s = 0; s < DT_MAX_BSTAGES; ++s) { mbar_init(&full_bar[s], I8 ? 1 : DT_PRODUCERS / 2 + 1); mbar_init(&empty_bar[s], nis); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&afull_bar[s], DT_PRODUCERS); mbar_init(&aempty_bar[s], nis); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&afull_bar[s], (I8 && !UNI) ? DT_PRODUCERS / 2 : DT_PRODUCERS); mbar_init(&aempty_bar[s], nis); }
         mbar_init(tfull_bar, nis);
         for (int s = 0; s < DT_MSUB_MAX; ++s) mbar_init(&tempty_bar[s], 128);
         mbar_fence_init();
@@ -383,10 +384,16 @@ __global__ void __launch_bounds__(448 + 32 * (NIS - 1), 1) detect_tc_kernel(Dete
             // I8: all 8 warps expand one A strip per 128-feature frame chunk: rows = the step's frames plus
             // fold-1 more, 8 k-groups of 16 bytes each, k-group stride kgs.  Row r of phase phi's A tile is
             // strip row r + phi, so the strip is expanded once and read by all `fold` phases.
-            const int tid = threadIdx.x - 32;                // 0..255
+            // ALT (the L = 1 / EM variant): the two groups of 4 warps take alternate strips, group g always strip buffer g.
+            // With L = 1 a strip feeds only 8 MMAs, and the chain wait -> expand -> proxy fence -> arrive of one strip
+            // (~2 000 cycles, mostly latency) set the kernel's pace when all 8 warps worked on the same strip.
+            constexpr bool ALT = !UNI;
+            constexpr int XT = ALT ? 128 : 256;              // threads per strip
+            const int grp = (threadIdx.x - 32) >> 7;         // ALT: group of this thread
+            const int tid = ALT ? (int)((threadIdx.x - 32) & 127) : (int)(threadIdx.x - 32);
             const int nw2 = f.rowwords >> 1;                 // 64-bit words per frame
             const int srows = step_rows + f.fold - 1;        // live strip rows
-            constexpr int RPT = (DT_MSUB_MAX * 128 + 255) / 256 + 1;   // strip rows per thread (<= 384 + fold - 1 rows)
+            constexpr int RPT = (DT_MSUB_MAX * 128 + XT - 1) / XT + 1;   // strip rows per thread (<= 384 + fold - 1 rows)
             uint32_t ita = 0;
             for (long long u = blockIdx.x; u < nunits; u += gridDim.x) {
                 int nt_unused; long long ur;
@@ -397,10 +404,11 @@ __global__ void __launch_bounds__(448 + 32 * (NIS - 1), 1) detect_tc_kernel(Dete
                 for (int step = 0; step < A.steps_per_unit; ++step) {
                     const long long g0 = o0 + (long long)step * step_rows;
                     for (int cf = 0; cf < f.ncf; ++cf, ++ita) {
+                        if (ALT && (int)(ita & 1) != grp) continue;
                         uint2 w[RPT], wh[RPT];
 #pragma unroll
                         for (int k = 0; k < RPT; ++k) {
-                            const int r = tid + 256 * k;
+                            const int r = tid + XT * k;
                             const long long fr = g0 + r;
                             const bool ok = r < srows && fr < in_end;
                             const uint2* src = reinterpret_cast<const uint2*>(A.bits + (ok ? fr : 0) * f.rowwords);
@@ -413,7 +421,7 @@ __global__ void __launch_bounds__(448 + 32 * (NIS - 1), 1) detect_tc_kernel(Dete
                         uint8_t* strip = smem + buf * S.strip_bytes;
 #pragma unroll
                         for (int k = 0; k < RPT; ++k) {
-                            const int r = tid + 256 * k;
+                            const int r = tid + XT * k;
                             if (r < f.strip_rows) {
                                 uint8_t* dst = strip + r * 16;
                                 const uint32_t kgs = (uint32_t)f.kgs;
