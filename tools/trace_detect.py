@@ -5,12 +5,17 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from tsr_b200 import ops, synth, _lib
 lib = _lib.lib()
 planes = int(sys.argv[1]) if len(sys.argv) > 1 else 4
-Tm, bgd = synth.templates(M=32, L=40, Fd=36, Kd=100)
-W, c = synth.linear_filters(Tm, bgd)
-bank = ops.FilterBank(W, cs=c, planes=planes)
 rs = np.random.RandomState(0)
-fb = torch.from_numpy(rs.randint(-2**31, 2**31 - 1, (1024, 296, 114), dtype=np.int64).astype(np.int32)).cuda()
-fb &= torch.from_numpy(rs.randint(-2**31, 2**31 - 1, (1024, 296, 114), dtype=np.int64).astype(np.int32)).cuda()
+if os.environ.get("TRACE_EM"):      # the EM E-step shape: N = 100 000 rows, D = 12 800 bits, K = 16 "templates" of one frame
+    bank = ops.FilterBank((rs.randn(16, 1, 12800) * 0.5).astype(np.float32), planes=planes)
+    g = torch.Generator(device="cuda").manual_seed(0)
+    fb = torch.randint(-2**31, 2**31 - 1, (1, 100000, 400), dtype=torch.int32, device="cuda", generator=g)
+else:
+    Tm, bgd = synth.templates(M=32, L=40, Fd=36, Kd=100)
+    W, c = synth.linear_filters(Tm, bgd)
+    bank = ops.FilterBank(W, cs=c, planes=planes)
+    fb = torch.from_numpy(rs.randint(-2**31, 2**31 - 1, (1024, 296, 114), dtype=np.int64).astype(np.int32)).cuda()
+    fb &= torch.from_numpy(rs.randint(-2**31, 2**31 - 1, (1024, 296, 114), dtype=np.int64).astype(np.int32)).cuda()
 ops.detect(fb, bank)
 torch.cuda.synchronize()
 buf = torch.zeros(256 * 8, dtype=torch.int64, device="cuda")
