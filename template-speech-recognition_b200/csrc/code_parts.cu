@@ -143,11 +143,20 @@ struct CodeArgs {
     int dbg;            // debug experiments: 1 = epilogue skips TMEM reads, 2 = MMA warp skips tcgen05.mma
     long long* trace;   // optional debug timeline of CTA 0: [tile][8] clock64 stamps (tools/trace_code_parts.py)
 };
+// The timeline stamps and debug switches are compiled in only with -DTSR_DEBUG_TRACE (tools/trace_code_parts.py needs
+// it): even predicated-off they sit in the issue loops, where every instruction shows up in the kernel time.
+#ifdef TSR_DEBUG_TRACE
+#define CP_DBG(x) (A.dbg & (x))
 #define CP_TRACE_TILES 96
 #define CP_TRACE(slot)                                                                              \
     do {                                                                                            \
         if (A.trace && blockIdx.x == 0 && it < CP_TRACE_TILES && lane == 0) A.trace[it * 8 + (slot)] = clock64(); \
     } while (0)
+#else
+#define CP_DBG(x) 0
+#define CP_TRACE_TILES 96
+#define CP_TRACE(slot) do { } while (0)
+#endif
 
 // --------------------------------------------------------------------------- SIMT path
 // One warp per location, lanes over parts; walks the set bits of the window in (a,b,z) order and
@@ -320,7 +329,7 @@ __global__ void __launch_bounds__(CP_THREADS, 1) code_parts_tc_kernel(CodeArgs A
             const int stage = it % CP_NSTAGE;
             const uint32_t ph = (it / CP_NSTAGE) & 1;
             mbar_wait_relaxed(&empty_bar[stage], ph ^ 1);
-            if (warp == 8 && !(A.dbg & 4)) CP_TRACE(0);
+            if (warp == 8 && !CP_DBG(4)) CP_TRACE(0);
             uint8_t* dst = smem + S.a + stage * S.stage_bytes;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -338,7 +347,7 @@ __global__ void __launch_bounds__(CP_THREADS, 1) code_parts_tc_kernel(CodeArgs A
             }
             fence_proxy_async_smem();
             mbar_arrive(&full_bar[stage]);
-            if (warp == 8 && !(A.dbg & 4)) CP_TRACE(1);
+            if (warp == 8 && !CP_DBG(4)) CP_TRACE(1);
             if (tile + gridDim.x < ntiles) prefetch(tile + gridDim.x);   // overlaps the next empty-slot wait
         }
     } else if (warp >= 12) {
@@ -389,13 +398,13 @@ __global__ void __launch_bounds__(CP_THREADS, 1) code_parts_tc_kernel(CodeArgs A
             const int acc = it % nacc;
             const uint32_t aph = (it / nacc) & 1;
             mbar_wait(&full_bar[stage], ph);
-            if (!(A.dbg & 4)) CP_TRACE(2);
+            if (!CP_DBG(4)) CP_TRACE(2);
             mbar_wait(&tempty_bar[acc], aph ^ 1);
-            if (!(A.dbg & 4)) CP_TRACE(3);
+            if (!CP_DBG(4)) CP_TRACE(3);
             tc_fence_after();
             const uint32_t a_base = smem_u32(smem + S.a + stage * S.stage_bytes) >> 4;
             const uint32_t d_tmem = tmem_base + acc * acc_cols;
-            if (!(A.dbg & 2)) {
+            if (!CP_DBG(2)) {
                 // accumulator := c[k] (constant-ones A x the c step), then the 2 x nsteps patch steps accumulate
                 umma_f16_elect(d_tmem, ones_desc, cstep_desc, idesc, 0u);
                 uint32_t b_lo = b_base;
@@ -417,7 +426,7 @@ __global__ void __launch_bounds__(CP_THREADS, 1) code_parts_tc_kernel(CodeArgs A
             }
             umma_commit_elect(&empty_bar[stage]);   // A stage reusable once these MMAs retire
             umma_commit_elect(&tfull_bar[acc]);     // accumulator ready for the epilogue
-            if (!(A.dbg & 4)) CP_TRACE(4);
+            if (!CP_DBG(4)) CP_TRACE(4);
         }
     } else {
         // ================================ epilogue ================================
@@ -445,13 +454,13 @@ __global__ void __launch_bounds__(CP_THREADS, 1) code_parts_tc_kernel(CodeArgs A
             float fcount = 0.f, fmcount = 0.f;
             float* srow = A.scores + loc * L.K;      // drop-in path only: the full score map
             // All TMEM loads of a 64-column block are issued back to back and waited for once.
-            for (int nb = 0; nb < ((A.dbg & 1) ? 0 : L.npad); nb += 64) {
+            for (int nb = 0; nb < (CP_DBG(1) ? 0 : L.npad); nb += 64) {
                 uint32_t v[64];
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
                     if (nb + 16 * j < L.npad) tmem_ld16(taddr + nb + 16 * j, *reinterpret_cast<uint32_t(*)[16]>(&v[16 * j]));
                 tmem_ld_wait();
-                if ((A.dbg & 4) && (warp & 3) == 0) CP_TRACE(nb ? 3 : 1);
+                if (CP_DBG(4) && (warp & 3) == 0) CP_TRACE(nb ? 3 : 1);
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const int n = nb + 16 * j;
@@ -477,7 +486,7 @@ __global__ void __launch_bounds__(CP_THREADS, 1) code_parts_tc_kernel(CodeArgs A
                     // padded range, i.e. static register indices (a data-dependent index would push v[] to local memory)
                     if (n + 16 == L.npad) { fcount = __uint_as_float(v[16 * j + 14]); fmcount = __uint_as_float(v[16 * j + 15]); }
                 }
-                if ((A.dbg & 4) && (warp & 3) == 0) CP_TRACE(nb ? 4 : 2);
+                if (CP_DBG(4) && (warp & 3) == 0) CP_TRACE(nb ? 4 : 2);
             }
             tc_fence_before();
             mbar_arrive(&tempty_bar[acc]);

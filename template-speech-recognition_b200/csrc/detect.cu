@@ -261,6 +261,11 @@ struct DetectArgs {
     long long* trace;   // optional debug timeline of CTA 0: [stage iteration][8] clock64 stamps
     int dbg;            // debug experiments (timing only, wrong results): 1 = every phase reads the strip at row 0
 };
+// The timeline stamps and debug switches are compiled in only with -DTSR_DEBUG_TRACE (TSR_NVCC_EXTRA=-DTSR_DEBUG_TRACE
+// python template-speech-recognition_b200/build.py --force; tools/trace_detect.py needs it): even predicated-off they
+// sit in the issue loops, where every instruction shows up in the kernel time.
+#ifdef TSR_DEBUG_TRACE
+#define DT_DBG(x) (A.dbg & (x))
 #define DT_TRACE_ITERS 256
 #define DT_TRACE(itv, slot)                                                                          \
     do {                                                                                             \
@@ -273,6 +278,12 @@ struct DetectArgs {
         if (A.trace && blockIdx.x == 0 && stepno == 1 && quad == 0 && lane == 0 && passno < 60)                    \
             A.trace[(192 + passno) * 8 + (slot)] = clock64();                                                      \
     } while (0)
+#else
+#define DT_DBG(x) 0
+#define DT_TRACE_ITERS 256
+#define DT_TRACE(itv, slot) do { } while (0)
+#define DT_TRACE_PASS(slot) do { } while (0)
+#endif
 
 struct DetectSmem {
     uint32_t b, stage, outacc, bars, stage_bytes, a_bytes, a_sub, strip_bytes, total;
@@ -572,7 +583,7 @@ __global__ void __launch_bounds__(448 + 32 * (NIS - 1), 1) detect_tc_kernel(Dete
                                         tc_fence_after();
                                     }
                                     const uint32_t d_tmem = tmem_base + sub * NT;
-                                    const uint32_t arow = sbase + (uint32_t)(sub * 128 + ((A.dbg & 1) ? 0 : phi));
+                                    const uint32_t arow = sbase + (uint32_t)(sub * 128 + (DT_DBG(1) ? 0 : phi));
 #pragma unroll
                                     for (int j = 0; j < 2; ++j) {   // K = 32 per MMA: k-groups 2*(2*half+j), +1
                                         const uint64_t adesc = a_hi8 | (uint64_t)(arow + (uint32_t)(2 * (2 * half + j)) * kgs16);

@@ -1,4 +1,7 @@
-"""Dump the per-stage timeline of CTA 0 of detect_tc_kernel (debug hook)."""
+"""Dump the per-stage timeline of CTA 0 of detect_tc_kernel (debug hook).
+Needs a library built with the stamps compiled in:
+    TSR_NVCC_EXTRA=-DTSR_DEBUG_TRACE python template-speech-recognition_b200/build.py --force
+(the default build leaves them out: even predicated off they slow the issue loops by 2-7 %)."""
 import ctypes, os, sys
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
