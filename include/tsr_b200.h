@@ -40,7 +40,7 @@ extern "C" {
 #define TSR_ERR_CUDA        -2   /* a CUDA runtime call or launch failed */
 #define TSR_ERR_UNSUPPORTED -3   /* not an sm_100 device, or shape outside the kernel's limits */
 
-#define TSR_ABI_VERSION 1
+#define TSR_ABI_VERSION 2
 
 /* detection kernels selectable through `impl` arguments (per-stage choice) */
 #define TSR_IMPL_TENSOR 0   /* tcgen05 / TMEM path (default) */
@@ -67,6 +67,10 @@ int         tsr_rowwords(int D);             /* uint32 words per packed feature 
 /* X uint8 [B][T][F][E] (any nonzero = edge, as `if X[i,j,z]` code_parts.pyx:29) -> bits [B][T][F] */
 int tsr_pack_edges(const uint8_t* X, uint8_t* bits, int B, int T, int F, int E, void* stream);
 int tsr_unpack_edges(const uint8_t* bits, uint8_t* X, int B, int T, int F, int E, void* stream);
+/* The same packing for edge tensors in HOST memory (both pointers are host pointers; E must be 8), on `nthreads`
+ * host threads of a persistent pool: callers that stream from the host pack before the copy and move 1 byte per
+ * (t,f) instead of 8 (ScoringPipeline.stream).  Pure data movement; no arithmetic of the path runs on the host. */
+int tsr_host_pack_edges(const uint8_t* X_host, uint8_t* bits_host, long long n_cells, int E, int nthreads);
 /* F uint8 [R][D] (nonzero test, compute_likelihood_linear_filter.pyx:168) -> bits [R][rowwords] */
 int tsr_pack_features_u8(const uint8_t* Fm, uint32_t* bits, long long R, int D, int rowwords, void* stream);
 int tsr_unpack_features_u8(const uint32_t* bits, uint8_t* Fm, long long R, int D, int rowwords, void* stream);
@@ -208,31 +212,55 @@ int tsr_edges_from_spectrogram(const double* S, uint8_t* bits, uint8_t* tail_bit
 
 /* ---- K4: Bernoulli-mixture EM -----------------------------------------------------------------
  * Replaces BernoulliMixture.get_template_loglikelihoods/_compute_loglikelihoods
- * (bernoulli_mixture.py:263-291), M_step/threshold_templates (:177-193) and the same steps
- * of bernoulli_em.Bernoulli_Mixture (bernoulli_em.py:36-49, 103-127).
- * E-step over this rank's rows: S[n][k] = sum_d x ? logT : logInvT; ll = S + logw;
- * aff = row-softmax(ll) (or one-hot argmax of S when hard != 0); stats[K*D .. K*D+K) += column
- * sums of aff; stats_ll[0] += sum_n logsumexp(ll).  M accumulation: stats[k*D+d] += sum_n
- * aff[n][k] x[n][d].  The caller all-reduces stats/stats_ll across ranks (NCCL) and calls
- * tsr_em_finalize, which every rank runs identically. */
-size_t tsr_em_workspace_bytes(long long N, int D, int K);   /* scratch for the two calls below (K <= 64) */
-int tsr_em_estep(const uint32_t* Xbits, long long N, int D, int rowwords, int K, const float* logT,
-                 const float* logInvT, const float* logw, float* aff, float* scores_or_null, float* stats,
-                 double* stats_ll, int hard, void* workspace, int impl, void* stream);
-/* Tensor-core M-step: needs XT, the bit matrix transposed once per data set:
- * XT uint32 [D][N_pad/32], N_pad = tsr_em_npad(N,D,K) (rows padded so each of the
- * tsr_em_segments(N,D,K) contraction segments is a multiple of 128 data rows). */
-int       tsr_em_segments(long long N, int D, int K);
-long long tsr_em_npad(long long N, int D, int K);
+ * (bernoulli_mixture.py:263-291), M_step/threshold_templates (:177-193), the run_EM loop's stopping rule
+ * (:139-156) and the same steps of bernoulli_em.Bernoulli_Mixture (bernoulli_em.py:22-49, 103-127).
+ * Any number of components 1 <= K <= 4095 (the reference trains 100-200-part dictionaries with this class,
+ * Notebook/12/reestimate_parts.py:79-83).
+ *
+ * Sufficient statistics are ONE int64 vector  stats[K*D + K + 1]:
+ *   stats[k*D+d]   = sum_n q(n,k) x[n][d]       q(n,k) = round(aff[n][k] * 8355711)   (numerators)
+ *   stats[K*D+k]   = sum_n q(n,k)                                                      (responsibility sums)
+ *   stats[K*D+K]   = sum_n round(logsumexp_k(S[n][k] + logw[k]) * 2^20)                (log-likelihood)
+ * Integer sums are exact, so the caller's single allreduce(sum, int64) over the ranks (NCCL) gives the same
+ * bits for every rank count; tsr_em_finalize then runs identically on every rank.
+ *
+ * E-step over this rank's rows: S[n][k] = sum_d x ? logT : logInvT; aff = row-softmax(S + logw) (or the one-hot
+ * first arg-max of S when hard != 0).  With update != 0 it writes aff_or_null [N][K], the posterior digit planes
+ * the next tsr_em_mstep uses, and the last K+1 entries of stats; with update == 0 only scores_or_null [N][K] is
+ * written and no EM state is touched.  logT_or_null == NULL: use the weight planes the last
+ * tsr_em_finalize(workspace, N_local) call laid out in this workspace.
+ * M-step accumulation: stats[0 .. K*D) = numerators from the posteriors of the last E-step (aff_or_null == NULL)
+ * or from the given aff [N][K] (then stats[K*D .. K*D+K) is set from it too).
+ * ctl_or_null: device control block (tsr_em_control_*); once it has stopped, every call that carries it is a no-op
+ * on the device, so the host may queue iterations without reading the log-likelihood back. */
+size_t    tsr_em_workspace_bytes(long long N, int D, int K);
+int       tsr_em_workspace_init(void* workspace, long long N, int D, int K, void* stream);   /* once, before first use */
+long long tsr_em_npad(long long N);                                                           /* N rounded up to 256 */
+/* XT uint32 [D][N_pad/32] = the bit matrix transposed once per data set (tensor-path M-step), N_pad = tsr_em_npad(N) */
 int tsr_transpose_bits(const uint32_t* Xbits, long long N, int D, int rowwords, uint32_t* XTbits, long long N_pad,
                        void* stream);
-int tsr_em_mstep(const uint32_t* Xbits, const uint32_t* XTbits_or_null /* required for TSR_IMPL_TENSOR */,
-                 long long N, int D, int rowwords, int K, const float* aff, float* stats, void* workspace, int impl,
+int tsr_em_estep(const uint32_t* Xbits, long long N, int D, int rowwords, int K, const float* logT_or_null,
+                 const float* logInvT_or_null, const float* logw, float* aff_or_null, float* scores_or_null,
+                 long long* stats_or_null, int hard, int update, void* workspace, const void* ctl_or_null, int impl,
                  void* stream);
-/* weights = respsum / N_total; T = numer / N_total / weights clipped to [min_prob, 1-min_prob];
- * logT, logInvT, logw refreshed (all float32, as bernoulli_mixture.py:178-184). */
-int tsr_em_finalize(const float* stats, long long N_total, int D, int K, float min_prob, float* templates,
-                    float* logT, float* logInvT, float* weights, float* logw, void* stream);
+int tsr_em_mstep(const uint32_t* Xbits, const uint32_t* XTbits_or_null /* required for TSR_IMPL_TENSOR */,
+                 long long N, int D, int rowwords, int K, const float* aff_or_null, long long* stats, void* workspace,
+                 const void* ctl_or_null, int impl, void* stream);
+/* weights = respsum / N_total; T = numer / N_total / weights clipped to [min_prob, 1-min_prob]; logT, logInvT,
+ * logw refreshed (all float32, as bernoulli_mixture.py:178-184).  workspace_or_null != NULL: also lays out the
+ * int8 weight planes of the next E-step over N_local rows in that workspace. */
+int tsr_em_finalize(const long long* stats, long long N_total, int D, int K, float min_prob, float* templates,
+                    float* logT, float* logInvT, float* weights, float* logw, void* workspace_or_null,
+                    long long N_local, const void* ctl_or_null, void* stream);
+/* Device-side stopping rule.  ctl = tsr_em_control_bytes(max_trace) bytes of device memory:
+ *   int32 done, iterations, ntrace, mode, min_iter, max_iter, cap, pad; double tol, ll_old; double trace[max_trace].
+ * tsr_em_control_step (after the allreduce of stats) appends the log-likelihood to trace and applies
+ *   mode 0: continue while (abs((old - new) / old) > tol and iterations < max_iter) or iterations < min_iter
+ *   mode 1: continue while new - old > tol (and iterations < max_iter)
+ * counting an iteration when it continues and setting done otherwise. */
+size_t tsr_em_control_bytes(int max_trace);
+int    tsr_em_control_init(void* ctl, int max_trace, double tol, int mode, int min_iter, int max_iter, void* stream);
+int    tsr_em_control_step(void* ctl, const long long* stats, int D, int K, void* stream);
 
 #ifdef __cplusplus
 }

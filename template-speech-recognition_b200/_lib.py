@@ -20,6 +20,7 @@ SIGNATURES = {
     "tsr_rowwords": (_i, [_i]),
     "tsr_pack_edges": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "tsr_unpack_edges": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
+    "tsr_host_pack_edges": (_i, [_vp, _vp, _ll, _i, _i]),
     "tsr_pack_features_u8": (_i, [_vp, _vp, _ll, _i, _i, _vp]),
     "tsr_unpack_features_u8": (_i, [_vp, _vp, _ll, _i, _i, _vp]),
     "tsr_spread_edges": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _i, _vp]),
@@ -45,14 +46,18 @@ SIGNATURES = {
     "tsr_threshold_edges": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, ctypes.c_double, _vp, _vp]),
     "tsr_edges_from_spectrogram": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, ctypes.c_double, _vp, _vp]),
     "tsr_em_workspace_bytes": (_sz, [_ll, _i, _i]),
-    "tsr_em_estep": (_i, [_vp, _ll, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _vp]),
-    "tsr_em_segments": (_i, [_ll, _i, _i]),
-    "tsr_em_npad": (_ll, [_ll, _i, _i]),
+    "tsr_em_workspace_init": (_i, [_vp, _ll, _i, _i, _vp]),
+    "tsr_em_npad": (_ll, [_ll]),
     "tsr_transpose_bits": (_i, [_vp, _ll, _i, _i, _vp, _ll, _vp]),
-    "tsr_em_mstep": (_i, [_vp, _vp, _ll, _i, _i, _i, _vp, _vp, _vp, _i, _vp]),
-    "tsr_em_finalize": (_i, [_vp, _ll, _i, _i, _f, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "tsr_em_estep": (_i, [_vp, _ll, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _i, _vp]),
+    "tsr_em_mstep": (_i, [_vp, _vp, _ll, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp]),
+    "tsr_em_finalize": (_i, [_vp, _ll, _i, _i, _f, _vp, _vp, _vp, _vp, _vp, _vp, _ll, _vp, _vp]),
+    "tsr_em_control_bytes": (_sz, [_i]),
+    "tsr_em_control_init": (_i, [_vp, _i, ctypes.c_double, _i, _i, _i, _vp]),
+    "tsr_em_control_step": (_i, [_vp, _vp, _i, _i, _vp]),
 }
 
+ABI_VERSION = 2
 _lib = None
 
 
@@ -72,7 +77,7 @@ def lib():
             fn = getattr(l, name)
             fn.restype = res
             fn.argtypes = args
-        if l.tsr_abi_version() != 1:
+        if l.tsr_abi_version() != ABI_VERSION:
             raise TsrError("libtsr_b200.so ABI version mismatch")
         _lib = l
     return _lib

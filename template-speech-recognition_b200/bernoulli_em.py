@@ -42,15 +42,10 @@ class Bernoulli_Mixture:
         self._pull()
 
     def run_EM(self, tol, save_template=False):                            # :22-34
-        loglikelihood = -np.inf
-        new_ll = self.compute_loglikelihoods()
-        self.iterations = 0
-        while new_ll - loglikelihood > tol:
-            loglikelihood = new_ll
-            self.M_step()
-            new_ll = self.compute_loglikelihoods()
-            self.iterations += 1
-        self.loglikelihood = new_ll
+        """Iterate while the log-likelihood gains more than `tol` (absolute); rule evaluated on the device."""
+        self.iterations, trace = self._drv.run(tol, mode="absolute", min_iter=0, max_iter=100000, min_prob=.05)
+        self.loglikelihood_trace = trace
+        self.loglikelihood = trace[-1]
         self._pull()
 
     def M_step(self):                                                      # :36-45
@@ -62,10 +57,19 @@ class Bernoulli_Mixture:
     def compute_loglikelihoods(self):                                      # :103-114
         return self._drv.expectation(hard=False)
 
-    def get_template_loglikelihoods(self, data_mat=None):                  # :122-127 (for the training data)
-        scores = torch.empty((self._engine.N, self.num_mix), dtype=torch.float32, device=self._engine.device)
+    def get_template_loglikelihoods(self, data_mat=None):                  # :122-127
+        """Scores (N,K) of `data_mat` (default: the training data) under the current templates; a pure accessor."""
         p = self._drv.params
-        self._engine.state.estep(p["logT"], p["logInvT"], p["logw"], scores_out=scores)
+        if data_mat is None or data_mat is self.data_mat:
+            state = self._engine.state
+        else:
+            data_mat = np.asarray(data_mat)
+            if data_mat.shape[1:] != (self.height, self.width):
+                raise ValueError("data_mat must be (n, %d, %d)" % (self.height, self.width))
+            D = self.height * self.width
+            state = GpuEmEngine((data_mat.reshape(data_mat.shape[0], D) > .5).astype(np.uint8), D, self.num_mix).state
+        scores = torch.empty((state.N, self.num_mix), dtype=torch.float32, device=self._engine.device)
+        state.estep(p["logT"], p["logInvT"], p["logw"], scores_out=scores, update=False)
         return scores.cpu().numpy().astype(np.float64)
 
     def _pull(self):

@@ -6,8 +6,9 @@ work_templates, weights, affinities, log_templates, log_invtemplates, iterations
 num_data, data_length, data_shape).  Differences, all documented in DESIGN.md:
   * posteriors are a true row soft-max (the reference's :277-279 is algebraically the same
     but can underflow to 0/0 with >= ~100 near-equal components);
-  * template scores are accumulated in fp32 from bf16 hi+lo weights on the tensor cores
-    (the reference: float32/float64 BLAS); log-likelihoods agree to ~1e-6 relative;
+  * template scores are exact integer sums of 24-bit fixed-point weights (three int8 digit planes on the
+    tensor cores; the reference: float32/float64 BLAS); log-likelihoods agree to ~1e-6 relative;
+  * any num_mix from 1 to 4095 (the reference trains 100-200-part dictionaries with this class);
   * prints are dropped; `init_type='unif_rand'` is the reference's deterministic round-robin.
 Multi-GPU: pass ``row_range=(lo, hi)`` (see em_driver.shard_rows) on every rank of an
 initialised torch.distributed group; the statistics are all-reduced once per iteration.
@@ -73,21 +74,14 @@ class BernoulliMixture:
     def run_EM(self, tol, min_probability=0.05, debug_plot=False, hard_assignment=False, rand_seed=None,
                use_templates=None, max_iter=500, min_iter=10):
         """:108-160, same stopping rule: iterate while the relative log-likelihood change
-        exceeds `tol` (and iterations < max_iter) or iterations < min_iter."""
+        exceeds `tol` (and iterations < max_iter) or iterations < min_iter.  The rule is evaluated on the
+        device (em_driver.EmDriver.run), so no log-likelihood is read back between iterations."""
         self.hard_assignment = hard_assignment
         self.min_probability = np.float32(min_probability)
-        new_ll = self._drv.expectation(hard=hard_assignment)               # first E-step (:135)
-        loglikelihood = new_ll / (1 - tol) - 10                            # :139
-        self.iterations = 0
-        self.loglikelihood_trace = [new_ll]
-        while (np.abs((loglikelihood - new_ll) / loglikelihood) > tol and self.iterations < max_iter) \
-                or self.iterations < min_iter:                             # :144
-            loglikelihood = new_ll
-            self._drv.maximization(self.min_probability)                   # M-step (:150)
-            new_ll = self._drv.expectation(hard=hard_assignment)           # E-step (:152)
-            self.loglikelihood_trace.append(new_ll)
-            self.iterations += 1
-        self.loglikelihood = new_ll
+        self.iterations, self.loglikelihood_trace = self._drv.run(
+            tol, mode="relative", min_iter=min_iter, max_iter=max_iter, hard=hard_assignment,
+            min_prob=self.min_probability)
+        self.loglikelihood = self.loglikelihood_trace[-1]
         self._pull_params()
         self.set_templates()                                               # :160
 
@@ -101,9 +95,11 @@ class BernoulliMixture:
         return ll
 
     def get_template_loglikelihoods(self):                                 # :287-291
+        """Pure accessor, as in the reference: scores of the (local) training rows under the current
+        templates; posteriors, statistics and the log-likelihood are left untouched."""
         scores = torch.empty((self._engine.N, self.num_mix), dtype=torch.float32, device=self._engine.device)
         p = self._drv.params
-        self._engine.state.estep(p["logT"], p["logInvT"], p["logw"], scores_out=scores)
+        self._engine.state.estep(p["logT"], p["logInvT"], p["logw"], scores_out=scores, update=False)
         return scores.cpu().numpy()
 
     # ----------------------------------------------------------------------- accessors

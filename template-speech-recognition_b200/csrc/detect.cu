@@ -1078,7 +1078,7 @@ int tsr_prepare_filters(const float* LF, int M, int L, int D, int plane_format, 
     TSR_CUDA(cudaMemsetAsync(blob, 0, f.hdr_bytes, st));
     dim3 g(16, M);
     filters_maxabs_kernel<<<g, 256, 0, st>>>(LF, M, (size_t)L * D, (uint8_t*)blob);
-    prepare_filters_kernel<<<148 * 8, 256, 0, st>>>(LF, (uint8_t*)blob, f, plane_format);
+    prepare_filters_kernel<<<sm_count() * 8, 256, 0, st>>>(LF, (uint8_t*)blob, f, plane_format);
     filters_publish_kernel<<<(M + 255) / 256, 256, 0, st>>>((uint8_t*)blob, plane_format, f);
     return check_launch("tsr_prepare_filters");
 }
@@ -1100,7 +1100,7 @@ int tsr_detect(const uint32_t* featbits, int B, int T, int D, int rowwords, cons
     if (impl == TSR_IMPL_SIMT) {
         TSR_REQUIRE(LF_or_null, "tsr_detect(simt): needs the fp32 filters");
         long long blocks = (R * M + 127) / 128;
-        if (blocks > 148LL * 32) blocks = 148LL * 32;
+        if (blocks > (long long)sm_count() * 32) blocks = (long long)sm_count() * 32;
         detect_simt_kernel<<<(unsigned)blocks, 128, 0, (cudaStream_t)stream>>>(featbits, LF_or_null, scores, R, T, D, rowwords, M, L);
         return check_launch("tsr_detect(simt)");
     }
@@ -1173,7 +1173,7 @@ int tsr_detect_reduce(const float* scores, const float* cs, int B, int T, int M,
     if (rc) return rc;
     const long long R = (long long)B * T;
     long long blocks = (R + 63) / 64;          // 2 x 32 rows per 256-thread CTA and iteration
-    if (blocks > 148LL * 32) blocks = 148LL * 32;
+    if (blocks > (long long)sm_count() * 32) blocks = (long long)sm_count() * 32;
     detect_reduce_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(scores, cs, R, T, M, L, tail_mode, best, arg);
     return check_launch("tsr_detect_reduce");
 }
@@ -1188,7 +1188,7 @@ int tsr_detect_float(const float* Fm, int B, int T, int D, const float* LF, int 
     if (rc) return rc;
     const long long R = (long long)B * T;
     long long blocks = (R * M + 127) / 128;
-    if (blocks > 148LL * 32) blocks = 148LL * 32;
+    if (blocks > (long long)sm_count() * 32) blocks = (long long)sm_count() * 32;
     detect_float_kernel<<<(unsigned)blocks, 128, 0, (cudaStream_t)stream>>>(Fm, LF, init_or_null, scores, R, T, D, M, L);
     return check_launch("tsr_detect_float");
 }

@@ -285,7 +285,7 @@ int tsr_edge_map(const double* S, double* mags, int B, int F, int T, void* strea
     if (rc) return rc;
     const long long n = (long long)B * 8 * F * T;
     long long blocks = (n + 255) / 256;
-    if (blocks > 148LL * 32) blocks = 148LL * 32;
+    if (blocks > (long long)sm_count() * 32) blocks = (long long)sm_count() * 32;
     edge_map_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(S, mags, n, F, T);
     return check_launch("tsr_edge_map");
 }

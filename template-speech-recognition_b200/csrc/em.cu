@@ -1,63 +1,698 @@
-// em.cu -- K4: Bernoulli-mixture EM sufficient statistics on bit-packed data
-// (bernoulli_mixture.py:263-291 E-step, :177-193 M-step; bernoulli_em.py:36-49, 103-127).
+// em.cu -- K4: Bernoulli-mixture EM on bit-packed data
+// (bernoulli_mixture.py:263-291 E-step, :177-193 M-step, :108-160 loop; bernoulli_em.py:22-49, 103-127).
 //
-// E-step:  S[n][k] = c[k] + sum_d x[n][d] * W[k][d],  W = logT - logInvT,  c[k] = sum_d logInvT[k][d]
-//          -- the same bit x bf16(hi+lo) contraction as detection with L = 1 (detect.cu), followed by
-//          a row kernel: ll = S + logw, log-sum-exp, posteriors, column sums, total log-likelihood.
-// M-step:  numer[k][d] = sum_n aff[n][k] * x[n][d], accumulated per row split in a fixed order
-//          (deterministic), then reduced; the caller all-reduces `stats` across ranks (NCCL).
+// Both contractions of an EM iteration are the same product  C[m][r] = sum_k Wq[m][k] * bit[r][k]  of an int8
+// matrix with a bit matrix, run by ONE tcgen05 kernel (bitgemm_kernel):
+//   E-step:  r = data row n, k = feature d, Wq = the 3 balanced base-256 digit planes of
+//            round((logT - logInvT) / scale[comp])                           (rows m = plane * KT + comp)
+//   M-step:  r = feature d, k = data row n (bits transposed once per data set), Wq = the 3 digit planes of
+//            round(aff * 8355711)
+// The bit rows are the UMMA *N* operand (N = 256 rows per MMA, expanded to u8 {0,1} in shared memory), the int8
+// planes the *M* operand (128 rows = up to 42 components x 3 planes; more components tile over M), so one MMA
+// carries 128 cycles of tensor work whatever the number of components.  int32 accumulation is exact, which makes
+// every sum order independent: the kernel is stream-K (each CTA owns an equal share of the (tile, chunk) space and
+// adds its partial tiles to global int32 accumulators with coalesced reductions), the sufficient statistics are
+// int64 and one integer allreduce across ranks gives bit-identical results for every rank count.
+//
+// Per iteration: bitgemm (E) -> em_posterior_kernel (soft-max, log-likelihood, posterior digit planes) ->
+// bitgemm (M) -> em_pack_kernel (int64 statistics) -> [allreduce by the caller] -> em_control_kernel (stopping rule
+// on the device) -> em_params_kernel (divide, clip, logs, weight planes of the next E-step).
+#include <math.h>
+#include <string.h>
+
 #include "common.cuh"
 
-extern "C" int tsr_prepare_filters(const float* LF, int M, int L, int D, int plane_format, void* blob, void* stream);
-extern "C" size_t tsr_filter_blob_bytes(int M, int L, int D, int plane_format);
 extern "C" int tsr_rowwords(int D);
-extern "C" int tsr_detect(const uint32_t* featbits, int B, int T, int D, int rowwords, const void* filter_blob,
-                          const float* LF_or_null, int M, int L, int plane_format, float* scores, int impl, void* stream);
-#define EM_PLANES TSR_PLANES_INT8X3
 
 namespace tsr {
 
-#define EM_MAX_K 64
-#define EM_MSPLIT 64
+#define EM_QMAX 8355711              // 127 * (1 + 256 + 65536): largest value of three balanced base-256 digits
+#define EM_KT_MAX 42                 // mixture components per 128-row M tile (3 planes each)
+#define EM_LL_SCALE 1048576.0        // 2^20: fixed-point unit of the log-likelihood in stats[K*D+K]
+#define EM_MAX_K 4095
 
-// Tensor-core M-step geometry: the transposed bit matrix XT [D][N_pad] is viewed as D*S rows of
-// N_pad/S "features" (row d*S+s = segment s of feature d's column); the posteriors become K*S
-// "templates" (template s*K+k = aff[segment s rows][k]); one detection-style contraction (L = 1,
-// INT8X3, exact int32 accumulation) yields every (row, template) product and the S useful
-// diagonal blocks are gathered into the numerators.  S only exists to spread the contraction
-// over enough CTAs; the off-diagonal work it wastes is a few percent of one E-step.
-struct EmGeom {
-    int S;
-    long long Npad, seg;
+#define BG_THREADS 448               // 14 warps: loader, 8 expanders, 4 epilogue, MMA issuer
+#define BG_NSTRIP 4                  // expanded bit strips in flight (one per expander group)
+#define BG_NW 4                      // ring of int8 weight tiles
+#define BG_STRIP_BYTES 32768         // 256 rows x 128 k-positions of u8
+#define BG_TBUF_WORDS (32 * 33)      // per-epilogue-warp transpose buffer
+
+struct EmShape {
+    int K, D, KT, Mtiles, mrows, mrp;   // mrows = 3*KT useful rows of an M tile, mrp = mrows rounded up to 8
+    long long N, Npad;                  // Npad = N rounded up to 256
+    int rwX, nchunkE, Dpad;             // words per data row, 128-feature chunks per row, D rounded up to 256
+    long long nchunkM;                  // 128-row chunks of the M-step contraction
+    size_t tile_bytes;                  // one int8 tile: 8 k-groups x mrp rows x 16 B
+    size_t off_wblob, off_c, off_scale, off_accE, off_accM, off_ablob, off_scratch, total;
 };
-static EmGeom em_geom(long long N, int D, int K) {
-    EmGeom g;
-    long long want = (2LL * 148 * 256 + D - 1) / D;      // row-steps for ~2 waves of 148 CTAs
-    int S = (int)(want < 1 ? 1 : (want > 16 ? 16 : want));
-    while (S > 1 && (long long)S * 128 > N) --S;
-    g.S = S;
-    g.Npad = ((N + (long long)S * 128 - 1) / ((long long)S * 128)) * (long long)S * 128;
-    g.seg = g.Npad / S;
-    return g;
+
+static EmShape em_shape(long long N, int D, int K) {
+    EmShape s;
+    auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    s.K = K; s.D = D; s.N = N;
+    s.KT = K < EM_KT_MAX ? K : EM_KT_MAX;
+    s.Mtiles = (K + s.KT - 1) / s.KT;
+    s.mrows = 3 * s.KT;
+    s.mrp = (s.mrows + 7) & ~7;
+    s.Npad = (N + 255) / 256 * 256;
+    s.rwX = tsr_rowwords(D);
+    s.nchunkE = (s.rwX + 3) / 4;
+    s.Dpad = (D + 255) / 256 * 256;
+    s.nchunkM = s.Npad / 128;
+    s.tile_bytes = (size_t)8 * s.mrp * 16;
+    s.off_wblob = 0;
+    s.off_c = up((size_t)s.Mtiles * s.nchunkE * s.tile_bytes);
+    s.off_scale = s.off_c + up((size_t)K * 8);
+    s.off_accE = s.off_scale + up((size_t)K * 4);
+    s.off_accM = s.off_accE + up((size_t)s.Mtiles * s.mrp * s.Npad * 4);
+    s.off_ablob = s.off_accM + up((size_t)s.Mtiles * s.mrp * s.Dpad * 4);
+    s.off_scratch = s.off_ablob + up((size_t)s.Mtiles * s.nchunkM * s.tile_bytes);
+    s.total = s.off_scratch + up((size_t)K * s.Npad * 4);
+    return s;
 }
 
-struct EmWorkspace {
-    size_t off_w, off_c, off_blob, off_scores, off_partial, off_mlf, off_mblob, off_mscores, total;
+// Device-side state of the EM loop: the stopping rule is evaluated on the device so that the host can queue
+// several iterations without reading the log-likelihood back (kernels of iterations past the stop exit at once).
+struct EmCtl {
+    int done, iterations, ntrace, mode;      // mode 0: relative change (bernoulli_mixture.py:144), 1: absolute gain (bernoulli_em.py:29)
+    int min_iter, max_iter, cap, pad;
+    double tol, ll_old;
+    // double trace[cap] follows
 };
-static EmWorkspace em_workspace(long long N, int D, int K) {
-    EmWorkspace w;
-    auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
-    const EmGeom g = em_geom(N, D, K);
-    w.off_w = 0;
-    w.off_c = up((size_t)K * D * 4);
-    w.off_blob = w.off_c + up((size_t)K * 4);
-    w.off_scores = w.off_blob + up(tsr_filter_blob_bytes(K, 1, D, EM_PLANES));
-    w.off_partial = w.off_scores + up((size_t)N * K * 4);
-    w.off_mlf = w.off_partial + up((size_t)EM_MSPLIT * K * D * 4);
-    w.off_mblob = w.off_mlf + up((size_t)K * g.Npad * 4);
-    w.off_mscores = w.off_mblob + up(tsr_filter_blob_bytes(K * g.S, 1, (int)g.seg, TSR_PLANES_INT8X3));
-    w.total = w.off_mscores + up((size_t)D * g.S * K * g.S * 4);
-    return w;
+
+// ------------------------------------------------------------------------------------------------
+// bit x int8 GEMM, stream-K.
+//   bits  [R][rw] uint32, row r, k-position order = bit order
+//   wblob [Mtiles][nchunk][8 k-groups][mrp rows][16 B]: byte b of k-group g of chunk c holds k-position
+//         128c + 32(g/2) + 8(b%4) + 4(g%2) + b/4  -- the order in which the expanders lay a 32-bit word out
+//         (word >> s) & 0x01010101 gives the four bytes of shift s with two instructions
+//   acc   [Mtiles][mrp][Rpad] int32 += products (Rpad = R rounded up to 256)
+struct BgArgs {
+    const uint32_t* bits;
+    const uint8_t* wblob;
+    int* acc;
+    long long R, Rpad;
+    int rw, nchunk, Mtiles, mrp, mrows, Rtiles;
+    const int* done;
+};
+
+// A CTA's share of the flattened (R tile, M tile, chunk) space, cut into segments at tile borders.
+struct BgWalk {
+    long long pos, end, tile;
+    int c, nchunk, Mtiles;
+    __device__ BgWalk(const BgArgs& A) {
+        const long long total = (long long)A.Rtiles * A.Mtiles * A.nchunk;
+        pos = total * blockIdx.x / gridDim.x;
+        end = total * (blockIdx.x + 1) / gridDim.x;
+        nchunk = A.nchunk; Mtiles = A.Mtiles;
+        tile = pos / nchunk;
+        c = (int)(pos - tile * nchunk);
+    }
+    // next segment: chunks [c0, c0 + n) of tile (rt, mt)
+    __device__ bool next_seg(int& rt, int& mt, int& c0, int& n) {
+        if (pos >= end) return false;
+        rt = (int)(tile / Mtiles); mt = (int)(tile - (long long)rt * Mtiles);
+        c0 = c;
+        long long len = nchunk - c;
+        if (len > end - pos) len = end - pos;
+        n = (int)len;
+        pos += len; c += n;
+        if (c == nchunk) { c = 0; ++tile; }
+        return true;
+    }
+};
+
+__device__ __forceinline__ void umma_i8_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+__global__ void __launch_bounds__(BG_THREADS, 1) bitgemm_kernel(BgArgs A) {
+    if (A.done && *A.done) return;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const uint32_t tile_bytes = 8u * (uint32_t)A.mrp * 16u;
+    uint8_t* wring = smem;                                            // BG_NW weight tiles; the M = 128 descriptors read past a
+    uint8_t* strips = smem + BG_NW * tile_bytes;                      // short tile into what follows (harmless: rows >= mrows unused)
+    int* tbuf = reinterpret_cast<int*>(strips + BG_NSTRIP * BG_STRIP_BYTES);
+    uint64_t* wfull = reinterpret_cast<uint64_t*>(tbuf + 4 * BG_TBUF_WORDS);
+    uint64_t* wempty = wfull + BG_NW;
+    uint64_t* afull = wempty + BG_NW;
+    uint64_t* aempty = afull + BG_NSTRIP;
+    uint64_t* tfull = aempty + BG_NSTRIP;
+    uint64_t* tempty = tfull + 2;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty + 2);
+
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < BG_NW; ++s) { mbar_init(&wfull[s], 1); mbar_init(&wempty[s], 1); }
+        for (int s = 0; s < BG_NSTRIP; ++s) { mbar_init(&afull[s], 64); mbar_init(&aempty[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 128); }
+        mbar_fence_init();
+    }
+    if (warp == 13) tmem_alloc<512>(tmem_ptr);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0) {
+        // ================================ weight-tile loader ================================
+        if (lane == 0) {
+            BgWalk w(A);
+            int rt, mt, c0, n, stage = 0;
+            uint32_t ph = 0;
+            while (w.next_seg(rt, mt, c0, n)) {
+                const uint8_t* src = A.wblob + ((size_t)mt * A.nchunk + c0) * tile_bytes;
+                for (int i = 0; i < n; ++i) {
+                    mbar_wait_relaxed(&wempty[stage], ph ^ 1);
+                    mbar_arrive_expect_tx(&wfull[stage], tile_bytes);
+                    bulk_g2s(wring + stage * tile_bytes, src + (size_t)i * tile_bytes, tile_bytes, &wfull[stage]);
+                    if (++stage == BG_NW) { stage = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp >= 1 && warp <= 8) {
+        // ================================== bit expanders ==================================
+        // Four groups of 64 threads; group g fills strip buffer g with every fourth chunk (a thread expands four of
+        // the strip's 256 rows).  The wait -> expand -> proxy fence -> arrive chain of one strip is mostly latency;
+        // four strips in flight hide it behind the 512 cycles the MMAs spend on a chunk.  The next chunk's words are
+        // fetched before the wait.
+        const int g = (warp - 1) >> 1;
+        const int tg = (threadIdx.x - 32) & 63;
+        BgWalk w(A);
+        int rt = 0, mt, c0 = 0, n = 0, i = 0;
+        uint32_t ic = 0;
+        // advance to the next chunk this group owns; returns false at the end of the CTA's share
+        auto advance = [&](int& o_rt, int& o_c) -> bool {
+            for (;;) {
+                if (i == n) {
+                    if (!w.next_seg(rt, mt, c0, n)) return false;
+                    i = 0;
+                }
+                const bool mine = (int)(ic & 3) == g;
+                o_rt = rt; o_c = c0 + i;
+                ++i; ++ic;
+                if (mine) return true;
+            }
+        };
+        auto load = [&](int l_rt, int l_c, uint4 (&x)[4]) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const long long row = (long long)l_rt * 256 + tg + 64 * k;
+                uint2 lo = make_uint2(0u, 0u), hi = make_uint2(0u, 0u);
+                if (row < A.R) {
+                    const uint2* p = reinterpret_cast<const uint2*>(A.bits + row * A.rw + 4 * l_c);
+                    lo = __ldg(p);
+                    if (4 * l_c + 2 < A.rw) hi = __ldg(p + 1);
+                }
+                x[k] = make_uint4(lo.x, lo.y, hi.x, hi.y);
+            }
+        };
+        uint4 x[4], y[4];
+        int crt, cc;
+        bool ok = advance(crt, cc);
+        if (ok) load(crt, cc, x);
+        uint32_t use = 0;
+        uint8_t* strip = strips + g * BG_STRIP_BYTES;
+        while (ok) {
+            int nrt, nc;
+            const bool ok2 = advance(nrt, nc);
+            if (ok2) load(nrt, nc, y);
+            mbar_wait_relaxed(&aempty[g], (use & 1) ^ 1);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                uint8_t* dst = strip + (tg + 64 * k) * 16;
+                const uint32_t wv[4] = {x[k].x, x[k].y, x[k].z, x[k].w};
+#pragma unroll
+                for (int wi = 0; wi < 4; ++wi) {
+                    const uint32_t v = wv[wi];
+                    const uint4 a = make_uint4(v & 0x01010101u, (v >> 1) & 0x01010101u, (v >> 2) & 0x01010101u, (v >> 3) & 0x01010101u);
+                    const uint4 b = make_uint4((v >> 4) & 0x01010101u, (v >> 5) & 0x01010101u, (v >> 6) & 0x01010101u, (v >> 7) & 0x01010101u);
+                    *reinterpret_cast<uint4*>(dst + (2 * wi) * 4096) = a;
+                    *reinterpret_cast<uint4*>(dst + (2 * wi + 1) * 4096) = b;
+                }
+            }
+            fence_proxy_async_smem();
+            mbar_arrive(&afull[g]);
+            ++use;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) x[k] = y[k];
+            ok = ok2;
+        }
+    } else if (warp == 13) {
+        // ==================================== MMA issuer ====================================
+        // M = 128 (int8 planes, signed) x N = 256 (bit rows, unsigned) x K = 32, S32 accumulate
+        const uint32_t idesc = (2u << 4) | (1u << 7) | (0u << 10) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        const uint32_t desc_hi = (uint32_t)(128 >> 4) | (1u << 14);                                 // SBO = 128 B, version 1
+        const uint64_t a_hi = ((uint64_t)desc_hi << 32) | ((uint64_t)((uint32_t)(A.mrp * 16) >> 4) << 16);   // LBO = k-group stride of a weight tile
+        const uint64_t b_hi = ((uint64_t)desc_hi << 32) | ((uint64_t)(4096 >> 4) << 16);                     // LBO = k-group stride of a strip
+        const uint32_t kstep_a = (uint32_t)(2 * A.mrp * 16) >> 4, kstep_b = (uint32_t)(2 * 4096) >> 4;
+        BgWalk w(A);
+        int rt, mt, c0, n, stage = 0;
+        uint32_t ph = 0, ic = 0, seg = 0;
+        while (w.next_seg(rt, mt, c0, n)) {
+            const uint32_t accb = seg & 1;
+            mbar_wait(&tempty[accb], ((seg >> 1) & 1) ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + accb * 256;
+            for (int i = 0; i < n; ++i, ++ic) {
+                const uint32_t buf = ic & 3;
+                mbar_wait(&afull[buf], (ic >> 2) & 1);
+                mbar_wait(&wfull[stage], ph);
+                tc_fence_after();
+                const uint32_t abase = smem_u32(wring + stage * tile_bytes) >> 4;
+                const uint32_t bbase = smem_u32(strips + buf * BG_STRIP_BYTES) >> 4;
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    umma_i8_ss(d_tmem, a_hi | (uint64_t)(abase + j * kstep_a), b_hi | (uint64_t)(bbase + j * kstep_b), idesc,
+                               (i | j) != 0 ? 1u : 0u);
+                umma_commit_elect(&aempty[buf]);
+                umma_commit_elect(&wempty[stage]);
+                if (++stage == BG_NW) { stage = 0; ph ^= 1; }
+            }
+            umma_commit_elect(&tfull[accb]);
+            ++seg;
+        }
+    } else if (warp >= 9 && warp <= 12) {
+        // ===================================== epilogue =====================================
+        // TMEM lane = row m of the tile, column = bit row r.  A warp transposes 32 x 32 blocks through its private
+        // shared-memory buffer so that one reduction instruction adds 32 consecutive r of one m (128 contiguous bytes).
+        const int quad = warp & 3;
+        int* tb = tbuf + (warp - 9) * BG_TBUF_WORDS;
+        int live = A.mrows - quad * 32;                     // rows of this quadrant that carry data
+        if (live > 32) live = 32;
+        BgWalk w(A);
+        int rt, mt, c0, n;
+        uint32_t seg = 0;
+        while (w.next_seg(rt, mt, c0, n)) {
+            const uint32_t accb = seg & 1;
+            mbar_wait_relaxed(&tfull[accb], (seg >> 1) & 1);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + accb * 256 + ((uint32_t)(quad * 32) << 16);
+            int* out = A.acc + ((size_t)mt * A.mrp + quad * 32) * A.Rpad + (size_t)rt * 256 + lane;
+            for (int cb = 0; cb < 8; ++cb) {
+                uint32_t v[32];
+                if (live > 0) {
+                    tmem_ld32(taddr + cb * 32, v);
+                    tmem_ld_wait();
+                }
+                if (cb == 7) {                              // accumulator read: hand it back to the MMA warp
+                    tc_fence_before();
+                    mbar_arrive(&tempty[accb]);
+                }
+                if (live > 0) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) tb[i * 33 + lane] = (int)v[i];
+                    __syncwarp();
+                    for (int mi = 0; mi < live; ++mi) {
+                        const int val = tb[lane * 33 + mi];
+                        if (val != 0) atomicAdd(out + (size_t)mi * A.Rpad + cb * 32, val);
+                    }
+                    __syncwarp();
+                }
+            }
+            ++seg;
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 13) {
+        tc_fence_after();
+        tmem_dealloc<512>(tmem_base);
+    }
+}
+
+static size_t bitgemm_smem(int mrp) {
+    return (size_t)BG_NW * 8 * mrp * 16 + (size_t)BG_NSTRIP * BG_STRIP_BYTES + 4 * BG_TBUF_WORDS * 4 + 256;
+}
+
+static int launch_bitgemm(const uint32_t* bits, long long R, int rw, const uint8_t* wblob, int* acc, long long Rpad, int nchunk,
+                          const EmShape& s, const int* done, cudaStream_t st) {
+    BgArgs A;
+    A.bits = bits; A.wblob = wblob; A.acc = acc; A.R = R; A.Rpad = Rpad; A.rw = rw; A.nchunk = nchunk;
+    A.Mtiles = s.Mtiles; A.mrp = s.mrp; A.mrows = s.mrows; A.Rtiles = (int)(Rpad / 256); A.done = done;
+    const size_t smem = bitgemm_smem(s.mrp);
+    static bool attr_set = false;
+    if (!attr_set) {
+        TSR_CUDA(cudaFuncSetAttribute(bitgemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_set = true;
+    }
+    const long long total = (long long)A.Rtiles * A.Mtiles * nchunk;
+    const int nsm = sm_count();
+    const int grid = (int)(total < nsm ? total : nsm);
+    if (grid < 1) return TSR_OK;
+    bitgemm_kernel<<<grid, BG_THREADS, smem, st>>>(A);
+    return check_launch("bitgemm_kernel");
+}
+
+// ------------------------------------------------------------------------------------------------
+// SIMT cross-checks (impl = TSR_IMPL_SIMT): sequential fp32 adds of the set bits' weights, the reference's
+// arithmetic for the scores; exact integer sums of the quantised posteriors for the numerators.
+__global__ void em_scores_simt_kernel(const uint32_t* __restrict__ X, long long N, int D, int rw, int K,
+                                      const float* __restrict__ logT, const float* __restrict__ logInvT,
+                                      const double* __restrict__ c, float* __restrict__ scratch, long long Npad, const int* done) {
+    if (done && *done) return;
+    const long long total = N * K;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int k = (int)(i / N);
+        const long long n = i - (long long)k * N;
+        const uint32_t* row = X + n * rw;
+        const float* lt = logT + (size_t)k * D;
+        const float* li = logInvT + (size_t)k * D;
+        float acc = 0.f;
+        for (int wi = 0; wi < rw; ++wi) {
+            uint32_t x = row[wi];
+            while (x) {
+                const int d = wi * 32 + __ffs(x) - 1;
+                x &= x - 1;
+                acc = __fadd_rn(acc, __fsub_rn(lt[d], li[d]));
+            }
+        }
+        scratch[(size_t)k * Npad + n] = (float)((double)acc + c[k]);
+    }
+}
+
+__global__ void em_mstep_simt_kernel(const uint32_t* __restrict__ X, long long N, int D, int rw, int K,
+                                     const float* __restrict__ aff, long long* __restrict__ stats, const int* done) {
+    if (done && *done) return;
+    const long long total = (long long)K * D;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int k = (int)(i / D), d = (int)(i - (long long)k * D);
+        long long acc = 0;
+        for (long long n = 0; n < N; ++n)
+            if ((X[n * rw + (d >> 5)] >> (d & 31)) & 1u) acc += (long long)rintf(fminf(fmaxf(aff[n * K + k], 0.f), 1.f) * (float)EM_QMAX);
+        stats[i] = acc;
+    }
+    // responsibility sums of the given posteriors
+    for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < K; k += (long long)gridDim.x * blockDim.x) {
+        long long acc = 0;
+        for (long long n = 0; n < N; ++n) acc += (long long)rintf(fminf(fmaxf(aff[n * K + k], 0.f), 1.f) * (float)EM_QMAX);
+        stats[total + k] = acc;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Parameters -> E-step operand.  One CTA per component k.
+//   FROM_STATS: the M-step proper (bernoulli_mixture.py:177-193): weights = resp / N, T = numer / N / weights,
+//   clipped to [min_prob, 1 - min_prob], logs in float32.
+//   Both: W = logT - logInvT, scale[k] = max|W| / EM_QMAX, c[k] = sum_d logInvT (double, fixed order), then the three
+//   balanced base-256 digits of round(W / scale) in the bitgemm tile order.
+struct ParamArgs {
+    const long long* stats;     // FROM_STATS
+    long long N_total;
+    float min_prob;
+    float *templates, *logT, *logInvT, *weights, *logw;   // FROM_STATS: written; else logT / logInvT are read
+    int D, K, KT, mrp, nchunk;
+    uint8_t* wblob;             // may be null (parameters only)
+    double* c;
+    float* scale;
+    const int* done;
+};
+
+template <bool FROM_STATS>
+__global__ void __launch_bounds__(256) em_params_kernel(ParamArgs P) {
+    if (P.done && *P.done) return;
+    __shared__ float s_mx[256];
+    __shared__ double s_c[256];
+    __shared__ float s_scale;
+    const int k = blockIdx.x, tid = threadIdx.x;
+    const size_t row = (size_t)k * P.D;
+    float w = 0.f;
+    if (FROM_STATS) w = (float)((double)P.stats[(size_t)P.K * P.D + k] / (double)EM_QMAX) / (float)P.N_total;   // np.mean(affinities, 0)
+    float mx = 0.f;
+    double csum = 0.0;
+    for (int d = tid; d < P.D; d += 256) {
+        float lt, li;
+        if (FROM_STATS) {
+            float t = (float)((double)P.stats[row + d] / (double)EM_QMAX);     // np.dot(affinities.T, data)
+            t = t / (float)P.N_total;                                          // /= num_data
+            t = t / w;                                                         // /= weights
+            t = fminf(fmaxf(t, P.min_prob), 1.f - P.min_prob);                 // threshold_templates
+            lt = logf(t); li = logf(1.f - t);
+            P.templates[row + d] = t; P.logT[row + d] = lt; P.logInvT[row + d] = li;
+        } else {
+            lt = P.logT[row + d]; li = P.logInvT[row + d];
+        }
+        mx = fmaxf(mx, fabsf(lt - li));
+        csum += (double)li;
+    }
+    s_mx[tid] = mx; s_c[tid] = csum;
+    __syncthreads();
+    for (int off = 128; off > 0; off >>= 1) {
+        if (tid < off) { s_mx[tid] = fmaxf(s_mx[tid], s_mx[tid + off]); s_c[tid] += s_c[tid + off]; }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        const float sc = s_mx[0] > 0.f ? s_mx[0] / (float)EM_QMAX : 1.f;
+        s_scale = sc;
+        if (P.scale) P.scale[k] = sc;
+        if (P.c) P.c[k] = s_c[0];
+        if (FROM_STATS) { P.weights[k] = w; P.logw[k] = logf(w); }
+    }
+    __syncthreads();
+    if (!P.wblob) return;
+    const float sc = s_scale;
+    const int mt = k / P.KT, kl = k - mt * P.KT;
+    // one thread per 32-feature word: 2 k-groups x 3 planes x 16 bytes
+    for (int it = tid; it < P.nchunk * 4; it += 256) {
+        const int c = it >> 2, wi = it & 3;
+        const int d0 = c * 128 + wi * 32;
+        uint32_t out[3][2][4];
+#pragma unroll
+        for (int p = 0; p < 3; ++p)
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) out[p][h][q] = 0u;
+#pragma unroll
+        for (int s = 0; s < 8; ++s)
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+                const int d = d0 + 8 * jj + s;
+                int q = 0;
+                if (d < P.D) {
+                    // the stores of this block above are visible after the barrier
+                    const float wv = P.logT[row + d] - P.logInvT[row + d];
+                    float qf = rintf(wv / sc);
+                    qf = fminf(fmaxf(qf, -(float)EM_QMAX), (float)EM_QMAX);
+                    q = (int)qf;
+                }
+#pragma unroll
+                for (int p = 0; p < 3; ++p) {
+                    const int digit = ((q + 128) & 255) - 128;
+                    q = (q - digit) >> 8;
+                    out[p][s >> 2][s & 3] |= (uint32_t)(digit & 255) << (8 * jj);
+                }
+            }
+        uint8_t* tile = P.wblob + ((size_t)mt * P.nchunk + c) * ((size_t)8 * P.mrp * 16);
+#pragma unroll
+        for (int p = 0; p < 3; ++p)
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+                *reinterpret_cast<uint4*>(tile + ((size_t)(2 * wi + h) * P.mrp + p * P.KT + kl) * 16) =
+                    make_uint4(out[p][h][0], out[p][h][1], out[p][h][2], out[p][h][3]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Posterior digit planes of 128 consecutive rows -> one M-step operand tile per M tile.  Position of row n in its
+// 128-row chunk: word i = (n % 128) / 32, r = n % 32 = 8 jj + s  ->  k-group 2i + s/4, byte 4 (s%4) + jj.
+__device__ __forceinline__ int em_tile_pos(int t /* 0..127 */) {
+    const int i = t >> 5, r = t & 31, s = r & 7, jj = r >> 3;
+    return ((2 * i + (s >> 2)) << 4) | (4 * (s & 3) + jj);        // (k-group << 4) | byte
+}
+
+// Row kernel of the E-step.  CTA = 128 consecutive rows (one chunk of the M-step contraction), thread = row.
+//   INT_SCORES: scores from the int32 digit-plane accumulators (which are cleared for the next E-step);
+//   otherwise scratch already holds float scores [K][Npad] (SIMT cross-check).
+struct PostArgs {
+    int* accE;
+    float* scratch;             // [K][Npad] float scores of the SIMT cross-check kernel
+    const double* c;
+    const float* scale;
+    const float* logw;
+    long long N, Npad;
+    int K, KT, Mtiles, mrp;
+    float* aff;                 // [N][K] or null
+    float* scores_out;          // [N][K] or null
+    uint8_t* ablob;             // [Mtiles][nchunkM][8][mrp][16] or null
+    long long* stats_resp;      // [K] += sum_n q, or null
+    long long* stats_ll;        // [1] += sum_n ll * 2^20, or null
+    int hard, update;
+    const int* done;
+};
+
+template <bool INT_SCORES>
+__global__ void __launch_bounds__(128) em_posterior_kernel(PostArgs P) {
+    if (P.done && *P.done) return;
+    extern __shared__ __align__(16) uint8_t psm[];
+    uint8_t* tile = psm;                                              // 8 * mrp * 16 bytes
+    int* s_resp = reinterpret_cast<int*>(psm + (size_t)8 * P.mrp * 16);   // [K]
+    __shared__ long long s_ll;
+    const int tid = threadIdx.x;
+    const long long n = blockIdx.x * 128LL + tid;
+    const bool live = n < P.N;
+    for (int k = tid; k < P.K; k += 128) s_resp[k] = 0;
+    if (tid == 0) s_ll = 0;
+    __syncthreads();
+    const size_t pstride = (size_t)P.KT * P.Npad;
+    // template score of component k in double: exact integer digit-plane sums, one scaling (or the SIMT kernel's
+    // float score); `clear` zeroes the accumulators behind the last read so that the next E-step starts from zero
+    auto score = [&](int k, bool clear) -> double {
+        if (INT_SCORES) {
+            const int mt = k / P.KT, kl = k - mt * P.KT;
+            int* a = P.accE + ((size_t)mt * P.mrp + kl) * P.Npad + n;
+            const int a0 = a[0], a1 = a[pstride], a2 = a[2 * pstride];
+            if (clear) { a[0] = 0; a[pstride] = 0; a[2 * pstride] = 0; }
+            const double q = (double)a0 + 256.0 * (double)a1 + 65536.0 * (double)a2;
+            return q * (double)P.scale[k] + P.c[k];
+        }
+        return (double)P.scratch[(size_t)k * P.Npad + n];
+    };
+    // pass 1: scores out, running maxima (soft-max in double up to the exponent: the posteriors then carry the
+    // weight quantisation only, ~1e-6, instead of the 3e-5 a float32 score of magnitude 500 would add)
+    double mx = -INFINITY, smx = -INFINITY;
+    int arg = 0;
+    for (int k = 0; k < P.K; ++k) {
+        const double s = score(k, !P.update);
+        if (live && P.scores_out) P.scores_out[n * P.K + k] = (float)s;
+        if (s > smx) { smx = s; arg = k; }                  // hard assignment: first arg-max of the template scores (:273-275)
+        const double v = s + (double)P.logw[k];
+        mx = fmax(mx, v);
+    }
+    if (!P.update) return;
+    // pass 2: log-sum-exp (:269-270)
+    double sum = 0.0;
+    for (int k = 0; k < P.K; ++k) sum += (double)expf((float)(score(k, false) + (double)P.logw[k] - mx));
+    const float inv = (float)(1.0 / sum);
+    long long my_ll = live ? llrint((log(sum) + mx) * EM_LL_SCALE) : 0;
+    // pass 3: posteriors, their digit planes, responsibility sums
+    const int pos = em_tile_pos(tid);
+    const size_t tile_bytes = (size_t)8 * P.mrp * 16;
+    for (int mt = 0; mt < P.Mtiles; ++mt) {
+        for (int i = tid; i < (int)(tile_bytes / 16); i += 128) reinterpret_cast<uint4*>(tile)[i] = make_uint4(0u, 0u, 0u, 0u);
+        __syncthreads();
+        const int k1 = (mt + 1) * P.KT < P.K ? (mt + 1) * P.KT : P.K;
+        for (int k = mt * P.KT; k < k1; ++k) {
+            const double v = score(k, true) + (double)P.logw[k];
+            float p = 0.f;
+            if (live) p = P.hard ? (k == arg ? 1.f : 0.f) : expf((float)(v - mx)) * inv;
+            if (live && P.aff) P.aff[n * P.K + k] = p;
+            int q = (int)rintf(fminf(p, 1.f) * (float)EM_QMAX);
+            const int qsum = __reduce_add_sync(0xffffffffu, q);
+            if ((tid & 31) == 0 && qsum) atomicAdd(&s_resp[k], qsum);
+            const int kl = k - mt * P.KT;
+#pragma unroll
+            for (int pl = 0; pl < 3; ++pl) {
+                const int digit = ((q + 128) & 255) - 128;
+                q = (q - digit) >> 8;
+                tile[((size_t)(pos >> 4) * P.mrp + pl * P.KT + kl) * 16 + (pos & 15)] = (uint8_t)(digit & 255);
+            }
+        }
+        __syncthreads();
+        if (P.ablob) {
+            uint4* dst = reinterpret_cast<uint4*>(P.ablob + ((size_t)mt * (P.Npad / 128) + blockIdx.x) * tile_bytes);
+            for (int i = tid; i < (int)(tile_bytes / 16); i += 128) dst[i] = reinterpret_cast<const uint4*>(tile)[i];
+        }
+        __syncthreads();
+    }
+    for (int off = 16; off > 0; off >>= 1) my_ll += __shfl_xor_sync(0xffffffffu, my_ll, off);
+    if ((tid & 31) == 0) atomicAdd(reinterpret_cast<unsigned long long*>(&s_ll), (unsigned long long)my_ll);
+    __syncthreads();
+    if (P.stats_resp)
+        for (int k = tid; k < P.K; k += 128)
+            if (s_resp[k]) atomicAdd(reinterpret_cast<unsigned long long*>(P.stats_resp + k), (unsigned long long)(long long)s_resp[k]);
+    if (tid == 0 && P.stats_ll) atomicAdd(reinterpret_cast<unsigned long long*>(P.stats_ll), (unsigned long long)s_ll);
+}
+
+// Posterior digit planes from caller-supplied affinities (initialisation; M-step from given posteriors)
+__global__ void __launch_bounds__(128) em_aff_planes_kernel(const float* __restrict__ aff, long long N, long long Npad, int K, int KT,
+                                                            int Mtiles, int mrp, uint8_t* __restrict__ ablob,
+                                                            long long* __restrict__ stats_resp, const int* done) {
+    if (done && *done) return;
+    extern __shared__ __align__(16) uint8_t psm[];
+    uint8_t* tile = psm;
+    int* s_resp = reinterpret_cast<int*>(psm + (size_t)8 * mrp * 16);
+    const int tid = threadIdx.x;
+    const long long n = blockIdx.x * 128LL + tid;
+    const bool live = n < N;
+    for (int k = tid; k < K; k += 128) s_resp[k] = 0;
+    const int pos = em_tile_pos(tid);
+    const size_t tile_bytes = (size_t)8 * mrp * 16;
+    for (int mt = 0; mt < Mtiles; ++mt) {
+        for (int i = tid; i < (int)(tile_bytes / 16); i += 128) reinterpret_cast<uint4*>(tile)[i] = make_uint4(0u, 0u, 0u, 0u);
+        __syncthreads();
+        const int k1 = (mt + 1) * KT < K ? (mt + 1) * KT : K;
+        for (int k = mt * KT; k < k1; ++k) {
+            const float p = live ? fminf(fmaxf(aff[n * K + k], 0.f), 1.f) : 0.f;
+            int q = (int)rintf(p * (float)EM_QMAX);
+            const int qsum = __reduce_add_sync(0xffffffffu, q);
+            if ((tid & 31) == 0 && qsum) atomicAdd(&s_resp[k], qsum);
+            const int kl = k - mt * KT;
+#pragma unroll
+            for (int pl = 0; pl < 3; ++pl) {
+                const int digit = ((q + 128) & 255) - 128;
+                q = (q - digit) >> 8;
+                tile[((size_t)(pos >> 4) * mrp + pl * KT + kl) * 16 + (pos & 15)] = (uint8_t)(digit & 255);
+            }
+        }
+        __syncthreads();
+        uint4* dst = reinterpret_cast<uint4*>(ablob + ((size_t)mt * (Npad / 128) + blockIdx.x) * tile_bytes);
+        for (int i = tid; i < (int)(tile_bytes / 16); i += 128) dst[i] = reinterpret_cast<const uint4*>(tile)[i];
+        __syncthreads();
+    }
+    if (stats_resp)
+        for (int k = tid; k < K; k += 128)
+            if (s_resp[k]) atomicAdd(reinterpret_cast<unsigned long long*>(stats_resp + k), (unsigned long long)(long long)s_resp[k]);
+}
+
+// int32 digit-plane accumulators of the M-step -> int64 numerators (units of 1 / EM_QMAX); clears the accumulators
+__global__ void em_pack_kernel(int* __restrict__ accM, int D, int Dpad, int K, int KT, int mrp, long long* __restrict__ stats,
+                               const int* done) {
+    if (done && *done) return;
+    const long long total = (long long)K * D;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int k = (int)(i / D), d = (int)(i - (long long)k * D);
+        const int mt = k / KT, kl = k - mt * KT;
+        int* a = accM + ((size_t)mt * mrp + kl) * Dpad + d;
+        const size_t ps = (size_t)KT * Dpad;
+        const long long q = (long long)a[0] + 256LL * (long long)a[ps] + 65536LL * (long long)a[2 * ps];
+        a[0] = 0; a[ps] = 0; a[2 * ps] = 0;
+        stats[i] = q;
+    }
+}
+
+__global__ void em_zero_tail_kernel(long long* stats, int K, long long KD, const int* done) {
+    if (done && *done) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i <= K) stats[KD + i] = 0;
+}
+
+// Stopping rule, evaluated on the (all-reduced) log-likelihood.  Mirrors the host loops
+//   while (abs((old - new) / old) > tol and it < max_iter) or it < min_iter      (bernoulli_mixture.py:139-156)
+//   while new - old > tol                                                          (bernoulli_em.py:24-33)
+__global__ void em_control_kernel(EmCtl* ctl, const long long* stats_ll) {
+    if (ctl->done) return;
+    double* trace = reinterpret_cast<double*>(ctl + 1);
+    const double ll = (double)*stats_ll / EM_LL_SCALE;
+    if (ctl->ntrace == 0) ctl->ll_old = ctl->mode == 0 ? ll / (1.0 - ctl->tol) - 10.0 : -INFINITY;
+    if (ctl->ntrace < ctl->cap) trace[ctl->ntrace] = ll;
+    ctl->ntrace++;
+    bool go;
+    if (ctl->mode == 0)
+        go = (fabs((ctl->ll_old - ll) / ctl->ll_old) > ctl->tol && ctl->iterations < ctl->max_iter) || ctl->iterations < ctl->min_iter;
+    else
+        go = (ll - ctl->ll_old > ctl->tol) && ctl->iterations < ctl->max_iter;
+    if (!go) { ctl->done = 1; return; }
+    ctl->ll_old = ll;
+    ctl->iterations++;
 }
 
 // XT[d][n] = X[n][d]: each warp transposes a 32x32 bit block with 32 ballots.
@@ -84,163 +719,6 @@ __global__ void transpose_bits_kernel(const uint32_t* __restrict__ X, long long 
     }
 }
 
-// LF[(s*K + k)][n'] = aff[s*seg + n'][k]  (zero beyond N)
-__global__ void em_aff_to_filters_kernel(const float* __restrict__ aff, long long N, int K, int S, long long seg,
-                                         float* __restrict__ LF) {
-    const long long total = (long long)K * S * seg;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const long long np = i % seg;
-        const long long m = i / seg;
-        const int sidx = (int)(m / K), k = (int)(m - (long long)sidx * K);
-        const long long n = sidx * seg + np;
-        LF[i] = n < N ? aff[n * K + k] : 0.f;
-    }
-}
-
-// numer[k][d] += sum_s scores[(d*S + s)][(s*K + k)]
-__global__ void em_gather_numer_kernel(const float* __restrict__ scores, int D, int K, int S, float* __restrict__ numer) {
-    const long long total = (long long)K * D;
-    const int M = K * S;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int k = (int)(i / D), d = (int)(i - (long long)k * D);
-        float acc = 0.f;
-        for (int sidx = 0; sidx < S; ++sidx) acc += scores[((size_t)d * S + sidx) * M + (size_t)sidx * K + k];
-        numer[i] += acc;
-    }
-}
-
-// W = logT - logInvT (one thread per element); c[k] by one warp per component, fixed order.
-__global__ void em_weights_kernel(const float* __restrict__ logT, const float* __restrict__ logInvT,
-                                  float* __restrict__ W, float* __restrict__ c, int K, int D) {
-    const long long n = (long long)K * D;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-        W[i] = logT[i] - logInvT[i];
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (warp < K) {
-        double acc = 0.0;
-        for (int d = lane; d < D; d += 32) acc += (double)logInvT[(size_t)warp * D + d];
-        for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
-        if (lane == 0) c[warp] = (float)acc;
-    }
-}
-
-// One thread per row: ll_k = S_k + c_k + logw_k; max, sum-exp, posteriors.  Block-level reduction
-// of the column sums and of the log-likelihood, one atomicAdd per block per value.
-__global__ void __launch_bounds__(256) em_posterior_kernel(const float* __restrict__ S, const float* __restrict__ c,
-                                                           const float* __restrict__ logw, long long N, int K,
-                                                           float* __restrict__ aff, float* __restrict__ scores_out,
-                                                           float* __restrict__ respsum, double* __restrict__ ll_out,
-                                                           int hard) {
-    __shared__ float s_resp[EM_MAX_K];
-    __shared__ double s_ll;
-    if (threadIdx.x < EM_MAX_K) s_resp[threadIdx.x] = 0.f;
-    if (threadIdx.x == 0) s_ll = 0.0;
-    __syncthreads();
-    const long long n = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    float a[EM_MAX_K];
-    double my_ll = 0.0;
-    if (n < N) {
-        float mx = -INFINITY, smx = -INFINITY;
-        int arg = 0;
-#pragma unroll 4
-        for (int k = 0; k < K; ++k) {
-            float s = S[n * K + k] + c[k];
-            if (scores_out) scores_out[n * K + k] = s;
-            if (s > smx) { smx = s; arg = k; }          // hard assignment: argmax of the template scores (:273-275)
-            float v = s + logw[k];
-            a[k] = v;
-            mx = fmaxf(mx, v);
-        }
-        float sum = 0.f;
-        for (int k = 0; k < K; ++k) { a[k] = expf(a[k] - mx); sum += a[k]; }
-        my_ll = (double)logf(sum) + (double)mx;            // :269-270
-        const float inv = 1.f / sum;
-        for (int k = 0; k < K; ++k) {
-            float p = hard ? (k == arg ? 1.f : 0.f) : a[k] * inv;
-            aff[n * K + k] = p;
-            a[k] = p;
-        }
-    }
-    // block reduction: warp shuffles then shared atomics (<= 8 warps per block)
-    for (int k = 0; k < K; ++k) {
-        float v = n < N ? a[k] : 0.f;
-        for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
-        if ((threadIdx.x & 31) == 0) atomicAdd(&s_resp[k], v);
-    }
-    for (int off = 16; off > 0; off >>= 1) my_ll += __shfl_xor_sync(0xffffffffu, my_ll, off);
-    if ((threadIdx.x & 31) == 0) atomicAdd(&s_ll, my_ll);
-    __syncthreads();
-    if (threadIdx.x < K) atomicAdd(&respsum[threadIdx.x], s_resp[threadIdx.x]);
-    if (threadIdx.x == 0) atomicAdd(ll_out, s_ll);
-}
-
-// M-step partials.  CTA = (group of 8 feature words = one 32-byte sector per row, row split);
-// warp w owns word 8*gx + w, lane = feature bit, and walks the split's rows in order adding the
-// row's K posteriors where its bit is set.  partial[split][k][d].
-__global__ void __launch_bounds__(256) em_mstep_partial_kernel(const uint32_t* __restrict__ X, const float* __restrict__ aff,
-                                                               long long N, int D, int rowwords, int K,
-                                                               float* __restrict__ partial) {
-    __shared__ float s_aff[128 * EM_MAX_K];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int word = blockIdx.x * 8 + warp;
-    const int split = blockIdx.y;
-    const long long rows_per = (N + gridDim.y - 1) / gridDim.y;
-    const long long n0 = split * rows_per;
-    long long n1 = n0 + rows_per; if (n1 > N) n1 = N;
-    float acc[EM_MAX_K];
-#pragma unroll
-    for (int k = 0; k < EM_MAX_K; ++k) acc[k] = 0.f;
-    for (long long nb = n0; nb < n1; nb += 128) {
-        const int cnt = (int)((n1 - nb) < 128 ? (n1 - nb) : 128);
-        __syncthreads();
-        for (int i = threadIdx.x; i < cnt * K; i += blockDim.x) s_aff[i] = aff[nb * K + i];
-        __syncthreads();
-        if (word < rowwords) {
-            for (int r = 0; r < cnt; ++r) {
-                const uint32_t x = __ldg(X + (nb + r) * rowwords + word);
-                if ((x >> lane) & 1u) {
-#pragma unroll
-                    for (int k = 0; k < EM_MAX_K; ++k)
-                        if (k < K) acc[k] += s_aff[r * K + k];
-                }
-            }
-        }
-    }
-    const int d = word * 32 + lane;
-    if (word < rowwords && d < D) {
-#pragma unroll
-        for (int k = 0; k < EM_MAX_K; ++k)
-            if (k < K) partial[((size_t)split * K + k) * D + d] = acc[k];
-    }
-}
-
-__global__ void em_mstep_reduce_kernel(const float* __restrict__ partial, int nsplit, int K, int D, float* __restrict__ numer) {
-    const long long n = (long long)K * D;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        float s = 0.f;
-        for (int sp = 0; sp < nsplit; ++sp) s += partial[(size_t)sp * n + i];
-        numer[i] += s;
-    }
-}
-
-__global__ void em_finalize_kernel(const float* __restrict__ stats, long long N_total, int D, int K, float min_prob,
-                                   float* __restrict__ templates, float* __restrict__ logT, float* __restrict__ logInvT,
-                                   float* __restrict__ weights, float* __restrict__ logw) {
-    const long long n = (long long)K * D;
-    const float* respsum = stats + n;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        const int k = (int)(i / D);
-        const float w = respsum[k] / (float)N_total;               // np.mean(affinities, 0)  (:178)
-        float t = stats[i] / (float)N_total;                       // /= num_data             (:180)
-        t = t / w;                                                 // /= weights              (:181)
-        t = fminf(fmaxf(t, min_prob), 1.f - min_prob);             // threshold_templates     (:192-193)
-        templates[i] = t;
-        logT[i] = logf(t);
-        logInvT[i] = logf(1.f - t);
-        if (i - (long long)k * D == 0) { weights[k] = w; logw[k] = logf(w); }
-    }
-}
-
 }  // namespace tsr
 
 using namespace tsr;
@@ -248,41 +726,111 @@ using namespace tsr;
 extern "C" {
 
 size_t tsr_em_workspace_bytes(long long N, int D, int K) {
-    if (N < 0 || D < 1 || K < 1 || K > EM_MAX_K) return 0;
-    return em_workspace(N, D, K).total;
+    if (N < 0 || N >= (1ll << 31) || D < 1 || K < 1 || K > EM_MAX_K) return 0;
+    return em_shape(N, D, K).total;
 }
 
-int tsr_em_estep(const uint32_t* Xbits, long long N, int D, int rowwords, int K, const float* logT,
-                 const float* logInvT, const float* logw, float* aff, float* scores_or_null, float* stats,
-                 double* stats_ll, int hard, void* workspace, int impl, void* stream) {
-    TSR_REQUIRE(Xbits && logT && logInvT && logw && aff && stats && stats_ll && workspace, "tsr_em_estep: null pointer");
+long long tsr_em_npad(long long N) { return N < 0 ? 0 : (N + 255) / 256 * 256; }
+
+size_t tsr_em_control_bytes(int max_trace) { return max_trace < 0 ? 0 : sizeof(EmCtl) + (size_t)max_trace * 8; }
+
+int tsr_em_workspace_init(void* workspace, long long N, int D, int K, void* stream) {
+    TSR_REQUIRE(workspace, "tsr_em_workspace_init: null pointer");
+    TSR_REQUIRE(N >= 0 && N < (1ll << 31) && D >= 1 && K >= 1 && K <= EM_MAX_K, "tsr_em_workspace_init: bad sizes (1 <= num_mix <= %d)", EM_MAX_K);
+    int rc = require_sm100("tsr_em_workspace_init");
+    if (rc) return rc;
+    const EmShape s = em_shape(N, D, K);
+    // weight / posterior tiles (rows no component maps to must read as zero) and the int32 accumulators
+    TSR_CUDA(cudaMemsetAsync(workspace, 0, s.off_scratch, (cudaStream_t)stream));
+    return TSR_OK;
+}
+
+int tsr_em_control_init(void* ctl, int max_trace, double tol, int mode, int min_iter, int max_iter, void* stream) {
+    TSR_REQUIRE(ctl && max_trace >= 1 && (mode == 0 || mode == 1), "tsr_em_control_init: bad arguments");
+    int rc = require_sm100("tsr_em_control_init");
+    if (rc) return rc;
+    EmCtl h;
+    memset(&h, 0, sizeof(h));
+    h.mode = mode; h.min_iter = min_iter; h.max_iter = max_iter; h.cap = max_trace; h.tol = tol;
+    TSR_CUDA(cudaMemcpyAsync(ctl, &h, sizeof(h), cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    TSR_CUDA(cudaStreamSynchronize((cudaStream_t)stream));      // `h` is a stack object
+    return TSR_OK;
+}
+
+int tsr_em_control_step(void* ctl, const long long* stats, int D, int K, void* stream) {
+    TSR_REQUIRE(ctl && stats && D >= 1 && K >= 1, "tsr_em_control_step: bad arguments");
+    int rc = require_sm100("tsr_em_control_step");
+    if (rc) return rc;
+    em_control_kernel<<<1, 1, 0, (cudaStream_t)stream>>>((EmCtl*)ctl, stats + (size_t)K * D + K);
+    return check_launch("tsr_em_control_step");
+}
+
+static int em_prepare(const EmShape& s, uint8_t* ws, const float* logT, const float* logInvT, const int* done, cudaStream_t st) {
+    ParamArgs P;
+    memset(&P, 0, sizeof(P));
+    P.logT = const_cast<float*>(logT); P.logInvT = const_cast<float*>(logInvT);
+    P.D = s.D; P.K = s.K; P.KT = s.KT; P.mrp = s.mrp; P.nchunk = s.nchunkE;
+    P.wblob = ws + s.off_wblob; P.c = (double*)(ws + s.off_c); P.scale = (float*)(ws + s.off_scale); P.done = done;
+    em_params_kernel<false><<<s.K, 256, 0, st>>>(P);
+    return check_launch("tsr_em_estep(prepare)");
+}
+
+int tsr_em_estep(const uint32_t* Xbits, long long N, int D, int rowwords, int K, const float* logT_or_null,
+                 const float* logInvT_or_null, const float* logw, float* aff_or_null, float* scores_or_null,
+                 long long* stats_or_null, int hard, int update, void* workspace, const void* ctl_or_null, int impl,
+                 void* stream) {
+    TSR_REQUIRE(Xbits && logw && workspace, "tsr_em_estep: null pointer");
+    TSR_REQUIRE((logT_or_null == nullptr) == (logInvT_or_null == nullptr), "tsr_em_estep: pass both logT and logInvT, or neither");
     TSR_REQUIRE(K >= 1 && K <= EM_MAX_K, "tsr_em_estep: need 1 <= num_mix <= %d (got %d)", EM_MAX_K, K);
     TSR_REQUIRE(N >= 0 && N < (1ll << 31) && D >= 1 && rowwords == tsr_rowwords(D), "tsr_em_estep: bad sizes");
-    if (N == 0) return TSR_OK;
+    TSR_REQUIRE(impl == TSR_IMPL_TENSOR || impl == TSR_IMPL_SIMT, "tsr_em_estep: unknown impl %d", impl);
+    TSR_REQUIRE(!update || stats_or_null, "tsr_em_estep: update needs the statistics vector");
+    TSR_REQUIRE(impl == TSR_IMPL_TENSOR || logT_or_null, "tsr_em_estep(simt): needs logT / logInvT");
     int rc = require_sm100("tsr_em_estep");
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
-    EmWorkspace w = em_workspace(N, D, K);
+    const EmShape s = em_shape(N, D, K);
     uint8_t* ws = (uint8_t*)workspace;
-    float* W = (float*)(ws + w.off_w);
-    float* c = (float*)(ws + w.off_c);
-    float* S = (float*)(ws + w.off_scores);
-    em_weights_kernel<<<148 * 2, 256, 0, st>>>(logT, logInvT, W, c, K, D);
-    rc = check_launch("tsr_em_estep(weights)");
-    if (rc) return rc;
-    if (impl == TSR_IMPL_TENSOR) {
-        rc = tsr_prepare_filters(W, K, 1, D, EM_PLANES, ws + w.off_blob, stream);
+    const int* done = ctl_or_null ? &((const EmCtl*)ctl_or_null)->done : nullptr;
+    if (N == 0) {          // a rank without rows contributes zeros to the allreduce
+        if (update) em_zero_tail_kernel<<<(K + 1 + 255) / 256, 256, 0, st>>>(stats_or_null, K, (long long)K * D, done);
+        return check_launch("tsr_em_estep(empty)");
+    }
+    if (logT_or_null) {
+        rc = em_prepare(s, ws, logT_or_null, logInvT_or_null, done, st);
         if (rc) return rc;
     }
-    rc = tsr_detect(Xbits, 1, (int)N, D, rowwords, ws + w.off_blob, W, K, 1, EM_PLANES, S, impl, stream);
+    PostArgs P;
+    memset(&P, 0, sizeof(P));
+    P.accE = (int*)(ws + s.off_accE); P.scratch = (float*)(ws + s.off_scratch); P.c = (const double*)(ws + s.off_c);
+    P.scale = (const float*)(ws + s.off_scale); P.logw = logw; P.N = N; P.Npad = s.Npad; P.K = K; P.KT = s.KT; P.Mtiles = s.Mtiles;
+    P.mrp = s.mrp; P.aff = aff_or_null; P.scores_out = scores_or_null; P.hard = hard; P.update = update; P.done = done;
+    if (update) {
+        P.ablob = ws + s.off_ablob;
+        P.stats_resp = stats_or_null + (size_t)K * D;
+        P.stats_ll = stats_or_null + (size_t)K * D + K;
+        em_zero_tail_kernel<<<(K + 1 + 255) / 256, 256, 0, st>>>(stats_or_null, K, (long long)K * D, done);
+    }
+    const size_t psm = s.tile_bytes + (size_t)K * 4;
+    const unsigned pgrid = (unsigned)(s.Npad / 128);
+    if (impl == TSR_IMPL_SIMT) {
+        long long blocks = (N * K + 127) / 128;
+        const long long cap = (long long)sm_count() * 32;
+        if (blocks > cap) blocks = cap;
+        em_scores_simt_kernel<<<(unsigned)blocks, 128, 0, st>>>(Xbits, N, D, rowwords, K, logT_or_null, logInvT_or_null, P.c, P.scratch,
+                                                               s.Npad, done);
+        rc = check_launch("tsr_em_estep(simt scores)");
+        if (rc) return rc;
+        TSR_CUDA(cudaFuncSetAttribute(em_posterior_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm));
+        em_posterior_kernel<false><<<pgrid, 128, psm, st>>>(P);
+        return check_launch("tsr_em_estep(posterior)");
+    }
+    rc = launch_bitgemm(Xbits, N, rowwords, ws + s.off_wblob, P.accE, s.Npad, s.nchunkE, s, done, st);
     if (rc) return rc;
-    em_posterior_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(S, c, logw, N, K, aff, scores_or_null,
-                                                                      stats + (size_t)K * D, stats_ll, hard);
+    TSR_CUDA(cudaFuncSetAttribute(em_posterior_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm));
+    em_posterior_kernel<true><<<pgrid, 128, psm, st>>>(P);
     return check_launch("tsr_em_estep(posterior)");
 }
-
-int tsr_em_segments(long long N, int D, int K) { return (N < 1 || D < 1 || K < 1) ? 0 : em_geom(N, D, K).S; }
-long long tsr_em_npad(long long N, int D, int K) { return (N < 1 || D < 1 || K < 1) ? 0 : em_geom(N, D, K).Npad; }
 
 int tsr_transpose_bits(const uint32_t* Xbits, long long N, int D, int rowwords, uint32_t* XTbits, long long N_pad,
                        void* stream) {
@@ -290,57 +838,77 @@ int tsr_transpose_bits(const uint32_t* Xbits, long long N, int D, int rowwords, 
     TSR_REQUIRE(N >= 1 && D >= 1 && rowwords == tsr_rowwords(D) && N_pad >= N && N_pad % 64 == 0, "tsr_transpose_bits: bad sizes");
     int rc = require_sm100("tsr_transpose_bits");
     if (rc) return rc;
-    transpose_bits_kernel<<<148 * 8, 256, 0, (cudaStream_t)stream>>>(Xbits, N, D, rowwords, XTbits, N_pad / 32);
+    transpose_bits_kernel<<<sm_count() * 8, 256, 0, (cudaStream_t)stream>>>(Xbits, N, D, rowwords, XTbits, N_pad / 32);
     return check_launch("tsr_transpose_bits");
 }
 
 int tsr_em_mstep(const uint32_t* Xbits, const uint32_t* XTbits_or_null, long long N, int D, int rowwords, int K,
-                 const float* aff, float* stats, void* workspace, int impl, void* stream) {
-    TSR_REQUIRE(Xbits && aff && stats && workspace, "tsr_em_mstep: null pointer");
+                 const float* aff_or_null, long long* stats, void* workspace, const void* ctl_or_null, int impl, void* stream) {
+    TSR_REQUIRE(Xbits && stats && workspace, "tsr_em_mstep: null pointer");
     TSR_REQUIRE(K >= 1 && K <= EM_MAX_K, "tsr_em_mstep: need 1 <= num_mix <= %d (got %d)", EM_MAX_K, K);
-    TSR_REQUIRE(N >= 0 && D >= 1 && rowwords == tsr_rowwords(D), "tsr_em_mstep: bad sizes");
+    TSR_REQUIRE(N >= 0 && N < (1ll << 24), "tsr_em_mstep: at most 2^24 rows per rank (int32 digit-plane accumulators)");
+    TSR_REQUIRE(D >= 1 && rowwords == tsr_rowwords(D), "tsr_em_mstep: bad sizes");
     TSR_REQUIRE(impl == TSR_IMPL_TENSOR || impl == TSR_IMPL_SIMT, "tsr_em_mstep: unknown impl %d", impl);
-    if (N == 0) return TSR_OK;
     int rc = require_sm100("tsr_em_mstep");
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
-    EmWorkspace w = em_workspace(N, D, K);
+    if (N == 0) {          // a rank without rows contributes zeros to the allreduce
+        TSR_CUDA(cudaMemsetAsync(stats, 0, ((size_t)K * D + (aff_or_null ? K : 0)) * 8, st));
+        return TSR_OK;
+    }
+    const EmShape s = em_shape(N, D, K);
     uint8_t* ws = (uint8_t*)workspace;
+    const int* done = ctl_or_null ? &((const EmCtl*)ctl_or_null)->done : nullptr;
     if (impl == TSR_IMPL_SIMT) {
-        float* partial = (float*)(ws + w.off_partial);
-        int nsplit = (int)(N < EM_MSPLIT * 128 ? (N + 127) / 128 : EM_MSPLIT);
-        dim3 grid((rowwords + 7) / 8, nsplit);
-        em_mstep_partial_kernel<<<grid, 256, 0, st>>>(Xbits, aff, N, D, rowwords, K, partial);
-        rc = check_launch("tsr_em_mstep(partial)");
-        if (rc) return rc;
-        em_mstep_reduce_kernel<<<148 * 2, 256, 0, st>>>(partial, nsplit, K, D, stats);
-        return check_launch("tsr_em_mstep(reduce)");
+        TSR_REQUIRE(aff_or_null, "tsr_em_mstep(simt): needs the posteriors");
+        long long blocks = ((long long)K * D + 127) / 128;
+        const long long cap = (long long)sm_count() * 32;
+        if (blocks > cap) blocks = cap;
+        em_mstep_simt_kernel<<<(unsigned)blocks, 128, 0, st>>>(Xbits, N, D, rowwords, K, aff_or_null, stats, done);
+        return check_launch("tsr_em_mstep(simt)");
     }
     TSR_REQUIRE(XTbits_or_null, "tsr_em_mstep: the tensor path needs the transposed bits (tsr_transpose_bits)");
-    const EmGeom g = em_geom(N, D, K);
-    TSR_REQUIRE(g.seg < (1ll << 31) && (long long)D * g.S < (1ll << 31), "tsr_em_mstep: problem too large");
-    float* LF = (float*)(ws + w.off_mlf);
-    float* scores = (float*)(ws + w.off_mscores);
-    em_aff_to_filters_kernel<<<148 * 8, 256, 0, st>>>(aff, N, K, g.S, g.seg, LF);
-    rc = check_launch("tsr_em_mstep(filters)");
+    if (aff_or_null) {     // digit planes from the caller's posteriors (otherwise the last E-step left them in the workspace)
+        const size_t psm = s.tile_bytes + (size_t)K * 4;
+        TSR_CUDA(cudaFuncSetAttribute(em_aff_planes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm));
+        em_zero_tail_kernel<<<(K + 255) / 256, 256, 0, st>>>(stats, K - 1, (long long)K * D, done);       // the K sums, not the log-likelihood
+        em_aff_planes_kernel<<<(unsigned)(s.Npad / 128), 128, psm, st>>>(aff_or_null, N, s.Npad, K, s.KT, s.Mtiles, s.mrp,
+                                                                         ws + s.off_ablob, stats + (size_t)K * D, done);
+        rc = check_launch("tsr_em_mstep(planes)");
+        if (rc) return rc;
+    }
+    rc = launch_bitgemm(XTbits_or_null, D, (int)(s.Npad / 32), ws + s.off_ablob, (int*)(ws + s.off_accM), s.Dpad, (int)s.nchunkM, s,
+                        done, st);
     if (rc) return rc;
-    rc = tsr_prepare_filters(LF, K * g.S, 1, (int)g.seg, TSR_PLANES_INT8X3, ws + w.off_mblob, stream);
-    if (rc) return rc;
-    rc = tsr_detect(XTbits_or_null, 1, D * g.S, (int)g.seg, tsr_rowwords((int)g.seg), ws + w.off_mblob, LF, K * g.S, 1,
-                    TSR_PLANES_INT8X3, scores, TSR_IMPL_TENSOR, stream);
-    if (rc) return rc;
-    em_gather_numer_kernel<<<148 * 2, 256, 0, st>>>(scores, D, K, g.S, stats);
-    return check_launch("tsr_em_mstep(gather)");
+    long long blocks = ((long long)K * D + 255) / 256;
+    const long long cap = (long long)sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    em_pack_kernel<<<(unsigned)blocks, 256, 0, st>>>((int*)(ws + s.off_accM), D, s.Dpad, K, s.KT, s.mrp, stats, done);
+    return check_launch("tsr_em_mstep(pack)");
 }
 
-int tsr_em_finalize(const float* stats, long long N_total, int D, int K, float min_prob, float* templates,
-                    float* logT, float* logInvT, float* weights, float* logw, void* stream) {
+int tsr_em_finalize(const long long* stats, long long N_total, int D, int K, float min_prob, float* templates, float* logT,
+                    float* logInvT, float* weights, float* logw, void* workspace_or_null, long long N_local,
+                    const void* ctl_or_null, void* stream) {
     TSR_REQUIRE(stats && templates && logT && logInvT && weights && logw, "tsr_em_finalize: null pointer");
     TSR_REQUIRE(K >= 1 && K <= EM_MAX_K && D >= 1 && N_total >= 1, "tsr_em_finalize: bad sizes");
     int rc = require_sm100("tsr_em_finalize");
     if (rc) return rc;
-    em_finalize_kernel<<<148 * 2, 256, 0, (cudaStream_t)stream>>>(stats, N_total, D, K, min_prob, templates, logT,
-                                                                 logInvT, weights, logw);
+    ParamArgs P;
+    memset(&P, 0, sizeof(P));
+    P.stats = stats; P.N_total = N_total; P.min_prob = min_prob; P.templates = templates; P.logT = logT; P.logInvT = logInvT;
+    P.weights = weights; P.logw = logw; P.D = D; P.K = K;
+    P.done = ctl_or_null ? &((const EmCtl*)ctl_or_null)->done : nullptr;
+    if (workspace_or_null) {       // also lay the next E-step's weight planes out (tsr_em_estep with logT = NULL uses them)
+        TSR_REQUIRE(N_local >= 0 && N_local < (1ll << 31), "tsr_em_finalize: bad N_local");
+        const EmShape s = em_shape(N_local, D, K);
+        uint8_t* ws = (uint8_t*)workspace_or_null;
+        P.KT = s.KT; P.mrp = s.mrp; P.nchunk = s.nchunkE;
+        P.wblob = ws + s.off_wblob; P.c = (double*)(ws + s.off_c); P.scale = (float*)(ws + s.off_scale);
+    } else {
+        P.KT = K < EM_KT_MAX ? K : EM_KT_MAX;
+    }
+    em_params_kernel<true><<<K, 256, 0, (cudaStream_t)stream>>>(P);
     return check_launch("tsr_em_finalize");
 }
 

@@ -323,7 +323,7 @@ int tsr_code_parts_mag_aux_terms(float* scores, uint8_t* gate_or_null, const uin
     if (rc) return rc;
     const long long n = (long long)B * (T - ph + 1) * (F - pw + 1) * K;
     long long blocks = (n + 255) / 256;
-    if (blocks > 148LL * 32) blocks = 148LL * 32;
+    if (blocks > (long long)sm_count() * 32) blocks = (long long)sm_count() * 32;
     mag_aux_terms_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(scores, gate_or_null, X_mags, X_aux, thresh_mask,
                                                                           log_mag_parts, log_mag_invparts, log_aux_parts,
                                                                           log_aux_invparts, n, T, F, K, ph, pw, mag_dim, aux_dim);
@@ -339,7 +339,7 @@ int tsr_patch_counts(const uint8_t* bits, const uint8_t* mask_or_null, int B, in
     if (rc) return rc;
     const long long n = (long long)B * (T - ph + 1) * (F - pw + 1);
     long long blocks = (n + 255) / 256;
-    if (blocks > 148LL * 32) blocks = 148LL * 32;
+    if (blocks > (long long)sm_count() * 32) blocks = (long long)sm_count() * 32;
     patch_counts_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(bits, mask_or_null, n, T, F, ph, pw, counts);
     return check_launch("tsr_patch_counts");
 }
@@ -381,7 +381,7 @@ int tsr_patch_gather(const uint8_t* bits, const double* S_or_null, const int32_t
     if (rc) return rc;
     const long long n = (long long)B * (T - ph + 1) * (F - pw + 1);
     long long blocks = (n + 7) / 8;
-    if (blocks > 148LL * 16) blocks = 148LL * 16;
+    if (blocks > (long long)sm_count() * 16) blocks = (long long)sm_count() * 16;
     patch_gather_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(bits, S_or_null, slot, n, T, F, E, ph, pw,
                                                                          tsr_rowwords(ph * pw * E), patch_set_or_null,
                                                                          S_patch_or_null, locs_or_null, patchbits_or_null);
@@ -397,7 +397,7 @@ int tsr_detect_peaks(const float* track, const int* lengths_or_null, int B, int 
     if (rc) return rc;
     const long long n = (long long)B * T;
     long long blocks = (n + 255) / 256;
-    if (blocks > 148LL * 32) blocks = 148LL * 32;
+    if (blocks > (long long)sm_count() * 32) blocks = (long long)sm_count() * 32;
     detect_peaks_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(track, lengths_or_null, n, T, C0, threshold, flags);
     return check_launch("tsr_detect_peaks");
 }
@@ -410,7 +410,7 @@ int tsr_peaks_gather(const float* track, const int32_t* slot, int B, int T, int3
     if (rc) return rc;
     const long long n = (long long)B * T;
     long long blocks = (n + 255) / 256;
-    if (blocks > 148LL * 32) blocks = 148LL * 32;
+    if (blocks > (long long)sm_count() * 32) blocks = (long long)sm_count() * 32;
     peaks_gather_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(track, slot, n, T, peak_bt, peak_val_or_null);
     return check_launch("tsr_peaks_gather");
 }

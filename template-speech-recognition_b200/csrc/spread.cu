@@ -576,7 +576,7 @@ int tsr_spread_graph(uint32_t* featbits, const uint8_t* graph, long long R, int 
     TSR_REQUIRE(smem <= 200 * 1024, "tsr_spread_graph: does not fit shared memory");
     if (smem > 48 * 1024)
         TSR_CUDA(cudaFuncSetAttribute(spread_graph_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    long long blocks = R < 148 * 8 ? R : 148 * 8;
+    long long blocks = R < (long long)sm_count() * 8 ? R : (long long)sm_count() * 8;
     spread_graph_kernel<<<(unsigned)blocks, 128, smem, (cudaStream_t)stream>>>(featbits, graph, R, Fo, K, rowwords);
     return check_launch("tsr_spread_graph");
 }

@@ -2,6 +2,15 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <condition_variable>
+#include <mutex>
+#include <thread>
+#include <vector>
+#if defined(__x86_64__) || defined(_M_X64)
+#include <emmintrin.h>
+#define TSR_HOST_SSE2 1
+#endif
+
 #include "common.cuh"
 
 namespace tsr {
@@ -25,9 +34,12 @@ int check_launch(const char* what) {
 }
 
 int sm_count() {
+    static int cache[64];                       // per device ordinal; 0 = not queried yet
     int dev = 0, n = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    if (dev >= 0 && dev < 64 && cache[dev] > 0) return cache[dev];
     if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+    if (dev >= 0 && dev < 64) cache[dev] = n;
     return n;
 }
 
@@ -108,11 +120,98 @@ __global__ void unpack_features_kernel(const uint32_t* __restrict__ bits, uint8_
     }
 }
 
+// ----------------------------------------------------------------------------- host-side packer
+// The boundary conversion for callers whose edge tensors live in HOST memory: packing before the copy moves 1 byte
+// per (t,f) over PCIe instead of 8.  16 input bytes (two cells) -> compare with zero -> byte mask -> two packed bytes.
+static void host_pack_range(const uint8_t* X, uint8_t* bits, long long c0, long long c1) {
+    long long i = c0;
+#ifdef TSR_HOST_SSE2
+    const __m128i zero = _mm_setzero_si128();
+    for (; i + 8 <= c1; i += 8) {                      // 64 input bytes -> 8 packed bytes
+        uint64_t out = 0;
+#pragma GCC unroll 4
+        for (int k = 0; k < 4; ++k) {
+            const __m128i v = _mm_loadu_si128(reinterpret_cast<const __m128i*>(X + (i + 2 * k) * 8));
+            const uint32_t nz = ~(uint32_t)_mm_movemask_epi8(_mm_cmpeq_epi8(v, zero)) & 0xFFFFu;
+            out |= (uint64_t)nz << (16 * k);
+        }
+        memcpy(bits + i, &out, 8);
+    }
+#endif
+    for (; i < c1; ++i) {
+        uint32_t b = 0;
+        for (int e = 0; e < 8; ++e) b |= (uint32_t)(X[i * 8 + e] != 0) << e;
+        bits[i] = (uint8_t)b;
+    }
+}
+
+// Persistent worker pool (created on first use): a call publishes a job, wakes the workers and waits for them.
+class HostPool {
+public:
+    void run(const uint8_t* X, uint8_t* bits, long long n, int nthreads) {
+        std::unique_lock<std::mutex> call_lock(call_mu_);              // one job at a time
+        if (nthreads < 1) nthreads = 1;
+        if (nthreads > 256) nthreads = 256;
+        {
+            std::unique_lock<std::mutex> lk(mu_);
+            while ((int)workers_.size() < nthreads - 1) {
+                const int id = (int)workers_.size();
+                workers_.emplace_back([this, id] { loop(id); });
+            }
+            X_ = X; bits_ = bits; n_ = n; parts_ = nthreads; pending_ = nthreads - 1; ++gen_;
+        }
+        cv_.notify_all();
+        slice(nthreads - 1);                                           // the caller takes the last slice
+        std::unique_lock<std::mutex> lk(mu_);
+        done_cv_.wait(lk, [this] { return pending_ == 0; });
+    }
+
+private:
+    void slice(int id) {
+        const long long per = ((n_ + parts_ - 1) / parts_ + 7) & ~7LL;   // 8-cell granules
+        long long c0 = per * id, c1 = c0 + per;
+        if (c0 > n_) c0 = n_;
+        if (c1 > n_) c1 = n_;
+        host_pack_range(X_, bits_, c0, c1);
+    }
+    void loop(int id) {
+        unsigned long long seen = 0;
+        for (;;) {
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_.wait(lk, [&] { return gen_ != seen; });
+                seen = gen_;
+                if (id >= parts_ - 1) continue;                        // not part of this job
+            }
+            slice(id);
+            std::unique_lock<std::mutex> lk(mu_);
+            if (--pending_ == 0) done_cv_.notify_all();
+        }
+    }
+    std::mutex mu_, call_mu_;
+    std::condition_variable cv_, done_cv_;
+    std::vector<std::thread> workers_;
+    const uint8_t* X_ = nullptr;
+    uint8_t* bits_ = nullptr;
+    long long n_ = 0;
+    int parts_ = 1, pending_ = 0;
+    unsigned long long gen_ = 0;
+};
+
 }  // namespace tsr
 
 using namespace tsr;
 
 extern "C" {
+
+int tsr_host_pack_edges(const uint8_t* X_host, uint8_t* bits_host, long long n_cells, int E, int nthreads) {
+    TSR_REQUIRE(X_host && bits_host, "tsr_host_pack_edges: null pointer");
+    TSR_REQUIRE(n_cells >= 0 && E == 8, "tsr_host_pack_edges: needs E == 8 orientation bytes per cell (got %d)", E);
+    static HostPool* pool = new HostPool();                           // never destroyed: workers outlive exit handlers
+    if (n_cells < 65536 || nthreads <= 1) host_pack_range(X_host, bits_host, 0, n_cells);
+    else pool->run(X_host, bits_host, n_cells, nthreads);
+    return TSR_OK;
+}
 
 int tsr_abi_version(void) { return TSR_ABI_VERSION; }
 const char* tsr_last_error(void) { return g_err; }
@@ -151,7 +250,7 @@ int tsr_pack_features_u8(const uint8_t* Fm, uint32_t* bits, long long R, int D, 
     if (rc) return rc;
     long long warps = R * rowwords;
     long long blocks = (warps + 7) / 8;
-    if (blocks > 148LL * 64) blocks = 148LL * 64;
+    if (blocks > (long long)sm_count() * 64) blocks = (long long)sm_count() * 64;
     pack_features_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(Fm, bits, R, D, rowwords);
     return check_launch("tsr_pack_features_u8");
 }
@@ -164,7 +263,7 @@ int tsr_unpack_features_u8(const uint32_t* bits, uint8_t* Fm, long long R, int D
     if (rc) return rc;
     long long n = R * D;
     long long blocks = (n + 255) / 256;
-    if (blocks > 148LL * 64) blocks = 148LL * 64;
+    if (blocks > (long long)sm_count() * 64) blocks = (long long)sm_count() * 64;
     unpack_features_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(bits, Fm, R, D, rowwords);
     return check_launch("tsr_unpack_features_u8");
 }

@@ -1,15 +1,19 @@
 """Host-side driver of Bernoulli-mixture EM over row shards (one shard per rank / GPU).
 
 The E- and M-step arithmetic lives behind a small "local engine" interface so that the
-host logic -- sharding, the allreduce of the sufficient statistics, the stopping rules of
-the two reference classes -- is the same code whether the engine is the CUDA one
-(``GpuEmEngine``, the product) or a stand-in used by the CPU/gloo tests.
+host logic -- sharding, the allreduce of the sufficient statistics, the speculative
+iteration loop -- is the same code whether the engine is the CUDA one (``GpuEmEngine``,
+the product) or a stand-in used by the CPU/gloo tests.
 
-Per EM iteration and rank:   E-step on the local rows (posteriors, responsibility sums,
-log-likelihood)  ->  M accumulation (numerators)  ->  ONE allreduce(sum) of the float32
-vector [K*D numerators | K responsibility sums] plus one of the float64 log-likelihood
-->  every rank finalises identical templates (divide, clip, log).  With a single rank no
-collective is issued.  Scoring/coding/detection never communicate.
+Per EM iteration and rank:   stopping rule on the reduced log-likelihood (``control_step``)
+->  finalize (divide, clip, log: identical on every rank)  ->  E-step on the local rows
+(posteriors, responsibility sums, log-likelihood)  ->  M accumulation (numerators)  ->  ONE
+allreduce(sum) of the statistics vector [K*D numerators | K responsibility sums |
+log-likelihood].  The CUDA engine keeps that vector in exact int64 fixed point, so the
+reduced values -- and everything derived from them -- are bit-identical for every rank count.
+The stopping rule runs on the device: the host queues ``batch`` iterations at a time and reads
+the control block back once per batch; iterations past the stop are no-ops.  With a single
+rank no collective is issued.  Scoring/coding/detection never communicate.
 """
 import numpy as np
 import torch
@@ -25,19 +29,23 @@ def shard_rows(N, rank, world):
 class GpuEmEngine:
     """Local engine backed by libtsr_b200.so: bit-packed rows resident in HBM."""
 
-    def __init__(self, data_rows, D, K, device=None, chunk_rows=16384):
+    def __init__(self, data_rows, D, K, device=None, chunk_rows=16384, packed=None):
         from . import ops
         from ._np import device as _device
         self.ops = ops
         self.device = _device() if device is None else device
-        n = data_rows.shape[0]
-        rw = ops.rowwords(D)
-        X = torch.empty((n, rw), dtype=torch.int32, device=self.device)
-        for s in range(0, n, chunk_rows):      # stage through uint8 chunks; pack on the device
-            blk = np.ascontiguousarray(data_rows[s:s + chunk_rows])
-            blk = (blk != 0).astype(np.uint8) if blk.dtype != np.uint8 else blk
-            d = torch.from_numpy(blk.reshape(1, -1, D)).to(self.device)
-            X[s:s + blk.shape[0]] = ops.pack_features(d)[0]
+        if packed is not None:                  # rows already bit-packed on the device
+            X = packed
+            n = X.shape[0]
+        else:
+            n = data_rows.shape[0]
+            rw = ops.rowwords(D)
+            X = torch.empty((n, rw), dtype=torch.int32, device=self.device)
+            for s in range(0, n, chunk_rows):      # stage through uint8 chunks; pack on the device
+                blk = np.ascontiguousarray(data_rows[s:s + chunk_rows])
+                blk = (blk != 0).astype(np.uint8) if blk.dtype != np.uint8 else blk
+                d = torch.from_numpy(blk.reshape(1, -1, D)).to(self.device)
+                X[s:s + blk.shape[0]] = ops.pack_features(d)[0]
         self.state = ops.EmState(X, D, K)
         self.N, self.D, self.K = n, D, K
 
@@ -52,25 +60,37 @@ class GpuEmEngine:
     def affinities(self):
         return self.state.aff
 
-    def estep(self, params, hard, impl=0):
-        """Posteriors for the local rows; fills stats[K*D:] (responsibility sums) and ll."""
-        self.state.estep(params["logT"], params["logInvT"], params["logw"], hard=hard, impl=impl)
-
-    def accumulate(self):
-        """stats[:K*D] += aff^T X over the local rows."""
-        self.state.mstep_accumulate()
-
     @property
     def stats(self):
         return self.state.stats
 
-    @property
-    def ll(self):
-        return self.state.ll
+    def estep(self, params, hard, impl=0, ctl=None, prepared=False):
+        """Posteriors for the local rows; fills the responsibility sums and the log-likelihood of stats.
+        prepared: the weight planes were laid out by the last finalize (skip the per-call preparation)."""
+        lt, li = (None, None) if (prepared and impl == 0) else (params["logT"], params["logInvT"])
+        self.state.estep(lt, li, params["logw"], hard=hard, impl=impl, ctl=ctl)
 
-    def finalize(self, stats, N_total, min_prob, params):
+    def accumulate(self, impl=0, from_affinities=False, ctl=None):
+        """stats[:K*D] = aff^T X over the local rows (from_affinities: from self.affinities(), also setting the
+        responsibility sums -- used to initialise templates from a hard assignment)."""
+        self.state.mstep_accumulate(impl=impl, aff=self.state.aff if from_affinities else None, ctl=ctl)
+
+    def loglik(self):
+        return self.state.loglik()
+
+    def finalize(self, stats, N_total, min_prob, params, ctl=None):
         self.ops.em_finalize(stats, N_total, self.D, self.K, min_prob, params["templates"], params["logT"],
-                             params["logInvT"], params["weights"], params["logw"])
+                             params["logInvT"], params["weights"], params["logw"], state=self.state, ctl=ctl)
+
+    # ---- stopping rule on the device
+    def control_init(self, tol, mode, min_iter, max_iter):
+        return self.ops.EmControl(self.device, tol, mode, min_iter, max_iter, max(min_iter, max_iter) + 2)
+
+    def control_step(self, ctl):
+        ctl.step(self.state.stats, self.D, self.K)
+
+    def control_read(self, ctl):
+        return ctl.read()
 
 
 class EmDriver:
@@ -83,33 +103,50 @@ class EmDriver:
                                           and torch.distributed.get_world_size() > 1 and group is not False)
         if group is False:
             self.dist = False
+        self.allreduces = 0
 
     def _allreduce(self, t):
         if self.dist:
             torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.SUM,
                                          group=self.group if self.group not in (None, False) else None)
+            self.allreduces += 1
+
+    def _estep(self, hard, impl, ctl, prepared, accumulate=True):
+        self.e.estep(self.params, hard, impl, ctl=ctl, prepared=prepared)
+        if accumulate:
+            self.e.accumulate(impl, ctl=ctl)
+        self._allreduce(self.e.stats)          # the ONE collective of an iteration
 
     def expectation(self, hard=False, impl=0, accumulate=True):
         """E-step (+ numerator accumulation) on every rank, then the sufficient-statistics
-        allreduce.  Returns the global log-likelihood (python float)."""
-        self.e.estep(self.params, hard, impl)
-        if accumulate:
-            self.e.accumulate()
-        self._allreduce(self.e.stats)
-        self._allreduce(self.e.ll)
-        return float(self.e.ll.item())
+        allreduce.  Returns the global log-likelihood (python float; synchronises)."""
+        self._estep(hard, impl, None, False, accumulate)
+        return self.e.loglik()
 
     def maximization(self, min_prob):
         """Finalise templates / weights from the reduced statistics (identical on every rank)."""
         self.e.finalize(self.e.stats, self.N_total, float(min_prob), self.params)
 
+    def run(self, tol, mode="relative", min_iter=10, max_iter=500, hard=False, min_prob=0.05, batch=8, impl=0):
+        """The EM loop of run_EM (bernoulli_mixture.py:135-156; mode "absolute": bernoulli_em.py:22-34) with the
+        stopping rule evaluated on the device.  Returns (iterations, log-likelihood trace)."""
+        e = self.e
+        ctl = e.control_init(float(tol), 0 if mode == "relative" else 1, int(min_iter), int(max_iter))
+        self._estep(hard, impl, ctl, False)                         # first E-step (:135)
+        while True:
+            for _ in range(max(1, int(batch))):
+                e.control_step(ctl)                                 # continue? (:144)  -- every rank sees the same reduced value
+                e.finalize(e.stats, self.N_total, float(min_prob), self.params, ctl=ctl)    # M-step (:150)
+                self._estep(hard, impl, ctl, True)                  # E-step (:152)
+            done, iterations, trace = e.control_read(ctl)           # one host synchronisation per batch
+            if done:
+                return iterations, trace
+
     def init_from_affinities(self, min_prob, uniform_weights=True):
         """Templates = affinity-weighted data means (the deterministic round-robin 'unif_rand'
         start of bernoulli_mixture.py:195-237); weights stay uniform as in the reference."""
         K = self.e.K
-        self.e.stats.zero_()
-        self.e.accumulate()
-        self.e.stats[K * self.e.D:] = self.e.affinities().sum(0)
+        self.e.accumulate(from_affinities=True)
         self._allreduce(self.e.stats)
         self.e.finalize(self.e.stats, self.N_total, float(min_prob), self.params)
         if uniform_weights:

@@ -22,6 +22,35 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+def _device_of(args, kwargs):
+    for a in list(args) + list(kwargs.values()):
+        if isinstance(a, torch.Tensor) and a.is_cuda:
+            return a.device
+        blob = getattr(a, "blob", None)          # PartsModel / FilterBank
+        if isinstance(blob, torch.Tensor) and blob.is_cuda:
+            return blob.device
+    return None
+
+
+def _on_device(fn):
+    """Run `fn` with the CUDA device of its first device argument current: the C ABI launches on the current device
+    and on torch's current stream OF THAT DEVICE, so tensors living on cuda:N must not be processed while another
+    device is current.  Tensors on different devices in one call are refused."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(*args, **kwargs):
+        dev = _device_of(args, kwargs)
+        if dev is None:
+            return fn(*args, **kwargs)
+        for a in list(args) + list(kwargs.values()):
+            if isinstance(a, torch.Tensor) and a.is_cuda and a.device != dev:
+                raise ValueError("%s: arguments live on different CUDA devices (%s, %s)" % (fn.__name__, dev, a.device))
+        with torch.cuda.device(dev):
+            return fn(*args, **kwargs)
+    return wrapped
+
+
 def _ptr(t):
     return 0 if t is None else t.data_ptr()
 
@@ -174,17 +203,18 @@ class PartsModel:
         self.K, self.ph, self.pw, self.E = lp.shape
         nbytes = _lib.lib().tsr_parts_blob_bytes(self.K, self.ph, self.pw)
         self.blob = torch.empty(nbytes, dtype=torch.uint8, device=device)
-        d_lp = torch.from_numpy(lp).to(device)
-        d_lip = torch.from_numpy(lip).to(device)
+        d_lp = torch.from_numpy(lp).to(self.blob.device)
+        d_lip = torch.from_numpy(lip).to(self.blob.device)
         d_mask = None
         if mask is not None:
             m = np.ascontiguousarray(mask, dtype=np.uint8)
             if m.shape != (self.ph, self.pw):
                 raise ValueError("mask must have the part window shape (%d,%d)" % (self.ph, self.pw))
-            d_mask = torch.from_numpy((m != 0).astype(np.uint8)).to(device)
-        _lib.call("tsr_prepare_parts", _ptr(d_lp), _ptr(d_lip), self.K, self.ph, self.pw, self.E, _ptr(d_mask),
-                  int(planes), _ptr(self.blob), _stream())
-        torch.cuda.current_stream().synchronize()   # d_lp/d_lip may be freed after this returns
+            d_mask = torch.from_numpy((m != 0).astype(np.uint8)).to(self.blob.device)
+        with torch.cuda.device(self.blob.device):
+            _lib.call("tsr_prepare_parts", _ptr(d_lp), _ptr(d_lip), self.K, self.ph, self.pw, self.E, _ptr(d_mask),
+                      int(planes), _ptr(self.blob), _stream())
+            torch.cuda.current_stream().synchronize()   # d_lp/d_lip may be freed after this returns
 
 
 def code_parts(bits, parts, threshold, mask_threshold=-1, want_codes=True, want_scores=False, want_counts=False,
@@ -319,7 +349,8 @@ class FilterBank:
         if nbytes == 0:
             raise ValueError("unsupported filter shape M=%d L=%d D=%d (need 1 <= L <= 256)" % (self.M, self.L, self.D))
         self.blob = torch.empty(nbytes, dtype=torch.uint8, device=device)
-        _lib.call("tsr_prepare_filters", _ptr(self.LF), self.M, self.L, self.D, int(planes), _ptr(self.blob), _stream())
+        with torch.cuda.device(self.blob.device):
+            _lib.call("tsr_prepare_filters", _ptr(self.LF), self.M, self.L, self.D, int(planes), _ptr(self.blob), _stream())
 
 
 def detect(featbits, bank, D=None, impl=IMPL_TENSOR, out=None):
@@ -400,6 +431,34 @@ def cluster_peaks(peak_bt, B, C0, C1):
 
 
 # ------------------------------------------------------------------------------- K4
+EM_QMAX = 8355711            # posteriors are quantised to q = round(aff * EM_QMAX) (three balanced base-256 digits)
+EM_LL_SCALE = float(1 << 20)  # fixed-point unit of the log-likelihood entry of the statistics vector
+
+
+class EmControl:
+    """Device-side stopping rule of the EM loop (tsr_em_control_*): lets the host queue iterations without
+    reading the log-likelihood back; kernels of iterations past the stop exit at once."""
+
+    def __init__(self, device, tol, mode, min_iter, max_iter, max_trace):
+        self.max_trace = int(max_trace)
+        nbytes = _lib.lib().tsr_em_control_bytes(self.max_trace)
+        self.buf = torch.zeros(nbytes, dtype=torch.uint8, device=device)
+        with torch.cuda.device(device):
+            _lib.call("tsr_em_control_init", _ptr(self.buf), self.max_trace, float(tol), int(mode), int(min_iter), int(max_iter),
+                      _stream())
+
+    def step(self, stats, D, K):
+        with torch.cuda.device(self.buf.device):
+            _lib.call("tsr_em_control_step", _ptr(self.buf), _ptr(stats), int(D), int(K), _stream())
+
+    def read(self):
+        """(done, iterations, trace) -- one device->host copy (synchronises the stream)."""
+        h = self.buf.cpu().numpy()
+        done, iterations, ntrace = (int(v) for v in h[:12].view(np.int32))
+        trace = h[48:48 + 8 * min(ntrace, self.max_trace)].view(np.float64)
+        return bool(done), iterations, [float(v) for v in trace]
+
+
 class EmState:
     """Device state of one rank's share of a Bernoulli-mixture EM problem."""
 
@@ -414,29 +473,62 @@ class EmState:
         dev = self.X.device
         nbytes = _lib.lib().tsr_em_workspace_bytes(self.N, self.D, self.K)
         if nbytes == 0:
-            raise ValueError("unsupported EM shape (need 1 <= num_mix <= 64)")
-        self.ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-        # transposed bits for the tensor-core M-step (one-time, 1 bit per datum)
-        self.Npad = int(_lib.lib().tsr_em_npad(self.N, self.D, self.K))
-        self.XT = torch.zeros((self.D, self.Npad // 32), dtype=torch.int32, device=dev)
-        _lib.call("tsr_transpose_bits", _ptr(self.X), self.N, self.D, self.rw, _ptr(self.XT), self.Npad, _stream())
+            raise ValueError("unsupported EM shape (need 1 <= num_mix <= 4095 and fewer than 2^31 rows)")
+        with torch.cuda.device(dev):
+            self.ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            _lib.call("tsr_em_workspace_init", _ptr(self.ws), self.N, self.D, self.K, _stream())
+            # transposed bits for the tensor-core M-step (one-time, 1 bit per datum)
+            self.Npad = int(_lib.lib().tsr_em_npad(self.N))
+            self.XT = torch.zeros((self.D, self.Npad // 32), dtype=torch.int32, device=dev)
+            if self.N:
+                _lib.call("tsr_transpose_bits", _ptr(self.X), self.N, self.D, self.rw, _ptr(self.XT), self.Npad, _stream())
         self.aff = torch.zeros((self.N, self.K), dtype=torch.float32, device=dev)
-        # stats = [K*D numerators | K responsibility sums]; ll kept separately in float64
-        self.stats = torch.zeros(self.K * self.D + self.K, dtype=torch.float32, device=dev)
-        self.ll = torch.zeros(1, dtype=torch.float64, device=dev)
+        # stats = [K*D numerators | K responsibility sums | log-likelihood] as exact integers (see tsr_b200.h)
+        self.stats = torch.zeros(self.K * self.D + self.K + 1, dtype=torch.int64, device=dev)
 
-    def estep(self, logT, logInvT, logw, hard=False, impl=IMPL_TENSOR, scores_out=None):
-        self.stats.zero_()
-        self.ll.zero_()
-        _lib.call("tsr_em_estep", _ptr(self.X), self.N, self.D, self.rw, self.K, _ptr(logT), _ptr(logInvT), _ptr(logw),
-                  _ptr(self.aff), _ptr(scores_out), _ptr(self.stats), _ptr(self.ll), int(bool(hard)), _ptr(self.ws),
-                  int(impl), _stream())
+    def estep(self, logT, logInvT, logw, hard=False, impl=IMPL_TENSOR, scores_out=None, update=True, ctl=None):
+        """logT = logInvT = None: use the weight planes the last em_finalize(..., state=self) laid out."""
+        with torch.cuda.device(self.X.device):
+            _lib.call("tsr_em_estep", _ptr(self.X), self.N, self.D, self.rw, self.K, _ptr(logT), _ptr(logInvT), _ptr(logw),
+                      _ptr(self.aff) if update else 0, _ptr(scores_out), _ptr(self.stats) if update else 0, int(bool(hard)),
+                      int(bool(update)), _ptr(self.ws), _ptr(ctl.buf) if ctl is not None else 0, int(impl), _stream())
 
-    def mstep_accumulate(self, impl=IMPL_TENSOR):
-        _lib.call("tsr_em_mstep", _ptr(self.X), _ptr(self.XT), self.N, self.D, self.rw, self.K, _ptr(self.aff),
-                  _ptr(self.stats), _ptr(self.ws), int(impl), _stream())
+    def mstep_accumulate(self, impl=IMPL_TENSOR, aff=None, ctl=None):
+        """stats[:K*D] = numerators from the last E-step's posteriors, or from `aff` (N,K) float32 when given
+        (then the responsibility sums are taken from it too)."""
+        if aff is not None:
+            aff = _dev(aff, torch.float32, "aff")
+        elif impl == IMPL_SIMT:
+            aff = self.aff
+        with torch.cuda.device(self.X.device):
+            _lib.call("tsr_em_mstep", _ptr(self.X), _ptr(self.XT), self.N, self.D, self.rw, self.K, _ptr(aff), _ptr(self.stats),
+                      _ptr(self.ws), _ptr(ctl.buf) if ctl is not None else 0, int(impl), _stream())
+
+    def numerators(self):
+        """float64 (K,D) view of the numerators in posterior units."""
+        return self.stats[:self.K * self.D].double().reshape(self.K, self.D) / EM_QMAX
+
+    def resp_sums(self):
+        return self.stats[self.K * self.D:self.K * self.D + self.K].double() / EM_QMAX
+
+    def loglik(self):
+        return float(self.stats[self.K * self.D + self.K].item()) / EM_LL_SCALE
 
 
-def em_finalize(stats, N_total, D, K, min_prob, templates, logT, logInvT, weights, logw):
-    _lib.call("tsr_em_finalize", _ptr(stats), int(N_total), int(D), int(K), float(min_prob), _ptr(templates), _ptr(logT),
-              _ptr(logInvT), _ptr(weights), _ptr(logw), _stream())
+def em_finalize(stats, N_total, D, K, min_prob, templates, logT, logInvT, weights, logw, state=None, ctl=None):
+    """M-step proper from the (all-reduced) statistics.  state: also lay out the weight planes of the next E-step
+    in that EmState's workspace (then its estep may be called with logT = logInvT = None)."""
+    stats = _dev(stats, torch.int64, "stats")
+    with torch.cuda.device(stats.device):
+        _lib.call("tsr_em_finalize", _ptr(stats), int(N_total), int(D), int(K), float(min_prob), _ptr(templates), _ptr(logT),
+                  _ptr(logInvT), _ptr(weights), _ptr(logw), _ptr(state.ws) if state is not None else 0,
+                  int(state.N) if state is not None else 0, _ptr(ctl.buf) if ctl is not None else 0, _stream())
+
+
+# every tensor-taking entry point runs with its arguments' device current (see _on_device)
+for _name in ("pack_edges", "unpack_edges", "pack_features", "unpack_features", "spread_edges", "edge_map", "threshold_edges",
+              "edges_from_spectrogram", "spread_edge_blocks", "code_parts", "code_parts_mag_aux_terms", "patch_counts",
+              "extract_patches", "spread_codes", "spread_graph", "detect", "detect_reduce", "detect_float", "detect_peaks",
+              "cluster_peaks", "em_finalize"):
+    globals()[_name] = _on_device(globals()[_name])
+del _name

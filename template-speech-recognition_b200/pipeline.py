@@ -55,67 +55,135 @@ class ScoringPipeline:
         """X uint8 (B,T,F,E) host array -> packed edge bytes on the device."""
         return ops.pack_edges(torch.from_numpy(np.ascontiguousarray(X)).to(self.parts.blob.device))
 
-    def stream(self, host_batches, ring=3):
-        """Score a sequence of host batches with the copies hidden behind the kernels.
+    def stream(self, host_batches, ring=3, pack="host", pack_threads=None):
+        """Score a sequence of host batches with packing, copies and kernels overlapped.
 
-        host_batches: iterable of uint8 (B,T,F,E) edge tensors in host memory (pinned torch tensors copy
-        asynchronously; NumPy arrays are accepted and staged through a pinned buffer).  Yields, per batch and in
+        host_batches: iterable of edge batches in host memory -- uint8 (B,T,F,E) edge tensors (the reference's
+        dtype; E = 8) or pre-packed uint8 (B,T,F) edge bytes (bit e = orientation e, what ``ops.pack_edges``
+        produces).  Pinned torch tensors copy asynchronously; NumPy arrays are accepted.  Yields, per batch and in
         order, ``(best float32 (B,To), argbest int16 (B,To))`` as pinned host tensors that stay valid until
         ``ring - 1`` further batches have been requested.
 
-        Three streams: the H2D copy of batch i+1 (into the other of two device buffers) and the D2H copy of
-        batch i-1's results run while batch i is packed, coded and scored; every batch still moves its own
-        inputs in and its own results out.
+        pack="host" (default): (B,T,F,E) batches are packed to one byte per (t,f) by a pool of host threads
+        (``tsr_host_pack_edges``, pure data movement) BEFORE the copy, so 1/8 of the bytes cross PCIe; a feeder thread
+        packs batch i+1 while batch i is copied and scored.  pack="device": the unpacked tensor is copied and packed
+        by the GPU (8x the H2D bytes; for hosts with few cores and a fast link).
+
+        Streams: H2D of batch i+1 (into the other of two device buffers) and D2H of batch i-1's results run while
+        batch i is coded and scored; every batch still moves its own inputs in and its own results out.
         """
+        import os
+        import queue
+        import threading
+        from . import _lib
+        if pack not in ("host", "device"):
+            raise ValueError("pack must be 'host' or 'device'")
         dev = self.parts.blob.device
+        nthreads = int(pack_threads) if pack_threads else max(1, min(32, (os.cpu_count() or 2) - 1))
+        q = queue.Queue(maxsize=2)
+        stop = threading.Event()
+        # Four staging buffers for a queue of two: when the feeder reuses slot i % 4 for batch i + 4 it has queued
+        # batches i + 2 and i + 3, so the consumer has taken batch i + 1 and therefore finished issuing batch i
+        # (whose copy-done event is then in `consumed`).
+        NSTAGE = 4
+        staging = [None] * NSTAGE                # pinned buffers the feeder packs / stages into
+        consumed = [None] * NSTAGE               # CUDA event: the H2D copy out of staging[j] has finished
+
+        def feeder():
+            try:
+                for i, xb in enumerate(host_batches):
+                    if stop.is_set():
+                        return
+                    j = i % NSTAGE
+                    is_t = isinstance(xb, torch.Tensor)
+                    if not is_t:
+                        xb = np.ascontiguousarray(xb)
+                    if xb.dtype not in (torch.uint8, np.uint8) or len(xb.shape) not in (3, 4):
+                        raise ValueError("edge batches must be uint8 (B,T,F,E) or packed uint8 (B,T,F)")
+                    if len(xb.shape) == 4 and xb.shape[3] != 8 and pack == "host":
+                        raise ValueError("host packing needs E == 8 orientation planes")
+                    direct = is_t and xb.is_pinned() and xb.is_contiguous() and (len(xb.shape) == 3 or pack == "device")
+                    if direct:                   # already what the copy engine needs
+                        q.put((xb, None))
+                        continue
+                    shape = tuple(xb.shape[:3]) if (len(xb.shape) == 4 and pack == "host") else tuple(xb.shape)
+                    if staging[j] is None or tuple(staging[j].shape) != shape:
+                        staging[j] = torch.empty(shape, dtype=torch.uint8).pin_memory()
+                    elif consumed[j] is not None:
+                        consumed[j].synchronize()
+                    src = xb.contiguous() if is_t else xb
+                    if len(xb.shape) == 4 and pack == "host":
+                        sp = src.data_ptr() if is_t else src.ctypes.data
+                        _lib.call("tsr_host_pack_edges", sp, staging[j].data_ptr(), int(np.prod(shape)), 8, nthreads)
+                    elif is_t:
+                        staging[j].copy_(src)
+                    else:
+                        staging[j].numpy()[...] = src
+                    q.put((staging[j], j))
+                q.put(None)
+            except BaseException as e:  # noqa: BLE001 -- re-raised in the consumer
+                q.put(e)
+
+        th = threading.Thread(target=feeder, daemon=True, name="tsr-stream-feeder")
+        th.start()
         main = torch.cuda.current_stream(dev)
         h2d, d2h = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
-        xd, staged, free_ev = [None, None], [None, None], [None, None]
+        xd, free_ev = [None, None], [None, None]
         outs, out_ev = [None] * ring, [None] * ring
         pending = None
-        for i, xb in enumerate(host_batches):
-            k = i & 1
-            if not isinstance(xb, torch.Tensor):
-                xb = np.ascontiguousarray(xb)
-                if staged[k] is None or staged[k].shape != xb.shape:
-                    staged[k] = torch.empty(xb.shape, dtype=torch.uint8).pin_memory()
-                if free_ev[k] is not None:
-                    free_ev[k].synchronize()              # the previous copy out of this staging buffer has been consumed
-                staged[k].numpy()[...] = xb
-                xb = staged[k]
-            if xb.dtype != torch.uint8 or xb.dim() != 4:
-                raise ValueError("edge batches must be uint8 (B,T,F,E)")
-            if xd[k] is None or xd[k].shape != xb.shape:
-                xd[k] = torch.empty(xb.shape, dtype=torch.uint8, device=dev)
-            with torch.cuda.stream(h2d):
-                if free_ev[k] is not None:
-                    h2d.wait_event(free_ev[k])            # pack_edges of batch i-2 has finished reading this buffer
-                xd[k].copy_(xb, non_blocking=True)
-                arrived = torch.cuda.Event()
-                arrived.record(h2d)
-            main.wait_event(arrived)
-            bits = ops.pack_edges(xd[k])
-            free_ev[k] = torch.cuda.Event()
-            free_ev[k].record(main)
-            best, arg, _ = self(bits)
-            scored = torch.cuda.Event()
-            scored.record(main)
-            r = i % ring
-            if outs[r] is None or outs[r][0].shape != best.shape:
-                outs[r] = (torch.empty(best.shape, dtype=torch.float32).pin_memory(),
-                           torch.empty(arg.shape, dtype=arg.dtype).pin_memory())
-            with torch.cuda.stream(d2h):
-                d2h.wait_event(scored)
-                outs[r][0].copy_(best, non_blocking=True)
-                outs[r][1].copy_(arg, non_blocking=True)
-                best.record_stream(d2h)
-                arg.record_stream(d2h)
-                out_ev[r] = torch.cuda.Event()
-                out_ev[r].record(d2h)
+        i = 0
+        try:
+            while True:
+                item = q.get()
+                if item is None:
+                    break
+                if isinstance(item, BaseException):
+                    raise item
+                xb, slot = item
+                k = i & 1
+                with torch.cuda.stream(h2d):
+                    if xd[k] is None or xd[k].shape != xb.shape:
+                        # A fresh block may be one that kernels still in flight on `main` were using (the caching
+                        # allocator reuses blocks per stream): order the first copy after everything queued there.
+                        h2d.wait_stream(main)
+                        xd[k] = torch.empty(xb.shape, dtype=torch.uint8, device=dev)
+                        xd[k].record_stream(main)
+                    elif free_ev[k] is not None:
+                        h2d.wait_event(free_ev[k])        # batch i-2 has finished reading this buffer
+                    xd[k].copy_(xb, non_blocking=True)
+                    arrived = torch.cuda.Event()
+                    arrived.record(h2d)
+                    if slot is not None:
+                        consumed[slot] = arrived
+                main.wait_event(arrived)
+                bits = ops.pack_edges(xd[k]) if xd[k].dim() == 4 else xd[k]
+                best, arg, _ = self(bits)
+                free_ev[k] = torch.cuda.Event()
+                free_ev[k].record(main)                   # the whole step is queued: xd[k] (== bits when packed) is free after it
+                r = i % ring
+                if outs[r] is None or outs[r][0].shape != best.shape:
+                    outs[r] = (torch.empty(best.shape, dtype=torch.float32).pin_memory(),
+                               torch.empty(arg.shape, dtype=arg.dtype).pin_memory())
+                with torch.cuda.stream(d2h):
+                    d2h.wait_event(free_ev[k])
+                    outs[r][0].copy_(best, non_blocking=True)
+                    outs[r][1].copy_(arg, non_blocking=True)
+                    best.record_stream(d2h)
+                    arg.record_stream(d2h)
+                    out_ev[r] = torch.cuda.Event()
+                    out_ev[r].record(d2h)
+                if pending is not None:
+                    out_ev[pending].synchronize()
+                    yield outs[pending]
+                pending = r
+                i += 1
             if pending is not None:
                 out_ev[pending].synchronize()
                 yield outs[pending]
-            pending = r
-        if pending is not None:
-            out_ev[pending].synchronize()
-            yield outs[pending]
+        finally:
+            stop.set()
+            while th.is_alive():                          # unblock a feeder waiting on the full queue
+                try:
+                    q.get_nowait()
+                except queue.Empty:
+                    th.join(timeout=0.05)

@@ -34,7 +34,7 @@ def test_library_exports_every_declared_symbol():
 def test_size_helpers_and_validation_without_device():
     from tsr_b200 import _lib
     lib = _lib.lib()
-    assert lib.tsr_abi_version() == 1
+    assert lib.tsr_abi_version() == 2
     assert lib.tsr_rowwords(3600) == 114 and lib.tsr_rowwords(64) == 2 and lib.tsr_rowwords(65) == 4
     assert lib.tsr_parts_blob_bytes(100, 5, 5) > 2 * 13 * 112 * 32
     assert lib.tsr_filter_blob_bytes(32, 40, 3600, 0) == 256 + 6 * 57 * 2 * 240 * 128  # header + 6 N-tiles x 57 chunks x 2 planes x 240 columns x 128 B

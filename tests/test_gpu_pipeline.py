@@ -63,3 +63,51 @@ def test_stream_equals_direct_calls(cuda):
         n += 1
     assert n == len(batches)
     assert list(pipe.stream(iter([]))) == []
+    # pre-packed edge bytes in, and the unpacked tensor packed on the device: same results
+    packed = [np.packbits(X != 0, axis=-1, bitorder="little")[..., 0] for X in batches]
+    for kw, feed in ((dict(), [torch.from_numpy(P).pin_memory() if i % 2 else P for i, P in enumerate(packed)]),
+                     (dict(pack="device"), mixed), (dict(pack_threads=1), batches)):
+        n = 0
+        for (best, arg), (wb, wa) in zip(pipe.stream(iter(feed), **kw), want):
+            np.testing.assert_array_equal(best.numpy(), wb)
+            np.testing.assert_array_equal(arg.numpy(), wa)
+            n += 1
+        assert n == len(batches)
+    with pytest.raises(ValueError):
+        list(pipe.stream(iter([np.zeros((2, 120, 40, 8), np.float32)])))
+    # abandoning the generator early stops the feeder thread
+    it = pipe.stream(iter(batches))
+    next(it)
+    it.close()
+
+
+_FRESH = r"""
+import sys, numpy as np, torch
+sys.path.insert(0, %r)
+from tsr_b200 import synth
+from tsr_b200.pipeline import ScoringPipeline
+lp, lip = synth.parts(100)
+T, bgd = synth.templates(M=8, L=40, Fd=36, Kd=100)
+W, c = synth.linear_filters(T, bgd)
+pipe = ScoringPipeline(lp, lip, W, c)
+batches = [synth.fast_edge_batch(b, seed=s) for s, b in enumerate([640, 640, 512, 640])]
+got = [(b.numpy().copy(), a.numpy().copy()) for b, a in pipe.stream(iter(batches), pack=sys.argv[1])]   # FIRST work of the process
+torch.cuda.synchronize()
+for X, (gb, ga) in zip(batches, got):
+    best, arg, _ = pipe(pipe.from_numpy(X))
+    assert np.array_equal(best.cpu().numpy(), gb) and np.array_equal(arg.cpu().numpy(), ga)
+print("fresh-process stream ok")
+"""
+
+
+@pytest.mark.parametrize("pack", ["host", "device"])
+def test_stream_large_batches_in_a_fresh_process(cuda, pack):
+    """Cross-stream hazard check (device input buffers are handed out by the caching allocator while kernels of the
+    previous batch may still be running on the main stream): bench-sized batches, allocator cache cold, stream() is
+    the first thing the process does; results must equal direct calls."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", _FRESH % root, pack], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "fresh-process stream ok" in r.stdout, r.stdout + r.stderr

@@ -25,48 +25,12 @@ if rank == 0:
     rel = np.max(np.abs(np.array(s.loglikelihood_trace[:n]) - np.array(m.loglikelihood_trace[:n])) / np.abs(s.loglikelihood_trace[:n]))
     dT = np.abs(s.templates - m.templates).max()
     print("ranks %d: loglik trace rel diff %.2e, templates max abs diff %.2e, iterations %d vs %d" % (world, rel, dT, m.iterations, s.iterations))
-    assert rel < 1e-5 and dT < 1e-3
+    assert rel < 1e-12 and dT < 1e-7
 dist.barrier()
 
-# timing at config 4 shapes: N = 100 000 rows in total, sharded; synthetic bits generated on the device
-N, D, K = 100000, 12800, 16
-lo, hi = shard_rows(N, rank, world)
-g = torch.Generator(device="cuda").manual_seed(3 + rank)
-rw = ops.rowwords(D)
-Xb = torch.randint(-2**31, 2**31 - 1, (hi - lo, rw), dtype=torch.int32, device="cuda", generator=g)
-Xb &= torch.randint(-2**31, 2**31 - 1, (hi - lo, rw), dtype=torch.int32, device="cuda", generator=g)
-
-
-class Eng:   # minimal engine around ops.EmState (the data is already packed on the device)
-    def __init__(self):
-        self.state = ops.EmState(Xb, D, K); self.N, self.D, self.K, self.device = hi - lo, D, K, Xb.device
-    def new_params(self):
-        z = lambda *s: torch.zeros(s, dtype=torch.float32, device=self.device)
-        return dict(templates=z(K, D), logT=z(K, D), logInvT=z(K, D), weights=z(K), logw=z(K))
-    def affinities(self): return self.state.aff
-    def estep(self, p, hard, impl=0): self.state.estep(p["logT"], p["logInvT"], p["logw"], hard=hard, impl=impl)
-    def accumulate(self): self.state.mstep_accumulate()
-    stats = property(lambda self: self.state.stats)
-    ll = property(lambda self: self.state.ll)
-    def finalize(self, stats, Nt, mp, p): ops.em_finalize(stats, Nt, D, K, mp, p["templates"], p["logT"], p["logInvT"], p["weights"], p["logw"])
-
-
-drv = EmDriver(Eng(), N, group=None)
-T0 = torch.rand((K, D), device="cuda", generator=torch.Generator(device="cuda").manual_seed(1)).clamp_(0.05, 0.95)
-drv.params["templates"].copy_(T0); drv.params["logT"].copy_(torch.log(T0)); drv.params["logInvT"].copy_(torch.log(1 - T0))
-drv.params["weights"].fill_(1.0 / K); drv.params["logw"].fill_(float(np.log(1.0 / K)))
-for _ in range(3):
-    drv.expectation(); drv.maximization(0.05)
-torch.cuda.synchronize(); dist.barrier()
-ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-iters = 10
-ev0.record()
-for _ in range(iters):
-    ll = drv.expectation(); drv.maximization(0.05)
-ev1.record(); torch.cuda.synchronize()
-t = torch.tensor([ev0.elapsed_time(ev1) / iters], device="cuda", dtype=torch.float64)
-dist.all_reduce(t, op=dist.ReduceOp.MAX)
+# bit-identical statistics for every rank count: the sharded run's trace equals the single-GPU trace exactly
 if rank == 0:
-    print("config 4 (N=100000, D=12800, K=16) on %d GPUs: %.3f ms per EM iteration (E + M + allreduce + finalize), loglik %.6e" % (world, t.item(), ll))
+    assert m.loglikelihood_trace[:n] == s.loglikelihood_trace[:n], "int64 statistics must make the trace rank-count independent"
+    print("trace bit-identical across rank counts; allreduces issued:", m._drv.allreduces)
 dist.barrier()
 dist.destroy_process_group()
