@@ -164,6 +164,14 @@ int tsr_detect(const uint32_t* featbits, int B, int T, int D, int rowwords, cons
  * (what get_train_data.py:962-992 produces by adding c to the zero tail). */
 int tsr_detect_reduce(const float* scores, const float* cs, int B, int T, int M, int L, int tail_mode, float* best,
                       uint16_t* arg, void* stream);
+/* tsr_detect (tensor path) with the mixture max fused into its epilogue: best / arg as tsr_detect_reduce with
+ * tail_mode 1 computes them (bit-identical), without materialising the [B][T][M] score matrix -- the running
+ * np.maximum of get_train_data.py:964-992 / detect_float_max :268-277.  scores_or_null: also write the matrix.
+ * keys_workspace: B*T*8 bytes of device scratch (64-bit (value, template) keys combined with atomicMax across the
+ * CTAs that hold different template tiles). */
+int tsr_detect_best(const uint32_t* featbits, int B, int T, int D, int rowwords, const void* filter_blob, int M, int L,
+                    int plane_format, const float* cs_or_null, float* scores_or_null, void* keys_workspace, float* best,
+                    uint16_t* arg, void* stream);
 /* Real-valued features: detect_float (:178-219), detect_float2d (:281-318), detect_spectral
  * (:322-359), detect_float_max (:221-278).  fp32, separate multiply and add in the reference's
  * (tau,f,k) order; each accumulation starts at init_or_null[m] (detect_float_max's cs, :258) or 0. */
@@ -214,15 +222,18 @@ int tsr_edges_from_spectrogram(const double* S, uint8_t* bits, uint8_t* tail_bit
  * Replaces BernoulliMixture.get_template_loglikelihoods/_compute_loglikelihoods
  * (bernoulli_mixture.py:263-291), M_step/threshold_templates (:177-193), the run_EM loop's stopping rule
  * (:139-156) and the same steps of bernoulli_em.Bernoulli_Mixture (bernoulli_em.py:22-49, 103-127).
- * Any number of components 1 <= K <= 4095 (the reference trains 100-200-part dictionaries with this class,
+ * Any number of components 1 <= K <= 4095, fewer than 2^24 rows per rank (the reference trains 100-200-part dictionaries with this class,
  * Notebook/12/reestimate_parts.py:79-83).
  *
- * Sufficient statistics are ONE int64 vector  stats[K*D + K + 1]:
- *   stats[k*D+d]   = sum_n q(n,k) x[n][d]       q(n,k) = round(aff[n][k] * 8355711)   (numerators)
- *   stats[K*D+k]   = sum_n q(n,k)                                                      (responsibility sums)
- *   stats[K*D+K]   = sum_n round(logsumexp_k(S[n][k] + logw[k]) * 2^20)                (log-likelihood)
- * Integer sums are exact, so the caller's single allreduce(sum, int64) over the ranks (NCCL) gives the same
- * bits for every rank count; tsr_em_finalize then runs identically on every rank.
+ * Sufficient statistics are ONE float64 vector  stats[K*D + K + 1]:
+ *   stats[k*D+d]   = sum_n aff[n][k] x[n][d]                     (numerators)
+ *   stats[K*D+k]   = sum_n aff[n][k]                             (responsibility sums)
+ *   stats[K*D+K]   = sum_n logsumexp_k(S[n][k] + logw[k])        (log-likelihood)
+ * Inside a rank every sum is an exact integer sum (posteriors quantised per component to 24 bits below a
+ * power-of-two scale s_k >= max_n aff[n][k], so components holding a vanishing share of the mass keep full
+ * relative precision; row log-likelihoods in 2^-20 fixed point), converted to float64 once: a rank's statistics
+ * are deterministic and independent of the summation order.  The caller's single allreduce(sum, float64) over the
+ * ranks (NCCL) combines them; tsr_em_finalize then runs identically on every rank.
  *
  * E-step over this rank's rows: S[n][k] = sum_d x ? logT : logInvT; aff = row-softmax(S + logw) (or the one-hot
  * first arg-max of S when hard != 0).  With update != 0 it writes aff_or_null [N][K], the posterior digit planes
@@ -241,15 +252,15 @@ int tsr_transpose_bits(const uint32_t* Xbits, long long N, int D, int rowwords, 
                        void* stream);
 int tsr_em_estep(const uint32_t* Xbits, long long N, int D, int rowwords, int K, const float* logT_or_null,
                  const float* logInvT_or_null, const float* logw, float* aff_or_null, float* scores_or_null,
-                 long long* stats_or_null, int hard, int update, void* workspace, const void* ctl_or_null, int impl,
+                 double* stats_or_null, int hard, int update, void* workspace, const void* ctl_or_null, int impl,
                  void* stream);
 int tsr_em_mstep(const uint32_t* Xbits, const uint32_t* XTbits_or_null /* required for TSR_IMPL_TENSOR */,
-                 long long N, int D, int rowwords, int K, const float* aff_or_null, long long* stats, void* workspace,
+                 long long N, int D, int rowwords, int K, const float* aff_or_null, double* stats, void* workspace,
                  const void* ctl_or_null, int impl, void* stream);
 /* weights = respsum / N_total; T = numer / N_total / weights clipped to [min_prob, 1-min_prob]; logT, logInvT,
  * logw refreshed (all float32, as bernoulli_mixture.py:178-184).  workspace_or_null != NULL: also lays out the
  * int8 weight planes of the next E-step over N_local rows in that workspace. */
-int tsr_em_finalize(const long long* stats, long long N_total, int D, int K, float min_prob, float* templates,
+int tsr_em_finalize(const double* stats, long long N_total, int D, int K, float min_prob, float* templates,
                     float* logT, float* logInvT, float* weights, float* logw, void* workspace_or_null,
                     long long N_local, const void* ctl_or_null, void* stream);
 /* Device-side stopping rule.  ctl = tsr_em_control_bytes(max_trace) bytes of device memory:
@@ -260,7 +271,7 @@ int tsr_em_finalize(const long long* stats, long long N_total, int D, int K, flo
  * counting an iteration when it continues and setting done otherwise. */
 size_t tsr_em_control_bytes(int max_trace);
 int    tsr_em_control_init(void* ctl, int max_trace, double tol, int mode, int min_iter, int max_iter, void* stream);
-int    tsr_em_control_step(void* ctl, const long long* stats, int D, int K, void* stream);
+int    tsr_em_control_step(void* ctl, const double* stats, int D, int K, void* stream);
 
 #ifdef __cplusplus
 }

@@ -38,6 +38,7 @@ SIGNATURES = {
     "tsr_prepare_filters": (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
     "tsr_detect": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _i, _vp, _i, _vp]),
     "tsr_detect_reduce": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "tsr_detect_best": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "tsr_detect_float": (_i, [_vp, _i, _i, _i, _vp, _i, _i, _vp, _vp, _vp]),
     "tsr_detect_peaks": (_i, [_vp, _vp, _i, _i, _i, _f, _vp, _vp]),
     "tsr_peaks_gather": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp]),

@@ -260,7 +260,18 @@ struct DetectArgs {
     FilterLayout f;
     long long* trace;   // optional debug timeline of CTA 0: [stage iteration][8] clock64 stamps
     int dbg;            // debug experiments (timing only, wrong results): 1 = every phase reads the strip at row 0
+    unsigned long long* keys;   // optional [R]: running max over templates of (score + cs[m]), see detect_key
+    const float* cs;            // optional [M] constants added before the max (detect_float_max :258, get_train_data.py:964-992)
 };
+
+// (value, template) packed so that an unsigned 64-bit max picks the larger value and, among equal values, the
+// LOWER template index (np.maximum chain / strict > of detect_float_max :275): the fused mixture max needs no
+// [R][M] score matrix and no second pass -- units holding different template tiles combine with atomicMax.
+__device__ __forceinline__ unsigned long long detect_key(float v, int m) {
+    uint32_t u = __float_as_uint(v);
+    u ^= (u >> 31) ? 0xFFFFFFFFu : 0x80000000u;              // monotone float -> uint
+    return ((unsigned long long)u << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)m);
+}
 // The timeline stamps and debug switches are compiled in only with -DTSR_DEBUG_TRACE (TSR_NVCC_EXTRA=-DTSR_DEBUG_TRACE
 // python template-speech-recognition_b200/build.py --force; tools/trace_detect.py needs it): even predicated-off they
 // sit in the issue loops, where every instruction shows up in the kernel time.
@@ -862,7 +873,7 @@ __global__ void __launch_bounds__(448 + 32 * (NIS - 1), 1) detect_tc_kernel(Dete
                     const int oi = i / tpt, ml = i - oi * tpt;
                     const long long g = gbase + oi;
                     const int m = nt * tpt + ml;
-                    if (g >= o0 && g < o1 && m < f.M) {
+                    if (A.scores && g >= o0 && g < o1 && m < f.M) {
                         const int tl = (int)(g % A.T);
                         float val = 0.f;
                         if (tl <= A.T - L) {
@@ -876,6 +887,35 @@ __global__ void __launch_bounds__(448 + 32 * (NIS - 1), 1) detect_tc_kernel(Dete
                             }
                         }
                         A.scores[g * f.M + m] = val;
+                    }
+                }
+                if (A.keys) {
+                    // fused mixture max: a thread walks the templates of this tile for its rows (odd accumulator
+                    // pitch: the lanes' rows sit in different banks) and publishes one key per row
+                    for (int oi = e; oi < step_rows; oi += 128) {
+                        const long long g = gbase + oi;
+                        if (g >= o0 && g < o1) {
+                            const bool valid = (int)(g % A.T) <= A.T - L;
+                            unsigned long long key = 0;
+                            for (int ml = 0; ml < tpt; ++ml) {
+                                const int m = nt * tpt + ml;
+                                if (m >= f.M) break;
+                                float val = 0.f;
+                                if (valid) {
+                                    const acc_t* a = outacc + oi * opitch + ml * vpt;
+                                    if (I8) {
+                                        double q = (double)a[0] + 256.0 * (double)a[1];
+                                        if (vpt == 3) q += 65536.0 * (double)a[2];
+                                        val = (float)(q * (double)scale[m]);
+                                    } else {
+                                        val = (float)a[0];
+                                    }
+                                }
+                                const unsigned long long k2 = detect_key(val + (A.cs ? __ldg(A.cs + m) : 0.f), m);
+                                key = k2 > key ? k2 : key;
+                            }
+                            atomicMax(A.keys + g, key);
+                        }
                     }
                 }
                 named_bar_sync(1, 128);
@@ -1047,6 +1087,18 @@ __global__ void __launch_bounds__(256) detect_reduce_kernel(const float* __restr
     }
 }
 
+// keys -> (best, arg)
+__global__ void detect_decode_kernel(const unsigned long long* __restrict__ keys, long long R, float* __restrict__ best,
+                                     uint16_t* __restrict__ arg) {
+    for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < R; g += (long long)gridDim.x * blockDim.x) {
+        const unsigned long long k = keys[g];
+        uint32_t u = (uint32_t)(k >> 32);
+        u ^= (u >> 31) ? 0x80000000u : 0xFFFFFFFFu;
+        if (best) best[g] = __uint_as_float(u);
+        if (arg) arg[g] = (uint16_t)(0xFFFFFFFFu - (uint32_t)k);
+    }
+}
+
 }  // namespace tsr
 
 using namespace tsr;
@@ -1083,10 +1135,11 @@ int tsr_prepare_filters(const float* LF, int M, int L, int D, int plane_format, 
     return check_launch("tsr_prepare_filters");
 }
 
-int tsr_detect(const uint32_t* featbits, int B, int T, int D, int rowwords, const void* filter_blob,
-               const float* LF_or_null, int M, int L, int plane_format, float* scores, int impl, void* stream) {
+static int detect_impl(const uint32_t* featbits, int B, int T, int D, int rowwords, const void* filter_blob,
+                       const float* LF_or_null, int M, int L, int plane_format, float* scores, unsigned long long* keys,
+                       const float* cs, int impl, void* stream) {
     if (B == 0) return TSR_OK;
-    TSR_REQUIRE(featbits && scores, "tsr_detect: null pointer");
+    TSR_REQUIRE(featbits && (scores || keys), "tsr_detect: null pointer");
     TSR_REQUIRE(B >= 0 && T >= 1 && D >= 1 && M >= 1 && L >= 1, "tsr_detect: bad sizes");
     TSR_REQUIRE(rowwords == tsr_rowwords(D), "tsr_detect: rowwords must be tsr_rowwords(D)");
     TSR_REQUIRE(impl == TSR_IMPL_TENSOR || impl == TSR_IMPL_SIMT, "tsr_detect: unknown impl %d", impl);
@@ -1094,10 +1147,12 @@ int tsr_detect(const uint32_t* featbits, int B, int T, int D, int rowwords, cons
     if (rc) return rc;
     const long long R = (long long)B * T;
     if (L > T) {   // no valid offset: all-zero output, like the reference's zero-initialised array
+        TSR_REQUIRE(scores, "tsr_detect_best: template longer than the utterances");
         TSR_CUDA(cudaMemsetAsync(scores, 0, sizeof(float) * R * M, (cudaStream_t)stream));
         return TSR_OK;
     }
     if (impl == TSR_IMPL_SIMT) {
+        TSR_REQUIRE(scores, "tsr_detect(simt): needs the score matrix");
         TSR_REQUIRE(LF_or_null, "tsr_detect(simt): needs the fp32 filters");
         long long blocks = (R * M + 127) / 128;
         if (blocks > (long long)sm_count() * 32) blocks = (long long)sm_count() * 32;
@@ -1109,6 +1164,7 @@ int tsr_detect(const uint32_t* featbits, int B, int T, int D, int rowwords, cons
     TSR_REQUIRE(plane_format >= 0 && plane_format <= 4, "tsr_detect: plane_format must be one of TSR_PLANES_*");
     DetectArgs A;
     A.bits = featbits; A.blob = (const uint8_t*)filter_blob; A.scores = scores; A.R = R; A.T = T;
+    A.keys = keys; A.cs = cs;
     A.f = filter_layout(M, L, D, plane_format);
     A.trace = g_detect_trace;
     A.dbg = g_detect_dbg;
@@ -1160,6 +1216,33 @@ int tsr_detect(const uint32_t* featbits, int B, int T, int D, int rowwords, cons
         detect_tc_kernel<false, 1, true><<<blocks, DT_THREADS - 32, S.total, (cudaStream_t)stream>>>(A);
     }
     return check_launch("tsr_detect");
+}
+
+int tsr_detect(const uint32_t* featbits, int B, int T, int D, int rowwords, const void* filter_blob,
+               const float* LF_or_null, int M, int L, int plane_format, float* scores, int impl, void* stream) {
+    if (B == 0) return TSR_OK;
+    TSR_REQUIRE(scores, "tsr_detect: null pointer");
+    return detect_impl(featbits, B, T, D, rowwords, filter_blob, LF_or_null, M, L, plane_format, scores, nullptr, nullptr, impl, stream);
+}
+
+int tsr_detect_best(const uint32_t* featbits, int B, int T, int D, int rowwords, const void* filter_blob, int M, int L,
+                    int plane_format, const float* cs_or_null, float* scores_or_null, void* keys_workspace, float* best,
+                    uint16_t* arg, void* stream) {
+    if (B == 0) return TSR_OK;
+    TSR_REQUIRE(featbits && filter_blob && keys_workspace && (best || arg), "tsr_detect_best: null pointer");
+    TSR_REQUIRE(B >= 0 && T >= 1 && L >= 1 && L <= T && M >= 1 && M <= 65535, "tsr_detect_best: bad sizes (need L <= T, M <= 65535)");
+    int rc = require_sm100("tsr_detect_best");
+    if (rc) return rc;
+    const long long R = (long long)B * T;
+    cudaStream_t st = (cudaStream_t)stream;
+    TSR_CUDA(cudaMemsetAsync(keys_workspace, 0, (size_t)R * 8, st));
+    rc = detect_impl(featbits, B, T, D, rowwords, filter_blob, nullptr, M, L, plane_format, scores_or_null,
+                     (unsigned long long*)keys_workspace, cs_or_null, TSR_IMPL_TENSOR, stream);
+    if (rc) return rc;
+    long long blocks = (R + 255) / 256;
+    if (blocks > (long long)sm_count() * 8) blocks = (long long)sm_count() * 8;
+    detect_decode_kernel<<<(unsigned)blocks, 256, 0, st>>>((const unsigned long long*)keys_workspace, R, best, arg);
+    return check_launch("tsr_detect_best");
 }
 
 int tsr_detect_reduce(const float* scores, const float* cs, int B, int T, int M, int L, int tail_mode, float* best,

@@ -11,12 +11,15 @@
 // planes the *M* operand (128 rows = up to 42 components x 3 planes; more components tile over M), so one MMA
 // carries 128 cycles of tensor work whatever the number of components.  int32 accumulation is exact, which makes
 // every sum order independent: the kernel is stream-K (each CTA owns an equal share of the (tile, chunk) space and
-// adds its partial tiles to global int32 accumulators with coalesced reductions), the sufficient statistics are
-// int64 and one integer allreduce across ranks gives bit-identical results for every rank count.
+// adds its partial tiles to global int32 accumulators with coalesced reductions) and a rank's statistics are
+// deterministic.  Posteriors are quantised per component with a power-of-two scale s_k >= max_n aff[n][k], so a
+// component that holds 1e-30 of the mass keeps 24 significant bits (the reference forms its template from the
+// RATIO of such sums, bernoulli_mixture.py:179-181; a global scale would silently kill it).
 //
-// Per iteration: bitgemm (E) -> em_posterior_kernel (soft-max, log-likelihood, posterior digit planes) ->
-// bitgemm (M) -> em_pack_kernel (int64 statistics) -> [allreduce by the caller] -> em_control_kernel (stopping rule
-// on the device) -> em_params_kernel (divide, clip, logs, weight planes of the next E-step).
+// Per iteration: bitgemm (E) -> em_posterior_kernel (soft-max, log-likelihood, column maxima) ->
+// em_aff_planes_kernel (digit planes, responsibility sums) -> bitgemm (M) -> em_pack_kernel (float64 statistics)
+// -> [allreduce by the caller] -> em_control_kernel (stopping rule on the device) -> em_params_kernel (divide,
+// clip, logs, weight planes of the next E-step).
 #include <math.h>
 #include <string.h>
 
@@ -28,7 +31,7 @@ namespace tsr {
 
 #define EM_QMAX 8355711              // 127 * (1 + 256 + 65536): largest value of three balanced base-256 digits
 #define EM_KT_MAX 42                 // mixture components per 128-row M tile (3 planes each)
-#define EM_LL_SCALE 1048576.0        // 2^20: fixed-point unit of the log-likelihood in stats[K*D+K]
+#define EM_LL_SCALE 1048576.0        // 2^20: fixed-point unit in which a rank sums its rows' log-likelihoods (order independent)
 #define EM_MAX_K 4095
 
 #define BG_THREADS 448               // 14 warps: loader, 8 expanders, 4 epilogue, MMA issuer
@@ -43,7 +46,7 @@ struct EmShape {
     int rwX, nchunkE, Dpad;             // words per data row, 128-feature chunks per row, D rounded up to 256
     long long nchunkM;                  // 128-row chunks of the M-step contraction
     size_t tile_bytes;                  // one int8 tile: 8 k-groups x mrp rows x 16 B
-    size_t off_wblob, off_c, off_scale, off_accE, off_accM, off_ablob, off_scratch, total;
+    size_t off_wblob, off_c, off_scale, off_accE, off_accM, off_ablob, off_small, off_scratch, off_aff, total;
 };
 
 static EmShape em_shape(long long N, int D, int K) {
@@ -66,8 +69,10 @@ static EmShape em_shape(long long N, int D, int K) {
     s.off_accE = s.off_scale + up((size_t)K * 4);
     s.off_accM = s.off_accE + up((size_t)s.Mtiles * s.mrp * s.Npad * 4);
     s.off_ablob = s.off_accM + up((size_t)s.Mtiles * s.mrp * s.Dpad * 4);
-    s.off_scratch = s.off_ablob + up((size_t)s.Mtiles * s.nchunkM * s.tile_bytes);
-    s.total = s.off_scratch + up((size_t)K * s.Npad * 4);
+    s.off_small = s.off_ablob + up((size_t)s.Mtiles * s.nchunkM * s.tile_bytes);
+    s.off_scratch = s.off_small + up(sizeof(long long) * ((size_t)K + 2) + sizeof(uint32_t) * (size_t)K);
+    s.off_aff = s.off_scratch + up((size_t)K * s.Npad * 4);
+    s.total = s.off_aff + up((size_t)K * (size_t)N * 4);
     return s;
 }
 
@@ -352,6 +357,30 @@ static int launch_bitgemm(const uint32_t* bits, long long R, int rw, const uint8
     return check_launch("bitgemm_kernel");
 }
 
+// Small per-call scratch in the workspace: [respQ int64[K] | llQ int64 | ticket int64 | colmax uint32[K]]
+struct EmSmall {
+    long long* respQ;
+    long long* llQ;
+    unsigned long long* ticket;
+    uint32_t* colmax;
+};
+static EmSmall em_small(uint8_t* ws, const EmShape& s) {
+    EmSmall m;
+    m.respQ = reinterpret_cast<long long*>(ws + s.off_small);
+    m.llQ = m.respQ + s.K;
+    m.ticket = reinterpret_cast<unsigned long long*>(m.llQ + 1);
+    m.colmax = reinterpret_cast<uint32_t*>(m.ticket + 1);
+    return m;
+}
+// power-of-two scale of component k's posteriors: the smallest 2^e >= column max (0 for an empty column)
+__device__ __forceinline__ float em_col_scale(uint32_t colmax_bits) {
+    const float mx = __uint_as_float(colmax_bits);
+    if (!(mx > 0.f)) return 0.f;
+    int e;
+    const float fr = frexpf(mx, &e);                       // mx = fr * 2^e, fr in [0.5, 1)
+    return ldexpf(1.f, fr == 0.5f ? e - 1 : e);
+}
+
 // ------------------------------------------------------------------------------------------------
 // SIMT cross-checks (impl = TSR_IMPL_SIMT): sequential fp32 adds of the set bits' weights, the reference's
 // arithmetic for the scores; exact integer sums of the quantised posteriors for the numerators.
@@ -379,22 +408,20 @@ __global__ void em_scores_simt_kernel(const uint32_t* __restrict__ X, long long 
     }
 }
 
+// numerators of the SIMT path: thread per (k, d), rows in order, the same quantised posteriors as the tensor path
 __global__ void em_mstep_simt_kernel(const uint32_t* __restrict__ X, long long N, int D, int rw, int K,
-                                     const float* __restrict__ aff, long long* __restrict__ stats, const int* done) {
+                                     const float* __restrict__ aff, const uint32_t* __restrict__ colmax, double* __restrict__ stats,
+                                     const int* done) {
     if (done && *done) return;
     const long long total = (long long)K * D;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const int k = (int)(i / D), d = (int)(i - (long long)k * D);
+        const float sk = em_col_scale(colmax[k]);
+        const float isk = sk >= 1.17549435e-38f ? 1.f / sk : 0.f;               // exact: s_k is a power of two
         long long acc = 0;
         for (long long n = 0; n < N; ++n)
-            if ((X[n * rw + (d >> 5)] >> (d & 31)) & 1u) acc += (long long)rintf(fminf(fmaxf(aff[n * K + k], 0.f), 1.f) * (float)EM_QMAX);
-        stats[i] = acc;
-    }
-    // responsibility sums of the given posteriors
-    for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < K; k += (long long)gridDim.x * blockDim.x) {
-        long long acc = 0;
-        for (long long n = 0; n < N; ++n) acc += (long long)rintf(fminf(fmaxf(aff[n * K + k], 0.f), 1.f) * (float)EM_QMAX);
-        stats[total + k] = acc;
+            if ((X[n * rw + (d >> 5)] >> (d & 31)) & 1u) acc += (long long)rintf(fmaxf(aff[n * K + k], 0.f) * isk * (float)EM_QMAX);
+        stats[i] = (double)acc * ((double)sk / (double)EM_QMAX);
     }
 }
 
@@ -405,7 +432,7 @@ __global__ void em_mstep_simt_kernel(const uint32_t* __restrict__ X, long long N
 //   Both: W = logT - logInvT, scale[k] = max|W| / EM_QMAX, c[k] = sum_d logInvT (double, fixed order), then the three
 //   balanced base-256 digits of round(W / scale) in the bitgemm tile order.
 struct ParamArgs {
-    const long long* stats;     // FROM_STATS
+    const double* stats;        // FROM_STATS
     long long N_total;
     float min_prob;
     float *templates, *logT, *logInvT, *weights, *logw;   // FROM_STATS: written; else logT / logInvT are read
@@ -425,13 +452,13 @@ __global__ void __launch_bounds__(256) em_params_kernel(ParamArgs P) {
     const int k = blockIdx.x, tid = threadIdx.x;
     const size_t row = (size_t)k * P.D;
     float w = 0.f;
-    if (FROM_STATS) w = (float)((double)P.stats[(size_t)P.K * P.D + k] / (double)EM_QMAX) / (float)P.N_total;   // np.mean(affinities, 0)
+    if (FROM_STATS) w = (float)P.stats[(size_t)P.K * P.D + k] / (float)P.N_total;     // np.mean(affinities, 0)
     float mx = 0.f;
     double csum = 0.0;
     for (int d = tid; d < P.D; d += 256) {
         float lt, li;
         if (FROM_STATS) {
-            float t = (float)((double)P.stats[row + d] / (double)EM_QMAX);     // np.dot(affinities.T, data)
+            float t = (float)P.stats[row + d];                                 // np.dot(affinities.T, data) as float32
             t = t / (float)P.N_total;                                          // /= num_data
             t = t / w;                                                         // /= weights
             t = fminf(fmaxf(t, P.min_prob), 1.f - P.min_prob);                 // threshold_templates
@@ -502,14 +529,7 @@ __global__ void __launch_bounds__(256) em_params_kernel(ParamArgs P) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// Posterior digit planes of 128 consecutive rows -> one M-step operand tile per M tile.  Position of row n in its
-// 128-row chunk: word i = (n % 128) / 32, r = n % 32 = 8 jj + s  ->  k-group 2i + s/4, byte 4 (s%4) + jj.
-__device__ __forceinline__ int em_tile_pos(int t /* 0..127 */) {
-    const int i = t >> 5, r = t & 31, s = r & 7, jj = r >> 3;
-    return ((2 * i + (s >> 2)) << 4) | (4 * (s & 3) + jj);        // (k-group << 4) | byte
-}
-
-// Row kernel of the E-step.  CTA = 128 consecutive rows (one chunk of the M-step contraction), thread = row.
+// Row kernel of the E-step.  Thread = data row.
 //   INT_SCORES: scores from the int32 digit-plane accumulators (which are cleared for the next E-step);
 //   otherwise scratch already holds float scores [K][Npad] (SIMT cross-check).
 struct PostArgs {
@@ -520,11 +540,10 @@ struct PostArgs {
     const float* logw;
     long long N, Npad;
     int K, KT, Mtiles, mrp;
-    float* aff;                 // [N][K] or null
+    float* aff;                 // [N][K] posteriors (update)
     float* scores_out;          // [N][K] or null
-    uint8_t* ablob;             // [Mtiles][nchunkM][8][mrp][16] or null
-    long long* stats_resp;      // [K] += sum_n q, or null
-    long long* stats_ll;        // [1] += sum_n ll * 2^20, or null
+    uint32_t* colmax;           // [K] max_n aff[n][k] as float bits (update)
+    long long* llQ;             // += sum_n round(ll * 2^20) (update)
     int hard, update;
     const int* done;
 };
@@ -533,13 +552,12 @@ template <bool INT_SCORES>
 __global__ void __launch_bounds__(128) em_posterior_kernel(PostArgs P) {
     if (P.done && *P.done) return;
     extern __shared__ __align__(16) uint8_t psm[];
-    uint8_t* tile = psm;                                              // 8 * mrp * 16 bytes
-    int* s_resp = reinterpret_cast<int*>(psm + (size_t)8 * P.mrp * 16);   // [K]
+    uint32_t* s_max = reinterpret_cast<uint32_t*>(psm);               // [K]
     __shared__ long long s_ll;
     const int tid = threadIdx.x;
     const long long n = blockIdx.x * 128LL + tid;
     const bool live = n < P.N;
-    for (int k = tid; k < P.K; k += 128) s_resp[k] = 0;
+    for (int k = tid; k < P.K; k += 128) s_max[k] = 0u;
     if (tid == 0) s_ll = 0;
     __syncthreads();
     const size_t pstride = (size_t)P.KT * P.Npad;
@@ -573,53 +591,53 @@ __global__ void __launch_bounds__(128) em_posterior_kernel(PostArgs P) {
     for (int k = 0; k < P.K; ++k) sum += (double)expf((float)(score(k, false) + (double)P.logw[k] - mx));
     const float inv = (float)(1.0 / sum);
     long long my_ll = live ? llrint((log(sum) + mx) * EM_LL_SCALE) : 0;
-    // pass 3: posteriors, their digit planes, responsibility sums
-    const int pos = em_tile_pos(tid);
-    const size_t tile_bytes = (size_t)8 * P.mrp * 16;
-    for (int mt = 0; mt < P.Mtiles; ++mt) {
-        for (int i = tid; i < (int)(tile_bytes / 16); i += 128) reinterpret_cast<uint4*>(tile)[i] = make_uint4(0u, 0u, 0u, 0u);
-        __syncthreads();
-        const int k1 = (mt + 1) * P.KT < P.K ? (mt + 1) * P.KT : P.K;
-        for (int k = mt * P.KT; k < k1; ++k) {
-            const double v = score(k, true) + (double)P.logw[k];
-            float p = 0.f;
-            if (live) p = P.hard ? (k == arg ? 1.f : 0.f) : expf((float)(v - mx)) * inv;
-            if (live && P.aff) P.aff[n * P.K + k] = p;
-            int q = (int)rintf(fminf(p, 1.f) * (float)EM_QMAX);
-            const int qsum = __reduce_add_sync(0xffffffffu, q);
-            if ((tid & 31) == 0 && qsum) atomicAdd(&s_resp[k], qsum);
-            const int kl = k - mt * P.KT;
-#pragma unroll
-            for (int pl = 0; pl < 3; ++pl) {
-                const int digit = ((q + 128) & 255) - 128;
-                q = (q - digit) >> 8;
-                tile[((size_t)(pos >> 4) * P.mrp + pl * P.KT + kl) * 16 + (pos & 15)] = (uint8_t)(digit & 255);
-            }
+    // pass 3: posteriors and their column maxima
+    for (int k = 0; k < P.K; ++k) {
+        const double v = score(k, true) + (double)P.logw[k];
+        float p = 0.f;
+        if (live) {
+            p = P.hard ? (k == arg ? 1.f : 0.f) : fminf(expf((float)(v - mx)) * inv, 1.f);
+            P.aff[n * P.K + k] = p;
         }
-        __syncthreads();
-        if (P.ablob) {
-            uint4* dst = reinterpret_cast<uint4*>(P.ablob + ((size_t)mt * (P.Npad / 128) + blockIdx.x) * tile_bytes);
-            for (int i = tid; i < (int)(tile_bytes / 16); i += 128) dst[i] = reinterpret_cast<const uint4*>(tile)[i];
-        }
-        __syncthreads();
+        const uint32_t wmax = __reduce_max_sync(0xffffffffu, __float_as_uint(p));     // p >= 0: bit patterns order like values
+        if ((tid & 31) == 0 && wmax) atomicMax(&s_max[k], wmax);
     }
     for (int off = 16; off > 0; off >>= 1) my_ll += __shfl_xor_sync(0xffffffffu, my_ll, off);
     if ((tid & 31) == 0) atomicAdd(reinterpret_cast<unsigned long long*>(&s_ll), (unsigned long long)my_ll);
     __syncthreads();
-    if (P.stats_resp)
-        for (int k = tid; k < P.K; k += 128)
-            if (s_resp[k]) atomicAdd(reinterpret_cast<unsigned long long*>(P.stats_resp + k), (unsigned long long)(long long)s_resp[k]);
-    if (tid == 0 && P.stats_ll) atomicAdd(reinterpret_cast<unsigned long long*>(P.stats_ll), (unsigned long long)s_ll);
+    for (int k = tid; k < P.K; k += 128)
+        if (s_max[k]) atomicMax(P.colmax + k, s_max[k]);
+    if (tid == 0) atomicAdd(reinterpret_cast<unsigned long long*>(P.llQ), (unsigned long long)s_ll);
 }
 
-// Posterior digit planes from caller-supplied affinities (initialisation; M-step from given posteriors)
+// column maxima of caller-supplied posteriors (initialisation; M-step from given posteriors)
+__global__ void em_colmax_kernel(const float* __restrict__ aff, long long N, int K, uint32_t* __restrict__ colmax, const int* done) {
+    if (done && *done) return;
+    const long long total = N * K;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const float p = fmaxf(aff[i], 0.f);
+        if (p > 0.f) atomicMax(colmax + (i % K), __float_as_uint(p));
+    }
+}
+
+// Position of row n in its 128-row chunk of the M-step contraction: word i = (n % 128) / 32, r = n % 32 = 8 jj + s
+// ->  k-group 2i + s/4, byte 4 (s%4) + jj   (the order the bitgemm expanders lay a word out).
+__device__ __forceinline__ int em_tile_pos(int t /* 0..127 */) {
+    const int i = t >> 5, r = t & 31, s = r & 7, jj = r >> 3;
+    return ((2 * i + (s >> 2)) << 4) | (4 * (s & 3) + jj);        // (k-group << 4) | byte
+}
+
+// Posteriors -> the M-step's int8 operand.  CTA = 128 consecutive rows = one chunk of the contraction.
+// q(n,k) = round(aff[n][k] / s_k * EM_QMAX), three balanced base-256 digits, one tile per M tile; respQ[k] += sum_n q.
+// The last CTA to finish turns the integer sums into the float64 tail of the statistics vector.
 __global__ void __launch_bounds__(128) em_aff_planes_kernel(const float* __restrict__ aff, long long N, long long Npad, int K, int KT,
-                                                            int Mtiles, int mrp, uint8_t* __restrict__ ablob,
-                                                            long long* __restrict__ stats_resp, const int* done) {
+                                                            int Mtiles, int mrp, uint8_t* __restrict__ ablob, EmSmall S,
+                                                            double* __restrict__ stats_tail, int write_ll, const int* done) {
     if (done && *done) return;
     extern __shared__ __align__(16) uint8_t psm[];
     uint8_t* tile = psm;
     int* s_resp = reinterpret_cast<int*>(psm + (size_t)8 * mrp * 16);
+    __shared__ bool s_last;
     const int tid = threadIdx.x;
     const long long n = blockIdx.x * 128LL + tid;
     const bool live = n < N;
@@ -631,8 +649,10 @@ __global__ void __launch_bounds__(128) em_aff_planes_kernel(const float* __restr
         __syncthreads();
         const int k1 = (mt + 1) * KT < K ? (mt + 1) * KT : K;
         for (int k = mt * KT; k < k1; ++k) {
-            const float p = live ? fminf(fmaxf(aff[n * K + k], 0.f), 1.f) : 0.f;
-            int q = (int)rintf(p * (float)EM_QMAX);
+            const float sk = em_col_scale(S.colmax[k]);
+            const float isk = sk >= 1.17549435e-38f ? 1.f / sk : 0.f;        // power-of-two s_k: aff / s_k is exact and <= 1
+            const float p = live ? fmaxf(aff[n * K + k], 0.f) : 0.f;
+            int q = (int)rintf(p * isk * (float)EM_QMAX);
             const int qsum = __reduce_add_sync(0xffffffffu, q);
             if ((tid & 31) == 0 && qsum) atomicAdd(&s_resp[k], qsum);
             const int kl = k - mt * KT;
@@ -648,14 +668,25 @@ __global__ void __launch_bounds__(128) em_aff_planes_kernel(const float* __restr
         for (int i = tid; i < (int)(tile_bytes / 16); i += 128) dst[i] = reinterpret_cast<const uint4*>(tile)[i];
         __syncthreads();
     }
-    if (stats_resp)
-        for (int k = tid; k < K; k += 128)
-            if (s_resp[k]) atomicAdd(reinterpret_cast<unsigned long long*>(stats_resp + k), (unsigned long long)(long long)s_resp[k]);
+    for (int k = tid; k < K; k += 128)
+        if (s_resp[k]) atomicAdd(reinterpret_cast<unsigned long long*>(S.respQ + k), (unsigned long long)(long long)s_resp[k]);
+    // last CTA: integer sums -> statistics tail
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = atomicAdd(S.ticket, 1ULL) == (unsigned long long)gridDim.x - 1;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    for (int k = tid; k < K; k += 128) {
+        const long long rq = *reinterpret_cast<volatile long long*>(S.respQ + k);
+        stats_tail[k] = (double)rq * ((double)em_col_scale(S.colmax[k]) / (double)EM_QMAX);
+    }
+    if (tid == 0 && write_ll) stats_tail[K] = (double)*reinterpret_cast<volatile long long*>(S.llQ) / EM_LL_SCALE;
 }
 
-// int32 digit-plane accumulators of the M-step -> int64 numerators (units of 1 / EM_QMAX); clears the accumulators
-__global__ void em_pack_kernel(int* __restrict__ accM, int D, int Dpad, int K, int KT, int mrp, long long* __restrict__ stats,
-                               const int* done) {
+// int32 digit-plane accumulators of the M-step -> float64 numerators; clears the accumulators
+__global__ void em_pack_kernel(int* __restrict__ accM, int D, int Dpad, int K, int KT, int mrp, const uint32_t* __restrict__ colmax,
+                               double* __restrict__ stats, const int* done) {
     if (done && *done) return;
     const long long total = (long long)K * D;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -665,23 +696,23 @@ __global__ void em_pack_kernel(int* __restrict__ accM, int D, int Dpad, int K, i
         const size_t ps = (size_t)KT * Dpad;
         const long long q = (long long)a[0] + 256LL * (long long)a[ps] + 65536LL * (long long)a[2 * ps];
         a[0] = 0; a[ps] = 0; a[2 * ps] = 0;
-        stats[i] = q;
+        stats[i] = (double)q * ((double)em_col_scale(colmax[k]) / (double)EM_QMAX);
     }
 }
 
-__global__ void em_zero_tail_kernel(long long* stats, int K, long long KD, const int* done) {
+__global__ void em_empty_tail_kernel(double* stats_tail, int n, const int* done) {
     if (done && *done) return;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i <= K) stats[KD + i] = 0;
+    if (i < n) stats_tail[i] = 0.0;
 }
 
 // Stopping rule, evaluated on the (all-reduced) log-likelihood.  Mirrors the host loops
 //   while (abs((old - new) / old) > tol and it < max_iter) or it < min_iter      (bernoulli_mixture.py:139-156)
 //   while new - old > tol                                                          (bernoulli_em.py:24-33)
-__global__ void em_control_kernel(EmCtl* ctl, const long long* stats_ll) {
+__global__ void em_control_kernel(EmCtl* ctl, const double* stats_ll) {
     if (ctl->done) return;
     double* trace = reinterpret_cast<double*>(ctl + 1);
-    const double ll = (double)*stats_ll / EM_LL_SCALE;
+    const double ll = *stats_ll;
     if (ctl->ntrace == 0) ctl->ll_old = ctl->mode == 0 ? ll / (1.0 - ctl->tol) - 10.0 : -INFINITY;
     if (ctl->ntrace < ctl->cap) trace[ctl->ntrace] = ll;
     ctl->ntrace++;
@@ -726,7 +757,7 @@ using namespace tsr;
 extern "C" {
 
 size_t tsr_em_workspace_bytes(long long N, int D, int K) {
-    if (N < 0 || N >= (1ll << 31) || D < 1 || K < 1 || K > EM_MAX_K) return 0;
+    if (N < 0 || N >= (1ll << 24) || D < 1 || K < 1 || K > EM_MAX_K) return 0;
     return em_shape(N, D, K).total;
 }
 
@@ -736,11 +767,12 @@ size_t tsr_em_control_bytes(int max_trace) { return max_trace < 0 ? 0 : sizeof(E
 
 int tsr_em_workspace_init(void* workspace, long long N, int D, int K, void* stream) {
     TSR_REQUIRE(workspace, "tsr_em_workspace_init: null pointer");
-    TSR_REQUIRE(N >= 0 && N < (1ll << 31) && D >= 1 && K >= 1 && K <= EM_MAX_K, "tsr_em_workspace_init: bad sizes (1 <= num_mix <= %d)", EM_MAX_K);
+    TSR_REQUIRE(N >= 0 && N < (1ll << 24) && D >= 1 && K >= 1 && K <= EM_MAX_K,
+                "tsr_em_workspace_init: need 1 <= num_mix <= %d and fewer than 2^24 rows per rank", EM_MAX_K);
     int rc = require_sm100("tsr_em_workspace_init");
     if (rc) return rc;
     const EmShape s = em_shape(N, D, K);
-    // weight / posterior tiles (rows no component maps to must read as zero) and the int32 accumulators
+    // weight / posterior tiles (rows no component maps to must read as zero), the int32 accumulators, the small scratch
     TSR_CUDA(cudaMemsetAsync(workspace, 0, s.off_scratch, (cudaStream_t)stream));
     return TSR_OK;
 }
@@ -757,7 +789,7 @@ int tsr_em_control_init(void* ctl, int max_trace, double tol, int mode, int min_
     return TSR_OK;
 }
 
-int tsr_em_control_step(void* ctl, const long long* stats, int D, int K, void* stream) {
+int tsr_em_control_step(void* ctl, const double* stats, int D, int K, void* stream) {
     TSR_REQUIRE(ctl && stats && D >= 1 && K >= 1, "tsr_em_control_step: bad arguments");
     int rc = require_sm100("tsr_em_control_step");
     if (rc) return rc;
@@ -775,14 +807,27 @@ static int em_prepare(const EmShape& s, uint8_t* ws, const float* logT, const fl
     return check_launch("tsr_em_estep(prepare)");
 }
 
+// posteriors (device, [N][K]) -> digit planes + responsibility sums (+ log-likelihood) in the statistics tail
+static int em_planes(const EmShape& s, uint8_t* ws, const float* aff, double* stats, int write_ll, const int* done, cudaStream_t st) {
+    const size_t psm = s.tile_bytes + (size_t)s.K * 4;
+    static size_t psm_set = 0;
+    if (psm > psm_set) {
+        TSR_CUDA(cudaFuncSetAttribute(em_aff_planes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm));
+        psm_set = psm;
+    }
+    em_aff_planes_kernel<<<(unsigned)(s.Npad / 128), 128, psm, st>>>(aff, s.N, s.Npad, s.K, s.KT, s.Mtiles, s.mrp, ws + s.off_ablob,
+                                                                     em_small(ws, s), stats + (size_t)s.K * s.D, write_ll, done);
+    return check_launch("em_aff_planes_kernel");
+}
+
 int tsr_em_estep(const uint32_t* Xbits, long long N, int D, int rowwords, int K, const float* logT_or_null,
                  const float* logInvT_or_null, const float* logw, float* aff_or_null, float* scores_or_null,
-                 long long* stats_or_null, int hard, int update, void* workspace, const void* ctl_or_null, int impl,
+                 double* stats_or_null, int hard, int update, void* workspace, const void* ctl_or_null, int impl,
                  void* stream) {
     TSR_REQUIRE(Xbits && logw && workspace, "tsr_em_estep: null pointer");
     TSR_REQUIRE((logT_or_null == nullptr) == (logInvT_or_null == nullptr), "tsr_em_estep: pass both logT and logInvT, or neither");
     TSR_REQUIRE(K >= 1 && K <= EM_MAX_K, "tsr_em_estep: need 1 <= num_mix <= %d (got %d)", EM_MAX_K, K);
-    TSR_REQUIRE(N >= 0 && N < (1ll << 31) && D >= 1 && rowwords == tsr_rowwords(D), "tsr_em_estep: bad sizes");
+    TSR_REQUIRE(N >= 0 && N < (1ll << 24) && D >= 1 && rowwords == tsr_rowwords(D), "tsr_em_estep: bad sizes (fewer than 2^24 rows per rank)");
     TSR_REQUIRE(impl == TSR_IMPL_TENSOR || impl == TSR_IMPL_SIMT, "tsr_em_estep: unknown impl %d", impl);
     TSR_REQUIRE(!update || stats_or_null, "tsr_em_estep: update needs the statistics vector");
     TSR_REQUIRE(impl == TSR_IMPL_TENSOR || logT_or_null, "tsr_em_estep(simt): needs logT / logInvT");
@@ -793,25 +838,23 @@ int tsr_em_estep(const uint32_t* Xbits, long long N, int D, int rowwords, int K,
     uint8_t* ws = (uint8_t*)workspace;
     const int* done = ctl_or_null ? &((const EmCtl*)ctl_or_null)->done : nullptr;
     if (N == 0) {          // a rank without rows contributes zeros to the allreduce
-        if (update) em_zero_tail_kernel<<<(K + 1 + 255) / 256, 256, 0, st>>>(stats_or_null, K, (long long)K * D, done);
+        if (update) em_empty_tail_kernel<<<(K + 1 + 255) / 256, 256, 0, st>>>(stats_or_null + (size_t)K * D, K + 1, done);
         return check_launch("tsr_em_estep(empty)");
     }
     if (logT_or_null) {
         rc = em_prepare(s, ws, logT_or_null, logInvT_or_null, done, st);
         if (rc) return rc;
     }
+    const EmSmall sm = em_small(ws, s);
     PostArgs P;
     memset(&P, 0, sizeof(P));
     P.accE = (int*)(ws + s.off_accE); P.scratch = (float*)(ws + s.off_scratch); P.c = (const double*)(ws + s.off_c);
     P.scale = (const float*)(ws + s.off_scale); P.logw = logw; P.N = N; P.Npad = s.Npad; P.K = K; P.KT = s.KT; P.Mtiles = s.Mtiles;
-    P.mrp = s.mrp; P.aff = aff_or_null; P.scores_out = scores_or_null; P.hard = hard; P.update = update; P.done = done;
-    if (update) {
-        P.ablob = ws + s.off_ablob;
-        P.stats_resp = stats_or_null + (size_t)K * D;
-        P.stats_ll = stats_or_null + (size_t)K * D + K;
-        em_zero_tail_kernel<<<(K + 1 + 255) / 256, 256, 0, st>>>(stats_or_null, K, (long long)K * D, done);
-    }
-    const size_t psm = s.tile_bytes + (size_t)K * 4;
+    P.mrp = s.mrp; P.aff = aff_or_null ? aff_or_null : (float*)(ws + s.off_aff); P.scores_out = scores_or_null; P.hard = hard;
+    P.update = update; P.done = done; P.colmax = sm.colmax; P.llQ = sm.llQ;
+    if (update)     // (a stopped loop skips the kernels that would consume this, so clearing unconditionally is harmless)
+        TSR_CUDA(cudaMemsetAsync(ws + s.off_small, 0, s.off_scratch - s.off_small, st));
+    const size_t psm = (size_t)K * 4;
     const unsigned pgrid = (unsigned)(s.Npad / 128);
     if (impl == TSR_IMPL_SIMT) {
         long long blocks = (N * K + 127) / 128;
@@ -821,15 +864,15 @@ int tsr_em_estep(const uint32_t* Xbits, long long N, int D, int rowwords, int K,
                                                                s.Npad, done);
         rc = check_launch("tsr_em_estep(simt scores)");
         if (rc) return rc;
-        TSR_CUDA(cudaFuncSetAttribute(em_posterior_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm));
         em_posterior_kernel<false><<<pgrid, 128, psm, st>>>(P);
-        return check_launch("tsr_em_estep(posterior)");
+    } else {
+        rc = launch_bitgemm(Xbits, N, rowwords, ws + s.off_wblob, P.accE, s.Npad, s.nchunkE, s, done, st);
+        if (rc) return rc;
+        em_posterior_kernel<true><<<pgrid, 128, psm, st>>>(P);
     }
-    rc = launch_bitgemm(Xbits, N, rowwords, ws + s.off_wblob, P.accE, s.Npad, s.nchunkE, s, done, st);
-    if (rc) return rc;
-    TSR_CUDA(cudaFuncSetAttribute(em_posterior_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm));
-    em_posterior_kernel<true><<<pgrid, 128, psm, st>>>(P);
-    return check_launch("tsr_em_estep(posterior)");
+    rc = check_launch("tsr_em_estep(posterior)");
+    if (rc || !update) return rc;
+    return em_planes(s, ws, P.aff, stats_or_null, 1, done, st);
 }
 
 int tsr_transpose_bits(const uint32_t* Xbits, long long N, int D, int rowwords, uint32_t* XTbits, long long N_pad,
@@ -843,7 +886,7 @@ int tsr_transpose_bits(const uint32_t* Xbits, long long N, int D, int rowwords, 
 }
 
 int tsr_em_mstep(const uint32_t* Xbits, const uint32_t* XTbits_or_null, long long N, int D, int rowwords, int K,
-                 const float* aff_or_null, long long* stats, void* workspace, const void* ctl_or_null, int impl, void* stream) {
+                 const float* aff_or_null, double* stats, void* workspace, const void* ctl_or_null, int impl, void* stream) {
     TSR_REQUIRE(Xbits && stats && workspace, "tsr_em_mstep: null pointer");
     TSR_REQUIRE(K >= 1 && K <= EM_MAX_K, "tsr_em_mstep: need 1 <= num_mix <= %d (got %d)", EM_MAX_K, K);
     TSR_REQUIRE(N >= 0 && N < (1ll << 24), "tsr_em_mstep: at most 2^24 rows per rank (int32 digit-plane accumulators)");
@@ -859,35 +902,36 @@ int tsr_em_mstep(const uint32_t* Xbits, const uint32_t* XTbits_or_null, long lon
     const EmShape s = em_shape(N, D, K);
     uint8_t* ws = (uint8_t*)workspace;
     const int* done = ctl_or_null ? &((const EmCtl*)ctl_or_null)->done : nullptr;
+    const EmSmall sm = em_small(ws, s);
+    if (aff_or_null) {     // digit planes from the caller's posteriors (otherwise the last E-step left them in the workspace)
+        TSR_CUDA(cudaMemsetAsync(ws + s.off_small, 0, s.off_scratch - s.off_small, st));
+        long long blocks = (N * K + 255) / 256;
+        const long long cap = (long long)sm_count() * 8;
+        if (blocks > cap) blocks = cap;
+        em_colmax_kernel<<<(unsigned)blocks, 256, 0, st>>>(aff_or_null, N, K, sm.colmax, done);
+        rc = em_planes(s, ws, aff_or_null, stats, 0, done, st);
+        if (rc) return rc;
+    }
     if (impl == TSR_IMPL_SIMT) {
-        TSR_REQUIRE(aff_or_null, "tsr_em_mstep(simt): needs the posteriors");
+        const float* aff = aff_or_null ? aff_or_null : (const float*)(ws + s.off_aff);
         long long blocks = ((long long)K * D + 127) / 128;
         const long long cap = (long long)sm_count() * 32;
         if (blocks > cap) blocks = cap;
-        em_mstep_simt_kernel<<<(unsigned)blocks, 128, 0, st>>>(Xbits, N, D, rowwords, K, aff_or_null, stats, done);
+        em_mstep_simt_kernel<<<(unsigned)blocks, 128, 0, st>>>(Xbits, N, D, rowwords, K, aff, sm.colmax, stats, done);
         return check_launch("tsr_em_mstep(simt)");
     }
     TSR_REQUIRE(XTbits_or_null, "tsr_em_mstep: the tensor path needs the transposed bits (tsr_transpose_bits)");
-    if (aff_or_null) {     // digit planes from the caller's posteriors (otherwise the last E-step left them in the workspace)
-        const size_t psm = s.tile_bytes + (size_t)K * 4;
-        TSR_CUDA(cudaFuncSetAttribute(em_aff_planes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm));
-        em_zero_tail_kernel<<<(K + 255) / 256, 256, 0, st>>>(stats, K - 1, (long long)K * D, done);       // the K sums, not the log-likelihood
-        em_aff_planes_kernel<<<(unsigned)(s.Npad / 128), 128, psm, st>>>(aff_or_null, N, s.Npad, K, s.KT, s.Mtiles, s.mrp,
-                                                                         ws + s.off_ablob, stats + (size_t)K * D, done);
-        rc = check_launch("tsr_em_mstep(planes)");
-        if (rc) return rc;
-    }
     rc = launch_bitgemm(XTbits_or_null, D, (int)(s.Npad / 32), ws + s.off_ablob, (int*)(ws + s.off_accM), s.Dpad, (int)s.nchunkM, s,
                         done, st);
     if (rc) return rc;
     long long blocks = ((long long)K * D + 255) / 256;
     const long long cap = (long long)sm_count() * 8;
     if (blocks > cap) blocks = cap;
-    em_pack_kernel<<<(unsigned)blocks, 256, 0, st>>>((int*)(ws + s.off_accM), D, s.Dpad, K, s.KT, s.mrp, stats, done);
+    em_pack_kernel<<<(unsigned)blocks, 256, 0, st>>>((int*)(ws + s.off_accM), D, s.Dpad, K, s.KT, s.mrp, sm.colmax, stats, done);
     return check_launch("tsr_em_mstep(pack)");
 }
 
-int tsr_em_finalize(const long long* stats, long long N_total, int D, int K, float min_prob, float* templates, float* logT,
+int tsr_em_finalize(const double* stats, long long N_total, int D, int K, float min_prob, float* templates, float* logT,
                     float* logInvT, float* weights, float* logw, void* workspace_or_null, long long N_local,
                     const void* ctl_or_null, void* stream) {
     TSR_REQUIRE(stats && templates && logT && logInvT && weights && logw, "tsr_em_finalize: null pointer");
@@ -900,7 +944,7 @@ int tsr_em_finalize(const long long* stats, long long N_total, int D, int K, flo
     P.weights = weights; P.logw = logw; P.D = D; P.K = K;
     P.done = ctl_or_null ? &((const EmCtl*)ctl_or_null)->done : nullptr;
     if (workspace_or_null) {       // also lay the next E-step's weight planes out (tsr_em_estep with logT = NULL uses them)
-        TSR_REQUIRE(N_local >= 0 && N_local < (1ll << 31), "tsr_em_finalize: bad N_local");
+        TSR_REQUIRE(N_local >= 0 && N_local < (1ll << 24), "tsr_em_finalize: bad N_local");
         const EmShape s = em_shape(N_local, D, K);
         uint8_t* ws = (uint8_t*)workspace_or_null;
         P.KT = s.KT; P.mrp = s.mrp; P.nchunk = s.nchunkE;

@@ -9,10 +9,10 @@ Per EM iteration and rank:   stopping rule on the reduced log-likelihood (``cont
 ->  finalize (divide, clip, log: identical on every rank)  ->  E-step on the local rows
 (posteriors, responsibility sums, log-likelihood)  ->  M accumulation (numerators)  ->  ONE
 allreduce(sum) of the statistics vector [K*D numerators | K responsibility sums |
-log-likelihood].  The CUDA engine keeps that vector in exact int64 fixed point, so the
-reduced values -- and everything derived from them -- are bit-identical for every rank count.
-The stopping rule runs on the device: the host queues ``batch`` iterations at a time and reads
-the control block back once per batch; iterations past the stop are no-ops.  With a single
+log-likelihood] (float64).  Inside a rank the CUDA engine forms every entry as an exact integer
+sum, so a rank's statistics do not depend on the order of summation.  The stopping rule runs on
+the device: the host queues ``batch`` iterations at a time and reads the control block back once
+per batch; iterations past the stop are no-ops.  With a single
 rank no collective is issued.  Scoring/coding/detection never communicate.
 """
 import numpy as np

@@ -367,6 +367,27 @@ def detect(featbits, bank, D=None, impl=IMPL_TENSOR, out=None):
     return out
 
 
+def detect_best(featbits, bank, D=None, want_scores=False):
+    """detect + the mixture max fused into the kernel epilogue: featbits int32 (B,T,rowwords) ->
+    (best float32 (B,T), arg int16 (B,T) holding uint16 ids, scores (B,T,M) | None).  Same bits as
+    detect() followed by detect_reduce(..., tail_mode=1), without the (B,T,M) score matrix."""
+    featbits = _dev(featbits, torch.int32, "featbits")
+    B, T, rw = featbits.shape
+    D = bank.D if D is None else D
+    if rw != rowwords(D) or D != bank.D:
+        raise ValueError("feature width %d does not match the filters (%d)" % (D, bank.D))
+    if bank.L > T:
+        raise ValueError("templates of %d frames do not fit utterances of %d" % (bank.L, T))
+    dev = featbits.device
+    best = torch.empty((B, T), dtype=torch.float32, device=dev)
+    arg = torch.empty((B, T), dtype=torch.int16, device=dev)
+    keys = torch.empty((B, T), dtype=torch.int64, device=dev)
+    scores = torch.empty((B, T, bank.M), dtype=torch.float32, device=dev) if want_scores else None
+    _lib.call("tsr_detect_best", _ptr(featbits), B, T, D, rw, _ptr(bank.blob), bank.M, bank.L, bank.planes, _ptr(bank.cs),
+              _ptr(scores), _ptr(keys), _ptr(best), _ptr(arg), _stream())
+    return best, arg, scores
+
+
 def detect_reduce(scores, cs, L, tail_mode=1):
     """scores (B,T,M), cs (M,) | None -> (best float32 (B,T), arg int16 (B,T) holding uint16 ids)."""
     scores = _dev(scores, torch.float32, "scores")
@@ -431,8 +452,7 @@ def cluster_peaks(peak_bt, B, C0, C1):
 
 
 # ------------------------------------------------------------------------------- K4
-EM_QMAX = 8355711            # posteriors are quantised to q = round(aff * EM_QMAX) (three balanced base-256 digits)
-EM_LL_SCALE = float(1 << 20)  # fixed-point unit of the log-likelihood entry of the statistics vector
+EM_QMAX = 8355711            # posteriors are quantised to q = round(aff / s_k * EM_QMAX), s_k = 2^ceil(log2 max_n aff[n][k])
 
 
 class EmControl:
@@ -473,7 +493,7 @@ class EmState:
         dev = self.X.device
         nbytes = _lib.lib().tsr_em_workspace_bytes(self.N, self.D, self.K)
         if nbytes == 0:
-            raise ValueError("unsupported EM shape (need 1 <= num_mix <= 4095 and fewer than 2^31 rows)")
+            raise ValueError("unsupported EM shape (need 1 <= num_mix <= 4095 and fewer than 2^24 rows per rank)")
         with torch.cuda.device(dev):
             self.ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
             _lib.call("tsr_em_workspace_init", _ptr(self.ws), self.N, self.D, self.K, _stream())
@@ -483,8 +503,8 @@ class EmState:
             if self.N:
                 _lib.call("tsr_transpose_bits", _ptr(self.X), self.N, self.D, self.rw, _ptr(self.XT), self.Npad, _stream())
         self.aff = torch.zeros((self.N, self.K), dtype=torch.float32, device=dev)
-        # stats = [K*D numerators | K responsibility sums | log-likelihood] as exact integers (see tsr_b200.h)
-        self.stats = torch.zeros(self.K * self.D + self.K + 1, dtype=torch.int64, device=dev)
+        # stats = [K*D numerators | K responsibility sums | log-likelihood], float64 (see tsr_b200.h)
+        self.stats = torch.zeros(self.K * self.D + self.K + 1, dtype=torch.float64, device=dev)
 
     def estep(self, logT, logInvT, logw, hard=False, impl=IMPL_TENSOR, scores_out=None, update=True, ctl=None):
         """logT = logInvT = None: use the weight planes the last em_finalize(..., state=self) laid out."""
@@ -505,20 +525,19 @@ class EmState:
                       _ptr(self.ws), _ptr(ctl.buf) if ctl is not None else 0, int(impl), _stream())
 
     def numerators(self):
-        """float64 (K,D) view of the numerators in posterior units."""
-        return self.stats[:self.K * self.D].double().reshape(self.K, self.D) / EM_QMAX
+        return self.stats[:self.K * self.D].reshape(self.K, self.D)
 
     def resp_sums(self):
-        return self.stats[self.K * self.D:self.K * self.D + self.K].double() / EM_QMAX
+        return self.stats[self.K * self.D:self.K * self.D + self.K]
 
     def loglik(self):
-        return float(self.stats[self.K * self.D + self.K].item()) / EM_LL_SCALE
+        return float(self.stats[self.K * self.D + self.K].item())
 
 
 def em_finalize(stats, N_total, D, K, min_prob, templates, logT, logInvT, weights, logw, state=None, ctl=None):
     """M-step proper from the (all-reduced) statistics.  state: also lay out the weight planes of the next E-step
     in that EmState's workspace (then its estep may be called with logT = logInvT = None)."""
-    stats = _dev(stats, torch.int64, "stats")
+    stats = _dev(stats, torch.float64, "stats")
     with torch.cuda.device(stats.device):
         _lib.call("tsr_em_finalize", _ptr(stats), int(N_total), int(D), int(K), float(min_prob), _ptr(templates), _ptr(logT),
                   _ptr(logInvT), _ptr(weights), _ptr(logw), _ptr(state.ws) if state is not None else 0,
@@ -528,7 +547,7 @@ def em_finalize(stats, N_total, D, K, min_prob, templates, logT, logInvT, weight
 # every tensor-taking entry point runs with its arguments' device current (see _on_device)
 for _name in ("pack_edges", "unpack_edges", "pack_features", "unpack_features", "spread_edges", "edge_map", "threshold_edges",
               "edges_from_spectrogram", "spread_edge_blocks", "code_parts", "code_parts_mag_aux_terms", "patch_counts",
-              "extract_patches", "spread_codes", "spread_graph", "detect", "detect_reduce", "detect_float", "detect_peaks",
+              "extract_patches", "spread_codes", "spread_graph", "detect", "detect_best", "detect_reduce", "detect_float", "detect_peaks",
               "cluster_peaks", "em_finalize"):
     globals()[_name] = _on_device(globals()[_name])
 del _name

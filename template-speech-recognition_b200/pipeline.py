@@ -28,6 +28,7 @@ class ScoringPipeline:
         self.edge_orientations = edge_orientations
         self.impl_code = ops.IMPL_TENSOR
         self.impl_detect = ops.IMPL_TENSOR
+        self.fused_max = True
 
     def code(self, bits):
         """K1a + K2 + K1b: packed edges -> (codes, part feature bits)."""
@@ -37,11 +38,15 @@ class ScoringPipeline:
         fb = ops.spread_codes(codes, self.parts.K, *self.part_spread)
         return codes, fb
 
-    def score(self, fb):
-        """K3 + reduction: part feature bits -> (best, argbest, per-template scores)."""
+    def score(self, fb, want_scores=False):
+        """K3 with the mixture max fused into its epilogue: part feature bits -> (best, argbest, per-template
+        scores or None).  The (B,To,M) score matrix is only materialised on request (or on the SIMT cross-check
+        path, which reduces it with a second kernel)."""
         Fo_K = fb.shape[2]
         if self.bank.D > Fo_K * 32:
             raise ValueError("filter width %d does not match the coded feature rows" % self.bank.D)
+        if self.impl_detect == ops.IMPL_TENSOR and self.fused_max:
+            return ops.detect_best(fb, self.bank, want_scores=want_scores)
         scores = ops.detect(fb, self.bank, impl=self.impl_detect)
         best, arg = ops.detect_reduce(scores, self.bank.cs, self.bank.L, tail_mode=1)
         return best, arg, scores

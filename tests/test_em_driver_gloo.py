@@ -13,19 +13,15 @@ import torch.multiprocessing as mp
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-QMAX = 8355711
-LL_SCALE = float(1 << 20)
-
-
 class NumpyEngine:
-    """Host stand-in with the engine interface of em_driver.GpuEmEngine, including its exact int64
-    fixed-point statistics and the stopping rule (evaluated on the host here)."""
+    """Host stand-in with the engine interface of em_driver.GpuEmEngine: float64 statistics vector
+    [K*D numerators | K responsibility sums | log-likelihood], stopping rule evaluated on the host here."""
 
     def __init__(self, X, D, K):
         self.X = X.astype(np.float64)
         self.N, self.D, self.K = X.shape[0], D, K
         self.aff = torch.zeros((self.N, K), dtype=torch.float32)
-        self.stats = torch.zeros(K * D + K + 1, dtype=torch.int64)
+        self.stats = torch.zeros(K * D + K + 1, dtype=torch.float64)
 
     def new_params(self):
         z = lambda *s: torch.zeros(s, dtype=torch.float32)  # noqa: E731
@@ -39,7 +35,7 @@ class NumpyEngine:
         return self.aff
 
     def _q(self):
-        return np.rint(self.aff.numpy().astype(np.float64) * QMAX).astype(np.int64)
+        return self.aff.numpy().astype(np.float64)
 
     def estep(self, params, hard, impl=0, ctl=None, prepared=False):
         if ctl is not None and ctl["done"]:
@@ -51,25 +47,25 @@ class NumpyEngine:
         self.aff.copy_(torch.as_tensor((p / p.sum(1, keepdims=True)).astype(np.float32)))
         K, D = self.K, self.D
         self.stats[K * D:K * D + K] = torch.as_tensor(self._q().sum(0))
-        self.stats[K * D + K] = int(np.rint((np.log(p.sum(1)) + mx[:, 0]) * LL_SCALE).astype(np.int64).sum())
+        self.stats[K * D + K] = float((np.log(p.sum(1)) + mx[:, 0]).sum())
 
     def accumulate(self, impl=0, from_affinities=False, ctl=None):
         if ctl is not None and ctl["done"]:
             return
         K, D = self.K, self.D
         q = self._q()
-        self.stats[:K * D] = torch.as_tensor((q.T @ self.X.astype(np.int64)).reshape(-1))
+        self.stats[:K * D] = torch.as_tensor((q.T @ self.X).reshape(-1))
         if from_affinities:
             self.stats[K * D:K * D + K] = torch.as_tensor(q.sum(0))
 
     def loglik(self):
-        return float(self.stats[self.K * self.D + self.K]) / LL_SCALE
+        return float(self.stats[self.K * self.D + self.K])
 
     def finalize(self, stats, N_total, min_prob, params, ctl=None):
         if ctl is not None and ctl["done"]:
             return
         K, D = self.K, self.D
-        st = stats.numpy().astype(np.float64) / QMAX
+        st = stats.numpy().astype(np.float64)
         w = (st[K * D:K * D + K] / N_total).astype(np.float32)
         T = np.clip((st[:K * D].reshape(K, D) / N_total).astype(np.float32) / w[:, None], min_prob, 1 - min_prob)
         params["templates"].copy_(torch.as_tensor(T))
@@ -160,14 +156,13 @@ def test_two_rank_em_matches_single_rank(tmp_path):
     port = 29500 + (os.getpid() % 2000)
     mp.spawn(_worker, args=(2, port, X, K, out), nprocs=2, join=True)
     r = np.load(out)
-    # integer statistics: the two-rank run reproduces the single-rank one to the last bit
-    np.testing.assert_array_equal(r["trace"], single[0])
-    np.testing.assert_array_equal(r["T"], single[1])
-    np.testing.assert_array_equal(r["w"], single[2])
+    np.testing.assert_allclose(r["trace"], single[0], rtol=1e-9)
+    np.testing.assert_allclose(r["T"], single[1], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(r["w"], single[2], rtol=1e-5)
     # the queued loop stops at the same iteration with the same trace on 1 and 2 ranks, and matches a plain host loop
     assert int(r["it"]) == single[3] and 3 <= single[3] < 50
-    np.testing.assert_array_equal(r["tr2"], single[4])
-    np.testing.assert_array_equal(r["T2"], single[5])
+    np.testing.assert_allclose(r["tr2"], single[4], rtol=1e-9)
+    np.testing.assert_allclose(r["T2"], single[5], rtol=1e-5, atol=1e-6)
     assert len(single[4]) == single[3] + 1
     np.testing.assert_array_equal(single[4][:6], single[0][:6])
     tr = np.array(single[4])

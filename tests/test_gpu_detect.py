@@ -141,6 +141,38 @@ def test_detect_reduce_and_mixture_semantics(cuda):
     assert np.all(best0.cpu().numpy()[:, T - L + 1:] == 0) and np.all(arg0.cpu().numpy()[:, T - L + 1:] == 0)
 
 
+@pytest.mark.parametrize("planes", [0, 3, 4], ids=["fp16", "int8x2", "int8x3"])
+@pytest.mark.parametrize("B,T,D,M,L,with_cs", [(2, 296, 3600, 32, 40, True), (3, 50, 63, 5, 1, True), (5, 77, 1, 33, 13, False),
+                                               (1, 700, 64, 100, 200, True), (4, 130, 320, 7, 40, True), (2, 300, 3600, 45, 40, True)])
+def test_fused_mixture_max_equals_detect_then_reduce(cuda, B, T, D, M, L, with_cs, planes):
+    """tsr_detect_best (max / arg-max over templates fused into the detection epilogue, combined across the CTAs
+    that hold different template tiles) returns exactly the bits of detect() followed by detect_reduce(tail_mode=1):
+    the running np.maximum of get_train_data.py:964-992, first maximum wins (:275), max_m cs[m] in the tail."""
+    from tsr_b200 import ops
+    rs = np.random.RandomState(B * 1000 + T + M)
+    F = (rs.rand(B, T, D) < 0.2).astype(np.uint8)
+    LF = rs.randn(M, L, D).astype(np.float32)
+    if M > 4:
+        LF[3] = LF[1]                                      # an exact tie between two templates: the lower index must win
+    cs = rs.randn(M).astype(np.float32) if with_cs else None
+    if with_cs and M > 4:
+        cs[3] = cs[1]
+    bank = ops.FilterBank(LF, cs=cs, planes=planes)
+    fb = ops.pack_features(torch.from_numpy(F).cuda())
+    scores = ops.detect(fb, bank)
+    wb, wa = ops.detect_reduce(scores, bank.cs, L, tail_mode=1)
+    best, arg, sc2 = ops.detect_best(fb, bank, want_scores=True)
+    best2, arg2, none = ops.detect_best(fb, bank)
+    torch.cuda.synchronize()
+    assert none is None
+    assert torch.equal(sc2, scores)
+    for bb, aa in ((best, arg), (best2, arg2)):
+        assert torch.equal(bb, wb)
+        assert torch.equal(aa, wa)
+    if M > 4:
+        assert not bool((arg == 3).any())
+
+
 def test_float_variants_bit_exact(cuda, golden):
     from tsr_b200 import compute_likelihood_linear_filter as clf
     g = golden

@@ -59,12 +59,16 @@ def test_estep_matches_numpy(cuda, N, D, K, impl):
     got_aff = st.aff.cpu().numpy()
     np.testing.assert_allclose(got_aff, aff, atol=1e-5 if impl == 0 else 2e-4)
     np.testing.assert_allclose(got_aff.sum(1), 1.0, atol=1e-5)
-    # statistics are exact integers of the quantised posteriors q = rint(aff32 * QMAX)
-    q = np.rint(got_aff * np.float32(QMAX)).astype(np.int64)
+    # statistics are exact integer sums of the posteriors quantised per component: q = rint(aff32 / s_k * QMAX) with
+    # s_k the smallest power of two >= max_n aff32[n][k]; one float64 scaling at the end
+    sk = np.exp2(np.ceil(np.log2(np.maximum(got_aff.max(0).astype(np.float64), 1e-300)))).astype(np.float32)
+    q = np.rint((got_aff * (np.float32(1) / sk)[None]) * np.float32(QMAX)).astype(np.int64)
+    unit = sk.astype(np.float64) / QMAX
     stats = st.stats.cpu().numpy()
-    np.testing.assert_array_equal(stats[K * D:K * D + K], q.sum(0))
-    np.testing.assert_array_equal(stats[:K * D].reshape(K, D), q.T @ X.astype(np.int64))
+    np.testing.assert_array_equal(stats[K * D:K * D + K], q.sum(0).astype(np.float64) * unit)
+    np.testing.assert_array_equal(stats[:K * D].reshape(K, D), (q.T @ X.astype(np.int64)).astype(np.float64) * unit[:, None])
     np.testing.assert_allclose(st.numerators().cpu().numpy(), aff.T @ Xd, rtol=1e-5, atol=1e-4 if impl == 0 else 2e-2)
+    np.testing.assert_allclose(st.resp_sums().cpu().numpy(), aff.sum(0), rtol=1e-5 if impl == 0 else 1e-3)
     # the accumulators were cleared behind the reads: a second pass gives the same bits
     before = st.stats.clone()
     st.estep(torch.from_numpy(logT).cuda(), torch.from_numpy(logI).cuda(), torch.from_numpy(logw).cuda(), impl=impl)
@@ -95,6 +99,33 @@ def test_mstep_from_identical_affinities(cuda, oracle, K, D):
         np.testing.assert_allclose(par["weights"].cpu().numpy(), a.weights, rtol=1e-5)
         np.testing.assert_allclose(par["logT"].cpu().numpy(), a.log_templates, rtol=1e-5, atol=1e-6)
         np.testing.assert_allclose(par["logInvT"].cpu().numpy(), a.log_invtemplates, rtol=1e-5, atol=1e-6)
+
+
+def test_vanishing_component_keeps_relative_precision(cuda, oracle):
+    """A component whose total responsibility is 1e-20 of the mass still defines its template through the RATIO of
+    its sums (bernoulli_mixture.py:179-181).  Posteriors are quantised below a per-component power-of-two scale, so
+    such a component keeps 24 significant bits instead of rounding to zero (which would kill it for good)."""
+    from tsr_b200 import ops, synth
+    N, D, K = 1500, 96, 4
+    X, _, _, _ = synth.em_data(N=N, D=D, K=3, seed=6)
+    rs = np.random.RandomState(3)
+    aff = rs.dirichlet(np.ones(K), size=N).astype(np.float32)
+    aff[:, 2] *= np.float32(1e-20)                       # vanishing column
+    aff[:, 3] = 0
+    aff[17, 3] = np.float32(3e-31)                       # a single row with a tiny weight owns component 3
+    a = oracle.BernoulliMixture(K, X)
+    a.affinities = aff.copy()
+    a.min_probability = np.float32(.05)
+    a.M_step()
+    st = ops.EmState(ops.pack_features(torch.from_numpy(X[None]).cuda())[0], D, K)
+    for impl in (0, 1):
+        st.mstep_accumulate(impl=impl, aff=torch.from_numpy(aff).cuda())
+        z = lambda *sh: torch.zeros(sh, dtype=torch.float32, device="cuda")  # noqa: E731
+        par = dict(templates=z(K, D), logT=z(K, D), logInvT=z(K, D), weights=z(K), logw=z(K))
+        ops.em_finalize(st.stats, N, D, K, .05, par["templates"], par["logT"], par["logInvT"], par["weights"], par["logw"])
+        np.testing.assert_allclose(par["templates"].cpu().numpy(), a.work_templates, rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(par["weights"].cpu().numpy(), a.weights, rtol=1e-5)
+        np.testing.assert_array_equal(par["templates"].cpu().numpy()[3], np.where(X[17] != 0, np.float32(.95), np.float32(.05)))
 
 
 def test_template_loglikelihoods_is_a_pure_accessor(cuda, oracle):

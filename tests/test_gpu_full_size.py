@@ -171,16 +171,15 @@ def test_em_config4_properties(cuda):
     st.mstep_accumulate()
     z = st.aff.argmax(1)
     assert torch.equal(st.aff.sum(1), torch.ones(N, device="cuda")) and set(torch.unique(st.aff).tolist()) <= {0.0, 1.0}
-    QMAX = 8355711
     numer = st.stats[:K * D].view(K, D)
     resp = st.stats[K * D:K * D + K]
-    assert torch.equal(resp, torch.bincount(z, minlength=K) * QMAX)
+    assert torch.equal(resp, torch.bincount(z, minlength=K).double())
     for k in (0, 7, 15):
         rows = X[z == k]
         bitsum = torch.zeros(D, dtype=torch.int64, device="cuda")
         for lo in range(0, rows.shape[0], 4096):
             bitsum += ops.unpack_features(rows[None, lo:lo + 4096].contiguous(), D)[0].sum(0, dtype=torch.int64)
-        assert torch.equal(numer[k], bitsum * QMAX)              # exact integer statistics
+        assert torch.equal(numer[k], bitsum.double())            # exact integer statistics
     # soft EM: monotone log-likelihood, parameters in range
     lls = []
     for _ in range(6):
@@ -194,12 +193,37 @@ def test_em_config4_properties(cuda):
     assert float((st.aff.sum(1) - 1).abs().max()) < 1e-5
 
 
+def _em_float64(X, K, minp, iters, init_minp=.01):
+    """The same EM (bernoulli_mixture.py: round-robin start :205-208, E :263-280, M :177-193) carried in float64
+    throughout: the yardstick that tells the reference's own float32 noise from an error of the GPU path."""
+    N, D = X.shape
+    Xd = X.astype(np.float64)
+    T = np.zeros((K, D))
+    for k in range(K):
+        T[k] = Xd[K * np.arange(N // K) + k].mean(0)
+    T = np.clip(T, init_minp, 1 - init_minp)
+    w = np.ones(K) / K
+    trace = []
+    for _ in range(iters + 1):
+        ll = Xd @ np.log(T).T + (1 - Xd) @ np.log(1 - T).T + np.log(w)[None]
+        mx = ll.max(1, keepdims=True)
+        p = np.exp(ll - mx)
+        s = p.sum(1, keepdims=True)
+        trace.append(float((np.log(s[:, 0]) + mx[:, 0]).sum()))
+        aff = p / s
+        w = aff.mean(0)
+        T = np.clip((aff.T @ Xd) / N / w[:, None], minp, 1 - minp)
+    return trace
+
+
 def test_part_dictionary_training_full_size(cuda, oracle):
     """The reference's real part-dictionary job (Notebook/12/reestimate_parts.py:79-83): 193 474 patches of
-    5x5x8 = 200 features, 200 components.  Log-likelihood trace of the first iterations against the NumPy
-    restatement, 1e-5 relative."""
-    from tsr_b200 import synth
+    5x5x8 = 200 features, 200 components.  Log-likelihood trace of the first iterations against (i) the same EM in
+    float64, 1e-6 relative, and (ii) the NumPy restatement of the reference (float32 BLAS products and sums, as the
+    reference computes them), 1e-5 relative except at iteration 2, where the restatement itself is 1.1e-5 away
+    from the float64 run (-19 678 834 vs -19 679 046.4) while the GPU trace is within 2e-8 of it."""
     from tsr_b200.bernoulli_mixture import BernoulliMixture
+    from tsr_b200 import synth
     N, D, K = 193474, 200, 200
     X, _, _, _ = synth.em_data(N=N, D=D, K=60, seed=12)
     a = oracle.BernoulliMixture(K, X)
@@ -207,6 +231,11 @@ def test_part_dictionary_training_full_size(cuda, oracle):
     b = BernoulliMixture(K, X)
     b.run_EM(1e-9, min_probability=.01, max_iter=4, min_iter=4)
     assert b.iterations == a.iterations == 4
-    np.testing.assert_allclose(b.loglikelihood_trace, a.loglikelihood_trace, rtol=1e-5)
+    t64 = _em_float64(X, K, .01, 4)
+    np.testing.assert_allclose(b.loglikelihood_trace, t64, rtol=1e-6)
+    ref = np.array(a.loglikelihood_trace, np.float64)
+    np.testing.assert_allclose(ref, t64, rtol=2e-5)                      # the reference's own float32 noise floor
+    np.testing.assert_allclose(b.loglikelihood_trace, ref, rtol=2e-5)
+    np.testing.assert_allclose(np.delete(b.loglikelihood_trace, 2), np.delete(ref, 2), rtol=1e-5)
     np.testing.assert_allclose(b.weights, a.weights, atol=1e-5)
     assert b.templates.shape == (K, D) and b.affinities.shape == (N, K)
