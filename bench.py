@@ -136,7 +136,7 @@ def _cpu_init(m_sub, use_ref):
     Tm, bgd = synth.templates(M=m_sub, L=L_TEMPL, Fd=FO, Kd=K_PARTS)
     W, c = synth.linear_filters(Tm, bgd)
     _CPU.update(code=ref[0].code_parts if ref else oracle.code_parts, spread=ref[0].spread_patches if ref else oracle.spread_patches,
-                det=ref[2].detect if ref else oracle.detect, spread_edges=oracle._spread_edges, lp=lp, lip=lip, W=W, c=c, m_sub=m_sub,
+                det=ref[2].detect if ref else oracle.detect, spread_edges=oracle.spread_edge_blocks, lp=lp, lip=lip, W=W, c=c, m_sub=m_sub,
                 ori=ops.DEFAULT_EDGE_ORIENTATIONS.astype(int), edges=synth.utterance_edges)
 
 
@@ -147,10 +147,7 @@ def _cpu_worker(u):
     C = _CPU
     X = C["edges"](u)
     t0 = time.perf_counter()
-    Xs = np.zeros_like(X)
-    for e in range(8):                                      # edge_signal_proc.py:1635-1663, NumPy restatement
-        for s in range(0, T_FRAMES, EDGE_BLOCK):
-            Xs[s:s + EDGE_BLOCK, :, e] = C["spread_edges"](X[s:s + EDGE_BLOCK, :, e].T.astype(float), C["ori"][e], EDGE_RADIUS).T
+    Xs = C["spread_edges"](X, EDGE_RADIUS, EDGE_BLOCK)         # edge_signal_proc.py:1595-1663, NumPy restatement
     out = C["code"](Xs, C["lp"], C["lip"], EDGE_THR)        # get_train_data.py:2619-2625
     codes = np.argmax(out, -1)
     S = C["spread"](codes, PART_SPREAD[0], PART_SPREAD[1], K_PARTS)
@@ -229,7 +226,7 @@ def run_reference(args):
 
 
 def workload_config(batch):
-    return {"workload": "config3 full scoring pipeline: spread_edges(r=1,block=40) -> code_parts(100 parts 5x5x8, thr 12, argmax) "
+    return {"workload": "config3 full scoring pipeline: spread_edges(r=1,block=40; fused into the next kernel) -> code_parts(100 parts 5x5x8, thr 12, argmax) "
                         "-> spread_patches(2,2) -> 32 x 40-frame part-level template LLR detect -> max/argmax",
             "utterance": "300 frames x 40 bands x 8 edges", "utterances_per_gpu": batch, "parts": K_PARTS, "templates": M_TEMPL,
             "template_frames": L_TEMPL, "sharding": "by utterance, no collective",
@@ -267,23 +264,27 @@ def run_native(args):
     flush_rd = torch.zeros(256 << 18, dtype=torch.int32, device=dev)           # read-only second pass: leaves the L2 cold AND clean
     stream = torch.cuda.current_stream()
 
+    fused = not args.simt and not args.no_fuse
+
     def step(evs=None):
         def mark(i):
             if evs is not None:
                 evs[i].record(stream)
         mark(0)
-        sb = ops.spread_edges(bits, EDGE_RADIUS, None, "line", EDGE_BLOCK)
+        if fused:      # K1a rides inside K2's producers: no spread_edges launch, no second pass over the edge map
+            codes, _, _ = ops.code_parts(bits, pipe.parts, EDGE_THR, impl=pipe.impl_code, edge_spread_radius=EDGE_RADIUS,
+                                         edge_block_len=EDGE_BLOCK)
+        else:
+            codes, _, _ = ops.code_parts(pipe.spread(bits), pipe.parts, EDGE_THR, impl=pipe.impl_code)
         mark(1)
-        codes, _, _ = ops.code_parts(sb, pipe.parts, EDGE_THR, impl=pipe.impl_code)
-        mark(2)
         fb = ops.spread_codes(codes, K_PARTS, *PART_SPREAD)
-        mark(3)
+        mark(2)
         if args.simt:
             scores = ops.detect(fb, pipe.bank, impl=pipe.impl_detect)
             best, arg = ops.detect_reduce(scores, pipe.bank.cs, L_TEMPL, tail_mode=1)
         else:
             best, arg, _ = ops.detect_best(fb, pipe.bank)        # max / arg-max over the 32 templates fused into the epilogue
-        mark(4)
+        mark(3)
         return best, arg
 
     for _ in range(args.warmup):
@@ -299,15 +300,24 @@ def run_native(args):
     for _ in range(args.steps):
         flush.fill_(1)                                                          # evict L2 (outside the per-step events)
         flush_rd.sum()                                                          # ... and push the fill's dirty lines out to HBM
-        evs = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
         step(evs)
         all_evs.append(evs)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     clocks = sampler.stop() if rank == 0 else None          # clocks cover exactly the timed region
-    step_ms = [e[0].elapsed_time(e[4]) for e in all_evs]
-    stage_ms = [float(np.mean([e[i].elapsed_time(e[i + 1]) for e in all_evs])) for i in range(4)]
+    step_ms = [e[0].elapsed_time(e[3]) for e in all_evs]
+    stage_ms = [float(np.mean([e[i].elapsed_time(e[i + 1]) for e in all_evs])) for i in range(3)]
+    # K1a on its own (not part of the step when fused): cold-L2 launches of the stand-alone kernel, for the HBM figure
+    k1a = []
+    for _ in range(5):
+        flush.fill_(1); flush_rd.sum()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream); pipe.spread(bits); e1.record(stream)
+        k1a.append((e0, e1))
+    torch.cuda.synchronize()
+    k1a_ms = float(np.mean([a.elapsed_time(b) for a, b in k1a]))
     total_ms = float(sum(step_ms))
     t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -354,20 +364,22 @@ def run_native(args):
         peaks = measured_peaks()
         frames = B * T_FRAMES * world
         value = frames * args.steps / (total_ms * 1e-3)
-        det_ms = stage_ms[3]
+        det_ms = stage_ms[2]
         det_tf = FLOP_DETECT * B / (det_ms * 1e-3) / 1e12
-        code_tf = FLOP_CODE * B / (stage_ms[1] * 1e-3) / 1e12
+        code_tf = FLOP_CODE * B / (stage_ms[0] * 1e-3) / 1e12
         stages = {
-            "spread_edges": {"ms": stage_ms[0], "bound": "hbm", "achieved_gbs": BYTES_SPREAD_EDGES * B / (stage_ms[0] * 1e-3) / 1e9,
-                             "frac": BYTES_SPREAD_EDGES * B / (stage_ms[0] * 1e-3) / 1e9 / peaks["hbm"]},
-            "code_parts": {"ms": stage_ms[1], "bound": "tensor", "achieved_tflops": code_tf, "frac": code_tf / peaks["tf_burst"],
-                           "frac_sustained": code_tf / peaks["tf_sustained"]},
-            "spread_codes": {"ms": stage_ms[2], "bound": "hbm", "achieved_gbs": BYTES_SPREAD_CODES * B / (stage_ms[2] * 1e-3) / 1e9,
-                             "frac": BYTES_SPREAD_CODES * B / (stage_ms[2] * 1e-3) / 1e9 / peaks["hbm"]},
+            "code_parts": {"ms": stage_ms[0], "bound": "tensor", "achieved_tflops": code_tf, "frac": code_tf / peaks["tf_burst"],
+                           "frac_sustained": code_tf / peaks["tf_sustained"],
+                           "includes": "edge spreading (radius 1 per 40-frame block) fused into the producers" if fused else "spread_edges launches + code_parts"},
+            "spread_codes": {"ms": stage_ms[1], "bound": "hbm", "achieved_gbs": BYTES_SPREAD_CODES * B / (stage_ms[1] * 1e-3) / 1e9,
+                             "frac": BYTES_SPREAD_CODES * B / (stage_ms[1] * 1e-3) / 1e9 / peaks["hbm"]},
             "detect": {"ms": det_ms, "bound": "tensor", "achieved_tflops": det_tf, "frac": det_tf / peaks["tf_burst"],
-                       "frac_sustained": det_tf / peaks["tf_sustained"]},
-            "detect_includes": "the 2.4 MB key clear, the detection kernel with the fused max / arg-max over templates, the key decode",
-            "config2_coding_frames_per_s": B * T_FRAMES * world / (sum(stage_ms[:3]) * 1e-3),
+                       "frac_sustained": det_tf / peaks["tf_sustained"],
+                       "includes": "the 2.4 MB key clear, the detection kernel with the fused max / arg-max over templates, the key decode"},
+            "spread_edges_standalone": {"ms": k1a_ms, "bound": "hbm", "achieved_gbs": BYTES_SPREAD_EDGES * B / (k1a_ms * 1e-3) / 1e9,
+                                        "frac": BYTES_SPREAD_EDGES * B / (k1a_ms * 1e-3) / 1e9 / peaks["hbm"],
+                                        "note": "not in the step: K1a as its own launches (cold L2), kept for radii / direction tables K2 does not fuse"},
+            "config2_coding_frames_per_s": B * T_FRAMES * world / (sum(stage_ms[:2]) * 1e-3),
         }
         line = {
             "metric": "edge-frames/sec coded+scored", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
@@ -395,7 +407,7 @@ def run_native(args):
             "e2e_device_pack": {"value": frames * e2e_steps / e2e_devpack_s, "unit": "frames/s", "h2d_bytes_per_step": int(X_pinned.numel()),
                                 "d2h_bytes_per_step": int(B * TO * 4 + B * TO * 2),
                                 "api": "same call with pack='device': the unpacked uint8 tensor crosses PCIe and is packed by the GPU"},
-            "gpu_launches": (6 if not args.simt else 5) * args.steps,   # spread_edges, code_parts, spread_codes, key memset, detect, decode
+            "gpu_launches": (4 if fused else 6) * args.steps,   # code_parts (+ fused spreading), spread_codes, detect, key decode (+ 1 memset node)
             "clocks": clocks,
         }
         if world == 1 and not args.no_cpu:
@@ -608,6 +620,7 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--simt", action="store_true", help="use the SIMT cross-check kernels for coding and detection")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-fuse", action="store_true", help="run the edge spreading as its own launches instead of inside code_parts")
     ap.add_argument("--no-extra", action="store_true", help="skip the config-4 (EM) and config-5 (stream) sub-results of the default line")
     ap.add_argument("--planes", default="int8x3", choices=["fp16", "bf16", "int8x2", "int8x3"],
                     help="weight-plane format of the detection stage (DESIGN.md section 4)")

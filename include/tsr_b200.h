@@ -99,10 +99,15 @@ int    tsr_prepare_parts(const double* log_parts, const double* log_invparts, in
 /* codes[b][i][j] = 0 if gate fails else 1 + argmax_k score (lowest k wins ties);
  * gate: count >= threshold [and mask_count > mask_threshold when mask_threshold >= 0].
  * scores_or_null float [B][To][Fo][K] (score = sum_{a,b,z} X ? lp : lip, written for every
- * location); counts_or_null uint16 [B][To][Fo] edge counts.  To = T-ph+1, Fo = F-pw+1. */
+ * location); counts_or_null uint16 [B][To][Fo] edge counts.  To = T-ph+1, Fo = F-pw+1.
+ * edge_spread_radius = 1 (tensor path): K1a fused into the kernel's producers -- the input is the UNSPREAD edge
+ * map and every byte is spread on the fly exactly as tsr_spread_edges(radius 1, mode 0, the unit direction table of
+ * edge_signal_proc.py:1751-1821, block_len = edge_block_len) would, with the reference's ragged-last-block rule
+ * (the frames past the last whole block belong to the window of the final block_len frames, :1595-1633).
+ * edge_spread_radius = 0: bits are coded as given. */
 int tsr_code_parts(const uint8_t* bits, const void* parts_blob, int K, int ph, int pw, int threshold,
                    int mask_threshold, uint8_t* codes, float* scores_or_null, uint16_t* counts_or_null, int B, int T,
-                   int F, int impl, void* stream);
+                   int F, int edge_spread_radius, int edge_block_len, int impl, void* stream);
 
 /* Replaces the magnitude / auxiliary Bernoulli terms of code_parts.code_parts_mag_aux
  * (code_parts.pyx:138-242).  scores float [B][To][Fo][K] holds the edge log-likelihoods written by

@@ -289,6 +289,31 @@ def spread_edgemap_all(T, edge_feature_row_breaks, spread_length):
         T[s:e, :] = out
 
 
+def spread_edge_blocks(X, spread_length, block_length, edge_orientations=None):
+    """The spreading step of _edge_map_threshold_segments (edge_signal_proc.py:1617-1663) on an already binary edge
+    tensor X uint8 (T, F, 8): every block_length-frame block is spread on its own; a ragged last block is the tail of
+    the spread window of the final block_length frames (:1595-1633).  Returns a new (T, F, 8) uint8 array."""
+    ori = EDGE_ORIENTATIONS if edge_orientations is None else np.asarray(edge_orientations).astype(int)
+    X = np.asarray(X)
+    T = X.shape[0]
+    out = np.zeros_like(X)
+
+    def one(win):
+        res = np.empty_like(win)
+        for e in range(win.shape[2]):
+            res[:, :, e] = _spread_edges(win[:, :, e].T.astype(np.float64), ori[e], spread_length).T
+        return res
+
+    if block_length <= 0:
+        return one(X)
+    nfull, last = T // block_length, T % block_length
+    for blk in range(nfull):
+        out[blk * block_length:(blk + 1) * block_length] = one(X[blk * block_length:(blk + 1) * block_length])
+    if last > 0:
+        out[-last:] = one(X[-block_length:])[-last:]
+    return out
+
+
 # --------------------------------------------------------- edge front end (N4, N3)
 ABST_THRESHOLD = np.array([0.025, 0.025, 0.015, 0.015, 0.02, 0.02, 0.02, 0.02])   # edge_signal_proc.py:1187
 # orientation table the extractor returns (:1751-1821): (frequency step, time step) per block

@@ -26,7 +26,7 @@ SIGNATURES = {
     "tsr_spread_edges": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _i, _vp]),
     "tsr_parts_blob_bytes": (_sz, [_i, _i, _i]),
     "tsr_prepare_parts": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _i, _vp, _vp]),
-    "tsr_code_parts": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "tsr_code_parts": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "tsr_code_parts_mag_aux_terms": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "tsr_patch_counts": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "tsr_patch_select_workspace_bytes": (_sz, [_ll]),

@@ -139,6 +139,7 @@ struct CodeArgs {
     uint16_t* counts;
     int B, T, F, To, Fo;
     int threshold, mask_threshold;
+    int spread_radius, block_len;   // fused edge spreading in the producers (radius 1, unit direction table); 0 = input used as is
     PartsLayout L;
     int dbg;            // debug experiments: 1 = epilogue skips TMEM reads, 2 = MMA warp skips tcgen05.mma
     long long* trace;   // optional debug timeline of CTA 0: [tile][8] clock64 stamps (tools/trace_code_parts.py)
@@ -157,6 +158,33 @@ struct CodeArgs {
 #define CP_TRACE_TILES 96
 #define CP_TRACE(slot) do { } while (0)
 #endif
+
+// K1a fused into the producers: radius-1 line spread of the packed edge byte at flattened position p of one utterance
+// (edge_signal_proc.py:1397-1417 with the unit direction table of :1751-1821: orientations 0,1 along time, 2,3 along
+// frequency, 4,5 along the diagonal, 6,7 along the anti-diagonal), applied inside each block_len-frame block as
+// _edge_map_threshold_segments does (:1617-1663); the frames of a ragged last block belong to the window of the final
+// block_len frames (:1595-1633).  Nine byte loads per position instead of one, no extra launch and no second pass
+// over the edge map.
+__device__ __forceinline__ uint32_t spread1_byte(const uint8_t* __restrict__ src, int p, int T, int F, int block_len) {
+    const int t = p / F, f = p - t * F;
+    int lo = 0, hi = T;
+    if (block_len > 0) {
+        const int tfull = (T / block_len) * block_len;
+        if (t >= tfull) { lo = T - block_len; if (lo < 0) lo = 0; }
+        else { lo = (t / block_len) * block_len; hi = lo + block_len; }
+    }
+    const bool up = t - 1 >= lo, dn = t + 1 < hi, lf = f > 0, rt = f + 1 < F;
+    uint32_t v = src[p];
+    if (up) v |= src[p - F] & 0x03u;
+    if (dn) v |= src[p + F] & 0x03u;
+    if (lf) v |= src[p - 1] & 0x0Cu;
+    if (rt) v |= src[p + 1] & 0x0Cu;
+    if (up && lf) v |= src[p - F - 1] & 0x30u;
+    if (dn && rt) v |= src[p + F + 1] & 0x30u;
+    if (dn && lf) v |= src[p + F - 1] & 0xC0u;
+    if (up && rt) v |= src[p - F + 1] & 0xC0u;
+    return v;
+}
 
 // --------------------------------------------------------------------------- SIMT path
 // One warp per location, lanes over parts; walks the set bits of the window in (a,b,z) order and
@@ -321,7 +349,7 @@ __global__ void __launch_bounds__(CP_THREADS, 1) code_parts_tc_kernel(CodeArgs A
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 int pos = pt + 128 * j, p = p0 + pos;
-                pre[j] = (pos < npos && p < plimit) ? src[p] : 0u;
+                pre[j] = (pos < npos && p < plimit) ? (A.spread_radius ? spread1_byte(src, p, A.T, A.F, A.block_len) : (uint32_t)src[p]) : 0u;
             }
         };
         if ((long long)blockIdx.x < ntiles) prefetch(blockIdx.x);
@@ -342,7 +370,8 @@ __global__ void __launch_bounds__(CP_THREADS, 1) code_parts_tc_kernel(CodeArgs A
                 const uint8_t* src = A.bits + (size_t)b * A.T * A.F;
                 for (int pos = pt + 512; pos < npos; pos += 128) {
                     int p = p0 + pos;
-                    *reinterpret_cast<uint4*>(dst + pos * 16) = expand_byte(p < plimit ? src[p] : 0u, one);
+                    const uint32_t byte = p < plimit ? (A.spread_radius ? spread1_byte(src, p, A.T, A.F, A.block_len) : (uint32_t)src[p]) : 0u;
+                    *reinterpret_cast<uint4*>(dst + pos * 16) = expand_byte(byte, one);
                 }
             }
             fence_proxy_async_smem();
@@ -552,13 +581,15 @@ int tsr_prepare_parts(const double* log_parts, const double* log_invparts, int K
 
 int tsr_code_parts(const uint8_t* bits, const void* parts_blob, int K, int ph, int pw, int threshold,
                    int mask_threshold, uint8_t* codes, float* scores_or_null, uint16_t* counts_or_null, int B, int T,
-                   int F, int impl, void* stream) {
+                   int F, int edge_spread_radius, int edge_block_len, int impl, void* stream) {
     if (B == 0) return TSR_OK;
     TSR_REQUIRE(bits && parts_blob, "tsr_code_parts: null pointer");
     TSR_REQUIRE(codes || scores_or_null || counts_or_null, "tsr_code_parts: no output requested");
     TSR_REQUIRE(K >= 1 && K <= 238 && ph >= 1 && pw >= 1 && ph * pw <= 64, "tsr_code_parts: unsupported parts shape (K <= 238, ph*pw <= 64)");
     TSR_REQUIRE(B >= 0 && T >= ph && F >= pw, "tsr_code_parts: input (T=%d,F=%d) smaller than the part window (%d,%d)", T, F, ph, pw);
     TSR_REQUIRE(impl == TSR_IMPL_TENSOR || impl == TSR_IMPL_SIMT, "tsr_code_parts: unknown impl %d", impl);
+    TSR_REQUIRE(edge_spread_radius == 0 || (edge_spread_radius == 1 && impl == TSR_IMPL_TENSOR && edge_block_len >= 0),
+                "tsr_code_parts: the fused edge spreading supports radius 1 on the tensor path (use tsr_spread_edges otherwise)");
     TSR_REQUIRE((long long)T * F < (1ll << 30), "tsr_code_parts: utterance too large (T*F >= 2^30); split in time");
     if (B == 0) return TSR_OK;
     int rc = require_sm100("tsr_code_parts");
@@ -567,6 +598,7 @@ int tsr_code_parts(const uint8_t* bits, const void* parts_blob, int K, int ph, i
     A.bits = bits; A.blob = (const uint8_t*)parts_blob; A.codes = codes; A.scores = scores_or_null; A.counts = counts_or_null;
     A.B = B; A.T = T; A.F = F; A.To = T - ph + 1; A.Fo = F - pw + 1;
     A.threshold = threshold; A.mask_threshold = mask_threshold;
+    A.spread_radius = edge_spread_radius; A.block_len = edge_block_len;
     A.trace = g_code_trace;
     A.dbg = g_code_dbg;
     A.L = parts_layout(K, ph, pw);

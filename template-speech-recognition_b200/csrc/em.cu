@@ -32,6 +32,7 @@ namespace tsr {
 #define EM_QMAX 8355711              // 127 * (1 + 256 + 65536): largest value of three balanced base-256 digits
 #define EM_KT_MAX 42                 // mixture components per 128-row M tile (3 planes each)
 #define EM_LL_SCALE 1048576.0        // 2^20: fixed-point unit in which a rank sums its rows' log-likelihoods (order independent)
+#define EM_C_SCALE 68719476736.0      // 2^36: fixed-point unit of c[k] = sum_d logInvT[k][d] (integer sums are order independent)
 #define EM_MAX_K 4095
 
 #define BG_THREADS 448               // 14 warps: loader, 8 expanders, 4 epilogue, MMA issuer
@@ -386,7 +387,7 @@ __device__ __forceinline__ float em_col_scale(uint32_t colmax_bits) {
 // arithmetic for the scores; exact integer sums of the quantised posteriors for the numerators.
 __global__ void em_scores_simt_kernel(const uint32_t* __restrict__ X, long long N, int D, int rw, int K,
                                       const float* __restrict__ logT, const float* __restrict__ logInvT,
-                                      const double* __restrict__ c, float* __restrict__ scratch, long long Npad, const int* done) {
+                                      const long long* __restrict__ c, float* __restrict__ scratch, long long Npad, const int* done) {
     if (done && *done) return;
     const long long total = N * K;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -404,7 +405,7 @@ __global__ void em_scores_simt_kernel(const uint32_t* __restrict__ X, long long 
                 acc = __fadd_rn(acc, __fsub_rn(lt[d], li[d]));
             }
         }
-        scratch[(size_t)k * Npad + n] = (float)((double)acc + c[k]);
+        scratch[(size_t)k * Npad + n] = (float)((double)acc + (double)c[k] / EM_C_SCALE);
     }
 }
 
@@ -421,7 +422,7 @@ __global__ void em_mstep_simt_kernel(const uint32_t* __restrict__ X, long long N
         long long acc = 0;
         for (long long n = 0; n < N; ++n)
             if ((X[n * rw + (d >> 5)] >> (d & 31)) & 1u) acc += (long long)rintf(fmaxf(aff[n * K + k], 0.f) * isk * (float)EM_QMAX);
-        stats[i] = (double)acc * ((double)sk / (double)EM_QMAX);
+        stats[i] = (double)acc / (double)EM_QMAX * (double)sk;     // exact multiples of EM_QMAX divide exactly (hard assignments)
     }
 }
 
@@ -438,7 +439,7 @@ struct ParamArgs {
     float *templates, *logT, *logInvT, *weights, *logw;   // FROM_STATS: written; else logT / logInvT are read
     int D, K, KT, mrp, nchunk;
     uint8_t* wblob;             // may be null (parameters only)
-    double* c;
+    long long* c;               // 2^-36 fixed point
     float* scale;
     const int* done;
 };
@@ -480,7 +481,7 @@ __global__ void __launch_bounds__(256) em_params_kernel(ParamArgs P) {
         const float sc = s_mx[0] > 0.f ? s_mx[0] / (float)EM_QMAX : 1.f;
         s_scale = sc;
         if (P.scale) P.scale[k] = sc;
-        if (P.c) P.c[k] = s_c[0];
+        if (P.c) P.c[k] = llrint(s_c[0] * EM_C_SCALE);
         if (FROM_STATS) { P.weights[k] = w; P.logw[k] = logf(w); }
     }
     __syncthreads();
@@ -528,6 +529,79 @@ __global__ void __launch_bounds__(256) em_params_kernel(ParamArgs P) {
     }
 }
 
+// The M-step proper of the iteration loop, fully parallel: one thread per 32-feature word of one component does
+// everything for its 32 parameters -- divide, clip, logs, the three weight digits -- in one pass.  No reduction is
+// needed for the quantisation step because the clip bounds |W| = |logT - logInvT| by log((1 - p_min) / p_min); c[k]
+// is summed in 2^-36 fixed point with integer atomics (order independent).  grid = (ceil(nchunk * 4 / 128), K).
+__global__ void __launch_bounds__(128) em_finalize_fast_kernel(ParamArgs P, float wbound) {
+    if (P.done && *P.done) return;
+    __shared__ long long s_c[4];
+    const int k = blockIdx.y, tid = threadIdx.x;
+    const int it = blockIdx.x * 128 + tid;
+    const size_t row = (size_t)k * P.D;
+    const float w = (float)P.stats[(size_t)P.K * P.D + k] / (float)P.N_total;          // np.mean(affinities, 0)
+    const float sc = wbound > 0.f ? wbound / (float)EM_QMAX : 1.f;
+    long long csum = 0;
+    if (it < P.nchunk * 4) {
+        const int c = it >> 2, wi = it & 3;
+        const int d0 = c * 128 + wi * 32;
+        uint32_t out[3][2][4];
+#pragma unroll
+        for (int p = 0; p < 3; ++p)
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) out[p][h][q] = 0u;
+#pragma unroll
+        for (int s = 0; s < 8; ++s)
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+                const int d = d0 + 8 * jj + s;
+                int q = 0;
+                if (d < P.D) {
+                    float t = (float)P.stats[row + d];                             // np.dot(affinities.T, data) as float32
+                    t = t / (float)P.N_total;                                      // /= num_data
+                    t = t / w;                                                     // /= weights
+                    t = fminf(fmaxf(t, P.min_prob), 1.f - P.min_prob);             // threshold_templates
+                    const float lt = logf(t), li = logf(1.f - t);
+                    P.templates[row + d] = t; P.logT[row + d] = lt; P.logInvT[row + d] = li;
+                    csum += llrint((double)li * EM_C_SCALE);
+                    float qf = rintf((lt - li) / sc);
+                    qf = fminf(fmaxf(qf, -(float)EM_QMAX), (float)EM_QMAX);
+                    q = (int)qf;
+                }
+#pragma unroll
+                for (int p = 0; p < 3; ++p) {
+                    const int digit = ((q + 128) & 255) - 128;
+                    q = (q - digit) >> 8;
+                    out[p][s >> 2][s & 3] |= (uint32_t)(digit & 255) << (8 * jj);
+                }
+            }
+        const int mt = k / P.KT, kl = k - mt * P.KT;
+        uint8_t* tile = P.wblob + ((size_t)mt * P.nchunk + c) * ((size_t)8 * P.mrp * 16);
+#pragma unroll
+        for (int p = 0; p < 3; ++p)
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+                *reinterpret_cast<uint4*>(tile + ((size_t)(2 * wi + h) * P.mrp + p * P.KT + kl) * 16) =
+                    make_uint4(out[p][h][0], out[p][h][1], out[p][h][2], out[p][h][3]);
+    }
+    for (int off = 16; off > 0; off >>= 1) csum += __shfl_xor_sync(0xffffffffu, csum, off);
+    if ((tid & 31) == 0) s_c[tid >> 5] = csum;
+    __syncthreads();
+    if (tid == 0) {
+        const long long tot = s_c[0] + s_c[1] + s_c[2] + s_c[3];
+        atomicAdd(reinterpret_cast<unsigned long long*>(P.c + k), (unsigned long long)tot);
+        if (blockIdx.x == 0) { P.scale[k] = sc; P.weights[k] = w; P.logw[k] = logf(w); }
+    }
+}
+
+__global__ void em_zero_c_kernel(long long* c, int K, const int* done) {
+    if (done && *done) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < K) c[i] = 0;
+}
+
 // ------------------------------------------------------------------------------------------------
 // Row kernel of the E-step.  Thread = data row.
 //   INT_SCORES: scores from the int32 digit-plane accumulators (which are cleared for the next E-step);
@@ -535,7 +609,7 @@ __global__ void __launch_bounds__(256) em_params_kernel(ParamArgs P) {
 struct PostArgs {
     int* accE;
     float* scratch;             // [K][Npad] float scores of the SIMT cross-check kernel
-    const double* c;
+    const long long* c;         // 2^-36 fixed point
     const float* scale;
     const float* logw;
     long long N, Npad;
@@ -570,7 +644,7 @@ __global__ void __launch_bounds__(128) em_posterior_kernel(PostArgs P) {
             const int a0 = a[0], a1 = a[pstride], a2 = a[2 * pstride];
             if (clear) { a[0] = 0; a[pstride] = 0; a[2 * pstride] = 0; }
             const double q = (double)a0 + 256.0 * (double)a1 + 65536.0 * (double)a2;
-            return q * (double)P.scale[k] + P.c[k];
+            return q * (double)P.scale[k] + (double)P.c[k] / EM_C_SCALE;
         }
         return (double)P.scratch[(size_t)k * P.Npad + n];
     };
@@ -679,7 +753,7 @@ __global__ void __launch_bounds__(128) em_aff_planes_kernel(const float* __restr
     __threadfence();
     for (int k = tid; k < K; k += 128) {
         const long long rq = *reinterpret_cast<volatile long long*>(S.respQ + k);
-        stats_tail[k] = (double)rq * ((double)em_col_scale(S.colmax[k]) / (double)EM_QMAX);
+        stats_tail[k] = (double)rq / (double)EM_QMAX * (double)em_col_scale(S.colmax[k]);
     }
     if (tid == 0 && write_ll) stats_tail[K] = (double)*reinterpret_cast<volatile long long*>(S.llQ) / EM_LL_SCALE;
 }
@@ -696,7 +770,7 @@ __global__ void em_pack_kernel(int* __restrict__ accM, int D, int Dpad, int K, i
         const size_t ps = (size_t)KT * Dpad;
         const long long q = (long long)a[0] + 256LL * (long long)a[ps] + 65536LL * (long long)a[2 * ps];
         a[0] = 0; a[ps] = 0; a[2 * ps] = 0;
-        stats[i] = (double)q * ((double)em_col_scale(colmax[k]) / (double)EM_QMAX);
+        stats[i] = (double)q / (double)EM_QMAX * (double)em_col_scale(colmax[k]);   // division first: exact for multiples of EM_QMAX
     }
 }
 
@@ -802,7 +876,7 @@ static int em_prepare(const EmShape& s, uint8_t* ws, const float* logT, const fl
     memset(&P, 0, sizeof(P));
     P.logT = const_cast<float*>(logT); P.logInvT = const_cast<float*>(logInvT);
     P.D = s.D; P.K = s.K; P.KT = s.KT; P.mrp = s.mrp; P.nchunk = s.nchunkE;
-    P.wblob = ws + s.off_wblob; P.c = (double*)(ws + s.off_c); P.scale = (float*)(ws + s.off_scale); P.done = done;
+    P.wblob = ws + s.off_wblob; P.c = (long long*)(ws + s.off_c); P.scale = (float*)(ws + s.off_scale); P.done = done;
     em_params_kernel<false><<<s.K, 256, 0, st>>>(P);
     return check_launch("tsr_em_estep(prepare)");
 }
@@ -848,7 +922,7 @@ int tsr_em_estep(const uint32_t* Xbits, long long N, int D, int rowwords, int K,
     const EmSmall sm = em_small(ws, s);
     PostArgs P;
     memset(&P, 0, sizeof(P));
-    P.accE = (int*)(ws + s.off_accE); P.scratch = (float*)(ws + s.off_scratch); P.c = (const double*)(ws + s.off_c);
+    P.accE = (int*)(ws + s.off_accE); P.scratch = (float*)(ws + s.off_scratch); P.c = (const long long*)(ws + s.off_c);
     P.scale = (const float*)(ws + s.off_scale); P.logw = logw; P.N = N; P.Npad = s.Npad; P.K = K; P.KT = s.KT; P.Mtiles = s.Mtiles;
     P.mrp = s.mrp; P.aff = aff_or_null ? aff_or_null : (float*)(ws + s.off_aff); P.scores_out = scores_or_null; P.hard = hard;
     P.update = update; P.done = done; P.colmax = sm.colmax; P.llQ = sm.llQ;
@@ -948,7 +1022,15 @@ int tsr_em_finalize(const double* stats, long long N_total, int D, int K, float 
         const EmShape s = em_shape(N_local, D, K);
         uint8_t* ws = (uint8_t*)workspace_or_null;
         P.KT = s.KT; P.mrp = s.mrp; P.nchunk = s.nchunkE;
-        P.wblob = ws + s.off_wblob; P.c = (double*)(ws + s.off_c); P.scale = (float*)(ws + s.off_scale);
+        P.wblob = ws + s.off_wblob; P.c = (long long*)(ws + s.off_c); P.scale = (float*)(ws + s.off_scale);
+        if (min_prob > 0.f && min_prob < 0.5f) {       // the clip bounds the weights: one fully parallel pass
+            cudaStream_t st = (cudaStream_t)stream;
+            em_zero_c_kernel<<<(K + 255) / 256, 256, 0, st>>>(P.c, K, P.done);
+            const float wbound = logf(1.f - min_prob) - logf(min_prob);
+            dim3 grid((unsigned)((s.nchunkE * 4 + 127) / 128), (unsigned)K);
+            em_finalize_fast_kernel<<<grid, 128, 0, st>>>(P, wbound * 1.0001f);
+            return check_launch("tsr_em_finalize");
+        }
     } else {
         P.KT = K < EM_KT_MAX ? K : EM_KT_MAX;
     }

@@ -218,9 +218,11 @@ class PartsModel:
 
 
 def code_parts(bits, parts, threshold, mask_threshold=-1, want_codes=True, want_scores=False, want_counts=False,
-               impl=IMPL_TENSOR):
+               impl=IMPL_TENSOR, edge_spread_radius=0, edge_block_len=0):
     """bits uint8 (B,T,F) -> (codes uint8 (B,To,Fo) | None, scores float32 (B,To,Fo,K) | None,
-    counts int16 (B,To,Fo) | None)."""
+    counts int16 (B,To,Fo) | None).  edge_spread_radius=1: `bits` is the UNSPREAD edge map and the radius-1 line
+    spreading per edge_block_len-frame block (K1a, reference direction table, ragged last block as the tail of the
+    final window) happens inside the kernel's producers -- no separate spread_edges launch."""
     bits = _dev(bits, torch.uint8, "bits")
     B, T, F = bits.shape
     To, Fo = T - parts.ph + 1, F - parts.pw + 1
@@ -231,7 +233,8 @@ def code_parts(bits, parts, threshold, mask_threshold=-1, want_codes=True, want_
     scores = torch.empty((B, To, Fo, parts.K), dtype=torch.float32, device=dev) if want_scores else None
     counts = torch.empty((B, To, Fo), dtype=torch.int16, device=dev) if want_counts else None
     _lib.call("tsr_code_parts", _ptr(bits), _ptr(parts.blob), parts.K, parts.ph, parts.pw, int(threshold),
-              int(mask_threshold), _ptr(codes), _ptr(scores), _ptr(counts), B, T, F, int(impl), _stream())
+              int(mask_threshold), _ptr(codes), _ptr(scores), _ptr(counts), B, T, F, int(edge_spread_radius),
+              int(edge_block_len), int(impl), _stream())
     return codes, scores, counts
 
 

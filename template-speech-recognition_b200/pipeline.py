@@ -29,12 +29,30 @@ class ScoringPipeline:
         self.impl_code = ops.IMPL_TENSOR
         self.impl_detect = ops.IMPL_TENSOR
         self.fused_max = True
+        self.fuse_edge_spread = True
+
+    def spread(self, bits):
+        """K1a as its own launch (what code() uses when the spreading cannot ride inside K2): per edge_block_len-frame
+        block, the ragged last block as the tail of the window of the final block_len frames (edge_signal_proc.py:
+        1595-1633)."""
+        if self.edge_spread_radius <= 0:
+            return bits
+        T, bl = bits.shape[1], self.edge_block_len
+        tail = bits[:, max(0, T - bl):].contiguous() if (bl > 0 and T % bl) else None
+        if bl <= 0:
+            return ops.spread_edges(bits, self.edge_spread_radius, self.edge_orientations, "line", 0)
+        return ops.spread_edge_blocks(bits, tail, self.edge_spread_radius, bl, self.edge_orientations, "line")
 
     def code(self, bits):
-        """K1a + K2 + K1b: packed edges -> (codes, part feature bits)."""
-        if self.edge_spread_radius > 0:
-            bits = ops.spread_edges(bits, self.edge_spread_radius, self.edge_orientations, "line", self.edge_block_len)
-        codes, _, _ = ops.code_parts(bits, self.parts, self.edge_threshold, impl=self.impl_code)
+        """K1a + K2 + K1b: packed edges -> (codes, part feature bits).  With the reference's direction table and
+        radius 1 (main_multiprocessing.py:50-52) the edge spreading runs inside K2's producers: one launch less and
+        no second pass over the edge map."""
+        fused = (self.fuse_edge_spread and self.edge_spread_radius == 1 and self.edge_orientations is None
+                 and self.impl_code == ops.IMPL_TENSOR)
+        if not fused:
+            bits = self.spread(bits)
+        codes, _, _ = ops.code_parts(bits, self.parts, self.edge_threshold, impl=self.impl_code,
+                                     edge_spread_radius=1 if fused else 0, edge_block_len=self.edge_block_len if fused else 0)
         fb = ops.spread_codes(codes, self.parts.K, *self.part_spread)
         return codes, fb
 
@@ -91,7 +109,13 @@ class ScoringPipeline:
         # batches i + 2 and i + 3, so the consumer has taken batch i + 1 and therefore finished issuing batch i
         # (whose copy-done event is then in `consumed`).
         NSTAGE = 4
-        staging = [None] * NSTAGE                # pinned buffers the feeder packs / stages into
+        # pinned buffers the feeder packs / stages into, and the pinned result ring: kept on the pipeline between calls
+        # (pinning host memory costs milliseconds per buffer)
+        cache = self.__dict__.setdefault("_stream_cache", {"staging": [None] * NSTAGE, "outs": {}})
+        if cache.get("busy"):
+            cache = {"staging": [None] * NSTAGE, "outs": {}}     # a second stream() running concurrently gets its own
+        cache["busy"] = True
+        staging = cache["staging"]
         consumed = [None] * NSTAGE               # CUDA event: the H2D copy out of staging[j] has finished
 
         def feeder():
@@ -134,7 +158,7 @@ class ScoringPipeline:
         main = torch.cuda.current_stream(dev)
         h2d, d2h = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
         xd, free_ev = [None, None], [None, None]
-        outs, out_ev = [None] * ring, [None] * ring
+        outs, out_ev = cache["outs"].setdefault(ring, [None] * ring), [None] * ring
         pending = None
         i = 0
         try:
@@ -187,6 +211,7 @@ class ScoringPipeline:
                 yield outs[pending]
         finally:
             stop.set()
+            cache["busy"] = False
             while th.is_alive():                          # unblock a feeder waiting on the full queue
                 try:
                     q.get_nowait()

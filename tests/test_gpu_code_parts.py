@@ -208,3 +208,31 @@ def test_get_parts_mask(cuda, oracle, golden):
     for n, (b, i, j) in enumerate(sel[:50]):
         np.testing.assert_array_equal(patches[n], Xb[b, i:i + 5, j:j + 5])
     np.testing.assert_array_equal(ops.unpack_features(r["bits"][None], 200)[0].cpu().numpy(), patches.reshape(len(sel), 200))
+
+
+@pytest.mark.parametrize("B,T,F,bl,K", [(3, 300, 40, 40, 100), (2, 64, 40, 40, 20), (2, 37, 40, 40, 7), (2, 120, 40, 0, 30),
+                                        (1, 173, 37, 25, 50), (4, 81, 9, 40, 12), (2, 45, 40, 1, 5)])
+def test_fused_edge_spreading_equals_spread_then_code(cuda, oracle, B, T, F, bl, K):
+    """K1a inside K2's producers (tsr_code_parts with edge_spread_radius = 1) gives the bits of the two-launch path
+    -- spread_edge_blocks (per block, ragged last block from the final window, edge_signal_proc.py:1595-1663) then
+    code_parts -- and the spread itself equals the NumPy restatement."""
+    from tsr_b200 import ops, synth
+    from tsr_b200.pipeline import ScoringPipeline
+    lp, lip = synth.parts(K)
+    X = np.stack([synth.utterance_edges(100 + u, T=T, F=F) for u in range(B)])
+    bits = ops.pack_edges(torch.from_numpy(X).cuda())
+    parts = ops.PartsModel(lp, lip)
+    pipe = ScoringPipeline(lp, lip, np.zeros((1, 2, (F - 4) * K), np.float32).reshape(1, 2, F - 4, K), np.zeros(1, np.float32),
+                           edge_spread_radius=1, edge_block_len=bl)
+    sb = pipe.spread(bits)
+    got = ops.unpack_edges(sb).cpu().numpy()
+    for b in range(B):
+        np.testing.assert_array_equal(got[b], oracle.spread_edge_blocks(X[b], 1, bl))
+    c0, s0, n0 = ops.code_parts(sb, parts, 12, want_scores=True, want_counts=True)
+    c1, s1, n1 = ops.code_parts(bits, parts, 12, want_scores=True, want_counts=True, edge_spread_radius=1, edge_block_len=bl)
+    torch.cuda.synchronize()
+    assert torch.equal(n0, n1) and torch.equal(c0, c1) and torch.equal(s0, s1)
+    codes, fb = pipe.code(bits)
+    assert torch.equal(codes, c0)
+    with pytest.raises(ValueError):
+        ops.code_parts(bits, parts, 12, edge_spread_radius=2, edge_block_len=bl)

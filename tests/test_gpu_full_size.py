@@ -35,12 +35,12 @@ def test_pipeline_batch_invariance(full):
     from tsr_b200 import ops
     pipe, bits = full["pipe"], full["bits"]
     codes, fb = pipe.code(bits)
-    best, arg, scores = pipe.score(fb)
+    best, arg, scores = pipe.score(fb, want_scores=True)
     rs = np.random.RandomState(0)
     for start in [0, B_FULL - 8] + list(rs.randint(0, B_FULL - 8, 4)):
         sl = slice(int(start), int(start) + 8)
         c8, fb8 = pipe.code(bits[sl].contiguous())
-        b8, a8, s8 = pipe.score(fb8)
+        b8, a8, s8 = pipe.score(fb8, want_scores=True)
         assert torch.equal(c8, codes[sl]) and torch.equal(fb8, fb[sl])
         assert torch.equal(s8, scores[sl]) and torch.equal(b8, best[sl]) and torch.equal(a8, arg[sl])
     # the L-1 tail frames of every utterance are zero, like the reference's detect (:157-158)
@@ -210,10 +210,12 @@ def _em_float64(X, K, minp, iters, init_minp=.01):
         p = np.exp(ll - mx)
         s = p.sum(1, keepdims=True)
         trace.append(float((np.log(s[:, 0]) + mx[:, 0]).sum()))
+        if len(trace) == iters + 1:
+            break
         aff = p / s
         w = aff.mean(0)
         T = np.clip((aff.T @ Xd) / N / w[:, None], minp, 1 - minp)
-    return trace
+    return trace, w
 
 
 def test_part_dictionary_training_full_size(cuda, oracle):
@@ -231,11 +233,12 @@ def test_part_dictionary_training_full_size(cuda, oracle):
     b = BernoulliMixture(K, X)
     b.run_EM(1e-9, min_probability=.01, max_iter=4, min_iter=4)
     assert b.iterations == a.iterations == 4
-    t64 = _em_float64(X, K, .01, 4)
+    t64, w64 = _em_float64(X, K, .01, 4)
     np.testing.assert_allclose(b.loglikelihood_trace, t64, rtol=1e-6)
+    np.testing.assert_allclose(b.weights, w64, rtol=1e-4, atol=1e-8)
     ref = np.array(a.loglikelihood_trace, np.float64)
     np.testing.assert_allclose(ref, t64, rtol=2e-5)                      # the reference's own float32 noise floor
     np.testing.assert_allclose(b.loglikelihood_trace, ref, rtol=2e-5)
     np.testing.assert_allclose(np.delete(b.loglikelihood_trace, 2), np.delete(ref, 2), rtol=1e-5)
-    np.testing.assert_allclose(b.weights, a.weights, atol=1e-5)
+    np.testing.assert_allclose(b.weights, a.weights, atol=1e-4)       # float32 reference: 1.3e-5 off the float64 run here
     assert b.templates.shape == (K, D) and b.affinities.shape == (N, K)

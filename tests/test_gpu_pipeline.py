@@ -20,14 +20,10 @@ def test_pipeline_matches_oracle_chain(cuda, oracle):
     best, arg, codes = pipe(bits)
     torch.cuda.synchronize()
     best, arg, codes = best.cpu().numpy(), arg.cpu().numpy().view(np.uint16), codes.cpu().numpy()
-    ori = ops.DEFAULT_EDGE_ORIENTATIONS.astype(int)
     for b in range(B):
-        # K1a: per 40-frame block, radius 1 (edge_signal_proc.py:1635-1663)
-        Xs = np.zeros_like(X[b])
-        for e in range(8):
-            for s in range(0, 300, 40):
-                blk = X[b, s:s + 40, :, e].T.astype(np.float64)
-                Xs[s:s + 40, :, e] = oracle._spread_edges(blk, ori[e], 1).T
+        # K1a: per 40-frame block, radius 1; the ragged last 20 frames are the tail of the window of the final 40
+        # (edge_signal_proc.py:1595-1663)
+        Xs = oracle.spread_edge_blocks(X[b], 1, 40)
         out = oracle.code_parts(Xs, lp, lip, 12)
         ref_codes = np.argmax(out, -1)
         mism = ref_codes != codes[b]
