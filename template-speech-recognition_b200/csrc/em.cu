@@ -23,6 +23,8 @@
 #include <math.h>
 #include <string.h>
 
+#include <cuda.h>      // CUtensorMap (the encoder is fetched through cudaGetDriverEntryPoint: no libcuda link dependency)
+
 #include "common.cuh"
 
 extern "C" int tsr_rowwords(int D);
@@ -39,6 +41,8 @@ namespace tsr {
 #define BG_NSTRIP 4                  // expanded bit strips in flight (one per expander group)
 #define BG_NW 4                      // ring of int8 weight tiles
 #define BG_STRIP_BYTES 32768         // 256 rows x 128 k-positions of u8
+#define BG_NRAW 4                    // ring of raw bit tiles (256 rows x 16 B) landed by TMA tensor loads
+#define BG_RAW_BYTES 4096
 #define BG_TBUF_WORDS (32 * 33)      // per-epilogue-warp transpose buffer
 
 struct EmShape {
@@ -71,7 +75,7 @@ static EmShape em_shape(long long N, int D, int K) {
     s.off_accM = s.off_accE + up((size_t)s.Mtiles * s.mrp * s.Npad * 4);
     s.off_ablob = s.off_accM + up((size_t)s.Mtiles * s.mrp * s.Dpad * 4);
     s.off_small = s.off_ablob + up((size_t)s.Mtiles * s.nchunkM * s.tile_bytes);
-    s.off_scratch = s.off_small + up(sizeof(long long) * ((size_t)K + 2) + sizeof(uint32_t) * (size_t)K);
+    s.off_scratch = s.off_small + up(sizeof(long long) * (2 * (size_t)K + 2) + sizeof(uint32_t) * (size_t)K);
     s.off_aff = s.off_scratch + up((size_t)K * s.Npad * 4);
     s.total = s.off_aff + up((size_t)K * (size_t)N * 4);
     return s;
@@ -94,6 +98,7 @@ struct EmCtl {
 //         (word >> s) & 0x01010101 gives the four bytes of shift s with two instructions
 //   acc   [Mtiles][mrp][Rpad] int32 += products (Rpad = R rounded up to 256)
 struct BgArgs {
+    alignas(64) CUtensorMap tmap;   // RAW_TMA: the bit matrix as a 2-D uint8 tensor {rw*4 bytes, R rows}, box {16 B, 256 rows}
     const uint32_t* bits;
     const uint8_t* wblob;
     int* acc;
@@ -101,6 +106,16 @@ struct BgArgs {
     int rw, nchunk, Mtiles, mrp, mrows, Rtiles;
     const int* done;
 };
+
+// 2-D tiled TMA load global -> shared (UTMALDG in SASS); completes on an mbarrier.  Rows past the tensor's extent are
+// zero filled, so the last row tile needs no bounds checks.
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tmap, int x, int y, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(tmap)), "r"(x), "r"(y), "r"(smem_u32(bar))
+        : "memory");
+}
 
 // A CTA's share of the flattened (R tile, M tile, chunk) space, cut into segments at tile borders.
 struct BgWalk {
@@ -138,20 +153,30 @@ __device__ __forceinline__ void umma_i8_ss(uint32_t d_tmem, uint64_t a_desc, uin
         : "memory");
 }
 
-__global__ void __launch_bounds__(BG_THREADS, 1) bitgemm_kernel(BgArgs A) {
+// RAW_TMA: the bit rows reach shared memory through TMA tensor loads (one 256-row x 16-byte box per chunk) and the
+// expanders read them with conflict-free LDS.128.  Loading them with per-thread LDG instead (rows are rw*4 bytes
+// apart, so a warp's load touches 32 sectors) put as many wavefronts on the L1 data pipe as the expanded stores, and
+// that pipe -- shared by the LSU and the tensor cores' operand reads -- is what bounds this kernel (ncu:
+// lsu wavefronts 70 % + tensor-operand wavefronts 36 % of its peak).  The LDG path remains for row pitches that are
+// not a multiple of 16 bytes.
+template <bool RAW_TMA>
+__global__ void __launch_bounds__(BG_THREADS, 1) bitgemm_kernel(const __grid_constant__ BgArgs A) {
     if (A.done && *A.done) return;
     extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t tile_bytes = 8u * (uint32_t)A.mrp * 16u;
     uint8_t* wring = smem;                                            // BG_NW weight tiles; the M = 128 descriptors read past a
     uint8_t* strips = smem + BG_NW * tile_bytes;                      // short tile into what follows (harmless: rows >= mrows unused)
-    int* tbuf = reinterpret_cast<int*>(strips + BG_NSTRIP * BG_STRIP_BYTES);
+    uint8_t* raw = strips + BG_NSTRIP * BG_STRIP_BYTES;               // RAW_TMA: BG_NRAW raw bit tiles
+    int* tbuf = reinterpret_cast<int*>(raw + (RAW_TMA ? BG_NRAW * BG_RAW_BYTES : 0));
     uint64_t* wfull = reinterpret_cast<uint64_t*>(tbuf + 4 * BG_TBUF_WORDS);
     uint64_t* wempty = wfull + BG_NW;
     uint64_t* afull = wempty + BG_NW;
     uint64_t* aempty = afull + BG_NSTRIP;
     uint64_t* tfull = aempty + BG_NSTRIP;
     uint64_t* tempty = tfull + 2;
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty + 2);
+    uint64_t* rfull = tempty + 2;                                     // [BG_NRAW]
+    uint64_t* rempty = rfull + BG_NRAW;                               // [BG_NRAW]
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(rempty + BG_NRAW);
 
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
 
@@ -159,6 +184,7 @@ __global__ void __launch_bounds__(BG_THREADS, 1) bitgemm_kernel(BgArgs A) {
         for (int s = 0; s < BG_NW; ++s) { mbar_init(&wfull[s], 1); mbar_init(&wempty[s], 1); }
         for (int s = 0; s < BG_NSTRIP; ++s) { mbar_init(&afull[s], 64); mbar_init(&aempty[s], 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 128); }
+        for (int s = 0; s < BG_NRAW; ++s) { mbar_init(&rfull[s], 1); mbar_init(&rempty[s], 64); }
         mbar_fence_init();
     }
     if (warp == 13) tmem_alloc<512>(tmem_ptr);
@@ -168,14 +194,20 @@ __global__ void __launch_bounds__(BG_THREADS, 1) bitgemm_kernel(BgArgs A) {
     const uint32_t tmem_base = *tmem_ptr;
 
     if (warp == 0) {
-        // ================================ weight-tile loader ================================
+        // ======================= weight-tile (and raw bit tile) loader =======================
         if (lane == 0) {
             BgWalk w(A);
             int rt, mt, c0, n, stage = 0;
-            uint32_t ph = 0;
+            uint32_t ph = 0, ic = 0;
             while (w.next_seg(rt, mt, c0, n)) {
                 const uint8_t* src = A.wblob + ((size_t)mt * A.nchunk + c0) * tile_bytes;
-                for (int i = 0; i < n; ++i) {
+                for (int i = 0; i < n; ++i, ++ic) {
+                    if (RAW_TMA) {
+                        const uint32_t rs = ic % BG_NRAW;
+                        mbar_wait_relaxed(&rempty[rs], ((ic / BG_NRAW) & 1) ^ 1);
+                        mbar_arrive_expect_tx(&rfull[rs], BG_RAW_BYTES);
+                        tma_load_2d(raw + rs * BG_RAW_BYTES, &A.tmap, 16 * (c0 + i), rt * 256, &rfull[rs]);
+                    }
                     mbar_wait_relaxed(&wempty[stage], ph ^ 1);
                     mbar_arrive_expect_tx(&wfull[stage], tile_bytes);
                     bulk_g2s(wring + stage * tile_bytes, src + (size_t)i * tile_bytes, tile_bytes, &wfull[stage]);
@@ -220,17 +252,8 @@ __global__ void __launch_bounds__(BG_THREADS, 1) bitgemm_kernel(BgArgs A) {
                 x[k] = make_uint4(lo.x, lo.y, hi.x, hi.y);
             }
         };
-        uint4 x[4], y[4];
-        int crt, cc;
-        bool ok = advance(crt, cc);
-        if (ok) load(crt, cc, x);
-        uint32_t use = 0;
         uint8_t* strip = strips + g * BG_STRIP_BYTES;
-        while (ok) {
-            int nrt, nc;
-            const bool ok2 = advance(nrt, nc);
-            if (ok2) load(nrt, nc, y);
-            mbar_wait_relaxed(&aempty[g], (use & 1) ^ 1);
+        auto expand = [&](const uint4 (&x)[4]) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 uint8_t* dst = strip + (tg + 64 * k) * 16;
@@ -244,12 +267,42 @@ __global__ void __launch_bounds__(BG_THREADS, 1) bitgemm_kernel(BgArgs A) {
                     *reinterpret_cast<uint4*>(dst + (2 * wi + 1) * 4096) = b;
                 }
             }
-            fence_proxy_async_smem();
-            mbar_arrive(&afull[g]);
-            ++use;
+        };
+        uint32_t use = 0;
+        if (RAW_TMA) {
+            // chunk ic (global count of this CTA) sits in raw tile ic % BG_NRAW; this group takes ic = g, g + 4, ...
+            int crt, cc;
+            while (advance(crt, cc)) {
+                const uint32_t icm = ic - 1, rs = icm % BG_NRAW;
+                mbar_wait_relaxed(&rfull[rs], (icm / BG_NRAW) & 1);
+                uint4 x[4];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) x[k] = y[k];
-            ok = ok2;
+                for (int k = 0; k < 4; ++k) x[k] = *reinterpret_cast<const uint4*>(raw + rs * BG_RAW_BYTES + (tg + 64 * k) * 16);
+                mbar_arrive(&rempty[rs]);                    // the words are in registers: the tile may be refilled
+                mbar_wait_relaxed(&aempty[g], (use & 1) ^ 1);
+                expand(x);
+                fence_proxy_async_smem();
+                mbar_arrive(&afull[g]);
+                ++use;
+            }
+        } else {
+            uint4 x[4], y[4];
+            int crt, cc;
+            bool ok = advance(crt, cc);
+            if (ok) load(crt, cc, x);
+            while (ok) {
+                int nrt, nc;
+                const bool ok2 = advance(nrt, nc);
+                if (ok2) load(nrt, nc, y);
+                mbar_wait_relaxed(&aempty[g], (use & 1) ^ 1);
+                expand(x);
+                fence_proxy_async_smem();
+                mbar_arrive(&afull[g]);
+                ++use;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) x[k] = y[k];
+                ok = ok2;
+            }
         }
     } else if (warp == 13) {
         // ==================================== MMA issuer ====================================
@@ -335,34 +388,67 @@ __global__ void __launch_bounds__(BG_THREADS, 1) bitgemm_kernel(BgArgs A) {
     }
 }
 
-static size_t bitgemm_smem(int mrp) {
-    return (size_t)BG_NW * 8 * mrp * 16 + (size_t)BG_NSTRIP * BG_STRIP_BYTES + 4 * BG_TBUF_WORDS * 4 + 256;
+static size_t bitgemm_smem(int mrp, bool raw_tma) {
+    return (size_t)BG_NW * 8 * mrp * 16 + (size_t)BG_NSTRIP * BG_STRIP_BYTES + (raw_tma ? BG_NRAW * BG_RAW_BYTES : 0) +
+           4 * BG_TBUF_WORDS * 4 + 512;
+}
+
+typedef CUresult (*tsr_encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                        const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                        CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static tsr_encode_tiled_fn encode_tiled_fn() {
+    static tsr_encode_tiled_fn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<tsr_encode_tiled_fn>(p);
+        cudaGetLastError();
+    }
+    return fn;
 }
 
 static int launch_bitgemm(const uint32_t* bits, long long R, int rw, const uint8_t* wblob, int* acc, long long Rpad, int nchunk,
                           const EmShape& s, const int* done, cudaStream_t st) {
     BgArgs A;
+    memset(&A, 0, sizeof(A));
     A.bits = bits; A.wblob = wblob; A.acc = acc; A.R = R; A.Rpad = Rpad; A.rw = rw; A.nchunk = nchunk;
     A.Mtiles = s.Mtiles; A.mrp = s.mrp; A.mrows = s.mrows; A.Rtiles = (int)(Rpad / 256); A.done = done;
-    const size_t smem = bitgemm_smem(s.mrp);
+    // the bit matrix as a TMA tensor when its row pitch allows (multiple of 16 bytes, 16-byte aligned base)
+    bool raw_tma = (rw % 4 == 0) && ((reinterpret_cast<uintptr_t>(bits) & 15) == 0) && getenv("TSR_DEBUG_BITGEMM_LDG") == nullptr;
+    if (raw_tma) {
+        tsr_encode_tiled_fn enc = encode_tiled_fn();
+        const cuuint64_t gdim[2] = {(cuuint64_t)rw * 4, (cuuint64_t)R};
+        const cuuint64_t gstride[1] = {(cuuint64_t)rw * 4};
+        const cuuint32_t box[2] = {16, 256}, estr[2] = {1, 1};
+        raw_tma = enc && enc(&A.tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<uint32_t*>(bits), gdim, gstride, box, estr,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    }
+    const size_t smem = bitgemm_smem(s.mrp, raw_tma);
     static bool attr_set = false;
     if (!attr_set) {
-        TSR_CUDA(cudaFuncSetAttribute(bitgemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        TSR_CUDA(cudaFuncSetAttribute(bitgemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        TSR_CUDA(cudaFuncSetAttribute(bitgemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set = true;
     }
     const long long total = (long long)A.Rtiles * A.Mtiles * nchunk;
     const int nsm = sm_count();
     const int grid = (int)(total < nsm ? total : nsm);
     if (grid < 1) return TSR_OK;
-    bitgemm_kernel<<<grid, BG_THREADS, smem, st>>>(A);
+    if (raw_tma) bitgemm_kernel<true><<<grid, BG_THREADS, smem, st>>>(A);
+    else bitgemm_kernel<false><<<grid, BG_THREADS, smem, st>>>(A);
     return check_launch("bitgemm_kernel");
 }
 
-// Small per-call scratch in the workspace: [respQ int64[K] | llQ int64 | ticket int64 | colmax uint32[K]]
+// Small per-call scratch in the workspace: [respQ int64[K] | llQ int64 | ticket int64 | sk double[K] | colmax uint32[K]]
 struct EmSmall {
     long long* respQ;
     long long* llQ;
     unsigned long long* ticket;
+    double* sk;                 // per-component posterior scale (power of two), published by the planes kernel
     uint32_t* colmax;
 };
 static EmSmall em_small(uint8_t* ws, const EmShape& s) {
@@ -370,7 +456,8 @@ static EmSmall em_small(uint8_t* ws, const EmShape& s) {
     m.respQ = reinterpret_cast<long long*>(ws + s.off_small);
     m.llQ = m.respQ + s.K;
     m.ticket = reinterpret_cast<unsigned long long*>(m.llQ + 1);
-    m.colmax = reinterpret_cast<uint32_t*>(m.ticket + 1);
+    m.sk = reinterpret_cast<double*>(m.ticket + 1);
+    m.colmax = reinterpret_cast<uint32_t*>(m.sk + s.K);
     return m;
 }
 // power-of-two scale of component k's posteriors: the smallest 2^e >= column max (0 for an empty column)
@@ -529,68 +616,60 @@ __global__ void __launch_bounds__(256) em_params_kernel(ParamArgs P) {
     }
 }
 
-// The M-step proper of the iteration loop, fully parallel: one thread per 32-feature word of one component does
-// everything for its 32 parameters -- divide, clip, logs, the three weight digits -- in one pass.  No reduction is
-// needed for the quantisation step because the clip bounds |W| = |logT - logInvT| by log((1 - p_min) / p_min); c[k]
-// is summed in 2^-36 fixed point with integer atomics (order independent).  grid = (ceil(nchunk * 4 / 128), K).
-__global__ void __launch_bounds__(128) em_finalize_fast_kernel(ParamArgs P, float wbound) {
+// The M-step proper of the iteration loop, fully parallel: one WARP per 32-feature word of one component, lane =
+// feature (coalesced reads of the statistics, coalesced writes of templates / logs).  Everything for a parameter --
+// divide, clip, logs, the three weight digits -- happens in one pass: no reduction is needed for the quantisation step
+// because the clip bounds |W| = |logT - logInvT| by log((1 - p_min) / p_min).  A lane's digit is byte jj = lane / 8 of
+// word s = lane % 8 of the tile row pair (see bitgemm_kernel); lanes 0..7 collect the four bytes of their word with
+// three shuffles.  c[k] is summed in 2^-36 fixed point with integer atomics (order independent).
+// grid = (ceil(nchunk * 4 / 8), K), 8 warps per CTA.
+__global__ void __launch_bounds__(256) em_finalize_fast_kernel(ParamArgs P, float wbound) {
     if (P.done && *P.done) return;
-    __shared__ long long s_c[4];
-    const int k = blockIdx.y, tid = threadIdx.x;
-    const int it = blockIdx.x * 128 + tid;
+    __shared__ long long s_c[8];
+    const int k = blockIdx.y, tid = threadIdx.x, lane = tid & 31, wp = tid >> 5;
+    const int it = blockIdx.x * 8 + wp;                    // 32-feature word of this warp
     const size_t row = (size_t)k * P.D;
     const float w = (float)P.stats[(size_t)P.K * P.D + k] / (float)P.N_total;          // np.mean(affinities, 0)
     const float sc = wbound > 0.f ? wbound / (float)EM_QMAX : 1.f;
     long long csum = 0;
     if (it < P.nchunk * 4) {
         const int c = it >> 2, wi = it & 3;
-        const int d0 = c * 128 + wi * 32;
-        uint32_t out[3][2][4];
-#pragma unroll
-        for (int p = 0; p < 3; ++p)
-#pragma unroll
-            for (int h = 0; h < 2; ++h)
-#pragma unroll
-                for (int q = 0; q < 4; ++q) out[p][h][q] = 0u;
-#pragma unroll
-        for (int s = 0; s < 8; ++s)
-#pragma unroll
-            for (int jj = 0; jj < 4; ++jj) {
-                const int d = d0 + 8 * jj + s;
-                int q = 0;
-                if (d < P.D) {
-                    float t = (float)P.stats[row + d];                             // np.dot(affinities.T, data) as float32
-                    t = t / (float)P.N_total;                                      // /= num_data
-                    t = t / w;                                                     // /= weights
-                    t = fminf(fmaxf(t, P.min_prob), 1.f - P.min_prob);             // threshold_templates
-                    const float lt = logf(t), li = logf(1.f - t);
-                    P.templates[row + d] = t; P.logT[row + d] = lt; P.logInvT[row + d] = li;
-                    csum += llrint((double)li * EM_C_SCALE);
-                    float qf = rintf((lt - li) / sc);
-                    qf = fminf(fmaxf(qf, -(float)EM_QMAX), (float)EM_QMAX);
-                    q = (int)qf;
-                }
-#pragma unroll
-                for (int p = 0; p < 3; ++p) {
-                    const int digit = ((q + 128) & 255) - 128;
-                    q = (q - digit) >> 8;
-                    out[p][s >> 2][s & 3] |= (uint32_t)(digit & 255) << (8 * jj);
-                }
-            }
+        const int d = c * 128 + wi * 32 + lane;
+        int q = 0;
+        if (d < P.D) {
+            float t = (float)P.stats[row + d];                             // np.dot(affinities.T, data) as float32
+            t = t / (float)P.N_total;                                      // /= num_data
+            t = t / w;                                                     // /= weights
+            t = fminf(fmaxf(t, P.min_prob), 1.f - P.min_prob);             // threshold_templates
+            const float lt = logf(t), li = logf(1.f - t);
+            P.templates[row + d] = t; P.logT[row + d] = lt; P.logInvT[row + d] = li;
+            csum = llrint((double)li * EM_C_SCALE);
+            float qf = rintf((lt - li) / sc);
+            qf = fminf(fmaxf(qf, -(float)EM_QMAX), (float)EM_QMAX);
+            q = (int)qf;
+        }
         const int mt = k / P.KT, kl = k - mt * P.KT;
         uint8_t* tile = P.wblob + ((size_t)mt * P.nchunk + c) * ((size_t)8 * P.mrp * 16);
+        const int s8 = lane & 7;                                           // word of the 32-byte row pair this lane belongs to
 #pragma unroll
-        for (int p = 0; p < 3; ++p)
-#pragma unroll
-            for (int h = 0; h < 2; ++h)
-                *reinterpret_cast<uint4*>(tile + ((size_t)(2 * wi + h) * P.mrp + p * P.KT + kl) * 16) =
-                    make_uint4(out[p][h][0], out[p][h][1], out[p][h][2], out[p][h][3]);
+        for (int p = 0; p < 3; ++p) {
+            const int digit = ((q + 128) & 255) - 128;
+            q = (q - digit) >> 8;
+            uint32_t v = (uint32_t)(digit & 255);
+            v |= __shfl_down_sync(0xffffffffu, v, 8) << 8;                 // lanes l, l+8, l+16, l+24 = bytes jj = 0..3
+            const uint32_t hi2 = __shfl_down_sync(0xffffffffu, v, 16);
+            v |= hi2 << 16;
+            if (lane < 8)
+                *reinterpret_cast<uint32_t*>(tile + ((size_t)(2 * wi + (s8 >> 2)) * P.mrp + p * P.KT + kl) * 16 + 4 * (s8 & 3)) = v;
+        }
     }
     for (int off = 16; off > 0; off >>= 1) csum += __shfl_xor_sync(0xffffffffu, csum, off);
-    if ((tid & 31) == 0) s_c[tid >> 5] = csum;
+    if (lane == 0) s_c[wp] = csum;
     __syncthreads();
     if (tid == 0) {
-        const long long tot = s_c[0] + s_c[1] + s_c[2] + s_c[3];
+        long long tot = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) tot += s_c[i];
         atomicAdd(reinterpret_cast<unsigned long long*>(P.c + k), (unsigned long long)tot);
         if (blockIdx.x == 0) { P.scale[k] = sc; P.weights[k] = w; P.logw[k] = logf(w); }
     }
@@ -622,7 +701,10 @@ struct PostArgs {
     const int* done;
 };
 
-template <bool INT_SCORES>
+// KREG > 0 (K <= KREG): the scores of a row are read ONCE into registers (3*K independent loads in flight, the
+// accumulators cleared behind them) and the three passes run out of registers.  KREG == 0: any K, the passes re-read
+// the accumulators (L2 resident) instead.
+template <bool INT_SCORES, int KREG>
 __global__ void __launch_bounds__(128) em_posterior_kernel(PostArgs P) {
     if (P.done && *P.done) return;
     extern __shared__ __align__(16) uint8_t psm[];
@@ -648,26 +730,59 @@ __global__ void __launch_bounds__(128) em_posterior_kernel(PostArgs P) {
         }
         return (double)P.scratch[(size_t)k * P.Npad + n];
     };
+    constexpr int NR = KREG > 0 ? KREG : 1;
+    double sv[NR];
+    if (KREG > 0) {
+        if (INT_SCORES) {      // all loads first (K <= 42: one M tile, rows plane * KT + k)
+            int a0[NR], a1[NR], a2[NR];
+            int* a = P.accE + n;
+#pragma unroll
+            for (int k = 0; k < NR; ++k)
+                if (k < P.K) { a0[k] = a[(size_t)k * P.Npad]; a1[k] = a[(size_t)k * P.Npad + pstride]; a2[k] = a[(size_t)k * P.Npad + 2 * pstride]; }
+#pragma unroll
+            for (int k = 0; k < NR; ++k)
+                if (k < P.K) {
+                    a[(size_t)k * P.Npad] = 0; a[(size_t)k * P.Npad + pstride] = 0; a[(size_t)k * P.Npad + 2 * pstride] = 0;
+                    const double q = (double)a0[k] + 256.0 * (double)a1[k] + 65536.0 * (double)a2[k];
+                    sv[k] = q * (double)P.scale[k] + (double)P.c[k] / EM_C_SCALE;
+                }
+        } else {
+#pragma unroll
+            for (int k = 0; k < NR; ++k)
+                if (k < P.K) sv[k] = (double)P.scratch[(size_t)k * P.Npad + n];
+        }
+    }
     // pass 1: scores out, running maxima (soft-max in double up to the exponent: the posteriors then carry the
     // weight quantisation only, ~1e-6, instead of the 3e-5 a float32 score of magnitude 500 would add)
     double mx = -INFINITY, smx = -INFINITY;
     int arg = 0;
-    for (int k = 0; k < P.K; ++k) {
-        const double s = score(k, !P.update);
+    auto pass1 = [&](int k, double s) {
         if (live && P.scores_out) P.scores_out[n * P.K + k] = (float)s;
         if (s > smx) { smx = s; arg = k; }                  // hard assignment: first arg-max of the template scores (:273-275)
-        const double v = s + (double)P.logw[k];
-        mx = fmax(mx, v);
+        mx = fmax(mx, s + (double)P.logw[k]);
+    };
+    if (KREG > 0) {
+#pragma unroll
+        for (int k = 0; k < NR; ++k)
+            if (k < P.K) pass1(k, sv[k]);
+    } else {
+        for (int k = 0; k < P.K; ++k) pass1(k, score(k, !P.update));
     }
     if (!P.update) return;
     // pass 2: log-sum-exp (:269-270)
     double sum = 0.0;
-    for (int k = 0; k < P.K; ++k) sum += (double)expf((float)(score(k, false) + (double)P.logw[k] - mx));
+    if (KREG > 0) {
+#pragma unroll
+        for (int k = 0; k < NR; ++k)
+            if (k < P.K) sum += (double)expf((float)(sv[k] + (double)P.logw[k] - mx));
+    } else {
+        for (int k = 0; k < P.K; ++k) sum += (double)expf((float)(score(k, false) + (double)P.logw[k] - mx));
+    }
     const float inv = (float)(1.0 / sum);
     long long my_ll = live ? llrint((log(sum) + mx) * EM_LL_SCALE) : 0;
     // pass 3: posteriors and their column maxima
-    for (int k = 0; k < P.K; ++k) {
-        const double v = score(k, true) + (double)P.logw[k];
+    auto pass3 = [&](int k, double s) {
+        const double v = s + (double)P.logw[k];
         float p = 0.f;
         if (live) {
             p = P.hard ? (k == arg ? 1.f : 0.f) : fminf(expf((float)(v - mx)) * inv, 1.f);
@@ -675,6 +790,13 @@ __global__ void __launch_bounds__(128) em_posterior_kernel(PostArgs P) {
         }
         const uint32_t wmax = __reduce_max_sync(0xffffffffu, __float_as_uint(p));     // p >= 0: bit patterns order like values
         if ((tid & 31) == 0 && wmax) atomicMax(&s_max[k], wmax);
+    };
+    if (KREG > 0) {
+#pragma unroll
+        for (int k = 0; k < NR; ++k)
+            if (k < P.K) pass3(k, sv[k]);
+    } else {
+        for (int k = 0; k < P.K; ++k) pass3(k, score(k, true));
     }
     for (int off = 16; off > 0; off >>= 1) my_ll += __shfl_xor_sync(0xffffffffu, my_ll, off);
     if ((tid & 31) == 0) atomicAdd(reinterpret_cast<unsigned long long*>(&s_ll), (unsigned long long)my_ll);
@@ -716,6 +838,8 @@ __global__ void __launch_bounds__(128) em_aff_planes_kernel(const float* __restr
     const long long n = blockIdx.x * 128LL + tid;
     const bool live = n < N;
     for (int k = tid; k < K; k += 128) s_resp[k] = 0;
+    if (blockIdx.x == 0)
+        for (int k = tid; k < K; k += 128) S.sk[k] = (double)em_col_scale(S.colmax[k]);     // for em_pack_kernel
     const int pos = em_tile_pos(tid);
     const size_t tile_bytes = (size_t)8 * mrp * 16;
     for (int mt = 0; mt < Mtiles; ++mt) {
@@ -759,7 +883,7 @@ __global__ void __launch_bounds__(128) em_aff_planes_kernel(const float* __restr
 }
 
 // int32 digit-plane accumulators of the M-step -> float64 numerators; clears the accumulators
-__global__ void em_pack_kernel(int* __restrict__ accM, int D, int Dpad, int K, int KT, int mrp, const uint32_t* __restrict__ colmax,
+__global__ void em_pack_kernel(int* __restrict__ accM, int D, int Dpad, int K, int KT, int mrp, const double* __restrict__ sk,
                                double* __restrict__ stats, const int* done) {
     if (done && *done) return;
     const long long total = (long long)K * D;
@@ -770,7 +894,7 @@ __global__ void em_pack_kernel(int* __restrict__ accM, int D, int Dpad, int K, i
         const size_t ps = (size_t)KT * Dpad;
         const long long q = (long long)a[0] + 256LL * (long long)a[ps] + 65536LL * (long long)a[2 * ps];
         a[0] = 0; a[ps] = 0; a[2 * ps] = 0;
-        stats[i] = (double)q / (double)EM_QMAX * (double)em_col_scale(colmax[k]);   // division first: exact for multiples of EM_QMAX
+        stats[i] = (double)q / (double)EM_QMAX * __ldg(sk + k);   // division first: exact for multiples of EM_QMAX
     }
 }
 
@@ -938,11 +1062,15 @@ int tsr_em_estep(const uint32_t* Xbits, long long N, int D, int rowwords, int K,
                                                                s.Npad, done);
         rc = check_launch("tsr_em_estep(simt scores)");
         if (rc) return rc;
-        em_posterior_kernel<false><<<pgrid, 128, psm, st>>>(P);
+        if (K <= 16) em_posterior_kernel<false, 16><<<pgrid, 128, psm, st>>>(P);
+        else if (K <= 32) em_posterior_kernel<false, 32><<<pgrid, 128, psm, st>>>(P);
+        else em_posterior_kernel<false, 0><<<pgrid, 128, psm, st>>>(P);
     } else {
         rc = launch_bitgemm(Xbits, N, rowwords, ws + s.off_wblob, P.accE, s.Npad, s.nchunkE, s, done, st);
         if (rc) return rc;
-        em_posterior_kernel<true><<<pgrid, 128, psm, st>>>(P);
+        if (K <= 16) em_posterior_kernel<true, 16><<<pgrid, 128, psm, st>>>(P);
+        else if (K <= 32) em_posterior_kernel<true, 32><<<pgrid, 128, psm, st>>>(P);
+        else em_posterior_kernel<true, 0><<<pgrid, 128, psm, st>>>(P);
     }
     rc = check_launch("tsr_em_estep(posterior)");
     if (rc || !update) return rc;
@@ -1001,7 +1129,7 @@ int tsr_em_mstep(const uint32_t* Xbits, const uint32_t* XTbits_or_null, long lon
     long long blocks = ((long long)K * D + 255) / 256;
     const long long cap = (long long)sm_count() * 8;
     if (blocks > cap) blocks = cap;
-    em_pack_kernel<<<(unsigned)blocks, 256, 0, st>>>((int*)(ws + s.off_accM), D, s.Dpad, K, s.KT, s.mrp, sm.colmax, stats, done);
+    em_pack_kernel<<<(unsigned)blocks, 256, 0, st>>>((int*)(ws + s.off_accM), D, s.Dpad, K, s.KT, s.mrp, sm.sk, stats, done);
     return check_launch("tsr_em_mstep(pack)");
 }
 
@@ -1027,8 +1155,8 @@ int tsr_em_finalize(const double* stats, long long N_total, int D, int K, float 
             cudaStream_t st = (cudaStream_t)stream;
             em_zero_c_kernel<<<(K + 255) / 256, 256, 0, st>>>(P.c, K, P.done);
             const float wbound = logf(1.f - min_prob) - logf(min_prob);
-            dim3 grid((unsigned)((s.nchunkE * 4 + 127) / 128), (unsigned)K);
-            em_finalize_fast_kernel<<<grid, 128, 0, st>>>(P, wbound * 1.0001f);
+            dim3 grid((unsigned)((s.nchunkE * 4 + 7) / 8), (unsigned)K);
+            em_finalize_fast_kernel<<<grid, 256, 0, st>>>(P, wbound * 1.0001f);
             return check_launch("tsr_em_finalize");
         }
     } else {
