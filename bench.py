@@ -318,6 +318,21 @@ def run_native(args):
         k1a.append((e0, e1))
     torch.cuda.synchronize()
     k1a_ms = float(np.mean([a.elapsed_time(b) for a, b in k1a]))
+    # A8 / A9: the real-valued detectors (detect_float / detect_float_max), bit-exact SIMT kernel, at an edge-level shape:
+    # 64 utterances x 300 frames x 320 real features against 8 templates of 40 frames
+    gf = torch.Generator(device=dev).manual_seed(9)
+    Ff = torch.rand((64, T_FRAMES, F_BANDS * E_EDGES), device=dev, generator=gf)
+    LFf = torch.randn((8, L_TEMPL, F_BANDS * E_EDGES), device=dev, generator=gf)
+    csf = torch.randn(8, device=dev, generator=gf)
+    ops.detect_float(Ff, LFf, csf)
+    dfl = []
+    for _ in range(3):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream); ops.detect_float(Ff, LFf, csf); e1.record(stream)
+        dfl.append((e0, e1))
+    torch.cuda.synchronize()
+    dfl_ms = float(np.mean([a.elapsed_time(b) for a, b in dfl]))
+    dfl_flop = 2.0 * 64 * (T_FRAMES - L_TEMPL + 1) * L_TEMPL * F_BANDS * E_EDGES * 8
     total_ms = float(sum(step_ms))
     t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -379,6 +394,13 @@ def run_native(args):
             "spread_edges_standalone": {"ms": k1a_ms, "bound": "hbm", "achieved_gbs": BYTES_SPREAD_EDGES * B / (k1a_ms * 1e-3) / 1e9,
                                         "frac": BYTES_SPREAD_EDGES * B / (k1a_ms * 1e-3) / 1e9 / peaks["hbm"],
                                         "note": "not in the step: K1a as its own launches (cold L2), kept for radii / direction tables K2 does not fuse"},
+            "detect_float": {"ms": dfl_ms, "bound": "fp32 mul+add issue (bit-exact sequential order: no FMA, no tensor cores)",
+                             "achieved_tflops": dfl_flop / (dfl_ms * 1e-3) / 1e12,
+                             "peak_tflops": 148 * 128 * (clocks or {}).get("sm_max_mhz", 1965.0) * 1e6 / 1e12,
+                             "frac": dfl_flop / (dfl_ms * 1e-3) / (148 * 128 * (clocks or {}).get("sm_max_mhz", 1965.0) * 1e6),
+                             "shape": "64 utterances x 300 frames x 320 real features, 8 templates x 40 frames (detect_float_max)",
+                             "note": "not in the step: the real-valued detectors reproduce the reference's float32 rounding bit for bit, "
+                                     "which fixes the order of every output's L*D additions; peak = one fp32 instruction per lane and clock"},
             "config2_coding_frames_per_s": B * T_FRAMES * world / (sum(stage_ms[:2]) * 1e-3),
         }
         line = {

@@ -131,6 +131,20 @@ __global__ void parts_publish_format_kernel(uint8_t* __restrict__ blob, PartsLay
     hdr[0] = pick_format(hdr[1], plane_format);
 }
 
+struct SpreadConst {      // per-launch constants of the fused spreading (divisions by F and block_len as multiply-high)
+    uint32_t magicF, magicB;
+    int T, F, block_len, tfull, tail_lo, last;
+};
+__host__ inline SpreadConst spread_const(int T, int F, int block_len) {
+    SpreadConst c;
+    c.T = T; c.F = F; c.block_len = block_len;
+    c.magicF = (uint32_t)(0xFFFFFFFFull / (unsigned)F) + 1u;
+    c.magicB = block_len > 0 ? (uint32_t)(0xFFFFFFFFull / (unsigned)block_len) + 1u : 0u;
+    c.tfull = block_len > 0 ? (T / block_len) * block_len : T;
+    c.tail_lo = block_len > 0 && T > block_len ? T - block_len : 0;
+    c.last = T * F - 1;
+    return c;
+}
 struct CodeArgs {
     const uint8_t* bits;
     const uint8_t* blob;
@@ -140,6 +154,7 @@ struct CodeArgs {
     int B, T, F, To, Fo;
     int threshold, mask_threshold;
     int spread_radius, block_len;   // fused edge spreading in the producers (radius 1, unit direction table); 0 = input used as is
+    SpreadConst sc;
     PartsLayout L;
     int dbg;            // debug experiments: 1 = epilogue skips TMEM reads, 2 = MMA warp skips tcgen05.mma
     long long* trace;   // optional debug timeline of CTA 0: [tile][8] clock64 stamps (tools/trace_code_parts.py)
@@ -165,24 +180,28 @@ struct CodeArgs {
 // _edge_map_threshold_segments does (:1617-1663); the frames of a ragged last block belong to the window of the final
 // block_len frames (:1595-1633).  Nine byte loads per position instead of one, no extra launch and no second pass
 // over the edge map.
-__device__ __forceinline__ uint32_t spread1_byte(const uint8_t* __restrict__ src, int p, int T, int F, int block_len, int plimit) {
-    const int t = p / F, f = p - t * F;
-    int lo = 0, hi = T;
-    if (block_len > 0) {
-        const int tfull = (T / block_len) * block_len;
-        if (t >= tfull) { lo = T - block_len; if (lo < 0) lo = 0; }
-        else { lo = (t / block_len) * block_len; hi = lo + block_len; }
-    }
-    // All nine loads are unconditional (addresses clamped into the utterance) so that they issue back to back; the
-    // validity of a neighbour is applied as a mask afterwards.  (Loads under `if` serialise their latencies: the
-    // first version of this function doubled the kernel's time.)
-    const uint32_t up = t - 1 >= lo ? 0xFFu : 0u, dn = t + 1 < hi ? 0xFFu : 0u, lf = f > 0 ? 0xFFu : 0u, rt = f + 1 < F ? 0xFFu : 0u;
-    const int last = plimit - 1;
-    auto at = [&](int q) -> uint32_t { return src[q < 0 ? 0 : (q > last ? last : q)]; };
-    const uint32_t c = src[p], u = at(p - F), d = at(p + F), l = at(p - 1), r = at(p + 1);
-    const uint32_t ul = at(p - F - 1), dr = at(p + F + 1), dl = at(p + F - 1), ur = at(p - F + 1);
-    return c | (u & up & 0x03u) | (d & dn & 0x03u) | (l & lf & 0x0Cu) | (r & rt & 0x0Cu) | (ul & up & lf & 0x30u) |
-           (dr & dn & rt & 0x30u) | (dl & dn & lf & 0xC0u) | (ur & up & rt & 0xC0u);
+// x / d for x < 2^31 with magic = floor((2^32 - 1) / d) + 1: the multiply-high is x / d or one more; one fix-up
+__device__ __forceinline__ int fast_div(int x, int d, uint32_t magic, int& rem) {
+    int q = (int)__umulhi((uint32_t)x, magic);
+    rem = x - q * d;
+    if (rem < 0) { rem += d; --q; }
+    return q;
+}
+__device__ __forceinline__ uint32_t spread1_byte(const uint8_t* __restrict__ src, int p, const SpreadConst& C) {
+    int f, r;
+    const int t = fast_div(p, C.F, C.magicF, f);
+    bool up, dn;
+    if (C.block_len <= 0) { up = t > 0; dn = t + 1 < C.T; }
+    else if (t >= C.tfull) { up = t - 1 >= C.tail_lo; dn = t + 1 < C.T; }        // ragged tail: window of the final block_len frames
+    else { fast_div(t, C.block_len, C.magicB, r); up = r != 0; dn = r != C.block_len - 1; }
+    // All nine loads are unconditional (addresses kept inside the utterance with four clamps) so that they issue back
+    // to back; the validity of a neighbour is applied as a mask afterwards.
+    const uint32_t mu = up ? 0xFFu : 0u, md = dn ? 0xFFu : 0u, ml = f > 0 ? 0xFFu : 0u, mr = f + 1 < C.F ? 0xFFu : 0u;
+    const int pu = up ? p - C.F : p, pd = dn ? p + C.F : p;          // a valid neighbour row keeps its true address
+    const uint32_t c = src[p], u = src[pu], d = src[pd], l = src[max(p - 1, 0)], rr = src[min(p + 1, C.last)];
+    const uint32_t ul = src[max(pu - 1, 0)], ur = src[min(pu + 1, C.last)], dl = src[max(pd - 1, 0)], dr = src[min(pd + 1, C.last)];
+    return c | (((u & mu) | (d & md)) & 0x03u) | (((l & ml) | (rr & mr)) & 0x0Cu) | (((ul & mu & ml) | (dr & md & mr)) & 0x30u) |
+           (((dl & md & ml) | (ur & mu & mr)) & 0xC0u);
 }
 
 // --------------------------------------------------------------------------- SIMT path
@@ -348,7 +367,7 @@ __global__ void __launch_bounds__(CP_THREADS, 1) code_parts_tc_kernel(CodeArgs A
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 int pos = pt + 128 * j, p = p0 + pos;
-                pre[j] = (pos < npos && p < plimit) ? (A.spread_radius ? spread1_byte(src, p, A.T, A.F, A.block_len, plimit) : (uint32_t)src[p]) : 0u;
+                pre[j] = (pos < npos && p < plimit) ? (A.spread_radius ? spread1_byte(src, p, A.sc) : (uint32_t)src[p]) : 0u;
             }
         };
         if ((long long)blockIdx.x < ntiles) prefetch(blockIdx.x);
@@ -369,7 +388,7 @@ __global__ void __launch_bounds__(CP_THREADS, 1) code_parts_tc_kernel(CodeArgs A
                 const uint8_t* src = A.bits + (size_t)b * A.T * A.F;
                 for (int pos = pt + 512; pos < npos; pos += 128) {
                     int p = p0 + pos;
-                    const uint32_t byte = p < plimit ? (A.spread_radius ? spread1_byte(src, p, A.T, A.F, A.block_len, plimit) : (uint32_t)src[p]) : 0u;
+                    const uint32_t byte = p < plimit ? (A.spread_radius ? spread1_byte(src, p, A.sc) : (uint32_t)src[p]) : 0u;
                     *reinterpret_cast<uint4*>(dst + pos * 16) = expand_byte(byte, one);
                 }
             }
@@ -598,6 +617,7 @@ int tsr_code_parts(const uint8_t* bits, const void* parts_blob, int K, int ph, i
     A.B = B; A.T = T; A.F = F; A.To = T - ph + 1; A.Fo = F - pw + 1;
     A.threshold = threshold; A.mask_threshold = mask_threshold;
     A.spread_radius = edge_spread_radius; A.block_len = edge_block_len;
+    A.sc = spread_const(T, F, edge_block_len);
     A.trace = g_code_trace;
     A.dbg = g_code_dbg;
     A.L = parts_layout(K, ph, pw);

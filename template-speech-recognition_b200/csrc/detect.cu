@@ -973,25 +973,63 @@ __global__ void detect_simt_kernel(const uint32_t* __restrict__ bits, const floa
     }
 }
 
-// Real-valued features: separate multiply and add in (tau, d) order (detect_float :206-216).
-__global__ void detect_float_kernel(const float* __restrict__ Fm, const float* __restrict__ LF,
-                                    const float* __restrict__ init, float* __restrict__ scores, long long R, int T,
-                                    int D, int M, int L) {
-    const long long total = R * M;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const long long g = i / M;
-        const int m = (int)(i - g * M);
-        const int tl = (int)(g % T);
-        float acc = 0.f;
-        if (tl <= T - L) {
-            if (init) acc = init[m];          // detect_float_max starts at cs[m] (:258)
-            for (int tau = 0; tau < L; ++tau) {
-                const float* x = Fm + (g + tau) * D;
-                const float* w = LF + ((size_t)m * L + tau) * D;
-                for (int d = 0; d < D; ++d) acc = __fadd_rn(acc, __fmul_rn(w[d], x[d]));
+// Real-valued features: separate multiply and add in (tau, d) order (detect_float :206-216) -- the reference's exact
+// float32 arithmetic, so the result is bit-identical to it.  That fixes the order of the L*D additions of every
+// output: an output is one dependent chain, and what a kernel can still do is keep several chains in flight per thread
+// and feed them from shared memory.  CTA = 128 consecutive frame rows x DF_TM templates; per (tau, 32-feature chunk)
+// the 128 x 32 window of features is staged coalesced (pitch 33: row-per-thread reads are conflict free) next to the
+// DF_TM weight rows (broadcast reads); a thread owns one row and DF_TM independent accumulators: 1 + DF_TM shared loads
+// for 2 * DF_TM arithmetic instructions per feature, no global load in the inner loop.
+#define DF_TM 4
+#define DF_DC 32
+__global__ void __launch_bounds__(128) detect_float_kernel(const float* __restrict__ Fm, const float* __restrict__ LF,
+                                                           const float* __restrict__ init, float* __restrict__ scores, long long R,
+                                                           int T, int D, int M, int L) {
+    __shared__ float sx[128 * (DF_DC + 1)];
+    __shared__ float sw[DF_TM * DF_DC];
+    const int tid = threadIdx.x;
+    const long long g0 = (long long)blockIdx.x * 128;
+    const int m0 = blockIdx.y * DF_TM;
+    const long long g = g0 + tid;
+    const bool valid = g < R && (int)(g % T) <= T - L;
+    float acc[DF_TM];
+#pragma unroll
+    for (int j = 0; j < DF_TM; ++j) acc[j] = (init && m0 + j < M) ? init[m0 + j] : 0.f;     // detect_float_max starts at cs[m] (:258)
+    for (int tau = 0; tau < L; ++tau) {
+        for (int d0 = 0; d0 < D; d0 += DF_DC) {
+            const int dc = D - d0 < DF_DC ? D - d0 : DF_DC;
+            __syncthreads();
+            for (int e = tid; e < 128 * DF_DC; e += 128) {
+                const int r = e / DF_DC, c = e - r * DF_DC;
+                const long long row = g0 + r + tau;
+                sx[r * (DF_DC + 1) + c] = (row < R && c < dc) ? Fm[row * D + d0 + c] : 0.f;
+            }
+            if (tid < DF_TM * DF_DC) {
+                const int j = tid / DF_DC, c = tid - j * DF_DC;
+                sw[tid] = (m0 + j < M && c < dc) ? LF[((size_t)(m0 + j) * L + tau) * D + d0 + c] : 0.f;
+            }
+            __syncthreads();
+            const float* xr = sx + tid * (DF_DC + 1);
+            if (dc == DF_DC) {
+#pragma unroll
+                for (int c = 0; c < DF_DC; ++c) {
+                    const float x = xr[c];
+#pragma unroll
+                    for (int j = 0; j < DF_TM; ++j) acc[j] = __fadd_rn(acc[j], __fmul_rn(sw[j * DF_DC + c], x));
+                }
+            } else {
+                for (int c = 0; c < dc; ++c) {
+                    const float x = xr[c];
+#pragma unroll
+                    for (int j = 0; j < DF_TM; ++j) acc[j] = __fadd_rn(acc[j], __fmul_rn(sw[j * DF_DC + c], x));
+                }
             }
         }
-        scores[i] = acc;
+    }
+    if (g < R) {
+#pragma unroll
+        for (int j = 0; j < DF_TM; ++j)
+            if (m0 + j < M) scores[g * M + m0 + j] = valid ? acc[j] : 0.f;
     }
 }
 
@@ -1270,9 +1308,9 @@ int tsr_detect_float(const float* Fm, int B, int T, int D, const float* LF, int 
     int rc = require_sm100("tsr_detect_float");
     if (rc) return rc;
     const long long R = (long long)B * T;
-    long long blocks = (R * M + 127) / 128;
-    if (blocks > (long long)sm_count() * 32) blocks = (long long)sm_count() * 32;
-    detect_float_kernel<<<(unsigned)blocks, 128, 0, (cudaStream_t)stream>>>(Fm, LF, init_or_null, scores, R, T, D, M, L);
+    TSR_REQUIRE((R + 127) / 128 < (1ll << 31) && (M + DF_TM - 1) / DF_TM <= 65535, "tsr_detect_float: problem too large");
+    dim3 grid((unsigned)((R + 127) / 128), (unsigned)((M + DF_TM - 1) / DF_TM));
+    detect_float_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(Fm, LF, init_or_null, scores, R, T, D, M, L);
     return check_launch("tsr_detect_float");
 }
 

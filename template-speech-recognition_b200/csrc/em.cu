@@ -182,9 +182,9 @@ __global__ void __launch_bounds__(BG_THREADS, 1) bitgemm_kernel(const __grid_con
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < BG_NW; ++s) { mbar_init(&wfull[s], 1); mbar_init(&wempty[s], 1); }
-        for (int s = 0; s < BG_NSTRIP; ++s) { mbar_init(&afull[s], 64); mbar_init(&aempty[s], 1); }
+        for (int s = 0; s < BG_NSTRIP; ++s) { mbar_init(&afull[s], 256); mbar_init(&aempty[s], 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 128); }
-        for (int s = 0; s < BG_NRAW; ++s) { mbar_init(&rfull[s], 1); mbar_init(&rempty[s], 64); }
+        for (int s = 0; s < BG_NRAW; ++s) { mbar_init(&rfull[s], 1); mbar_init(&rempty[s], 256); }
         mbar_fence_init();
     }
     if (warp == 13) tmem_alloc<512>(tmem_ptr);
@@ -217,91 +217,76 @@ __global__ void __launch_bounds__(BG_THREADS, 1) bitgemm_kernel(const __grid_con
         }
     } else if (warp >= 1 && warp <= 8) {
         // ================================== bit expanders ==================================
-        // Four groups of 64 threads; group g fills strip buffer g with every fourth chunk (a thread expands four of
-        // the strip's 256 rows).  The wait -> expand -> proxy fence -> arrive chain of one strip is mostly latency;
-        // four strips in flight hide it behind the 512 cycles the MMAs spend on a chunk.  The next chunk's words are
-        // fetched before the wait.
-        const int g = (warp - 1) >> 1;
-        const int tg = (threadIdx.x - 32) & 63;
+        // All 256 threads work on every strip, one row each (68 instructions), into strip buffer ic % 4.  A buffer's
+        // cycle is MMA (512 cycles) -> wake-up -> expand -> proxy fence -> arrive -> MMA wake-up; with a quarter of the
+        // threads per strip (one group of 64 per buffer, four rows per thread) the expansion alone took ~500 cycles and
+        // the whole cycle ~4000, twice what four buffers can hide; one row per thread keeps it near 1000.
+        const int tg = threadIdx.x - 32;                     // row of the strip
         BgWalk w(A);
-        int rt = 0, mt, c0 = 0, n = 0, i = 0;
+        int rt, mt, c0, n;
         uint32_t ic = 0;
-        // advance to the next chunk this group owns; returns false at the end of the CTA's share
-        auto advance = [&](int& o_rt, int& o_c) -> bool {
-            for (;;) {
-                if (i == n) {
-                    if (!w.next_seg(rt, mt, c0, n)) return false;
-                    i = 0;
-                }
-                const bool mine = (int)(ic & 3) == g;
-                o_rt = rt; o_c = c0 + i;
-                ++i; ++ic;
-                if (mine) return true;
+        auto expand = [&](uint8_t* strip, const uint4& x) {
+            uint8_t* dst = strip + tg * 16;
+            const uint32_t wv[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+            for (int wi = 0; wi < 4; ++wi) {
+                const uint32_t v = wv[wi];
+                const uint4 a = make_uint4(v & 0x01010101u, (v >> 1) & 0x01010101u, (v >> 2) & 0x01010101u, (v >> 3) & 0x01010101u);
+                const uint4 b = make_uint4((v >> 4) & 0x01010101u, (v >> 5) & 0x01010101u, (v >> 6) & 0x01010101u, (v >> 7) & 0x01010101u);
+                *reinterpret_cast<uint4*>(dst + (2 * wi) * 4096) = a;
+                *reinterpret_cast<uint4*>(dst + (2 * wi + 1) * 4096) = b;
             }
         };
-        auto load = [&](int l_rt, int l_c, uint4 (&x)[4]) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const long long row = (long long)l_rt * 256 + tg + 64 * k;
-                uint2 lo = make_uint2(0u, 0u), hi = make_uint2(0u, 0u);
-                if (row < A.R) {
-                    const uint2* p = reinterpret_cast<const uint2*>(A.bits + row * A.rw + 4 * l_c);
-                    lo = __ldg(p);
-                    if (4 * l_c + 2 < A.rw) hi = __ldg(p + 1);
-                }
-                x[k] = make_uint4(lo.x, lo.y, hi.x, hi.y);
+        auto load = [&](int l_rt, int l_c) -> uint4 {        // LDG path: the row's four words of chunk l_c
+            const long long row = (long long)l_rt * 256 + tg;
+            uint2 lo = make_uint2(0u, 0u), hi = make_uint2(0u, 0u);
+            if (row < A.R) {
+                const uint2* p = reinterpret_cast<const uint2*>(A.bits + row * A.rw + 4 * l_c);
+                lo = __ldg(p);
+                if (4 * l_c + 2 < A.rw) hi = __ldg(p + 1);
             }
+            return make_uint4(lo.x, lo.y, hi.x, hi.y);
         };
-        uint8_t* strip = strips + g * BG_STRIP_BYTES;
-        auto expand = [&](const uint4 (&x)[4]) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                uint8_t* dst = strip + (tg + 64 * k) * 16;
-                const uint32_t wv[4] = {x[k].x, x[k].y, x[k].z, x[k].w};
-#pragma unroll
-                for (int wi = 0; wi < 4; ++wi) {
-                    const uint32_t v = wv[wi];
-                    const uint4 a = make_uint4(v & 0x01010101u, (v >> 1) & 0x01010101u, (v >> 2) & 0x01010101u, (v >> 3) & 0x01010101u);
-                    const uint4 b = make_uint4((v >> 4) & 0x01010101u, (v >> 5) & 0x01010101u, (v >> 6) & 0x01010101u, (v >> 7) & 0x01010101u);
-                    *reinterpret_cast<uint4*>(dst + (2 * wi) * 4096) = a;
-                    *reinterpret_cast<uint4*>(dst + (2 * wi + 1) * 4096) = b;
-                }
-            }
-        };
-        uint32_t use = 0;
         if (RAW_TMA) {
-            // chunk ic (global count of this CTA) sits in raw tile ic % BG_NRAW; this group takes ic = g, g + 4, ...
-            int crt, cc;
-            while (advance(crt, cc)) {
-                const uint32_t icm = ic - 1, rs = icm % BG_NRAW;
-                mbar_wait_relaxed(&rfull[rs], (icm / BG_NRAW) & 1);
-                uint4 x[4];
-#pragma unroll
-                for (int k = 0; k < 4; ++k) x[k] = *reinterpret_cast<const uint4*>(raw + rs * BG_RAW_BYTES + (tg + 64 * k) * 16);
-                mbar_arrive(&rempty[rs]);                    // the words are in registers: the tile may be refilled
-                mbar_wait_relaxed(&aempty[g], (use & 1) ^ 1);
-                expand(x);
-                fence_proxy_async_smem();
-                mbar_arrive(&afull[g]);
-                ++use;
+            while (w.next_seg(rt, mt, c0, n)) {
+                for (int i = 0; i < n; ++i, ++ic) {
+                    const uint32_t buf = ic & 3, rs = ic % BG_NRAW;
+                    mbar_wait_relaxed(&rfull[rs], (ic / BG_NRAW) & 1);
+                    const uint4 x = *reinterpret_cast<const uint4*>(raw + rs * BG_RAW_BYTES + tg * 16);
+                    mbar_arrive(&rempty[rs]);                // the words are in registers: the tile may be refilled
+                    mbar_wait_relaxed(&aempty[buf], ((ic >> 2) & 1) ^ 1);
+                    expand(strips + buf * BG_STRIP_BYTES, x);
+                    fence_proxy_async_smem();
+                    mbar_arrive(&afull[buf]);
+                }
             }
         } else {
-            uint4 x[4], y[4];
-            int crt, cc;
-            bool ok = advance(crt, cc);
-            if (ok) load(crt, cc, x);
-            while (ok) {
-                int nrt, nc;
-                const bool ok2 = advance(nrt, nc);
-                if (ok2) load(nrt, nc, y);
-                mbar_wait_relaxed(&aempty[g], (use & 1) ^ 1);
-                expand(x);
+            // two chunks of look-ahead in registers
+            int prt[3], pc[3];
+            uint4 x[3];
+            int have = 0;
+            bool more = true;
+            int i = 0;
+            n = 0;
+            auto fetch = [&]() {                             // queue the next chunk's words, if any
+                if (i == n) {
+                    if (!w.next_seg(rt, mt, c0, n)) { more = false; return; }
+                    i = 0;
+                }
+                prt[have] = rt; pc[have] = c0 + i; x[have] = load(rt, c0 + i);
+                ++i; ++have;
+            };
+            fetch(); if (more) fetch();
+            while (have > 0) {
+                if (more) fetch();
+                const uint32_t buf = ic & 3;
+                mbar_wait_relaxed(&aempty[buf], ((ic >> 2) & 1) ^ 1);
+                expand(strips + buf * BG_STRIP_BYTES, x[0]);
                 fence_proxy_async_smem();
-                mbar_arrive(&afull[g]);
-                ++use;
-#pragma unroll
-                for (int k = 0; k < 4; ++k) x[k] = y[k];
-                ok = ok2;
+                mbar_arrive(&afull[buf]);
+                ++ic;
+                x[0] = x[1]; x[1] = x[2];
+                --have;
             }
         }
     } else if (warp == 13) {
@@ -709,6 +694,7 @@ __global__ void __launch_bounds__(128) em_posterior_kernel(PostArgs P) {
     if (P.done && *P.done) return;
     extern __shared__ __align__(16) uint8_t psm[];
     uint32_t* s_max = reinterpret_cast<uint32_t*>(psm);               // [K]
+    float* s_aff = reinterpret_cast<float*>(psm + (((size_t)P.K * 4 + 15) & ~(size_t)15));   // KREG > 0: [128][K + 1] staging of the posteriors
     __shared__ long long s_ll;
     const int tid = threadIdx.x;
     const long long n = blockIdx.x * 128LL + tid;
@@ -784,10 +770,9 @@ __global__ void __launch_bounds__(128) em_posterior_kernel(PostArgs P) {
     auto pass3 = [&](int k, double s) {
         const double v = s + (double)P.logw[k];
         float p = 0.f;
-        if (live) {
-            p = P.hard ? (k == arg ? 1.f : 0.f) : fminf(expf((float)(v - mx)) * inv, 1.f);
-            P.aff[n * P.K + k] = p;
-        }
+        if (live) p = P.hard ? (k == arg ? 1.f : 0.f) : fminf(expf((float)(v - mx)) * inv, 1.f);
+        if (KREG > 0) s_aff[tid * (P.K + 1) + k] = p;          // written out as one contiguous 128 x K block below
+        else if (live) P.aff[n * P.K + k] = p;
         const uint32_t wmax = __reduce_max_sync(0xffffffffu, __float_as_uint(p));     // p >= 0: bit patterns order like values
         if ((tid & 31) == 0 && wmax) atomicMax(&s_max[k], wmax);
     };
@@ -801,6 +786,14 @@ __global__ void __launch_bounds__(128) em_posterior_kernel(PostArgs P) {
     for (int off = 16; off > 0; off >>= 1) my_ll += __shfl_xor_sync(0xffffffffu, my_ll, off);
     if ((tid & 31) == 0) atomicAdd(reinterpret_cast<unsigned long long*>(&s_ll), (unsigned long long)my_ll);
     __syncthreads();
+    if (KREG > 0) {      // rows n0 .. n0+127 of aff are one contiguous block of 128 * K floats: coalesced stores
+        const long long base = blockIdx.x * 128LL * P.K;
+        const long long lim = P.N * P.K;
+        for (int e = tid; e < 128 * P.K; e += 128) {
+            const int r = e / P.K, k = e - r * P.K;
+            if (base + e < lim) P.aff[base + e] = s_aff[r * (P.K + 1) + k];
+        }
+    }
     for (int k = tid; k < P.K; k += 128)
         if (s_max[k]) atomicMax(P.colmax + k, s_max[k]);
     if (tid == 0) atomicAdd(reinterpret_cast<unsigned long long*>(P.llQ), (unsigned long long)s_ll);
@@ -840,6 +833,16 @@ __global__ void __launch_bounds__(128) em_aff_planes_kernel(const float* __restr
     for (int k = tid; k < K; k += 128) s_resp[k] = 0;
     if (blockIdx.x == 0)
         for (int k = tid; k < K; k += 128) S.sk[k] = (double)em_col_scale(S.colmax[k]);     // for em_pack_kernel
+    float* s_aff = reinterpret_cast<float*>(psm + (((size_t)8 * mrp * 16 + (size_t)K * 4 + 15) & ~(size_t)15));
+    const bool staged = K <= 32;
+    if (staged) {        // the block's 128 x K posteriors are contiguous in global memory: coalesced loads, pitch K + 1 in smem
+        const long long base = blockIdx.x * 128LL * K, lim = N * K;
+        for (int e = tid; e < 128 * K; e += 128) {
+            const int r = e / K, k = e - r * K;
+            s_aff[r * (K + 1) + k] = base + e < lim ? aff[base + e] : 0.f;
+        }
+        __syncthreads();
+    }
     const int pos = em_tile_pos(tid);
     const size_t tile_bytes = (size_t)8 * mrp * 16;
     for (int mt = 0; mt < Mtiles; ++mt) {
@@ -849,7 +852,7 @@ __global__ void __launch_bounds__(128) em_aff_planes_kernel(const float* __restr
         for (int k = mt * KT; k < k1; ++k) {
             const float sk = em_col_scale(S.colmax[k]);
             const float isk = sk >= 1.17549435e-38f ? 1.f / sk : 0.f;        // power-of-two s_k: aff / s_k is exact and <= 1
-            const float p = live ? fmaxf(aff[n * K + k], 0.f) : 0.f;
+            const float p = live ? fmaxf(staged ? s_aff[tid * (K + 1) + k] : aff[n * K + k], 0.f) : 0.f;
             int q = (int)rintf(p * isk * (float)EM_QMAX);
             const int qsum = __reduce_add_sync(0xffffffffu, q);
             if ((tid & 31) == 0 && qsum) atomicAdd(&s_resp[k], qsum);
@@ -1007,7 +1010,7 @@ static int em_prepare(const EmShape& s, uint8_t* ws, const float* logT, const fl
 
 // posteriors (device, [N][K]) -> digit planes + responsibility sums (+ log-likelihood) in the statistics tail
 static int em_planes(const EmShape& s, uint8_t* ws, const float* aff, double* stats, int write_ll, const int* done, cudaStream_t st) {
-    const size_t psm = s.tile_bytes + (size_t)s.K * 4;
+    const size_t psm = ((s.tile_bytes + (size_t)s.K * 4 + 15) & ~(size_t)15) + (s.K <= 32 ? (size_t)128 * (s.K + 1) * 4 : 0);
     static size_t psm_set = 0;
     if (psm > psm_set) {
         TSR_CUDA(cudaFuncSetAttribute(em_aff_planes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm));
@@ -1052,7 +1055,7 @@ int tsr_em_estep(const uint32_t* Xbits, long long N, int D, int rowwords, int K,
     P.update = update; P.done = done; P.colmax = sm.colmax; P.llQ = sm.llQ;
     if (update)     // (a stopped loop skips the kernels that would consume this, so clearing unconditionally is harmless)
         TSR_CUDA(cudaMemsetAsync(ws + s.off_small, 0, s.off_scratch - s.off_small, st));
-    const size_t psm = (size_t)K * 4;
+    const size_t psm = (((size_t)K * 4 + 15) & ~(size_t)15) + (K <= 32 ? (size_t)128 * (K + 1) * 4 : 0);
     const unsigned pgrid = (unsigned)(s.Npad / 128);
     if (impl == TSR_IMPL_SIMT) {
         long long blocks = (N * K + 127) / 128;
