@@ -226,7 +226,7 @@ def run_reference(args):
 
 
 def workload_config(batch):
-    return {"workload": "config3 full scoring pipeline: spread_edges(r=1,block=40; fused into the next kernel) -> code_parts(100 parts 5x5x8, thr 12, argmax) "
+    return {"workload": "config3 full scoring pipeline: spread_edges(r=1,block=40) -> code_parts(100 parts 5x5x8, thr 12, argmax) "
                         "-> spread_patches(2,2) -> 32 x 40-frame part-level template LLR detect -> max/argmax",
             "utterance": "300 frames x 40 bands x 8 edges", "utterances_per_gpu": batch, "parts": K_PARTS, "templates": M_TEMPL,
             "template_frames": L_TEMPL, "sharding": "by utterance, no collective",
@@ -264,7 +264,7 @@ def run_native(args):
     flush_rd = torch.zeros(256 << 18, dtype=torch.int32, device=dev)           # read-only second pass: leaves the L2 cold AND clean
     stream = torch.cuda.current_stream()
 
-    fused = not args.simt and not args.no_fuse
+    fused = args.fuse and not args.simt
 
     def step(evs=None):
         def mark(i):
@@ -429,7 +429,7 @@ def run_native(args):
             "e2e_device_pack": {"value": frames * e2e_steps / e2e_devpack_s, "unit": "frames/s", "h2d_bytes_per_step": int(X_pinned.numel()),
                                 "d2h_bytes_per_step": int(B * TO * 4 + B * TO * 2),
                                 "api": "same call with pack='device': the unpacked uint8 tensor crosses PCIe and is packed by the GPU"},
-            "gpu_launches": (4 if fused else 6) * args.steps,   # code_parts (+ fused spreading), spread_codes, detect, key decode (+ 1 memset node)
+            "gpu_launches": (4 if fused else 5) * args.steps,   # spread_edges, code_parts, spread_codes, detect (fused mixture max), key decode; + one 2.4 MB memset node
             "clocks": clocks,
         }
         if world == 1 and not args.no_cpu:
@@ -642,7 +642,7 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--simt", action="store_true", help="use the SIMT cross-check kernels for coding and detection")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--no-fuse", action="store_true", help="run the edge spreading as its own launches instead of inside code_parts")
+    ap.add_argument("--fuse", action="store_true", help="run the edge spreading inside code_parts' producers (bit-identical, measured slower) instead of as its own launch")
     ap.add_argument("--no-extra", action="store_true", help="skip the config-4 (EM) and config-5 (stream) sub-results of the default line")
     ap.add_argument("--planes", default="int8x3", choices=["fp16", "bf16", "int8x2", "int8x3"],
                     help="weight-plane format of the detection stage (DESIGN.md section 4)")

@@ -81,10 +81,12 @@ int tsr_unpack_features_u8(const uint32_t* bits, uint8_t* Fm, long long R, int D
  * out bit e at (t,f) = OR_{k=-radius..radius} in bit e at (t + k*dt[e], f + k*df[e]), zero
  * outside the utterance and outside the `block_len`-frame block of t (block_len = 0: no
  * blocks; the reference spreads per 40-frame block, edge_signal_proc.py:1635-1663).
+ * tail_window != 0: a ragged last block (T % block_len frames) is spread as the tail of the window of the final
+ *         block_len frames, as _edge_map_threshold_segments does (:1595-1633), instead of as a short block of its own.
  * mode 0: line along host_dirs[e] = {df (frequency step), dt (time step)} per orientation
  *         (int8 [8][2], HOST pointer, copied at launch);  mode 1: (2r+1)^2 box, dirs ignored. */
 int tsr_spread_edges(const uint8_t* bits_in, uint8_t* bits_out, int B, int T, int F, int radius, int mode,
-                     const int8_t* host_dirs, int block_len, void* stream);
+                     const int8_t* host_dirs, int block_len, int tail_window, void* stream);
 
 /* ---- K2: part coding --------------------------------------------------------------------
  * Replaces code_parts.code_parts (code_parts.pyx:70-135), code_parts_fast (:247-295),

@@ -23,7 +23,7 @@ SIGNATURES = {
     "tsr_host_pack_edges": (_i, [_vp, _vp, _ll, _i, _i]),
     "tsr_pack_features_u8": (_i, [_vp, _vp, _ll, _i, _i, _vp]),
     "tsr_unpack_features_u8": (_i, [_vp, _vp, _ll, _i, _i, _vp]),
-    "tsr_spread_edges": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _i, _vp]),
+    "tsr_spread_edges": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _i, _i, _vp]),
     "tsr_parts_blob_bytes": (_sz, [_i, _i, _i]),
     "tsr_prepare_parts": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _i, _vp, _vp]),
     "tsr_code_parts": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),

@@ -182,6 +182,7 @@ struct CodeArgs {
 // over the edge map.
 // x / d for x < 2^31 with magic = floor((2^32 - 1) / d) + 1: the multiply-high is x / d or one more; one fix-up
 __device__ __forceinline__ int fast_div(int x, int d, uint32_t magic, int& rem) {
+    if (magic == 0u) { rem = 0; return x; }               // d == 1 (2^32 / 1 does not fit the 32-bit magic)
     int q = (int)__umulhi((uint32_t)x, magic);
     rem = x - q * d;
     if (rem < 0) { rem += d; --q; }

@@ -75,7 +75,7 @@ static EmShape em_shape(long long N, int D, int K) {
     s.off_accM = s.off_accE + up((size_t)s.Mtiles * s.mrp * s.Npad * 4);
     s.off_ablob = s.off_accM + up((size_t)s.Mtiles * s.mrp * s.Dpad * 4);
     s.off_small = s.off_ablob + up((size_t)s.Mtiles * s.nchunkM * s.tile_bytes);
-    s.off_scratch = s.off_small + up(sizeof(long long) * (2 * (size_t)K + 2) + sizeof(uint32_t) * (size_t)K);
+    s.off_scratch = s.off_small + up(sizeof(long long) * (32 * (size_t)K + 32 + (size_t)K) + sizeof(uint32_t) * 32 * (size_t)K);
     s.off_aff = s.off_scratch + up((size_t)K * s.Npad * 4);
     s.total = s.off_aff + up((size_t)K * (size_t)N * 4);
     return s;
@@ -428,20 +428,22 @@ static int launch_bitgemm(const uint32_t* bits, long long R, int rw, const uint8
     return check_launch("bitgemm_kernel");
 }
 
-// Small per-call scratch in the workspace: [respQ int64[K] | llQ int64 | ticket int64 | sk double[K] | colmax uint32[K]]
+// Small per-call scratch in the workspace.  Per-CTA partial results are combined with integer atomics; 782 CTAs
+// hitting the same 17 addresses serialise in the L2 atomic unit (~12 us), so every value has EM_SLOTS replicas
+// (CTA b uses slot b % EM_SLOTS) that the consumer reduces.
+//   [respQ int64[SLOTS][K] | llQ int64[SLOTS] | sk double[K] | colmax uint32[SLOTS][K]]
+#define EM_SLOTS 32
 struct EmSmall {
     long long* respQ;
     long long* llQ;
-    unsigned long long* ticket;
     double* sk;                 // per-component posterior scale (power of two), published by the planes kernel
     uint32_t* colmax;
 };
 static EmSmall em_small(uint8_t* ws, const EmShape& s) {
     EmSmall m;
     m.respQ = reinterpret_cast<long long*>(ws + s.off_small);
-    m.llQ = m.respQ + s.K;
-    m.ticket = reinterpret_cast<unsigned long long*>(m.llQ + 1);
-    m.sk = reinterpret_cast<double*>(m.ticket + 1);
+    m.llQ = m.respQ + (size_t)EM_SLOTS * s.K;
+    m.sk = reinterpret_cast<double*>(m.llQ + EM_SLOTS);
     m.colmax = reinterpret_cast<uint32_t*>(m.sk + s.K);
     return m;
 }
@@ -483,13 +485,13 @@ __global__ void em_scores_simt_kernel(const uint32_t* __restrict__ X, long long 
 
 // numerators of the SIMT path: thread per (k, d), rows in order, the same quantised posteriors as the tensor path
 __global__ void em_mstep_simt_kernel(const uint32_t* __restrict__ X, long long N, int D, int rw, int K,
-                                     const float* __restrict__ aff, const uint32_t* __restrict__ colmax, double* __restrict__ stats,
+                                     const float* __restrict__ aff, const double* __restrict__ skd, double* __restrict__ stats,
                                      const int* done) {
     if (done && *done) return;
     const long long total = (long long)K * D;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const int k = (int)(i / D), d = (int)(i - (long long)k * D);
-        const float sk = em_col_scale(colmax[k]);
+        const float sk = (float)skd[k];
         const float isk = sk >= 1.17549435e-38f ? 1.f / sk : 0.f;               // exact: s_k is a power of two
         long long acc = 0;
         for (long long n = 0; n < N; ++n)
@@ -794,9 +796,10 @@ __global__ void __launch_bounds__(128) em_posterior_kernel(PostArgs P) {
             if (base + e < lim) P.aff[base + e] = s_aff[r * (P.K + 1) + k];
         }
     }
+    const int slot = blockIdx.x % EM_SLOTS;
     for (int k = tid; k < P.K; k += 128)
-        if (s_max[k]) atomicMax(P.colmax + k, s_max[k]);
-    if (tid == 0) atomicAdd(reinterpret_cast<unsigned long long*>(P.llQ), (unsigned long long)s_ll);
+        if (s_max[k]) atomicMax(P.colmax + (size_t)slot * P.K + k, s_max[k]);
+    if (tid == 0) atomicAdd(reinterpret_cast<unsigned long long*>(P.llQ + slot), (unsigned long long)s_ll);
 }
 
 // column maxima of caller-supplied posteriors (initialisation; M-step from given posteriors)
@@ -805,7 +808,7 @@ __global__ void em_colmax_kernel(const float* __restrict__ aff, long long N, int
     const long long total = N * K;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const float p = fmaxf(aff[i], 0.f);
-        if (p > 0.f) atomicMax(colmax + (i % K), __float_as_uint(p));
+        if (p > 0.f) atomicMax(colmax + (size_t)(blockIdx.x % EM_SLOTS) * K + (i % K), __float_as_uint(p));
     }
 }
 
@@ -817,23 +820,27 @@ __device__ __forceinline__ int em_tile_pos(int t /* 0..127 */) {
 }
 
 // Posteriors -> the M-step's int8 operand.  CTA = 128 consecutive rows = one chunk of the contraction.
-// q(n,k) = round(aff[n][k] / s_k * EM_QMAX), three balanced base-256 digits, one tile per M tile; respQ[k] += sum_n q.
-// The last CTA to finish turns the integer sums into the float64 tail of the statistics vector.
+// q(n,k) = round(aff[n][k] / s_k * EM_QMAX), three balanced base-256 digits, one tile per M tile; respQ[slot][k] += sum_n q.
+// Every CTA reduces the column-maximum replicas to the scales s_k itself (EM_SLOTS * K loads); CTA 0 publishes them.
 __global__ void __launch_bounds__(128) em_aff_planes_kernel(const float* __restrict__ aff, long long N, long long Npad, int K, int KT,
-                                                            int Mtiles, int mrp, uint8_t* __restrict__ ablob, EmSmall S,
-                                                            double* __restrict__ stats_tail, int write_ll, const int* done) {
+                                                            int Mtiles, int mrp, uint8_t* __restrict__ ablob, EmSmall S, const int* done) {
     if (done && *done) return;
     extern __shared__ __align__(16) uint8_t psm[];
     uint8_t* tile = psm;
     int* s_resp = reinterpret_cast<int*>(psm + (size_t)8 * mrp * 16);
-    __shared__ bool s_last;
+    float* s_isk = reinterpret_cast<float*>(s_resp + K);                                  // 1 / s_k (0 for an empty column)
+    float* s_aff = reinterpret_cast<float*>(psm + (((size_t)8 * mrp * 16 + (size_t)K * 8 + 15) & ~(size_t)15));
     const int tid = threadIdx.x;
     const long long n = blockIdx.x * 128LL + tid;
     const bool live = n < N;
-    for (int k = tid; k < K; k += 128) s_resp[k] = 0;
-    if (blockIdx.x == 0)
-        for (int k = tid; k < K; k += 128) S.sk[k] = (double)em_col_scale(S.colmax[k]);     // for em_pack_kernel
-    float* s_aff = reinterpret_cast<float*>(psm + (((size_t)8 * mrp * 16 + (size_t)K * 4 + 15) & ~(size_t)15));
+    for (int k = tid; k < K; k += 128) {
+        s_resp[k] = 0;
+        uint32_t mx = 0;
+        for (int sl = 0; sl < EM_SLOTS; ++sl) mx = max(mx, S.colmax[(size_t)sl * K + k]);
+        const float sk = em_col_scale(mx);
+        s_isk[k] = sk >= 1.17549435e-38f ? 1.f / sk : 0.f;                               // power-of-two s_k: aff / s_k is exact and <= 1
+        if (blockIdx.x == 0) S.sk[k] = (double)sk;                                       // for em_tail_kernel / em_pack_kernel
+    }
     const bool staged = K <= 32;
     if (staged) {        // the block's 128 x K posteriors are contiguous in global memory: coalesced loads, pitch K + 1 in smem
         const long long base = blockIdx.x * 128LL * K, lim = N * K;
@@ -841,8 +848,8 @@ __global__ void __launch_bounds__(128) em_aff_planes_kernel(const float* __restr
             const int r = e / K, k = e - r * K;
             s_aff[r * (K + 1) + k] = base + e < lim ? aff[base + e] : 0.f;
         }
-        __syncthreads();
     }
+    __syncthreads();
     const int pos = em_tile_pos(tid);
     const size_t tile_bytes = (size_t)8 * mrp * 16;
     for (int mt = 0; mt < Mtiles; ++mt) {
@@ -850,10 +857,8 @@ __global__ void __launch_bounds__(128) em_aff_planes_kernel(const float* __restr
         __syncthreads();
         const int k1 = (mt + 1) * KT < K ? (mt + 1) * KT : K;
         for (int k = mt * KT; k < k1; ++k) {
-            const float sk = em_col_scale(S.colmax[k]);
-            const float isk = sk >= 1.17549435e-38f ? 1.f / sk : 0.f;        // power-of-two s_k: aff / s_k is exact and <= 1
             const float p = live ? fmaxf(staged ? s_aff[tid * (K + 1) + k] : aff[n * K + k], 0.f) : 0.f;
-            int q = (int)rintf(p * isk * (float)EM_QMAX);
+            int q = (int)rintf(p * s_isk[k] * (float)EM_QMAX);
             const int qsum = __reduce_add_sync(0xffffffffu, q);
             if ((tid & 31) == 0 && qsum) atomicAdd(&s_resp[k], qsum);
             const int kl = k - mt * KT;
@@ -869,20 +874,24 @@ __global__ void __launch_bounds__(128) em_aff_planes_kernel(const float* __restr
         for (int i = tid; i < (int)(tile_bytes / 16); i += 128) dst[i] = reinterpret_cast<const uint4*>(tile)[i];
         __syncthreads();
     }
+    const int slot = blockIdx.x % EM_SLOTS;
     for (int k = tid; k < K; k += 128)
-        if (s_resp[k]) atomicAdd(reinterpret_cast<unsigned long long*>(S.respQ + k), (unsigned long long)(long long)s_resp[k]);
-    // last CTA: integer sums -> statistics tail
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) s_last = atomicAdd(S.ticket, 1ULL) == (unsigned long long)gridDim.x - 1;
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
-    for (int k = tid; k < K; k += 128) {
-        const long long rq = *reinterpret_cast<volatile long long*>(S.respQ + k);
-        stats_tail[k] = (double)rq / (double)EM_QMAX * (double)em_col_scale(S.colmax[k]);
+        if (s_resp[k]) atomicAdd(reinterpret_cast<unsigned long long*>(S.respQ + (size_t)slot * K + k), (unsigned long long)(long long)s_resp[k]);
+}
+
+// integer sums -> the float64 tail of the statistics vector (one CTA)
+__global__ void em_tail_kernel(EmSmall S, int K, double* __restrict__ stats_tail, int write_ll, const int* done) {
+    if (done && *done) return;
+    for (int k = threadIdx.x; k < K; k += blockDim.x) {
+        long long rq = 0;
+        for (int sl = 0; sl < EM_SLOTS; ++sl) rq += S.respQ[(size_t)sl * K + k];
+        stats_tail[k] = (double)rq / (double)EM_QMAX * S.sk[k];
     }
-    if (tid == 0 && write_ll) stats_tail[K] = (double)*reinterpret_cast<volatile long long*>(S.llQ) / EM_LL_SCALE;
+    if (threadIdx.x == 0 && write_ll) {
+        long long ll = 0;
+        for (int sl = 0; sl < EM_SLOTS; ++sl) ll += S.llQ[sl];
+        stats_tail[K] = (double)ll / EM_LL_SCALE;
+    }
 }
 
 // int32 digit-plane accumulators of the M-step -> float64 numerators; clears the accumulators
@@ -1010,14 +1019,15 @@ static int em_prepare(const EmShape& s, uint8_t* ws, const float* logT, const fl
 
 // posteriors (device, [N][K]) -> digit planes + responsibility sums (+ log-likelihood) in the statistics tail
 static int em_planes(const EmShape& s, uint8_t* ws, const float* aff, double* stats, int write_ll, const int* done, cudaStream_t st) {
-    const size_t psm = ((s.tile_bytes + (size_t)s.K * 4 + 15) & ~(size_t)15) + (s.K <= 32 ? (size_t)128 * (s.K + 1) * 4 : 0);
+    const size_t psm = ((s.tile_bytes + (size_t)s.K * 8 + 15) & ~(size_t)15) + (s.K <= 32 ? (size_t)128 * (s.K + 1) * 4 : 0);
     static size_t psm_set = 0;
     if (psm > psm_set) {
         TSR_CUDA(cudaFuncSetAttribute(em_aff_planes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm));
         psm_set = psm;
     }
-    em_aff_planes_kernel<<<(unsigned)(s.Npad / 128), 128, psm, st>>>(aff, s.N, s.Npad, s.K, s.KT, s.Mtiles, s.mrp, ws + s.off_ablob,
-                                                                     em_small(ws, s), stats + (size_t)s.K * s.D, write_ll, done);
+    const EmSmall sm = em_small(ws, s);
+    em_aff_planes_kernel<<<(unsigned)(s.Npad / 128), 128, psm, st>>>(aff, s.N, s.Npad, s.K, s.KT, s.Mtiles, s.mrp, ws + s.off_ablob, sm, done);
+    em_tail_kernel<<<1, 256, 0, st>>>(sm, s.K, stats + (size_t)s.K * s.D, write_ll, done);
     return check_launch("em_aff_planes_kernel");
 }
 
@@ -1122,7 +1132,7 @@ int tsr_em_mstep(const uint32_t* Xbits, const uint32_t* XTbits_or_null, long lon
         long long blocks = ((long long)K * D + 127) / 128;
         const long long cap = (long long)sm_count() * 32;
         if (blocks > cap) blocks = cap;
-        em_mstep_simt_kernel<<<(unsigned)blocks, 128, 0, st>>>(Xbits, N, D, rowwords, K, aff, sm.colmax, stats, done);
+        em_mstep_simt_kernel<<<(unsigned)blocks, 128, 0, st>>>(Xbits, N, D, rowwords, K, aff, sm.sk, stats, done);
         return check_launch("tsr_em_mstep(simt)");
     }
     TSR_REQUIRE(XTbits_or_null, "tsr_em_mstep: the tensor path needs the transposed bits (tsr_transpose_bits)");

@@ -27,7 +27,7 @@ struct SpreadTaps {
 // dt and every tap of that row is a funnel shift of them; otherwise each tap fetches an unaligned
 // 4-byte window = two aligned LDS.32 + one funnel shift.
 __global__ void __launch_bounds__(256) spread_edges_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out,
-                                                           int T, int F, int TT, int block_len, SpreadTaps taps) {
+                                                           int T, int F, int TT, int block_len, int tail_lo, SpreadTaps taps) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const int b = blockIdx.y;
     const int t0 = blockIdx.x * TT;
@@ -69,6 +69,7 @@ __global__ void __launch_bounds__(256) spread_edges_kernel(const uint8_t* __rest
         if (block_len > 0) {
             blk_lo = (t / block_len) * block_len;
             blk_hi = min(T, blk_lo + block_len);
+            if (tail_lo >= 0 && blk_lo + block_len > T) blk_lo = tail_lo;   // ragged last block: window of the final block_len frames
         }
         uint32_t acc = 0;
         if (near) {
@@ -123,7 +124,7 @@ struct SpreadLineMasks { uint32_t h, v, d, a; };   // orientation masks x 0x0101
 
 template <int R>
 __global__ void __launch_bounds__(128) spread_edges_line_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out,
-                                                                int T, int wpr, int TT, int RL, int block_len,
+                                                                int T, int wpr, int TT, int RL, int block_len, int tail_lo,
                                                                 SpreadLineMasks mk) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint32_t* sw = reinterpret_cast<uint32_t*>(smem);
@@ -147,7 +148,10 @@ __global__ void __launch_bounds__(128) spread_edges_line_kernel(const uint32_t* 
         if (ta >= T) continue;
         const int rb = min(min(ra + RL, TT), T - t0);
         int lo = 0, hi = T;                           // block of the run in absolute frames
-        if (block_len > 0) { lo = (ta / block_len) * block_len; hi = min(T, lo + block_len); }
+        if (block_len > 0) {
+            lo = (ta / block_len) * block_len; hi = min(T, lo + block_len);
+            if (tail_lo >= 0 && lo + block_len > T) lo = tail_lo;            // ragged last block: window of the final block_len frames
+        }
         const uint32_t* col = sw + R * pitch + 1 + w; // tile row 0, word w
         uint32_t wl[W], wm[W], wh[W];
         auto load = [&](int slot, int r) {            // tile-relative source row r (may be a halo row)
@@ -414,7 +418,7 @@ using namespace tsr;
 extern "C" {
 
 int tsr_spread_edges(const uint8_t* bits_in, uint8_t* bits_out, int B, int T, int F, int radius, int mode,
-                     const int8_t* host_dirs, int block_len, void* stream) {
+                     const int8_t* host_dirs, int block_len, int tail_window, void* stream) {
     if (B == 0) return TSR_OK;
     TSR_REQUIRE(bits_in && bits_out, "tsr_spread_edges: null pointer");
     TSR_REQUIRE(bits_in != bits_out, "tsr_spread_edges: in-place operation is not supported");
@@ -422,6 +426,9 @@ int tsr_spread_edges(const uint8_t* bits_in, uint8_t* bits_out, int B, int T, in
     TSR_REQUIRE(mode == 0 || mode == 1, "tsr_spread_edges: mode must be 0 (line) or 1 (box)");
     TSR_REQUIRE(mode == 1 || host_dirs, "tsr_spread_edges: line mode needs host_dirs[8][2]");
     if ((long long)B * T * F == 0) return TSR_OK;
+    // tail_window: the frames past the last whole block see neighbours down to frame T - block_len (the reference
+    // spreads the window of the final block_len frames and keeps its last T % block_len columns)
+    const int tail_lo = (tail_window && block_len > 0 && T % block_len) ? (T > block_len ? T - block_len : 0) : -1;
     SpreadTaps taps;
     taps.n = 0;
     taps.max_dt = taps.max_df = 0;
@@ -489,9 +496,9 @@ int tsr_spread_edges(const uint8_t* bits_in, uint8_t* bits_out, int B, int T, in
                 const uint32_t* in32 = reinterpret_cast<const uint32_t*>(bits_in);
                 uint32_t* out32 = reinterpret_cast<uint32_t*>(bits_out);
                 cudaStream_t st = (cudaStream_t)stream;
-                if (radius == 1) spread_edges_line_kernel<1><<<grid, 128, smem, st>>>(in32, out32, T, wpr, TT, RL, block_len, mk);
-                else if (radius == 2) spread_edges_line_kernel<2><<<grid, 128, smem, st>>>(in32, out32, T, wpr, TT, RL, block_len, mk);
-                else spread_edges_line_kernel<3><<<grid, 128, smem, st>>>(in32, out32, T, wpr, TT, RL, block_len, mk);
+                if (radius == 1) spread_edges_line_kernel<1><<<grid, 128, smem, st>>>(in32, out32, T, wpr, TT, RL, block_len, tail_lo, mk);
+                else if (radius == 2) spread_edges_line_kernel<2><<<grid, 128, smem, st>>>(in32, out32, T, wpr, TT, RL, block_len, tail_lo, mk);
+                else spread_edges_line_kernel<3><<<grid, 128, smem, st>>>(in32, out32, T, wpr, TT, RL, block_len, tail_lo, mk);
                 return check_launch("tsr_spread_edges");
             }
         }
@@ -516,7 +523,7 @@ int tsr_spread_edges(const uint8_t* bits_in, uint8_t* bits_out, int B, int T, in
     if (smem > 48 * 1024)
         TSR_CUDA(cudaFuncSetAttribute(spread_edges_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((T + TT - 1) / TT, B);
-    spread_edges_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(bits_in, bits_out, T, F, TT, block_len, taps);
+    spread_edges_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(bits_in, bits_out, T, F, TT, block_len, tail_lo, taps);
     return check_launch("tsr_spread_edges");
 }
 

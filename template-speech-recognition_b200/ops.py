@@ -104,8 +104,10 @@ def unpack_features(featbits, D):
 
 
 # ------------------------------------------------------------------------------ K1a
-def spread_edges(bits, radius, orientations=None, mode="line", block_len=0):
-    """Edge spreading on packed edge bytes (edge_signal_proc.py:1397-1417 / :1623-1632)."""
+def spread_edges(bits, radius, orientations=None, mode="line", block_len=0, tail_window=False):
+    """Edge spreading on packed edge bytes (edge_signal_proc.py:1397-1417 / :1623-1632), inside block_len-frame blocks
+    when block_len > 0.  tail_window: a ragged last block is spread as the tail of the window of the final block_len
+    frames (what _edge_map_threshold_segments does, :1595-1633) instead of as a short block of its own."""
     bits = _dev(bits, torch.uint8, "bits")
     B, T, F = bits.shape
     out = torch.empty_like(bits)
@@ -114,9 +116,11 @@ def spread_edges(bits, radius, orientations=None, mode="line", block_len=0):
         if dirs.shape != (8, 2) or np.any(dirs != np.round(dirs)):
             raise ValueError("orientations must be 8 integer (frequency step, time step) pairs")
         dirs = np.ascontiguousarray(dirs, dtype=np.int8)
-        _lib.call("tsr_spread_edges", _ptr(bits), _ptr(out), B, T, F, int(radius), 0, dirs.ctypes.data, int(block_len), _stream())
+        _lib.call("tsr_spread_edges", _ptr(bits), _ptr(out), B, T, F, int(radius), 0, dirs.ctypes.data, int(block_len),
+                  int(bool(tail_window)), _stream())
     elif mode == "box":
-        _lib.call("tsr_spread_edges", _ptr(bits), _ptr(out), B, T, F, int(radius), 1, 0, int(block_len), _stream())
+        _lib.call("tsr_spread_edges", _ptr(bits), _ptr(out), B, T, F, int(radius), 1, 0, int(block_len), int(bool(tail_window)),
+                  _stream())
     else:
         raise ValueError("mode must be 'line' or 'box'")
     return out

@@ -29,7 +29,10 @@ class ScoringPipeline:
         self.impl_code = ops.IMPL_TENSOR
         self.impl_detect = ops.IMPL_TENSOR
         self.fused_max = True
-        self.fuse_edge_spread = True
+        # K1a inside K2's producers (tsr_code_parts edge_spread_radius = 1) is bit-identical but measured SLOWER than the
+        # two launches (1.01 ms against 0.69 + 0.06 ms at config 3: the four producer warps become the bottleneck of an
+        # MMA-bound kernel), so it is off by default; see DESIGN.md section 3.
+        self.fuse_edge_spread = False
 
     def spread(self, bits):
         """K1a as its own launch (what code() uses when the spreading cannot ride inside K2): per edge_block_len-frame
@@ -37,16 +40,12 @@ class ScoringPipeline:
         1595-1633)."""
         if self.edge_spread_radius <= 0:
             return bits
-        T, bl = bits.shape[1], self.edge_block_len
-        tail = bits[:, max(0, T - bl):].contiguous() if (bl > 0 and T % bl) else None
-        if bl <= 0:
-            return ops.spread_edges(bits, self.edge_spread_radius, self.edge_orientations, "line", 0)
-        return ops.spread_edge_blocks(bits, tail, self.edge_spread_radius, bl, self.edge_orientations, "line")
+        return ops.spread_edges(bits, self.edge_spread_radius, self.edge_orientations, "line", max(self.edge_block_len, 0),
+                                tail_window=True)
 
     def code(self, bits):
-        """K1a + K2 + K1b: packed edges -> (codes, part feature bits).  With the reference's direction table and
-        radius 1 (main_multiprocessing.py:50-52) the edge spreading runs inside K2's producers: one launch less and
-        no second pass over the edge map."""
+        """K1a + K2 + K1b: packed edges -> (codes, part feature bits).  With fuse_edge_spread set (and the reference's
+        direction table, radius 1, main_multiprocessing.py:50-52) the edge spreading runs inside K2's producers."""
         fused = (self.fuse_edge_spread and self.edge_spread_radius == 1 and self.edge_orientations is None
                  and self.impl_code == ops.IMPL_TENSOR)
         if not fused:
