@@ -980,7 +980,7 @@ __global__ void detect_simt_kernel(const uint32_t* __restrict__ bits, const floa
 // the 128 x 32 window of features is staged coalesced (pitch 33: row-per-thread reads are conflict free) next to the
 // DF_TM weight rows (broadcast reads); a thread owns one row and DF_TM independent accumulators: 1 + DF_TM shared loads
 // for 2 * DF_TM arithmetic instructions per feature, no global load in the inner loop.
-#define DF_TM 4
+#define DF_TM 4     // DF_TM * DF_DC must equal the 128 threads of a CTA (one weight per thread and step)
 #define DF_DC 32
 __global__ void __launch_bounds__(128) detect_float_kernel(const float* __restrict__ Fm, const float* __restrict__ LF,
                                                            const float* __restrict__ init, float* __restrict__ scores, long long R,
@@ -995,35 +995,40 @@ __global__ void __launch_bounds__(128) detect_float_kernel(const float* __restri
     float acc[DF_TM];
 #pragma unroll
     for (int j = 0; j < DF_TM; ++j) acc[j] = (init && m0 + j < M) ? init[m0 + j] : 0.f;     // detect_float_max starts at cs[m] (:258)
-    for (int tau = 0; tau < L; ++tau) {
-        for (int d0 = 0; d0 < D; d0 += DF_DC) {
-            const int dc = D - d0 < DF_DC ? D - d0 : DF_DC;
-            __syncthreads();
-            for (int e = tid; e < 128 * DF_DC; e += 128) {
-                const int r = e / DF_DC, c = e - r * DF_DC;
-                const long long row = g0 + r + tau;
-                sx[r * (DF_DC + 1) + c] = (row < R && c < dc) ? Fm[row * D + d0 + c] : 0.f;
-            }
-            if (tid < DF_TM * DF_DC) {
-                const int j = tid / DF_DC, c = tid - j * DF_DC;
-                sw[tid] = (m0 + j < M && c < dc) ? LF[((size_t)(m0 + j) * L + tau) * D + d0 + c] : 0.f;
-            }
-            __syncthreads();
-            const float* xr = sx + tid * (DF_DC + 1);
-            if (dc == DF_DC) {
+    // (tau, chunk) steps in the reference's order; the next step's 128 x 32 window and weight rows are fetched into
+    // registers while the current one is being consumed from shared memory
+    const int nd = (D + DF_DC - 1) / DF_DC;
+    const int nstep = L * nd;
+    float px[DF_DC], pw = 0.f;
+    auto fetch = [&](int step) {
+        const int tau = step / nd, d0 = (step - tau * nd) * DF_DC;
+        const int dc = D - d0 < DF_DC ? D - d0 : DF_DC;
 #pragma unroll
-                for (int c = 0; c < DF_DC; ++c) {
-                    const float x = xr[c];
+        for (int i = 0; i < DF_DC; ++i) {                   // element e = tid + 128 i of the window: row e / 32, column e % 32
+            const int e = tid + 128 * i, r = e >> 5, c = e & 31;
+            const long long row = g0 + r + tau;
+            px[i] = (row < R && c < dc) ? __ldg(Fm + row * D + d0 + c) : 0.f;
+        }
+        const int j = tid >> 5, c = tid & 31;               // 128 threads = DF_TM x 32 weights
+        pw = (m0 + j < M && c < dc) ? __ldg(LF + ((size_t)(m0 + j) * L + tau) * D + d0 + c) : 0.f;
+    };
+    fetch(0);
+    for (int step = 0; step < nstep; ++step) {
+        __syncthreads();
 #pragma unroll
-                    for (int j = 0; j < DF_TM; ++j) acc[j] = __fadd_rn(acc[j], __fmul_rn(sw[j * DF_DC + c], x));
-                }
-            } else {
-                for (int c = 0; c < dc; ++c) {
-                    const float x = xr[c];
+        for (int i = 0; i < DF_DC; ++i) {
+            const int e = tid + 128 * i;
+            sx[(e >> 5) * (DF_DC + 1) + (e & 31)] = px[i];
+        }
+        sw[tid] = pw;
+        __syncthreads();
+        if (step + 1 < nstep) fetch(step + 1);
+        const float* xr = sx + tid * (DF_DC + 1);
 #pragma unroll
-                    for (int j = 0; j < DF_TM; ++j) acc[j] = __fadd_rn(acc[j], __fmul_rn(sw[j * DF_DC + c], x));
-                }
-            }
+        for (int c = 0; c < DF_DC; ++c) {                  // columns past the end of the row hold zeros: x * w = +-0, acc unchanged
+            const float x = xr[c];
+#pragma unroll
+            for (int j = 0; j < DF_TM; ++j) acc[j] = __fadd_rn(acc[j], __fmul_rn(sw[j * DF_DC + c], x));
         }
     }
     if (g < R) {

@@ -46,7 +46,7 @@ namespace tsr {
 #define BG_TBUF_WORDS (32 * 33)      // per-epilogue-warp transpose buffer
 
 struct EmShape {
-    int K, D, KT, Mtiles, mrows, mrp;   // mrows = 3*KT useful rows of an M tile, mrp = mrows rounded up to 8
+    int K, D, KT, Mtiles, mrows, mrp;   // mrows = 3*KT useful rows of an M tile, mrp = mrows rounded up to 16
     long long N, Npad;                  // Npad = N rounded up to 256
     int rwX, nchunkE, Dpad;             // words per data row, 128-feature chunks per row, D rounded up to 256
     long long nchunkM;                  // 128-row chunks of the M-step contraction
@@ -61,7 +61,7 @@ static EmShape em_shape(long long N, int D, int K) {
     s.KT = K < EM_KT_MAX ? K : EM_KT_MAX;
     s.Mtiles = (K + s.KT - 1) / s.KT;
     s.mrows = 3 * s.KT;
-    s.mrp = (s.mrows + 7) & ~7;
+    s.mrp = (s.mrows + 15) & ~15;     // also the UMMA N of the TS kernel (M = 128 needs N % 16 == 0)
     s.Npad = (N + 255) / 256 * 256;
     s.rwX = tsr_rowwords(D);
     s.nchunkE = (s.rwX + 3) / 4;
@@ -373,6 +373,231 @@ __global__ void __launch_bounds__(BG_THREADS, 1) bitgemm_kernel(const __grid_con
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// bitgemm_ts_kernel: the same product with the operand roles swapped once more and the bit rows as the A operand
+// *in tensor memory*:   C[m][r] += sum_k bit[r][k] * Wq[m][k]   as   D[128 bit rows][N = mrp planes] += A(TMEM) * B(smem).
+// The SS kernel above is bound by the L1/shared-memory data pipe: every expanded byte is written to shared memory by
+// the expanders and read back by the tensor core (ncu: lsu 42 % + tensor-operand 39 % of the pipe's peak, tensor pipe
+// 47 %).  Here an expander thread owns TMEM lane = bit row, expands its words in registers and stores them with
+// tcgen05.st (TMEM write port, 256 B/clk, no shared memory); the tensor core reads A from TMEM and only the small
+// int8 weight tile (N rows x 32 B per MMA) from shared memory.  One MMA is M = 128 x N = mrp x K = 32, i.e. short
+// (N / 2 cycles), so with mrp <= 64 two issuer warps take alternate chunks into their own accumulators.
+// Used when all components fit one M tile (K <= 42) and the rows can be fetched by TMA; otherwise the SS kernel runs.
+//   TMEM columns: [0, 2 * NIS * mrp) accumulators (segment parity, issuer); [256, 512) ring of 8 A chunks x 32 columns.
+#define TS_THREADS 480               // warp 0 loader, 1-8 expanders, 9-12 epilogue, 13-14 MMA issuers
+#define TS_NA 8                      // A chunks in flight in TMEM
+#define TS_NRAW 4
+#define TS_RAW_BYTES 2048            // 128 rows x 16 B
+#define TS_NW 4
+
+struct TsWalk {     // as BgWalk with 128-row tiles and one M tile
+    long long pos, end, tile;
+    int c, nchunk;
+    __device__ TsWalk(int Rtiles, int nchunk_) {
+        const long long total = (long long)Rtiles * nchunk_;
+        pos = total * blockIdx.x / gridDim.x;
+        end = total * (blockIdx.x + 1) / gridDim.x;
+        nchunk = nchunk_;
+        tile = pos / nchunk;
+        c = (int)(pos - tile * nchunk);
+    }
+    __device__ bool next_seg(int& rt, int& c0, int& n) {
+        if (pos >= end) return false;
+        rt = (int)tile; c0 = c;
+        long long len = nchunk - c;
+        if (len > end - pos) len = end - pos;
+        n = (int)len;
+        pos += len; c += n;
+        if (c == nchunk) { c = 0; ++tile; }
+        return true;
+    }
+};
+
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]),
+                 "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void umma_i8_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+template <int NIS>
+__global__ void __launch_bounds__(TS_THREADS, 1) bitgemm_ts_kernel(const __grid_constant__ BgArgs A) {
+    if (A.done && *A.done) return;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const uint32_t tile_bytes = 8u * (uint32_t)A.mrp * 16u;
+    uint8_t* wring = smem;
+    uint8_t* raw = smem + TS_NW * tile_bytes;
+    uint64_t* wfull = reinterpret_cast<uint64_t*>(raw + TS_NRAW * TS_RAW_BYTES);
+    uint64_t* wempty = wfull + TS_NW;
+    uint64_t* rfull = wempty + TS_NW;
+    uint64_t* rempty = rfull + TS_NRAW;
+    uint64_t* afull = rempty + TS_NRAW;          // [TS_NA]
+    uint64_t* aempty = afull + TS_NA;            // [TS_NA]
+    uint64_t* tfull = aempty + TS_NA;            // [2]
+    uint64_t* tempty = tfull + 2;                // [2]
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty + 2);
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+    const int N = A.mrp;
+    const int Rtiles = (int)(A.Rpad / 128);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < TS_NW; ++s) { mbar_init(&wfull[s], 1); mbar_init(&wempty[s], 1); }
+        for (int s = 0; s < TS_NRAW; ++s) { mbar_init(&rfull[s], 1); mbar_init(&rempty[s], 256); }
+        for (int s = 0; s < TS_NA; ++s) { mbar_init(&afull[s], 256); mbar_init(&aempty[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], NIS); mbar_init(&tempty[s], 128); }
+        mbar_fence_init();
+    }
+    if (warp == 13) tmem_alloc<512>(tmem_ptr);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+    const uint32_t a_col0 = 256;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            TsWalk w(Rtiles, A.nchunk);
+            int rt, c0, n, stage = 0;
+            uint32_t ph = 0, ic = 0;
+            while (w.next_seg(rt, c0, n)) {
+                const uint8_t* src = A.wblob + (size_t)c0 * tile_bytes;
+                for (int i = 0; i < n; ++i, ++ic) {
+                    const uint32_t rs = ic % TS_NRAW;
+                    mbar_wait_relaxed(&rempty[rs], ((ic / TS_NRAW) & 1) ^ 1);
+                    mbar_arrive_expect_tx(&rfull[rs], TS_RAW_BYTES);
+                    tma_load_2d(raw + rs * TS_RAW_BYTES, &A.tmap, 16 * (c0 + i), rt * 128, &rfull[rs]);
+                    mbar_wait_relaxed(&wempty[stage], ph ^ 1);
+                    mbar_arrive_expect_tx(&wfull[stage], tile_bytes);
+                    bulk_g2s(wring + stage * tile_bytes, src + (size_t)i * tile_bytes, tile_bytes, &wfull[stage]);
+                    if (++stage == TS_NW) { stage = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp >= 1 && warp <= 8) {
+        // ================================== bit expanders ==================================
+        // TMEM lane = bit row: a warp may only touch lanes 32 * (warp % 4) .. +31, so warps {1..4} and {5..8} cover the
+        // four quadrants once each; the first set expands words 0, 1 of a chunk (columns 0..15), the second words 2, 3.
+        const int quad = warp & 3, half = (warp - 1) >> 2;
+        const int row = quad * 32 + lane;
+        TsWalk w(Rtiles, A.nchunk);
+        int rt, c0, n;
+        uint32_t ic = 0;
+        while (w.next_seg(rt, c0, n)) {
+            for (int i = 0; i < n; ++i, ++ic) {
+                const uint32_t rs = ic % TS_NRAW, slot = ic % TS_NA;
+                mbar_wait_relaxed(&rfull[rs], (ic / TS_NRAW) & 1);
+                const uint2 x = *reinterpret_cast<const uint2*>(raw + rs * TS_RAW_BYTES + row * 16 + half * 8);
+                mbar_arrive(&rempty[rs]);
+                mbar_wait_relaxed(&aempty[slot], ((ic / TS_NA) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + a_col0 + slot * 32 + half * 16 + ((uint32_t)(quad * 32) << 16);
+                uint32_t v[8];
+#pragma unroll
+                for (int s8 = 0; s8 < 8; ++s8) v[s8] = (x.x >> s8) & 0x01010101u;     // K index 4 s + jj  <->  bit 8 jj + s of the word
+                tmem_st8(taddr, v);
+#pragma unroll
+                for (int s8 = 0; s8 < 8; ++s8) v[s8] = (x.y >> s8) & 0x01010101u;
+                tmem_st8(taddr + 8, v);
+                tmem_st_wait();
+                tc_fence_before();
+                mbar_arrive(&afull[slot]);
+            }
+        }
+    } else if (warp == 13 || (NIS == 2 && warp == 14)) {
+        // ==================================== MMA issuers ====================================
+        // issuer `iss` takes the chunks ic % NIS == iss into accumulator (segment parity, iss)
+        const int iss = warp - 13;
+        const uint32_t idesc = (2u << 4) | (0u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);   // S32 += U8 * S8
+        const uint32_t desc_hi = (uint32_t)(128 >> 4) | (1u << 14);                                 // SBO = 128 B, version 1
+        const uint64_t b_hi = ((uint64_t)desc_hi << 32) | ((uint64_t)((uint32_t)(N * 16) >> 4) << 16);   // LBO = k-group stride of a weight tile
+        const uint32_t kstep_b = (uint32_t)(2 * N * 16) >> 4;
+        TsWalk w(Rtiles, A.nchunk);
+        int rt, c0, n;
+        uint32_t ic = 0, seg = 0;
+        while (w.next_seg(rt, c0, n)) {
+            const uint32_t sp = seg & 1;
+            mbar_wait(&tempty[sp], ((seg >> 1) & 1) ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + (sp * NIS + iss) * N;
+            bool first = true;
+            for (int i = 0; i < n; ++i, ++ic) {
+                if ((int)(ic % NIS) != iss) continue;
+                const uint32_t slot = ic % TS_NA, stage = ic % TS_NW;
+                mbar_wait(&afull[slot], (ic / TS_NA) & 1);
+                mbar_wait(&wfull[stage], (ic / TS_NW) & 1);
+                tc_fence_after();
+                const uint32_t bbase = smem_u32(wring + stage * tile_bytes) >> 4;
+                const uint32_t abase = tmem_base + a_col0 + slot * 32;
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    umma_i8_ts(d_tmem, abase + 8 * j, b_hi | (uint64_t)(bbase + j * kstep_b), idesc, (first && j == 0) ? 0u : 1u);
+                first = false;
+                umma_commit_elect(&aempty[slot]);
+                umma_commit_elect(&wempty[stage]);
+            }
+            umma_commit_elect(&tfull[sp]);        // (arrives even if this issuer had no chunk in the segment)
+            ++seg;
+        }
+    } else if (warp >= 9 && warp <= 12) {
+        // ===================================== epilogue =====================================
+        // lane = bit row r, column = plane row m: for a fixed m the warp's 32 lanes are 32 consecutive r of acc[m][.],
+        // one coalesced 128-byte reduction
+        const int quad = warp & 3;
+        TsWalk w(Rtiles, A.nchunk);
+        int rt, c0, n;
+        uint32_t seg = 0, ic = 0;
+        while (w.next_seg(rt, c0, n)) {
+            const uint32_t sp = seg & 1;
+            // which issuers contributed to this segment
+            bool used[2] = {false, false};
+            if (NIS == 1) used[0] = true;
+            else {
+                used[ic % 2] = true;
+                if (n > 1) used[(ic + 1) % 2] = true;
+            }
+            ic += n;
+            mbar_wait_relaxed(&tfull[sp], (seg >> 1) & 1);
+            tc_fence_after();
+            int* out = A.acc + (size_t)rt * 128 + quad * 32 + lane;
+            for (int m0 = 0; m0 < N; m0 += 16) {
+                uint32_t v[16], u[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) { v[i] = 0u; u[i] = 0u; }
+                const uint32_t lanebits = (uint32_t)(quad * 32) << 16;
+                if (used[0]) tmem_ld16(tmem_base + (sp * NIS + 0) * N + m0 + lanebits, v);
+                if (NIS == 2 && used[1]) tmem_ld16(tmem_base + (sp * NIS + 1) * N + m0 + lanebits, u);
+                tmem_ld_wait();
+                if (m0 + 16 >= N) {                         // accumulators read: hand them back to the issuers
+                    tc_fence_before();
+                    mbar_arrive(&tempty[sp]);
+                }
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const int val = (int)v[i] + (int)u[i];
+                    if (m0 + i < A.mrows && val != 0) atomicAdd(out + (size_t)(m0 + i) * A.Rpad, val);
+                }
+            }
+            ++seg;
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 13) {
+        tc_fence_after();
+        tmem_dealloc<512>(tmem_base);
+    }
+}
+
 static size_t bitgemm_smem(int mrp, bool raw_tma) {
     return (size_t)BG_NW * 8 * mrp * 16 + (size_t)BG_NSTRIP * BG_STRIP_BYTES + (raw_tma ? BG_NRAW * BG_RAW_BYTES : 0) +
            4 * BG_TBUF_WORDS * 4 + 512;
@@ -411,6 +636,31 @@ static int launch_bitgemm(const uint32_t* bits, long long R, int rw, const uint8
         raw_tma = enc && enc(&A.tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<uint32_t*>(bits), gdim, gstride, box, estr,
                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    }
+    if (raw_tma && s.Mtiles == 1 && Rpad % 128 == 0 && getenv("TSR_DEBUG_BITGEMM_SS") == nullptr) {
+        // bit rows as the A operand in tensor memory (see bitgemm_ts_kernel); the box of the row tensor is 128 rows
+        tsr_encode_tiled_fn enc = encode_tiled_fn();
+        const cuuint64_t gdim[2] = {(cuuint64_t)rw * 4, (cuuint64_t)R};
+        const cuuint64_t gstride[1] = {(cuuint64_t)rw * 4};
+        const cuuint32_t box[2] = {16, 128}, estr[2] = {1, 1};
+        if (enc(&A.tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<uint32_t*>(bits), gdim, gstride, box, estr,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS) {
+            const size_t tsmem = (size_t)TS_NW * 8 * s.mrp * 16 + TS_NRAW * TS_RAW_BYTES + 512;
+            const long long ttotal = (Rpad / 128) * nchunk;
+            const int nsm2 = sm_count();
+            const int tgrid = (int)(ttotal < nsm2 ? ttotal : nsm2);
+            if (tgrid < 1) return TSR_OK;
+            static bool ts_attr = false;
+            if (!ts_attr) {
+                TSR_CUDA(cudaFuncSetAttribute(bitgemm_ts_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+                TSR_CUDA(cudaFuncSetAttribute(bitgemm_ts_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+                ts_attr = true;
+            }
+            if (s.mrp <= 64) bitgemm_ts_kernel<2><<<tgrid, TS_THREADS, tsmem, st>>>(A);
+            else bitgemm_ts_kernel<1><<<tgrid, TS_THREADS - 32, tsmem, st>>>(A);
+            return check_launch("bitgemm_ts_kernel");
+        }
     }
     const size_t smem = bitgemm_smem(s.mrp, raw_tma);
     static bool attr_set = false;

@@ -58,6 +58,32 @@ def test_spread_edges_bit_exact(cuda, oracle, radius, block_len, box):
         np.testing.assert_array_equal(got[b], _oracle_spread(oracle, X[b], radius, ORI, block_len, box))
 
 
+@pytest.mark.parametrize("T,F,radius,block_len,box", [(95, 40, 1, 40, False), (300, 40, 1, 40, False), (95, 40, 3, 40, False),
+                                                      (64, 37, 2, 25, False), (33, 40, 1, 40, False), (95, 40, 2, 40, True),
+                                                      (120, 40, 1, 40, False), (51, 9, 3, 10, True)])
+def test_spread_edges_ragged_tail_window(cuda, oracle, T, F, radius, block_len, box):
+    """tail_window: the frames past the last whole block are the tail of the spread window of the final block_len frames
+    (_edge_map_threshold_segments, edge_signal_proc.py:1595-1633) -- one launch, equal to the two-call composition
+    ops.spread_edge_blocks and to the NumPy restatement."""
+    from tsr_b200 import ops, synth
+    X = np.stack([synth.utterance_edges(40 + u, T=T, F=F) for u in range(3)])
+    bits = ops.pack_edges(torch.from_numpy(X).cuda())
+    mode = "box" if box else "line"
+    out = ops.spread_edges(bits, radius, ORI, mode, block_len, tail_window=True)
+    tail = bits[:, max(0, T - block_len):].contiguous() if T % block_len else None
+    two = ops.spread_edge_blocks(bits, tail, radius, block_len, ORI, mode)
+    assert torch.equal(out, two)
+    got = ops.unpack_edges(out, 8).cpu().numpy()
+    for b in range(3):
+        want = _oracle_spread(oracle, X[b], radius, ORI, block_len, box)
+        last = T % block_len
+        if last:
+            want[-last:] = _oracle_spread(oracle, X[b, -block_len:], radius, ORI, 0, box)[-last:]
+            if not box:
+                np.testing.assert_array_equal(want, oracle.spread_edge_blocks(X[b], radius, block_len, ORI))
+        np.testing.assert_array_equal(got[b], want)
+
+
 def test_spread_edges_odd_shapes_and_other_orientations(cuda, oracle):
     from tsr_b200 import ops
     rs = np.random.RandomState(1)
