@@ -104,6 +104,7 @@ struct BgArgs {
     int* acc;
     long long R, Rpad;
     int rw, nchunk, Mtiles, mrp, mrows, Rtiles;
+    int nw;                         // TS kernel: weight tiles in flight
     const int* done;
 };
 
@@ -384,11 +385,11 @@ __global__ void __launch_bounds__(BG_THREADS, 1) bitgemm_kernel(const __grid_con
 // (N / 2 cycles), so with mrp <= 64 two issuer warps take alternate chunks into their own accumulators.
 // Used when all components fit one M tile (K <= 42) and the rows can be fetched by TMA; otherwise the SS kernel runs.
 //   TMEM columns: [0, 2 * NIS * mrp) accumulators (segment parity, issuer); [256, 512) ring of 8 A chunks x 32 columns.
-#define TS_THREADS 480               // warp 0 loader, 1-8 expanders, 9-12 epilogue, 13-14 MMA issuers
+#define TS_THREADS 512               // warp 0 raw-tile loader, 1-8 expanders, 9-12 epilogue, 13-14 MMA issuers, 15 weight-tile loader
 #define TS_NA 8                      // A chunks in flight in TMEM
-#define TS_NRAW 4
+#define TS_NRAW 16                   // raw bit tiles in flight: a chunk lasts ~200 cycles, a TMA round trip ~2000-3000
 #define TS_RAW_BYTES 2048            // 128 rows x 16 B
-#define TS_NW 4
+#define TS_NW_MAX 16                 // weight tiles in flight (as many as fit 144 KB)
 
 struct TsWalk {     // as BgWalk with 128-row tiles and one M tile
     long long pos, end, tile;
@@ -434,11 +435,12 @@ __global__ void __launch_bounds__(TS_THREADS, 1) bitgemm_ts_kernel(const __grid_
     if (A.done && *A.done) return;
     extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t tile_bytes = 8u * (uint32_t)A.mrp * 16u;
+    const uint32_t TS_NW = (uint32_t)A.nw;
     uint8_t* wring = smem;
     uint8_t* raw = smem + TS_NW * tile_bytes;
     uint64_t* wfull = reinterpret_cast<uint64_t*>(raw + TS_NRAW * TS_RAW_BYTES);
-    uint64_t* wempty = wfull + TS_NW;
-    uint64_t* rfull = wempty + TS_NW;
+    uint64_t* wempty = wfull + TS_NW_MAX;
+    uint64_t* rfull = wempty + TS_NW_MAX;
     uint64_t* rempty = rfull + TS_NRAW;
     uint64_t* afull = rempty + TS_NRAW;          // [TS_NA]
     uint64_t* aempty = afull + TS_NA;            // [TS_NA]
@@ -450,7 +452,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) bitgemm_ts_kernel(const __grid_
     const int Rtiles = (int)(A.Rpad / 128);
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < TS_NW; ++s) { mbar_init(&wfull[s], 1); mbar_init(&wempty[s], 1); }
+        for (int s = 0; s < TS_NW_MAX; ++s) { mbar_init(&wfull[s], 1); mbar_init(&wempty[s], 1); }
         for (int s = 0; s < TS_NRAW; ++s) { mbar_init(&rfull[s], 1); mbar_init(&rempty[s], 256); }
         for (int s = 0; s < TS_NA; ++s) { mbar_init(&afull[s], 256); mbar_init(&aempty[s], 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], NIS); mbar_init(&tempty[s], 128); }
@@ -464,21 +466,33 @@ __global__ void __launch_bounds__(TS_THREADS, 1) bitgemm_ts_kernel(const __grid_
     const uint32_t a_col0 = 256;
 
     if (warp == 0) {
+        // raw bit tiles: one TMA tensor load (128 rows x 16 B) per chunk
         if (lane == 0) {
             TsWalk w(Rtiles, A.nchunk);
-            int rt, c0, n, stage = 0;
-            uint32_t ph = 0, ic = 0;
+            int rt, c0, n;
+            uint32_t ic = 0;
             while (w.next_seg(rt, c0, n)) {
-                const uint8_t* src = A.wblob + (size_t)c0 * tile_bytes;
                 for (int i = 0; i < n; ++i, ++ic) {
                     const uint32_t rs = ic % TS_NRAW;
                     mbar_wait_relaxed(&rempty[rs], ((ic / TS_NRAW) & 1) ^ 1);
                     mbar_arrive_expect_tx(&rfull[rs], TS_RAW_BYTES);
                     tma_load_2d(raw + rs * TS_RAW_BYTES, &A.tmap, 16 * (c0 + i), rt * 128, &rfull[rs]);
-                    mbar_wait_relaxed(&wempty[stage], ph ^ 1);
+                }
+            }
+        }
+    } else if (warp == 15) {
+        // weight tiles: one bulk copy per chunk
+        if (lane == 0) {
+            TsWalk w(Rtiles, A.nchunk);
+            int rt, c0, n;
+            uint32_t ic = 0;
+            while (w.next_seg(rt, c0, n)) {
+                const uint8_t* src = A.wblob + (size_t)c0 * tile_bytes;
+                for (int i = 0; i < n; ++i, ++ic) {
+                    const uint32_t stage = ic % TS_NW;
+                    mbar_wait_relaxed(&wempty[stage], ((ic / TS_NW) & 1) ^ 1);
                     mbar_arrive_expect_tx(&wfull[stage], tile_bytes);
                     bulk_g2s(wring + stage * tile_bytes, src + (size_t)i * tile_bytes, tile_bytes, &wfull[stage]);
-                    if (++stage == TS_NW) { stage = 0; ph ^= 1; }
                 }
             }
         }
@@ -646,19 +660,22 @@ static int launch_bitgemm(const uint32_t* bits, long long R, int rw, const uint8
         if (enc(&A.tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<uint32_t*>(bits), gdim, gstride, box, estr,
                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS) {
-            const size_t tsmem = (size_t)TS_NW * 8 * s.mrp * 16 + TS_NRAW * TS_RAW_BYTES + 512;
+            size_t nw = (size_t)(144 * 1024) / s.tile_bytes;
+            if (nw > TS_NW_MAX) nw = TS_NW_MAX;
+            A.nw = (int)nw;
+            const size_t tsmem = nw * s.tile_bytes + TS_NRAW * TS_RAW_BYTES + 1024;
             const long long ttotal = (Rpad / 128) * nchunk;
             const int nsm2 = sm_count();
             const int tgrid = (int)(ttotal < nsm2 ? ttotal : nsm2);
             if (tgrid < 1) return TSR_OK;
             static bool ts_attr = false;
             if (!ts_attr) {
-                TSR_CUDA(cudaFuncSetAttribute(bitgemm_ts_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-                TSR_CUDA(cudaFuncSetAttribute(bitgemm_ts_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+                TSR_CUDA(cudaFuncSetAttribute(bitgemm_ts_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+                TSR_CUDA(cudaFuncSetAttribute(bitgemm_ts_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
                 ts_attr = true;
             }
             if (s.mrp <= 64) bitgemm_ts_kernel<2><<<tgrid, TS_THREADS, tsmem, st>>>(A);
-            else bitgemm_ts_kernel<1><<<tgrid, TS_THREADS - 32, tsmem, st>>>(A);
+            else bitgemm_ts_kernel<1><<<tgrid, TS_THREADS, tsmem, st>>>(A);
             return check_launch("bitgemm_ts_kernel");
         }
     }
@@ -1129,18 +1146,19 @@ __global__ void __launch_bounds__(128) em_aff_planes_kernel(const float* __restr
         if (s_resp[k]) atomicAdd(reinterpret_cast<unsigned long long*>(S.respQ + (size_t)slot * K + k), (unsigned long long)(long long)s_resp[k]);
 }
 
-// integer sums -> the float64 tail of the statistics vector (one CTA)
+// integer sums -> the float64 tail of the statistics vector (one CTA; warp per component, lanes = the EM_SLOTS replicas)
 __global__ void em_tail_kernel(EmSmall S, int K, double* __restrict__ stats_tail, int write_ll, const int* done) {
     if (done && *done) return;
-    for (int k = threadIdx.x; k < K; k += blockDim.x) {
-        long long rq = 0;
-        for (int sl = 0; sl < EM_SLOTS; ++sl) rq += S.respQ[(size_t)sl * K + k];
-        stats_tail[k] = (double)rq / (double)EM_QMAX * S.sk[k];
+    const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int k = wp; k < K; k += nw) {
+        long long rq = S.respQ[(size_t)lane * K + k];
+        for (int off = 16; off > 0; off >>= 1) rq += __shfl_xor_sync(0xffffffffu, rq, off);
+        if (lane == 0) stats_tail[k] = (double)rq / (double)EM_QMAX * S.sk[k];
     }
-    if (threadIdx.x == 0 && write_ll) {
-        long long ll = 0;
-        for (int sl = 0; sl < EM_SLOTS; ++sl) ll += S.llQ[sl];
-        stats_tail[K] = (double)ll / EM_LL_SCALE;
+    if (wp == 0 && write_ll) {
+        long long ll = S.llQ[lane];
+        for (int off = 16; off > 0; off >>= 1) ll += __shfl_xor_sync(0xffffffffu, ll, off);
+        if (lane == 0) stats_tail[K] = (double)ll / EM_LL_SCALE;
     }
 }
 

@@ -117,6 +117,10 @@ class ScoringPipeline:
         staging = cache["staging"]
         consumed = [None] * NSTAGE               # CUDA event: the H2D copy out of staging[j] has finished
 
+        import time as _time
+        stats = self.__dict__.setdefault("stream_stats", {})
+        stats.update(pack_s=0.0, pack_calls=0, feeder_wait_s=0.0, consumer_wait_s=0.0)
+
         def feeder():
             try:
                 for i, xb in enumerate(host_batches):
@@ -138,11 +142,16 @@ class ScoringPipeline:
                     if staging[j] is None or tuple(staging[j].shape) != shape:
                         staging[j] = torch.empty(shape, dtype=torch.uint8).pin_memory()
                     elif consumed[j] is not None:
+                        t0 = _time.perf_counter()
                         consumed[j].synchronize()
+                        stats["feeder_wait_s"] += _time.perf_counter() - t0
                     src = xb.contiguous() if is_t else xb
                     if len(xb.shape) == 4 and pack == "host":
                         sp = src.data_ptr() if is_t else src.ctypes.data
+                        t0 = _time.perf_counter()
                         _lib.call("tsr_host_pack_edges", sp, staging[j].data_ptr(), int(np.prod(shape)), 8, nthreads)
+                        stats["pack_s"] += _time.perf_counter() - t0
+                        stats["pack_calls"] += 1
                     elif is_t:
                         staging[j].copy_(src)
                     else:
@@ -162,7 +171,9 @@ class ScoringPipeline:
         i = 0
         try:
             while True:
+                t0 = _time.perf_counter()
                 item = q.get()
+                stats["consumer_wait_s"] += _time.perf_counter() - t0
                 if item is None:
                     break
                 if isinstance(item, BaseException):
