@@ -366,9 +366,15 @@ def run_native(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    threads = max(1, min(32, (os.cpu_count() or 2) // max(1, min(world, 8)) - 1))
-    e2e_s = e2e_run(X_pinned, pack="host", pack_threads=threads)
-    e2e_stats = dict(getattr(pipe, "stream_stats", {}))
+    # host packing competes with the launching thread for cores: try a few pool sizes, report the best (all listed)
+    cores_here = max(1, (os.cpu_count() or 2) // max(1, min(world, 8)))
+    sweep = {}
+    for threads in sorted({max(1, cores_here // 4), max(1, cores_here // 2), max(1, cores_here - 2)}):
+        sweep[threads] = e2e_run(X_pinned, pack="host", pack_threads=threads)
+        if threads == min(sweep, key=sweep.get):
+            e2e_stats = dict(getattr(pipe, "stream_stats", {}))
+    threads = min(sweep, key=sweep.get)
+    e2e_s = sweep[threads]
     e2e_packed_s = e2e_run(P_pinned)
     e2e_devpack_s = e2e_run(X_pinned, pack="device")
     t0 = time.perf_counter()
@@ -421,6 +427,7 @@ def run_native(args):
             "e2e": {"value": frames * e2e_steps / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": int(P_pinned.numel()),
                     "d2h_bytes_per_step": int(B * TO * 4 + B * TO * 2), "host_input_bytes_per_step": int(X_pinned.numel()),
                     "host_pack_threads": threads, "host_pack_gbs": host_pack_gbs, "stream_stats": e2e_stats,
+                    "pack_thread_sweep_frames_per_s": {str(k): frames * e2e_steps / v for k, v in sweep.items()},
                     "api": "pipeline.ScoringPipeline.stream over pinned uint8 (B,300,40,8) host batches (the reference's dtype): host threads "
                            "pack to 1 byte per (t,f) (feeder thread, batch i+1 while batch i runs), double-buffered H2D of the packed "
                            "bytes, full pipeline, results D2H to pinned host; %d steps in one call, fill and drain inside the clock" % e2e_steps},

@@ -385,7 +385,7 @@ __global__ void __launch_bounds__(BG_THREADS, 1) bitgemm_kernel(const __grid_con
 // (N / 2 cycles), so with mrp <= 64 two issuer warps take alternate chunks into their own accumulators.
 // Used when all components fit one M tile (K <= 42) and the rows can be fetched by TMA; otherwise the SS kernel runs.
 //   TMEM columns: [0, 2 * NIS * mrp) accumulators (segment parity, issuer); [256, 512) ring of 8 A chunks x 32 columns.
-#define TS_THREADS 512               // warp 0 raw-tile loader, 1-8 expanders, 9-12 epilogue, 13-14 MMA issuers, 15 weight-tile loader
+#define TS_THREADS 768               // warp 0 raw-tile loader, 1-16 expanders, 17-20 epilogue, 21-22 MMA issuers, 23 weight-tile loader
 #define TS_NA 8                      // A chunks in flight in TMEM
 #define TS_NRAW 16                   // raw bit tiles in flight: a chunk lasts ~200 cycles, a TMA round trip ~2000-3000
 #define TS_RAW_BYTES 2048            // 128 rows x 16 B
@@ -453,12 +453,12 @@ __global__ void __launch_bounds__(TS_THREADS, 1) bitgemm_ts_kernel(const __grid_
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < TS_NW_MAX; ++s) { mbar_init(&wfull[s], 1); mbar_init(&wempty[s], 1); }
-        for (int s = 0; s < TS_NRAW; ++s) { mbar_init(&rfull[s], 1); mbar_init(&rempty[s], 256); }
-        for (int s = 0; s < TS_NA; ++s) { mbar_init(&afull[s], 256); mbar_init(&aempty[s], 1); }
+        for (int s = 0; s < TS_NRAW; ++s) { mbar_init(&rfull[s], 1); mbar_init(&rempty[s], 128); }
+        for (int s = 0; s < TS_NA; ++s) { mbar_init(&afull[s], 128); mbar_init(&aempty[s], 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], NIS); mbar_init(&tempty[s], 128); }
         mbar_fence_init();
     }
-    if (warp == 13) tmem_alloc<512>(tmem_ptr);
+    if (warp == 21) tmem_alloc<512>(tmem_ptr);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -480,7 +480,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) bitgemm_ts_kernel(const __grid_
                 }
             }
         }
-    } else if (warp == 15) {
+    } else if (warp == 23) {
         // weight tiles: one bulk copy per chunk
         if (lane == 0) {
             TsWalk w(Rtiles, A.nchunk);
@@ -496,40 +496,44 @@ __global__ void __launch_bounds__(TS_THREADS, 1) bitgemm_ts_kernel(const __grid_
                 }
             }
         }
-    } else if (warp >= 1 && warp <= 8) {
+    } else if (warp >= 1 && warp <= 16) {
         // ================================== bit expanders ==================================
-        // TMEM lane = bit row: a warp may only touch lanes 32 * (warp % 4) .. +31, so warps {1..4} and {5..8} cover the
-        // four quadrants once each; the first set expands words 0, 1 of a chunk (columns 0..15), the second words 2, 3.
-        const int quad = warp & 3, half = (warp - 1) >> 2;
+        // TMEM lane = bit row: a warp may only touch lanes 32 * (warp % 4) .. +31.  Four sets of four warps (one per lane
+        // quadrant); set p expands the chunks ic % 4 == p, a thread its row's four words (128 bytes = 32 TMEM columns).
+        // One chunk costs a warp ~100 instructions plus ~400 cycles of latencies it cannot overlap (barrier waits, the
+        // shared-memory load, tcgen05.wait::st), so the sets work on four chunks concurrently.
+        const int quad = warp & 3, set = (warp - 1) >> 2;
         const int row = quad * 32 + lane;
         TsWalk w(Rtiles, A.nchunk);
         int rt, c0, n;
         uint32_t ic = 0;
         while (w.next_seg(rt, c0, n)) {
             for (int i = 0; i < n; ++i, ++ic) {
+                if ((int)(ic & 3) != set) continue;
                 const uint32_t rs = ic % TS_NRAW, slot = ic % TS_NA;
                 mbar_wait_relaxed(&rfull[rs], (ic / TS_NRAW) & 1);
-                const uint2 x = *reinterpret_cast<const uint2*>(raw + rs * TS_RAW_BYTES + row * 16 + half * 8);
+                const uint4 x = *reinterpret_cast<const uint4*>(raw + rs * TS_RAW_BYTES + row * 16);
                 mbar_arrive(&rempty[rs]);
                 mbar_wait_relaxed(&aempty[slot], ((ic / TS_NA) & 1) ^ 1);
                 tc_fence_after();
-                const uint32_t taddr = tmem_base + a_col0 + slot * 32 + half * 16 + ((uint32_t)(quad * 32) << 16);
-                uint32_t v[8];
+                const uint32_t taddr = tmem_base + a_col0 + slot * 32 + ((uint32_t)(quad * 32) << 16);
+                const uint32_t wv[4] = {x.x, x.y, x.z, x.w};
 #pragma unroll
-                for (int s8 = 0; s8 < 8; ++s8) v[s8] = (x.x >> s8) & 0x01010101u;     // K index 4 s + jj  <->  bit 8 jj + s of the word
-                tmem_st8(taddr, v);
+                for (int wi = 0; wi < 4; ++wi) {
+                    uint32_t v[8];
 #pragma unroll
-                for (int s8 = 0; s8 < 8; ++s8) v[s8] = (x.y >> s8) & 0x01010101u;
-                tmem_st8(taddr + 8, v);
+                    for (int s8 = 0; s8 < 8; ++s8) v[s8] = (wv[wi] >> s8) & 0x01010101u;     // K index 4 s + jj  <->  bit 8 jj + s of the word
+                    tmem_st8(taddr + 8 * wi, v);
+                }
                 tmem_st_wait();
                 tc_fence_before();
                 mbar_arrive(&afull[slot]);
             }
         }
-    } else if (warp == 13 || (NIS == 2 && warp == 14)) {
+    } else if (warp == 21 || (NIS == 2 && warp == 22)) {
         // ==================================== MMA issuers ====================================
         // issuer `iss` takes the chunks ic % NIS == iss into accumulator (segment parity, iss)
-        const int iss = warp - 13;
+        const int iss = warp - 21;
         const uint32_t idesc = (2u << 4) | (0u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);   // S32 += U8 * S8
         const uint32_t desc_hi = (uint32_t)(128 >> 4) | (1u << 14);                                 // SBO = 128 B, version 1
         const uint64_t b_hi = ((uint64_t)desc_hi << 32) | ((uint64_t)((uint32_t)(N * 16) >> 4) << 16);   // LBO = k-group stride of a weight tile
@@ -561,7 +565,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) bitgemm_ts_kernel(const __grid_
             umma_commit_elect(&tfull[sp]);        // (arrives even if this issuer had no chunk in the segment)
             ++seg;
         }
-    } else if (warp >= 9 && warp <= 12) {
+    } else if (warp >= 17 && warp <= 20) {
         // ===================================== epilogue =====================================
         // lane = bit row r, column = plane row m: for a fixed m the warp's 32 lanes are 32 consecutive r of acc[m][.],
         // one coalesced 128-byte reduction
@@ -606,7 +610,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) bitgemm_ts_kernel(const __grid_
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 13) {
+    if (warp == 21) {
         tc_fence_after();
         tmem_dealloc<512>(tmem_base);
     }
@@ -1069,6 +1073,108 @@ __global__ void __launch_bounds__(128) em_posterior_kernel(PostArgs P) {
     if (tid == 0) atomicAdd(reinterpret_cast<unsigned long long*>(P.llQ + slot), (unsigned long long)s_ll);
 }
 
+// K <= 32: four threads per row.  CTA = 32 rows x 4 warps; warp q owns the components k = q, q + 4, ... (<= 8 of them) of
+// the 32 rows (lane = row: every accumulator load is one coalesced 128-byte line), so a thread reads its 3 * 8 integers once,
+// keeps 8 scores in registers (full occupancy instead of the 128 registers of a thread-per-row kernel) and the row-wise
+// max / sum go through shared memory (two barriers).
+template <bool INT_SCORES>
+__global__ void __launch_bounds__(128) em_posterior4_kernel(PostArgs P) {
+    if (P.done && *P.done) return;
+    extern __shared__ __align__(16) uint8_t psm[];
+    float* s_aff = reinterpret_cast<float*>(psm);                      // [32][K + 1]
+    __shared__ double s_mx[4][32], s_sc[4][32], s_sum[4][32];
+    __shared__ int s_arg[4][32];
+    const int lane = threadIdx.x & 31, q = threadIdx.x >> 5;
+    const long long n = blockIdx.x * 32LL + lane;
+    const bool live = n < P.N;
+    const size_t pstride = (size_t)P.KT * P.Npad;
+    constexpr int KQ = 8;
+    double sv[KQ];
+    int a0[KQ], a1[KQ], a2[KQ];
+    if (INT_SCORES) {
+        int* a = P.accE + n;
+#pragma unroll
+        for (int j = 0; j < KQ; ++j) {
+            const int k = q + 4 * j;
+            if (k < P.K) { a0[j] = a[(size_t)k * P.Npad]; a1[j] = a[(size_t)k * P.Npad + pstride]; a2[j] = a[(size_t)k * P.Npad + 2 * pstride]; }
+        }
+#pragma unroll
+        for (int j = 0; j < KQ; ++j) {
+            const int k = q + 4 * j;
+            if (k < P.K) {
+                a[(size_t)k * P.Npad] = 0; a[(size_t)k * P.Npad + pstride] = 0; a[(size_t)k * P.Npad + 2 * pstride] = 0;
+                const double qq = (double)a0[j] + 256.0 * (double)a1[j] + 65536.0 * (double)a2[j];
+                sv[j] = qq * (double)P.scale[k] + (double)P.c[k] * (1.0 / EM_C_SCALE);
+            }
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < KQ; ++j) {
+            const int k = q + 4 * j;
+            if (k < P.K) sv[j] = (double)P.scratch[(size_t)k * P.Npad + n];
+        }
+    }
+    // partial maxima of this warp's components
+    double mx = -INFINITY, smx = -INFINITY;
+    int arg = 0x7fffffff;
+#pragma unroll
+    for (int j = 0; j < KQ; ++j) {
+        const int k = q + 4 * j;
+        if (k < P.K) {
+            if (live && P.scores_out) P.scores_out[n * P.K + k] = (float)sv[j];
+            if (sv[j] > smx) { smx = sv[j]; arg = k; }
+            mx = fmax(mx, sv[j] + (double)P.logw[k]);
+        }
+    }
+    if (!P.update) return;
+    s_mx[q][lane] = mx; s_sc[q][lane] = smx; s_arg[q][lane] = arg;
+    __syncthreads();
+    mx = fmax(fmax(s_mx[0][lane], s_mx[1][lane]), fmax(s_mx[2][lane], s_mx[3][lane]));
+    // hard assignment: first arg-max of the template scores (:273-275): largest score, lowest index among equals
+    smx = s_sc[0][lane]; arg = s_arg[0][lane];
+#pragma unroll
+    for (int w = 1; w < 4; ++w) {
+        const double o = s_sc[w][lane];
+        const int oa = s_arg[w][lane];
+        if (o > smx || (o == smx && oa < arg)) { smx = o; arg = oa; }
+    }
+    float ev[KQ];
+    double sum = 0.0;
+#pragma unroll
+    for (int j = 0; j < KQ; ++j) {
+        const int k = q + 4 * j;
+        ev[j] = 0.f;
+        if (k < P.K) { ev[j] = expf((float)(sv[j] + (double)P.logw[k] - mx)); sum += (double)ev[j]; }
+    }
+    s_sum[q][lane] = sum;
+    __syncthreads();
+    sum = (s_sum[0][lane] + s_sum[1][lane]) + (s_sum[2][lane] + s_sum[3][lane]);
+    const float inv = (float)(1.0 / sum);
+#pragma unroll
+    for (int j = 0; j < KQ; ++j) {
+        const int k = q + 4 * j;
+        if (k < P.K) {
+            float p = 0.f;
+            if (live) p = P.hard ? (k == arg ? 1.f : 0.f) : fminf(ev[j] * inv, 1.f);
+            s_aff[lane * (P.K + 1) + k] = p;
+            const uint32_t wmax = __reduce_max_sync(0xffffffffu, __float_as_uint(p));     // p >= 0: bit patterns order like values
+            if (lane == 0 && wmax) atomicMax(P.colmax + (size_t)(blockIdx.x % EM_SLOTS) * P.K + k, wmax);
+        }
+    }
+    if (q == 0) {
+        long long my_ll = live ? llrint((log(sum) + mx) * EM_LL_SCALE) : 0;
+        for (int off = 16; off > 0; off >>= 1) my_ll += __shfl_xor_sync(0xffffffffu, my_ll, off);
+        if (lane == 0) atomicAdd(reinterpret_cast<unsigned long long*>(P.llQ + blockIdx.x % EM_SLOTS), (unsigned long long)my_ll);
+    }
+    __syncthreads();
+    // rows n0 .. n0+31 of aff are one contiguous block of 32 * K floats: coalesced stores
+    const long long base = blockIdx.x * 32LL * P.K, lim = P.N * P.K;
+    for (int e = threadIdx.x; e < 32 * P.K; e += 128) {
+        const int r = e / P.K, k = e - r * P.K;
+        if (base + e < lim) P.aff[base + e] = s_aff[r * (P.K + 1) + k];
+    }
+}
+
 // column maxima of caller-supplied posteriors (initialisation; M-step from given posteriors)
 __global__ void em_colmax_kernel(const float* __restrict__ aff, long long N, int K, uint32_t* __restrict__ colmax, const int* done) {
     if (done && *done) return;
@@ -1343,14 +1449,12 @@ int tsr_em_estep(const uint32_t* Xbits, long long N, int D, int rowwords, int K,
                                                                s.Npad, done);
         rc = check_launch("tsr_em_estep(simt scores)");
         if (rc) return rc;
-        if (K <= 16) em_posterior_kernel<false, 16><<<pgrid, 128, psm, st>>>(P);
-        else if (K <= 32) em_posterior_kernel<false, 32><<<pgrid, 128, psm, st>>>(P);
+        if (K <= 32) em_posterior4_kernel<false><<<(unsigned)(s.Npad / 32), 128, (size_t)32 * (K + 1) * 4, st>>>(P);
         else em_posterior_kernel<false, 0><<<pgrid, 128, psm, st>>>(P);
     } else {
         rc = launch_bitgemm(Xbits, N, rowwords, ws + s.off_wblob, P.accE, s.Npad, s.nchunkE, s, done, st);
         if (rc) return rc;
-        if (K <= 16) em_posterior_kernel<true, 16><<<pgrid, 128, psm, st>>>(P);
-        else if (K <= 32) em_posterior_kernel<true, 32><<<pgrid, 128, psm, st>>>(P);
+        if (K <= 32) em_posterior4_kernel<true><<<(unsigned)(s.Npad / 32), 128, (size_t)32 * (K + 1) * 4, st>>>(P);
         else em_posterior_kernel<true, 0><<<pgrid, 128, psm, st>>>(P);
     }
     rc = check_launch("tsr_em_estep(posterior)");
