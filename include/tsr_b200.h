@@ -257,11 +257,17 @@ long long tsr_em_npad(long long N);                                             
 /* XT uint32 [D][N_pad/32] = the bit matrix transposed once per data set (tensor-path M-step), N_pad = tsr_em_npad(N) */
 int tsr_transpose_bits(const uint32_t* Xbits, long long N, int D, int rowwords, uint32_t* XTbits, long long N_pad,
                        void* stream);
-int tsr_em_estep(const uint32_t* Xbits, long long N, int D, int rowwords, int K, const float* logT_or_null,
+/* Tile order of a bit matrix [R][rw]: [128-row tile][16-byte chunk][128 rows][4 words], zero padded to a multiple of 256
+ * rows -- what the tensor-core contraction reads for one chunk of one row tile is then one contiguous 2 KB block
+ * (sequential HBM reads; 16 bytes per row at a stride of the row pitch ran at 18 % of the HBM peak).  Built once per
+ * data set for X (E-step) and for the transposed X (M-step). */
+size_t tsr_em_tiled_words(long long R, int rw);
+int    tsr_em_tile_bits(const uint32_t* bits, long long R, int rw, uint32_t* tiled, void* stream);
+int tsr_em_estep(const uint32_t* Xbits, const uint32_t* Xtiled_or_null, long long N, int D, int rowwords, int K, const float* logT_or_null,
                  const float* logInvT_or_null, const float* logw, float* aff_or_null, float* scores_or_null,
                  double* stats_or_null, int hard, int update, void* workspace, const void* ctl_or_null, int impl,
                  void* stream);
-int tsr_em_mstep(const uint32_t* Xbits, const uint32_t* XTbits_or_null /* required for TSR_IMPL_TENSOR */,
+int tsr_em_mstep(const uint32_t* Xbits, const uint32_t* XTbits_or_null, const uint32_t* XTtiled_or_null /* one of the two for TSR_IMPL_TENSOR */,
                  long long N, int D, int rowwords, int K, const float* aff_or_null, double* stats, void* workspace,
                  const void* ctl_or_null, int impl, void* stream);
 /* weights = respsum / N_total; T = numer / N_total / weights clipped to [min_prob, 1-min_prob]; logT, logInvT,

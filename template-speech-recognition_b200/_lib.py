@@ -50,8 +50,10 @@ SIGNATURES = {
     "tsr_em_workspace_init": (_i, [_vp, _ll, _i, _i, _vp]),
     "tsr_em_npad": (_ll, [_ll]),
     "tsr_transpose_bits": (_i, [_vp, _ll, _i, _i, _vp, _ll, _vp]),
-    "tsr_em_estep": (_i, [_vp, _ll, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _i, _vp]),
-    "tsr_em_mstep": (_i, [_vp, _vp, _ll, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp]),
+    "tsr_em_tiled_words": (_sz, [_ll, _i]),
+    "tsr_em_tile_bits": (_i, [_vp, _ll, _i, _vp, _vp]),
+    "tsr_em_estep": (_i, [_vp, _vp, _ll, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _i, _vp]),
+    "tsr_em_mstep": (_i, [_vp, _vp, _vp, _ll, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp]),
     "tsr_em_finalize": (_i, [_vp, _ll, _i, _i, _f, _vp, _vp, _vp, _vp, _vp, _vp, _ll, _vp, _vp]),
     "tsr_em_control_bytes": (_sz, [_i]),
     "tsr_em_control_init": (_i, [_vp, _i, ctypes.c_double, _i, _i, _i, _vp]),

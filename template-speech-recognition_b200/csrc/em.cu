@@ -23,8 +23,6 @@
 #include <math.h>
 #include <string.h>
 
-#include <cuda.h>      // CUtensorMap (the encoder is fetched through cudaGetDriverEntryPoint: no libcuda link dependency)
-
 #include "common.cuh"
 
 extern "C" int tsr_rowwords(int D);
@@ -98,7 +96,7 @@ struct EmCtl {
 //         (word >> s) & 0x01010101 gives the four bytes of shift s with two instructions
 //   acc   [Mtiles][mrp][Rpad] int32 += products (Rpad = R rounded up to 256)
 struct BgArgs {
-    alignas(64) CUtensorMap tmap;   // RAW_TMA: the bit matrix as a 2-D uint8 tensor {rw*4 bytes, R rows}, box {16 B, 256 rows}
+    const uint32_t* tiled;          // the bit matrix in tile order [128-row tile][chunk][128 rows][16 B] (tsr_em_tile_bits), or null
     const uint32_t* bits;
     const uint8_t* wblob;
     int* acc;
@@ -107,16 +105,6 @@ struct BgArgs {
     int nw;                         // TS kernel: weight tiles in flight
     const int* done;
 };
-
-// 2-D tiled TMA load global -> shared (UTMALDG in SASS); completes on an mbarrier.  Rows past the tensor's extent are
-// zero filled, so the last row tile needs no bounds checks.
-__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tmap, int x, int y, uint64_t* bar) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
-            smem_u32(smem_dst)),
-        "l"(reinterpret_cast<uint64_t>(tmap)), "r"(x), "r"(y), "r"(smem_u32(bar))
-        : "memory");
-}
 
 // A CTA's share of the flattened (R tile, M tile, chunk) space, cut into segments at tile borders.
 struct BgWalk {
@@ -154,12 +142,12 @@ __device__ __forceinline__ void umma_i8_ss(uint32_t d_tmem, uint64_t a_desc, uin
         : "memory");
 }
 
-// RAW_TMA: the bit rows reach shared memory through TMA tensor loads (one 256-row x 16-byte box per chunk) and the
-// expanders read them with conflict-free LDS.128.  Loading them with per-thread LDG instead (rows are rw*4 bytes
-// apart, so a warp's load touches 32 sectors) put as many wavefronts on the L1 data pipe as the expanded stores, and
-// that pipe -- shared by the LSU and the tensor cores' operand reads -- is what bounds this kernel (ncu:
-// lsu wavefronts 70 % + tensor-operand wavefronts 36 % of its peak).  The LDG path remains for row pitches that are
-// not a multiple of 16 bytes.
+// RAW_TMA: the bit rows reach shared memory as bulk (TMA) copies of the pre-tiled matrix (tsr_em_tile_bits: the
+// 256 rows x 16 bytes a chunk needs are two contiguous 2 KB blocks) and the expanders read them with conflict-free
+// LDS.128.  Fetching 16 bytes per row straight from the row-major matrix -- per-thread LDG, or a 2-D tensor-map TMA
+// box -- touches one 32-byte DRAM sector per row at a stride of the row pitch and ran at 1.2 TB/s (18 % of the HBM
+// peak) whatever the rest of the kernel did; the per-thread loads also put as many wavefronts on the L1 data pipe
+// as the expanded stores.  The LDG path remains for callers without a tiled copy.
 template <bool RAW_TMA>
 __global__ void __launch_bounds__(BG_THREADS, 1) bitgemm_kernel(const __grid_constant__ BgArgs A) {
     if (A.done && *A.done) return;
@@ -207,7 +195,9 @@ __global__ void __launch_bounds__(BG_THREADS, 1) bitgemm_kernel(const __grid_con
                         const uint32_t rs = ic % BG_NRAW;
                         mbar_wait_relaxed(&rempty[rs], ((ic / BG_NRAW) & 1) ^ 1);
                         mbar_arrive_expect_tx(&rfull[rs], BG_RAW_BYTES);
-                        tma_load_2d(raw + rs * BG_RAW_BYTES, &A.tmap, 16 * (c0 + i), rt * 256, &rfull[rs]);
+                        const uint32_t* t0 = A.tiled + (((size_t)(2 * rt) * A.nchunk + (c0 + i)) << 9);       // 512 words per (tile, chunk)
+                        bulk_g2s(raw + rs * BG_RAW_BYTES, t0, 2048, &rfull[rs]);
+                        bulk_g2s(raw + rs * BG_RAW_BYTES + 2048, t0 + ((size_t)A.nchunk << 9), 2048, &rfull[rs]);
                     }
                     mbar_wait_relaxed(&wempty[stage], ph ^ 1);
                     mbar_arrive_expect_tx(&wfull[stage], tile_bytes);
@@ -466,7 +456,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) bitgemm_ts_kernel(const __grid_
     const uint32_t a_col0 = 256;
 
     if (warp == 0) {
-        // raw bit tiles: one TMA tensor load (128 rows x 16 B) per chunk
+        // raw bit tiles: one 2 KB bulk copy (128 rows x 16 B, contiguous in the tiled matrix) per chunk
         if (lane == 0) {
             TsWalk w(Rtiles, A.nchunk);
             int rt, c0, n;
@@ -476,7 +466,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) bitgemm_ts_kernel(const __grid_
                     const uint32_t rs = ic % TS_NRAW;
                     mbar_wait_relaxed(&rempty[rs], ((ic / TS_NRAW) & 1) ^ 1);
                     mbar_arrive_expect_tx(&rfull[rs], TS_RAW_BYTES);
-                    tma_load_2d(raw + rs * TS_RAW_BYTES, &A.tmap, 16 * (c0 + i), rt * 128, &rfull[rs]);
+                    bulk_g2s(raw + rs * TS_RAW_BYTES, A.tiled + (((size_t)rt * A.nchunk + (c0 + i)) << 9), TS_RAW_BYTES, &rfull[rs]);
                 }
             }
         }
@@ -621,67 +611,32 @@ static size_t bitgemm_smem(int mrp, bool raw_tma) {
            4 * BG_TBUF_WORDS * 4 + 512;
 }
 
-typedef CUresult (*tsr_encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                        const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                        CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static tsr_encode_tiled_fn encode_tiled_fn() {
-    static tsr_encode_tiled_fn fn = nullptr;
-    static bool tried = false;
-    if (!tried) {
-        tried = true;
-        void* p = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<tsr_encode_tiled_fn>(p);
-        cudaGetLastError();
-    }
-    return fn;
-}
-
-static int launch_bitgemm(const uint32_t* bits, long long R, int rw, const uint8_t* wblob, int* acc, long long Rpad, int nchunk,
-                          const EmShape& s, const int* done, cudaStream_t st) {
+static int launch_bitgemm(const uint32_t* bits, const uint32_t* tiled, long long R, int rw, const uint8_t* wblob, int* acc,
+                          long long Rpad, int nchunk, const EmShape& s, const int* done, cudaStream_t st) {
     BgArgs A;
     memset(&A, 0, sizeof(A));
-    A.bits = bits; A.wblob = wblob; A.acc = acc; A.R = R; A.Rpad = Rpad; A.rw = rw; A.nchunk = nchunk;
+    A.bits = bits; A.tiled = tiled; A.wblob = wblob; A.acc = acc; A.R = R; A.Rpad = Rpad; A.rw = rw; A.nchunk = nchunk;
     A.Mtiles = s.Mtiles; A.mrp = s.mrp; A.mrows = s.mrows; A.Rtiles = (int)(Rpad / 256); A.done = done;
-    // the bit matrix as a TMA tensor when its row pitch allows (multiple of 16 bytes, 16-byte aligned base)
-    bool raw_tma = (rw % 4 == 0) && ((reinterpret_cast<uintptr_t>(bits) & 15) == 0) && getenv("TSR_DEBUG_BITGEMM_LDG") == nullptr;
-    if (raw_tma) {
-        tsr_encode_tiled_fn enc = encode_tiled_fn();
-        const cuuint64_t gdim[2] = {(cuuint64_t)rw * 4, (cuuint64_t)R};
-        const cuuint64_t gstride[1] = {(cuuint64_t)rw * 4};
-        const cuuint32_t box[2] = {16, 256}, estr[2] = {1, 1};
-        raw_tma = enc && enc(&A.tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<uint32_t*>(bits), gdim, gstride, box, estr,
-                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
-                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-    }
-    if (raw_tma && s.Mtiles == 1 && Rpad % 128 == 0 && getenv("TSR_DEBUG_BITGEMM_SS") == nullptr) {
-        // bit rows as the A operand in tensor memory (see bitgemm_ts_kernel); the box of the row tensor is 128 rows
-        tsr_encode_tiled_fn enc = encode_tiled_fn();
-        const cuuint64_t gdim[2] = {(cuuint64_t)rw * 4, (cuuint64_t)R};
-        const cuuint64_t gstride[1] = {(cuuint64_t)rw * 4};
-        const cuuint32_t box[2] = {16, 128}, estr[2] = {1, 1};
-        if (enc(&A.tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<uint32_t*>(bits), gdim, gstride, box, estr,
-                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
-                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS) {
-            size_t nw = (size_t)(144 * 1024) / s.tile_bytes;
-            if (nw > TS_NW_MAX) nw = TS_NW_MAX;
-            A.nw = (int)nw;
-            const size_t tsmem = nw * s.tile_bytes + TS_NRAW * TS_RAW_BYTES + 1024;
-            const long long ttotal = (Rpad / 128) * nchunk;
-            const int nsm2 = sm_count();
-            const int tgrid = (int)(ttotal < nsm2 ? ttotal : nsm2);
-            if (tgrid < 1) return TSR_OK;
-            static bool ts_attr = false;
-            if (!ts_attr) {
-                TSR_CUDA(cudaFuncSetAttribute(bitgemm_ts_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-                TSR_CUDA(cudaFuncSetAttribute(bitgemm_ts_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-                ts_attr = true;
-            }
-            if (s.mrp <= 64) bitgemm_ts_kernel<2><<<tgrid, TS_THREADS, tsmem, st>>>(A);
-            else bitgemm_ts_kernel<1><<<tgrid, TS_THREADS, tsmem, st>>>(A);
-            return check_launch("bitgemm_ts_kernel");
+    const bool raw_tma = tiled != nullptr && getenv("TSR_DEBUG_BITGEMM_LDG") == nullptr;
+    const int nsm = sm_count();
+    if (raw_tma && s.Mtiles == 1 && getenv("TSR_DEBUG_BITGEMM_SS") == nullptr) {
+        // all components in one M tile: bit rows as the A operand in tensor memory (bitgemm_ts_kernel)
+        size_t nw = (size_t)(144 * 1024) / s.tile_bytes;
+        if (nw > TS_NW_MAX) nw = TS_NW_MAX;
+        A.nw = (int)nw;
+        const size_t tsmem = nw * s.tile_bytes + TS_NRAW * TS_RAW_BYTES + 1024;
+        const long long ttotal = (Rpad / 128) * nchunk;
+        const int tgrid = (int)(ttotal < nsm ? ttotal : nsm);
+        if (tgrid < 1) return TSR_OK;
+        static bool ts_attr = false;
+        if (!ts_attr) {
+            TSR_CUDA(cudaFuncSetAttribute(bitgemm_ts_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            TSR_CUDA(cudaFuncSetAttribute(bitgemm_ts_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            ts_attr = true;
         }
+        if (s.mrp <= 64) bitgemm_ts_kernel<2><<<tgrid, TS_THREADS, tsmem, st>>>(A);
+        else bitgemm_ts_kernel<1><<<tgrid, TS_THREADS, tsmem, st>>>(A);
+        return check_launch("bitgemm_ts_kernel");
     }
     const size_t smem = bitgemm_smem(s.mrp, raw_tma);
     static bool attr_set = false;
@@ -691,12 +646,33 @@ static int launch_bitgemm(const uint32_t* bits, long long R, int rw, const uint8
         attr_set = true;
     }
     const long long total = (long long)A.Rtiles * A.Mtiles * nchunk;
-    const int nsm = sm_count();
     const int grid = (int)(total < nsm ? total : nsm);
     if (grid < 1) return TSR_OK;
     if (raw_tma) bitgemm_kernel<true><<<grid, BG_THREADS, smem, st>>>(A);
     else bitgemm_kernel<false><<<grid, BG_THREADS, smem, st>>>(A);
     return check_launch("bitgemm_kernel");
+}
+
+// bits [R][rw] -> tile order [128-row tile][chunk][128 rows][4 words] (rows >= R and words >= rw read as zero): what a CTA
+// needs for one chunk of one row tile is then one contiguous 2 KB block (sequential DRAM reads instead of one 32-byte
+// sector per row at a stride of the row pitch).  One thread per (tile, chunk, row): 16 bytes.
+__global__ void tile_bits_kernel(const uint32_t* __restrict__ bits, long long R, int rw, int nchunk, long long ntile,
+                                 uint4* __restrict__ tiled) {
+    const long long total = ntile * nchunk * 128;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int r = (int)(i & 127);
+        const long long tc = i >> 7;
+        const int c = (int)(tc % nchunk);
+        const long long row = (tc / nchunk) * 128 + r;
+        uint32_t w[4] = {0u, 0u, 0u, 0u};
+        if (row < R) {
+            const uint32_t* p = bits + row * rw + 4 * c;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (4 * c + j < rw) w[j] = __ldg(p + j);
+        }
+        tiled[i] = make_uint4(w[0], w[1], w[2], w[3]);
+    }
 }
 
 // Small per-call scratch in the workspace.  Per-CTA partial results are combined with integer atomics; 782 CTAs
@@ -1405,7 +1381,22 @@ static int em_planes(const EmShape& s, uint8_t* ws, const float* aff, double* st
     return check_launch("em_aff_planes_kernel");
 }
 
-int tsr_em_estep(const uint32_t* Xbits, long long N, int D, int rowwords, int K, const float* logT_or_null,
+size_t tsr_em_tiled_words(long long R, int rw) {
+    if (R < 0 || rw < 1) return 0;
+    return (size_t)((R + 255) / 256 * 256) * (size_t)((rw + 3) / 4) * 4;
+}
+
+int tsr_em_tile_bits(const uint32_t* bits, long long R, int rw, uint32_t* tiled, void* stream) {
+    TSR_REQUIRE(bits && tiled, "tsr_em_tile_bits: null pointer");
+    TSR_REQUIRE(R >= 1 && rw >= 1, "tsr_em_tile_bits: bad sizes");
+    int rc = require_sm100("tsr_em_tile_bits");
+    if (rc) return rc;
+    const long long ntile = (R + 255) / 256 * 2;
+    tile_bits_kernel<<<sm_count() * 8, 256, 0, (cudaStream_t)stream>>>(bits, R, rw, (rw + 3) / 4, ntile, reinterpret_cast<uint4*>(tiled));
+    return check_launch("tsr_em_tile_bits");
+}
+
+int tsr_em_estep(const uint32_t* Xbits, const uint32_t* Xtiled_or_null, long long N, int D, int rowwords, int K, const float* logT_or_null,
                  const float* logInvT_or_null, const float* logw, float* aff_or_null, float* scores_or_null,
                  double* stats_or_null, int hard, int update, void* workspace, const void* ctl_or_null, int impl,
                  void* stream) {
@@ -1452,7 +1443,7 @@ int tsr_em_estep(const uint32_t* Xbits, long long N, int D, int rowwords, int K,
         if (K <= 32) em_posterior4_kernel<false><<<(unsigned)(s.Npad / 32), 128, (size_t)32 * (K + 1) * 4, st>>>(P);
         else em_posterior_kernel<false, 0><<<pgrid, 128, psm, st>>>(P);
     } else {
-        rc = launch_bitgemm(Xbits, N, rowwords, ws + s.off_wblob, P.accE, s.Npad, s.nchunkE, s, done, st);
+        rc = launch_bitgemm(Xbits, Xtiled_or_null, N, rowwords, ws + s.off_wblob, P.accE, s.Npad, s.nchunkE, s, done, st);
         if (rc) return rc;
         if (K <= 32) em_posterior4_kernel<true><<<(unsigned)(s.Npad / 32), 128, (size_t)32 * (K + 1) * 4, st>>>(P);
         else em_posterior_kernel<true, 0><<<pgrid, 128, psm, st>>>(P);
@@ -1472,7 +1463,7 @@ int tsr_transpose_bits(const uint32_t* Xbits, long long N, int D, int rowwords, 
     return check_launch("tsr_transpose_bits");
 }
 
-int tsr_em_mstep(const uint32_t* Xbits, const uint32_t* XTbits_or_null, long long N, int D, int rowwords, int K,
+int tsr_em_mstep(const uint32_t* Xbits, const uint32_t* XTbits_or_null, const uint32_t* XTtiled_or_null, long long N, int D, int rowwords, int K,
                  const float* aff_or_null, double* stats, void* workspace, const void* ctl_or_null, int impl, void* stream) {
     TSR_REQUIRE(Xbits && stats && workspace, "tsr_em_mstep: null pointer");
     TSR_REQUIRE(K >= 1 && K <= EM_MAX_K, "tsr_em_mstep: need 1 <= num_mix <= %d (got %d)", EM_MAX_K, K);
@@ -1507,9 +1498,9 @@ int tsr_em_mstep(const uint32_t* Xbits, const uint32_t* XTbits_or_null, long lon
         em_mstep_simt_kernel<<<(unsigned)blocks, 128, 0, st>>>(Xbits, N, D, rowwords, K, aff, sm.sk, stats, done);
         return check_launch("tsr_em_mstep(simt)");
     }
-    TSR_REQUIRE(XTbits_or_null, "tsr_em_mstep: the tensor path needs the transposed bits (tsr_transpose_bits)");
-    rc = launch_bitgemm(XTbits_or_null, D, (int)(s.Npad / 32), ws + s.off_ablob, (int*)(ws + s.off_accM), s.Dpad, (int)s.nchunkM, s,
-                        done, st);
+    TSR_REQUIRE(XTbits_or_null || XTtiled_or_null, "tsr_em_mstep: the tensor path needs the transposed bits (tsr_transpose_bits), plain or tiled");
+    rc = launch_bitgemm(XTbits_or_null, XTtiled_or_null, D, (int)(s.Npad / 32), ws + s.off_ablob, (int*)(ws + s.off_accM), s.Dpad,
+                        (int)s.nchunkM, s, done, st);
     if (rc) return rc;
     long long blocks = ((long long)K * D + 255) / 256;
     const long long cap = (long long)sm_count() * 8;

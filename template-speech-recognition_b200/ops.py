@@ -504,11 +504,19 @@ class EmState:
         with torch.cuda.device(dev):
             self.ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
             _lib.call("tsr_em_workspace_init", _ptr(self.ws), self.N, self.D, self.K, _stream())
-            # transposed bits for the tensor-core M-step (one-time, 1 bit per datum)
+            # one-time re-layouts for the tensor-core contractions (1 bit per datum each): X in tile order for the E-step,
+            # X transposed and in tile order for the M-step
             self.Npad = int(_lib.lib().tsr_em_npad(self.N))
-            self.XT = torch.zeros((self.D, self.Npad // 32), dtype=torch.int32, device=dev)
+            self.Xt = self.XTt = None
             if self.N:
-                _lib.call("tsr_transpose_bits", _ptr(self.X), self.N, self.D, self.rw, _ptr(self.XT), self.Npad, _stream())
+                XT = torch.zeros((self.D, self.Npad // 32), dtype=torch.int32, device=dev)
+                _lib.call("tsr_transpose_bits", _ptr(self.X), self.N, self.D, self.rw, _ptr(XT), self.Npad, _stream())
+                self.Xt = torch.empty(_lib.lib().tsr_em_tiled_words(self.N, self.rw), dtype=torch.int32, device=dev)
+                _lib.call("tsr_em_tile_bits", _ptr(self.X), self.N, self.rw, _ptr(self.Xt), _stream())
+                self.XTt = torch.empty(_lib.lib().tsr_em_tiled_words(self.D, self.Npad // 32), dtype=torch.int32, device=dev)
+                _lib.call("tsr_em_tile_bits", _ptr(XT), self.D, self.Npad // 32, _ptr(self.XTt), _stream())
+                torch.cuda.current_stream().synchronize()        # XT is released on return
+                del XT
         self.aff = torch.zeros((self.N, self.K), dtype=torch.float32, device=dev)
         # stats = [K*D numerators | K responsibility sums | log-likelihood], float64 (see tsr_b200.h)
         self.stats = torch.zeros(self.K * self.D + self.K + 1, dtype=torch.float64, device=dev)
@@ -516,7 +524,7 @@ class EmState:
     def estep(self, logT, logInvT, logw, hard=False, impl=IMPL_TENSOR, scores_out=None, update=True, ctl=None):
         """logT = logInvT = None: use the weight planes the last em_finalize(..., state=self) laid out."""
         with torch.cuda.device(self.X.device):
-            _lib.call("tsr_em_estep", _ptr(self.X), self.N, self.D, self.rw, self.K, _ptr(logT), _ptr(logInvT), _ptr(logw),
+            _lib.call("tsr_em_estep", _ptr(self.X), _ptr(self.Xt), self.N, self.D, self.rw, self.K, _ptr(logT), _ptr(logInvT), _ptr(logw),
                       _ptr(self.aff) if update else 0, _ptr(scores_out), _ptr(self.stats) if update else 0, int(bool(hard)),
                       int(bool(update)), _ptr(self.ws), _ptr(ctl.buf) if ctl is not None else 0, int(impl), _stream())
 
@@ -528,7 +536,7 @@ class EmState:
         elif impl == IMPL_SIMT:
             aff = self.aff
         with torch.cuda.device(self.X.device):
-            _lib.call("tsr_em_mstep", _ptr(self.X), _ptr(self.XT), self.N, self.D, self.rw, self.K, _ptr(aff), _ptr(self.stats),
+            _lib.call("tsr_em_mstep", _ptr(self.X), 0, _ptr(self.XTt), self.N, self.D, self.rw, self.K, _ptr(aff), _ptr(self.stats),
                       _ptr(self.ws), _ptr(ctl.buf) if ctl is not None else 0, int(impl), _stream())
 
     def numerators(self):

@@ -119,7 +119,8 @@ class ScoringPipeline:
 
         import time as _time
         stats = self.__dict__.setdefault("stream_stats", {})
-        stats.update(pack_s=0.0, pack_calls=0, feeder_wait_s=0.0, consumer_wait_s=0.0)
+        stats.update(pack_s=0.0, pack_calls=0, feeder_wait_s=0.0, consumer_wait_s=0.0, h2d_issue_s=0.0, compute_issue_s=0.0,
+                     d2h_issue_s=0.0, result_wait_s=0.0)
 
         def feeder():
             try:
@@ -180,6 +181,7 @@ class ScoringPipeline:
                     raise item
                 xb, slot = item
                 k = i & 1
+                t1 = _time.perf_counter()
                 with torch.cuda.stream(h2d):
                     if xd[k] is None or xd[k].shape != xb.shape:
                         # A fresh block may be one that kernels still in flight on `main` were using (the caching
@@ -195,10 +197,14 @@ class ScoringPipeline:
                     if slot is not None:
                         consumed[slot] = arrived
                 main.wait_event(arrived)
+                t2 = _time.perf_counter()
+                stats["h2d_issue_s"] += t2 - t1
                 bits = ops.pack_edges(xd[k]) if xd[k].dim() == 4 else xd[k]
                 best, arg, _ = self(bits)
                 free_ev[k] = torch.cuda.Event()
                 free_ev[k].record(main)                   # the whole step is queued: xd[k] (== bits when packed) is free after it
+                t3 = _time.perf_counter()
+                stats["compute_issue_s"] += t3 - t2
                 r = i % ring
                 if outs[r] is None or outs[r][0].shape != best.shape:
                     outs[r] = (torch.empty(best.shape, dtype=torch.float32).pin_memory(),
@@ -211,8 +217,11 @@ class ScoringPipeline:
                     arg.record_stream(d2h)
                     out_ev[r] = torch.cuda.Event()
                     out_ev[r].record(d2h)
+                t4 = _time.perf_counter()
+                stats["d2h_issue_s"] += t4 - t3
                 if pending is not None:
                     out_ev[pending].synchronize()
+                    stats["result_wait_s"] += _time.perf_counter() - t4
                     yield outs[pending]
                 pending = r
                 i += 1
