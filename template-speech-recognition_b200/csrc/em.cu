@@ -103,8 +103,38 @@ struct BgArgs {
     long long R, Rpad;
     int rw, nchunk, Mtiles, mrp, mrows, Rtiles;
     int nw;                         // TS kernel: weight tiles in flight
+    int wait_mode;                  // see bg_wait
     const int* done;
 };
+
+// Barrier wait of the bitgemm pipelines.  A slot of these kernels holds only ~500 cycles of tensor work, so the time a
+// waiter needs to notice a completed phase is on the critical path (slots / latency = chunks per cycle).  mode 0: the
+// suspending try_wait of common.cuh (100 us hint); 1: non-blocking test_wait polls with a short sleep; 2: try_wait with
+// a 1 us hint.
+__device__ __forceinline__ void bg_wait(uint64_t* bar, uint32_t parity, int mode) {
+    if (mode == 0) { mbar_wait_relaxed(bar, parity); return; }
+    uint32_t spins = 0, ok = 0;
+    do {
+        if (mode == 1) {
+            asm volatile(
+                "{\n\t.reg .pred p;\n\t"
+                "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                "selp.u32 %0, 1, 0, p;\n\t}"
+                : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+            if (!ok) __nanosleep(32);
+        } else {
+            asm volatile(
+                "{\n\t.reg .pred p;\n\t"
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+                "selp.u32 %0, 1, 0, p;\n\t}"
+                : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(1000u) : "memory");
+        }
+        if (!ok && ++spins > TSR_SPIN_LIMIT) {
+            printf("tsr_b200: bitgemm barrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+            __trap();
+        }
+    } while (!ok);
+}
 
 // A CTA's share of the flattened (R tile, M tile, chunk) space, cut into segments at tile borders.
 struct BgWalk {
@@ -193,13 +223,13 @@ __global__ void __launch_bounds__(BG_THREADS, 1) bitgemm_kernel(const __grid_con
                 for (int i = 0; i < n; ++i, ++ic) {
                     if (RAW_TMA) {
                         const uint32_t rs = ic % BG_NRAW;
-                        mbar_wait_relaxed(&rempty[rs], ((ic / BG_NRAW) & 1) ^ 1);
+                        bg_wait(&rempty[rs], ((ic / BG_NRAW) & 1) ^ 1, A.wait_mode);
                         mbar_arrive_expect_tx(&rfull[rs], BG_RAW_BYTES);
                         const uint32_t* t0 = A.tiled + (((size_t)(2 * rt) * A.nchunk + (c0 + i)) << 9);       // 512 words per (tile, chunk)
                         bulk_g2s(raw + rs * BG_RAW_BYTES, t0, 2048, &rfull[rs]);
                         bulk_g2s(raw + rs * BG_RAW_BYTES + 2048, t0 + ((size_t)A.nchunk << 9), 2048, &rfull[rs]);
                     }
-                    mbar_wait_relaxed(&wempty[stage], ph ^ 1);
+                    bg_wait(&wempty[stage], ph ^ 1, A.wait_mode);
                     mbar_arrive_expect_tx(&wfull[stage], tile_bytes);
                     bulk_g2s(wring + stage * tile_bytes, src + (size_t)i * tile_bytes, tile_bytes, &wfull[stage]);
                     if (++stage == BG_NW) { stage = 0; ph ^= 1; }
@@ -242,10 +272,10 @@ __global__ void __launch_bounds__(BG_THREADS, 1) bitgemm_kernel(const __grid_con
             while (w.next_seg(rt, mt, c0, n)) {
                 for (int i = 0; i < n; ++i, ++ic) {
                     const uint32_t buf = ic & 3, rs = ic % BG_NRAW;
-                    mbar_wait_relaxed(&rfull[rs], (ic / BG_NRAW) & 1);
+                    bg_wait(&rfull[rs], (ic / BG_NRAW) & 1, A.wait_mode);
                     const uint4 x = *reinterpret_cast<const uint4*>(raw + rs * BG_RAW_BYTES + tg * 16);
                     mbar_arrive(&rempty[rs]);                // the words are in registers: the tile may be refilled
-                    mbar_wait_relaxed(&aempty[buf], ((ic >> 2) & 1) ^ 1);
+                    bg_wait(&aempty[buf], ((ic >> 2) & 1) ^ 1, A.wait_mode);
                     expand(strips + buf * BG_STRIP_BYTES, x);
                     fence_proxy_async_smem();
                     mbar_arrive(&afull[buf]);
@@ -271,7 +301,7 @@ __global__ void __launch_bounds__(BG_THREADS, 1) bitgemm_kernel(const __grid_con
             while (have > 0) {
                 if (more) fetch();
                 const uint32_t buf = ic & 3;
-                mbar_wait_relaxed(&aempty[buf], ((ic >> 2) & 1) ^ 1);
+                bg_wait(&aempty[buf], ((ic >> 2) & 1) ^ 1, A.wait_mode);
                 expand(strips + buf * BG_STRIP_BYTES, x[0]);
                 fence_proxy_async_smem();
                 mbar_arrive(&afull[buf]);
@@ -293,13 +323,13 @@ __global__ void __launch_bounds__(BG_THREADS, 1) bitgemm_kernel(const __grid_con
         uint32_t ph = 0, ic = 0, seg = 0;
         while (w.next_seg(rt, mt, c0, n)) {
             const uint32_t accb = seg & 1;
-            mbar_wait(&tempty[accb], ((seg >> 1) & 1) ^ 1);
+            bg_wait(&tempty[accb], ((seg >> 1) & 1) ^ 1, A.wait_mode);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + accb * 256;
             for (int i = 0; i < n; ++i, ++ic) {
                 const uint32_t buf = ic & 3;
-                mbar_wait(&afull[buf], (ic >> 2) & 1);
-                mbar_wait(&wfull[stage], ph);
+                bg_wait(&afull[buf], (ic >> 2) & 1, A.wait_mode);
+                bg_wait(&wfull[stage], ph, A.wait_mode);
                 tc_fence_after();
                 const uint32_t abase = smem_u32(wring + stage * tile_bytes) >> 4;
                 const uint32_t bbase = smem_u32(strips + buf * BG_STRIP_BYTES) >> 4;
@@ -327,7 +357,7 @@ __global__ void __launch_bounds__(BG_THREADS, 1) bitgemm_kernel(const __grid_con
         uint32_t seg = 0;
         while (w.next_seg(rt, mt, c0, n)) {
             const uint32_t accb = seg & 1;
-            mbar_wait_relaxed(&tfull[accb], (seg >> 1) & 1);
+            bg_wait(&tfull[accb], (seg >> 1) & 1, A.wait_mode);
             tc_fence_after();
             const uint32_t taddr = tmem_base + accb * 256 + ((uint32_t)(quad * 32) << 16);
             int* out = A.acc + ((size_t)mt * A.mrp + quad * 32) * A.Rpad + (size_t)rt * 256 + lane;
@@ -464,7 +494,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) bitgemm_ts_kernel(const __grid_
             while (w.next_seg(rt, c0, n)) {
                 for (int i = 0; i < n; ++i, ++ic) {
                     const uint32_t rs = ic % TS_NRAW;
-                    mbar_wait_relaxed(&rempty[rs], ((ic / TS_NRAW) & 1) ^ 1);
+                    bg_wait(&rempty[rs], ((ic / TS_NRAW) & 1) ^ 1, A.wait_mode);
                     mbar_arrive_expect_tx(&rfull[rs], TS_RAW_BYTES);
                     bulk_g2s(raw + rs * TS_RAW_BYTES, A.tiled + (((size_t)rt * A.nchunk + (c0 + i)) << 9), TS_RAW_BYTES, &rfull[rs]);
                 }
@@ -480,7 +510,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) bitgemm_ts_kernel(const __grid_
                 const uint8_t* src = A.wblob + (size_t)c0 * tile_bytes;
                 for (int i = 0; i < n; ++i, ++ic) {
                     const uint32_t stage = ic % TS_NW;
-                    mbar_wait_relaxed(&wempty[stage], ((ic / TS_NW) & 1) ^ 1);
+                    bg_wait(&wempty[stage], ((ic / TS_NW) & 1) ^ 1, A.wait_mode);
                     mbar_arrive_expect_tx(&wfull[stage], tile_bytes);
                     bulk_g2s(wring + stage * tile_bytes, src + (size_t)i * tile_bytes, tile_bytes, &wfull[stage]);
                 }
@@ -501,10 +531,10 @@ __global__ void __launch_bounds__(TS_THREADS, 1) bitgemm_ts_kernel(const __grid_
             for (int i = 0; i < n; ++i, ++ic) {
                 if ((int)(ic & 3) != set) continue;
                 const uint32_t rs = ic % TS_NRAW, slot = ic % TS_NA;
-                mbar_wait_relaxed(&rfull[rs], (ic / TS_NRAW) & 1);
+                bg_wait(&rfull[rs], (ic / TS_NRAW) & 1, A.wait_mode);
                 const uint4 x = *reinterpret_cast<const uint4*>(raw + rs * TS_RAW_BYTES + row * 16);
                 mbar_arrive(&rempty[rs]);
-                mbar_wait_relaxed(&aempty[slot], ((ic / TS_NA) & 1) ^ 1);
+                bg_wait(&aempty[slot], ((ic / TS_NA) & 1) ^ 1, A.wait_mode);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + a_col0 + slot * 32 + ((uint32_t)(quad * 32) << 16);
                 const uint32_t wv[4] = {x.x, x.y, x.z, x.w};
@@ -533,15 +563,15 @@ __global__ void __launch_bounds__(TS_THREADS, 1) bitgemm_ts_kernel(const __grid_
         uint32_t ic = 0, seg = 0;
         while (w.next_seg(rt, c0, n)) {
             const uint32_t sp = seg & 1;
-            mbar_wait(&tempty[sp], ((seg >> 1) & 1) ^ 1);
+            bg_wait(&tempty[sp], ((seg >> 1) & 1) ^ 1, A.wait_mode);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + (sp * NIS + iss) * N;
             bool first = true;
             for (int i = 0; i < n; ++i, ++ic) {
                 if ((int)(ic % NIS) != iss) continue;
                 const uint32_t slot = ic % TS_NA, stage = ic % TS_NW;
-                mbar_wait(&afull[slot], (ic / TS_NA) & 1);
-                mbar_wait(&wfull[stage], (ic / TS_NW) & 1);
+                bg_wait(&afull[slot], (ic / TS_NA) & 1, A.wait_mode);
+                bg_wait(&wfull[stage], (ic / TS_NW) & 1, A.wait_mode);
                 tc_fence_after();
                 const uint32_t bbase = smem_u32(wring + stage * tile_bytes) >> 4;
                 const uint32_t abase = tmem_base + a_col0 + slot * 32;
@@ -573,7 +603,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) bitgemm_ts_kernel(const __grid_
                 if (n > 1) used[(ic + 1) % 2] = true;
             }
             ic += n;
-            mbar_wait_relaxed(&tfull[sp], (seg >> 1) & 1);
+            bg_wait(&tfull[sp], (seg >> 1) & 1, A.wait_mode);
             tc_fence_after();
             int* out = A.acc + (size_t)rt * 128 + quad * 32 + lane;
             for (int m0 = 0; m0 < N; m0 += 16) {
@@ -618,6 +648,7 @@ static int launch_bitgemm(const uint32_t* bits, const uint32_t* tiled, long long
     A.bits = bits; A.tiled = tiled; A.wblob = wblob; A.acc = acc; A.R = R; A.Rpad = Rpad; A.rw = rw; A.nchunk = nchunk;
     A.Mtiles = s.Mtiles; A.mrp = s.mrp; A.mrows = s.mrows; A.Rtiles = (int)(Rpad / 256); A.done = done;
     const bool raw_tma = tiled != nullptr && getenv("TSR_DEBUG_BITGEMM_LDG") == nullptr;
+    if (const char* wm = getenv("TSR_DEBUG_BG_WAIT")) A.wait_mode = atoi(wm);
     const int nsm = sm_count();
     if (raw_tma && s.Mtiles == 1 && getenv("TSR_DEBUG_BITGEMM_SS") == nullptr) {
         // all components in one M tile: bit rows as the A operand in tensor memory (bitgemm_ts_kernel)
