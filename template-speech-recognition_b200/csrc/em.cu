@@ -104,6 +104,7 @@ struct BgArgs {
     int rw, nchunk, Mtiles, mrp, mrows, Rtiles;
     int nw;                         // TS kernel: weight tiles in flight
     int wait_mode;                  // see bg_wait
+    int dbg;                        // timing experiments (wrong results): 1 no MMAs, 2 no expansion, 4 no reductions, 8 no loads
     const int* done;
 };
 
@@ -495,6 +496,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) bitgemm_ts_kernel(const __grid_
                 for (int i = 0; i < n; ++i, ++ic) {
                     const uint32_t rs = ic % TS_NRAW;
                     bg_wait(&rempty[rs], ((ic / TS_NRAW) & 1) ^ 1, A.wait_mode);
+                    if (A.dbg & 8) { mbar_arrive(&rfull[rs]); continue; }
                     mbar_arrive_expect_tx(&rfull[rs], TS_RAW_BYTES);
                     bulk_g2s(raw + rs * TS_RAW_BYTES, A.tiled + (((size_t)rt * A.nchunk + (c0 + i)) << 9), TS_RAW_BYTES, &rfull[rs]);
                 }
@@ -511,6 +513,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) bitgemm_ts_kernel(const __grid_
                 for (int i = 0; i < n; ++i, ++ic) {
                     const uint32_t stage = ic % TS_NW;
                     bg_wait(&wempty[stage], ((ic / TS_NW) & 1) ^ 1, A.wait_mode);
+                    if (A.dbg & 8) { mbar_arrive(&wfull[stage]); continue; }
                     mbar_arrive_expect_tx(&wfull[stage], tile_bytes);
                     bulk_g2s(wring + stage * tile_bytes, src + (size_t)i * tile_bytes, tile_bytes, &wfull[stage]);
                 }
@@ -540,6 +543,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) bitgemm_ts_kernel(const __grid_
                 const uint32_t wv[4] = {x.x, x.y, x.z, x.w};
 #pragma unroll
                 for (int wi = 0; wi < 4; ++wi) {
+                    if (A.dbg & 2) break;
                     uint32_t v[8];
 #pragma unroll
                     for (int s8 = 0; s8 < 8; ++s8) v[s8] = (wv[wi] >> s8) & 0x01010101u;     // K index 4 s + jj  <->  bit 8 jj + s of the word
@@ -577,7 +581,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) bitgemm_ts_kernel(const __grid_
                 const uint32_t abase = tmem_base + a_col0 + slot * 32;
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
-                    umma_i8_ts(d_tmem, abase + 8 * j, b_hi | (uint64_t)(bbase + j * kstep_b), idesc, (first && j == 0) ? 0u : 1u);
+                    if (!(A.dbg & 1)) umma_i8_ts(d_tmem, abase + 8 * j, b_hi | (uint64_t)(bbase + j * kstep_b), idesc, (first && j == 0) ? 0u : 1u);
                 first = false;
                 umma_commit_elect(&aempty[slot]);
                 umma_commit_elect(&wempty[stage]);
@@ -621,7 +625,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) bitgemm_ts_kernel(const __grid_
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
                     const int val = (int)v[i] + (int)u[i];
-                    if (m0 + i < A.mrows && val != 0) atomicAdd(out + (size_t)(m0 + i) * A.Rpad, val);
+                    if (m0 + i < A.mrows && val != 0 && !(A.dbg & 4)) atomicAdd(out + (size_t)(m0 + i) * A.Rpad, val);
                 }
             }
             ++seg;
@@ -649,6 +653,7 @@ static int launch_bitgemm(const uint32_t* bits, const uint32_t* tiled, long long
     A.Mtiles = s.Mtiles; A.mrp = s.mrp; A.mrows = s.mrows; A.Rtiles = (int)(Rpad / 256); A.done = done;
     const bool raw_tma = tiled != nullptr && getenv("TSR_DEBUG_BITGEMM_LDG") == nullptr;
     if (const char* wm = getenv("TSR_DEBUG_BG_WAIT")) A.wait_mode = atoi(wm);
+    if (const char* dm = getenv("TSR_DEBUG_BG_DBG")) A.dbg = atoi(dm);
     const int nsm = sm_count();
     if (raw_tma && s.Mtiles == 1 && getenv("TSR_DEBUG_BITGEMM_SS") == nullptr) {
         // all components in one M tile: bit rows as the A operand in tensor memory (bitgemm_ts_kernel)
