@@ -113,10 +113,17 @@ struct BgArgs {
 // suspending try_wait of common.cuh (100 us hint); 1: non-blocking test_wait polls with a short sleep; 2: try_wait with
 // a 1 us hint.
 __device__ __forceinline__ void bg_wait(uint64_t* bar, uint32_t parity, int mode) {
+    mode &= 15;
     if (mode == 0) { mbar_wait_relaxed(bar, parity); return; }
     uint32_t spins = 0, ok = 0;
     do {
-        if (mode == 1) {
+        if (mode == 3) {          // pure spin on the non-blocking test
+            asm volatile(
+                "{\n\t.reg .pred p;\n\t"
+                "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                "selp.u32 %0, 1, 0, p;\n\t}"
+                : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        } else if (mode == 1) {
             asm volatile(
                 "{\n\t.reg .pred p;\n\t"
                 "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
@@ -495,7 +502,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) bitgemm_ts_kernel(const __grid_
             while (w.next_seg(rt, c0, n)) {
                 for (int i = 0; i < n; ++i, ++ic) {
                     const uint32_t rs = ic % TS_NRAW;
-                    bg_wait(&rempty[rs], ((ic / TS_NRAW) & 1) ^ 1, A.wait_mode);
+                    bg_wait(&rempty[rs], ((ic / TS_NRAW) & 1) ^ 1, A.wait_mode >> 8);
                     if (A.dbg & 8) { mbar_arrive(&rfull[rs]); continue; }
                     mbar_arrive_expect_tx(&rfull[rs], TS_RAW_BYTES);
                     bulk_g2s(raw + rs * TS_RAW_BYTES, A.tiled + (((size_t)rt * A.nchunk + (c0 + i)) << 9), TS_RAW_BYTES, &rfull[rs]);
@@ -512,7 +519,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) bitgemm_ts_kernel(const __grid_
                 const uint8_t* src = A.wblob + (size_t)c0 * tile_bytes;
                 for (int i = 0; i < n; ++i, ++ic) {
                     const uint32_t stage = ic % TS_NW;
-                    bg_wait(&wempty[stage], ((ic / TS_NW) & 1) ^ 1, A.wait_mode);
+                    bg_wait(&wempty[stage], ((ic / TS_NW) & 1) ^ 1, A.wait_mode >> 8);
                     if (A.dbg & 8) { mbar_arrive(&wfull[stage]); continue; }
                     mbar_arrive_expect_tx(&wfull[stage], tile_bytes);
                     bulk_g2s(wring + stage * tile_bytes, src + (size_t)i * tile_bytes, tile_bytes, &wfull[stage]);
@@ -534,10 +541,10 @@ __global__ void __launch_bounds__(TS_THREADS, 1) bitgemm_ts_kernel(const __grid_
             for (int i = 0; i < n; ++i, ++ic) {
                 if ((int)(ic & 3) != set) continue;
                 const uint32_t rs = ic % TS_NRAW, slot = ic % TS_NA;
-                bg_wait(&rfull[rs], (ic / TS_NRAW) & 1, A.wait_mode);
+                bg_wait(&rfull[rs], (ic / TS_NRAW) & 1, A.wait_mode >> 4);
                 const uint4 x = *reinterpret_cast<const uint4*>(raw + rs * TS_RAW_BYTES + row * 16);
                 mbar_arrive(&rempty[rs]);
-                bg_wait(&aempty[slot], ((ic / TS_NA) & 1) ^ 1, A.wait_mode);
+                bg_wait(&aempty[slot], ((ic / TS_NA) & 1) ^ 1, A.wait_mode >> 4);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + a_col0 + slot * 32 + ((uint32_t)(quad * 32) << 16);
                 const uint32_t wv[4] = {x.x, x.y, x.z, x.w};
@@ -607,7 +614,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) bitgemm_ts_kernel(const __grid_
                 if (n > 1) used[(ic + 1) % 2] = true;
             }
             ic += n;
-            bg_wait(&tfull[sp], (seg >> 1) & 1, A.wait_mode);
+            bg_wait(&tfull[sp], (seg >> 1) & 1, A.wait_mode >> 12);
             tc_fence_after();
             int* out = A.acc + (size_t)rt * 128 + quad * 32 + lane;
             for (int m0 = 0; m0 < N; m0 += 16) {
@@ -652,7 +659,7 @@ static int launch_bitgemm(const uint32_t* bits, const uint32_t* tiled, long long
     A.bits = bits; A.tiled = tiled; A.wblob = wblob; A.acc = acc; A.R = R; A.Rpad = Rpad; A.rw = rw; A.nchunk = nchunk;
     A.Mtiles = s.Mtiles; A.mrp = s.mrp; A.mrows = s.mrows; A.Rtiles = (int)(Rpad / 256); A.done = done;
     const bool raw_tma = tiled != nullptr && getenv("TSR_DEBUG_BITGEMM_LDG") == nullptr;
-    if (const char* wm = getenv("TSR_DEBUG_BG_WAIT")) A.wait_mode = atoi(wm);
+    if (const char* wm = getenv("TSR_DEBUG_BG_WAIT")) A.wait_mode = (int)strtol(wm, nullptr, 16);      // hex: epilogue|loaders|expanders|issuers
     if (const char* dm = getenv("TSR_DEBUG_BG_DBG")) A.dbg = atoi(dm);
     const int nsm = sm_count();
     if (raw_tma && s.Mtiles == 1 && getenv("TSR_DEBUG_BITGEMM_SS") == nullptr) {
