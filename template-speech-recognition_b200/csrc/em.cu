@@ -209,9 +209,11 @@ __global__ void __launch_bounds__(BG_THREADS, 1) bitgemm_kernel(const __grid_con
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < BG_NW; ++s) { mbar_init(&wfull[s], 1); mbar_init(&wempty[s], 1); }
-        for (int s = 0; s < BG_NSTRIP; ++s) { mbar_init(&afull[s], 256); mbar_init(&aempty[s], 1); }
+        // (one arrival per expander WARP: 256 per-thread arrivals on one barrier word serialise in the shared-memory
+        // atomic unit -- with the work removed the pipeline skeleton alone took 85 % of the kernel time)
+        for (int s = 0; s < BG_NSTRIP; ++s) { mbar_init(&afull[s], 8); mbar_init(&aempty[s], 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 128); }
-        for (int s = 0; s < BG_NRAW; ++s) { mbar_init(&rfull[s], 1); mbar_init(&rempty[s], 256); }
+        for (int s = 0; s < BG_NRAW; ++s) { mbar_init(&rfull[s], 1); mbar_init(&rempty[s], 8); }
         mbar_fence_init();
     }
     if (warp == 13) tmem_alloc<512>(tmem_ptr);
@@ -282,11 +284,13 @@ __global__ void __launch_bounds__(BG_THREADS, 1) bitgemm_kernel(const __grid_con
                     const uint32_t buf = ic & 3, rs = ic % BG_NRAW;
                     bg_wait(&rfull[rs], (ic / BG_NRAW) & 1, A.wait_mode);
                     const uint4 x = *reinterpret_cast<const uint4*>(raw + rs * BG_RAW_BYTES + tg * 16);
-                    mbar_arrive(&rempty[rs]);                // the words are in registers: the tile may be refilled
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&rempty[rs]);  // the warp's words are in registers: the tile may be refilled
                     bg_wait(&aempty[buf], ((ic >> 2) & 1) ^ 1, A.wait_mode);
                     expand(strips + buf * BG_STRIP_BYTES, x);
                     fence_proxy_async_smem();
-                    mbar_arrive(&afull[buf]);
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&afull[buf]);
                 }
             }
         } else {
@@ -312,7 +316,8 @@ __global__ void __launch_bounds__(BG_THREADS, 1) bitgemm_kernel(const __grid_con
                 bg_wait(&aempty[buf], ((ic >> 2) & 1) ^ 1, A.wait_mode);
                 expand(strips + buf * BG_STRIP_BYTES, x[0]);
                 fence_proxy_async_smem();
-                mbar_arrive(&afull[buf]);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&afull[buf]);
                 ++ic;
                 x[0] = x[1]; x[1] = x[2];
                 --have;
@@ -481,8 +486,8 @@ __global__ void __launch_bounds__(TS_THREADS, 1) bitgemm_ts_kernel(const __grid_
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < TS_NW_MAX; ++s) { mbar_init(&wfull[s], 1); mbar_init(&wempty[s], 1); }
-        for (int s = 0; s < TS_NRAW; ++s) { mbar_init(&rfull[s], 1); mbar_init(&rempty[s], 128); }
-        for (int s = 0; s < TS_NA; ++s) { mbar_init(&afull[s], 128); mbar_init(&aempty[s], 1); }
+        for (int s = 0; s < TS_NRAW; ++s) { mbar_init(&rfull[s], 1); mbar_init(&rempty[s], 4); }      // one arrival per warp of a set
+        for (int s = 0; s < TS_NA; ++s) { mbar_init(&afull[s], 4); mbar_init(&aempty[s], 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], NIS); mbar_init(&tempty[s], 128); }
         mbar_fence_init();
     }
@@ -543,7 +548,8 @@ __global__ void __launch_bounds__(TS_THREADS, 1) bitgemm_ts_kernel(const __grid_
                 const uint32_t rs = ic % TS_NRAW, slot = ic % TS_NA;
                 bg_wait(&rfull[rs], (ic / TS_NRAW) & 1, A.wait_mode >> 4);
                 const uint4 x = *reinterpret_cast<const uint4*>(raw + rs * TS_RAW_BYTES + row * 16);
-                mbar_arrive(&rempty[rs]);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&rempty[rs]);
                 bg_wait(&aempty[slot], ((ic / TS_NA) & 1) ^ 1, A.wait_mode >> 4);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + a_col0 + slot * 32 + ((uint32_t)(quad * 32) << 16);
@@ -558,7 +564,8 @@ __global__ void __launch_bounds__(TS_THREADS, 1) bitgemm_ts_kernel(const __grid_
                 }
                 tmem_st_wait();
                 tc_fence_before();
-                mbar_arrive(&afull[slot]);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&afull[slot]);
             }
         }
     } else if (warp == 21 || (NIS == 2 && warp == 22)) {
