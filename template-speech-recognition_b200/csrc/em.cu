@@ -562,8 +562,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) bitgemm_ts_kernel(const __grid_
                     for (int s8 = 0; s8 < 8; ++s8) v[s8] = (wv[wi] >> s8) & 0x01010101u;     // K index 4 s + jj  <->  bit 8 jj + s of the word
                     tmem_st8(taddr + 8 * wi, v);
                 }
-                tmem_st_wait();
-                tc_fence_before();
+                if (!(A.dbg & 32)) { tmem_st_wait(); tc_fence_before(); }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&afull[slot]);
             }
@@ -597,8 +596,13 @@ __global__ void __launch_bounds__(TS_THREADS, 1) bitgemm_ts_kernel(const __grid_
                 for (int j = 0; j < 4; ++j)
                     if (!(A.dbg & 1)) umma_i8_ts(d_tmem, abase + 8 * j, b_hi | (uint64_t)(bbase + j * kstep_b), idesc, (first && j == 0) ? 0u : 1u);
                 first = false;
-                umma_commit_elect(&aempty[slot]);
-                umma_commit_elect(&wempty[stage]);
+                if (A.dbg & 16) {                    // experiment: plain arrivals instead of tcgen05.commit
+                    if (lane == 0) { mbar_arrive(&aempty[slot]); mbar_arrive(&wempty[stage]); }
+                    __syncwarp();
+                } else {
+                    umma_commit_elect(&aempty[slot]);
+                    umma_commit_elect(&wempty[stage]);
+                }
             }
             umma_commit_elect(&tfull[sp]);        // (arrives even if this issuer had no chunk in the segment)
             ++seg;
