@@ -144,6 +144,14 @@ __device__ __forceinline__ void bg_wait(uint64_t* bar, uint32_t parity, int mode
     } while (!ok);
 }
 
+// The same wait executed by ONE lane of a converged warp, the others held at __syncwarp (which also orders memory
+// among the lanes).  Every lane of a warp polling the same barrier word is 32 operations on the SM's barrier unit;
+// with ~10 waiting warps per 500-cycle chunk that unit, not the data path, set the pace of these kernels.
+__device__ __forceinline__ void bg_wait_warp(uint64_t* bar, uint32_t parity, int mode) {
+    if ((threadIdx.x & 31) == 0) bg_wait(bar, parity, mode);
+    __syncwarp();
+}
+
 // A CTA's share of the flattened (R tile, M tile, chunk) space, cut into segments at tile borders.
 struct BgWalk {
     long long pos, end, tile;
@@ -546,11 +554,11 @@ __global__ void __launch_bounds__(TS_THREADS, 1) bitgemm_ts_kernel(const __grid_
             for (int i = 0; i < n; ++i, ++ic) {
                 if ((int)(ic & 3) != set) continue;
                 const uint32_t rs = ic % TS_NRAW, slot = ic % TS_NA;
-                bg_wait(&rfull[rs], (ic / TS_NRAW) & 1, A.wait_mode >> 4);
+                bg_wait_warp(&rfull[rs], (ic / TS_NRAW) & 1, A.wait_mode >> 4);
                 const uint4 x = *reinterpret_cast<const uint4*>(raw + rs * TS_RAW_BYTES + row * 16);
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&rempty[rs]);
-                bg_wait(&aempty[slot], ((ic / TS_NA) & 1) ^ 1, A.wait_mode >> 4);
+                bg_wait_warp(&aempty[slot], ((ic / TS_NA) & 1) ^ 1, A.wait_mode >> 4);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + a_col0 + slot * 32 + ((uint32_t)(quad * 32) << 16);
                 const uint32_t wv[4] = {x.x, x.y, x.z, x.w};
@@ -580,15 +588,15 @@ __global__ void __launch_bounds__(TS_THREADS, 1) bitgemm_ts_kernel(const __grid_
         uint32_t ic = 0, seg = 0;
         while (w.next_seg(rt, c0, n)) {
             const uint32_t sp = seg & 1;
-            bg_wait(&tempty[sp], ((seg >> 1) & 1) ^ 1, A.wait_mode);
+            bg_wait_warp(&tempty[sp], ((seg >> 1) & 1) ^ 1, A.wait_mode);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + (sp * NIS + iss) * N;
             bool first = true;
             for (int i = 0; i < n; ++i, ++ic) {
                 if ((int)(ic % NIS) != iss) continue;
                 const uint32_t slot = ic % TS_NA, stage = ic % TS_NW;
-                bg_wait(&afull[slot], (ic / TS_NA) & 1, A.wait_mode);
-                bg_wait(&wfull[stage], (ic / TS_NW) & 1, A.wait_mode);
+                bg_wait_warp(&afull[slot], (ic / TS_NA) & 1, A.wait_mode);
+                bg_wait_warp(&wfull[stage], (ic / TS_NW) & 1, A.wait_mode);
                 tc_fence_after();
                 const uint32_t bbase = smem_u32(wring + stage * tile_bytes) >> 4;
                 const uint32_t abase = tmem_base + a_col0 + slot * 32;
@@ -625,7 +633,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) bitgemm_ts_kernel(const __grid_
                 if (n > 1) used[(ic + 1) % 2] = true;
             }
             ic += n;
-            bg_wait(&tfull[sp], (seg >> 1) & 1, A.wait_mode >> 12);
+            bg_wait_warp(&tfull[sp], (seg >> 1) & 1, A.wait_mode >> 12);
             tc_fence_after();
             int* out = A.acc + (size_t)rt * 128 + quad * 32 + lane;
             for (int m0 = 0; m0 < N; m0 += 16) {
