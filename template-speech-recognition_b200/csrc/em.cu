@@ -103,54 +103,8 @@ struct BgArgs {
     long long R, Rpad;
     int rw, nchunk, Mtiles, mrp, mrows, Rtiles;
     int nw;                         // TS kernel: weight tiles in flight
-    int wait_mode;                  // see bg_wait
-    int dbg;                        // timing experiments (wrong results): 1 no MMAs, 2 no expansion, 4 no reductions, 8 no loads
     const int* done;
 };
-
-// Barrier wait of the bitgemm pipelines.  A slot of these kernels holds only ~500 cycles of tensor work, so the time a
-// waiter needs to notice a completed phase is on the critical path (slots / latency = chunks per cycle).  mode 0: the
-// suspending try_wait of common.cuh (100 us hint); 1: non-blocking test_wait polls with a short sleep; 2: try_wait with
-// a 1 us hint.
-__device__ __forceinline__ void bg_wait(uint64_t* bar, uint32_t parity, int mode) {
-    mode &= 15;
-    if (mode == 0) { mbar_wait_relaxed(bar, parity); return; }
-    uint32_t spins = 0, ok = 0;
-    do {
-        if (mode == 3) {          // pure spin on the non-blocking test
-            asm volatile(
-                "{\n\t.reg .pred p;\n\t"
-                "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-                "selp.u32 %0, 1, 0, p;\n\t}"
-                : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-        } else if (mode == 1) {
-            asm volatile(
-                "{\n\t.reg .pred p;\n\t"
-                "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-                "selp.u32 %0, 1, 0, p;\n\t}"
-                : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-            if (!ok) __nanosleep(32);
-        } else {
-            asm volatile(
-                "{\n\t.reg .pred p;\n\t"
-                "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
-                "selp.u32 %0, 1, 0, p;\n\t}"
-                : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(1000u) : "memory");
-        }
-        if (!ok && ++spins > TSR_SPIN_LIMIT) {
-            printf("tsr_b200: bitgemm barrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
-            __trap();
-        }
-    } while (!ok);
-}
-
-// The same wait executed by ONE lane of a converged warp, the others held at __syncwarp (which also orders memory
-// among the lanes).  Every lane of a warp polling the same barrier word is 32 operations on the SM's barrier unit;
-// with ~10 waiting warps per 500-cycle chunk that unit, not the data path, set the pace of these kernels.
-__device__ __forceinline__ void bg_wait_warp(uint64_t* bar, uint32_t parity, int mode) {
-    if ((threadIdx.x & 31) == 0) bg_wait(bar, parity, mode);
-    __syncwarp();
-}
 
 // A CTA's share of the flattened (R tile, M tile, chunk) space, cut into segments at tile borders.
 struct BgWalk {
@@ -241,13 +195,13 @@ __global__ void __launch_bounds__(BG_THREADS, 1) bitgemm_kernel(const __grid_con
                 for (int i = 0; i < n; ++i, ++ic) {
                     if (RAW_TMA) {
                         const uint32_t rs = ic % BG_NRAW;
-                        bg_wait(&rempty[rs], ((ic / BG_NRAW) & 1) ^ 1, A.wait_mode);
+                        mbar_wait_relaxed(&rempty[rs], ((ic / BG_NRAW) & 1) ^ 1);
                         mbar_arrive_expect_tx(&rfull[rs], BG_RAW_BYTES);
                         const uint32_t* t0 = A.tiled + (((size_t)(2 * rt) * A.nchunk + (c0 + i)) << 9);       // 512 words per (tile, chunk)
                         bulk_g2s(raw + rs * BG_RAW_BYTES, t0, 2048, &rfull[rs]);
                         bulk_g2s(raw + rs * BG_RAW_BYTES + 2048, t0 + ((size_t)A.nchunk << 9), 2048, &rfull[rs]);
                     }
-                    bg_wait(&wempty[stage], ph ^ 1, A.wait_mode);
+                    mbar_wait_relaxed(&wempty[stage], ph ^ 1);
                     mbar_arrive_expect_tx(&wfull[stage], tile_bytes);
                     bulk_g2s(wring + stage * tile_bytes, src + (size_t)i * tile_bytes, tile_bytes, &wfull[stage]);
                     if (++stage == BG_NW) { stage = 0; ph ^= 1; }
@@ -290,11 +244,11 @@ __global__ void __launch_bounds__(BG_THREADS, 1) bitgemm_kernel(const __grid_con
             while (w.next_seg(rt, mt, c0, n)) {
                 for (int i = 0; i < n; ++i, ++ic) {
                     const uint32_t buf = ic & 3, rs = ic % BG_NRAW;
-                    bg_wait(&rfull[rs], (ic / BG_NRAW) & 1, A.wait_mode);
+                    mbar_wait_relaxed(&rfull[rs], (ic / BG_NRAW) & 1);
                     const uint4 x = *reinterpret_cast<const uint4*>(raw + rs * BG_RAW_BYTES + tg * 16);
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&rempty[rs]);  // the warp's words are in registers: the tile may be refilled
-                    bg_wait(&aempty[buf], ((ic >> 2) & 1) ^ 1, A.wait_mode);
+                    mbar_wait_relaxed(&aempty[buf], ((ic >> 2) & 1) ^ 1);
                     expand(strips + buf * BG_STRIP_BYTES, x);
                     fence_proxy_async_smem();
                     __syncwarp();
@@ -321,7 +275,7 @@ __global__ void __launch_bounds__(BG_THREADS, 1) bitgemm_kernel(const __grid_con
             while (have > 0) {
                 if (more) fetch();
                 const uint32_t buf = ic & 3;
-                bg_wait(&aempty[buf], ((ic >> 2) & 1) ^ 1, A.wait_mode);
+                mbar_wait_relaxed(&aempty[buf], ((ic >> 2) & 1) ^ 1);
                 expand(strips + buf * BG_STRIP_BYTES, x[0]);
                 fence_proxy_async_smem();
                 __syncwarp();
@@ -344,13 +298,13 @@ __global__ void __launch_bounds__(BG_THREADS, 1) bitgemm_kernel(const __grid_con
         uint32_t ph = 0, ic = 0, seg = 0;
         while (w.next_seg(rt, mt, c0, n)) {
             const uint32_t accb = seg & 1;
-            bg_wait(&tempty[accb], ((seg >> 1) & 1) ^ 1, A.wait_mode);
+            mbar_wait(&tempty[accb], ((seg >> 1) & 1) ^ 1);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + accb * 256;
             for (int i = 0; i < n; ++i, ++ic) {
                 const uint32_t buf = ic & 3;
-                bg_wait(&afull[buf], (ic >> 2) & 1, A.wait_mode);
-                bg_wait(&wfull[stage], ph, A.wait_mode);
+                mbar_wait(&afull[buf], (ic >> 2) & 1);
+                mbar_wait(&wfull[stage], ph);
                 tc_fence_after();
                 const uint32_t abase = smem_u32(wring + stage * tile_bytes) >> 4;
                 const uint32_t bbase = smem_u32(strips + buf * BG_STRIP_BYTES) >> 4;
@@ -378,7 +332,7 @@ __global__ void __launch_bounds__(BG_THREADS, 1) bitgemm_kernel(const __grid_con
         uint32_t seg = 0;
         while (w.next_seg(rt, mt, c0, n)) {
             const uint32_t accb = seg & 1;
-            bg_wait(&tfull[accb], (seg >> 1) & 1, A.wait_mode);
+            mbar_wait_relaxed(&tfull[accb], (seg >> 1) & 1);
             tc_fence_after();
             const uint32_t taddr = tmem_base + accb * 256 + ((uint32_t)(quad * 32) << 16);
             int* out = A.acc + ((size_t)mt * A.mrp + quad * 32) * A.Rpad + (size_t)rt * 256 + lane;
@@ -425,9 +379,9 @@ __global__ void __launch_bounds__(BG_THREADS, 1) bitgemm_kernel(const __grid_con
 // int8 weight tile (N rows x 32 B per MMA) from shared memory.  One MMA is M = 128 x N = mrp x K = 32, i.e. short
 // (N / 2 cycles), so with mrp <= 64 two issuer warps take alternate chunks into their own accumulators.
 // Used when all components fit one M tile (K <= 42) and the rows can be fetched by TMA; otherwise the SS kernel runs.
-//   TMEM columns: [0, 2 * NIS * mrp) accumulators (segment parity, issuer); [256, 512) ring of 8 A chunks x 32 columns.
+//   TMEM columns: [0, 2 * NIS * mrp) accumulators (segment parity, issuer); the rest a ring of A chunks x 32 columns.
 #define TS_THREADS 768               // warp 0 raw-tile loader, 1-16 expanders, 17-20 epilogue, 21-22 MMA issuers, 23 weight-tile loader
-#define TS_NA 8                      // A chunks in flight in TMEM
+#define TS_NA_MAX 16                 // A chunks in flight in TMEM: every 32-column slot the accumulators leave free (10 at K = 16)
 #define TS_NRAW 16                   // raw bit tiles in flight: a chunk lasts ~200 cycles, a TMA round trip ~2000-3000
 #define TS_RAW_BYTES 2048            // 128 rows x 16 B
 #define TS_NW_MAX 16                 // weight tiles in flight (as many as fit 144 KB)
@@ -483,9 +437,9 @@ __global__ void __launch_bounds__(TS_THREADS, 1) bitgemm_ts_kernel(const __grid_
     uint64_t* wempty = wfull + TS_NW_MAX;
     uint64_t* rfull = wempty + TS_NW_MAX;
     uint64_t* rempty = rfull + TS_NRAW;
-    uint64_t* afull = rempty + TS_NRAW;          // [TS_NA]
-    uint64_t* aempty = afull + TS_NA;            // [TS_NA]
-    uint64_t* tfull = aempty + TS_NA;            // [2]
+    uint64_t* afull = rempty + TS_NRAW;          // [TS_NA_MAX]
+    uint64_t* aempty = afull + TS_NA_MAX;        // [TS_NA_MAX]
+    uint64_t* tfull = aempty + TS_NA_MAX;        // [2]
     uint64_t* tempty = tfull + 2;                // [2]
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty + 2);
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
@@ -495,7 +449,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) bitgemm_ts_kernel(const __grid_
     if (threadIdx.x == 0) {
         for (int s = 0; s < TS_NW_MAX; ++s) { mbar_init(&wfull[s], 1); mbar_init(&wempty[s], 1); }
         for (int s = 0; s < TS_NRAW; ++s) { mbar_init(&rfull[s], 1); mbar_init(&rempty[s], 4); }      // one arrival per warp of a set
-        for (int s = 0; s < TS_NA; ++s) { mbar_init(&afull[s], 4); mbar_init(&aempty[s], 1); }
+        for (int s = 0; s < TS_NA_MAX; ++s) { mbar_init(&afull[s], 4); mbar_init(&aempty[s], 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], NIS); mbar_init(&tempty[s], 128); }
         mbar_fence_init();
     }
@@ -504,7 +458,8 @@ __global__ void __launch_bounds__(TS_THREADS, 1) bitgemm_ts_kernel(const __grid_
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
-    const uint32_t a_col0 = 256;
+    const uint32_t a_col0 = (uint32_t)(2 * NIS * N + 31) & ~31u;      // first column of the A ring
+    const uint32_t TS_NA = (512u - a_col0) / 32u < TS_NA_MAX ? (512u - a_col0) / 32u : TS_NA_MAX;
 
     if (warp == 0) {
         // raw bit tiles: one 2 KB bulk copy (128 rows x 16 B, contiguous in the tiled matrix) per chunk
@@ -515,8 +470,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) bitgemm_ts_kernel(const __grid_
             while (w.next_seg(rt, c0, n)) {
                 for (int i = 0; i < n; ++i, ++ic) {
                     const uint32_t rs = ic % TS_NRAW;
-                    bg_wait(&rempty[rs], ((ic / TS_NRAW) & 1) ^ 1, A.wait_mode >> 8);
-                    if (A.dbg & 8) { mbar_arrive(&rfull[rs]); continue; }
+                    mbar_wait_relaxed(&rempty[rs], ((ic / TS_NRAW) & 1) ^ 1);
                     mbar_arrive_expect_tx(&rfull[rs], TS_RAW_BYTES);
                     bulk_g2s(raw + rs * TS_RAW_BYTES, A.tiled + (((size_t)rt * A.nchunk + (c0 + i)) << 9), TS_RAW_BYTES, &rfull[rs]);
                 }
@@ -532,8 +486,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) bitgemm_ts_kernel(const __grid_
                 const uint8_t* src = A.wblob + (size_t)c0 * tile_bytes;
                 for (int i = 0; i < n; ++i, ++ic) {
                     const uint32_t stage = ic % TS_NW;
-                    bg_wait(&wempty[stage], ((ic / TS_NW) & 1) ^ 1, A.wait_mode >> 8);
-                    if (A.dbg & 8) { mbar_arrive(&wfull[stage]); continue; }
+                    mbar_wait_relaxed(&wempty[stage], ((ic / TS_NW) & 1) ^ 1);
                     mbar_arrive_expect_tx(&wfull[stage], tile_bytes);
                     bulk_g2s(wring + stage * tile_bytes, src + (size_t)i * tile_bytes, tile_bytes, &wfull[stage]);
                 }
@@ -554,23 +507,23 @@ __global__ void __launch_bounds__(TS_THREADS, 1) bitgemm_ts_kernel(const __grid_
             for (int i = 0; i < n; ++i, ++ic) {
                 if ((int)(ic & 3) != set) continue;
                 const uint32_t rs = ic % TS_NRAW, slot = ic % TS_NA;
-                bg_wait_warp(&rfull[rs], (ic / TS_NRAW) & 1, A.wait_mode >> 4);
+                mbar_wait_relaxed(&rfull[rs], (ic / TS_NRAW) & 1);
                 const uint4 x = *reinterpret_cast<const uint4*>(raw + rs * TS_RAW_BYTES + row * 16);
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&rempty[rs]);
-                bg_wait_warp(&aempty[slot], ((ic / TS_NA) & 1) ^ 1, A.wait_mode >> 4);
+                mbar_wait_relaxed(&aempty[slot], ((ic / TS_NA) & 1) ^ 1);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + a_col0 + slot * 32 + ((uint32_t)(quad * 32) << 16);
                 const uint32_t wv[4] = {x.x, x.y, x.z, x.w};
 #pragma unroll
                 for (int wi = 0; wi < 4; ++wi) {
-                    if (A.dbg & 2) break;
                     uint32_t v[8];
 #pragma unroll
                     for (int s8 = 0; s8 < 8; ++s8) v[s8] = (wv[wi] >> s8) & 0x01010101u;     // K index 4 s + jj  <->  bit 8 jj + s of the word
                     tmem_st8(taddr + 8 * wi, v);
                 }
-                if (!(A.dbg & 32)) { tmem_st_wait(); tc_fence_before(); }
+                tmem_st_wait();
+                tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&afull[slot]);
             }
@@ -588,29 +541,24 @@ __global__ void __launch_bounds__(TS_THREADS, 1) bitgemm_ts_kernel(const __grid_
         uint32_t ic = 0, seg = 0;
         while (w.next_seg(rt, c0, n)) {
             const uint32_t sp = seg & 1;
-            bg_wait_warp(&tempty[sp], ((seg >> 1) & 1) ^ 1, A.wait_mode);
+            mbar_wait(&tempty[sp], ((seg >> 1) & 1) ^ 1);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + (sp * NIS + iss) * N;
             bool first = true;
             for (int i = 0; i < n; ++i, ++ic) {
                 if ((int)(ic % NIS) != iss) continue;
                 const uint32_t slot = ic % TS_NA, stage = ic % TS_NW;
-                bg_wait_warp(&afull[slot], (ic / TS_NA) & 1, A.wait_mode);
-                bg_wait_warp(&wfull[stage], (ic / TS_NW) & 1, A.wait_mode);
+                mbar_wait(&afull[slot], (ic / TS_NA) & 1);
+                mbar_wait(&wfull[stage], (ic / TS_NW) & 1);
                 tc_fence_after();
                 const uint32_t bbase = smem_u32(wring + stage * tile_bytes) >> 4;
                 const uint32_t abase = tmem_base + a_col0 + slot * 32;
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
-                    if (!(A.dbg & 1)) umma_i8_ts(d_tmem, abase + 8 * j, b_hi | (uint64_t)(bbase + j * kstep_b), idesc, (first && j == 0) ? 0u : 1u);
+                    umma_i8_ts(d_tmem, abase + 8 * j, b_hi | (uint64_t)(bbase + j * kstep_b), idesc, (first && j == 0) ? 0u : 1u);
                 first = false;
-                if (A.dbg & 16) {                    // experiment: plain arrivals instead of tcgen05.commit
-                    if (lane == 0) { mbar_arrive(&aempty[slot]); mbar_arrive(&wempty[stage]); }
-                    __syncwarp();
-                } else {
-                    umma_commit_elect(&aempty[slot]);
-                    umma_commit_elect(&wempty[stage]);
-                }
+                umma_commit_elect(&aempty[slot]);
+                umma_commit_elect(&wempty[stage]);
             }
             umma_commit_elect(&tfull[sp]);        // (arrives even if this issuer had no chunk in the segment)
             ++seg;
@@ -633,7 +581,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) bitgemm_ts_kernel(const __grid_
                 if (n > 1) used[(ic + 1) % 2] = true;
             }
             ic += n;
-            bg_wait_warp(&tfull[sp], (seg >> 1) & 1, A.wait_mode >> 12);
+            mbar_wait_relaxed(&tfull[sp], (seg >> 1) & 1);
             tc_fence_after();
             int* out = A.acc + (size_t)rt * 128 + quad * 32 + lane;
             for (int m0 = 0; m0 < N; m0 += 16) {
@@ -651,7 +599,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) bitgemm_ts_kernel(const __grid_
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
                     const int val = (int)v[i] + (int)u[i];
-                    if (m0 + i < A.mrows && val != 0 && !(A.dbg & 4)) atomicAdd(out + (size_t)(m0 + i) * A.Rpad, val);
+                    if (m0 + i < A.mrows && val != 0) atomicAdd(out + (size_t)(m0 + i) * A.Rpad, val);
                 }
             }
             ++seg;
@@ -678,15 +626,13 @@ static int launch_bitgemm(const uint32_t* bits, const uint32_t* tiled, long long
     A.bits = bits; A.tiled = tiled; A.wblob = wblob; A.acc = acc; A.R = R; A.Rpad = Rpad; A.rw = rw; A.nchunk = nchunk;
     A.Mtiles = s.Mtiles; A.mrp = s.mrp; A.mrows = s.mrows; A.Rtiles = (int)(Rpad / 256); A.done = done;
     const bool raw_tma = tiled != nullptr && getenv("TSR_DEBUG_BITGEMM_LDG") == nullptr;
-    if (const char* wm = getenv("TSR_DEBUG_BG_WAIT")) A.wait_mode = (int)strtol(wm, nullptr, 16);      // hex: epilogue|loaders|expanders|issuers
-    if (const char* dm = getenv("TSR_DEBUG_BG_DBG")) A.dbg = atoi(dm);
     const int nsm = sm_count();
     if (raw_tma && s.Mtiles == 1 && getenv("TSR_DEBUG_BITGEMM_SS") == nullptr) {
         // all components in one M tile: bit rows as the A operand in tensor memory (bitgemm_ts_kernel)
         size_t nw = (size_t)(144 * 1024) / s.tile_bytes;
         if (nw > TS_NW_MAX) nw = TS_NW_MAX;
         A.nw = (int)nw;
-        const size_t tsmem = nw * s.tile_bytes + TS_NRAW * TS_RAW_BYTES + 1024;
+        const size_t tsmem = nw * s.tile_bytes + TS_NRAW * TS_RAW_BYTES + 1280;
         const long long ttotal = (Rpad / 128) * nchunk;
         const int tgrid = (int)(ttotal < nsm ? ttotal : nsm);
         if (tgrid < 1) return TSR_OK;
