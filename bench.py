@@ -528,10 +528,13 @@ def em_bench(ctx, args, steps, warmup):
     ctl = ops.EmControl(dev, 0.0, 0, 10**9, 10**9, 64)          # never stops: every queued iteration runs
     drv._estep(False, 0, ctl, False)
 
+    graph = drv.capture_iteration(False, 0, ctl, 0.05)        # what run_EM replays; None -> eager launches
+
     def step():
-        eng.control_step(ctl)
-        eng.finalize(eng.stats, N, 0.05, drv.params, ctl=ctl)
-        drv._estep(False, 0, ctl, True)
+        if graph is not None:
+            graph.replay()
+        else:
+            drv._iteration(False, 0, ctl, 0.05)
     ms = _timed(torch, dist, world, dev, step, steps, warmup)
     done, iters, trace = ctl.read()
     # the pieces, each timed alone (events around `steps` back-to-back calls)
@@ -548,14 +551,14 @@ def em_bench(ctx, args, steps, warmup):
            "dtype": "u8 {0,1} x int8 (3 base-256 digit planes) -> int32 exact; float64 statistics",
            "config": {"workload": "config4 bernoulli_em", "N": N, "D": D, "K": K, "rows_per_gpu": hi - lo,
                       "allreduce_bytes": int(eng.stats.numel() * 8), "allreduces_per_iter": 1 if world > 1 else 0,
-                      "host_syncs_per_iter": 0},
+                      "host_syncs_per_iter": 0, "cuda_graph": graph is not None},
            "roofline": {"kernel": "bitgemm_kernel (E and M contractions)", "bound": "hbm", "achieved": xbytes / (ms * 1e-3) / 1e9,
                         "peak": peaks["hbm"], "unit": "GB/s", "frac": xbytes / (ms * 1e-3) / 1e9 / peaks["hbm"], "traffic": None,
                         "note": "algorithmic bytes = the bit-packed rows read once by the E contraction and once (transposed copy) by the M "
                                 "contraction per iteration (SURVEY 8(d) counts one fused read: halve for that figure); 4*N*D*K flop/iter = "
                                 "%.3g on %d-column operands keeps the tensor pipe, not HBM, the practical bound" % (4.0 * N * D * K, 3 * K),
                         "algorithmic_tflops": 4.0 * (hi - lo) * D * K / (ms * 1e-3) / 1e12},
-           "loglik": trace[-1] if trace else None, "iterations_run": iters, "gpu_launches_per_iter": 7}
+           "loglik": trace[-1] if trace else None, "iterations_run": iters, "gpu_launches_per_iter": 10}
     out.update(parts)
     if world == 1 and rank == 0 and not args.no_cpu:
         out["cpu_baseline"] = em_cpu_baseline(D, K, N)

@@ -48,6 +48,7 @@ class GpuEmEngine:
                 X[s:s + blk.shape[0]] = ops.pack_features(d)[0]
         self.state = ops.EmState(X, D, K)
         self.N, self.D, self.K = n, D, K
+        self.graph_ok = True                    # every launch of an iteration is stream ordered and capturable
 
     def new_params(self):
         z = lambda *s: torch.zeros(s, dtype=torch.float32, device=self.device)  # noqa: E731
@@ -127,17 +128,46 @@ class EmDriver:
         """Finalise templates / weights from the reduced statistics (identical on every rank)."""
         self.e.finalize(self.e.stats, self.N_total, float(min_prob), self.params)
 
+    def _iteration(self, hard, impl, ctl, min_prob):
+        """One queued EM iteration: stopping rule, M-step proper, E-step, M accumulation, allreduce (no host sync)."""
+        e = self.e
+        e.control_step(ctl)                                     # continue? (:144)  -- every rank sees the same reduced value
+        e.finalize(e.stats, self.N_total, float(min_prob), self.params, ctl=ctl)    # M-step (:150)
+        self._estep(hard, impl, ctl, True)                      # E-step (:152)
+
+    def capture_iteration(self, hard, impl, ctl, min_prob):
+        """The ~11 launches (and the allreduce) of an iteration as ONE CUDA graph, or None when the engine cannot be
+        captured: at 0.3 ms of GPU work per iteration the per-launch host cost would otherwise set the pace."""
+        import os
+        if not getattr(self.e, "graph_ok", False) or os.environ.get("TSR_EM_NO_GRAPH"):
+            return None
+        try:
+            side = torch.cuda.Stream(device=self.e.device)
+            side.wait_stream(torch.cuda.current_stream(self.e.device))
+            with torch.cuda.stream(side):
+                self._iteration(hard, impl, ctl, min_prob)      # warm-up on the capture stream (a real iteration)
+            torch.cuda.current_stream(self.e.device).wait_stream(side)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=side):
+                self._iteration(hard, impl, ctl, min_prob)
+            return g
+        except Exception:  # noqa: BLE001 -- e.g. a collective that cannot be captured: fall back to eager launches
+            torch.cuda.synchronize()
+            return None
+
     def run(self, tol, mode="relative", min_iter=10, max_iter=500, hard=False, min_prob=0.05, batch=8, impl=0):
         """The EM loop of run_EM (bernoulli_mixture.py:135-156; mode "absolute": bernoulli_em.py:22-34) with the
         stopping rule evaluated on the device.  Returns (iterations, log-likelihood trace)."""
         e = self.e
         ctl = e.control_init(float(tol), 0 if mode == "relative" else 1, int(min_iter), int(max_iter))
         self._estep(hard, impl, ctl, False)                         # first E-step (:135)
+        graph = self.capture_iteration(hard, impl, ctl, min_prob)   # (runs one real iteration while warming up)
         while True:
             for _ in range(max(1, int(batch))):
-                e.control_step(ctl)                                 # continue? (:144)  -- every rank sees the same reduced value
-                e.finalize(e.stats, self.N_total, float(min_prob), self.params, ctl=ctl)    # M-step (:150)
-                self._estep(hard, impl, ctl, True)                  # E-step (:152)
+                if graph is not None:
+                    graph.replay()
+                else:
+                    self._iteration(hard, impl, ctl, min_prob)
             done, iterations, trace = e.control_read(ctl)           # one host synchronisation per batch
             if done:
                 return iterations, trace
