@@ -78,27 +78,31 @@ __host__ __device__ inline FilterLayout filter_layout(int M, int L, int D, int p
     // consecutive frames into K divides the number of (row, column) products the epilogue has to
     // diagonal-sum by `fold` at identical MMA work.  Pick the fold that fills the N tiles best;
     // ties go to the larger fold.
-    int best_fold = 1;
+    int best_fold = 1, best_cap = DT_NT_MAX;
     if (f.kind) {
         double best = -1.0;
-        for (int fo = 1; fo <= L; ++fo) {
-            const int Lf = (L + fo - 1) / fo;
-            if (f.vpt * Lf > DT_NT_MAX) continue;
-            int tp = (DT_NT_MAX / (f.vpt * Lf)) * f.vpt;
-            if (tp > M * f.vpt) tp = M * f.vpt;
-            const int NT = (tp * Lf + 15) & ~15;
-            const int nt = (M * f.vpt + tp - 1) / tp;
-            double eff = (double)(M * f.vpt) * L / fo / ((double)nt * NT);    // useful columns / issued columns
-            eff *= NT >= 208 ? 1.0 : (double)NT / 208.0;                        // small-N MMAs are issue bound
-            eff /= 1.0 + 0.65 / fo;                                             // epilogue ~0.65x the MMA time unfolded
-            if (eff >= best - 1e-9) { best = eff; best_fold = fo; }
-        }
+        // N-tile caps: 240 carries 15-column groups (3 planes x 5 folded frames) without waste; 256 = the widest UMMA N,
+        // which 8-column groups (2 planes x 4 folded frames) fill exactly -- 32 templates in ONE tile; taken only for a
+        // clear gain (it leaves less shared memory for the filter-tile ring)
+        for (int cap = DT_NT_MAX; cap <= 256; cap += 16)
+            for (int fo = 1; fo <= L; ++fo) {
+                const int Lf = (L + fo - 1) / fo;
+                if (f.vpt * Lf > cap) continue;
+                int tp = (cap / (f.vpt * Lf)) * f.vpt;
+                if (tp > M * f.vpt) tp = M * f.vpt;
+                const int NT = (tp * Lf + 15) & ~15;
+                const int nt = (M * f.vpt + tp - 1) / tp;
+                double eff = (double)(M * f.vpt) * L / fo / ((double)nt * NT);    // useful columns / issued columns
+                eff *= NT >= 208 ? 1.0 : (double)NT / 208.0;                        // small-N MMAs are issue bound
+                eff /= 1.0 + 0.65 / fo;                                             // epilogue ~0.65x the MMA time unfolded
+                if (eff > best * 1.02 || (cap == best_cap && eff >= best - 1e-9)) { best = eff; best_fold = fo; best_cap = cap; }
+            }
     }
-#ifndef __CUDA_ARCH__
+#if !defined(__CUDA_ARCH__) && defined(TSR_DEBUG_TRACE)
     if (f.kind)   // experiments only: force the fold (must be the same when the filters are prepared and when they are used)
         if (const char* ov = getenv("TSR_DEBUG_DETECT_FOLD")) {
             const int fo = atoi(ov);
-            if (fo >= 1 && fo <= L && f.vpt * ((L + fo - 1) / fo) <= DT_NT_MAX) best_fold = fo;
+            if (fo >= 1 && fo <= L && f.vpt * ((L + fo - 1) / fo) <= DT_NT_MAX) { best_fold = fo; best_cap = DT_NT_MAX; }
         }
 #endif
     f.fold = best_fold;
@@ -107,7 +111,7 @@ __host__ __device__ inline FilterLayout filter_layout(int M, int L, int D, int p
     f.Kf = f.fold * f.rowwords * 32;
     // I8 contraction order: (frame chunk cf, phase phi, 64-feature half) -- one expanded A strip per cf
     f.nchunks = f.kind ? f.ncf * f.fold * 2 : (f.Kf + f.fps - 1) / f.fps;
-    int tptv = (DT_NT_MAX / (f.vpt * f.Lf)) * f.vpt;
+    int tptv = (best_cap / (f.vpt * f.Lf)) * f.vpt;
     if (tptv < f.vpt) tptv = f.vpt;
     if (tptv > M * f.vpt) tptv = M * f.vpt;
     int msub_cap = DT_MSUB_MAX;

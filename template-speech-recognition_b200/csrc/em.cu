@@ -1253,19 +1253,17 @@ __global__ void em_tail_kernel(EmSmall S, int K, double* __restrict__ stats_tail
 }
 
 // int32 digit-plane accumulators of the M-step -> float64 numerators; clears the accumulators
-__global__ void em_pack_kernel(int* __restrict__ accM, int D, int Dpad, int K, int KT, int mrp, const double* __restrict__ sk,
-                               double* __restrict__ stats, const int* done) {
+__global__ void __launch_bounds__(256) em_pack_kernel(int* __restrict__ accM, int D, int Dpad, int K, int KT, int mrp,
+                                                      const double* __restrict__ sk, double* __restrict__ stats, const int* done) {
     if (done && *done) return;
-    const long long total = (long long)K * D;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int k = (int)(i / D), d = (int)(i - (long long)k * D);
-        const int mt = k / KT, kl = k - mt * KT;
-        int* a = accM + ((size_t)mt * mrp + kl) * Dpad + d;
-        const size_t ps = (size_t)KT * Dpad;
-        const long long q = (long long)a[0] + 256LL * (long long)a[ps] + 65536LL * (long long)a[2 * ps];
-        a[0] = 0; a[ps] = 0; a[2 * ps] = 0;
-        stats[i] = (double)q / (double)EM_QMAX * __ldg(sk + k);   // division first: exact for multiples of EM_QMAX
-    }
+    const int k = blockIdx.y, d = blockIdx.x * 256 + threadIdx.x;       // grid = (ceil(D / 256), K): no index divisions
+    if (d >= D) return;
+    const int mt = k / KT, kl = k - mt * KT;
+    int* a = accM + ((size_t)mt * mrp + kl) * Dpad + d;
+    const size_t ps = (size_t)KT * Dpad;
+    const long long q = (long long)a[0] + 256LL * (long long)a[ps] + 65536LL * (long long)a[2 * ps];
+    a[0] = 0; a[ps] = 0; a[2 * ps] = 0;
+    stats[(size_t)k * D + d] = (double)q / (double)EM_QMAX * __ldg(sk + k);   // division first: exact for multiples of EM_QMAX
 }
 
 __global__ void em_empty_tail_kernel(double* stats_tail, int n, const int* done) {
@@ -1510,10 +1508,8 @@ int tsr_em_mstep(const uint32_t* Xbits, const uint32_t* XTbits_or_null, const ui
     rc = launch_bitgemm(XTbits_or_null, XTtiled_or_null, D, (int)(s.Npad / 32), ws + s.off_ablob, (int*)(ws + s.off_accM), s.Dpad,
                         (int)s.nchunkM, s, done, st);
     if (rc) return rc;
-    long long blocks = ((long long)K * D + 255) / 256;
-    const long long cap = (long long)sm_count() * 8;
-    if (blocks > cap) blocks = cap;
-    em_pack_kernel<<<(unsigned)blocks, 256, 0, st>>>((int*)(ws + s.off_accM), D, s.Dpad, K, s.KT, s.mrp, sm.sk, stats, done);
+    em_pack_kernel<<<dim3((unsigned)((D + 255) / 256), (unsigned)K), 256, 0, st>>>((int*)(ws + s.off_accM), D, s.Dpad, K, s.KT, s.mrp, sm.sk,
+                                                                                   stats, done);
     return check_launch("tsr_em_mstep(pack)");
 }
 
