@@ -34,6 +34,9 @@ namespace tsr {
 #define DT_THREADS 480     // 15 warps: <= 136 registers per thread
 #define DT_PRODUCERS 256   // two groups of 128 expander threads
 #define DT_TAU_CHUNK 40    // diagonal sums are staged through smem in chunks of <= 40 filter frames
+#define DT_TN_MAX_STAGES 8  // TN kernel: ring of 16 KB filter-tile pairs
+#define DT_TN_STEP_MAX 256 // TN kernel: frames per step (UMMA N)
+#define DT_TN_MAX_CARRY 96 // TN kernel: unfinished frames carried between steps (fold * (Lf - 1))
 #define DT_NT_MAX 240      // widest N tile: tcgen05.mma issue costs ~100 cycles, so each MMA should carry >= that much work
 
 // Operand kinds.  F16: hi+lo 16-bit float planes accumulate into the same fp32 TMEM columns.
@@ -43,7 +46,7 @@ namespace tsr {
 // integer, and the planes are recombined and scaled once per output value.
 struct FilterLayout {
     int M, L, D, rowwords, nchunks;
-    int kind;     // 0 = F16 planes, 1 = I8 planes
+    int kind;     // 0 = F16 planes, 1 = I8 planes (detect_tc_kernel), 2 = I8 planes in the TN layout (detect_tn_kernel)
     int P;        // planes (2 for F16; 2 or 3 for I8)
     int vpt;      // column groups per template: P for I8, 1 for F16
     int tptv;     // column groups ("virtual templates") per N tile, a multiple of vpt
@@ -67,42 +70,72 @@ __host__ __device__ inline FilterLayout filter_layout(int M, int L, int D, int p
     FilterLayout f;
     f.M = M; f.L = L; f.D = D;
     f.rowwords = ((D + 63) / 64) * 2;
-    f.kind = (planes == TSR_PLANES_INT8X2 || planes == TSR_PLANES_INT8X3) ? 1 : 0;
+    f.kind = planes == TSR_PLANES_INT8X2 ? 2 : (planes == TSR_PLANES_INT8X3 ? 1 : 0);
     f.P = planes == TSR_PLANES_INT8X3 ? 3 : 2;
     f.vpt = f.kind ? f.P : 1;
     f.fps = 64;
     f.ncf = (f.rowwords * 32 + 127) / 128;
     f.strip_rows = f.kgs = 0;
     f.hdr_bytes = 128 + (((size_t)M * 4 + 127) & ~(size_t)127);
+    if (f.kind == 2) {
+        // TN layout (detect_tn_kernel): the filter columns are the UMMA *M* operand -- tiles of 128 columns = 128 / Lf
+        // groups -- and the frames the N operand (<= 256 per step).  Lf is a power of two <= 8 so that the diagonal sum
+        // over a group's Lf columns is a butterfly over adjacent TMEM lanes.  MMA work ~ ntiles * fold; near-ties go to
+        // the smaller Lf (fewer tiles re-reading the frame bits, longer-lived A strips, shorter epilogue).
+        double best = -1.0;
+        int bestLf = 1;
+        for (int Lf = 1; Lf <= 8; Lf *= 2) {
+            const int fo = (L + Lf - 1) / Lf;
+            if (fo * (Lf - 1) > DT_TN_MAX_CARRY) continue;
+            const int tp = 128 / Lf;
+            const int nt = (M * 2 + tp - 1) / tp;
+            const double cost = (double)nt * fo * (1.0 + 0.01 * Lf);
+            if (best < 0 || cost < best * 0.97) { best = cost; bestLf = Lf; }
+        }
+        f.Lf = bestLf;
+        f.fold = (L + f.Lf - 1) / f.Lf;
+        f.Lc = f.fold * (f.Lf - 1);
+        f.Kf = f.fold * f.rowwords * 32;
+        f.nchunks = f.ncf * f.fold * 2;
+        f.tptv = 128 / f.Lf;
+        if (f.tptv > M * 2) f.tptv = M * 2;
+        f.NT = 128;
+        f.ntiles = (M * 2 + f.tptv - 1) / f.tptv;
+        f.msub = 1;
+        f.tile_bytes = 128 * 64;
+        f.strip_rows = (DT_TN_STEP_MAX + f.fold - 1 + 7) & ~7;
+        f.kgs = f.strip_rows * 16;
+        const long long rest = 227 * 1024 - 1024 - 2LL * 8 * f.kgs - (long long)f.Lc * 128 * 4;
+        int ns = (int)(rest / (2 * (long long)f.tile_bytes));      // a ring stage = the two 64-feature tiles of one phase
+        f.nstage = ns > DT_TN_MAX_STAGES ? DT_TN_MAX_STAGES : (ns < 2 ? 2 : ns);
+        f.total = f.hdr_bytes + (size_t)f.ntiles * f.nchunks * f.tile_bytes;
+        return f;
+    }
     // Frame folding (I8 only: integer accumulation is exact however long the chain).  Folding `fold`
     // consecutive frames into K divides the number of (row, column) products the epilogue has to
     // diagonal-sum by `fold` at identical MMA work.  Pick the fold that fills the N tiles best;
     // ties go to the larger fold.
-    int best_fold = 1, best_cap = DT_NT_MAX;
+    int best_fold = 1;
     if (f.kind) {
         double best = -1.0;
-        // N-tile caps: 240 carries 15-column groups (3 planes x 5 folded frames) without waste; 256 = the widest UMMA N,
-        // which 8-column groups (2 planes x 4 folded frames) fill exactly -- 32 templates in ONE tile; taken only for a
-        // clear gain (it leaves less shared memory for the filter-tile ring)
-        for (int cap = DT_NT_MAX; cap <= 256; cap += 16)
-            for (int fo = 1; fo <= L; ++fo) {
-                const int Lf = (L + fo - 1) / fo;
-                if (f.vpt * Lf > cap) continue;
-                int tp = (cap / (f.vpt * Lf)) * f.vpt;
-                if (tp > M * f.vpt) tp = M * f.vpt;
-                const int NT = (tp * Lf + 15) & ~15;
-                const int nt = (M * f.vpt + tp - 1) / tp;
-                double eff = (double)(M * f.vpt) * L / fo / ((double)nt * NT);    // useful columns / issued columns
-                eff *= NT >= 208 ? 1.0 : (double)NT / 208.0;                        // small-N MMAs are issue bound
-                eff /= 1.0 + 0.65 / fo;                                             // epilogue ~0.65x the MMA time unfolded
-                if (eff > best * 1.02 || (cap == best_cap && eff >= best - 1e-9)) { best = eff; best_fold = fo; best_cap = cap; }
-            }
+        for (int fo = 1; fo <= L; ++fo) {
+            const int Lf = (L + fo - 1) / fo;
+            if (f.vpt * Lf > DT_NT_MAX) continue;
+            int tp = (DT_NT_MAX / (f.vpt * Lf)) * f.vpt;
+            if (tp > M * f.vpt) tp = M * f.vpt;
+            const int NT = (tp * Lf + 15) & ~15;
+            const int nt = (M * f.vpt + tp - 1) / tp;
+            double eff = (double)(M * f.vpt) * L / fo / ((double)nt * NT);    // useful columns / issued columns
+            eff *= NT >= 208 ? 1.0 : (double)NT / 208.0;                        // small-N MMAs are issue bound
+            eff /= 1.0 + 0.65 / fo;                                             // epilogue ~0.65x the MMA time unfolded
+            if (eff >= best - 1e-9) { best = eff; best_fold = fo; }
+        }
     }
 #if !defined(__CUDA_ARCH__) && defined(TSR_DEBUG_TRACE)
     if (f.kind)   // experiments only: force the fold (must be the same when the filters are prepared and when they are used)
         if (const char* ov = getenv("TSR_DEBUG_DETECT_FOLD")) {
             const int fo = atoi(ov);
-            if (fo >= 1 && fo <= L && f.vpt * ((L + fo - 1) / fo) <= DT_NT_MAX) { best_fold = fo; best_cap = DT_NT_MAX; }
+            if (fo >= 1 && fo <= L && f.vpt * ((L + fo - 1) / fo) <= DT_NT_MAX) best_fold = fo;
         }
 #endif
     f.fold = best_fold;
@@ -111,7 +144,7 @@ __host__ __device__ inline FilterLayout filter_layout(int M, int L, int D, int p
     f.Kf = f.fold * f.rowwords * 32;
     // I8 contraction order: (frame chunk cf, phase phi, 64-feature half) -- one expanded A strip per cf
     f.nchunks = f.kind ? f.ncf * f.fold * 2 : (f.Kf + f.fps - 1) / f.fps;
-    int tptv = (best_cap / (f.vpt * f.Lf)) * f.vpt;
+    int tptv = (DT_NT_MAX / (f.vpt * f.Lf)) * f.vpt;
     if (tptv < f.vpt) tptv = f.vpt;
     if (tptv > M * f.vpt) tptv = M * f.vpt;
     int msub_cap = DT_MSUB_MAX;
@@ -260,6 +293,7 @@ struct DetectArgs {
     int units_per_ntile;
     int steps_per_unit;
     int ntile_group;        // N tiles whose filter tiles share the L2 at one time (unit order: group, row unit, tile in group)
+    int step_rows;          // TN kernel: frames per step (UMMA N, a multiple of 16)
     int nissue;             // I8: MMA issuer warps (2 when the whole filter bank is L2 resident, else 1 -- measured, see tsr_detect)
     FilterLayout f;
     long long* trace;   // optional debug timeline of CTA 0: [stage iteration][8] clock64 stamps
@@ -948,6 +982,339 @@ __global__ void __launch_bounds__(448 + 32 * (NIS - 1), 1) detect_tc_kernel(Dete
     }
 }
 
+// ------------------------------------------------------------------------------ TN kernel
+// detect_tn_kernel (TSR_PLANES_INT8X2): the same contraction with the operand roles swapped,
+//   D[(v,tau') : 128 TMEM lanes][frame g : <= 256 TMEM columns] += Wq[(v,tau')][k] * bit[g + phi][k],
+// so that the diagonal of the sliding window runs along TMEM *columns*:  scores[g][v] = sum_tau' D[(v,tau')][g + fold*tau'].
+// A group's Lf columns are Lf adjacent lanes (Lf a power of two), so an epilogue thread loads its own lane at the column
+// offsets fold*tau', keeps the one that belongs to its tau' and a butterfly of log2(Lf) shuffles finishes the sum: no
+// shared-memory staging, no per-step accumulator matrix.  What the 2 x 240-column accumulators of detect_tc_kernel could
+// not have follows from that: one 128-lane x 256-column accumulator per step leaves room for a second one, the epilogue
+// of step s runs while the MMAs of step s+1 fill the other (in detect_tc_kernel the tensor pipe idles ~12 % of every
+// step while both accumulators drain), and ~100 KB of shared memory go to a deeper filter-tile ring instead.
+//   TMEM: accumulator a = step parity at columns [256 a, 256 a + step_rows).  The epilogue zeroes an accumulator after
+//   reading it (tcgen05.st) and every MMA accumulates, so the two issuer warps can take alternate filter tiles without
+//   ordering their first MMAs.
+//   Unfinished frames (the last Lc = fold*(Lf-1) of a step) leave their partial sums in a thread-private shared-memory
+//   slot [Lc][128] and are completed by the same thread in the next step.
+//   step_rows (UMMA N, a multiple of 16) is picked by the host so that the units' steps are evenly filled.
+struct TnSmem { uint32_t strip_bytes, b, carry, bars, total; };
+__host__ __device__ inline TnSmem tn_smem_layout(const FilterLayout& f) {
+    TnSmem S;
+    S.strip_bytes = 8u * (uint32_t)f.kgs;
+    S.b = 2 * S.strip_bytes;
+    S.carry = S.b + (uint32_t)f.nstage * 2u * (uint32_t)f.tile_bytes;
+    S.bars = (S.carry + (uint32_t)f.Lc * 128u * 4u + 127u) & ~127u;
+    S.total = S.bars + 512;
+    return S;
+}
+
+__device__ __forceinline__ void tmem_ld1(uint32_t taddr, uint32_t& v) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v) : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_st8_zero(uint32_t taddr) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1};" ::"r"(taddr), "r"(0u) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait_all() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// x holds the 8 columns loaded at a clamped position; d = wanted start - loaded start.  Columns outside the slot read as 0.
+__device__ __forceinline__ void tn_shift_window(uint32_t (&x)[8], int d) {
+#pragma unroll
+    for (int sft = 1; sft < 8; ++sft) {
+        if (d == -sft) {
+#pragma unroll
+            for (int i = 7; i >= 0; --i) x[i] = i >= sft ? x[i - sft] : 0u;
+        }
+        if (d == sft) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) x[i] = i + sft < 8 ? x[i + sft] : 0u;
+        }
+    }
+}
+
+template <int NIS>
+__global__ void __launch_bounds__(448 + 32 * (NIS - 1), 1) detect_tn_kernel(DetectArgs A) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const FilterLayout& f = A.f;
+    const TnSmem S = tn_smem_layout(f);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S.bars);   // [DT_MAX_BSTAGES] filter tile landed
+    uint64_t* empty_bar = full_bar + DT_TN_MAX_STAGES;
+    uint64_t* afull_bar = empty_bar + DT_TN_MAX_STAGES;                  // [2] strip expanded
+    uint64_t* aempty_bar = afull_bar + 2;                              // [2]
+    uint64_t* tfull_bar = aempty_bar + 2;                              // [2] accumulator complete
+    uint64_t* tempty_bar = tfull_bar + 2;                              // [2] accumulator drained and zeroed
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+    const int L = f.L, nstage = f.nstage, fold = f.fold;
+    const int step_rows = A.step_rows;
+    const long long nunits = (long long)f.ntiles * A.units_per_ntile;
+    // Integer accumulation is order independent, so every CTA walks the contraction from its own starting chunk: at any
+    // moment the SMs read different filter tiles (all CTAs fetching the same 8 KB at the same time load a few L2 slices
+    // with 148 requests per line while the others idle).
+    const int rot = DT_DBG(32) ? 0 : (int)(blockIdx.x % (unsigned)f.ncf);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < DT_TN_MAX_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], NIS); }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&afull_bar[s], DT_PRODUCERS); mbar_init(&aempty_bar[s], NIS);
+            mbar_init(&tfull_bar[s], NIS); mbar_init(&tempty_bar[s], 128);
+        }
+        mbar_fence_init();
+    }
+    if (warp == 13) tmem_alloc<512>(tmem_ptr);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp >= 1 && warp <= 8) {
+        // ============================ frame-bit expanders ============================
+        // one strip per 128-feature chunk of a frame: rows = the step's frames plus fold-1 more, 8 k-groups of 16 bytes
+        // (k-group stride kgs); phase phi of the contraction reads it `phi` rows further down
+        const int tid = (int)threadIdx.x - 32;
+        const int nw2 = f.rowwords >> 1;
+        const int srows = step_rows + fold - 1;
+        constexpr int RPT = 2;                       // strip_rows <= 256 + 255
+        uint32_t ita = 0;
+        for (long long u = blockIdx.x; u < nunits; u += gridDim.x) {
+            int nt_unused; long long ur;
+            detect_unit_coords(u, f.ntiles, A.units_per_ntile, A.ntile_group, nt_unused, ur);
+            const long long o0 = ur * A.rows_per_unit;
+            long long o1 = o0 + A.rows_per_unit; if (o1 > A.R) o1 = A.R;
+            long long in_end = o1 + L - 1; if (in_end > A.R) in_end = A.R;
+            for (int step = 0; step < A.steps_per_unit; ++step) {
+                const long long g0 = o0 + (long long)step * step_rows;
+                for (int cfi = 0; cfi < f.ncf; ++cfi, ++ita) {
+                    int cf = cfi + rot; if (cf >= f.ncf) cf -= f.ncf;
+                    uint2 w[RPT], wh[RPT];
+#pragma unroll
+                    for (int k = 0; k < RPT; ++k) {
+                        const int r = tid + 256 * k;
+                        const long long fr = g0 + r;
+                        const bool ok = r < srows && fr < in_end;
+                        const uint2* src = reinterpret_cast<const uint2*>(A.bits + (ok ? fr : 0) * f.rowwords);
+                        w[k] = (ok && 2 * cf < nw2) ? __ldg(src + 2 * cf) : make_uint2(0u, 0u);
+                        wh[k] = (ok && 2 * cf + 1 < nw2) ? __ldg(src + 2 * cf + 1) : make_uint2(0u, 0u);
+                    }
+                    const int buf = ita & 1;
+                    mbar_wait_relaxed(&aempty_bar[buf], ((ita >> 1) & 1) ^ 1);
+                    uint8_t* strip = smem + buf * S.strip_bytes;
+#pragma unroll
+                    for (int k = 0; k < RPT; ++k) {
+                        const int r = tid + 256 * k;
+                        if (r < f.strip_rows && !DT_DBG(8)) {
+                            uint8_t* dst = strip + r * 16;
+                            const uint32_t kgs = (uint32_t)f.kgs;
+                            *reinterpret_cast<uint4*>(dst) = expand16_u8(w[k].x & 0xFFFF);
+                            *reinterpret_cast<uint4*>(dst + kgs) = expand16_u8(w[k].x >> 16);
+                            *reinterpret_cast<uint4*>(dst + 2 * kgs) = expand16_u8(w[k].y & 0xFFFF);
+                            *reinterpret_cast<uint4*>(dst + 3 * kgs) = expand16_u8(w[k].y >> 16);
+                            *reinterpret_cast<uint4*>(dst + 4 * kgs) = expand16_u8(wh[k].x & 0xFFFF);
+                            *reinterpret_cast<uint4*>(dst + 5 * kgs) = expand16_u8(wh[k].x >> 16);
+                            *reinterpret_cast<uint4*>(dst + 6 * kgs) = expand16_u8(wh[k].y & 0xFFFF);
+                            *reinterpret_cast<uint4*>(dst + 7 * kgs) = expand16_u8(wh[k].y >> 16);
+                        }
+                    }
+                    fence_proxy_async_smem();
+                    mbar_arrive(&afull_bar[buf]);
+                }
+            }
+        }
+    } else if (warp == 0) {
+        // ============================ filter-tile loader ============================
+        if (lane == 0) {
+            int stage = 0; uint32_t ph = 0;
+            for (long long u = blockIdx.x; u < nunits; u += gridDim.x) {
+                int nt; long long ur_unused;
+                detect_unit_coords(u, f.ntiles, A.units_per_ntile, A.ntile_group, nt, ur_unused);
+                const uint8_t* src = A.blob + f.hdr_bytes + (size_t)nt * f.nchunks * f.tile_bytes;
+                // One thread pays ~300 cycles of dependent latencies per copy (try_wait, expect_tx, UBLKCP): a stage is
+                // therefore the 16 KB pair of tiles of one phase (480 cycles of MMAs), not a single 8 KB tile.
+                const uint32_t sbytes = 2u * (uint32_t)f.tile_bytes;
+                const int nst = f.ncf * fold;
+                for (int step = 0; step < A.steps_per_unit; ++step)
+                    for (int ci = 0; ci < nst; ++ci) {
+                        int c = ci + rot * fold; if (c >= nst) c -= nst;
+                        mbar_wait_relaxed(&empty_bar[stage], ph ^ 1);
+                        if (DT_DBG(4)) { mbar_arrive(&full_bar[stage]); } else {
+                        mbar_arrive_expect_tx(&full_bar[stage], sbytes);
+                        bulk_g2s(smem + S.b + stage * sbytes, src + (size_t)c * sbytes, sbytes, &full_bar[stage]);
+                        }
+                        if (++stage == nstage) { stage = 0; ph ^= 1; }
+                    }
+            }
+        }
+    } else if (warp == 13 || (NIS == 2 && warp == 14)) {
+        // ================================ MMA issuers ================================
+        // A = filter tile (int8, 128 columns x 32 per MMA), B = strip rows phi .. phi + step_rows (uint8 {0,1}), D = int32.
+        // With two issuers, issuer i takes the 64-feature tile i of every stage; every MMA accumulates (zeroed accumulators).
+        const int iss = warp - 13;
+        const uint32_t idesc = (2u << 4) | (1u << 7) | (0u << 10) | ((uint32_t)(step_rows >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        const uint32_t desc_hi = (uint32_t)(128 >> 4) | (1u << 14);                                  // SBO = 128 B, version 1
+        const uint64_t a_hi = ((uint64_t)desc_hi << 32) | ((uint64_t)128 << 16);                     // LBO = 128 rows * 16 B
+        const uint64_t b_hi = ((uint64_t)desc_hi << 32) | ((uint64_t)((uint32_t)f.kgs >> 4) << 16);  // LBO = k-group stride
+        const uint32_t kgs16 = (uint32_t)f.kgs >> 4;
+        int stage = 0; uint32_t ph = 0;
+        uint32_t stepno = 0, ita = 0;
+        for (long long u = blockIdx.x; u < nunits; u += gridDim.x)
+            for (int step = 0; step < A.steps_per_unit; ++step, ++stepno) {
+                const uint32_t acc = stepno & 1;
+                mbar_wait(&tempty_bar[acc], (stepno >> 1) & 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * 256;
+                for (int cf = 0; cf < f.ncf; ++cf, ++ita) {
+                    const int buf = ita & 1;
+                    mbar_wait(&afull_bar[buf], (ita >> 1) & 1);
+                    tc_fence_after();
+                    const uint32_t sbase = smem_u32(smem + buf * S.strip_bytes) >> 4;
+                    for (int phi = 0; phi < fold; ++phi) {
+                        mbar_wait(&full_bar[stage], ph);
+                        tc_fence_after();
+                        const uint32_t abase = smem_u32(smem + S.b + stage * 2u * (uint32_t)f.tile_bytes) >> 4;
+#pragma unroll
+                        for (int half = (NIS == 2 ? iss : 0); half < 2; half += NIS) {   // two issuers: one 64-feature tile each
+#pragma unroll
+                            for (int j = 0; j < 2; ++j) {   // K = 32 per MMA: k-groups 2j, 2j+1 of the tile, 2(2 half + j), +1 of the strip
+                                const uint64_t adesc = a_hi | (uint64_t)(abase + (uint32_t)half * 512u + (uint32_t)j * 2 * 128);
+                                const uint64_t bdesc = b_hi | (uint64_t)(sbase + (uint32_t)(DT_DBG(1) ? 0 : phi) + (uint32_t)(2 * (2 * half + j)) * kgs16);
+                                umma_i8_elect(d_tmem, adesc, bdesc, idesc, 1u);
+                            }
+                        }
+                        umma_commit_elect(&empty_bar[stage]);
+                        if (++stage == nstage) { stage = 0; ph ^= 1; }
+                    }
+                    umma_commit_elect(&aempty_bar[buf]);
+                }
+                umma_commit_elect(&tfull_bar[acc]);
+            }
+    } else if (warp >= 9 && warp <= 12) {
+        // ================================= epilogue =================================
+        const int quad = warp & 3;
+        const int e = quad * 32 + lane;                       // TMEM lane == filter column of the tile
+        const int Lf = f.Lf, Lc = f.Lc;
+        const int tr = e & (Lf - 1), vl = e / Lf;             // tau', group
+        const float* scale = reinterpret_cast<const float*>(A.blob + 128);
+        int* carry = reinterpret_cast<int*>(smem + S.carry) + e;      // [Lc][128], column e is private to this thread
+        const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
+        // both accumulators start zeroed
+        for (int c = 0; c < 512; c += 8) tmem_st8_zero(tmem_base + lane_addr + c);
+        tmem_st_wait_all();
+        tc_fence_before();
+        mbar_arrive(&tempty_bar[0]);
+        mbar_arrive(&tempty_bar[1]);
+        const bool small_r = A.R < (1ll << 31);
+        const int Lc8 = (Lc + 7) & ~7;
+        uint32_t stepno = 0;
+        for (long long u = blockIdx.x; u < nunits; u += gridDim.x) {
+            int nt; long long ur;
+            detect_unit_coords(u, f.ntiles, A.units_per_ntile, A.ntile_group, nt, ur);
+            const long long o0 = ur * A.rows_per_unit;
+            long long o1 = o0 + A.rows_per_unit; if (o1 > A.R) o1 = A.R;
+            const int v = nt * f.tptv + vl;
+            const int m = v >> 1, plane = v & 1;
+            const bool live = vl < f.tptv && m < f.M;
+            const float sc_m = live ? scale[m] : 0.f;
+            const float cs_m = (live && A.cs) ? __ldg(A.cs + m) : 0.f;
+            for (int step = 0; step < A.steps_per_unit; ++step, ++stepno) {
+                const uint32_t acc = stepno & 1;
+                mbar_wait_relaxed(&tfull_bar[acc], (stepno >> 1) & 1);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + lane_addr + acc * 256;
+                const long long F0 = o0 + (long long)step * step_rows;
+                for (int c0 = -Lc8; c0 < step_rows; c0 += 8) {
+                    if (DT_DBG(16)) break;
+                    const long long gb = F0 + c0;
+                    if (gb + 8 <= o0 || gb >= o1 + Lc) continue;                  // nothing owned or carried in this block
+                    int val[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) val[i] = 0;
+                    // window t = columns [c0 + fold t, +8) of this lane; the lane keeps the window of its own tau'.  Columns
+                    // [step_rows, 256) of an accumulator slot are never written and read as zero; a window that sticks out
+                    // of [0, 256) is loaded from the clamped position and shifted (boundary blocks only).
+                    for (int t = 0; t < Lf; t += 2) {
+                        uint32_t x0[8], x1[8];
+                        const int col0 = c0 + fold * t, col1 = col0 + fold;
+                        const bool h0 = col0 + 8 > 0 && col0 < step_rows;
+                        const bool h1 = t + 1 < Lf && col1 + 8 > 0 && col1 < step_rows;
+                        const int cc0 = col0 < 0 ? 0 : (col0 > 248 ? 248 : col0), cc1 = col1 < 0 ? 0 : (col1 > 248 ? 248 : col1);
+                        if (h0) tmem_ld8(taddr + cc0, x0);
+                        if (h1) tmem_ld8(taddr + cc1, x1);
+                        if (h0 || h1) tmem_ld_wait();
+                        if (h0) {
+                            if (cc0 != col0) tn_shift_window(x0, col0 - cc0);
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) val[i] = tr == t ? (int)x0[i] : val[i];
+                        }
+                        if (h1) {
+                            if (cc1 != col1) tn_shift_window(x1, col1 - cc1);
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) val[i] = tr == t + 1 ? (int)x1[i] : val[i];
+                        }
+                    }
+                    for (int off = 1; off < Lf; off <<= 1) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) val[i] += __shfl_xor_sync(0xffffffffu, val[i], off);
+                    }
+                    int tl = 0;
+                    {
+                        const long long gq = gb < 0 ? 0 : gb;
+                        tl = small_r ? (int)((unsigned)gq % (unsigned)A.T) : (int)(gq % A.T);
+                        if (gb < 0) tl += (int)gb;                                   // only blocks that are skipped below
+                    }
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int c = c0 + i;
+                        const long long g = gb + i;
+                        int s = val[i];
+                        if (c < -Lc) continue;
+                        if (c < 0) s += carry[(c + Lc) * 128];
+                        if (c >= step_rows - Lc) { carry[(c - (step_rows - Lc)) * 128] = s; continue; }
+                        if (g < o0 || g >= o1) continue;                            // warp-uniform
+                        int tli = tl + i; while (tli >= A.T) tli -= A.T;
+                        const int other = __shfl_xor_sync(0xffffffffu, s, Lf);      // the other digit plane of this template
+                        float sc = 0.f;
+                        if (tli <= A.T - L) {
+                            // q = lo + 256 hi in fp32 (no FP64: a DFMA costs this SM hundreds of cycles): |hi| < 2^24 converts
+                            // exactly, so the result carries three fp32 roundings (~2e-7 relative), far below the 1.5e-5
+                            // quantisation step of the 16-bit weights
+                            const float lo = (float)(plane ? other : s), hi = (float)(plane ? s : other);
+                            sc = __fmaf_rn(hi, 256.f, lo) * sc_m;
+                        }
+                        if (A.scores && live && plane == 0 && tr == 0) A.scores[g * f.M + m] = sc;
+                        if (A.keys) {
+                            // max over the warp's templates: one REDUX on the monotone bit pattern; the lowest lane that holds
+                            // the maximum belongs to the lowest template index (first maximum wins, like detect_key)
+                            uint32_t uk = __float_as_uint(sc + cs_m);
+                            uk ^= (uk >> 31) ? 0xFFFFFFFFu : 0x80000000u;
+                            if (!live) uk = 0u;
+                            const uint32_t umax = __reduce_max_sync(0xffffffffu, uk);
+                            const uint32_t who = __ballot_sync(0xffffffffu, live && uk == umax);
+                            if (lane == 0 && who) {
+                                const int bl = __ffs(who) - 1;
+                                const int mb = (nt * f.tptv + (quad * 32 + bl) / Lf) >> 1;
+                                atomicMax(A.keys + g, ((unsigned long long)umax << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)mb));
+                            }
+                        }
+                    }
+                }
+                // hand the accumulator back zeroed
+                for (int c = 0; c < step_rows; c += 8) tmem_st8_zero(taddr + c);
+                tmem_st_wait_all();
+                tc_fence_before();
+                mbar_arrive(&tempty_bar[acc]);
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 13) {
+        tc_fence_after();
+        tmem_dealloc<512>(tmem_base);
+    }
+}
+
 // ------------------------------------------------------------------------------ SIMT
 // One thread per (g, m): walks the set bits of the L rows in (tau, d) order and adds fp32 filter
 // values sequentially -- the reference's exact arithmetic (detect, :162-175).  Cross-check kernel.
@@ -1182,6 +1549,55 @@ int tsr_prepare_filters(const float* LF, int M, int L, int D, int plane_format, 
     return check_launch("tsr_prepare_filters");
 }
 
+// TN kernel: partition the rows into units and the units into evenly filled steps of step_rows <= 256 frames
+static int detect_tn_launch(DetectArgs& A, cudaStream_t st) {
+    const FilterLayout& f = A.f;
+    const TnSmem S = tn_smem_layout(f);
+    if (S.total > 227 * 1024) {
+        set_error("tsr_detect: L=%d needs %u B of shared memory (> 227 KB)", f.L, S.total);
+        return TSR_ERR_UNSUPPORTED;
+    }
+    const int nsm = sm_count();
+    const long long R = A.R;
+    const int min_rows = 128;                      // narrower MMAs are issue bound; also keeps step_rows > Lc + 8
+    long long best_cost = -1;
+    int best_U = 1, best_steps = 1, best_sr = DT_TN_STEP_MAX;
+    const long long maxU = (R + min_rows - 1) / min_rows;
+    for (long long U = 1; U <= maxU && U <= 8192; ++U) {
+        const long long need = (R + U - 1) / U + f.Lc;
+        const long long steps = (need + DT_TN_STEP_MAX - 1) / DT_TN_STEP_MAX;
+        long long sr = (((need + steps - 1) / steps) + 15) & ~15LL;
+        if (sr < min_rows) sr = min_rows;
+        const long long waves = ((long long)f.ntiles * U + nsm - 1) / nsm;
+        const long long cost = waves * steps * (sr + 8);        // + a per-step constant (accumulator hand-over)
+        if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_U = (int)U; best_steps = (int)steps; best_sr = (int)sr; }
+    }
+    A.units_per_ntile = best_U;
+    A.rows_per_unit = (int)((R + best_U - 1) / best_U);
+    A.steps_per_unit = best_steps;
+    A.step_rows = best_sr;
+    const size_t set_bytes = (size_t)f.nchunks * f.tile_bytes;
+    long long G = (long long)(64u << 20) / (long long)(set_bytes ? set_bytes : 1);
+    if (G < 1) G = 1;
+    if (G > f.ntiles) G = f.ntiles;
+    A.ntile_group = (int)G;
+    A.nissue = 2;
+#ifdef TSR_DEBUG_TRACE
+    if (const char* ov = getenv("TSR_DEBUG_DETECT_FLAGS")) A.dbg = atoi(ov);   // timing experiments, wrong results
+#endif
+    if (const char* ov = getenv("TSR_DEBUG_DETECT_NISSUE")) A.nissue = ov[0] == '1' ? 1 : 2;   // experiments only
+    const long long nunits = (long long)f.ntiles * best_U;
+    const int blocks = (int)(nunits < nsm ? nunits : nsm);
+    if (A.nissue == 2) {
+        TSR_CUDA(cudaFuncSetAttribute(detect_tn_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S.total));
+        detect_tn_kernel<2><<<blocks, DT_THREADS, S.total, st>>>(A);
+    } else {
+        TSR_CUDA(cudaFuncSetAttribute(detect_tn_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S.total));
+        detect_tn_kernel<1><<<blocks, DT_THREADS - 32, S.total, st>>>(A);
+    }
+    return check_launch("tsr_detect");
+}
+
 static int detect_impl(const uint32_t* featbits, int B, int T, int D, int rowwords, const void* filter_blob,
                        const float* LF_or_null, int M, int L, int plane_format, float* scores, unsigned long long* keys,
                        const float* cs, int impl, void* stream) {
@@ -1215,6 +1631,7 @@ static int detect_impl(const uint32_t* featbits, int B, int T, int D, int rowwor
     A.f = filter_layout(M, L, D, plane_format);
     A.trace = g_detect_trace;
     A.dbg = g_detect_dbg;
+    if (A.f.kind == 2) return detect_tn_launch(A, (cudaStream_t)stream);
     DetectSmem S = detect_smem_layout(A.f);
     if (S.total > 227 * 1024) {
         set_error("tsr_detect: L=%d needs %u B of shared memory (> 227 KB)", L, S.total);
