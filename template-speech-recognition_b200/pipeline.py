@@ -18,7 +18,7 @@ from . import ops
 class ScoringPipeline:
     def __init__(self, log_parts, log_invparts, filters, cs, edge_threshold=12, part_spread=(2, 2),
                  edge_spread_radius=1, edge_block_len=40, edge_orientations=None, device="cuda",
-                 detect_planes=ops.PLANES_INT8X3):
+                 detect_planes=ops.PLANES_INT8X2):
         self.parts = ops.PartsModel(log_parts, log_invparts, device=device)
         self.bank = ops.FilterBank(filters, cs=cs, device=device, planes=detect_planes)
         self.edge_threshold = int(edge_threshold)

@@ -102,11 +102,13 @@ def test_detect_part_level_mixture(cuda, oracle, impl, planes):
             worst = max(worst, _close(got[b, :, m], ref64))   # 16-bit int8x2 weights stay inside 1e-5 at this scale too
             if planes == 4:
                 _close_each(got[b, :, m], ref64, np.abs(ref64).max(), 3e-7)
+            if planes == 3:   # the pipeline default: 16-bit fixed-point weights, exact integer sums (measured 2.6e-6 of the scale)
+                _close_each(got[b, :, m], ref64, np.abs(ref64).max(), 5e-6)
     print("part-level detect (impl %d planes %d) rel err %.2e" % (impl, planes, worst))
     assert np.all(got[:, 257:, :] == 0)
 
 
-@pytest.mark.parametrize("planes", [0, 4], ids=["fp16", "int8x3"])
+@pytest.mark.parametrize("planes", [0, 3, 4], ids=["fp16", "int8x2", "int8x3"])
 @pytest.mark.parametrize("B,T,D1,D2,M,L", [(1, 9, 3, 5, 1, 9), (3, 50, 7, 9, 5, 1), (2, 130, 40, 8, 7, 40),
                                          (5, 77, 1, 1, 33, 13), (1, 700, 4, 16, 2, 200), (4, 20, 36, 100, 2, 3),
                                          (2, 300, 40, 8, 9, 80)])
@@ -118,12 +120,23 @@ def test_detect_shapes(cuda, B, T, D1, D2, M, L, planes):
     s = _gpu_detect(F, LF, 1)
     scale = np.abs(s).max()
     for b in range(B):
+        ones = np.ones((L,) + F.shape[2:], np.float32)
+        nset = _f64_detect(F[b], ones)                                # set bits in every window
         for m in range(M):
             ref64 = _f64_detect(F[b], LF[m])
+            if planes == 3:
+                # 16-bit fixed-point weights (step = max|w| / 32639 per template), exact integer sums: the error is bounded by
+                # half a step per set bit whatever the weights are.  With unstructured Gaussian weights (this test) that bound
+                # is not 1e-5 of the score scale; with the clipped log-odds filters of the scoring path it is (measured
+                # 2.6e-6, test_detect_part_level_mixture).
+                bound = 0.5 * np.abs(LF[m]).max() / 32639.0 * nset + 1e-6 * scale
+                assert np.all(np.abs(t[b, :, m] - ref64) <= bound)
+                continue
             _close(t[b, :, m], ref64, scale)
             if planes == 4:
                 _close_each(t[b, :, m], ref64, scale, 3e-7)
-    np.testing.assert_allclose(t, s, atol=RTOL * scale)
+    if planes != 3:
+        np.testing.assert_allclose(t, s, atol=RTOL * scale)
     if L > 1:
         assert np.all(t[:, T - L + 1:, :] == 0)
 
