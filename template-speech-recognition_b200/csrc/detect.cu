@@ -1163,7 +1163,11 @@ __global__ void __launch_bounds__(448 + 32 * (NIS - 1), 1) detect_tn_kernel(Dete
                 mbar_wait(&tempty_bar[acc], (stepno >> 1) & 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * 256;
-                for (int cf = 0; cf < f.ncf; ++cf, ++ita) {
+                for (int cfi = 0; cfi < f.ncf; ++cfi, ++ita) {
+                    int cf = cfi + rot; if (cf >= f.ncf) cf -= f.ncf;
+                    // 32-feature K-steps of this chunk that hold features at all (the last chunk of D = 3600: 1 of 4)
+                    const int feats = f.D - cf * 128;
+                    const int ksteps = feats >= 128 ? 4 : (feats + 31) >> 5;
                     const int buf = ita & 1;
                     mbar_wait(&afull_bar[buf], (ita >> 1) & 1);
                     tc_fence_after();
@@ -1178,7 +1182,7 @@ __global__ void __launch_bounds__(448 + 32 * (NIS - 1), 1) detect_tn_kernel(Dete
                             for (int j = 0; j < 2; ++j) {   // K = 32 per MMA: k-groups 2j, 2j+1 of the tile, 2(2 half + j), +1 of the strip
                                 const uint64_t adesc = a_hi | (uint64_t)(abase + (uint32_t)half * 512u + (uint32_t)j * 2 * 128);
                                 const uint64_t bdesc = b_hi | (uint64_t)(sbase + (uint32_t)(DT_DBG(1) ? 0 : phi) + (uint32_t)(2 * (2 * half + j)) * kgs16);
-                                umma_i8_elect(d_tmem, adesc, bdesc, idesc, 1u);
+                                if (2 * half + j < ksteps) umma_i8_elect(d_tmem, adesc, bdesc, idesc, 1u);
                             }
                         }
                         umma_commit_elect(&empty_bar[stage]);

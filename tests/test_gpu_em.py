@@ -65,8 +65,9 @@ def test_estep_matches_numpy(cuda, N, D, K, impl):
     q = np.rint((got_aff * (np.float32(1) / sk)[None]) * np.float32(QMAX)).astype(np.int64)
     stats = st.stats.cpu().numpy()
     np.testing.assert_array_equal(stats[K * D:K * D + K], q.sum(0).astype(np.float64) / QMAX * sk.astype(np.float64))
+    qs = q.T @ X.astype(np.int64)                      # em_pack_kernel: integer quotient + remainder term (exact for multiples of QMAX)
     np.testing.assert_array_equal(stats[:K * D].reshape(K, D),
-                                  (q.T @ X.astype(np.int64)).astype(np.float64) / QMAX * sk.astype(np.float64)[:, None])
+                                  ((qs // QMAX).astype(np.float64) + (qs % QMAX).astype(np.float64) * (1.0 / QMAX)) * sk.astype(np.float64)[:, None])
     np.testing.assert_allclose(st.numerators().cpu().numpy(), aff.T @ Xd, rtol=1e-5, atol=1e-4 if impl == 0 else 2e-2)
     np.testing.assert_allclose(st.resp_sums().cpu().numpy(), aff.sum(0), rtol=1e-5 if impl == 0 else 1e-3)
     # the accumulators were cleared behind the reads: a second pass gives the same bits

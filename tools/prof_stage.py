@@ -14,7 +14,7 @@ ap.add_argument("stage")
 ap.add_argument("--batch", type=int, default=1024)
 ap.add_argument("--iters", type=int, default=3)
 ap.add_argument("--simt", action="store_true")
-ap.add_argument("--planes", type=int, default=4)
+ap.add_argument("--planes", type=int, default=3, help="3 = INT8X2 (detect_tn_kernel, the pipeline default), 4 = INT8X3 (detect_tc_kernel)")
 a = ap.parse_args()
 impl = ops.IMPL_SIMT if a.simt else ops.IMPL_TENSOR
 B = a.batch
