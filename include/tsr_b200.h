@@ -52,9 +52,12 @@ extern "C" {
 #define TSR_PLANES_AUTO 0
 #define TSR_PLANES_BF16 1
 #define TSR_PLANES_FP16 2
-/* Detection / EM only: fixed-point filters q = round(w / scale[m]) as 2 or 3 balanced base-256
- * int8 digit planes, uint8 {0,1} bits, tcgen05 kind::i8 with exact int32 accumulation (twice the
- * f16 rate).  Falls back to the FP16/BF16 kind when planes * L > 240 columns. */
+/* Detection only: fixed-point filters q = round(w / scale[m]), scale[m] = max|w_m| / qmax, as 2
+ * (16-bit, qmax 32639) or 3 (24-bit, qmax 8355711) balanced base-256 int8 digit planes, uint8 {0,1}
+ * bits, tcgen05 kind::i8 with exact int32 accumulation (twice the f16 rate).  INT8X2 runs on
+ * detect_tn_kernel (frames as UMMA N, ping-pong accumulators; the scoring pipeline's default:
+ * |err| <= 0.5 * scale[m] * set bits, 2.6e-6 of the score scale for log-odds filters), INT8X3 on
+ * detect_tc_kernel (6e-8). */
 #define TSR_PLANES_INT8X2 3
 #define TSR_PLANES_INT8X3 4
 

@@ -1279,7 +1279,7 @@ __global__ void __launch_bounds__(448 + 32 * (NIS - 1), 1) detect_tn_kernel(Dete
                         const int other = __shfl_xor_sync(0xffffffffu, s, Lf);      // the other digit plane of this template
                         float sc = 0.f;
                         if (tli <= A.T - L) {
-                            // q = lo + 256 hi in fp32 (no FP64: a DFMA costs this SM hundreds of cycles): |hi| < 2^24 converts
+                            // q = lo + 256 hi in fp32 (the I2F.F64 -> DFMA -> DMUL -> F2F chain per output stalled these warps): |hi| < 2^24 converts
                             // exactly, so the result carries three fp32 roundings (~2e-7 relative), far below the 1.5e-5
                             // quantisation step of the 16-bit weights
                             const float lo = (float)(plane ? other : s), hi = (float)(plane ? s : other);

@@ -712,8 +712,8 @@ __device__ __forceinline__ float em_col_scale(uint32_t colmax_bits) {
 }
 
 // q / EM_QMAX * s_k with the division split into an integer quotient and a remainder term: exact for multiples of EM_QMAX
-// (hard assignments give the bit counts themselves) and 4 FP64-pipe instructions instead of a double division (FP64 issues
-// at ~1 warp instruction per 64 cycles per SM here).  No FMA contraction: two roundings, as the tests' NumPy restatement.
+// (hard assignments give the bit counts themselves) without the ~20-instruction double division per element.  No FMA
+// contraction: two roundings, as the tests' NumPy restatement.
 __device__ __forceinline__ double em_q_to_stat(long long q, double sk) {
     const long long qi = q / (long long)EM_QMAX, qr = q - qi * (long long)EM_QMAX;
     return __dadd_rn((double)qi, __dmul_rn((double)qr, 1.0 / (double)EM_QMAX)) * sk;
@@ -932,60 +932,6 @@ __global__ void em_zero_c_kernel(long long* c, int K, const int* done) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// Double-float arithmetic (value = h + l, |l| <= ulp(h) / 2: ~48 significant bits) for the row kernels.  The scores are
-// sums of ~1e11 magnitude fixed-point integers times a scale, and the posteriors need their DIFFERENCES to ~1e-6 absolute,
-// i.e. more than fp32 -- but the FP64 pipe of this SM issues about one warp instruction per 64 cycles (a DFMA in a busy
-// warp costs hundreds of cycles; measured on detect_tn_kernel's epilogue and em_pack_kernel), which made the posterior
-// kernel FP64 bound.  Error-free fp32 transformations run on the FMA pipe at full rate.  Explicit _rn intrinsics keep the
-// compiler from contracting or reassociating them.
-struct df { float h, l; };
-__device__ __forceinline__ df df_fast_two_sum(float a, float b) {          // |a| >= |b| or a == 0
-    const float s = __fadd_rn(a, b);
-    return df{s, __fadd_rn(b, -__fadd_rn(s, -a))};
-}
-__device__ __forceinline__ df df_two_sum(float a, float b) {
-    const float s = __fadd_rn(a, b), bb = __fadd_rn(s, -a);
-    const float e = __fadd_rn(__fadd_rn(a, -__fadd_rn(s, -bb)), __fadd_rn(b, -bb));
-    return df{s, (s - s == 0.f) ? e : 0.f};                               // an infinite sum (log weight of an empty component) has no error term
-}
-__device__ __forceinline__ df df_from_ll(long long q) {                    // exact for |q| < 2^48
-    const float h = __ll2float_rn(q);
-    return df{h, __ll2float_rn(q - __float2ll_rz(h))};
-}
-__device__ __forceinline__ df df_mul_f(df a, float b) {
-    const float ph = __fmul_rn(a.h, b);
-    const float pe = __fmaf_rn(a.l, b, __fmaf_rn(a.h, b, -ph));
-    return df_fast_two_sum(ph, pe);
-}
-__device__ __forceinline__ df df_add(df a, df b) {
-    df s = df_two_sum(a.h, b.h);
-    s.l = __fadd_rn(s.l, __fadd_rn(a.l, b.l));
-    return df_fast_two_sum(s.h, s.l);
-}
-__device__ __forceinline__ df df_add_f(df a, float b) {
-    df s = df_two_sum(a.h, b);
-    s.l = __fadd_rn(s.l, a.l);
-    return df_fast_two_sum(s.h, s.l);
-}
-__device__ __forceinline__ bool df_gt(df a, df b) { return a.h > b.h || (a.h == b.h && a.l > b.l); }
-__device__ __forceinline__ df df_max(df a, df b) { return df_gt(b, a) ? b : a; }
-__device__ __forceinline__ float df_diff(df a, df b) {                     // a - b rounded to fp32
-    return __fadd_rn(__fadd_rn(a.h, -b.h), __fadd_rn(a.l, -b.l));
-}
-// template score from the three digit-plane sums: (a0 + 256 a1 + 65536 a2) * scale + c * 2^-36
-__device__ __forceinline__ df em_score_df(int a0, int a1, int a2, float scale, long long cfix) {
-    const long long q = (long long)a0 + 256LL * (long long)a1 + 65536LL * (long long)a2;
-    df c = df_from_ll(cfix);
-    c.h *= (float)(1.0 / EM_C_SCALE); c.l *= (float)(1.0 / EM_C_SCALE);      // exact: power of two
-    return df_add(df_mul_f(df_from_ll(q), scale), c);
-}
-// row log-likelihood (log(sum) + mx) in 2^-20 fixed point
-__device__ __forceinline__ long long em_ll_fixed(df sum, df mx) {
-    const float lg = logf(sum.h) + sum.l / sum.h;
-    return __float2ll_rn(__fmul_rn(mx.h, (float)EM_LL_SCALE)) + __float2ll_rn(__fmul_rn(__fadd_rn(mx.l, lg), (float)EM_LL_SCALE));
-}
-
-// ------------------------------------------------------------------------------------------------
 // Row kernel of the E-step.  Thread = data row.
 //   INT_SCORES: scores from the int32 digit-plane accumulators (which are cleared for the next E-step);
 //   otherwise scratch already holds float scores [K][Npad] (SIMT cross-check).
@@ -1022,20 +968,21 @@ __global__ void __launch_bounds__(128) em_posterior_kernel(PostArgs P) {
     if (tid == 0) s_ll = 0;
     __syncthreads();
     const size_t pstride = (size_t)P.KT * P.Npad;
-    // template score of component k in double-float: exact integer digit-plane sums, one scaling (or the SIMT kernel's
+    // template score of component k in double: exact integer digit-plane sums, one scaling (or the SIMT kernel's
     // float score); `clear` zeroes the accumulators behind the last read so that the next E-step starts from zero
-    auto score = [&](int k, bool clear) -> df {
+    auto score = [&](int k, bool clear) -> double {
         if (INT_SCORES) {
             const int mt = k / P.KT, kl = k - mt * P.KT;
             int* a = P.accE + ((size_t)mt * P.mrp + kl) * P.Npad + n;
             const int a0 = a[0], a1 = a[pstride], a2 = a[2 * pstride];
             if (clear) { a[0] = 0; a[pstride] = 0; a[2 * pstride] = 0; }
-            return em_score_df(a0, a1, a2, P.scale[k], P.c[k]);
+            const double q = (double)a0 + 256.0 * (double)a1 + 65536.0 * (double)a2;
+            return q * (double)P.scale[k] + (double)P.c[k] / EM_C_SCALE;
         }
-        return df{P.scratch[(size_t)k * P.Npad + n], 0.f};
+        return (double)P.scratch[(size_t)k * P.Npad + n];
     };
     constexpr int NR = KREG > 0 ? KREG : 1;
-    df sv[NR];
+    double sv[NR];
     if (KREG > 0) {
         if (INT_SCORES) {      // all loads first (K <= 42: one M tile, rows plane * KT + k)
             int a0[NR], a1[NR], a2[NR];
@@ -1047,22 +994,23 @@ __global__ void __launch_bounds__(128) em_posterior_kernel(PostArgs P) {
             for (int k = 0; k < NR; ++k)
                 if (k < P.K) {
                     a[(size_t)k * P.Npad] = 0; a[(size_t)k * P.Npad + pstride] = 0; a[(size_t)k * P.Npad + 2 * pstride] = 0;
-                    sv[k] = em_score_df(a0[k], a1[k], a2[k], P.scale[k], P.c[k]);
+                    const double q = (double)a0[k] + 256.0 * (double)a1[k] + 65536.0 * (double)a2[k];
+                    sv[k] = q * (double)P.scale[k] + (double)P.c[k] / EM_C_SCALE;
                 }
         } else {
 #pragma unroll
             for (int k = 0; k < NR; ++k)
-                if (k < P.K) sv[k] = df{P.scratch[(size_t)k * P.Npad + n], 0.f};
+                if (k < P.K) sv[k] = (double)P.scratch[(size_t)k * P.Npad + n];
         }
     }
-    // pass 1: scores out, running maxima (soft-max in double-float up to the exponent: the posteriors then carry the
+    // pass 1: scores out, running maxima (soft-max in double up to the exponent: the posteriors then carry the
     // weight quantisation only, ~1e-6, instead of the 3e-5 a float32 score of magnitude 500 would add)
-    df mx = df{-INFINITY, 0.f}, smx = df{-INFINITY, 0.f};
+    double mx = -INFINITY, smx = -INFINITY;
     int arg = 0;
-    auto pass1 = [&](int k, df s) {
-        if (live && P.scores_out) P.scores_out[n * P.K + k] = s.h;
-        if (df_gt(s, smx)) { smx = s; arg = k; }            // hard assignment: first arg-max of the template scores (:273-275)
-        mx = df_max(mx, df_add_f(s, P.logw[k]));
+    auto pass1 = [&](int k, double s) {
+        if (live && P.scores_out) P.scores_out[n * P.K + k] = (float)s;
+        if (s > smx) { smx = s; arg = k; }                  // hard assignment: first arg-max of the template scores (:273-275)
+        mx = fmax(mx, s + (double)P.logw[k]);
     };
     if (KREG > 0) {
 #pragma unroll
@@ -1073,21 +1021,21 @@ __global__ void __launch_bounds__(128) em_posterior_kernel(PostArgs P) {
     }
     if (!P.update) return;
     // pass 2: log-sum-exp (:269-270)
-    df sum = df{0.f, 0.f};
+    double sum = 0.0;
     if (KREG > 0) {
 #pragma unroll
         for (int k = 0; k < NR; ++k)
-            if (k < P.K) sum = df_add_f(sum, expf(df_diff(df_add_f(sv[k], P.logw[k]), mx)));
+            if (k < P.K) sum += (double)expf((float)(sv[k] + (double)P.logw[k] - mx));
     } else {
-        for (int k = 0; k < P.K; ++k) sum = df_add_f(sum, expf(df_diff(df_add_f(score(k, false), P.logw[k]), mx)));
+        for (int k = 0; k < P.K; ++k) sum += (double)expf((float)(score(k, false) + (double)P.logw[k] - mx));
     }
-    const float inv = 1.f / sum.h;
-    long long my_ll = live ? em_ll_fixed(sum, mx) : 0;
+    const float inv = (float)(1.0 / sum);
+    long long my_ll = live ? llrint((log(sum) + mx) * EM_LL_SCALE) : 0;
     // pass 3: posteriors and their column maxima
-    auto pass3 = [&](int k, df s) {
-        const df v = df_add_f(s, P.logw[k]);
+    auto pass3 = [&](int k, double s) {
+        const double v = s + (double)P.logw[k];
         float p = 0.f;
-        if (live) p = P.hard ? (k == arg ? 1.f : 0.f) : fminf(expf(df_diff(v, mx)) * inv, 1.f);
+        if (live) p = P.hard ? (k == arg ? 1.f : 0.f) : fminf(expf((float)(v - mx)) * inv, 1.f);
         if (KREG > 0) s_aff[tid * (P.K + 1) + k] = p;          // written out as one contiguous 128 x K block below
         else if (live) P.aff[n * P.K + k] = p;
         const uint32_t wmax = __reduce_max_sync(0xffffffffu, __float_as_uint(p));     // p >= 0: bit patterns order like values
@@ -1126,14 +1074,14 @@ __global__ void __launch_bounds__(128) em_posterior4_kernel(PostArgs P) {
     if (P.done && *P.done) return;
     extern __shared__ __align__(16) uint8_t psm[];
     float* s_aff = reinterpret_cast<float*>(psm);                      // [32][K + 1]
-    __shared__ df s_mx[4][32], s_sc[4][32], s_sum[4][32];
+    __shared__ double s_mx[4][32], s_sc[4][32], s_sum[4][32];
     __shared__ int s_arg[4][32];
     const int lane = threadIdx.x & 31, q = threadIdx.x >> 5;
     const long long n = blockIdx.x * 32LL + lane;
     const bool live = n < P.N;
     const size_t pstride = (size_t)P.KT * P.Npad;
     constexpr int KQ = 8;
-    df sv[KQ];
+    double sv[KQ];
     int a0[KQ], a1[KQ], a2[KQ];
     if (INT_SCORES) {
         int* a = P.accE + n;
@@ -1147,53 +1095,53 @@ __global__ void __launch_bounds__(128) em_posterior4_kernel(PostArgs P) {
             const int k = q + 4 * j;
             if (k < P.K) {
                 a[(size_t)k * P.Npad] = 0; a[(size_t)k * P.Npad + pstride] = 0; a[(size_t)k * P.Npad + 2 * pstride] = 0;
-                sv[j] = em_score_df(a0[j], a1[j], a2[j], P.scale[k], P.c[k]);
+                const double qq = (double)a0[j] + 256.0 * (double)a1[j] + 65536.0 * (double)a2[j];
+                sv[j] = qq * (double)P.scale[k] + (double)P.c[k] * (1.0 / EM_C_SCALE);
             }
         }
     } else {
 #pragma unroll
         for (int j = 0; j < KQ; ++j) {
             const int k = q + 4 * j;
-            if (k < P.K) sv[j] = df{P.scratch[(size_t)k * P.Npad + n], 0.f};
+            if (k < P.K) sv[j] = (double)P.scratch[(size_t)k * P.Npad + n];
         }
     }
     // partial maxima of this warp's components
-    df mx = df{-INFINITY, 0.f}, smx = df{-INFINITY, 0.f};
+    double mx = -INFINITY, smx = -INFINITY;
     int arg = 0x7fffffff;
 #pragma unroll
     for (int j = 0; j < KQ; ++j) {
         const int k = q + 4 * j;
         if (k < P.K) {
-            if (live && P.scores_out) P.scores_out[n * P.K + k] = sv[j].h;
-            if (df_gt(sv[j], smx)) { smx = sv[j]; arg = k; }
-            sv[j] = df_add_f(sv[j], P.logw[k]);                // from here on: score + log weight
-            mx = df_max(mx, sv[j]);
+            if (live && P.scores_out) P.scores_out[n * P.K + k] = (float)sv[j];
+            if (sv[j] > smx) { smx = sv[j]; arg = k; }
+            mx = fmax(mx, sv[j] + (double)P.logw[k]);
         }
     }
     if (!P.update) return;
     s_mx[q][lane] = mx; s_sc[q][lane] = smx; s_arg[q][lane] = arg;
     __syncthreads();
-    mx = df_max(df_max(s_mx[0][lane], s_mx[1][lane]), df_max(s_mx[2][lane], s_mx[3][lane]));
+    mx = fmax(fmax(s_mx[0][lane], s_mx[1][lane]), fmax(s_mx[2][lane], s_mx[3][lane]));
     // hard assignment: first arg-max of the template scores (:273-275): largest score, lowest index among equals
     smx = s_sc[0][lane]; arg = s_arg[0][lane];
 #pragma unroll
     for (int w = 1; w < 4; ++w) {
-        const df o = s_sc[w][lane];
+        const double o = s_sc[w][lane];
         const int oa = s_arg[w][lane];
-        if (df_gt(o, smx) || (o.h == smx.h && o.l == smx.l && oa < arg)) { smx = o; arg = oa; }
+        if (o > smx || (o == smx && oa < arg)) { smx = o; arg = oa; }
     }
     float ev[KQ];
-    df sum = df{0.f, 0.f};
+    double sum = 0.0;
 #pragma unroll
     for (int j = 0; j < KQ; ++j) {
         const int k = q + 4 * j;
         ev[j] = 0.f;
-        if (k < P.K) { ev[j] = expf(df_diff(sv[j], mx)); sum = df_add_f(sum, ev[j]); }
+        if (k < P.K) { ev[j] = expf((float)(sv[j] + (double)P.logw[k] - mx)); sum += (double)ev[j]; }
     }
     s_sum[q][lane] = sum;
     __syncthreads();
-    sum = df_add(df_add(s_sum[0][lane], s_sum[1][lane]), df_add(s_sum[2][lane], s_sum[3][lane]));
-    const float inv = 1.f / sum.h;
+    sum = (s_sum[0][lane] + s_sum[1][lane]) + (s_sum[2][lane] + s_sum[3][lane]);
+    const float inv = (float)(1.0 / sum);
 #pragma unroll
     for (int j = 0; j < KQ; ++j) {
         const int k = q + 4 * j;
@@ -1206,7 +1154,7 @@ __global__ void __launch_bounds__(128) em_posterior4_kernel(PostArgs P) {
         }
     }
     if (q == 0) {
-        long long my_ll = live ? em_ll_fixed(sum, mx) : 0;
+        long long my_ll = live ? llrint((log(sum) + mx) * EM_LL_SCALE) : 0;
         for (int off = 16; off > 0; off >>= 1) my_ll += __shfl_xor_sync(0xffffffffu, my_ll, off);
         if (lane == 0) atomicAdd(reinterpret_cast<unsigned long long*>(P.llQ + blockIdx.x % EM_SLOTS), (unsigned long long)my_ll);
     }
