@@ -360,7 +360,7 @@ def run_native(args):
     #                them to 1 byte per (t,f) before the copy (tsr_host_pack_edges: data movement only)
     #   e2e_packed   the caller already holds packed edge bytes (B,300,40)
     #   e2e_device_pack  the unpacked tensor is copied (8x the bytes) and packed on the GPU (round-1 path)
-    e2e_steps = max(4, args.steps)
+    e2e_steps = max(4, 3 * args.steps)      # a longer call than the device-timed region: fill and drain are inside the clock
     P_pinned = torch.from_numpy(np.packbits(X != 0, axis=-1, bitorder="little")[..., 0].copy()).pin_memory()
 
     def e2e_run(feed, **kw):
@@ -559,7 +559,7 @@ def em_bench(ctx, args, steps, warmup):
             graph.replay()
         else:
             drv._iteration(False, 0, ctl, 0.05)
-    ms = _timed(torch, dist, world, dev, step, steps, warmup)
+    ms = _timed(torch, dist, world, dev, step, steps, warmup) / (drv.graph_iters if graph is not None else 1)   # a replay may hold two iterations
     done, iters, trace = ctl.read()
     # the pieces, each timed alone (events around `steps` back-to-back calls)
     parts = {}
@@ -567,7 +567,15 @@ def em_bench(ctx, args, steps, warmup):
     parts["mstep_ms"] = _timed(torch, dist, world, dev, lambda: eng.accumulate(0), steps, 1)
     parts["finalize_ms"] = _timed(torch, dist, world, dev, lambda: eng.finalize(eng.stats, N * 64, 0.05, drv.params), steps, 1)
     scratch = torch.zeros_like(eng.stats)
-    parts["allreduce_ms"] = _timed(torch, dist, world, dev, lambda: dist.all_reduce(scratch), max(steps, 20), 3) if world > 1 else 0.0
+    if world > 1 and drv.peer is not None:      # the library's own one-launch sum over NVLink peer memory
+        slot = [0]
+
+        def peer_sum():
+            drv.peer.allreduce(slot[0] & 1, scratch); slot[0] += 1
+        parts["allreduce_ms"] = _timed(torch, dist, world, dev, peer_sum, max(steps, 20), 4)
+        parts["nccl_allreduce_ms"] = _timed(torch, dist, world, dev, lambda: dist.all_reduce(scratch), max(steps, 20), 3)
+    else:
+        parts["allreduce_ms"] = _timed(torch, dist, world, dev, lambda: dist.all_reduce(scratch), max(steps, 20), 3) if world > 1 else 0.0
     peaks = measured_peaks()
     xbytes = 2.0 * (hi - lo) * D / 8.0                                   # the bit rows once for E and once (transposed) for M
     out = {"metric": "Bernoulli-mixture EM iteration time (control + finalize + E + M + allreduce)", "ms_per_iter": ms, "unit": "ms",
@@ -575,7 +583,10 @@ def em_bench(ctx, args, steps, warmup):
            "dtype": "u8 {0,1} x int8 (3 base-256 digit planes) -> int32 exact; float64 statistics",
            "config": {"workload": "config4 bernoulli_em", "N": N, "D": D, "K": K, "rows_per_gpu": hi - lo,
                       "allreduce_bytes": int(eng.stats.numel() * 8), "allreduces_per_iter": 1 if world > 1 else 0,
-                      "host_syncs_per_iter": 0, "cuda_graph": graph is not None},
+                      "host_syncs_per_iter": 0, "cuda_graph": graph is not None,
+                      "allreduce": ("tsr_em_allreduce_peer: one kernel over NVLink peer memory (symmetric allocation), rank-ordered sums"
+                                    if drv.peer is not None else ("nccl all_reduce" + (" (peer path unavailable: %s)" % drv.peer_error if drv.peer_error else "")))
+                      if world > 1 else "none"},
            "roofline": {"kernel": "bitgemm_kernel (E and M contractions)", "bound": "hbm", "achieved": xbytes / (ms * 1e-3) / 1e9,
                         "peak": peaks["hbm"], "unit": "GB/s", "frac": xbytes / (ms * 1e-3) / 1e9 / peaks["hbm"], "traffic": None,
                         "note": "algorithmic bytes = the bit-packed rows read once by the E contraction and once (transposed copy) by the M "

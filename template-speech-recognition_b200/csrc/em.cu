@@ -1300,6 +1300,94 @@ __global__ void em_control_kernel(EmCtl* ctl, const double* stats_ll) {
     ctl->iterations++;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Sum of the ranks' statistics vectors over NVLink peer memory (one launch, no NCCL call): every rank keeps its
+// vector in a symmetric allocation that all peers have mapped; rank r's CTA b
+//   1. publishes "rank r has finished writing its vector" by storing the launch's epoch into slot [r][b] of every
+//      peer's flag array (system-scope release; the vector was written by earlier kernels of the same stream),
+//   2. waits until slot [t][b] of its own flag array carries the epoch for every peer t (system-scope acquire),
+//   3. reads its share of all W vectors straight from the peers' memory and adds them in rank order (every rank
+//      forms the same sums in the same order: bit-identical results on all ranks) into a LOCAL output vector.
+// The caller alternates between two symmetric source vectors (epoch parity): a rank can only overwrite a source two
+// iterations later, after it has passed the next launch's step 2, which every peer reaches only after its own reads
+// of this launch are complete (stream order) -- so no closing barrier is needed.  Per-CTA flags make step 2 a
+// per-CTA wait instead of a grid-wide one.  Once the control block has stopped, every rank skips the launch alike.
+#define EM_AR_CTAS 64
+struct PeerArgs {
+    const uint8_t* const* bufs;     // device array [world]: base of every rank's symmetric allocation
+    long long src_off, flag_off;    // byte offsets of the source vector and of the flag array [world][EM_AR_CTAS] uint32
+    long long n;                    // doubles
+    double* out;
+    unsigned int* epoch;            // [EM_AR_CTAS] launch counters of this rank (zero-initialised once)
+    int rank, world;
+    const int* done;
+};
+__device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
+    unsigned int v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// no "memory" clobber: the loads of one element from all peers may be in flight together (an NVLink round trip is ~2 us);
+// they are issued after the __syncthreads that follows the flag acquire, which the compiler does not move them across
+__device__ __forceinline__ double2 ld_relaxed_sys_f64x2(const double* p) {
+    double2 v;
+    asm volatile("ld.relaxed.sys.global.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    return v;
+}
+__global__ void __launch_bounds__(1024) em_allreduce_peer_kernel(PeerArgs P) {
+    if (P.done && *P.done) return;
+    __shared__ unsigned int s_epoch;
+    const int b = blockIdx.x;
+    if (threadIdx.x == 0) s_epoch = ++P.epoch[b];
+    __syncthreads();
+    const unsigned int e = s_epoch;
+    if ((int)threadIdx.x < P.world) {
+        const int t = threadIdx.x;
+        // (the vector was written by earlier kernels of this stream: the release below is cumulative over it)
+        unsigned int* theirs = reinterpret_cast<unsigned int*>(const_cast<uint8_t*>(P.bufs[t]) + P.flag_off);
+        st_release_sys(theirs + (size_t)P.rank * EM_AR_CTAS + b, e);
+        const unsigned int* mine = reinterpret_cast<const unsigned int*>(P.bufs[P.rank] + P.flag_off);
+        unsigned int spins = 0;
+        while (ld_acquire_sys(mine + (size_t)t * EM_AR_CTAS + b) < e) {       // epochs only grow: "<" tolerates a peer one launch ahead
+            __nanosleep(20);
+            if (++spins > (1u << 26)) {
+                printf("tsr_b200: peer allreduce timed out waiting for rank %d (rank %d block %d epoch %u)\n", t, P.rank, b, e);
+                __trap();
+            }
+        }
+    }
+    __syncthreads();
+    const long long npair = P.n >> 1;
+    for (long long i = (long long)b * blockDim.x + threadIdx.x; i < npair; i += (long long)gridDim.x * blockDim.x) {
+        double2 acc = make_double2(0.0, 0.0);
+        for (int t0 = 0; t0 < P.world; t0 += 8) {          // up to 8 peers' loads in flight, added in rank order
+            double2 v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                if (t0 + u < P.world) {
+                    const double* q = reinterpret_cast<const double*>(P.bufs[t0 + u] + P.src_off) + 2 * i;
+                    v[u] = (t0 + u == P.rank) ? *reinterpret_cast<const double2*>(q) : ld_relaxed_sys_f64x2(q);
+                }
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                if (t0 + u < P.world) { acc.x += v[u].x; acc.y += v[u].y; }
+        }
+        reinterpret_cast<double2*>(P.out)[i] = acc;
+    }
+    if ((P.n & 1) && b == 0 && threadIdx.x == 0) {
+        double acc = 0.0;
+        for (int t = 0; t < P.world; ++t) {
+            double v;
+            asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(reinterpret_cast<const double*>(P.bufs[t] + P.src_off) + P.n - 1) : "memory");
+            acc += v;
+        }
+        P.out[P.n - 1] = acc;
+    }
+}
+
 // XT[d][n] = X[n][d]: each warp transposes a 32x32 bit block with 32 ballots.
 __global__ void transpose_bits_kernel(const uint32_t* __restrict__ X, long long N, int D, int rowwords,
                                       uint32_t* __restrict__ XT, long long nt_words) {
@@ -1519,6 +1607,26 @@ int tsr_em_mstep(const uint32_t* Xbits, const uint32_t* XTbits_or_null, const ui
     em_pack_kernel<<<dim3((unsigned)((D + 255) / 256), (unsigned)K), 256, 0, st>>>((int*)(ws + s.off_accM), D, s.Dpad, K, s.KT, s.mrp, sm.sk,
                                                                                    stats, done);
     return check_launch("tsr_em_mstep(pack)");
+}
+
+size_t tsr_em_peer_flag_bytes(int world) { return world < 1 ? 0 : (size_t)world * EM_AR_CTAS * sizeof(unsigned int); }
+size_t tsr_em_peer_epoch_bytes(void) { return EM_AR_CTAS * sizeof(unsigned int); }
+
+int tsr_em_allreduce_peer(const void* const* peer_bufs_dev, int rank, int world, long long src_offset_bytes, long long flag_offset_bytes,
+                          long long n_doubles, double* out, void* epoch_counters, const void* ctl_or_null, void* stream) {
+    TSR_REQUIRE(peer_bufs_dev && out && epoch_counters, "tsr_em_allreduce_peer: null pointer");
+    TSR_REQUIRE(world >= 1 && world <= 64 && rank >= 0 && rank < world, "tsr_em_allreduce_peer: bad rank %d / world %d", rank, world);
+    TSR_REQUIRE(n_doubles >= 0 && (src_offset_bytes & 15) == 0 && (flag_offset_bytes & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
+                "tsr_em_allreduce_peer: offsets / output must be 16-byte aligned");
+    int rc = require_sm100("tsr_em_allreduce_peer");
+    if (rc) return rc;
+    PeerArgs P;
+    P.bufs = reinterpret_cast<const uint8_t* const*>(peer_bufs_dev);
+    P.src_off = src_offset_bytes; P.flag_off = flag_offset_bytes; P.n = n_doubles; P.out = out;
+    P.epoch = (unsigned int*)epoch_counters; P.rank = rank; P.world = world;
+    P.done = ctl_or_null ? &((const EmCtl*)ctl_or_null)->done : nullptr;
+    em_allreduce_peer_kernel<<<EM_AR_CTAS, 1024, 0, (cudaStream_t)stream>>>(P);
+    return check_launch("tsr_em_allreduce_peer");
 }
 
 int tsr_em_finalize(const double* stats, long long N_total, int D, int K, float min_prob, float* templates, float* logT,

@@ -15,6 +15,8 @@ the device: the host queues ``batch`` iterations at a time and reads the control
 per batch; iterations past the stop are no-ops.  With a single
 rank no collective is issued.  Scoring/coding/detection never communicate.
 """
+import os
+
 import numpy as np
 import torch
 
@@ -65,16 +67,20 @@ class GpuEmEngine:
     def stats(self):
         return self.state.stats
 
-    def estep(self, params, hard, impl=0, ctl=None, prepared=False):
+    def estep(self, params, hard, impl=0, ctl=None, prepared=False, stats=None):
         """Posteriors for the local rows; fills the responsibility sums and the log-likelihood of stats.
         prepared: the weight planes were laid out by the last finalize (skip the per-call preparation)."""
         lt, li = (None, None) if (prepared and impl == 0) else (params["logT"], params["logInvT"])
-        self.state.estep(lt, li, params["logw"], hard=hard, impl=impl, ctl=ctl)
+        self.state.estep(lt, li, params["logw"], hard=hard, impl=impl, ctl=ctl, stats=stats)
 
-    def accumulate(self, impl=0, from_affinities=False, ctl=None):
+    def accumulate(self, impl=0, from_affinities=False, ctl=None, stats=None):
         """stats[:K*D] = aff^T X over the local rows (from_affinities: from self.affinities(), also setting the
         responsibility sums -- used to initialise templates from a hard assignment)."""
-        self.state.mstep_accumulate(impl=impl, aff=self.state.aff if from_affinities else None, ctl=ctl)
+        self.state.mstep_accumulate(impl=impl, aff=self.state.aff if from_affinities else None, ctl=ctl, stats=stats)
+
+    def peer_stats(self, group):
+        """Peer-mapped home of the statistics vector (NVLink one-shot allreduce), or raises."""
+        return self.ops.PeerStats(self.state.stats.numel(), self.device, group)
 
     def loglik(self):
         return self.state.loglik()
@@ -105,18 +111,47 @@ class EmDriver:
         if group is False:
             self.dist = False
         self.allreduces = 0
+        self.graph_iters = 1
+        # Sharded rows on GPUs of one NVLink domain: the sum of the statistics is ONE kernel of this library over peer
+        # memory (ops.PeerStats / tsr_em_allreduce_peer) instead of an NCCL call; NCCL stays the path for engines or
+        # systems without symmetric memory (and the CPU/gloo tests).  TSR_EM_PEER=0 forces NCCL.
+        self.peer, self.peer_error, self.it = None, None, 0
+        if self.dist and hasattr(engine, "peer_stats") and os.environ.get("TSR_EM_PEER", "1") != "0":
+            ok = 0
+            try:
+                self.peer = engine.peer_stats(self.group if self.group not in (None, False) else None)
+                ok = 1
+            except Exception as exc:  # noqa: BLE001 -- no symmetric memory here: NCCL
+                self.peer_error = "%s: %s" % (type(exc).__name__, exc)
+            flag = torch.tensor([ok], dtype=torch.int32, device=engine.device)
+            torch.distributed.all_reduce(flag, op=torch.distributed.ReduceOp.MIN,
+                                         group=self.group if self.group not in (None, False) else None)
+            if int(flag.item()) == 0:          # all ranks or none
+                self.peer = None
 
-    def _allreduce(self, t):
-        if self.dist:
-            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.SUM,
+    def _src(self):
+        """Where this iteration's local statistics go: the engine's vector, or the peer-mapped slot of this parity."""
+        return None if self.peer is None else self.peer.src[self.it & 1]
+
+    def _allreduce(self, ctl=None):
+        """Global statistics -> engine.stats on every rank (the ONE collective of an iteration)."""
+        if self.peer is not None:
+            self.peer.allreduce(self.it & 1, self.e.stats, ctl)
+            self.it += 1
+            self.allreduces += 1
+        elif self.dist:
+            torch.distributed.all_reduce(self.e.stats, op=torch.distributed.ReduceOp.SUM,
                                          group=self.group if self.group not in (None, False) else None)
             self.allreduces += 1
 
     def _estep(self, hard, impl, ctl, prepared, accumulate=True):
-        self.e.estep(self.params, hard, impl, ctl=ctl, prepared=prepared)
+        kw = {} if self.peer is None else {"stats": self._src()}
+        self.e.estep(self.params, hard, impl, ctl=ctl, prepared=prepared, **kw)
         if accumulate:
-            self.e.accumulate(impl, ctl=ctl)
-        self._allreduce(self.e.stats)          # the ONE collective of an iteration
+            self.e.accumulate(impl, ctl=ctl, **kw)
+        elif self.peer is not None:
+            self.peer.src[self.it & 1][:self.e.K * self.e.D].zero_()      # no numerators this time: the slot's are stale
+        self._allreduce(ctl)
 
     def expectation(self, hard=False, impl=0, accumulate=True):
         """E-step (+ numerator accumulation) on every rank, then the sufficient-statistics
@@ -141,15 +176,21 @@ class EmDriver:
         import os
         if not getattr(self.e, "graph_ok", False) or os.environ.get("TSR_EM_NO_GRAPH"):
             return None
+        # the peer allreduce alternates between two source slots: the graph then holds an even number of iterations
+        self.graph_iters = 2 if self.peer is not None else 1
         try:
+            if self.peer is not None and (self.it & 1):
+                self._iteration(hard, impl, ctl, min_prob)      # start the captured pair on an even launch
             side = torch.cuda.Stream(device=self.e.device)
             side.wait_stream(torch.cuda.current_stream(self.e.device))
             with torch.cuda.stream(side):
-                self._iteration(hard, impl, ctl, min_prob)      # warm-up on the capture stream (a real iteration)
+                for _ in range(self.graph_iters):
+                    self._iteration(hard, impl, ctl, min_prob)  # warm-up on the capture stream (real iterations)
             torch.cuda.current_stream(self.e.device).wait_stream(side)
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g, stream=side):
-                self._iteration(hard, impl, ctl, min_prob)
+                for _ in range(self.graph_iters):
+                    self._iteration(hard, impl, ctl, min_prob)
             return g
         except Exception:  # noqa: BLE001 -- e.g. a collective that cannot be captured: fall back to eager launches
             torch.cuda.synchronize()
@@ -163,7 +204,7 @@ class EmDriver:
         self._estep(hard, impl, ctl, False)                         # first E-step (:135)
         graph = self.capture_iteration(hard, impl, ctl, min_prob)   # (runs one real iteration while warming up)
         while True:
-            for _ in range(max(1, int(batch))):
+            for _ in range(max(1, int(batch)) // (self.graph_iters if graph is not None else 1) or 1):
                 if graph is not None:
                     graph.replay()
                 else:
@@ -176,8 +217,9 @@ class EmDriver:
         """Templates = affinity-weighted data means (the deterministic round-robin 'unif_rand'
         start of bernoulli_mixture.py:195-237); weights stay uniform as in the reference."""
         K = self.e.K
-        self.e.accumulate(from_affinities=True)
-        self._allreduce(self.e.stats)
+        kw = {} if self.peer is None else {"stats": self._src()}
+        self.e.accumulate(from_affinities=True, **kw)
+        self._allreduce()
         self.e.finalize(self.e.stats, self.N_total, float(min_prob), self.params)
         if uniform_weights:
             self.params["weights"].fill_(1.0 / K)

@@ -521,22 +521,25 @@ class EmState:
         # stats = [K*D numerators | K responsibility sums | log-likelihood], float64 (see tsr_b200.h)
         self.stats = torch.zeros(self.K * self.D + self.K + 1, dtype=torch.float64, device=dev)
 
-    def estep(self, logT, logInvT, logw, hard=False, impl=IMPL_TENSOR, scores_out=None, update=True, ctl=None):
-        """logT = logInvT = None: use the weight planes the last em_finalize(..., state=self) laid out."""
+    def estep(self, logT, logInvT, logw, hard=False, impl=IMPL_TENSOR, scores_out=None, update=True, ctl=None, stats=None):
+        """logT = logInvT = None: use the weight planes the last em_finalize(..., state=self) laid out.
+        stats: write this rank's statistics there instead of self.stats (a peer-mapped source slot, see PeerStats)."""
+        stats = self.stats if stats is None else stats
         with torch.cuda.device(self.X.device):
             _lib.call("tsr_em_estep", _ptr(self.X), _ptr(self.Xt), self.N, self.D, self.rw, self.K, _ptr(logT), _ptr(logInvT), _ptr(logw),
-                      _ptr(self.aff) if update else 0, _ptr(scores_out), _ptr(self.stats) if update else 0, int(bool(hard)),
+                      _ptr(self.aff) if update else 0, _ptr(scores_out), _ptr(stats) if update else 0, int(bool(hard)),
                       int(bool(update)), _ptr(self.ws), _ptr(ctl.buf) if ctl is not None else 0, int(impl), _stream())
 
-    def mstep_accumulate(self, impl=IMPL_TENSOR, aff=None, ctl=None):
+    def mstep_accumulate(self, impl=IMPL_TENSOR, aff=None, ctl=None, stats=None):
         """stats[:K*D] = numerators from the last E-step's posteriors, or from `aff` (N,K) float32 when given
         (then the responsibility sums are taken from it too)."""
+        stats = self.stats if stats is None else stats
         if aff is not None:
             aff = _dev(aff, torch.float32, "aff")
         elif impl == IMPL_SIMT:
             aff = self.aff
         with torch.cuda.device(self.X.device):
-            _lib.call("tsr_em_mstep", _ptr(self.X), 0, _ptr(self.XTt), self.N, self.D, self.rw, self.K, _ptr(aff), _ptr(self.stats),
+            _lib.call("tsr_em_mstep", _ptr(self.X), 0, _ptr(self.XTt), self.N, self.D, self.rw, self.K, _ptr(aff), _ptr(stats),
                       _ptr(self.ws), _ptr(ctl.buf) if ctl is not None else 0, int(impl), _stream())
 
     def numerators(self):
@@ -547,6 +550,41 @@ class EmState:
 
     def loglik(self):
         return float(self.stats[self.K * self.D + self.K].item())
+
+
+class PeerStats:
+    """Home of a rank's EM statistics vector in NVLink peer-mapped (symmetric) memory, for tsr_em_allreduce_peer:
+    one allocation per rank holding two source slots (alternated from launch to launch) and the flag array, mapped
+    by every rank of `group`.  Raises when symmetric memory is unavailable (the driver then keeps the NCCL allreduce)."""
+
+    def __init__(self, n, device, group=None):
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        group = dist.group.WORLD if group is None else group
+        self.world, self.rank, self.n = dist.get_world_size(group), dist.get_rank(group), int(n)
+        self.slot_bytes = (self.n * 8 + 255) // 256 * 256
+        self.flag_off = 2 * self.slot_bytes
+        total = self.flag_off + int(_lib.lib().tsr_em_peer_flag_bytes(self.world))
+        with torch.cuda.device(device):
+            self.buf = symm.empty(total, dtype=torch.uint8, device=device)
+            self.buf.zero_()
+            self.handle = symm.rendezvous(self.buf, group.group_name if hasattr(group, "group_name") else group)
+            ptrs = [int(p) for p in self.handle.buffer_ptrs]
+            if len(ptrs) != self.world or ptrs[self.rank] != self.buf.data_ptr():
+                raise RuntimeError("symmetric memory rendezvous returned unexpected peer pointers")
+            self.ptrs = torch.tensor(ptrs, dtype=torch.int64, device=device)
+            self.epoch = torch.zeros(int(_lib.lib().tsr_em_peer_epoch_bytes()) // 4, dtype=torch.int32, device=device)
+            self.src = [self.buf[i * self.slot_bytes:i * self.slot_bytes + self.n * 8].view(torch.float64) for i in (0, 1)]
+            torch.cuda.synchronize(device)
+        dist.barrier(group)                     # every rank's flags are zero before anybody signals
+        self.launches = 0
+
+    def allreduce(self, slot, out, ctl=None):
+        """out (local float64 [n]) = sum over ranks of their source slot `slot`; one kernel launch on the current stream."""
+        with torch.cuda.device(out.device):
+            _lib.call("tsr_em_allreduce_peer", _ptr(self.ptrs), self.rank, self.world, int(slot) * self.slot_bytes, self.flag_off, self.n,
+                      _ptr(out), _ptr(self.epoch), _ptr(ctl.buf) if ctl is not None else 0, _stream())
+        self.launches += 1
 
 
 def em_finalize(stats, N_total, D, K, min_prob, templates, logT, logInvT, weights, logw, state=None, ctl=None):

@@ -29,6 +29,6 @@ if rank == 0:
 dist.barrier()
 
 if rank == 0:
-    print("allreduces issued:", m._drv.allreduces)
+    print("allreduces issued:", m._drv.allreduces, "| path:", "peer-memory kernel" if m._drv.peer is not None else "nccl (%s)" % m._drv.peer_error)
 dist.barrier()
 dist.destroy_process_group()
