@@ -1574,7 +1574,10 @@ static int detect_tn_launch(DetectArgs& A, cudaStream_t st) {
         if (sr < min_rows) sr = min_rows;
         const long long waves = ((long long)f.ntiles * U + nsm - 1) / nsm;
         const long long cost = waves * steps * (sr + 8);        // + a per-step constant (accumulator hand-over)
-        if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_U = (int)U; best_steps = (int)steps; best_sr = (int)sr; }
+        // ties go to more units as long as they fit one wave: every SM gets a unit and each unit fewer padded rows
+        if (best_cost < 0 || cost < best_cost || (cost == best_cost && (long long)f.ntiles * U <= nsm)) {
+            best_cost = cost; best_U = (int)U; best_steps = (int)steps; best_sr = (int)sr;
+        }
     }
     A.units_per_ntile = best_U;
     A.rows_per_unit = (int)((R + best_U - 1) / best_U);
@@ -1589,7 +1592,9 @@ static int detect_tn_launch(DetectArgs& A, cudaStream_t st) {
 #ifdef TSR_DEBUG_TRACE
     if (const char* ov = getenv("TSR_DEBUG_DETECT_FLAGS")) A.dbg = atoi(ov);   // timing experiments, wrong results
 #endif
+#ifdef TSR_DEBUG_TRACE
     if (const char* ov = getenv("TSR_DEBUG_DETECT_NISSUE")) A.nissue = ov[0] == '1' ? 1 : 2;   // experiments only
+#endif
     const long long nunits = (long long)f.ntiles * best_U;
     const int blocks = (int)(nunits < nsm ? nunits : nsm);
     if (A.nissue == 2) {
@@ -1664,7 +1669,9 @@ static int detect_impl(const uint32_t* featbits, int B, int T, int D, int rowwor
         // Two issuer warps lift config 3 (32 templates, bank L2 resident) from 141 to 128 cycles per MMA, 2.62 -> 2.49 ms,
         // but slow the 1000-template stream (bank 438 MB, streamed through L2 group by group) from 264 to 290 ms.
         A.nissue = (size_t)A.f.ntiles * set_bytes <= ((size_t)64 << 20) ? 2 : 1;
+#ifdef TSR_DEBUG_TRACE
         if (const char* ov = getenv("TSR_DEBUG_DETECT_NISSUE")) A.nissue = ov[0] == '2' ? 2 : 1;   // experiments only
+#endif
     }
     A.rows_per_unit = (int)((R + best_U - 1) / best_U);
     A.steps_per_unit = (A.rows_per_unit + A.f.Lc + step_rows - 1) / step_rows;
