@@ -347,6 +347,18 @@ def run_native(args):
     torch.cuda.synchronize()
     dfl_ms = float(np.mean([a.elapsed_time(b) for a, b in dfl]))
     dfl_flop = 2.0 * 64 * (T_FRAMES - L_TEMPL + 1) * L_TEMPL * F_BANDS * E_EDGES * 8
+    # ... and at the shape the reference calls them with (get_train_data.py:1055-1079: ONE utterance's spectrogram against one
+    # spectral template per call, a handful of mixture components): 300 frames x 160 bands, 40-frame template
+    F1 = torch.rand((1, T_FRAMES, 160), device=dev, generator=gf)
+    LF1 = torch.randn((1, L_TEMPL, 160), device=dev, generator=gf)
+    ops.detect_float(F1, LF1)
+    dfl1 = []
+    for _ in range(5):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream); ops.detect_float(F1, LF1); e1.record(stream)
+        dfl1.append((e0, e1))
+    torch.cuda.synchronize()
+    dfl1_us = 1e3 * float(np.mean([a.elapsed_time(b) for a, b in dfl1]))
     total_ms = float(sum(step_ms))
     t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -426,7 +438,10 @@ def run_native(args):
                              "frac": dfl_flop / (dfl_ms * 1e-3) / (148 * 128 * (clocks or {}).get("sm_max_mhz", 1965.0) * 1e6),
                              "shape": "64 utterances x 300 frames x 320 real features, 8 templates x 40 frames (detect_float_max)",
                              "note": "not in the step: the real-valued detectors reproduce the reference's float32 rounding bit for bit, "
-                                     "which fixes the order of every output's L*D additions; peak = one fp32 instruction per lane and clock"},
+                                     "which fixes the order of every output's L*D additions; peak = one fp32 instruction per lane and clock",
+                             "reference_call_shape_us": dfl1_us,
+                             "reference_call_shape": "1 utterance x 300 frames x 160 bands, one 40-frame spectral template (get_train_data.py:1055-1079): "
+                                                     "3.3 MFLOP per call, launch / latency bound on any path"},
             "config2_coding_frames_per_s": B * T_FRAMES * world / (sum(stage_ms[:2]) * 1e-3),
         }
         line = {

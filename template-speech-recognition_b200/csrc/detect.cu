@@ -1355,60 +1355,76 @@ __global__ void detect_simt_kernel(const uint32_t* __restrict__ bits, const floa
 // the 128 x 32 window of features is staged coalesced (pitch 33: row-per-thread reads are conflict free) next to the
 // DF_TM weight rows (broadcast reads); a thread owns one row and DF_TM independent accumulators: 1 + DF_TM shared loads
 // for 2 * DF_TM arithmetic instructions per feature, no global load in the inner loop.
-#define DF_TM 4     // DF_TM * DF_DC must equal the 128 threads of a CTA (one weight per thread and step)
-#define DF_DC 32
+// TM = templates per thread (independent chains; their weights are broadcast LDS.128), DC = features per staged step.
+// TM = 8 when the grid still fills the SMs several times over, else 4 (more CTAs); DC = 64 for launches of at most one CTA
+// per SM (fewer steps: a step costs two barriers and exposes part of a global-load latency, which is what a single-utterance
+// call consists of), else 32 (128 instead of 243 registers).
+template <int TM, int DC>
 __global__ void __launch_bounds__(128) detect_float_kernel(const float* __restrict__ Fm, const float* __restrict__ LF,
                                                            const float* __restrict__ init, float* __restrict__ scores, long long R,
                                                            int T, int D, int M, int L) {
-    __shared__ float sx[128 * (DF_DC + 1)];
-    __shared__ float sw[DF_TM * DF_DC];
+    __shared__ float sx[128 * (DC + 1)];
+    __shared__ __align__(16) float sw[DC * TM];                // [feature c][template j]
     const int tid = threadIdx.x;
     const long long g0 = (long long)blockIdx.x * 128;
-    const int m0 = blockIdx.y * DF_TM;
+    const int m0 = blockIdx.y * TM;
     const long long g = g0 + tid;
     const bool valid = g < R && (int)(g % T) <= T - L;
-    float acc[DF_TM];
+    float acc[TM];
 #pragma unroll
-    for (int j = 0; j < DF_TM; ++j) acc[j] = (init && m0 + j < M) ? init[m0 + j] : 0.f;     // detect_float_max starts at cs[m] (:258)
-    // (tau, chunk) steps in the reference's order; the next step's 128 x 32 window and weight rows are fetched into
-    // registers while the current one is being consumed from shared memory
-    const int nd = (D + DF_DC - 1) / DF_DC;
+    for (int j = 0; j < TM; ++j) acc[j] = (init && m0 + j < M) ? init[m0 + j] : 0.f;     // detect_float_max starts at cs[m] (:258)
+    // (tau, chunk) steps in the reference's order; the next step's 128 x DC window and weight rows are fetched into
+    // registers while the current one is being consumed from shared memory.  Per feature a thread issues 1 + TM/4 shared
+    // loads (its x, float4s of weights) for 2 TM arithmetic instructions.
+    const int nd = (D + DC - 1) / DC;
     const int nstep = L * nd;
-    float px[DF_DC], pw = 0.f;
+    constexpr int NW = TM * DC / 128;                           // weights per thread and step
+    float px[DC], pw[NW];
     auto fetch = [&](int step) {
-        const int tau = step / nd, d0 = (step - tau * nd) * DF_DC;
-        const int dc = D - d0 < DF_DC ? D - d0 : DF_DC;
+        const int tau = step / nd, d0 = (step - tau * nd) * DC;
+        const int dc = D - d0 < DC ? D - d0 : DC;
 #pragma unroll
-        for (int i = 0; i < DF_DC; ++i) {                   // element e = tid + 128 i of the window: row e / 32, column e % 32
-            const int e = tid + 128 * i, r = e >> 5, c = e & 31;
+        for (int i = 0; i < DC; ++i) {                      // element e = tid + 128 i of the window: row e / DC, column e % DC
+            const int e = tid + 128 * i, r = e / DC, c = e % DC;
             const long long row = g0 + r + tau;
             px[i] = (row < R && c < dc) ? __ldg(Fm + row * D + d0 + c) : 0.f;
         }
-        const int j = tid >> 5, c = tid & 31;               // 128 threads = DF_TM x 32 weights
-        pw = (m0 + j < M && c < dc) ? __ldg(LF + ((size_t)(m0 + j) * L + tau) * D + d0 + c) : 0.f;
+#pragma unroll
+        for (int h = 0; h < NW; ++h) {                      // weight e = tid + 128 h: template e / DC, feature e % DC
+            const int e = tid + 128 * h, j = e / DC, c = e % DC;
+            pw[h] = (m0 + j < M && c < dc) ? __ldg(LF + ((size_t)(m0 + j) * L + tau) * D + d0 + c) : 0.f;
+        }
     };
     fetch(0);
     for (int step = 0; step < nstep; ++step) {
         __syncthreads();
 #pragma unroll
-        for (int i = 0; i < DF_DC; ++i) {
+        for (int i = 0; i < DC; ++i) {
             const int e = tid + 128 * i;
-            sx[(e >> 5) * (DF_DC + 1) + (e & 31)] = px[i];
+            sx[(e / DC) * (DC + 1) + (e % DC)] = px[i];
         }
-        sw[tid] = pw;
+#pragma unroll
+        for (int h = 0; h < NW; ++h) {
+            const int e = tid + 128 * h;
+            sw[(e % DC) * TM + (e / DC)] = pw[h];
+        }
         __syncthreads();
         if (step + 1 < nstep) fetch(step + 1);
-        const float* xr = sx + tid * (DF_DC + 1);
+        const float* xr = sx + tid * (DC + 1);
 #pragma unroll
-        for (int c = 0; c < DF_DC; ++c) {                  // columns past the end of the row hold zeros: x * w = +-0, acc unchanged
+        for (int c = 0; c < DC; ++c) {                     // columns past the end of the row hold zeros: x * w = +-0, acc unchanged
             const float x = xr[c];
 #pragma unroll
-            for (int j = 0; j < DF_TM; ++j) acc[j] = __fadd_rn(acc[j], __fmul_rn(sw[j * DF_DC + c], x));
+            for (int q = 0; q < TM / 4; ++q) {
+                const float4 w = *reinterpret_cast<const float4*>(sw + c * TM + 4 * q);
+                acc[4 * q + 0] = __fadd_rn(acc[4 * q + 0], __fmul_rn(w.x, x)); acc[4 * q + 1] = __fadd_rn(acc[4 * q + 1], __fmul_rn(w.y, x));
+                acc[4 * q + 2] = __fadd_rn(acc[4 * q + 2], __fmul_rn(w.z, x)); acc[4 * q + 3] = __fadd_rn(acc[4 * q + 3], __fmul_rn(w.w, x));
+            }
         }
     }
     if (g < R) {
 #pragma unroll
-        for (int j = 0; j < DF_TM; ++j)
+        for (int j = 0; j < TM; ++j)
             if (m0 + j < M) scores[g * M + m0 + j] = valid ? acc[j] : 0.f;
     }
 }
@@ -1745,9 +1761,16 @@ int tsr_detect_float(const float* Fm, int B, int T, int D, const float* LF, int 
     int rc = require_sm100("tsr_detect_float");
     if (rc) return rc;
     const long long R = (long long)B * T;
-    TSR_REQUIRE((R + 127) / 128 < (1ll << 31) && (M + DF_TM - 1) / DF_TM <= 65535, "tsr_detect_float: problem too large");
-    dim3 grid((unsigned)((R + 127) / 128), (unsigned)((M + DF_TM - 1) / DF_TM));
-    detect_float_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(Fm, LF, init_or_null, scores, R, T, D, M, L);
+    const long long rb = (R + 127) / 128;
+    const int tm = (rb * ((M + 7) / 8) >= 4LL * sm_count()) ? 8 : 4;
+    TSR_REQUIRE(rb < (1ll << 31) && (M + tm - 1) / tm <= 65535, "tsr_detect_float: problem too large");
+    dim3 grid((unsigned)rb, (unsigned)((M + tm - 1) / tm));
+    cudaStream_t st = (cudaStream_t)stream;
+    // measured (64 x 300 x 320 features, 8 templates): <4,32> 0.79 ms, <8,32> 0.89 ms (150 CTAs: too few), <4,64> 1.11 ms (243
+    // registers); one utterance x 160 bands x 1 template: <4,32> 383 us, <4,64> 221 us
+    if (tm == 8) detect_float_kernel<8, 32><<<grid, 128, 0, st>>>(Fm, LF, init_or_null, scores, R, T, D, M, L);
+    else if (D > 32 && rb * grid.y <= (long long)sm_count()) detect_float_kernel<4, 64><<<grid, 128, 0, st>>>(Fm, LF, init_or_null, scores, R, T, D, M, L);
+    else detect_float_kernel<4, 32><<<grid, 128, 0, st>>>(Fm, LF, init_or_null, scores, R, T, D, M, L);
     return check_launch("tsr_detect_float");
 }
 

@@ -73,7 +73,7 @@ static EmShape em_shape(long long N, int D, int K) {
     s.off_accM = s.off_accE + up((size_t)s.Mtiles * s.mrp * s.Npad * 4);
     s.off_ablob = s.off_accM + up((size_t)s.Mtiles * s.mrp * s.Dpad * 4);
     s.off_small = s.off_ablob + up((size_t)s.Mtiles * s.nchunkM * s.tile_bytes);
-    s.off_scratch = s.off_small + up(sizeof(long long) * (32 * (size_t)K + 32 + (size_t)K) + sizeof(uint32_t) * 32 * (size_t)K);
+    s.off_scratch = s.off_small + up(sizeof(long long) * (32 * (size_t)K + 32 + (size_t)K) + sizeof(uint32_t) * 32 * (size_t)K + 64);
     s.off_aff = s.off_scratch + up((size_t)K * s.Npad * 4);
     s.total = s.off_aff + up((size_t)K * (size_t)N * 4);
     return s;
@@ -693,6 +693,7 @@ struct EmSmall {
     long long* llQ;
     double* sk;                 // per-component posterior scale (power of two), published by the planes kernel
     uint32_t* colmax;
+    unsigned int* ticket;       // CTAs of em_aff_planes_kernel that have finished (the last one writes the statistics tail)
 };
 static EmSmall em_small(uint8_t* ws, const EmShape& s) {
     EmSmall m;
@@ -700,6 +701,7 @@ static EmSmall em_small(uint8_t* ws, const EmShape& s) {
     m.llQ = m.respQ + (size_t)EM_SLOTS * s.K;
     m.sk = reinterpret_cast<double*>(m.llQ + EM_SLOTS);
     m.colmax = reinterpret_cast<uint32_t*>(m.sk + s.K);
+    m.ticket = reinterpret_cast<unsigned int*>(m.colmax + (size_t)EM_SLOTS * s.K);
     return m;
 }
 // power-of-two scale of component k's posteriors: the smallest 2^e >= column max (0 for an empty column)
@@ -1188,9 +1190,11 @@ __device__ __forceinline__ int em_tile_pos(int t /* 0..127 */) {
 // q(n,k) = round(aff[n][k] / s_k * EM_QMAX), three balanced base-256 digits, one tile per M tile; respQ[slot][k] += sum_n q.
 // Every CTA reduces the column-maximum replicas to the scales s_k itself (EM_SLOTS * K loads); CTA 0 publishes them.
 __global__ void __launch_bounds__(128) em_aff_planes_kernel(const float* __restrict__ aff, long long N, long long Npad, int K, int KT,
-                                                            int Mtiles, int mrp, uint8_t* __restrict__ ablob, EmSmall S, const int* done) {
+                                                            int Mtiles, int mrp, uint8_t* __restrict__ ablob, EmSmall S,
+                                                            double* __restrict__ stats_tail, int write_ll, const int* done) {
     if (done && *done) return;
     extern __shared__ __align__(16) uint8_t psm[];
+    __shared__ int s_last;
     uint8_t* tile = psm;
     int* s_resp = reinterpret_cast<int*>(psm + (size_t)8 * mrp * 16);
     float* s_isk = reinterpret_cast<float*>(s_resp + K);                                  // 1 / s_k (0 for an empty column)
@@ -1204,7 +1208,7 @@ __global__ void __launch_bounds__(128) em_aff_planes_kernel(const float* __restr
         for (int sl = 0; sl < EM_SLOTS; ++sl) mx = max(mx, S.colmax[(size_t)sl * K + k]);
         const float sk = em_col_scale(mx);
         s_isk[k] = sk >= 1.17549435e-38f ? 1.f / sk : 0.f;                               // power-of-two s_k: aff / s_k is exact and <= 1
-        if (blockIdx.x == 0) S.sk[k] = (double)sk;                                       // for em_tail_kernel / em_pack_kernel
+        if (blockIdx.x == 0) S.sk[k] = (double)sk;                                       // for the statistics tail / em_pack_kernel
     }
     const bool staged = K <= 32;
     if (staged) {        // the block's 128 x K posteriors are contiguous in global memory: coalesced loads, pitch K + 1 in smem
@@ -1242,22 +1246,28 @@ __global__ void __launch_bounds__(128) em_aff_planes_kernel(const float* __restr
     const int slot = blockIdx.x % EM_SLOTS;
     for (int k = tid; k < K; k += 128)
         if (s_resp[k]) atomicAdd(reinterpret_cast<unsigned long long*>(S.respQ + (size_t)slot * K + k), (unsigned long long)(long long)s_resp[k]);
-}
-
-// integer sums -> the float64 tail of the statistics vector (one CTA; warp per component, lanes = the EM_SLOTS replicas)
-__global__ void em_tail_kernel(EmSmall S, int K, double* __restrict__ stats_tail, int write_ll, const int* done) {
-    if (done && *done) return;
-    const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    for (int k = wp; k < K; k += nw) {
-        long long rq = S.respQ[(size_t)lane * K + k];
+    // The last CTA to get here turns the integer sums into the float64 tail of the statistics vector (responsibility sums,
+    // log-likelihood): warp per component, lanes = the EM_SLOTS replicas.  (Was a launch of its own: ~5 us per iteration.)
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence();
+        s_last = atomicAdd(S.ticket, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    const int lane = tid & 31, wp = tid >> 5;
+    for (int k = wp; k < K; k += 4) {
+        long long rq = __ldcg(S.respQ + (size_t)lane * K + k);
         for (int off = 16; off > 0; off >>= 1) rq += __shfl_xor_sync(0xffffffffu, rq, off);
-        if (lane == 0) stats_tail[k] = (double)rq / (double)EM_QMAX * S.sk[k];
+        if (lane == 0) stats_tail[k] = (double)rq / (double)EM_QMAX * __ldcg(S.sk + k);
     }
     if (wp == 0 && write_ll) {
-        long long ll = S.llQ[lane];
+        long long ll = __ldcg(S.llQ + lane);
         for (int off = 16; off > 0; off >>= 1) ll += __shfl_xor_sync(0xffffffffu, ll, off);
         if (lane == 0) stats_tail[K] = (double)ll / EM_LL_SCALE;
     }
+    if (tid == 0) *S.ticket = 0u;
 }
 
 // int32 digit-plane accumulators of the M-step -> float64 numerators; clears the accumulators
@@ -1478,8 +1488,8 @@ static int em_planes(const EmShape& s, uint8_t* ws, const float* aff, double* st
         psm_set = psm;
     }
     const EmSmall sm = em_small(ws, s);
-    em_aff_planes_kernel<<<(unsigned)(s.Npad / 128), 128, psm, st>>>(aff, s.N, s.Npad, s.K, s.KT, s.Mtiles, s.mrp, ws + s.off_ablob, sm, done);
-    em_tail_kernel<<<1, 256, 0, st>>>(sm, s.K, stats + (size_t)s.K * s.D, write_ll, done);
+    em_aff_planes_kernel<<<(unsigned)(s.Npad / 128), 128, psm, st>>>(aff, s.N, s.Npad, s.K, s.KT, s.Mtiles, s.mrp, ws + s.off_ablob, sm,
+                                                                     stats + (size_t)s.K * s.D, write_ll, done);
     return check_launch("em_aff_planes_kernel");
 }
 

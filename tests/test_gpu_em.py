@@ -283,3 +283,34 @@ def test_preset_first_version_filters_reference_golden(cuda):
     np.testing.assert_array_equal(fs[1][0], g["lfs_W1"])
     s, C = tt.score_template_background_section(g["sc_template"], g["sc_bgd"], g["sc_E"])
     np.testing.assert_allclose([s, C], [g["sc_s"], g["sc_C"]], rtol=1e-5)
+
+
+def test_peer_memory_allreduce_single_rank_group(cuda, oracle):
+    """The library's own sum of the statistics over NVLink peer memory (tsr_em_allreduce_peer, ops.PeerStats) in a
+    one-rank NCCL group on one GPU: the flag handshake, the two alternating source slots and the two-iteration CUDA
+    graph all run (the only peer is the rank itself), and the result must equal the run without a group bit for bit.
+    (Two ranks: tools/em_dist_check.py under torchrun; host logic over gloo: tests/test_em_driver_gloo.py.)"""
+    import os
+    import torch.distributed as dist
+    from tsr_b200 import synth
+    from tsr_b200.bernoulli_mixture import BernoulliMixture
+    if dist.is_initialized():
+        pytest.skip("a process group is already initialised in this process")
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    os.environ.setdefault("MASTER_PORT", "29577")
+    dist.init_process_group("nccl", rank=0, world_size=1, device_id=torch.device("cuda", torch.cuda.current_device()))
+    try:
+        X, _, _, _ = synth.em_data(N=3000, D=640, K=8, seed=5)
+        a = BernoulliMixture(8, X)
+        a.run_EM(1e-6, min_probability=.01, max_iter=14)
+        b = BernoulliMixture(8, X, row_range=(0, 3000), group=dist.group.WORLD)
+        if b._drv.peer is None:
+            pytest.skip("symmetric memory unavailable here: %s" % b._drv.peer_error)
+        b.run_EM(1e-6, min_probability=.01, max_iter=14)
+        assert b._drv.peer.launches > 0
+        assert b.iterations == a.iterations
+        np.testing.assert_array_equal(np.array(b.loglikelihood_trace), np.array(a.loglikelihood_trace))
+        np.testing.assert_array_equal(b.templates, a.templates)
+        np.testing.assert_array_equal(b.affinities, a.affinities)
+    finally:
+        dist.destroy_process_group()

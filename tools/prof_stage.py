@@ -39,6 +39,12 @@ for it in range(a.iters):
         ops.spread_codes(codes, 100, 2, 2)
     if a.stage in ("detect", "all"):
         ops.detect(fb, bank, impl=impl)
+    if a.stage == "detect_float":              # A8 / A9: real-valued detectors (bit-exact sequential fp32, SIMT)
+        if it == 0:
+            g = torch.Generator(device="cuda").manual_seed(9)
+            Ff = torch.rand((64, 300, 320), device="cuda", generator=g)
+            LFf = torch.randn((8, 40, 320), device="cuda", generator=g)
+        ops.detect_float(Ff, LFf)
     if a.stage == "threshold_blocks":          # N4 + N3 front end: spectrogram -> packed edge bytes
         if it == 0:
             g = torch.Generator(device="cuda").manual_seed(1)

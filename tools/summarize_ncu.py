@@ -22,6 +22,7 @@ REPORTS = [
     ("spread_codes", "python tools/prof_stage.py spread_codes --iters 2"),
     ("spread_edges", "python tools/prof_stage.py spread_edges --iters 2"),
     ("threshold_blocks", "python tools/prof_stage.py threshold_blocks --iters 2"),
+    ("detect_float", "python tools/prof_stage.py detect_float --iters 2   (64 utterances x 300 frames x 320 real features, 8 x 40-frame templates)"),
     ("em", "python bench.py --workload em --steps 2 --warmup 3 --no-cpu   (config 4: N=100000, D=12800, K=16; one EM iteration's kernels)"),
 ]
 
