@@ -404,10 +404,12 @@ def run_native(args):
     e2e_packed_s = e2e_run(P_pinned)
     e2e_devpack_s = e2e_run(X_pinned, pack="device")
     e2e_hostpack_s = e2e_s
+    e2e_split_s = e2e_run(X_pinned, pack="split", pack_threads=threads)
+    split_rows = getattr(pipe, "stream_stats", {}).get("split_rows")
     # the headline e2e takes the reference-dtype input either way; which side packs is the caller's `pack=` argument, and the
-    # better choice depends on the box (host cores per GPU against the 8x larger PCIe copy): report the faster one, name it
-    pack_mode = "host" if e2e_hostpack_s <= e2e_devpack_s else "device"
-    e2e_s = min(e2e_hostpack_s, e2e_devpack_s)
+    # better choice depends on the box (host cores per GPU against the 8x larger PCIe copy; "split" uses both and adapts the
+    # split point to their measured rates): report the fastest one, name it
+    pack_mode, e2e_s = min((("host", e2e_hostpack_s), ("device", e2e_devpack_s), ("split", e2e_split_s)), key=lambda kv: kv[1])
     t0 = time.perf_counter()
     for _ in range(3):
         _lib.call("tsr_host_pack_edges", X_pinned.data_ptr(), P_pinned.data_ptr(), int(P_pinned.numel()), 8, threads)
@@ -460,15 +462,18 @@ def run_native(args):
                          "note": ROOF_NOTES[args.planes]},
             "stages": stages,
             "e2e": {"value": frames * e2e_steps / e2e_s, "unit": "frames/s", "pack": pack_mode,
-                    "h2d_bytes_per_step": int(P_pinned.numel()) if pack_mode == "host" else int(X_pinned.numel()),
-                    "e2e_host_pack": frames * e2e_steps / e2e_hostpack_s,
+                    "h2d_bytes_per_step": (int(P_pinned.numel()) if pack_mode == "host" else int(X_pinned.numel()) if pack_mode == "device"
+                                           else int((split_rows or 0) * (P_pinned.numel() // B) + (B - (split_rows or 0)) * (X_pinned.numel() // B))),
+                    "e2e_host_pack": frames * e2e_steps / e2e_hostpack_s, "e2e_split_pack": frames * e2e_steps / e2e_split_s,
+                    "split_host_rows": split_rows,
                     "d2h_bytes_per_step": int(B * TO * 4 + B * TO * 2), "host_input_bytes_per_step": int(X_pinned.numel()),
                     "host_pack_threads": threads, "host_pack_gbs": host_pack_gbs, "stream_stats": e2e_stats,
                     "pack_thread_sweep_frames_per_s": {str(k): frames * e2e_steps / v for k, v in sweep.items()},
                     "api": "pipeline.ScoringPipeline.stream(pack=...) over pinned uint8 (B,300,40,8) host batches (the reference's dtype); "
                            "pack='host': host threads pack to 1 byte per (t,f) (feeder thread, batch i+1 while batch i runs) and the packed bytes "
-                           "cross PCIe; pack='device': the unpacked tensor crosses PCIe and the GPU packs; the faster of the two on this box is "
-                           "the value (see `pack`), both are listed; double-buffered H2D, full pipeline, results D2H to pinned host; %d steps in "
+                           "cross PCIe; pack='device': the unpacked tensor crosses PCIe and the GPU packs; pack='split': the host packs the first "
+                           "rows of each batch, the GPU the rest, split point adapted to the measured rates; the fastest of the three on this box "
+                           "is the value (see `pack`), all are listed; double-buffered H2D, full pipeline, results D2H to pinned host; %d steps in "
                            "one call, fill and drain inside the clock" % e2e_steps},
             "e2e_packed": {"value": frames * e2e_steps / e2e_packed_s, "unit": "frames/s", "h2d_bytes_per_step": int(P_pinned.numel()),
                            "d2h_bytes_per_step": int(B * TO * 4 + B * TO * 2),

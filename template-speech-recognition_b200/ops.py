@@ -68,11 +68,13 @@ def rowwords(D):
 
 
 # ------------------------------------------------------------------------------- K0
-def pack_edges(X):
-    """X uint8 (B,T,F,E) -> bits uint8 (B,T,F); any nonzero counts as an edge."""
+def pack_edges(X, out=None):
+    """X uint8 (B,T,F,E) -> bits uint8 (B,T,F); any nonzero counts as an edge.  out: write into this contiguous (B,T,F) tensor."""
     X = _dev(X, torch.uint8, "X")
     B, T, F, E = X.shape
-    bits = torch.empty((B, T, F), dtype=torch.uint8, device=X.device)
+    bits = torch.empty((B, T, F), dtype=torch.uint8, device=X.device) if out is None else _dev(out, torch.uint8, "out")
+    if tuple(bits.shape) != (B, T, F):
+        raise ValueError("out must have shape (B,T,F)")
     _lib.call("tsr_pack_edges", _ptr(X), _ptr(bits), B, T, F, E, _stream())
     return bits
 

@@ -89,7 +89,10 @@ class ScoringPipeline:
         pack="host" (default): (B,T,F,E) batches are packed to one byte per (t,f) by a pool of host threads
         (``tsr_host_pack_edges``, pure data movement) BEFORE the copy, so 1/8 of the bytes cross PCIe; a feeder thread
         packs batch i+1 while batch i is copied and scored.  pack="device": the unpacked tensor is copied and packed
-        by the GPU (8x the H2D bytes; for hosts with few cores and a fast link).
+        by the GPU (8x the H2D bytes; for hosts with few cores and a fast link).  pack="split": both at once -- the first
+        rows of every batch are packed by the host threads, the rest cross PCIe unpacked and are packed by the GPU; the
+        split point follows the measured rates of the two paths from batch to batch (for boxes where neither the cores
+        per GPU nor the link alone keep up: 8 GPUs behind 32 cores).  Needs pinned (B,T,F,8) torch tensors.
 
         Streams: H2D of batch i+1 (into the other of two device buffers) and D2H of batch i-1's results run while
         batch i is coded and scored; every batch still moves its own inputs in and its own results out.
@@ -98,8 +101,8 @@ class ScoringPipeline:
         import queue
         import threading
         from . import _lib
-        if pack not in ("host", "device"):
-            raise ValueError("pack must be 'host' or 'device'")
+        if pack not in ("host", "device", "split"):
+            raise ValueError("pack must be 'host', 'device' or 'split'")
         dev = self.parts.blob.device
         nthreads = int(pack_threads) if pack_threads else max(1, min(32, (os.cpu_count() or 2) - 1))
         q = queue.Queue(maxsize=2)
@@ -115,6 +118,7 @@ class ScoringPipeline:
             cache = {"staging": [None] * NSTAGE, "outs": {}}     # a second stream() running concurrently gets its own
         cache["busy"] = True
         staging = cache["staging"]
+        split = cache.setdefault("split", {"rows": None})     # split mode: rows of a batch the host packs (adapted per batch, kept between calls)
         consumed = [None] * NSTAGE               # CUDA event: the H2D copy out of staging[j] has finished
 
         import time as _time
@@ -138,6 +142,24 @@ class ScoringPipeline:
                     direct = is_t and xb.is_pinned() and xb.is_contiguous() and (len(xb.shape) == 3 or pack == "device")
                     if direct:                   # already what the copy engine needs
                         q.put((xb, None))
+                        continue
+                    if pack == "split" and is_t and len(xb.shape) == 4 and xb.shape[3] == 8 and xb.shape[0] >= 16 and xb.is_pinned() \
+                            and xb.is_contiguous():
+                        Bn = xb.shape[0]
+                        nh = int(min(max(split["rows"] if split["rows"] is not None else Bn // 2, 1), Bn - 1)) if Bn > 1 else Bn
+                        shape = tuple(xb.shape[:3])
+                        if staging[j] is None or tuple(staging[j].shape) != shape:
+                            staging[j] = torch.empty(shape, dtype=torch.uint8).pin_memory()
+                        elif consumed[j] is not None:
+                            t0 = _time.perf_counter()
+                            consumed[j].synchronize()
+                            stats["feeder_wait_s"] += _time.perf_counter() - t0
+                        t0 = _time.perf_counter()
+                        _lib.call("tsr_host_pack_edges", xb.data_ptr(), staging[j].data_ptr(), nh * shape[1] * shape[2], 8, nthreads)
+                        dt = _time.perf_counter() - t0
+                        stats["pack_s"] += dt
+                        stats["pack_calls"] += 1
+                        q.put(((staging[j][:nh], xb[nh:], dt), j))
                         continue
                     shape = tuple(xb.shape[:3]) if (len(xb.shape) == 4 and pack == "host") else tuple(xb.shape)
                     if staging[j] is None or tuple(staging[j].shape) != shape:
@@ -167,6 +189,8 @@ class ScoringPipeline:
         main = torch.cuda.current_stream(dev)
         h2d, d2h = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
         xd, free_ev = [None, None], [None, None]
+        xu = [None, None]                        # split mode: the unpacked rows of a batch on the device
+        split_ev = [None, None]                  # split mode: (start, end) events around the unpacked copy, host pack seconds, rows
         outs, out_ev = cache["outs"].setdefault(ring, [None] * ring), [None] * ring
         pending = None
         i = 0
@@ -182,24 +206,53 @@ class ScoringPipeline:
                 xb, slot = item
                 k = i & 1
                 t1 = _time.perf_counter()
-                with torch.cuda.stream(h2d):
-                    if xd[k] is None or xd[k].shape != xb.shape:
-                        # A fresh block may be one that kernels still in flight on `main` were using (the caching
-                        # allocator reuses blocks per stream): order the first copy after everything queued there.
-                        h2d.wait_stream(main)
-                        xd[k] = torch.empty(xb.shape, dtype=torch.uint8, device=dev)
-                        xd[k].record_stream(main)
-                    elif free_ev[k] is not None:
-                        h2d.wait_event(free_ev[k])        # batch i-2 has finished reading this buffer
-                    xd[k].copy_(xb, non_blocking=True)
-                    arrived = torch.cuda.Event()
-                    arrived.record(h2d)
-                    if slot is not None:
+                if isinstance(xb, tuple):        # split mode: (host-packed head, unpacked tail, host pack seconds)
+                    hp, tail, pack_dt = xb
+                    nh, nt_rows = hp.shape[0], tail.shape[0]
+                    full = (nh + nt_rows,) + tuple(hp.shape[1:])
+                    with torch.cuda.stream(h2d):
+                        if xd[k] is None or tuple(xd[k].shape) != full or xu[k] is None or tuple(xu[k].shape[1:]) != tuple(tail.shape[1:]) \
+                                or xu[k].shape[0] < full[0]:
+                            h2d.wait_stream(main)
+                            xd[k] = torch.empty(full, dtype=torch.uint8, device=dev)
+                            xu[k] = torch.empty((full[0],) + tuple(tail.shape[1:]), dtype=torch.uint8, device=dev)
+                            xd[k].record_stream(main)
+                            xu[k].record_stream(main)
+                        elif free_ev[k] is not None:
+                            h2d.wait_event(free_ev[k])
+                        xd[k][:nh].copy_(hp, non_blocking=True)
+                        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                        e0.record(h2d)
+                        xu[k][:nt_rows].copy_(tail, non_blocking=True)
+                        e1.record(h2d)
+                        arrived = torch.cuda.Event()
+                        arrived.record(h2d)
                         consumed[slot] = arrived
-                main.wait_event(arrived)
-                t2 = _time.perf_counter()
-                stats["h2d_issue_s"] += t2 - t1
-                bits = ops.pack_edges(xd[k]) if xd[k].dim() == 4 else xd[k]
+                    main.wait_event(arrived)
+                    split_ev[k] = (e0, e1, pack_dt, nh, nt_rows)
+                    t2 = _time.perf_counter()
+                    stats["h2d_issue_s"] += t2 - t1
+                    ops.pack_edges(xu[k][:nt_rows], out=xd[k][nh:])          # the GPU packs its share into place
+                    bits = xd[k]
+                else:
+                    with torch.cuda.stream(h2d):
+                        if xd[k] is None or xd[k].shape != xb.shape:
+                            # A fresh block may be one that kernels still in flight on `main` were using (the caching
+                            # allocator reuses blocks per stream): order the first copy after everything queued there.
+                            h2d.wait_stream(main)
+                            xd[k] = torch.empty(xb.shape, dtype=torch.uint8, device=dev)
+                            xd[k].record_stream(main)
+                        elif free_ev[k] is not None:
+                            h2d.wait_event(free_ev[k])        # batch i-2 has finished reading this buffer
+                        xd[k].copy_(xb, non_blocking=True)
+                        arrived = torch.cuda.Event()
+                        arrived.record(h2d)
+                        if slot is not None:
+                            consumed[slot] = arrived
+                    main.wait_event(arrived)
+                    t2 = _time.perf_counter()
+                    stats["h2d_issue_s"] += t2 - t1
+                    bits = ops.pack_edges(xd[k]) if xd[k].dim() == 4 else xd[k]
                 best, arg, _ = self(bits)
                 free_ev[k] = torch.cuda.Event()
                 free_ev[k].record(main)                   # the whole step is queued: xd[k] (== bits when packed) is free after it
@@ -222,6 +275,18 @@ class ScoringPipeline:
                 if pending is not None:
                     out_ev[pending].synchronize()
                     stats["result_wait_s"] += _time.perf_counter() - t4
+                    pk = (i - 1) & 1
+                    if split_ev[pk] is not None:              # batch i-1 is complete: its copy time and pack time set the next split
+                        e0, e1, pack_dt, nh, nt_rows = split_ev[pk]
+                        split_ev[pk] = None
+                        c_h = pack_dt / max(nh, 1)                        # host seconds per packed row
+                        c_d = e0.elapsed_time(e1) * 1e-3 / max(nt_rows, 1)   # link seconds per unpacked row
+                        tot = nh + nt_rows
+                        want = tot * c_d / max(c_h + c_d, 1e-12)
+                        cur = split["rows"] if split["rows"] is not None else nh
+                        new_rows = int(round((0.5 * cur + 0.5 * want) / 8.0)) * 8
+                        split["rows"] = min(max(new_rows, 8), max(tot - 8, 8))
+                        stats["split_rows"] = split["rows"]
                     yield outs[pending]
                 pending = r
                 i += 1

@@ -87,7 +87,8 @@ T, bgd = synth.templates(M=8, L=40, Fd=36, Kd=100)
 W, c = synth.linear_filters(T, bgd)
 pipe = ScoringPipeline(lp, lip, W, c)
 batches = [synth.fast_edge_batch(b, seed=s) for s, b in enumerate([640, 640, 512, 640])]
-got = [(b.numpy().copy(), a.numpy().copy()) for b, a in pipe.stream(iter(batches), pack=sys.argv[1])]   # FIRST work of the process
+feed = [torch.from_numpy(b).pin_memory() for b in batches] if sys.argv[1] == "split" else batches     # split needs pinned tensors
+got = [(b.numpy().copy(), a.numpy().copy()) for b, a in pipe.stream(iter(feed), pack=sys.argv[1])]   # FIRST work of the process
 torch.cuda.synchronize()
 for X, (gb, ga) in zip(batches, got):
     best, arg, _ = pipe(pipe.from_numpy(X))
@@ -96,7 +97,7 @@ print("fresh-process stream ok")
 """
 
 
-@pytest.mark.parametrize("pack", ["host", "device"])
+@pytest.mark.parametrize("pack", ["host", "device", "split"])
 def test_stream_large_batches_in_a_fresh_process(cuda, pack):
     """Cross-stream hazard check (device input buffers are handed out by the caching allocator while kernels of the
     previous batch may still be running on the main stream): bench-sized batches, allocator cache cold, stream() is
@@ -107,3 +108,27 @@ def test_stream_large_batches_in_a_fresh_process(cuda, pack):
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, "-c", _FRESH % root, pack], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "fresh-process stream ok" in r.stdout, r.stdout + r.stderr
+
+
+def test_stream_split_packing_equals_direct_calls(cuda):
+    """pack="split": the host packs the first rows of every batch, the GPU the rest, and the split point moves from batch
+    to batch with the measured rates -- whatever it is, every batch must score exactly like a direct call."""
+    from tsr_b200 import synth
+    from tsr_b200.pipeline import ScoringPipeline
+    lp, lip = synth.parts(30)
+    T, bgd = synth.templates(M=3, L=10, Fd=36, Kd=30)
+    W, c = synth.linear_filters(T, bgd)
+    pipe = ScoringPipeline(lp, lip, W, c)
+    batches = [synth.fast_edge_batch(b, T=120, seed=s) for s, b in enumerate([64, 64, 64, 40, 40, 64, 64, 8])]
+    want = []
+    for X in batches:
+        best, arg, _ = pipe(pipe.from_numpy(X))
+        want.append((best.cpu().numpy().copy(), arg.cpu().numpy().copy()))
+    pinned = [torch.from_numpy(X).pin_memory() for X in batches]
+    n = 0
+    for (best, arg), (wb, wa) in zip(pipe.stream(iter(pinned), pack="split", pack_threads=2), want):
+        np.testing.assert_array_equal(best.numpy(), wb)
+        np.testing.assert_array_equal(arg.numpy(), wa)
+        n += 1
+    assert n == len(batches)
+    assert pipe.stream_stats.get("split_rows") is not None
