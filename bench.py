@@ -591,7 +591,7 @@ def em_bench(ctx, args, steps, warmup):
         slot = [0]
 
         def peer_sum():
-            drv.peer.allreduce(slot[0] & 1, scratch); slot[0] += 1
+            drv.peer.allreduce(slot[0] & 1, drv.peer.out if drv.peer.two_phase else scratch); slot[0] += 1
         parts["allreduce_ms"] = _timed(torch, dist, world, dev, peer_sum, max(steps, 20), 4)
         parts["nccl_allreduce_ms"] = _timed(torch, dist, world, dev, lambda: dist.all_reduce(scratch), max(steps, 20), 3)
     else:

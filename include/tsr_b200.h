@@ -283,16 +283,19 @@ int tsr_em_finalize(const double* stats, long long N_total, int D, int K, float 
  * em_driver.py, i.e. the sum the reference would form over all rows in bernoulli_mixture.py:177-181 when rows are sharded).
  * Every rank owns one symmetric allocation mapped by all peers (torch.distributed._symmetric_memory); peer_bufs_dev is a
  * DEVICE array of the world base pointers in rank order.  Inside each allocation: the source vector (n_doubles float64) at
- * src_offset_bytes and world x 64 uint32 flags (tsr_em_peer_flag_bytes, zeroed once) at flag_offset_bytes.  out (local,
+ * src_offset_bytes and 2 x world x 64 uint32 flags (tsr_em_peer_flag_bytes, zeroed once) at flag_offset_bytes.  out (local,
  * 16-byte aligned) receives sum_r src_r, added in rank order on every rank (bit-identical everywhere).  epoch_counters:
  * tsr_em_peer_epoch_bytes() bytes of local device memory, zeroed once.  The caller must alternate between TWO source
  * offsets from launch to launch (that is what makes the kernel safe without a closing barrier) and every rank must issue
- * the same sequence of launches.  Honours ctl_or_null like the other EM entries. */
+ * the same sequence of launches.  Honours ctl_or_null like the other EM entries.
+ * out_offset_bytes >= 0 selects the two-phase form (for more than two ranks): rank r sums only its 1/world share and
+ * stores it into the result slot at out_offset_bytes of EVERY rank's allocation, a second flag round closes the launch;
+ * `out` is then ignored and the result is read from the caller's own allocation. */
 size_t tsr_em_peer_flag_bytes(int world);
 size_t tsr_em_peer_epoch_bytes(void);
 int    tsr_em_allreduce_peer(const void* const* peer_bufs_dev, int rank, int world, long long src_offset_bytes,
-                             long long flag_offset_bytes, long long n_doubles, double* out, void* epoch_counters,
-                             const void* ctl_or_null, void* stream);
+                             long long flag_offset_bytes, long long n_doubles, double* out, long long out_offset_bytes,
+                             void* epoch_counters, const void* ctl_or_null, void* stream);
 /* Device-side stopping rule.  ctl = tsr_em_control_bytes(max_trace) bytes of device memory:
  *   int32 done, iterations, ntrace, mode, min_iter, max_iter, cap, pad; double tol, ll_old; double trace[max_trace].
  * tsr_em_control_step (after the allreduce of stats) appends the log-likelihood to trace and applies

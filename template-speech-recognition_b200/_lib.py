@@ -60,7 +60,7 @@ SIGNATURES = {
     "tsr_em_control_step": (_i, [_vp, _vp, _i, _i, _vp]),
     "tsr_em_peer_flag_bytes": (_sz, [_i]),
     "tsr_em_peer_epoch_bytes": (_sz, []),
-    "tsr_em_allreduce_peer": (_i, [_vp, _i, _i, _ll, _ll, _ll, _vp, _vp, _vp, _vp]),
+    "tsr_em_allreduce_peer": (_i, [_vp, _i, _i, _ll, _ll, _ll, _vp, _ll, _vp, _vp, _vp]),
 }
 
 ABI_VERSION = 2

@@ -1327,7 +1327,8 @@ struct PeerArgs {
     const uint8_t* const* bufs;     // device array [world]: base of every rank's symmetric allocation
     long long src_off, flag_off;    // byte offsets of the source vector and of the flag array [world][EM_AR_CTAS] uint32
     long long n;                    // doubles
-    double* out;
+    double* out;                    // one-phase form: local result vector
+    long long out_off;              // two-phase form (>= 0): byte offset of the result vector inside every rank's allocation
     unsigned int* epoch;            // [EM_AR_CTAS] launch counters of this rank (zero-initialised once)
     int rank, world;
     const int* done;
@@ -1396,6 +1397,76 @@ __global__ void __launch_bounds__(1024) em_allreduce_peer_kernel(PeerArgs P) {
         }
         P.out[P.n - 1] = acc;
     }
+}
+
+// Two-phase form for more than two ranks (reduce-scatter + all-gather by remote stores): rank r sums only ITS 1/W share
+// of the vector (reads (W-1)/W of a vector over NVLink instead of W-1 vectors) and stores the result into the result
+// slot of every rank's allocation; a second per-CTA flag round ("my share has landed everywhere") closes the launch.
+// The sums are still formed in rank order by exactly one rank each, so every rank ends with the same bits.
+// Flags: [2][world][EM_AR_CTAS] (start, landed).  A peer's stores into this rank's result slot of launch i+1 happen
+// after that peer passed the start flags of launch i+1, i.e. after this rank's own launch i+1 began: the kernels that
+// read the result of launch i (stopping rule, finalize) are earlier in this rank's stream.
+__global__ void __launch_bounds__(1024) em_allreduce_peer2_kernel(PeerArgs P) {
+    if (P.done && *P.done) return;
+    __shared__ unsigned int s_epoch;
+    const int b = blockIdx.x, W = P.world, r = P.rank;
+    if (threadIdx.x == 0) s_epoch = ++P.epoch[b];
+    __syncthreads();
+    const unsigned int e = s_epoch;
+    const unsigned int* mine = reinterpret_cast<const unsigned int*>(P.bufs[r] + P.flag_off);
+    auto flag_round = [&](int which) {
+        if ((int)threadIdx.x < W) {
+            const int t = threadIdx.x;
+            unsigned int* theirs = reinterpret_cast<unsigned int*>(const_cast<uint8_t*>(P.bufs[t]) + P.flag_off) + (size_t)which * W * EM_AR_CTAS;
+            st_release_sys(theirs + (size_t)r * EM_AR_CTAS + b, e);
+            const unsigned int* m = mine + (size_t)which * W * EM_AR_CTAS + (size_t)t * EM_AR_CTAS + b;
+            unsigned int spins = 0;
+            while (ld_acquire_sys(m) < e) {
+                __nanosleep(20);
+                if (++spins > (1u << 26)) {
+                    printf("tsr_b200: peer allreduce (phase %d) timed out waiting for rank %d (rank %d block %d epoch %u)\n", which, t, r, b, e);
+                    __trap();
+                }
+            }
+        }
+        __syncthreads();
+    };
+    flag_round(0);
+    const long long npair = P.n >> 1;
+    const long long cp = (npair + W - 1) / W;
+    const long long lo = (long long)r * cp, hi = lo + cp < npair ? lo + cp : npair;
+    for (long long i = lo + (long long)b * blockDim.x + threadIdx.x; i < hi; i += (long long)gridDim.x * blockDim.x) {
+        double2 acc = make_double2(0.0, 0.0);
+        for (int t0 = 0; t0 < W; t0 += 8) {
+            double2 v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                if (t0 + u < W) {
+                    const double* q = reinterpret_cast<const double*>(P.bufs[t0 + u] + P.src_off) + 2 * i;
+                    v[u] = (t0 + u == r) ? *reinterpret_cast<const double2*>(q) : ld_relaxed_sys_f64x2(q);
+                }
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                if (t0 + u < W) { acc.x += v[u].x; acc.y += v[u].y; }
+        }
+        for (int t = 0; t < W; ++t) {
+            double* q = reinterpret_cast<double*>(const_cast<uint8_t*>(P.bufs[t]) + P.out_off) + 2 * i;
+            asm volatile("st.relaxed.sys.global.v2.f64 [%0], {%1,%2};" ::"l"(q), "d"(acc.x), "d"(acc.y) : "memory");
+        }
+    }
+    if ((P.n & 1) && r == 0 && b == 0 && threadIdx.x == 0) {
+        double acc = 0.0;
+        for (int t = 0; t < W; ++t) {
+            double v;
+            asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(reinterpret_cast<const double*>(P.bufs[t] + P.src_off) + P.n - 1) : "memory");
+            acc += v;
+        }
+        for (int t = 0; t < W; ++t)
+            asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(reinterpret_cast<double*>(const_cast<uint8_t*>(P.bufs[t]) + P.out_off) + P.n - 1), "d"(acc) : "memory");
+    }
+    __threadfence_system();          // this thread's remote stores are visible system-wide before the CTA's "landed" flags go out
+    __syncthreads();
+    flag_round(1);
 }
 
 // XT[d][n] = X[n][d]: each warp transposes a 32x32 bit block with 32 ballots.
@@ -1619,23 +1690,26 @@ int tsr_em_mstep(const uint32_t* Xbits, const uint32_t* XTbits_or_null, const ui
     return check_launch("tsr_em_mstep(pack)");
 }
 
-size_t tsr_em_peer_flag_bytes(int world) { return world < 1 ? 0 : (size_t)world * EM_AR_CTAS * sizeof(unsigned int); }
+size_t tsr_em_peer_flag_bytes(int world) { return world < 1 ? 0 : 2 * (size_t)world * EM_AR_CTAS * sizeof(unsigned int); }
 size_t tsr_em_peer_epoch_bytes(void) { return EM_AR_CTAS * sizeof(unsigned int); }
 
 int tsr_em_allreduce_peer(const void* const* peer_bufs_dev, int rank, int world, long long src_offset_bytes, long long flag_offset_bytes,
-                          long long n_doubles, double* out, void* epoch_counters, const void* ctl_or_null, void* stream) {
-    TSR_REQUIRE(peer_bufs_dev && out && epoch_counters, "tsr_em_allreduce_peer: null pointer");
+                          long long n_doubles, double* out, long long out_offset_bytes, void* epoch_counters, const void* ctl_or_null,
+                          void* stream) {
+    TSR_REQUIRE(peer_bufs_dev && epoch_counters && (out || out_offset_bytes >= 0), "tsr_em_allreduce_peer: null pointer");
+    TSR_REQUIRE(out_offset_bytes < 0 || (out_offset_bytes & 15) == 0, "tsr_em_allreduce_peer: result offset must be 16-byte aligned");
     TSR_REQUIRE(world >= 1 && world <= 64 && rank >= 0 && rank < world, "tsr_em_allreduce_peer: bad rank %d / world %d", rank, world);
-    TSR_REQUIRE(n_doubles >= 0 && (src_offset_bytes & 15) == 0 && (flag_offset_bytes & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
+    TSR_REQUIRE(n_doubles >= 0 && (src_offset_bytes & 15) == 0 && (flag_offset_bytes & 3) == 0 && (out_offset_bytes >= 0 || (reinterpret_cast<uintptr_t>(out) & 15) == 0),
                 "tsr_em_allreduce_peer: offsets / output must be 16-byte aligned");
     int rc = require_sm100("tsr_em_allreduce_peer");
     if (rc) return rc;
     PeerArgs P;
     P.bufs = reinterpret_cast<const uint8_t* const*>(peer_bufs_dev);
-    P.src_off = src_offset_bytes; P.flag_off = flag_offset_bytes; P.n = n_doubles; P.out = out;
+    P.src_off = src_offset_bytes; P.flag_off = flag_offset_bytes; P.n = n_doubles; P.out = out; P.out_off = out_offset_bytes;
     P.epoch = (unsigned int*)epoch_counters; P.rank = rank; P.world = world;
     P.done = ctl_or_null ? &((const EmCtl*)ctl_or_null)->done : nullptr;
-    em_allreduce_peer_kernel<<<EM_AR_CTAS, 1024, 0, (cudaStream_t)stream>>>(P);
+    if (out_offset_bytes >= 0) em_allreduce_peer2_kernel<<<EM_AR_CTAS, 1024, 0, (cudaStream_t)stream>>>(P);
+    else em_allreduce_peer_kernel<<<EM_AR_CTAS, 1024, 0, (cudaStream_t)stream>>>(P);
     return check_launch("tsr_em_allreduce_peer");
 }
 

@@ -128,6 +128,9 @@ class EmDriver:
                                          group=self.group if self.group not in (None, False) else None)
             if int(flag.item()) == 0:          # all ranks or none
                 self.peer = None
+            elif self.peer.two_phase:          # peers store the sums straight into this rank's statistics vector
+                self.peer.out.copy_(engine.state.stats)
+                engine.state.stats = self.peer.out
 
     def _src(self):
         """Where this iteration's local statistics go: the engine's vector, or the peer-mapped slot of this parity."""

@@ -5,6 +5,8 @@ spread_waliji_patches.py, compute_likelihood_linear_filter.py, bernoulli_mixture
 sit on.  torch is used for device memory and streams only; every computation is a call
 into libtsr_b200.so on the current CUDA stream.  Nothing here touches the CPU oracle.
 """
+import os
+
 import numpy as np
 import torch
 
@@ -565,7 +567,9 @@ class PeerStats:
         group = dist.group.WORLD if group is None else group
         self.world, self.rank, self.n = dist.get_world_size(group), dist.get_rank(group), int(n)
         self.slot_bytes = (self.n * 8 + 255) // 256 * 256
-        self.flag_off = 2 * self.slot_bytes
+        self.flag_off = 3 * self.slot_bytes                       # [source slot 0 | source slot 1 | result slot | flags]
+        tp = os.environ.get("TSR_EM_PEER_TWO_PHASE")            # testing: "1" / "0" force the form
+        self.two_phase = (self.world > 2) if tp is None else tp == "1"   # reduce-scatter + all-gather by remote stores
         total = self.flag_off + int(_lib.lib().tsr_em_peer_flag_bytes(self.world))
         with torch.cuda.device(device):
             self.buf = symm.empty(total, dtype=torch.uint8, device=device)
@@ -577,15 +581,22 @@ class PeerStats:
             self.ptrs = torch.tensor(ptrs, dtype=torch.int64, device=device)
             self.epoch = torch.zeros(int(_lib.lib().tsr_em_peer_epoch_bytes()) // 4, dtype=torch.int32, device=device)
             self.src = [self.buf[i * self.slot_bytes:i * self.slot_bytes + self.n * 8].view(torch.float64) for i in (0, 1)]
+            self.out = self.buf[2 * self.slot_bytes:2 * self.slot_bytes + self.n * 8].view(torch.float64)   # result slot (peers store into it)
             torch.cuda.synchronize(device)
         dist.barrier(group)                     # every rank's flags are zero before anybody signals
         self.launches = 0
 
     def allreduce(self, slot, out, ctl=None):
-        """out (local float64 [n]) = sum over ranks of their source slot `slot`; one kernel launch on the current stream."""
-        with torch.cuda.device(out.device):
+        """out (float64 [n]) = sum over ranks of their source slot `slot`; one kernel launch on the current stream.
+        With more than two ranks the two-phase kernel leaves the result in self.out (the symmetric result slot): pass
+        out=self.out (the driver makes the engine's statistics vector that view)."""
+        two = self.two_phase
+        if two and out.data_ptr() != self.out.data_ptr():
+            raise ValueError("the two-phase peer allreduce writes the symmetric result slot: pass out=PeerStats.out")
+        with torch.cuda.device(self.buf.device):
             _lib.call("tsr_em_allreduce_peer", _ptr(self.ptrs), self.rank, self.world, int(slot) * self.slot_bytes, self.flag_off, self.n,
-                      _ptr(out), _ptr(self.epoch), _ptr(ctl.buf) if ctl is not None else 0, _stream())
+                      0 if two else _ptr(out), 2 * self.slot_bytes if two else -1, _ptr(self.epoch),
+                      _ptr(ctl.buf) if ctl is not None else 0, _stream())
         self.launches += 1
 
 
