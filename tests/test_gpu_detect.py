@@ -171,7 +171,8 @@ def test_detect_reduce_and_mixture_semantics(cuda):
 
 @pytest.mark.parametrize("planes", [0, 3, 4], ids=["fp16", "int8x2", "int8x3"])
 @pytest.mark.parametrize("B,T,D,M,L,with_cs", [(2, 296, 3600, 32, 40, True), (3, 50, 63, 5, 1, True), (5, 77, 1, 33, 13, False),
-                                               (1, 700, 64, 100, 200, True), (4, 130, 320, 7, 40, True), (2, 300, 3600, 45, 40, True)])
+                                               (1, 700, 64, 100, 200, True), (4, 130, 320, 7, 40, True), (2, 300, 3600, 45, 40, True),
+                                               (2, 150, 200, 15, 40, True), (3, 1000, 96, 16, 37, False), (1, 5000, 64, 3, 40, True)])
 def test_fused_mixture_max_equals_detect_then_reduce(cuda, B, T, D, M, L, with_cs, planes):
     """tsr_detect_best (max / arg-max over templates fused into the detection epilogue, combined across the CTAs
     that hold different template tiles) returns exactly the bits of detect() followed by detect_reduce(tail_mode=1):
