@@ -625,9 +625,15 @@ static int launch_bitgemm(const uint32_t* bits, const uint32_t* tiled, long long
     memset(&A, 0, sizeof(A));
     A.bits = bits; A.tiled = tiled; A.wblob = wblob; A.acc = acc; A.R = R; A.Rpad = Rpad; A.rw = rw; A.nchunk = nchunk;
     A.Mtiles = s.Mtiles; A.mrp = s.mrp; A.mrows = s.mrows; A.Rtiles = (int)(Rpad / 256); A.done = done;
+#ifdef TSR_DEBUG_TRACE      // experiments only: force the per-thread LDG fetch / the SS-form kernel
     const bool raw_tma = tiled != nullptr && getenv("TSR_DEBUG_BITGEMM_LDG") == nullptr;
+    const bool allow_ts = getenv("TSR_DEBUG_BITGEMM_SS") == nullptr;
+#else
+    const bool raw_tma = tiled != nullptr;
+    const bool allow_ts = true;
+#endif
     const int nsm = sm_count();
-    if (raw_tma && s.Mtiles == 1 && getenv("TSR_DEBUG_BITGEMM_SS") == nullptr) {
+    if (raw_tma && s.Mtiles == 1 && allow_ts) {
         // all components in one M tile: bit rows as the A operand in tensor memory (bitgemm_ts_kernel)
         size_t nw = (size_t)(144 * 1024) / s.tile_bytes;
         if (nw > TS_NW_MAX) nw = TS_NW_MAX;
