@@ -45,6 +45,12 @@ extern "C" {
 /* detection kernels selectable through `impl` arguments (per-stage choice) */
 #define TSR_IMPL_TENSOR 0   /* tcgen05 / TMEM path (default) */
 #define TSR_IMPL_SIMT   1   /* CUDA-core cross-check path, fp32 sequential accumulation */
+/* tsr_code_parts only: tcgen05 kind::i8 path.  All parts share one 16-bit fixed-point scale (two balanced base-255
+ * int8 digits that accumulate into the same int32 column, half the MMAs of the 16-bit hi+lo form), integer arg-max
+ * with the runner-up tracked; every location whose runner-up lies within the rounding bound (set bits + 2 units) is
+ * re-evaluated by a second kernel with the reference's own float64 sum (code_parts.pyx:123-131).  Codes are therefore
+ * the reference's codes with no near-tie exception; scores_or_null, if requested, carry the 16-bit fixed point. */
+#define TSR_IMPL_TENSOR_INT8 2
 
 /* 16-bit float format of the hi+lo weight planes (and of the expanded {0,1} bits) on the tensor
  * path; both run at the same tcgen05 kind::f16 rate.  AUTO picks FP16 (22 mantissa bits over the

@@ -4,10 +4,10 @@ import ctypes
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libtsr_b200.so")
+LIB_PATH = os.environ.get("TSR_B200_LIB") or os.path.join(HERE, "libtsr_b200.so")   # override: debug builds (tools/trace_*.py)
 
 TSR_OK, TSR_ERR_INVALID, TSR_ERR_CUDA, TSR_ERR_UNSUPPORTED = 0, -1, -2, -3
-IMPL_TENSOR, IMPL_SIMT = 0, 1
+IMPL_TENSOR, IMPL_SIMT, IMPL_TENSOR_INT8 = 0, 1, 2
 PLANES_AUTO, PLANES_BF16, PLANES_FP16, PLANES_INT8X2, PLANES_INT8X3 = 0, 1, 2, 3, 4
 
 _vp, _i, _ll, _sz, _f = ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_size_t, ctypes.c_float

@@ -242,6 +242,17 @@ __device__ __forceinline__ void umma_f16_elect(uint32_t d_tmem, uint64_t a_desc,
         "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// kind::i8: int32 accumulators, K = 32 per instruction, twice the kind::f16 MAC rate
+__device__ __forceinline__ void umma_i8_elect(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                              uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 __device__ __forceinline__ void umma_commit_elect(uint64_t* bar) {
     asm volatile(
         "{\n\t.reg .pred q;\n\t"
@@ -349,6 +360,14 @@ __device__ __forceinline__ uint4 expand_byte(uint32_t b, uint32_t one) {
     b >>= 2;
     r.w = (((b) | (b << 15)) & 0x00010001u) * one;
     return r;
+}
+
+// 8 bits -> 16 bytes: bytes 0-7 = the bits as uint8 {0,1}, bytes 8-15 = 255 x the same (the A operand row of
+// code_parts' int8 form: both base-255 weight digits meet their factor inside one K = 16 group)
+__device__ __forceinline__ uint4 expand_byte_u8x2(uint32_t b) {
+    const uint32_t lo = ((b & 0xFu) * 0x00204081u) & 0x01010101u;
+    const uint32_t hi = (((b >> 4) & 0xFu) * 0x00204081u) & 0x01010101u;
+    return make_uint4(lo, hi, lo * 255u, hi * 255u);
 }
 
 // hi + lo split of a weight into two 16-bit floats of format `fmt` (returned as raw bits)

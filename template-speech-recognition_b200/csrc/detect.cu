@@ -370,16 +370,6 @@ __device__ __forceinline__ uint4 expand16_u8(uint32_t b) {
     r.w = (((b >> 12) & 0xFu) * 0x00204081u) & 0x01010101u;
     return r;
 }
-__device__ __forceinline__ void umma_i8_elect(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
-                                              uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p, q;\n\t"
-        "elect.sync _|q, 0xffffffff;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "@q tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
 
 // Unit u -> (N tile, row unit).  Units are ordered (tile group, row unit, tile within group) so that the CTAs
 // running at any one time share the filter tiles of a few N tiles (they stay L2 resident: with many

@@ -11,7 +11,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import (IMPL_SIMT, IMPL_TENSOR, PLANES_AUTO, PLANES_BF16, PLANES_FP16,  # noqa: F401
+from ._lib import (IMPL_SIMT, IMPL_TENSOR, IMPL_TENSOR_INT8, PLANES_AUTO, PLANES_BF16, PLANES_FP16,  # noqa: F401
                    PLANES_INT8X2, PLANES_INT8X3)
 
 # Orientation table produced by the reference edge extractor (edge_signal_proc.py:1751-1821,

@@ -26,7 +26,11 @@ class ScoringPipeline:
         self.edge_spread_radius = int(edge_spread_radius)
         self.edge_block_len = int(edge_block_len)
         self.edge_orientations = edge_orientations
-        self.impl_code = ops.IMPL_TENSOR
+        # K2: the 16-bit hi+lo planes up to 126 parts (one 128-column accumulator per tile: 0.63 ms at config 3 against
+        # 0.75 ms), the int8 form above (200 parts: 1.48 against 1.91 ms).  The int8 form's codes equal the reference's
+        # float64 arg-max everywhere (set impl_code = ops.IMPL_TENSOR_INT8 to have that at any size); the hi+lo form
+        # may differ at near-ties below 1e-5 relative.
+        self.impl_code = ops.IMPL_TENSOR_INT8 if self.parts.K > 126 else ops.IMPL_TENSOR
         self.impl_detect = ops.IMPL_TENSOR
         self.fused_max = True
         # K1a inside K2's producers (tsr_code_parts edge_spread_radius = 1) is bit-identical but measured SLOWER than the
@@ -47,7 +51,7 @@ class ScoringPipeline:
         """K1a + K2 + K1b: packed edges -> (codes, part feature bits).  With fuse_edge_spread set (and the reference's
         direction table, radius 1, main_multiprocessing.py:50-52) the edge spreading runs inside K2's producers."""
         fused = (self.fuse_edge_spread and self.edge_spread_radius == 1 and self.edge_orientations is None
-                 and self.impl_code == ops.IMPL_TENSOR)
+                 and self.impl_code in (ops.IMPL_TENSOR, ops.IMPL_TENSOR_INT8))
         if not fused:
             bits = self.spread(bits)
         codes, _, _ = ops.code_parts(bits, self.parts, self.edge_threshold, impl=self.impl_code,

@@ -87,6 +87,130 @@ def test_code_parts_edge_cases(cuda, oracle, impl, T, F, E, K, ph, pw, thr):
         np.testing.assert_allclose(scores[b], oracle.code_parts(X[b], lp, lip, 0)[..., 1:], rtol=RTOL, atol=1e-6)
 
 
+# ---------------------------------------------------------------------------- int8 form (impl 2)
+def _check_int8(X, lp, lip, thr, oracle, mask=None, mask_thr=-1, spread=None):
+    """TSR_IMPL_TENSOR_INT8: codes EQUAL the float64 reference arg-max (no near-tie exception: everything inside the
+    rounding bound is re-evaluated with the reference's own float64 sum); edge counts exact; the optional scores
+    carry the 16-bit fixed point: |err| <= (set bits + 1) / 2 units of max|w| / 32512."""
+    codes, scores, counts = _gpu_code(X, lp, lip, thr, 2, mask=mask, mask_thr=mask_thr)
+    W = lp - lip
+    unit = np.abs(W).max() / 32512.0
+    for b in range(X.shape[0]):
+        ref = oracle.code_parts(X[b], lp, lip, thr)
+        np.testing.assert_array_equal(codes[b], np.argmax(ref, -1))
+        full = oracle.code_parts(X[b], lp, lip, 0)[..., 1:]
+        cnt = counts[b].astype(np.float64)[..., None]
+        assert np.all(np.abs(scores[b] - full) <= 0.5 * (cnt + 1) * unit * 1.001 + 1e-6 * np.abs(full))
+    return codes
+
+
+def test_code_parts_int8_golden(cuda, golden, oracle):
+    g = golden
+    codes = _check_int8(g["cp_X"][None], g["cp_lp"], g["cp_lip"], 12, oracle)
+    np.testing.assert_array_equal(codes[0], np.argmax(g["cp_out"], -1))            # the compiled reference's own output
+    codes2, _, _ = _gpu_code(g["cp_X"][None], g["cp2_lp"], g["cp2_lip"], 5, 2)
+    np.testing.assert_array_equal(codes2[0], np.argmax(g["cp2_out"], -1))
+
+
+def test_code_parts_int8_config_shapes(cuda, oracle):
+    from tsr_b200 import synth
+    lp, lip = synth.parts(100)
+    X = synth.utterance_batch(3)
+    codes = _check_int8(X, lp, lip, 12, oracle)
+    assert 0.1 < (codes != 0).mean() < 0.9
+
+
+@pytest.mark.parametrize("T,F,E,K,ph,pw,thr", [(5, 5, 8, 1, 5, 5, 0), (9, 40, 8, 50, 5, 5, 30), (31, 7, 3, 9, 5, 5, 4),
+                                              (40, 45, 8, 200, 5, 5, 12), (17, 23, 8, 13, 3, 7, 6), (300, 6, 8, 5, 6, 6, 1),
+                                              (12, 12, 8, 100, 1, 1, 1), (33, 21, 8, 238, 5, 5, 8)])
+def test_code_parts_int8_edge_cases(cuda, oracle, T, F, E, K, ph, pw, thr):
+    rs = np.random.RandomState(T * 131 + F)
+    X = (rs.rand(2, T, F, E) < 0.18).astype(np.uint8)
+    P = np.clip(rs.rand(K, ph, pw, E) ** 2, .01, .99)
+    _check_int8(X, np.log(P), np.log(1 - P), thr, oracle)
+
+
+def test_code_parts_int8_ties_and_wide_constants(cuda, oracle):
+    """Duplicate parts (exact ties: the lowest index must win, as np.argmax), near-duplicate parts (differences far
+    below the fixed-point unit: only the float64 refinement can order them), more than 32 candidates at a location,
+    and a dictionary whose constants c[k] span several constant K-steps."""
+    rs = np.random.RandomState(5)
+    X = (rs.rand(2, 24, 16, 8) < 0.2).astype(np.uint8)
+    P = np.clip(rs.rand(60, 5, 5, 8) ** 2, .01, .99)
+    P[7] = P[3]; P[40] = P[3]                              # exact duplicates
+    P[11] = np.clip(P[5] * (1 + 1e-9), .01, .99)           # 1e-9 apart
+    P[12] = np.clip(P[5] * (1 - 1e-9), .01, .99)
+    _check_int8(X, np.log(P), np.log(1 - P), 6, oracle)
+    P = np.repeat(np.clip(rs.rand(1, 5, 5, 8), .05, .95), 50, 0) * (1 + 1e-7 * rs.randn(50, 5, 5, 8))   # 50 candidates everywhere
+    _check_int8(X, np.log(P), np.log(1 - P), 6, oracle)
+    # more undecided locations than the work list holds candidate sets for (capacity: one location in eight + 1024):
+    # the rest arrive as bare locations and the refinement recomputes their integer accumulators first
+    Xb = (rs.rand(4, 60, 40, 8) < 0.2).astype(np.uint8)
+    _check_int8(Xb, np.log(P), np.log(1 - P), 1, oracle)                      # 50 candidates each: rounds of 32
+    P3 = np.clip(rs.rand(20, 5, 5, 8) ** 2, .01, .99)
+    P3 = np.concatenate([P3, P3[:3] * (1 + 1e-8 * rs.randn(3, 5, 5, 8))])      # parts 20-22 shadow parts 0-2
+    P3 = np.concatenate([P3[:3], P3[:3], P3], 0)                               # and exact duplicates in front
+    _check_int8(Xb, np.log(P3), np.log(1 - P3), 1, oracle)
+    # small weights (|w| <= 0.2) and constants that differ by hundreds of them: three constant K-steps, reduced qmax
+    P = 0.45 + 0.1 * (rs.permutation(40) / 39.0)[:, None, None, None] + 0.004 * rs.rand(40, 5, 5, 8)
+    _check_int8(X, np.log(P), np.log(1 - P), 6, oracle)
+
+
+def test_code_parts_int8_full_size(cuda):
+    """256 BASELINE utterances: the int8 form against the float32 SIMT kernel -- equal except where the SIMT kernel's
+    own float32 rounding flips a near-tie -- and no location is left marked."""
+    from tsr_b200 import ops, synth
+    lp, lip = synth.parts(100)
+    parts = ops.PartsModel(lp, lip)
+    X = synth.fast_edge_batch(256)
+    bits = ops.pack_edges(torch.from_numpy(X).cuda())
+    c_i, _, n_i = ops.code_parts(bits, parts, 12, want_counts=True, impl=2)
+    c_s, s_s, n_s = ops.code_parts(bits, parts, 12, want_counts=True, want_scores=True, impl=1)
+    torch.cuda.synchronize()
+    assert torch.equal(n_i, n_s)
+    assert int(c_i.max()) <= 100
+    diff = c_i != c_s
+    ndiff = int(diff.sum())
+    print("int8 vs simt code differences: %d of %d" % (ndiff, c_i.numel()))
+    assert ndiff <= 1e-5 * c_i.numel() + 5
+    if ndiff:
+        idx = diff.nonzero()
+        sc = s_s[idx[:, 0], idx[:, 1], idx[:, 2]]
+        a = torch.gather(sc, 1, (c_i[diff].long() - 1)[:, None])[:, 0]
+        b = torch.gather(sc, 1, (c_s[diff].long() - 1)[:, None])[:, 0]
+        assert float(((b - a).abs() / b.abs()).max()) < 2e-6
+    # fused edge spreading in the producers and in the refinement: same codes as spreading first
+    raw = ops.pack_edges(torch.from_numpy(synth.fast_edge_batch(8, seed=3)).cuda())
+    sp = ops.spread_edges(raw, 1, None, "line", 40, tail_window=True)
+    a, _, _ = ops.code_parts(sp, parts, 12, impl=2)
+    b, _, _ = ops.code_parts(raw, parts, 12, impl=2, edge_spread_radius=1, edge_block_len=40)
+    assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("impl", [0, 2], ids=["tensor", "int8"])
+def test_code_parts_200_parts_many_tiles(cuda, impl):
+    """200 parts (N_pad = 208: two 256-column accumulators instead of four) over enough utterances that every CTA
+    walks dozens of tiles -- the accumulator hand-over between issuers and epilogue sets -- against the SIMT kernel."""
+    from tsr_b200 import ops, synth
+    lp, lip = synth.parts(200)
+    parts = ops.PartsModel(lp, lip)
+    bits = ops.pack_edges(torch.from_numpy(synth.fast_edge_batch(96, seed=5)).cuda())
+    c_t, _, n_t = ops.code_parts(bits, parts, 12, want_counts=True, impl=impl)
+    c_s, s_s, n_s = ops.code_parts(bits, parts, 12, want_counts=True, want_scores=True, impl=1)
+    torch.cuda.synchronize()
+    assert torch.equal(n_t, n_s)
+    diff = c_t != c_s
+    ndiff = int(diff.sum())
+    print("200 parts, impl %d vs simt: %d of %d codes differ" % (impl, ndiff, c_t.numel()))
+    assert ndiff <= 2e-5 * c_t.numel() + 5
+    if ndiff:
+        idx = diff.nonzero()
+        sc = s_s[idx[:, 0], idx[:, 1], idx[:, 2]]
+        a = torch.gather(sc, 1, (c_t[diff].long() - 1)[:, None])[:, 0]
+        b = torch.gather(sc, 1, (c_s[diff].long() - 1)[:, None])[:, 0]
+        assert float(((b - a).abs() / b.abs()).max()) < 1e-5
+
+
 def test_dropin_functions_match_reference_layout(cuda, oracle, golden):
     from tsr_b200 import code_parts as cp
     g = golden

@@ -17,6 +17,7 @@ ap.add_argument("--batch", type=int, default=1024)
 ap.add_argument("--reps", type=int, default=10)
 ap.add_argument("--planes", type=int, default=4)
 ap.add_argument("--radius", type=int, default=1)
+ap.add_argument("--impl-code", type=int, default=2, help="tsr_code_parts impl: 0 = 16-bit hi+lo planes, 2 = int8 form + float64 refinement")
 ap.add_argument("--cold", action="store_true", help="flush the L2 (write + read pass) before every call and time each call with its own events")
 a = ap.parse_args()
 B = a.batch
@@ -39,7 +40,7 @@ flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 torch.cuda.synchronize()
 calls = {
     "spread_edges": (lambda: ops.spread_edges(bits, a.radius, None, "line", 40), 2.0 * 300 * 40 * B, "B"),
-    "code_parts": (lambda: ops.code_parts(sb, parts, 12), 2.0 * 296 * 36 * 200 * 100 * B, "FLOP"),
+    "code_parts": (lambda: ops.code_parts(sb, parts, 12, impl=a.impl_code), 2.0 * 296 * 36 * 200 * 100 * B, "FLOP"),
     "spread_codes": (lambda: ops.spread_codes(codes, 100, 2, 2), 17.0 * 36 * 296 * B, "B"),
     "detect": (lambda: ops.detect(fb, bank, out=scores), 2.0 * 257 * 40 * 3600 * 32 * B, "FLOP"),
     "edges_fused": (lambda: ops.edges_from_spectrogram(spec, 40, 0.7), 9.0 * 300 * 40 * B, "B"),

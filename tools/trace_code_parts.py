@@ -7,10 +7,11 @@ import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from tsr_b200 import ops, synth, _lib
 lib = _lib.lib()
+impl = int(sys.argv[2]) if len(sys.argv) > 2 else 2
 lp, lip = synth.parts(100)
 parts = ops.PartsModel(lp, lip)
 bits = ops.pack_edges(torch.from_numpy(synth.fast_edge_batch(1024)).cuda())
-ops.code_parts(bits, parts, 12)
+ops.code_parts(bits, parts, 12, impl=impl)
 torch.cuda.synchronize()
 flags = int(sys.argv[1]) if len(sys.argv) > 1 else 0
 lib.tsr_debug_set_code_flags(flags)
@@ -18,7 +19,7 @@ print("debug flags", flags)
 buf = torch.zeros(96 * 8, dtype=torch.int64, device="cuda")
 lib.tsr_debug_set_code_trace.argtypes = [ctypes.c_void_p]
 lib.tsr_debug_set_code_trace(buf.data_ptr())
-ops.code_parts(bits, parts, 12)
+ops.code_parts(bits, parts, 12, impl=impl)
 torch.cuda.synchronize()
 lib.tsr_debug_set_code_trace(None)
 t = buf.cpu().numpy().reshape(96, 8)
@@ -27,7 +28,7 @@ names = ["prod:empty_ok", "prod:arrived", "mma:full_ok", "mma:tempty_ok", "mma:i
 if flags & 4:   # epilogue detail: slots 1-4 = first wait::ld done, first block reduced, second wait done, second block reduced
     names = ["-", "epi:ld1_done", "epi:red1_done", "epi:ld2_done", "epi:red2_done", "epi:tfull_ok", "epi:tmem_free", "epi:done"]
 print("tile " + " ".join("%14s" % n for n in names))
-for i in range(30, 36):
+for i in range(30, 38):
     print("%4d " % i + " ".join("%14d" % (x - t0 if x else -1) for x in t[i]))
 d = np.diff(t[8:90, 4])
 print("mean cycles between consecutive tiles' MMA issue:", d.mean())
