@@ -332,6 +332,24 @@ def run_native(args):
         k1a.append((e0, e1))
     torch.cuda.synchronize()
     k1a_ms = float(np.mean([a.elapsed_time(b) for a, b in k1a]))
+    # K2's two tensor forms side by side (not in the step): 16-bit hi+lo planes against the int8 form with its float64
+    # refinement, at the config's 100 parts and at 200 parts (the largest dictionaries the reference trains)
+    sb_once = pipe.spread(bits)
+
+    def time_code(parts_model, impl):
+        ops.code_parts(sb_once, parts_model, EDGE_THR, impl=impl)
+        evs_c = []
+        for _ in range(3):
+            flush.fill_(1); flush_rd.sum()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream); ops.code_parts(sb_once, parts_model, EDGE_THR, impl=impl); e1.record(stream)
+            evs_c.append((e0, e1))
+        torch.cuda.synchronize()
+        return float(np.mean([a.elapsed_time(b) for a, b in evs_c]))
+    parts200 = ops.PartsModel(*synth.parts(200), device=dev)
+    code_forms = {"parts100_hilo_ms": time_code(pipe.parts, ops.IMPL_TENSOR), "parts100_int8_ms": time_code(pipe.parts, ops.IMPL_TENSOR_INT8),
+                  "parts200_hilo_ms": time_code(parts200, ops.IMPL_TENSOR), "parts200_int8_ms": time_code(parts200, ops.IMPL_TENSOR_INT8)}
+    del parts200, sb_once
     # A8 / A9: the real-valued detectors (detect_float / detect_float_max), bit-exact SIMT kernel, at an edge-level shape:
     # 64 utterances x 300 frames x 320 real features against 8 templates of 40 frames
     gf = torch.Generator(device=dev).manual_seed(9)
@@ -426,6 +444,11 @@ def run_native(args):
             "code_parts": {"ms": stage_ms[0], "bound": "tensor", "achieved_tflops": code_tf, "frac": code_tf / peaks["tf_burst"],
                            "frac_sustained": code_tf / peaks["tf_sustained"],
                            "includes": "edge spreading (radius 1 per 40-frame block) fused into the producers" if fused else "spread_edges launches + code_parts"},
+            "code_parts_forms": dict(code_forms, note="not in the step: tsr_code_parts alone, cold L2.  hilo = 16-bit hi+lo planes (kind::f16, 27 MMAs per "
+                                     "128-location tile; the pipeline's choice up to 126 parts); int8 = one fixed-point scale, both base-255 digits in one "
+                                     "K group (kind::i8, 14 MMAs) + float64 refinement of the undecided locations: codes equal the reference's "
+                                     "arg-max everywhere; the pipeline's choice above 126 parts",
+                                     parts200_int8_tflops=2.0 * FLOP_CODE * B / (code_forms["parts200_int8_ms"] * 1e-3) / 1e12),
             "spread_codes": {"ms": stage_ms[1], "bound": "hbm", "achieved_gbs": BYTES_SPREAD_CODES * B / (stage_ms[1] * 1e-3) / 1e9,
                              "frac": BYTES_SPREAD_CODES * B / (stage_ms[1] * 1e-3) / 1e9 / peaks["hbm"]},
             "detect": {"ms": det_ms, "bound": "tensor", "achieved_tflops": det_tf, "frac": det_tf / peaks["tf_burst"],

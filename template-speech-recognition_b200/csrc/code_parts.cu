@@ -445,6 +445,19 @@ __host__ __device__ inline CodeSmem code_smem_layout(const PartsLayout& L, int F
     return S;
 }
 
+// (utterance, tile inside the utterance) of a tile index that advances by a constant stride: no 64-bit divisions in the
+// per-tile loops
+struct TileWalk {
+    int b, q, sb, sq, tpu;
+    __device__ __forceinline__ TileWalk(long long tile0, long long stride, int tiles_per_utt) : tpu(tiles_per_utt) {
+        b = (int)(tile0 / tpu); q = (int)(tile0 % tpu); sb = (int)(stride / tpu); sq = (int)(stride % tpu);
+    }
+    __device__ __forceinline__ void next() {
+        b += sb; q += sq;
+        if (q >= tpu) { q -= tpu; ++b; }
+    }
+};
+
 // NSTEPS_CT > 0: K-step count known at compile time (13 for the 5x5 parts of every reference config): the
 // issue loop is fully unrolled with the descriptor words in registers.  NSTEPS_CT == 0: generic, smem table.
 // I8: the int8 form (prepare_parts_i8_kernel): kind::i8 MMAs of K = 32 -- both weight digits of two positions per
@@ -516,22 +529,29 @@ __global__ void __launch_bounds__(CP_THREADS, 1) code_parts_tc_kernel(CodeArgs A
         const int plimit = A.T * A.F;
         const int npos = (int)S.npos;
         uint32_t it = 0;
-        uint32_t pre[4];
-        auto prefetch = [&](long long tile) {
-            const int b = (int)(tile / tiles_per_utt);
-            const int p0 = (int)(tile % tiles_per_utt) * 128;
-            const uint8_t* src = A.bits + (size_t)b * A.T * A.F;
+        // The packed bytes of a tile are fetched TWO tiles ahead into alternating register sets: with one set the global
+        // load latency (~900 cycles) sat inside every iteration, which is what bounds the int8 form once its MMAs take
+        // half the time.
+        uint32_t preA[4], preB[4];
+        const uint32_t nap = 40u;
+        TileWalk wf(blockIdx.x, gridDim.x, tiles_per_utt);       // the tile being fetched
+        TileWalk wt(blockIdx.x, gridDim.x, tiles_per_utt);       // the tile being written
+        auto fetch = [&](uint32_t (&pre)[4], long long tile) {
+            if (tile < ntiles) {
+                const int p0 = wf.q * 128;
+                const uint8_t* src = A.bits + (size_t)wf.b * A.T * A.F;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                int pos = pt + 128 * j, p = p0 + pos;
-                pre[j] = (pos < npos && p < plimit) ? (A.spread_radius ? spread1_byte(src, p, A.sc) : (uint32_t)src[p]) : 0u;
+                for (int j = 0; j < 4; ++j) {
+                    int pos = pt + 128 * j, p = p0 + pos;
+                    pre[j] = (pos < npos && p < plimit) ? (A.spread_radius ? spread1_byte(src, p, A.sc) : (uint32_t)src[p]) : 0u;
+                }
             }
+            wf.next();
         };
-        if ((long long)blockIdx.x < ntiles) prefetch(blockIdx.x);
-        for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+        auto put = [&](const uint32_t (&pre)[4]) {
             const int stage = it % CP_NSTAGE;
             const uint32_t ph = (it / CP_NSTAGE) & 1;
-            mbar_wait_relaxed(&empty_bar[stage], ph ^ 1);
+            mbar_wait_relaxed(&empty_bar[stage], ph ^ 1, nap);
             if (warp == 8 && !CP_DBG(4)) CP_TRACE(0);
             uint8_t* dst = smem + S.a + stage * S.stage_bytes;
 #pragma unroll
@@ -540,9 +560,8 @@ __global__ void __launch_bounds__(CP_THREADS, 1) code_parts_tc_kernel(CodeArgs A
                 if (pos < npos) *reinterpret_cast<uint4*>(dst + pos * 16) = I8 ? expand_byte_u8x2(pre[j]) : expand_byte(pre[j], one);
             }
             if (npos > 512) {   // very wide inputs: remaining positions straight from global
-                const int b = (int)(tile / tiles_per_utt);
-                const int p0 = (int)(tile % tiles_per_utt) * 128;
-                const uint8_t* src = A.bits + (size_t)b * A.T * A.F;
+                const int p0 = wt.q * 128;
+                const uint8_t* src = A.bits + (size_t)wt.b * A.T * A.F;
                 for (int pos = pt + 512; pos < npos; pos += 128) {
                     int p = p0 + pos;
                     const uint32_t byte = p < plimit ? (A.spread_radius ? spread1_byte(src, p, A.sc) : (uint32_t)src[p]) : 0u;
@@ -552,7 +571,20 @@ __global__ void __launch_bounds__(CP_THREADS, 1) code_parts_tc_kernel(CodeArgs A
             fence_proxy_async_smem();
             mbar_arrive(&full_bar[stage]);
             if (warp == 8 && !CP_DBG(4)) CP_TRACE(1);
-            if (tile + gridDim.x < ntiles) prefetch(tile + gridDim.x);   // overlaps the next empty-slot wait
+            wt.next();
+            ++it;
+        };
+        long long tile = blockIdx.x;
+        fetch(preA, tile);
+        fetch(preB, tile + gridDim.x);
+        while (tile < ntiles) {
+            put(preA);
+            fetch(preA, tile + 2ll * gridDim.x);
+            tile += gridDim.x;
+            if (tile >= ntiles) break;
+            put(preB);
+            fetch(preB, tile + 2ll * gridDim.x);
+            tile += gridDim.x;
         }
     } else if (warp >= 12) {
         // ================================ MMA issuers ================================
@@ -658,12 +690,14 @@ __global__ void __launch_bounds__(CP_THREADS, 1) code_parts_tc_kernel(CodeArgs A
         const int eset = warp >= 4 ? 1 : 0;
         const int e = (warp & 3) * 32 + lane;   // TMEM lane == tile row (lane quadrant = warp % 4)
         uint32_t it = eset;
-        for (long long tile = blockIdx.x + (long long)eset * gridDim.x; tile < ntiles; tile += 2ll * gridDim.x, it += 2) {
+        TileWalk we(blockIdx.x + (long long)eset * gridDim.x, 2ll * gridDim.x, tiles_per_utt);
+        for (long long tile = blockIdx.x + (long long)eset * gridDim.x; tile < ntiles; tile += 2ll * gridDim.x, it += 2, we.next()) {
             const int acc = it % nacc;             // this set owns accumulators eset and (with four) eset + 2
             const uint32_t aph = (it / nacc) & 1;
-            const int b = (int)(tile / tiles_per_utt);
-            const int p = (int)(tile % tiles_per_utt) * 128 + e;
-            const int t = p / A.F, f = p - t * A.F;
+            const int b = we.b;
+            const int p = we.q * 128 + e;
+            int f;
+            const int t = fast_div(p, A.F, A.sc.magicF, f);
             const bool valid = t < A.To && f < A.Fo;
             const size_t loc = ((size_t)b * A.To + t) * A.Fo + f;
             mbar_wait_relaxed(&tfull_bar[acc], aph);

@@ -89,10 +89,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // Same wait for warps that are NOT on the critical issue path (producers, epilogue): back off
 // between polls so the spinning warp does not take issue slots from the MMA-issuing warp (the
 // SMSP arbiter favours higher warp ids; a tight poll loop in a higher-id warp starves it).
-__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity, uint32_t sleep_ns = 40) {
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
-        __nanosleep(40);
+        __nanosleep(sleep_ns);
         if (++spins > TSR_SPIN_LIMIT) {
             printf("tsr_b200: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
             __trap();

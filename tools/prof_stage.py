@@ -14,19 +14,22 @@ ap.add_argument("stage")
 ap.add_argument("--batch", type=int, default=1024)
 ap.add_argument("--iters", type=int, default=3)
 ap.add_argument("--simt", action="store_true")
+ap.add_argument("--impl-code", type=int, default=0, help="tsr_code_parts impl: 0 = 16-bit hi+lo planes, 2 = int8 form + float64 refinement")
+ap.add_argument("--parts", type=int, default=100)
 ap.add_argument("--planes", type=int, default=3, help="3 = INT8X2 (detect_tn_kernel, the pipeline default), 4 = INT8X3 (detect_tc_kernel)")
 a = ap.parse_args()
 impl = ops.IMPL_SIMT if a.simt else ops.IMPL_TENSOR
 B = a.batch
-lp, lip = synth.parts(100)
+lp, lip = synth.parts(a.parts)
 parts = ops.PartsModel(lp, lip)
 Tm, bgd = synth.templates(M=32, L=40, Fd=36, Kd=100)
 W, c = synth.linear_filters(Tm, bgd)
 bank = ops.FilterBank(W, cs=c, planes=a.planes)
 bits = ops.pack_edges(torch.from_numpy(synth.fast_edge_batch(B)).cuda())
 sb = ops.spread_edges(bits, 1, None, "line", 40)
-codes, _, _ = ops.code_parts(sb, parts, 12, impl=impl)
-fb = ops.spread_codes(codes, 100, 2, 2)
+impl_code = impl if a.simt else a.impl_code
+codes, _, _ = ops.code_parts(sb, parts, 12, impl=impl_code)
+fb = ops.spread_codes(codes, a.parts, 2, 2)
 torch.cuda.synchronize()
 ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
 for it in range(a.iters):
@@ -34,9 +37,9 @@ for it in range(a.iters):
     if a.stage in ("spread_edges", "all"):
         ops.spread_edges(bits, 1, None, "line", 40)
     if a.stage in ("code_parts", "all"):
-        ops.code_parts(sb, parts, 12, impl=impl)
+        ops.code_parts(sb, parts, 12, impl=impl_code)
     if a.stage in ("spread_codes", "all"):
-        ops.spread_codes(codes, 100, 2, 2)
+        ops.spread_codes(codes, a.parts, 2, 2)
     if a.stage in ("detect", "all"):
         ops.detect(fb, bank, impl=impl)
     if a.stage == "detect_float":              # A8 / A9: real-valued detectors (bit-exact sequential fp32, SIMT)

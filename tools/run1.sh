@@ -1,3 +1,9 @@
 mkdir -p gpurun_out
-timeout 300 python -m pytest tests/test_gpu_code_parts.py -q -m gpu --timeout=200 -x -k "int8 or 200_parts" -s > gpurun_out/test_cp_int8.log 2>&1; echo "int8 tests exit $?"; grep -v "timed out" gpurun_out/test_cp_int8.log | tail -6
-timeout 120 python tools/refine_probe.py 2>&1 | grep -v "timed out" | tail -5
+bash tools/gpu_suite.sh --steps 20 --warmup 5 > gpurun_out/suite.log 2>&1
+cat gpurun_out/summary.txt
+timeout 120 python tools/refine_probe.py 2>&1 | grep -v "timed out" | tail -3
+timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref.log 2>&1; echo "ref rc $?"
+python bench.py --steps 2 --warmup 3 --no-cpu > gpurun_out/bench_plain.log 2>&1 &&
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file gpurun_out/r02_launches.csv \
+    python bench.py --steps 2 --warmup 3 --no-cpu > gpurun_out/ncu_launches.log 2>&1
+echo "launch list exit $?"

@@ -19,6 +19,8 @@ REPORTS = [
     ("detect", "python tools/prof_stage.py detect --iters 2   (B=1024 utterances, config 3; INT8X2 = detect_tn_kernel, the pipeline default)"),
     ("detect_x3", "python tools/prof_stage.py detect --iters 2 --planes 4   (the exact 24-bit variant, detect_tc_kernel)"),
     ("code_parts", "python tools/prof_stage.py code_parts --iters 2   (B=1024 utterances, 100 parts)"),
+    ("code_parts_int8", "python tools/prof_stage.py code_parts --iters 2 --impl-code 2   (the int8 form: code_parts_tc_kernel<13, true> + code_parts_refine_kernel)"),
+    ("code_parts_int8_200", "python tools/prof_stage.py code_parts --iters 2 --impl-code 2 --parts 200   (200 parts: N = 208, two 256-column accumulators)"),
     ("spread_codes", "python tools/prof_stage.py spread_codes --iters 2"),
     ("spread_edges", "python tools/prof_stage.py spread_edges --iters 2"),
     ("threshold_blocks", "python tools/prof_stage.py threshold_blocks --iters 2"),
@@ -33,6 +35,8 @@ def to_bytes(v, unit):
 
 def short(name):
     n = name.split("(")[0].replace("void ", "").replace("tsr::", "")
+    if n.startswith("code_parts_tc_kernel") and "true" in n:     # <NSTEPS, true> = the int8 form
+        return "code_parts_tc_kernel_int8"
     return n.split("<")[0]
 
 
@@ -62,7 +66,7 @@ for suffix, command in REPORTS:
         rd = [to_bytes(v, u) for h, (v, u) in d.items() if h == "dram__bytes_read.sum"]
         wr = [to_bytes(v, u) for h, (v, u) in d.items() if h == "dram__bytes_write.sum"]
         dur = [float(v) * {"ms": 1e-3, "us": 1e-6, "ns": 1e-9, "s": 1}.get(u, 1) for h, (v, u) in d.items() if h == "gpu__time_duration.sum"]
-        summary[short(kname)] = {"batch": 1024 if suffix != "em" else None, "dram_bytes": (rd[0] + wr[0]) if rd and wr else None,
+        summary[short(kname) + ("_200parts" if suffix.endswith("_200") else "")] = {"batch": 1024 if suffix != "em" else None, "dram_bytes": (rd[0] + wr[0]) if rd and wr else None,
                                  "duration_s_under_ncu": dur[0] if dur else None, "capture": "%s_%s" % (tag, suffix)}
         lines.append("")
     open(os.path.join(ROOT, "profiles", "%s_%s_ncu_full.txt" % (tag, suffix)), "w").write("\n".join(lines) + "\n")
