@@ -425,7 +425,20 @@ __global__ void __launch_bounds__(256) code_parts_simt_kernel(CodeArgs A) {
 // ------------------------------------------------------------------------- tensor path
 #define CP_NSTAGE 4
 #define CP_NISSUE 4
-#define CP_THREADS (384 + 32 * CP_NISSUE)   // warps 0-3 / 4-7 epilogue (even / odd tiles), 8-11 producers, 12.. MMA issuers (tile % CP_NISSUE; highest ids win arbitration)
+#define CP_THREADS (384 + 32 * CP_NISSUE)   // hi+lo form: warps 0-3 / 4-7 epilogue (even / odd tiles), 8-11 producers, 12.. MMA issuers (tile % CP_NISSUE; highest ids win arbitration)
+// Roles (the same for both forms).  Measured for the int8 form, which issues 14 MMAs per tile instead of 27 and is bound
+// by its epilogue: two producer warps + two issuers with the other four warps retired (fewer polling warps) 1.09 ms
+// against 0.72; a third epilogue set in their place 1.07 ms -- a tile's MMAs leave ONE thread at ~125 cycles each, so
+// the four issuers (four tiles in flight) are what overlaps them.
+template <bool I8> struct CodeRoles {
+    static constexpr int kEpiSets = 2;
+    static constexpr int kProdWarp0 = 4 * kEpiSets;
+    static constexpr int kProdWarps = 4;
+    static constexpr int kIssueWarp0 = kProdWarp0 + kProdWarps;
+    static constexpr int kIssueWarps = CP_NISSUE;
+    static constexpr int kProdSlots = 512 / (32 * kProdWarps);      // positions a producer thread keeps in registers
+    static_assert(32 * (kIssueWarp0 + kIssueWarps) <= CP_THREADS, "roles must fit the CTA");
+};
 #define CP_MAX_STEPS 32
 #define CP_NACC 4         // barrier slots; TMEM accumulators in use: 4 x 128 columns when N_pad <= 128, else 2 x 256
 
@@ -467,6 +480,7 @@ struct TileWalk {
 template <int NSTEPS_CT, bool I8>
 __global__ void __launch_bounds__(CP_THREADS, 1) code_parts_tc_kernel(CodeArgs A, int tiles_per_utt, long long ntiles) {
     extern __shared__ __align__(1024) uint8_t smem[];
+    using R = CodeRoles<I8>;
     const PartsLayout& L = A.L;
     const CodeSmem S = code_smem_layout(L, A.F, I8);
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S.bars);       // [CP_NSTAGE]
@@ -483,12 +497,12 @@ __global__ void __launch_bounds__(CP_THREADS, 1) code_parts_tc_kernel(CodeArgs A
     const uint32_t nacc = L.npad <= 128 ? 4u : 2u, acc_cols = 512u / nacc;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < CP_NSTAGE; ++s) { mbar_init(&full_bar[s], 128); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < CP_NSTAGE; ++s) { mbar_init(&full_bar[s], 32 * R::kProdWarps); mbar_init(&empty_bar[s], 1); }
         for (int a = 0; a < CP_NACC; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 128); }
         mbar_init(w_bar, 1);
         mbar_fence_init();
     }
-    if (warp == 12) {
+    if (warp == R::kIssueWarp0) {
         tmem_alloc<512>(tmem_ptr);
     }
     {   // constant A operand of the c[k] step: k-group 0 rows = [1,1,1,0,0,0,0,0], k-group 1 (2 KB further) = 0
@@ -522,9 +536,10 @@ __global__ void __launch_bounds__(CP_THREADS, 1) code_parts_tc_kernel(CodeArgs A
         }
     }
 
-    if (warp >= 8 && warp <= 11) {
+    if (warp >= R::kProdWarp0 && warp < R::kIssueWarp0) {
         // ================================ producers ================================
-        const int pt = threadIdx.x - 256;
+        const int pt = threadIdx.x - 32 * R::kProdWarp0;
+        constexpr int PT = 32 * R::kProdWarps, NJ = R::kProdSlots;
         const uint32_t one = fmt_one(fmt);
         const int plimit = A.T * A.F;
         const int npos = (int)S.npos;
@@ -532,37 +547,37 @@ __global__ void __launch_bounds__(CP_THREADS, 1) code_parts_tc_kernel(CodeArgs A
         // The packed bytes of a tile are fetched TWO tiles ahead into alternating register sets: with one set the global
         // load latency (~900 cycles) sat inside every iteration, which is what bounds the int8 form once its MMAs take
         // half the time.
-        uint32_t preA[4], preB[4];
+        uint32_t preA[NJ], preB[NJ];
         const uint32_t nap = 40u;
         TileWalk wf(blockIdx.x, gridDim.x, tiles_per_utt);       // the tile being fetched
         TileWalk wt(blockIdx.x, gridDim.x, tiles_per_utt);       // the tile being written
-        auto fetch = [&](uint32_t (&pre)[4], long long tile) {
+        auto fetch = [&](uint32_t (&pre)[NJ], long long tile) {
             if (tile < ntiles) {
                 const int p0 = wf.q * 128;
                 const uint8_t* src = A.bits + (size_t)wf.b * A.T * A.F;
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    int pos = pt + 128 * j, p = p0 + pos;
+                for (int j = 0; j < NJ; ++j) {
+                    int pos = pt + PT * j, p = p0 + pos;
                     pre[j] = (pos < npos && p < plimit) ? (A.spread_radius ? spread1_byte(src, p, A.sc) : (uint32_t)src[p]) : 0u;
                 }
             }
             wf.next();
         };
-        auto put = [&](const uint32_t (&pre)[4]) {
+        auto put = [&](const uint32_t (&pre)[NJ]) {
             const int stage = it % CP_NSTAGE;
             const uint32_t ph = (it / CP_NSTAGE) & 1;
             mbar_wait_relaxed(&empty_bar[stage], ph ^ 1, nap);
-            if (warp == 8 && !CP_DBG(4)) CP_TRACE(0);
+            if (warp == R::kProdWarp0 && !CP_DBG(4)) CP_TRACE(0);
             uint8_t* dst = smem + S.a + stage * S.stage_bytes;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                int pos = pt + 128 * j;
+            for (int j = 0; j < NJ; ++j) {
+                int pos = pt + PT * j;
                 if (pos < npos) *reinterpret_cast<uint4*>(dst + pos * 16) = I8 ? expand_byte_u8x2(pre[j]) : expand_byte(pre[j], one);
             }
             if (npos > 512) {   // very wide inputs: remaining positions straight from global
                 const int p0 = wt.q * 128;
                 const uint8_t* src = A.bits + (size_t)wt.b * A.T * A.F;
-                for (int pos = pt + 512; pos < npos; pos += 128) {
+                for (int pos = pt + 512; pos < npos; pos += PT) {
                     int p = p0 + pos;
                     const uint32_t byte = p < plimit ? (A.spread_radius ? spread1_byte(src, p, A.sc) : (uint32_t)src[p]) : 0u;
                     *reinterpret_cast<uint4*>(dst + pos * 16) = I8 ? expand_byte_u8x2(byte) : expand_byte(byte, one);
@@ -570,7 +585,7 @@ __global__ void __launch_bounds__(CP_THREADS, 1) code_parts_tc_kernel(CodeArgs A
             }
             fence_proxy_async_smem();
             mbar_arrive(&full_bar[stage]);
-            if (warp == 8 && !CP_DBG(4)) CP_TRACE(1);
+            if (warp == R::kProdWarp0 && !CP_DBG(4)) CP_TRACE(1);
             wt.next();
             ++it;
         };
@@ -586,7 +601,9 @@ __global__ void __launch_bounds__(CP_THREADS, 1) code_parts_tc_kernel(CodeArgs A
             fetch(preB, tile + 2ll * gridDim.x);
             tile += gridDim.x;
         }
-    } else if (warp >= 12) {
+    } else if (warp >= R::kIssueWarp0 + R::kIssueWarps) {
+        // spare warps (int8 form): nothing to do
+    } else if (warp >= R::kIssueWarp0) {
         // ================================ MMA issuers ================================
         // One thread can issue a tcgen05.mma only every ~75-90 cycles (tools/ts_probe.cu: 90.7 cycles per MMA from
         // one warp, 60.4 from two, against 59 cycles of tensor work at N = 112), so two warps on different SMSPs
@@ -629,7 +646,7 @@ __global__ void __launch_bounds__(CP_THREADS, 1) code_parts_tc_kernel(CodeArgs A
         }
         // With two 256-column accumulators (N_pad > 128) only two issuers run: an accumulator must belong to ONE issuer,
         // whose program order is what makes its tempty parity waits see every second release.
-        const int iss = warp - 12, nissue = nacc == 4u ? CP_NISSUE : 2;
+        const int iss = warp - R::kIssueWarp0, nissue = nacc == 4u ? R::kIssueWarps : 2;
         uint32_t it = iss;
         for (long long tile = iss < nissue ? blockIdx.x + (long long)iss * gridDim.x : ntiles; tile < ntiles; tile += (long long)nissue * gridDim.x, it += nissue) {
             const int stage = it % CP_NSTAGE;
@@ -687,11 +704,12 @@ __global__ void __launch_bounds__(CP_THREADS, 1) code_parts_tc_kernel(CodeArgs A
     } else {
         // ================================ epilogue ================================
         // two warp sets: warps 0-3 drain accumulator 0 (even tiles), warps 4-7 accumulator 1 (odd tiles)
-        const int eset = warp >= 4 ? 1 : 0;
+        const int eset = warp >> 2;
+        constexpr int NSETS = R::kEpiSets;
         const int e = (warp & 3) * 32 + lane;   // TMEM lane == tile row (lane quadrant = warp % 4)
         uint32_t it = eset;
-        TileWalk we(blockIdx.x + (long long)eset * gridDim.x, 2ll * gridDim.x, tiles_per_utt);
-        for (long long tile = blockIdx.x + (long long)eset * gridDim.x; tile < ntiles; tile += 2ll * gridDim.x, it += 2, we.next()) {
+        TileWalk we(blockIdx.x + (long long)eset * gridDim.x, (long long)NSETS * gridDim.x, tiles_per_utt);
+        for (long long tile = blockIdx.x + (long long)eset * gridDim.x; tile < ntiles; tile += (long long)NSETS * gridDim.x, it += NSETS, we.next()) {
             const int acc = it % nacc;             // this set owns accumulators eset and (with four) eset + 2
             const uint32_t aph = (it / nacc) & 1;
             const int b = we.b;
@@ -823,7 +841,7 @@ __global__ void __launch_bounds__(CP_THREADS, 1) code_parts_tc_kernel(CodeArgs A
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 12) {
+    if (warp == R::kIssueWarp0) {
         tc_fence_after();
         tmem_dealloc<512>(tmem_base);
     }

@@ -80,7 +80,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
         if (++spins > TSR_SPIN_LIMIT) {
-            printf("tsr_b200: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+            if ((threadIdx.x & 31) == 0) printf("tsr_b200: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
             __trap();
         }
     }
@@ -94,7 +94,7 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity
     while (!mbar_try_wait(bar, parity)) {
         __nanosleep(sleep_ns);
         if (++spins > TSR_SPIN_LIMIT) {
-            printf("tsr_b200: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+            if ((threadIdx.x & 31) == 0) printf("tsr_b200: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
             __trap();
         }
     }
