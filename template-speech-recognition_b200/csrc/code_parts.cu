@@ -1109,6 +1109,18 @@ int tsr_code_parts(const uint8_t* bits, const void* parts_blob, int K, int ph, i
         // two-candidate entries for one location in eight (forty times what log-odds dictionaries produce), then one
         // word per location for whatever does not fit or has more candidates
         A.ws_cap = (unsigned int)(nloc / 8 + 1024);
+        {   // keep freed blocks in the device's pool across synchronisations: the default threshold (0) hands them back to
+            // the driver at every sync and the next call pays a fresh allocation
+            static bool pool_kept[64] = {};
+            int dev = 0;
+            TSR_CUDA(cudaGetDevice(&dev));
+            if (dev >= 0 && dev < 64 && !pool_kept[dev]) {
+                cudaMemPool_t pool;
+                unsigned long long keep = ~0ull;
+                if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+                pool_kept[dev] = true;
+            }
+        }
         TSR_CUDA(cudaMallocAsync((void**)&ws, (2 * (size_t)A.ws_cap + (size_t)nloc + 4) * sizeof(unsigned int), (cudaStream_t)stream));
         TSR_CUDA(cudaMemsetAsync(ws, 0, 16, (cudaStream_t)stream));
         A.ws = ws;

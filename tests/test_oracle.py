@@ -133,6 +133,36 @@ def test_code_parts_equals_correlation(oracle):
         np.testing.assert_allclose(out[..., k + 1], ref, rtol=1e-12, atol=1e-10)
 
 
+def test_int8_coding_bound_restatement(oracle):
+    """The argument behind TSR_IMPL_TENSOR_INT8 (code_parts.cu, prepare_parts_i8_kernel), restated in NumPy: with one
+    fixed-point scale for all parts (q = rint(w / scale), cq = rint(c / scale) - mid) the integer accumulator of a part is
+    within (set bits + 1) / 2 units of its exact score, so wherever the runner-up is more than set bits + 2 units behind,
+    the integer arg-max IS the float64 oracle's arg-max; the GPU kernel re-evaluates every other location in float64."""
+    lp, lip = synth.parts(40)
+    W = (lp - lip).reshape(40, -1)
+    c = lip.reshape(40, -1).sum(1)
+    scale = np.abs(W).max() / 32512.0
+    q = np.rint(W / scale).astype(np.int64)
+    assert np.abs(q).max() <= 32512
+    d1 = np.rint(q / 255.0).astype(np.int64)                 # two balanced base-255 digits, both int8
+    d0 = q - 255 * d1
+    assert np.abs(d0).max() <= 127 and np.abs(d1).max() <= 127
+    cq = np.rint(c / scale).astype(np.int64) - int(np.rint((c.max() + c.min()) / 2 / scale))
+    X = synth.utterance_batch(1, T=60)[0]
+    ref = oracle.code_parts(X, lp, lip, 0)[..., 1:]
+    P = np.lib.stride_tricks.sliding_window_view(X, (5, 5), axis=(0, 1)).transpose(0, 1, 3, 4, 2).reshape(ref.shape[0], ref.shape[1], -1)
+    cnt = P.sum(-1).astype(np.int64)
+    acc = P.astype(np.int64) @ (d0 + 255 * d1).T + cq           # what the kind::i8 MMAs accumulate (exactly)
+    mid = int(np.rint((c.max() + c.min()) / 2 / scale))
+    assert np.all(np.abs(ref / scale - mid - acc) <= 0.5 * (cnt[..., None] + 1) + 1e-6)
+    srt = np.sort(acc, -1)
+    decided = srt[..., -1] - srt[..., -2] > cnt + 2
+    assert decided.mean() > 0.95 and (~decided).any()        # both branches occur in this sample
+    np.testing.assert_array_equal(np.argmax(acc, -1)[decided], np.argmax(ref, -1)[decided])
+    # |acc| * 256 + 255 stays inside int32 (the epilogue packs (acc, 255 - k) into one key)
+    assert (200 + (c.max() - c.min()) / 2 / np.abs(W).max() + 1) * 32512 < 2 ** 23
+
+
 def test_planted_parts_are_recovered(oracle):
     """Development/092412/scripts/test_waliji_coding.py:72-120 pattern: every 5x5x8 block is the
     most likely configuration of part j, so the code at block origins must be j+1."""

@@ -1,9 +1,14 @@
 mkdir -p gpurun_out
-timeout 100 python -m pytest tests/test_gpu_code_parts.py -q -m gpu --timeout=60 -x -k "int8 or 200_parts" > gpurun_out/test_code_parts.log 2>&1; echo "code_parts tests exit $?"; grep -v "timed out" gpurun_out/test_code_parts.log | tail -2
-timeout 60 python tools/refine_probe.py 2>&1 | grep -v "timed out" | tail -3
-for f in "" "--fuse"; do timeout 200 python bench.py --steps 10 --warmup 3 --no-cpu --no-extra $f 2>/dev/null | python -c "
-import json,sys
-for l in sys.stdin:
-    if l.startswith('{'):
-        d=json.loads(l); print('$f', round(d['ms_per_step'],4), {k:round(v['ms'],4) for k,v in d['stages'].items() if isinstance(v,dict) and 'ms' in v})
-"; done
+bash tools/gpu_suite.sh --steps 20 --warmup 5 > gpurun_out/suite.log 2>&1
+cat gpurun_out/summary.txt
+timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref.log 2>&1; echo "ref rc $?"
+prof() {  # suffix, prof_stage args
+  local sfx=$1; shift
+  python tools/prof_stage.py code_parts --iters 2 "$@" > gpurun_out/prof_plain_$sfx.log 2>&1 &&
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:code_parts -s 2 -c 2 -f -o gpurun_out/r02_$sfx \
+      python tools/prof_stage.py code_parts --iters 2 "$@" > gpurun_out/ncu_$sfx.log 2>&1
+  echo "ncu $sfx exit $?"
+}
+prof code_parts
+prof code_parts_int8 --impl-code 2
+prof code_parts_int8_200 --impl-code 2 --parts 200
