@@ -23,6 +23,12 @@
 // Four TMEM accumulator buffers (two per epilogue set) and a 4-deep A ring overlap the three roles: an
 // accumulator is held by the epilogue for about as long as the MMAs need to fill it, so with only two the MMA
 // warps idled half the time waiting for a free one.
+//
+// Int8 form (TSR_IMPL_TENSOR_INT8, template parameter I8): same roles and the same in-place im2col, but one fixed-point
+// scale for all parts, both base-255 weight digits of a position inside one 16-byte K group (A row = [x | 255 x]),
+// kind::i8 MMAs of K = 32 (14 per tile instead of 27), an integer arg-max that also tracks the runner-up, and
+// code_parts_refine_kernel, which re-evaluates every location whose runner-up lies inside the rounding bound with the
+// reference's own float64 sum: the codes equal the reference's arg-max everywhere.  See prepare_parts_i8_kernel.
 #include "common.cuh"
 
 namespace tsr {
