@@ -230,7 +230,10 @@ def code_parts(bits, parts, threshold, mask_threshold=-1, want_codes=True, want_
     """bits uint8 (B,T,F) -> (codes uint8 (B,To,Fo) | None, scores float32 (B,To,Fo,K) | None,
     counts int16 (B,To,Fo) | None).  edge_spread_radius=1: `bits` is the UNSPREAD edge map and the radius-1 line
     spreading per edge_block_len-frame block (K1a, reference direction table, ragged last block as the tail of the
-    final window) happens inside the kernel's producers -- no separate spread_edges launch."""
+    final window) happens inside the kernel's producers -- no separate spread_edges launch.
+    impl: IMPL_TENSOR (16-bit hi+lo weight planes, kind::f16: codes may differ from the reference at near-ties below 1e-5
+    relative, scores carry 22 bits), IMPL_TENSOR_INT8 (kind::i8 + float64 refinement: codes EQUAL the reference's arg-max
+    at every location, scores carry 16-bit fixed point; the faster form above 126 parts), IMPL_SIMT (fp32 cross-check)."""
     bits = _dev(bits, torch.uint8, "bits")
     B, T, F = bits.shape
     To, Fo = T - parts.ph + 1, F - parts.pw + 1
