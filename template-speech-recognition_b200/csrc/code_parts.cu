@@ -29,6 +29,8 @@
 // kind::i8 MMAs of K = 32 (14 per tile instead of 27), an integer arg-max that also tracks the runner-up, and
 // code_parts_refine_kernel, which re-evaluates every location whose runner-up lies inside the rounding bound with the
 // reference's own float64 sum: the codes equal the reference's arg-max everywhere.  See prepare_parts_i8_kernel.
+#include <atomic>
+
 #include "common.cuh"
 
 namespace tsr {
@@ -1117,14 +1119,14 @@ int tsr_code_parts(const uint8_t* bits, const void* parts_blob, int K, int ph, i
         A.ws_cap = (unsigned int)(nloc / 8 + 1024);
         {   // keep freed blocks in the device's pool across synchronisations: the default threshold (0) hands them back to
             // the driver at every sync and the next call pays a fresh allocation
-            static bool pool_kept[64] = {};
+            static std::atomic<unsigned long long> pool_kept{0ull};     // one bit per device ordinal
             int dev = 0;
             TSR_CUDA(cudaGetDevice(&dev));
-            if (dev >= 0 && dev < 64 && !pool_kept[dev]) {
+            if (dev >= 0 && dev < 64 && !((pool_kept.load(std::memory_order_relaxed) >> dev) & 1ull)) {
                 cudaMemPool_t pool;
                 unsigned long long keep = ~0ull;
                 if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-                pool_kept[dev] = true;
+                pool_kept.fetch_or(1ull << dev, std::memory_order_relaxed);
             }
         }
         TSR_CUDA(cudaMallocAsync((void**)&ws, (2 * (size_t)A.ws_cap + (size_t)nloc + 4) * sizeof(unsigned int), (cudaStream_t)stream));
