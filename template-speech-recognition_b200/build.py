@@ -12,6 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libtsr_b200.so")
 SOURCES = ("util.cu", "spread.cu", "code_parts.cu", "patches.cu", "edges.cu", "detect.cu", "em.cu")
+HOST_SOURCES = ("host_pack.cpp",)      # plain C++ (g++): host-side SIMD with per-function target attributes
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "--use_fast_math=false", "-Xcompiler", "-fPIC", "-Xcompiler", "-O2", "-Xptxas", "-v"]
 
@@ -43,13 +44,18 @@ def build(force=False, verbose=False):
         cmd = [_nvcc()] + [f for f in NVCC_FLAGS if f != "--use_fast_math=false"] + extra + ["-c", os.path.join(CSRC, src), "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(obj)
+    for src in HOST_SOURCES:
+        obj = os.path.join(HERE, "build", src.replace(".cpp", ".o"))
+        cmd = [os.environ.get("CXX", "g++"), "-O3", "-fPIC", "-std=c++17", "-c", os.path.join(CSRC, src), "-o", obj]
+        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        objs.append(obj)
     log = []
     for src, p in procs:
         out, _ = p.communicate()
         log.append("== %s\n%s" % (src, out))
         if p.returncode != 0:
             sys.stderr.write(out)
-            raise RuntimeError("nvcc failed on %s" % src)
+            raise RuntimeError("compiler failed on %s" % src)
     with open(os.path.join(HERE, "build", "ptxas.log"), "w") as f:
         f.write("\n".join(log))
     if verbose:

@@ -123,7 +123,11 @@ __global__ void unpack_features_kernel(const uint32_t* __restrict__ bits, uint8_
 // ----------------------------------------------------------------------------- host-side packer
 // The boundary conversion for callers whose edge tensors live in HOST memory: packing before the copy moves 1 byte
 // per (t,f) over PCIe instead of 8.  16 input bytes (two cells) -> compare with zero -> byte mask -> two packed bytes.
+extern "C" int tsr_hostpack_has_avx512(void);                                                   // host_pack.cpp
+extern "C" void tsr_hostpack_range_avx512(const uint8_t* X, uint8_t* bits, long long c0, long long c1);
 static void host_pack_range(const uint8_t* X, uint8_t* bits, long long c0, long long c1) {
+    static const bool avx512 = tsr_hostpack_has_avx512() != 0;
+    if (avx512) { tsr_hostpack_range_avx512(X, bits, c0, c1); return; }
     long long i = c0;
 #ifdef TSR_HOST_SSE2
     const __m128i zero = _mm_setzero_si128();

@@ -94,3 +94,26 @@ def test_cython_style_argument_errors():
                                       np.zeros((3, 7)), np.zeros((3, 10)), np.zeros((3, 10)), np.zeros((8, 8), np.uint8))
     with pytest.raises(ValueError, match="wrong number of dimensions"):
         code_parts.get_parts_mask(np.zeros((8, 8), np.uint8), np.ones((5, 5), np.uint8), np.zeros((8, 8)), 3)
+
+
+def test_host_pack_edges_matches_packbits():
+    """tsr_host_pack_edges (the host-side boundary conversion of ScoringPipeline.stream: uint8 (..., 8) edge tensors ->
+    one byte per (t, f)) against np.packbits, for every loop of its body (AVX-512 / SSE2 main loops, 8-cell and scalar
+    tails), any non-zero byte counting as an edge, single- and multi-threaded."""
+    import numpy as np
+    from tsr_b200 import _lib
+    lib = _lib.lib()
+    rs = np.random.RandomState(3)
+    X = (rs.rand(70001, 8) < 0.2).astype(np.uint8) * rs.randint(1, 256, size=(70001, 8)).astype(np.uint8)
+    want = np.packbits(X != 0, axis=-1, bitorder="little")[:, 0]
+    for n in (0, 1, 7, 8, 9, 31, 32, 33, 65, 4099, 70001):
+        for off in (0, 3):                      # unaligned starts
+            if off + n > X.shape[0]:
+                continue
+            Xs = np.ascontiguousarray(X[off:off + n])
+            for nt in (1, 4):
+                out = np.full(n + 1, 0xA5, np.uint8)
+                rc = lib.tsr_host_pack_edges(Xs.ctypes.data if n else X.ctypes.data, out.ctypes.data, n, 8, nt)
+                assert rc == 0
+                np.testing.assert_array_equal(out[:n], want[off:off + n])
+                assert out[n] == 0xA5            # nothing written past the end
