@@ -413,7 +413,7 @@ def run_native(args):
     # host packing competes with the launching thread for cores: try a few pool sizes, report the best (all listed)
     cores_here = max(1, (os.cpu_count() or 2) // max(1, min(world, 8)))
     sweep = {}
-    for threads in sorted({max(1, cores_here // 4), max(1, cores_here // 2), max(1, cores_here - 2)}):
+    for threads in sorted({max(1, cores_here // 4), max(1, cores_here // 2), max(1, cores_here - 2), max(1, cores_here - 1)}):
         sweep[threads] = e2e_run(X_pinned, pack="host", pack_threads=threads)
         if threads == min(sweep, key=sweep.get):
             e2e_stats = dict(getattr(pipe, "stream_stats", {}))
