@@ -37,6 +37,35 @@ def test_pipeline_matches_oracle_chain(cuda, oracle):
         np.testing.assert_array_equal(arg[b][clear], v.argmax(-1)[clear])
 
 
+def test_pipeline_with_a_large_dictionary_takes_the_int8_coding_form(cuda, oracle):
+    """More than 126 parts: ScoringPipeline codes with TSR_IMPL_TENSOR_INT8 (its stream-ordered work list is allocated
+    and freed on the pipeline's stream, also inside stream()'s multi-stream schedule); the codes equal the oracle's
+    arg-max at every location and stream() returns what direct calls return."""
+    from tsr_b200 import ops, synth
+    from tsr_b200.pipeline import ScoringPipeline
+    K, M = 140, 3
+    lp, lip = synth.parts(K)
+    T, bgd = synth.templates(M=M, L=10, Fd=36, Kd=K)
+    W, c = synth.linear_filters(T, bgd)
+    pipe = ScoringPipeline(lp, lip, W, c, edge_threshold=12, part_spread=(2, 2), edge_spread_radius=1, edge_block_len=40)
+    assert pipe.impl_code == ops.IMPL_TENSOR_INT8
+    batches = [synth.fast_edge_batch(b, T=100, seed=10 + s) for s, b in enumerate([3, 3, 6, 2])]
+    want = []
+    for X in batches:
+        best, arg, codes = pipe(pipe.from_numpy(X))
+        torch.cuda.synchronize()
+        want.append((best.cpu().numpy().copy(), arg.cpu().numpy().copy()))
+        for b in range(X.shape[0]):
+            ref = oracle.code_parts(oracle.spread_edge_blocks(X[b], 1, 40), lp, lip, 12)
+            np.testing.assert_array_equal(codes[b].cpu().numpy(), np.argmax(ref, -1))
+    n = 0
+    for (best, arg), (wb, wa) in zip(pipe.stream(iter(batches)), want):
+        np.testing.assert_array_equal(best.numpy(), wb)
+        np.testing.assert_array_equal(arg.numpy(), wa)
+        n += 1
+    assert n == len(batches)
+
+
 def test_stream_equals_direct_calls(cuda):
     """ScoringPipeline.stream (double-buffered H2D / D2H on side streams) returns, batch by batch, exactly what a
     direct call on the same batch returns -- pinned tensors and NumPy arrays in, changing batch sizes, ring reuse."""
