@@ -67,12 +67,24 @@ __global__ void __launch_bounds__(256) edge_map_kernel(const double* __restrict_
 // The ragged last block is thresholded on the window of the final `block_len` frames
 // (edge_signal_proc.py:1595-1633) and written both to its own columns of `bits` and, as a whole window, to
 // `tail_bits` (the reference spreads that window before keeping its last columns).
+// x / d for 0 <= x < 2^31 through a multiply-high (magic = floor((2^32 - 1) / d) + 1; 0 stands for d == 1): the per-cell
+// index arithmetic of the kernel below was a fifth of its instructions as runtime integer divisions
+__host__ inline uint32_t div_magic(int d) { return d > 1 ? (uint32_t)(0xFFFFFFFFull / (unsigned)d) + 1u : 0u; }
+__device__ __forceinline__ int div_fast(int x, int d, uint32_t magic, int& rem) {
+    if (magic == 0u) { rem = 0; return x; }
+    int q = (int)__umulhi((uint32_t)x, magic);
+    rem = x - q * d;
+    if (rem < 0) { rem += d; --q; }
+    return q;
+}
+
 struct ThresholdArgs {
     const double* src;    // FUSED: spectrogram [B][F][T]; else magnitudes [B][8][F][T]
     uint8_t* bits;        // [B][T][F]
     uint8_t* tail_bits;   // [B][tail_window][F] or null
     double* taus;         // [B][nblocks][8] quantile values (report_level), or null
     int F, T, block_len, nfull, tail_len, tail_window, cap;
+    uint32_t m_F, m_len[2], m_ld[2];   // division magics: F; window length / tile pitch of a whole block [0] and of the tail window [1]
     double quantile;
     double abst[8];
 };
@@ -113,13 +125,15 @@ __global__ void __launch_bounds__(256) threshold_blocks_kernel(ThresholdArgs A) 
     const int len = tail ? A.tail_window : A.block_len;
     const int nel = A.F * len, F = A.F, T = A.T, cap = A.cap;
     const int ld = len + 3;
+    const uint32_t m_len = A.m_len[tail ? 1 : 0], m_ld = A.m_ld[tail ? 1 : 0];
     unsigned long long* keys = s_dyn;
     double* s_tile = reinterpret_cast<double*>(s_dyn + 8 * (size_t)cap);   // column 0 = frame t0 - 1
     const double* base = A.src + (long long)b * (FUSED ? 1 : 8) * F * T;
     if (threadIdx.x < 8) s_cnt[threadIdx.x] = 0;
     if (FUSED) {
         for (int i = threadIdx.x; i < F * ld; i += blockDim.x) {
-            const int r = i / ld, c = i - r * ld, t = t0 - 1 + c;
+            int c;
+            const int r = div_fast(i, ld, m_ld, c), t = t0 - 1 + c;
             s_tile[i] = (t >= 0 && t < T) ? base[(long long)r * T + t] : 0.0;
         }
     }
@@ -132,12 +146,15 @@ __global__ void __launch_bounds__(256) threshold_blocks_kernel(ThresholdArgs A) 
             pos = m[0]; neg = m[(long long)F * T];
         }
     };
-    // ---- 1. candidate lists
-    for (int pair = 0; pair < 4; ++pair) {
-        for (int i = threadIdx.x; i < nel; i += blockDim.x) {
-            const int r = i / len;
+    // ---- 1. candidate lists (cell outside, the four pairs unrolled inside: one index split per cell, and every copy of the
+    // evaluation specialised to its pair; the order of a list does not matter to the order statistic)
+    for (int i = threadIdx.x; i < nel; i += blockDim.x) {
+        int tl1;
+        const int r = div_fast(i, len, m_len, tl1);
+#pragma unroll
+        for (int pair = 0; pair < 4; ++pair) {
             double pos, neg;
-            mag_pair(pair, r, i - r * len, pos, neg);
+            mag_pair(pair, r, tl1, pos, neg);
             if (pos > 0.0) {
                 const unsigned int slot = atomicAdd(&s_cnt[2 * pair], 1u);
                 if (slot < (unsigned)cap) keys[(size_t)(2 * pair) * cap + slot] = (unsigned long long)__double_as_longlong(pos);
@@ -217,7 +234,8 @@ __global__ void __launch_bounds__(256) threshold_blocks_kernel(ThresholdArgs A) 
     __syncthreads();
     // ---- 3. packed bytes: bit e = magnitude positive and >= threshold (:1286, :1297)
     for (int i = threadIdx.x; i < nel; i += blockDim.x) {
-        const int tl = i / F, r = i - tl * F;           // consecutive threads = consecutive frequency bins of a frame
+        int r;
+        const int tl = div_fast(i, F, A.m_F, r);        // consecutive threads = consecutive frequency bins of a frame
         const int t = t0 + tl;
         uint32_t byte = 0;
 #pragma unroll
@@ -255,6 +273,9 @@ static int launch_threshold(bool fused, const char* what, const double* src, uin
     A.tail_window = T < block_len ? T : block_len;
     A.quantile = quantile;
     for (int e = 0; e < 8; ++e) A.abst[e] = host_abst[e];
+    A.m_F = div_magic(F);
+    A.m_len[0] = div_magic(block_len); A.m_ld[0] = div_magic(block_len + 3);
+    A.m_len[1] = div_magic(A.tail_window); A.m_ld[1] = div_magic(A.tail_window + 3);
     dim3 grid(A.nfull + (A.tail_len ? 1 : 0), B);
     const int nel = F * A.tail_window;
     A.cap = nel < 640 ? nel : 640;                       // candidate list capacity per orientation (overflow re-evaluates)
