@@ -1,7 +1,11 @@
 """Dump the per-tile timeline of CTA 0 of code_parts_tc_kernel (debug hook).
 Needs a library built with the stamps compiled in:
     TSR_NVCC_EXTRA=-DTSR_DEBUG_TRACE python template-speech-recognition_b200/build.py --force
-(the default build leaves them out: even predicated off they slow the issue loops by 2-7 %)."""
+(the default build leaves them out: even predicated off they slow the issue loops by 2-7 %).
+    python tools/trace_code_parts.py [flags] [impl]     impl: 0 = 16-bit hi+lo planes, 2 = int8 form (default)
+flags (tsr_debug_set_code_flags): 1 = the epilogue skips the TMEM reads and the arg-max, 2 = the issuers skip the MMAs,
+4 = epilogue detail stamps, 8 = int8 form without its float64 refinement launch.  Point TSR_B200_LIB at the trace build
+to keep the product library untouched."""
 import ctypes, os, sys
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
