@@ -102,7 +102,9 @@ int tsr_spread_edges(const uint8_t* bits_in, uint8_t* bits_out, int B, int T, in
  * code_parts_mask (:353-404) and the np.argmax the callers apply (get_train_data.py:2621).
  * tsr_prepare_parts turns the reference's float64 log_parts / log_invparts [K][ph][pw][E]
  * (device pointers) into the kernel's weight blob: W = lp - lip split into 16-bit hi + lo
- * planes (TSR_PLANES_*) in UMMA core-matrix order, c[k] = sum(lip) in fp32, edge-count columns. */
+ * planes (TSR_PLANES_*) in UMMA core-matrix order, c[k] = sum(lip) in fp32, edge-count columns -- and, for
+ * TSR_IMPL_TENSOR_INT8, the same model in one fixed-point scale (two base-255 int8 digits per weight, integer constants)
+ * together with the float64 log tables its refinement sums in the reference's order. */
 size_t tsr_parts_blob_bytes(int K, int ph, int pw);
 int    tsr_prepare_parts(const double* log_parts, const double* log_invparts, int K, int ph, int pw, int E,
                          const uint8_t* mask_or_null /* [ph][pw], code_parts_mask's M */, int plane_format,
@@ -115,7 +117,10 @@ int    tsr_prepare_parts(const double* log_parts, const double* log_invparts, in
  * map and every byte is spread on the fly exactly as tsr_spread_edges(radius 1, mode 0, the unit direction table of
  * edge_signal_proc.py:1751-1821, block_len = edge_block_len) would, with the reference's ragged-last-block rule
  * (the frames past the last whole block belong to the window of the final block_len frames, :1595-1633).
- * edge_spread_radius = 0: bits are coded as given. */
+ * edge_spread_radius = 0: bits are coded as given.
+ * impl: TSR_IMPL_TENSOR (hi+lo planes; codes may differ from the reference where two parts score within 1e-5 relative),
+ * TSR_IMPL_TENSOR_INT8 (codes equal the reference's arg-max at every location; takes B*To*Fo*4 + B*To*Fo + 8 KB bytes of
+ * stream-ordered scratch through cudaMallocAsync for the call; needs B*To*Fo < 2^32), TSR_IMPL_SIMT (cross-check). */
 int tsr_code_parts(const uint8_t* bits, const void* parts_blob, int K, int ph, int pw, int threshold,
                    int mask_threshold, uint8_t* codes, float* scores_or_null, uint16_t* counts_or_null, int B, int T,
                    int F, int edge_spread_radius, int edge_block_len, int impl, void* stream);
